@@ -1,0 +1,210 @@
+"""TEST INFRASTRUCTURE: ctypes doors into the CPU restatement (oracle/libmods_oracle.so, prefix
+``orc_``) and, when it has been built, the reference compiled in place
+(oracle/_ref/libmods_ref.so, prefix ``ref_``).  Both export the same call shapes, so tests loop
+over them.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KP = 9  # x y a11 a12 a21 a22 s response sub_type
+
+
+class HessParams(C.Structure):
+    """[HessianAffine] of config_iter_mods_cviu.ini (reference defaults: structures.hpp:146-165, affine.h:52-63)."""
+    _fields_ = [("threshold", C.c_float), ("numberOfScales", C.c_int), ("initialSigma", C.c_float),
+                ("edgeEigenValueRatio", C.c_float), ("border", C.c_int), ("maxIterations", C.c_int),
+                ("convergenceThreshold", C.c_float), ("smmWindowSize", C.c_int), ("doBaumberg", C.c_int),
+                ("mode", C.c_int), ("reg_number", C.c_int), ("rel_threshold", C.c_float),
+                ("rel_reg_number", C.c_float), ("patchSize", C.c_int), ("mrSize", C.c_float)]
+
+    @staticmethod
+    def default():
+        return HessParams(5.3333, 3, 1.6, 10.0, 5, 16, 0.05, 19, 1, 0, 2000, -1.0, -1.0, 41, 3.0 * 3.0 ** 0.5)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Lib:
+    def __init__(self, path, prefix):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+
+    def fn(self, name, restype=C.c_int):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = restype
+        return f
+
+    # ---- image helpers
+    def gaussian_blur(self, img, sigma):
+        img = _f32(img); out = np.empty_like(img)
+        self.fn("gaussian_blur", None)(_p(img), _p(out), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_float(sigma))
+        return out
+
+    def hessian_response(self, img, norm):
+        img = _f32(img); out = np.zeros_like(img)
+        self.fn("hessian_response", None)(_p(img), _p(out), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_float(norm))
+        return out
+
+    def atan2(self, y, x):
+        return self.fn("atan2LUTff", C.c_float)(C.c_float(y), C.c_float(x))
+
+    def interpolate(self, img, ox, oy, a11, a12, a21, a22, ow, oh):
+        img = _f32(img); out = np.zeros((oh, ow), np.float32)
+        r = self.fn("interpolate")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_float(ox), C.c_float(oy),
+                                   C.c_float(a11), C.c_float(a12), C.c_float(a21), C.c_float(a22), _p(out), C.c_int(ow), C.c_int(oh))
+        return out, r
+
+    # ---- detectors
+    def hessaff_detect(self, img, hp=None, raw=False, max_out=400000):
+        img = _f32(img); hp = hp or HessParams.default()
+        out = np.zeros((max_out, KP))
+        n = self.fn("hessaff_detect")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.byref(hp), C.c_int(int(raw)),
+                                      _p(out), C.c_int(max_out))
+        assert n <= max_out
+        return out[:n].copy()
+
+    def mser_detect(self, img, max_area=0.05, min_size=30, min_margin=8.0, mode=0, reg_number=500, raw=False, max_out=200000):
+        img = _f32(img); out = np.zeros((max_out, KP))
+        n = self.fn("mser_detect")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_double(max_area), C.c_int(min_size),
+                                   C.c_double(min_margin), C.c_int(mode), C.c_int(reg_number), C.c_int(int(raw)), _p(out), C.c_int(max_out))
+        return out[:n].copy()
+
+    def detect_orientation(self, img, kps, mrSize=1.0, patchSize=41, maxAngles=1, th=0.8):
+        img = _f32(img); kps = _f64(kps); n = len(kps)
+        out = np.zeros((max(1, n * max(1, maxAngles) * 2), KP))
+        m = self.fn("detect_orientation")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(kps), C.c_int(n), C.c_double(mrSize),
+                                          C.c_int(patchSize), C.c_int(maxAngles), C.c_double(th), _p(out), C.c_int(len(out)))
+        return out[:m].copy()
+
+    def reproject(self, kps, H, w, h, which=0, mrSize=5.1962):
+        kps = _f64(kps); H = _f64(H).ravel(); n = len(kps)
+        od = np.zeros((max(1, n), KP)); orp = np.zeros((max(1, n), KP))
+        m = self.fn("reproject")(_p(kps), C.c_int(n), _p(H), C.c_int(w), C.c_int(h), C.c_int(which), C.c_double(mrSize), _p(od), _p(orp))
+        return od[:m].copy(), orp[:m].copy()
+
+    def describe(self, img, kps, mrSize=5.1962, patchSize=41, fast=False, photoNorm=True, rootsift=True, want_patches=False):
+        img = _f32(img); kps = _f64(kps); n = len(kps)
+        desc = np.zeros((max(1, n), 128), np.float32)
+        args = [_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(kps), C.c_int(n), C.c_double(mrSize), C.c_int(patchSize),
+                C.c_int(int(fast)), C.c_int(int(photoNorm)), C.c_int(int(rootsift)), _p(desc)]
+        patches = None
+        if self.prefix == "orc_":
+            patches = np.zeros((max(1, n), patchSize, patchSize), np.float32) if want_patches else None
+            args.append(_p(patches) if want_patches else C.c_void_p(0))
+        self.fn("describe", None)(*args)
+        return (desc[:n].copy(), patches[:n].copy()) if want_patches else desc[:n].copy()
+
+    def sift_patch(self, patch, rootsift=True):
+        patch = _f32(patch); out = np.zeros(128, np.float32)
+        self.fn("sift_patch", None)(_p(patch), C.c_int(int(rootsift)), _p(out))
+        return out
+
+    def view_pipeline(self, img, detector=0, hp=None, mser=(0.05, 30, 8.0), ori=(1.0, 41, 1, 0.8), desc=(5.1962, 41, True, True),
+                      max_out=400000):
+        img = _f32(img); hp = hp or HessParams.default()
+        det = np.zeros((max_out, KP)); rep = np.zeros((max_out, KP)); d = np.zeros((max_out, 128), np.float32)
+        n = self.fn("view_pipeline")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(detector), C.byref(hp),
+                                     C.c_double(mser[0]), C.c_int(mser[1]), C.c_double(mser[2]),
+                                     C.c_double(ori[0]), C.c_int(ori[1]), C.c_int(ori[2]), C.c_double(ori[3]),
+                                     C.c_double(desc[0]), C.c_int(desc[1]), C.c_int(int(desc[2])), C.c_int(int(desc[3])),
+                                     _p(det), _p(rep), _p(d), C.c_int(max_out))
+        assert 0 <= n <= max_out, n
+        return det[:n].copy(), rep[:n].copy(), d[:n].copy()
+
+    # ---- matching / verification
+    def score(self, which, u, M):
+        u = _f64(u); M = _f64(M).ravel(); n = len(u)
+        d = np.zeros(n)
+        self.fn("score", None)(C.c_int(which), _p(u), _p(M), _p(d), C.c_int(n))
+        return d
+
+
+class Oracle(Lib):
+    def __init__(self):
+        path = os.path.join(HERE, "libmods_oracle.so")
+        if not os.path.exists(path):
+            build()
+        super().__init__(path, "orc_")
+
+    def match_fginn(self, q, t, txy, ratio=0.8, contradDist=30.0, nn=50):
+        q = _f32(q); t = _f32(t); txy = _f64(txy)
+        out = np.zeros((max(1, len(q)), 7))
+        n = self.fn("match_fginn")(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), _p(txy), C.c_double(ratio), C.c_double(contradDist),
+                                   C.c_int(nn), _p(out), C.c_int(len(out)))
+        return out[:n].copy()
+
+    def resize_half(self, img):
+        img = _f32(img)
+        oh, ow = int(np.rint(img.shape[0] * 0.5)), int(np.rint(img.shape[1] * 0.5))
+        out = np.zeros((oh, ow), np.float32)
+        self.fn("resize_half", None)(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(out))
+        return out
+
+    def pyramid(self, img, hp=None):
+        """All (octave, level) blurred images + Hessian responses and the localized points."""
+        img = _f32(img); hp = hp or HessParams.default()
+        f = self.fn("pyramid_build", C.c_void_p)
+        h = C.c_void_p(f(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.byref(hp)))
+        levels = []
+        for i in range(self.fn("pyramid_num_levels")(h)):
+            o, l, r, c, s = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_float()
+            self.fn("pyramid_level_info", None)(h, C.c_int(i), C.byref(o), C.byref(l), C.byref(r), C.byref(c), C.byref(s))
+            blur = np.zeros((r.value, c.value), np.float32); resp = np.zeros_like(blur)
+            self.fn("pyramid_level_data", None)(h, C.c_int(i), _p(blur), _p(resp))
+            levels.append(dict(octave=o.value, level=l.value, sigma=s.value, blur=blur, resp=resp))
+        e, lz = C.c_int(), C.c_int()
+        nkeys = self.fn("pyramid_counts")(h, C.byref(e), C.byref(lz))
+        loc = np.zeros((max(1, lz.value), 8), np.float32)
+        self.fn("pyramid_localized", None)(h, _p(loc))
+        self.fn("pyramid_free", None)(h)
+        return dict(levels=levels, extrema=e.value, localized=loc[:lz.value].copy(), nkeys=nkeys)
+
+
+class Reference(Lib):
+    """The reference's own code (oracle/_ref).  Present in the build container and, as a prebuilt
+    .so, on the GPU box; absent => tests that need it skip."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libmods_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        super().__init__(path, "ref_")
+
+    def exp_ransacH(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1):
+        u = _f64(u); n = len(u)
+        H = np.zeros(9); inl = np.zeros(n, np.uint8); out4 = np.zeros(4, np.int32)
+        f = self.fn("exp_ransacH", C.c_double)
+        J = f(_p(u), C.c_int(n), C.c_double(th), C.c_double(conf), C.c_int(max_sam), C.c_int(errorType), C.c_int(doSymCheck),
+              C.c_long(seed), _p(H), _p(inl), _p(out4))
+        return dict(H=H, inl=inl, I=int(out4[0]), samples=int(out4[1]), lo=int(out4[2]), rejected=int(out4[3]), J=J)
+
+    def u2h(self, u, idx):
+        u = _f64(u); idx = np.ascontiguousarray(idx, np.int32); H = np.zeros(9)
+        self.fn("u2h", None)(_p(u), _p(idx), C.c_int(len(idx)), _p(H))
+        return H
+
+
+def have_reference():
+    return os.path.exists(os.path.join(HERE, "_ref", "libmods_ref.so"))
+
+
+def build(with_ref=True):
+    """Compile the restatement and (when /root/reference is present) the reference."""
+    subprocess.check_call(["make", "-C", HERE, "libmods_oracle.so"], stdout=subprocess.DEVNULL)
+    if with_ref:
+        subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
