@@ -1,0 +1,174 @@
+/* mods_b200 -- C ABI of the B200-native MODS feature pipeline (libmods_b200.so).
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference interface it stands in
+ * for (paths relative to the ducha-aiki/mods tree).  Conventions kept from the reference
+ * (SURVEY.md 8b): integer status/count returns, nothing is thrown across the ABI, an empty
+ * output on failure.  Negative return = error (mb2_last_error() has the text).
+ *
+ * All `const float* / const uint8_t* / double*` data arguments marked [H|D] may be host or
+ * device pointers (decided with cudaPointerGetAttributes); host buffers are staged through
+ * pinned memory on the context's stream.
+ *
+ * Keypoint record: MB2_KP = 9 doubles  { x, y, a11, a12, a21, a22, s, response, sub_type }
+ * (AffineKeypoint, detectors/structures.hpp:187-196; octave_number / pyramid_scale are never
+ * initialised by the reference for these detectors and are not carried).
+ */
+#ifndef MODS_B200_H
+#define MODS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB2_KP 9
+#define MB2_DESC_DIM 128
+
+#define MB2_OK 0
+#define MB2_ERR_CUDA (-1)
+#define MB2_ERR_ARG (-2)
+#define MB2_ERR_UNSUPPORTED (-3)
+#define MB2_ERR_CAPACITY (-4)
+
+typedef struct mb2_ctx mb2_ctx;
+
+/* [HessianAffine] section of config_iter_mods_cviu.ini == PyramidParams + AffineShapeParams
+ * (detectors/structures.hpp:120-165, detectors/affinedetectors/affine.h:28-63). */
+typedef struct {
+  float threshold;            /* 16/3 */
+  int numberOfScales;         /* 3 */
+  float initialSigma;         /* 1.6 */
+  float edgeEigenValueRatio;  /* 10 */
+  int border;                 /* 5 */
+  int maxIterations;          /* 16 */
+  float convergenceThreshold; /* 0.05 */
+  int smmWindowSize;          /* 19 */
+  int doBaumberg;             /* 1 */
+  int mode;                   /* detection_mode_t: 0 FIXED_TH .. 4 NOT_LESS_THAN_REGIONS */
+  int reg_number;
+  float rel_threshold;
+  float rel_reg_number;
+  int patchSize;              /* 41 */
+  float mrSize;               /* 3*sqrt(3) */
+} mb2_hessaff_params;
+
+/* [DominantOrientation] (descriptors_parameters.hpp) as passed to DetectOrientation
+ * (synth-detection.cpp:841-849). */
+typedef struct {
+  double mrSize;   /* 1.0 in config_iter_mods_cviu.ini */
+  int patchSize;   /* 41 */
+  int maxAngles;   /* 1 */
+  double threshold;/* 0.8 */
+} mb2_orientation_params;
+
+/* [SIFTDescriptor] as passed to DescribeRegions<SIFTDescriptor> (synth-detection.hpp:169-172,
+ * matching/siftdesc.h:32-79). */
+typedef struct {
+  double mrSize;   /* 5.1962 */
+  int patchSize;   /* 41 */
+  int photoNorm;   /* 1 */
+  int rootSIFT;    /* 1 = RootSIFT, 0 = SIFT */
+  int fastPatchExtraction; /* 0 */
+} mb2_sift_params;
+
+/* ---- context --------------------------------------------------------------------------- */
+int mb2_ctx_create(int device, mb2_ctx** out);
+void mb2_ctx_destroy(mb2_ctx* ctx);
+const char* mb2_last_error(const mb2_ctx* ctx);
+/* Blocks until everything queued on the context's stream has finished. */
+int mb2_ctx_sync(mb2_ctx* ctx);
+/* cudaStream_t of the context (for CUDA-event timing by the caller). */
+void* mb2_ctx_stream(mb2_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long mb2_ctx_launch_count(const mb2_ctx* ctx);
+
+/* ---- detection ------------------------------------------------------------------------- */
+/* Replaces the detector hook `int DetectAffineKeypoints(cv::Mat&, vector<AffineKeypoint>&,
+ * ScaleSpaceDetectorParams, ScalePyramid&, tilt, zoom)` (scale-space-detector.hpp:231,
+ * scale-space-detector.cpp:43-85) *plus* the post-step of DetectAffineRegions<>
+ * (synth-detection.hpp:93-126) when `as_regions` != 0 (s *= sqrt|det A|, rectifyTransformation).
+ * pixels: w*h f32 gray image [H|D].  out_kp: capacity*MB2_KP doubles [H].
+ * Returns the number of keypoints (detection order of the reference); > capacity => truncated
+ * output and MB2_ERR_CAPACITY. */
+int mb2_hessaff_detect(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_hessaff_params* par,
+                       double tilt, double zoom, int as_regions, double* out_kp, int capacity);
+
+/* Replaces `int DetectOrientation(AffineRegionList&, AffineRegionList&, SynthImage&, mrSize,
+ * patchSize, doHalfSIFT=0, maxAngNum, th, addUpRight=false)` (synth-detection.cpp:841-919). */
+int mb2_detect_orientation(mb2_ctx* ctx, const float* pixels, int w, int h, const double* in_kp, int n,
+                           const mb2_orientation_params* par, double* out_kp, int capacity);
+
+/* Replaces `template<FuncType> void DescribeRegions(AffineRegionList&, SynthImage&, SIFTDescriptor,
+ * mrSize, patchSize, fast_extraction, photoNorm)` (synth-detection.hpp:169-255) with the
+ * SIFTDescriptor functor (matching/siftdesc.cpp:401-442).  desc_u8: n*128 bytes (the reference
+ * stores the same integers 0..255 as float); patches (optional, may be NULL): n*ps*ps f32. */
+int mb2_describe_sift(mb2_ctx* ctx, const float* pixels, int w, int h, const double* kp, int n,
+                      const mb2_sift_params* par, uint8_t* desc_u8, float* patches);
+
+/* One (detector = HessianAffine, view) pass of ImageRepresentation::SynthDetectDescribeKeypoints
+ * (imagerepresentation.cpp:717-720, 1254-1341): detect -> DetectOrientation -> ReprojectRegions
+ * (synth-detection.cpp:541-616) -> DescribeRegions.  `H` is SynthImage::H (original -> view,
+ * affine, row-major 3x3); pixels is the view's image.  Outputs [H]: det_kp / reproj_kp
+ * (capacity*MB2_KP doubles each), desc_u8 (capacity*128).  The described regions also stay
+ * resident on the device as region set `slot` (0..MB2_MAX_SLOTS-1) for mb2_match_slots().
+ * Returns the region count. */
+#define MB2_MAX_SLOTS 8
+int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H,
+                             int orig_w, int orig_h, const mb2_hessaff_params* det,
+                             const mb2_orientation_params* ori, const mb2_sift_params* desc,
+                             int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8,
+                             int capacity);
+
+/* ---- matching -------------------------------------------------------------------------- */
+/* Replaces `int MatchFlannFGINN(const AffineRegionList& q, const AffineRegionList& t,
+ * TentativeCorrespListExt&, const MatchPars&, int nn = 50)` (matching/matching.cpp:357-461) for
+ * vector_matcher = linear (exact kNN): squared-L2 first NN, first-geometrically-inconsistent
+ * ratio test.  q_desc/t_desc: n*128 u8 [H|D]; t_xy: nt*2 doubles = reproj_kp.(x,y) of the trains
+ * [H|D].  out [H]: rows of 7 doubles { query, idx0, idxJ, idx1, d0, dJ, d1 } in query order,
+ * i.e. TentativeCorrespExt{first, second, secondbad, secondbadby2ndcl, d1, d2, d2by2ndcl}.
+ * Ties between equal distances: lower train index first (FLANN's order is unspecified).
+ * matchRatio >= 1 (the "all points" branch, matching.cpp:402-428) is MB2_ERR_UNSUPPORTED.
+ * Returns the number of tentatives. */
+int mb2_match_fginn(mb2_ctx* ctx, const uint8_t* q_desc, int nq, const uint8_t* t_desc, int nt,
+                    const double* t_xy, double matchRatio, double contradDist, int nn, double* out,
+                    int capacity);
+/* Same, on two device-resident region sets left by mb2_detect_describe_view. */
+int mb2_match_slots(mb2_ctx* ctx, int q_slot, int t_slot, double matchRatio, double contradDist, int nn,
+                    double* out, int capacity);
+
+/* ---- verification ---------------------------------------------------------------------- */
+/* Batched form of the DEGENSAC scorer hooks `typedef void (*HDsPtr)(const double* lin, const
+ * double* u, const double* H, double* p, int len)` (degensac/Htools.h:1; HDs Htools.c:158-196,
+ * HDsSym :199-240, HDsSymMax :241-282) and `FDsPtr` (degensac/Fcustomdef.h:3; FDs Ftools.c:82-100,
+ * FDsSym :102-123).  u: len*6 doubles (x1 y1 1 x2 y2 1) [H|D]; models: K*9 doubles (h stored as in
+ * DEGENSAC, column-wise, 2nd image -> 1st) [H|D].  which: 0 HDs, 1 HDsSym, 2 HDsSymMax, 3 FDs,
+ * 4 FDsSym.  Outputs [H], each may be NULL: resid K*len doubles; I[K] = #{d <= th};
+ * J[K] = sum truncQuad(d, th) (rtools.c:228-236). */
+int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const double* models, int K,
+                     double th, double* resid, int* I, double* J);
+
+/* Replaces `Score exp_ransacHcustom(double* u, int len, double th, double conf, int max_sam,
+ * double* H, unsigned char* inl, int iter_type = 4, int* data_out, int oriented_constraint = 1,
+ * unsigned inlLimit = 0, double** resids, HDsPtr, HDsiPtr, HDsidxPtr, int doSymCheck)`
+ * (degensac/exp_ranH.h:32-36, exp_ranH.c:796-1236) as LORANSACFiltering calls it
+ * (matching/matching.cpp:891): LO-RANSAC homography with MSAC scoring.  Hypotheses are generated
+ * on the host exactly as the reference does (same libc rand() stream from `seed`, where the
+ * reference uses time(NULL)), scored in batches on the GPU, and replayed through the reference's
+ * sequential best-so-far / LO / adaptive-stop logic.  errorType: 0 Sampson, 1 SymmMax, 2 SymmSum.
+ * data_out[0..2] = samples, LO count, rejected-by-orientation.  Returns #inliers (Score.I). */
+int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, double conf, int max_sam,
+                 int errorType, int doSymCheck, long seed, double* H, unsigned char* inl, int* data_out,
+                 double* J);
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+/* Copies one plane of the most recent scale-space pyramid (ScalePyramid / Octave::blurs,
+ * detectors/structures.hpp:167-185, which DetectAffineKeypoints exports through its
+ * `ScalePyramid&` argument) to the host: want_resp = 0 the blurred level, 1 its Hessian response.
+ * out may be NULL to query rows/cols.  Returns the number of octaves. */
+int mb2_debug_pyramid_level(mb2_ctx* ctx, int octave, int level, int want_resp, float* out, int* rows, int* cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

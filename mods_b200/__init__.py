@@ -1,0 +1,220 @@
+"""mods_b200: B200-native (sm_100a) implementation of the MODS per-view feature pipeline.
+
+The product is ``libmods_b200.so`` (hand-written CUDA behind the C ABI in ``include/mods_b200.h``).
+This module is only the ctypes door used by the tests, ``bench.py`` and ``__graft_entry__``; it
+never falls back to a CPU path: if the library or a GPU is missing, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmods_b200.so")
+KP = 9
+EXPORTS = [
+    "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
+    "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view",
+    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level",
+]
+
+
+class Mb2Error(RuntimeError):
+    pass
+
+
+class HessaffParams(C.Structure):
+    """mb2_hessaff_params == [HessianAffine] of config_iter_mods_cviu.ini."""
+    _fields_ = [("threshold", C.c_float), ("numberOfScales", C.c_int), ("initialSigma", C.c_float),
+                ("edgeEigenValueRatio", C.c_float), ("border", C.c_int), ("maxIterations", C.c_int),
+                ("convergenceThreshold", C.c_float), ("smmWindowSize", C.c_int), ("doBaumberg", C.c_int),
+                ("mode", C.c_int), ("reg_number", C.c_int), ("rel_threshold", C.c_float),
+                ("rel_reg_number", C.c_float), ("patchSize", C.c_int), ("mrSize", C.c_float)]
+
+    @staticmethod
+    def default():
+        return HessaffParams(5.3333, 3, 1.6, 10.0, 5, 16, 0.05, 19, 1, 0, 2000, -1.0, -1.0, 41, 3.0 * 3.0 ** 0.5)
+
+
+class OrientationParams(C.Structure):
+    _fields_ = [("mrSize", C.c_double), ("patchSize", C.c_int), ("maxAngles", C.c_int), ("threshold", C.c_double)]
+
+    @staticmethod
+    def default():
+        return OrientationParams(1.0, 41, 1, 0.8)
+
+
+class SiftParams(C.Structure):
+    _fields_ = [("mrSize", C.c_double), ("patchSize", C.c_int), ("photoNorm", C.c_int), ("rootSIFT", C.c_int),
+                ("fastPatchExtraction", C.c_int)]
+
+    @staticmethod
+    def default():
+        return SiftParams(5.1962, 41, 1, 1, 0)
+
+
+def build(force=False):
+    """Compile libmods_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.check_call(["make", "-C", HERE, "libmods_b200.so"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Mb2Error("libmods_b200.so is not built (run python -c 'import __graft_entry__ as g; g.build()'); "
+                           "there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.mb2_last_error.restype = C.c_char_p
+        _lib.mb2_ctx_stream.restype = C.c_void_p
+        _lib.mb2_ctx_launch_count.restype = C.c_longlong
+    return _lib
+
+
+def _ptr(a):
+    """numpy array -> host pointer; torch CUDA tensor / int -> device pointer."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+class Context:
+    """One mb2_ctx (one GPU, one stream)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        rc = lib().mb2_ctx_create(C.c_int(device), C.byref(self.h))
+        if rc != 0:
+            raise Mb2Error("mb2_ctx_create(device=%d) failed with %d: no usable CUDA device (no CPU fallback)" % (device, rc))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().mb2_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise Mb2Error("%s failed (%d): %s" % (what, rc, lib().mb2_last_error(self.h).decode()))
+        return rc
+
+    def sync(self):
+        self._check(lib().mb2_ctx_sync(self.h), "sync")
+
+    @property
+    def stream(self):
+        return lib().mb2_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return lib().mb2_ctx_launch_count(self.h)
+
+    def pyramid_level(self, octave, level, want_resp=False):
+        r, c = C.c_int(), C.c_int()
+        n_oct = self._check(lib().mb2_debug_pyramid_level(self.h, C.c_int(octave), C.c_int(level), C.c_int(int(want_resp)),
+                                                          C.c_void_p(0), C.byref(r), C.byref(c)), "pyramid_level")
+        out = np.zeros((r.value, c.value), np.float32)
+        self._check(lib().mb2_debug_pyramid_level(self.h, C.c_int(octave), C.c_int(level), C.c_int(int(want_resp)), _ptr(out),
+                                                  C.byref(r), C.byref(c)), "pyramid_level")
+        return out, n_oct
+
+    # ---- detection
+    def hessaff_detect(self, img, par=None, as_regions=True, capacity=None, shape=None):
+        h, w = shape if shape is not None else img.shape
+        par = par or HessaffParams.default()
+        capacity = capacity or max(4096, (h * w) // 16)
+        out = np.zeros((capacity, KP))
+        n = self._check(lib().mb2_hessaff_detect(self.h, _ptr(img), C.c_int(w), C.c_int(h), C.byref(par), C.c_double(1.0),
+                                                 C.c_double(1.0), C.c_int(int(as_regions)), _ptr(out), C.c_int(capacity)), "hessaff_detect")
+        return out[:n].copy()
+
+    def detect_orientation(self, img, kps, par=None, shape=None):
+        h, w = shape if shape is not None else img.shape
+        par = par or OrientationParams.default()
+        kps = np.ascontiguousarray(kps, np.float64)
+        cap = max(1, len(kps) * max(1, par.maxAngles))
+        out = np.zeros((cap, KP))
+        n = self._check(lib().mb2_detect_orientation(self.h, _ptr(img), C.c_int(w), C.c_int(h), _ptr(kps), C.c_int(len(kps)),
+                                                     C.byref(par), _ptr(out), C.c_int(cap)), "detect_orientation")
+        return out[:n].copy()
+
+    def describe_sift(self, img, kps, par=None, want_patches=False, shape=None):
+        h, w = shape if shape is not None else img.shape
+        par = par or SiftParams.default()
+        kps = np.ascontiguousarray(kps, np.float64)
+        n = len(kps)
+        desc = np.zeros((max(1, n), 128), np.uint8)
+        patches = np.zeros((max(1, n), 41, 41), np.float32) if want_patches else None
+        self._check(lib().mb2_describe_sift(self.h, _ptr(img), C.c_int(w), C.c_int(h), _ptr(kps), C.c_int(n), C.byref(par),
+                                            _ptr(desc), _ptr(patches)), "describe_sift")
+        return (desc[:n].copy(), patches[:n].copy()) if want_patches else desc[:n].copy()
+
+    def detect_describe_view(self, img, H=None, orig_shape=None, det=None, ori=None, desc=None, slot=0, append=False,
+                             capacity=None, want_host=True, shape=None):
+        h, w = shape if shape is not None else img.shape
+        oh, ow = orig_shape or (h, w)
+        H = np.ascontiguousarray(np.eye(3) if H is None else H, np.float64)
+        det = det or HessaffParams.default(); ori = ori or OrientationParams.default(); desc = desc or SiftParams.default()
+        capacity = capacity or max(4096, (h * w) // 16)
+        if want_host:
+            dk = np.zeros((capacity, KP)); rk = np.zeros((capacity, KP)); du = np.zeros((capacity, 128), np.uint8)
+        else:
+            dk = rk = du = None
+        n = self._check(lib().mb2_detect_describe_view(self.h, _ptr(img), C.c_int(w), C.c_int(h), _ptr(H), C.c_int(ow), C.c_int(oh),
+                                                       C.byref(det), C.byref(ori), C.byref(desc), C.c_int(slot), C.c_int(int(append)),
+                                                       _ptr(dk), _ptr(rk), _ptr(du), C.c_int(capacity)), "detect_describe_view")
+        if want_host:
+            return dk[:n].copy(), rk[:n].copy(), du[:n].copy()
+        return n
+
+    # ---- matching
+    def match_fginn(self, q_desc, t_desc, t_xy, ratio=0.8, contradDist=30.0, nn=50, nq=None, nt=None):
+        nq = len(q_desc) if nq is None else nq
+        nt = len(t_desc) if nt is None else nt
+        out = np.zeros((max(1, nq), 7))
+        n = self._check(lib().mb2_match_fginn(self.h, _ptr(q_desc), C.c_int(nq), _ptr(t_desc), C.c_int(nt), _ptr(t_xy),
+                                              C.c_double(ratio), C.c_double(contradDist), C.c_int(nn), _ptr(out), C.c_int(len(out))),
+                        "match_fginn")
+        return out[:n].copy()
+
+    def match_slots(self, q_slot, t_slot, ratio=0.8, contradDist=30.0, nn=50, capacity=1 << 20):
+        out = np.zeros((capacity, 7))
+        n = self._check(lib().mb2_match_slots(self.h, C.c_int(q_slot), C.c_int(t_slot), C.c_double(ratio), C.c_double(contradDist),
+                                              C.c_int(nn), _ptr(out), C.c_int(capacity)), "match_slots")
+        return out[:n].copy()
+
+    # ---- verification
+    def score_models(self, which, u, models, th, want_resid=False, len_=None, K=None):
+        n = len(u) if len_ is None else len_
+        K = (np.asarray(models).size // 9) if K is None else K
+        I = np.zeros(max(1, K), np.int32); J = np.zeros(max(1, K))
+        resid = np.zeros((max(1, K), max(1, n))) if want_resid else None
+        self._check(lib().mb2_score_models(self.h, C.c_int(which), _ptr(u), C.c_int(n), _ptr(models), C.c_int(K), C.c_double(th),
+                                           _ptr(resid), _ptr(I), _ptr(J)), "score_models")
+        return (I[:K], J[:K], resid) if want_resid else (I[:K], J[:K])
+
+    def ransac_h(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1):
+        u = np.ascontiguousarray(u, np.float64)
+        n = len(u)
+        H = np.zeros(9); inl = np.zeros(max(1, n), np.uint8); data = np.zeros(3, np.int32); J = C.c_double()
+        I = self._check(lib().mb2_ransac_h(self.h, _ptr(u), C.c_int(n), C.c_double(th), C.c_double(conf), C.c_int(max_sam),
+                                           C.c_int(errorType), C.c_int(doSymCheck), C.c_long(seed), _ptr(H), _ptr(inl), _ptr(data),
+                                           C.byref(J)), "ransac_h")
+        return dict(H=H, inl=inl[:n], I=I, samples=int(data[0]), lo=int(data[1]), rejected=int(data[2]), J=J.value)

@@ -1,0 +1,785 @@
+// C ABI of libmods_b200.so (include/mods_b200.h): host orchestration of the kernels.
+// No oracle / CPU fallback anywhere on this path: every entry point either runs the CUDA kernels
+// or fails with an error code.
+#include "common.cuh"
+#undef MB2_NS
+#define MB2_NS mb2_capi_detail
+#include "pyramid.cuh"
+#include "describe.cuh"
+#include "nn.cuh"
+#include "ransac.cuh"
+#include "host_tables.hpp"
+
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace MB2_NS {
+
+struct CtxTables {
+  DevBuf smm_mask, orimask, desc_tables, tap_n, tap_off, tap_w, octaves;
+  int smm_size = 0, tap_max_m = -1;
+  double tap_mrsize_key = -1;
+  int tap_patch = 0;
+};
+struct CtxPriv {
+  CtxTables t;
+  std::vector<OctaveLevels> last_octaves;  // geometry of the most recent pyramid (diagnostics)
+};
+std::mutex g_lut_mutex;
+bool g_lut_uploaded[64] = {false};
+
+CtxPriv* priv(mb2_ctx* ctx);
+
+int upload_lut(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_lut_mutex);
+  if (ctx->device < 64 && g_lut_uploaded[ctx->device]) return MB2_OK;
+  double lut[256];
+  mb2host::build_atan_lut(lut);
+  MB2_CUDA_CHECK(ctx, cudaMemcpyToSymbol(c_atan_lut, lut, sizeof lut));
+  if (ctx->device < 64) g_lut_uploaded[ctx->device] = true;
+  return MB2_OK;
+}
+
+inline int pitch_of(int cols) { return (cols + 31) & ~31; }
+
+// ---- cub helpers (bookkeeping only: ordering + stable compaction of short lists) ------------------
+__global__ void k_iota_keys(const KeyOut* __restrict__ in, int n, unsigned long long* keys, int* idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = in[i].order; idx[i] = i; }
+}
+__global__ void k_gather(const KeyOut* __restrict__ in, const int* __restrict__ idx, int n, KeyOut* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+__global__ void k_flags(const KeyOut* __restrict__ in, int n, int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = in[i].keep ? 1 : 0;
+}
+__global__ void k_scatter(const KeyOut* __restrict__ in, const KeyOut* __restrict__ in2, const int* __restrict__ flags,
+                          const int* __restrict__ pos, int n, KeyOut* __restrict__ out, KeyOut* __restrict__ out2, int* __restrict__ total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flags[i]) { out[pos[i]] = in[i]; if (in2) out2[pos[i]] = in2[i]; }
+  if (i == n - 1) *total = pos[i] + flags[i];
+}
+__global__ void k_scan_offsets_total(const unsigned long long* need, const unsigned long long* off, int n, unsigned long long* total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *total = n ? off[n - 1] + need[n - 1] : 0ull;
+}
+__global__ void k_kp_from_doubles(const double* __restrict__ kp, int n, KeyOut* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  KeyOut o;
+  for (int j = 0; j < MB2_KP; j++) o.v[j] = kp[(size_t)i * MB2_KP + j];
+  o.order = (unsigned long long)i; o.keep = 1; o.pad = 0;
+  out[i] = o;
+}
+__global__ void k_kp_to_doubles(const KeyOut* __restrict__ in, int n, double* __restrict__ kp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int j = 0; j < MB2_KP; j++) kp[(size_t)i * MB2_KP + j] = in[i].v[j];
+}
+__global__ void k_xy_from_keys(const KeyOut* __restrict__ in, int n, double* __restrict__ xy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { xy[2 * i] = in[i].v[0]; xy[2 * i + 1] = in[i].v[1]; }
+}
+__global__ void k_match_flags(const int* __restrict__ accept, int n, int* flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = accept[i];
+}
+__global__ void k_match_scatter(const MatchRow* __restrict__ rows, const int* __restrict__ flags, const int* __restrict__ pos, int n,
+                                double* __restrict__ out, int capacity, int* __restrict__ total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flags[i] && pos[i] < capacity) {
+    const MatchRow r = rows[i];
+    double* o = out + (size_t)pos[i] * 7;
+    o[0] = r.q; o[1] = r.idx0; o[2] = r.idxJ; o[3] = r.idx1; o[4] = r.d0; o[5] = r.dJ; o[6] = r.d1;
+  }
+  if (i == n - 1) *total = pos[i] + flags[i];
+}
+
+#define LAUNCH1D(ctx, kernel, n, ...) \
+  do { if ((n) > 0) MB2_LAUNCH(ctx, kernel, ((n) + 255) / 256, 256, 0, __VA_ARGS__); } while (0)
+
+// sort `n` records by KeyOut::order (ascending) into out
+int sort_by_order(mb2_ctx* ctx, const KeyOut* in, int n, KeyOut* out, DevBuf& tmp) {
+  if (n <= 0) return MB2_OK;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
+                                  (int*)nullptr, n, 0, 64, ctx->stream);
+  size_t need = (size_t)n * (8 + 8 + 4 + 4) + cub_bytes + 64;
+  MB2_CUDA_CHECK(ctx, tmp.reserve(need));
+  unsigned long long* k0 = tmp.as<unsigned long long>();
+  unsigned long long* k1 = k0 + n;
+  int* i0 = (int*)(k1 + n);
+  int* i1 = i0 + n;
+  void* cub_tmp = (void*)(((uintptr_t)(i1 + n) + 15) & ~(uintptr_t)15);
+  LAUNCH1D(ctx, k_iota_keys, n, in, n, k0, i0);
+  MB2_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k0, k1, i0, i1, n, 0, 64, ctx->stream));
+  ctx->launches += 3;
+  LAUNCH1D(ctx, k_gather, n, in, i1, n, out);
+  return MB2_OK;
+}
+
+// stable compaction of records with keep != 0 (optionally a second array in lockstep).  *n_out on host.
+int compact(mb2_ctx* ctx, const KeyOut* in, const KeyOut* in2, int n, KeyOut* out, KeyOut* out2, DevBuf& tmp, int* n_out) {
+  *n_out = 0;
+  if (n <= 0) return MB2_OK;
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr, n, ctx->stream);
+  size_t need = (size_t)n * 8 + 16 + cub_bytes + 64;
+  MB2_CUDA_CHECK(ctx, tmp.reserve(need));
+  int* flags = tmp.as<int>();
+  int* pos = flags + n;
+  int* total = pos + n;
+  void* cub_tmp = (void*)(((uintptr_t)(total + 1) + 15) & ~(uintptr_t)15);
+  LAUNCH1D(ctx, k_flags, n, in, n, flags);
+  MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, flags, pos, n, ctx->stream));
+  ctx->launches += 1;
+  LAUNCH1D(ctx, k_scatter, n, in, in2, flags, pos, n, out, out2, total);
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(n_out, total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MB2_OK;
+}
+
+// ---- per-context tables -----------------------------------------------------------------------
+std::vector<std::pair<mb2_ctx*, CtxPriv*>> g_privs;
+std::mutex g_priv_mutex;
+CtxPriv* priv(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_priv_mutex);
+  for (auto& p : g_privs) if (p.first == ctx) return p.second;
+  g_privs.emplace_back(ctx, new CtxPriv());
+  return g_privs.back().second;
+}
+void drop_priv(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_priv_mutex);
+  for (size_t i = 0; i < g_privs.size(); i++)
+    if (g_privs[i].first == ctx) {
+      CtxTables& t = g_privs[i].second->t;
+      t.smm_mask.release(); t.orimask.release(); t.desc_tables.release(); t.tap_n.release(); t.tap_off.release(); t.tap_w.release();
+      t.octaves.release();
+      delete g_privs[i].second;
+      g_privs.erase(g_privs.begin() + i);
+      return;
+    }
+}
+
+int ensure_smm_mask(mb2_ctx* ctx, int size) {
+  CtxTables& t = priv(ctx)->t;
+  if (t.smm_size == size) return MB2_OK;
+  std::vector<float> m((size_t)size * size);
+  mb2host::gauss_mask(m.data(), size);
+  MB2_CUDA_CHECK(ctx, t.smm_mask.reserve(m.size() * 4));
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(t.smm_mask.p, m.data(), m.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  t.smm_size = size;
+  return MB2_OK;
+}
+int ensure_orimask(mb2_ctx* ctx) {
+  CtxTables& t = priv(ctx)->t;
+  if (t.orimask.p) return MB2_OK;
+  std::vector<float> m(41 * 41);
+  mb2host::circular_gauss_mask(m.data(), 41, 41 / 3.0f);  // synth-detection.cpp:762
+  MB2_CUDA_CHECK(ctx, t.orimask.reserve(m.size() * 4));
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(t.orimask.p, m.data(), m.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MB2_OK;
+}
+int ensure_desc_tables(mb2_ctx* ctx) {
+  CtxTables& t = priv(ctx)->t;
+  if (t.desc_tables.p) return MB2_OK;
+  DescTables* h = new DescTables();
+  mb2host::circular_gauss_mask(h->mask, 41);
+  mb2host::sift_bins(41, 4, 8, h->bin0, h->bin1, h->w0, h->w1);
+  MB2_CUDA_CHECK(ctx, t.desc_tables.reserve(sizeof(DescTables)));
+  cudaError_t e = cudaMemcpyAsync(t.desc_tables.p, h, sizeof(DescTables), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  delete h;
+  MB2_CUDA_CHECK(ctx, e);
+  return MB2_OK;
+}
+// taps for every m in [0, max_m]
+int ensure_taps(mb2_ctx* ctx, int max_m, int patchSize, TapTable* out) {
+  CtxTables& t = priv(ctx)->t;
+  if (t.tap_max_m < max_m || t.tap_patch != patchSize) {
+    int want = std::max(max_m, 256);
+    std::vector<int> n(want + 1, 0), off(want + 1, 0);
+    std::vector<float> w;
+    for (int m = 0; m <= want; m++) {
+      const int patchImageSize = 2 * m + 1;
+      const float scale = float(patchImageSize) / float(patchSize);
+      off[m] = (int)w.size();
+      if (scale > 0.4) {
+        const float sigma = 1.5f * scale;  // synth-detection.hpp:208
+        const int ks = mb2host::gauss_ksize(sigma);
+        std::vector<float> k = mb2host::gauss_kernel(ks, sigma);
+        n[m] = ks;
+        w.insert(w.end(), k.begin(), k.end());
+      }
+    }
+    MB2_CUDA_CHECK(ctx, t.tap_n.reserve(n.size() * 4));
+    MB2_CUDA_CHECK(ctx, t.tap_off.reserve(off.size() * 4));
+    MB2_CUDA_CHECK(ctx, t.tap_w.reserve(w.size() * 4 + 4));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(t.tap_n.p, n.data(), n.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(t.tap_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(t.tap_w.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    t.tap_max_m = want; t.tap_patch = patchSize;
+  }
+  out->n = t.tap_n.as<int>(); out->off = t.tap_off.as<int>(); out->w = t.tap_w.as<float>(); out->max_m = t.tap_max_m;
+  return MB2_OK;
+}
+
+// ---- staging -------------------------------------------------------------------------------
+int stage_image(mb2_ctx* ctx, const float* pixels, int w, int h, ImgView* view) {
+  const int pitch = pitch_of(w);
+  MB2_CUDA_CHECK(ctx, ctx->img.reserve((size_t)pitch * h * 4));
+  cudaMemcpyKind kind = mb2_is_device_ptr(pixels) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  MB2_CUDA_CHECK(ctx, cudaMemcpy2DAsync(ctx->img.p, (size_t)pitch * 4, pixels, (size_t)w * 4, (size_t)w * 4, h, kind, ctx->stream));
+  view->p = ctx->img.as<float>(); view->rows = h; view->cols = w; view->pitch = pitch;
+  return MB2_OK;
+}
+
+struct PyramidLayout {
+  int n_octaves = 0;
+  std::vector<int> rows, cols, pitch;
+  std::vector<size_t> off;  // float offset of level 0 of each octave; levels are consecutive planes
+  size_t total = 0;
+};
+
+// ---- detection core: pixels on device -> ordered KeyOut list on device --------------------------
+// Result: ctx->kp_b holds n KeyOut (ordered like the reference's key vector, keep == 1 for all).
+int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par, double tilt, double zoom, int as_regions, int* n_out) {
+  (void)tilt; (void)zoom;  // reg_number rescale only matters for the non-FIXED_TH modes
+  *n_out = 0;
+  if (par.mode != 0) { ctx->set_error("hessaff: only DetectorMode FIXED_TH is built so far"); return MB2_ERR_UNSUPPORTED; }
+  if (par.numberOfScales + 2 > MB2_MAX_LEVELS || par.smmWindowSize != 19 || par.border < 2) {
+    ctx->set_error("hessaff: unsupported numberOfScales / smmWindowSize / border"); return MB2_ERR_ARG;
+  }
+  int rc;
+  if ((rc = upload_lut(ctx))) return rc;
+  if ((rc = ensure_smm_mask(ctx, par.smmWindowSize))) return rc;
+  const int S = par.numberOfScales, NL = S + 2;
+  // octave geometry (pyramid.cpp:564-572, cv::resize output size = cvRound(dim * 0.5))
+  PyramidLayout L;
+  {
+    int r = img.rows, c = img.cols;
+    const int minSize = 2 * par.border + 2;
+    while (r > minSize && c > minSize) {
+      L.rows.push_back(r); L.cols.push_back(c); L.pitch.push_back(pitch_of(c));
+      L.off.push_back(L.total);
+      L.total += (size_t)L.pitch.back() * r * NL;
+      r = mb2host::cv_round(r * 0.5); c = mb2host::cv_round(c * 0.5);
+    }
+    L.n_octaves = (int)L.rows.size();
+  }
+  if (L.n_octaves == 0) return MB2_OK;
+  MB2_CUDA_CHECK(ctx, ctx->pyr.reserve(L.total * 4));
+  MB2_CUDA_CHECK(ctx, ctx->resp.reserve(L.total * 4));
+  float* pyr = ctx->pyr.as<float>(); float* resp = ctx->resp.as<float>();
+
+  // sigmas exactly as pyramid.cpp:459-487 computes them in float
+  const float sigmaStep = std::pow(2.0f, 1.0f / (float)S);
+  std::vector<float> levelSigma(NL), incSigma(NL);
+  {
+    float curSigma = par.initialSigma;
+    levelSigma[0] = curSigma;
+    for (int i = 1; i < NL; i++) {
+      incSigma[i] = curSigma * std::sqrt(sigmaStep * sigmaStep - 1.0f);
+      levelSigma[i] = curSigma * sigmaStep;  // "sigma = curSigma*sigmaStep" used for the response norm
+      curSigma *= sigmaStep;
+    }
+  }
+  auto make_taps = [](float sigma) {
+    BlurTaps t; t.n = mb2host::gauss_ksize(sigma);
+    std::vector<float> k = mb2host::gauss_kernel(t.n, sigma);
+    for (int i = 0; i < t.n && i < 33; i++) t.k[i] = k[i];
+    return t;
+  };
+  std::vector<OctaveLevels> octs(L.n_octaves);
+  for (int o = 0; o < L.n_octaves; o++) {
+    octs[o].nlevels = NL;
+    for (int l = 0; l < NL; l++) {
+      size_t off = L.off[o] + (size_t)l * L.pitch[o] * L.rows[o];
+      octs[o].blur[l] = ImgView{pyr + off, L.rows[o], L.cols[o], L.pitch[o]};
+      octs[o].resp[l] = ImgView{resp + off, L.rows[o], L.cols[o], L.pitch[o]};
+    }
+  }
+  CtxTables& T = priv(ctx)->t;
+  priv(ctx)->last_octaves = octs;
+  MB2_CUDA_CHECK(ctx, T.octaves.reserve(sizeof(OctaveLevels) * L.n_octaves));
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(T.octaves.p, octs.data(), sizeof(OctaveLevels) * L.n_octaves, cudaMemcpyHostToDevice, ctx->stream));
+
+  // thresholds (pyramid.h:46-69)
+  const float finalThreshold = par.threshold * par.threshold;
+  const float positiveThreshold = (float)(0.8 * par.threshold), negativeThreshold = -positiveThreshold;
+  const double er = par.edgeEigenValueRatio;
+  const double edgeScoreThreshold = (er + 1.0f) * (er + 1.0f) / er;
+
+  // capacity of the per-octave candidate list and the global keypoint list
+  const size_t px0 = (size_t)L.rows[0] * L.cols[0];
+  const int cand_cap = (int)std::min<size_t>(px0 / 8 + 4096, (size_t)1 << 26);
+  const int kp_cap = (int)std::min<size_t>(px0 / 16 + 4096, (size_t)1 << 25);
+  MB2_CUDA_CHECK(ctx, ctx->cand.reserve((size_t)cand_cap * (sizeof(Candidate) + sizeof(Localized)) + 64));
+  Candidate* d_cand = ctx->cand.as<Candidate>();
+  Localized* d_loc = (Localized*)(d_cand + cand_cap);
+  MB2_CUDA_CHECK(ctx, ctx->kp_a.reserve((size_t)kp_cap * sizeof(KeypointRec) + 64));
+  KeypointRec* d_kp = ctx->kp_a.as<KeypointRec>();
+  MB2_CUDA_CHECK(ctx, ctx->octmap.reserve(px0 * 8 + 64));
+  unsigned long long* d_octmap = ctx->octmap.as<unsigned long long>();
+  MB2_CUDA_CHECK(ctx, ctx->misc.reserve(4096));
+  int* d_counts = ctx->misc.as<int>();  // [0] = candidates (per octave), [1] = keypoints (global)
+  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, 64, ctx->stream));
+
+  // ---- scale space -----------------------------------------------------------------------------
+  float pixelDistance = 1.0f;
+  for (int o = 0; o < L.n_octaves; o++) {
+    const OctaveLevels& oc = octs[o];
+    if (o == 0) {
+      // first level: initial blur sqrt(initialSigma^2 - 0.5^2) (pyramid.cpp:555-562) fused with its response
+      const float curSigma0 = 0.5f;
+      float n0 = levelSigma[0] * levelSigma[0];
+      if (par.initialSigma > curSigma0) {
+        const float sigma = std::sqrt(par.initialSigma * par.initialSigma - curSigma0 * curSigma0);
+        rc = mb2_launch_blur(ctx, img, (float*)oc.blur[0].p, (float*)oc.resp[0].p, oc.blur[0].pitch, make_taps(sigma), n0 * n0, 1);
+        if (rc) return rc;
+      } else {
+        MB2_CUDA_CHECK(ctx, cudaMemcpy2DAsync((void*)oc.blur[0].p, (size_t)oc.blur[0].pitch * 4, img.p, (size_t)img.pitch * 4,
+                                              (size_t)img.cols * 4, img.rows, cudaMemcpyDeviceToDevice, ctx->stream));
+        mb2_launch_hessian(ctx, oc.blur[0], (float*)oc.resp[0].p, oc.resp[0].pitch, n0 * n0);
+      }
+    } else {
+      // next octave = cv::resize(level S, 0.5) of the previous one (pyramid.cpp:517-520)
+      mb2_launch_resize_half(ctx, octs[o - 1].blur[S], (float*)oc.blur[0].p, oc.blur[0].rows, oc.blur[0].cols, oc.blur[0].pitch);
+      float n0 = levelSigma[0] * levelSigma[0];
+      mb2_launch_hessian(ctx, oc.blur[0], (float*)oc.resp[0].p, oc.resp[0].pitch, n0 * n0);
+    }
+    for (int i = 1; i < NL; i++) {
+      float nrm = levelSigma[i] * levelSigma[i];  // Response(nextBlur, sigma*sigma); HessianResponse squares it again
+      rc = mb2_launch_blur(ctx, oc.blur[i - 1], (float*)oc.blur[i].p, (float*)oc.resp[i].p, oc.blur[i].pitch, make_taps(incSigma[i]),
+                           nrm * nrm, 1);
+      if (rc) return rc;
+    }
+    // ---- extrema -> localisation -> de-duplication, levels 1..S in the reference's order --------
+    MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int), ctx->stream));
+    for (int lv = 1; lv <= S; lv++)
+      mb2_launch_nms(ctx, oc.resp[lv - 1], oc.resp[lv], oc.resp[lv + 1], par.border, positiveThreshold, negativeThreshold, lv, d_cand,
+                     d_counts, cand_cap);
+    int n_cand = 0;
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_cand, d_counts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_cand > cand_cap) { ctx->set_error("hessaff: candidate list overflow"); return MB2_ERR_CAPACITY; }
+    if (n_cand > 0) {
+      LocalizeParams lp;
+      lp.edgeScoreThreshold = edgeScoreThreshold; lp.finalThreshold = finalThreshold; lp.pixelDistance = pixelDistance;
+      lp.numberOfScales = S;
+      // findLevelKeypoints(curSigma): curSigma at level lv is initialSigma * sigmaStep^lv accumulated in float
+      {
+        float cs = par.initialSigma;
+        for (int l = 0; l < NL; l++) { lp.levelSigma[l] = cs; cs *= sigmaStep; }
+      }
+      mb2_launch_fill_u64(ctx, d_octmap, (size_t)L.rows[o] * L.cols[o], ~0ull);
+      mb2_launch_localize(ctx, oc, d_cand, n_cand, lp, d_octmap, d_loc);
+      mb2_launch_emit(ctx, oc, d_loc, n_cand, d_octmap, lp, o, d_kp, d_counts + 1, kp_cap);
+    }
+    pixelDistance *= 2.0;
+  }
+  int n_kp = 0;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_kp, d_counts + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_kp > kp_cap) { ctx->set_error("hessaff: keypoint list overflow"); return MB2_ERR_CAPACITY; }
+  if (n_kp == 0) return MB2_OK;
+
+  // ---- Baumberg, export, ordering ---------------------------------------------------------------
+  AffineParams ap;
+  ap.maxIterations = par.maxIterations; ap.smmWindowSize = par.smmWindowSize; ap.doBaumberg = par.doBaumberg;
+  ap.convergenceThreshold = par.convergenceThreshold; ap.initialSigma = par.initialSigma;
+  mb2_launch_affine_shape(ctx, T.octaves.as<OctaveLevels>(), L.n_octaves, d_kp, n_kp, ap, T.smm_mask.as<float>());
+  MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)n_kp * sizeof(KeyOut)));
+  MB2_CUDA_CHECK(ctx, ctx->kp_c.reserve((size_t)n_kp * sizeof(KeyOut)));
+  mb2_launch_export(ctx, d_kp, n_kp, ctx->kp_c.as<KeyOut>(), as_regions);
+  if ((rc = sort_by_order(ctx, ctx->kp_c.as<KeyOut>(), n_kp, ctx->kp_b.as<KeyOut>(), ctx->misc))) return rc;
+  int n_keep = 0;
+  if ((rc = compact(ctx, ctx->kp_b.as<KeyOut>(), nullptr, n_kp, ctx->kp_c.as<KeyOut>(), nullptr, ctx->misc, &n_keep))) return rc;
+  std::swap(ctx->kp_b, ctx->kp_c);
+  *n_out = n_keep;
+  return MB2_OK;
+}
+
+int download_keys(mb2_ctx* ctx, const KeyOut* d_keys, int n, double* out, int capacity, DevBuf& tmp) {
+  const int m = std::min(n, capacity);
+  if (m <= 0) return MB2_OK;
+  MB2_CUDA_CHECK(ctx, tmp.reserve((size_t)m * MB2_KP * 8));
+  LAUNCH1D(ctx, k_kp_to_doubles, m, d_keys, m, tmp.as<double>());
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(out, tmp.p, (size_t)m * MB2_KP * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return MB2_OK;
+}
+
+// orientation on ctx->kp_b (n records) -> ctx->kp_c (n_out records), ordered
+int orient_core(mb2_ctx* ctx, const ImgView& img, int n, const mb2_orientation_params& op, int* n_out) {
+  *n_out = 0;
+  if (n <= 0) return MB2_OK;
+  if (op.patchSize != 41) { ctx->set_error("orientation: patchSize must be 41"); return MB2_ERR_ARG; }
+  int rc;
+  if ((rc = upload_lut(ctx))) return rc;
+  if ((rc = ensure_orimask(ctx))) return rc;
+  const int maxA = std::max(op.maxAngles, 0);
+  if (maxA == 0) return MB2_OK;
+  if (maxA > 36) { ctx->set_error("orientation: maxAngles > 36"); return MB2_ERR_ARG; }
+  const size_t slots = (size_t)n * maxA;
+  MB2_CUDA_CHECK(ctx, ctx->kp_a.reserve(slots * sizeof(KeyOut) + (size_t)n * 4 + 64));
+  KeyOut* d_slots = ctx->kp_a.as<KeyOut>();
+  int* d_cnt = (int*)(d_slots + slots);
+  OrientParams p{op.mrSize, op.patchSize, maxA, op.threshold};
+  mb2_launch_orientation(ctx, img, ctx->kp_b.as<KeyOut>(), n, p, priv(ctx)->t.orimask.as<float>(), d_slots, d_cnt);
+  MB2_CUDA_CHECK(ctx, ctx->kp_c.reserve(slots * sizeof(KeyOut)));
+  return compact(ctx, d_slots, nullptr, (int)slots, ctx->kp_c.as<KeyOut>(), nullptr, ctx->misc, n_out);
+}
+
+// describe the n records at d_keys; descriptors -> ctx->desc_u8 (device)
+int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n, const mb2_sift_params& sp, float* d_patches) {
+  if (n <= 0) return MB2_OK;
+  if (sp.patchSize != 41) { ctx->set_error("describe: patchSize must be 41"); return MB2_ERR_ARG; }
+  int rc;
+  if ((rc = upload_lut(ctx))) return rc;
+  if ((rc = ensure_desc_tables(ctx))) return rc;
+  DescribeParams dp{sp.mrSize, sp.patchSize, sp.photoNorm, sp.rootSIFT, sp.fastPatchExtraction};
+  // largest possible m: the region must fit in the image for the earlier boundary tests, bound by the image diagonal
+  const int max_m = (int)std::ceil(std::sqrt((double)img.rows * img.rows + (double)img.cols * img.cols)) + 8;
+  TapTable taps;
+  if ((rc = ensure_taps(ctx, max_m, sp.patchSize, &taps))) return rc;
+  // scratch plan: need[i] floats per region, exclusive scan -> offsets
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, ctx->stream);
+  MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)n * 16 + 64 + cub_bytes + 64));
+  unsigned long long* d_need = ctx->rs_a.as<unsigned long long>();
+  unsigned long long* d_off = d_need + n;
+  unsigned long long* d_total = d_off + n;
+  int* d_toobig = (int*)(d_total + 1);
+  void* cub_tmp = (void*)(((uintptr_t)(d_toobig + 2) + 15) & ~(uintptr_t)15);
+  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_toobig, 0, 8, ctx->stream));
+  mb2_describe_plan(ctx, d_keys, n, dp, taps.max_m, d_need, d_toobig);
+  MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, d_need, d_off, n, ctx->stream));
+  ctx->launches += 1;
+  MB2_LAUNCH(ctx, k_scan_offsets_total, 1, 32, 0, d_need, d_off, n, d_total);
+  unsigned long long total = 0; int toobig = 0;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&toobig, d_toobig, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (toobig) { ctx->set_error("describe: region larger than the tap table (m=" + std::to_string(toobig) + ")"); return MB2_ERR_CAPACITY; }
+  if (total > ((size_t)24 << 30) / 4) { ctx->set_error("describe: patch scratch would exceed 24 GiB"); return MB2_ERR_CAPACITY; }
+  MB2_CUDA_CHECK(ctx, ctx->patch_scratch.reserve((size_t)total * 4 + 64));
+  MB2_CUDA_CHECK(ctx, ctx->desc_u8.reserve((size_t)n * 128));
+  return mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, d_off,
+                                    ctx->patch_scratch.as<float>(), ctx->desc_u8.as<uint8_t>(), d_patches);
+}
+
+// FGINN on device-resident data.  out rows on host.
+int match_core(mb2_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, const double* d_txy, double matchRatio,
+               double contradDist, int nn, double* out, int capacity) {
+  if (nq <= 0 || nt <= 0) return 0;
+  if (!(matchRatio > 0)) { ctx->set_error("match: matchRatio must be > 0"); return MB2_ERR_ARG; }
+  const double sqminratio = matchRatio * matchRatio, contr2 = contradDist * contradDist;
+  if (sqminratio >= 1.0) { ctx->set_error("match: the matchRatio >= 1 branch (matching.cpp:402-428) is not built"); return MB2_ERR_UNSUPPORTED; }
+  const int nq_pad = (nq + 255) & ~255, nt_pad = (nt + 255) & ~255;
+  MB2_CUDA_CHECK(ctx, ctx->nn_a.reserve((size_t)nq_pad * 128 * 2 + (size_t)nq_pad * 4));
+  MB2_CUDA_CHECK(ctx, ctx->nn_b.reserve((size_t)nt_pad * 128 * 2 + (size_t)nt_pad * 4));
+  void* q_bf16 = ctx->nn_a.p; float* qn = (float*)((uint8_t*)q_bf16 + (size_t)nq_pad * 256);
+  void* t_bf16 = ctx->nn_b.p; float* tn = (float*)((uint8_t*)t_bf16 + (size_t)nt_pad * 256);
+  mb2_nn_prepare(ctx, d_q, nq, nq_pad, q_bf16, qn, 0.f);
+  mb2_nn_prepare(ctx, d_t, nt, nt_pad, t_bf16, tn, 3.0e38f);
+  // per-query state
+  const size_t per_q = 8 * 3 + 4 * 6;
+  MB2_CUDA_CHECK(ctx, ctx->nn_c.reserve((size_t)nq * (per_q + sizeof(MatchRow) + 16) + 256));
+  uint8_t* base = ctx->nn_c.as<uint8_t>();
+  NNState st;
+  st.best0 = (unsigned long long*)base; st.best1 = st.best0 + nq; st.bestP = st.best1 + nq;
+  st.cnt = (int*)(st.bestP + nq); st.incons = st.cnt + nq; st.idx0 = st.incons + nq;
+  st.d0 = (float*)(st.idx0 + nq); st.thr = st.d0 + nq; st.thr_rel = st.thr + nq;
+  MatchRow* rows = (MatchRow*)(((uintptr_t)(st.thr_rel + nq) + 15) & ~(uintptr_t)15);
+  int* accept = (int*)(rows + nq);
+  mb2_nn_init_state(ctx, st, nq);
+  const char* impl = std::getenv("MB2_NN_IMPL");
+  const bool simt = impl && std::strcmp(impl, "simt") == 0;
+  int rc;
+  for (int pass = 1; pass <= 2; pass++) {
+    if (simt) mb2_nn_pass_simt(ctx, pass, d_q, nq, d_t, nt, qn, tn, st, d_txy, contr2);
+    else if ((rc = mb2_nn_pass_tc(ctx, pass, q_bf16, nq, nq_pad, t_bf16, nt_pad, qn, tn, st, d_txy, contr2))) return rc;
+    if (pass == 1) mb2_nn_threshold(ctx, st, nq, qn, sqminratio);
+  }
+  mb2_nn_finalize(ctx, st, nq, nt, nn, rows, accept);
+  // ordered compaction of the accepted rows
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr, nq, ctx->stream);
+  const int cap = std::min(capacity, nq);
+  MB2_CUDA_CHECK(ctx, ctx->nn_d.reserve((size_t)nq * 4 + 16 + cub_bytes + 64 + (size_t)std::max(cap, 1) * 7 * 8));
+  int* pos = ctx->nn_d.as<int>();
+  int* total = pos + nq;
+  void* cub_tmp = (void*)(((uintptr_t)(total + 1) + 15) & ~(uintptr_t)15);
+  double* d_out = (double*)(((uintptr_t)((uint8_t*)cub_tmp + cub_bytes) + 15) & ~(uintptr_t)15);
+  MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, accept, pos, nq, ctx->stream));
+  ctx->launches += 1;
+  LAUNCH1D(ctx, k_match_scatter, nq, rows, accept, pos, nq, d_out, cap, total);
+  int n_match = 0;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_match, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int m = std::min(n_match, cap);
+  if (m > 0) {
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_out, (size_t)m * 7 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (n_match > capacity) { ctx->set_error("match: output capacity too small"); return MB2_ERR_CAPACITY; }
+  return n_match;
+}
+
+}  // namespace
+using namespace MB2_NS;
+
+bool mb2_is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int mb2_stage_in(mb2_ctx* ctx, const void* src, size_t bytes, DevBuf& dst, const void** dev_ptr) {
+  if (mb2_is_device_ptr(src)) { *dev_ptr = src; return MB2_OK; }
+  MB2_CUDA_CHECK(ctx, dst.reserve(bytes ? bytes : 1));
+  if (bytes) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dev_ptr = dst.p;
+  return MB2_OK;
+}
+
+// =================================================================================================
+extern "C" {
+
+int mb2_ctx_create(int device, mb2_ctx** out) {
+  if (!out) return MB2_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return MB2_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) return MB2_ERR_CUDA;
+  mb2_ctx* c = new mb2_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MB2_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return MB2_OK;
+}
+
+void mb2_ctx_destroy(mb2_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->img, &ctx->pyr, &ctx->resp, &ctx->cand, &ctx->misc, &ctx->kp_a, &ctx->kp_b, &ctx->kp_c, &ctx->desc_u8,
+                    &ctx->patch_scratch, &ctx->nn_a, &ctx->nn_b, &ctx->nn_c, &ctx->nn_d, &ctx->rs_a, &ctx->rs_b, &ctx->rs_c, &ctx->octmap};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& s : ctx->slots) { s.desc.release(); s.xy.release(); }
+  ctx->h_a.release(); ctx->h_b.release(); ctx->h_c.release();
+  drop_priv(ctx);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* mb2_last_error(const mb2_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int mb2_ctx_sync(mb2_ctx* ctx) { MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return MB2_OK; }
+void* mb2_ctx_stream(mb2_ctx* ctx) { return (void*)ctx->stream; }
+long long mb2_ctx_launch_count(const mb2_ctx* ctx) { return ctx->launches; }
+
+int mb2_hessaff_detect(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_hessaff_params* par, double tilt, double zoom,
+                       int as_regions, double* out_kp, int capacity) {
+  if (!ctx || !pixels || !par || w <= 0 || h <= 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView img;
+  int rc, n = 0;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  if ((rc = detect_core(ctx, img, *par, tilt, zoom, as_regions, &n))) return rc;
+  if ((rc = download_keys(ctx, ctx->kp_b.as<KeyOut>(), n, out_kp, capacity, ctx->rs_b))) return rc;
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n > capacity) { ctx->set_error("hessaff: output capacity too small"); return MB2_ERR_CAPACITY; }
+  return n;
+}
+
+int mb2_detect_orientation(mb2_ctx* ctx, const float* pixels, int w, int h, const double* in_kp, int n,
+                           const mb2_orientation_params* par, double* out_kp, int capacity) {
+  if (!ctx || !pixels || !par || w <= 0 || h <= 0 || n < 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (n == 0) return 0;
+  ImgView img;
+  int rc, m = 0;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  const void* d_in;
+  if ((rc = mb2_stage_in(ctx, in_kp, (size_t)n * MB2_KP * 8, ctx->rs_b, &d_in))) return rc;
+  MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)n * sizeof(KeyOut)));
+  LAUNCH1D(ctx, k_kp_from_doubles, n, (const double*)d_in, n, ctx->kp_b.as<KeyOut>());
+  if ((rc = orient_core(ctx, img, n, *par, &m))) return rc;
+  if ((rc = download_keys(ctx, ctx->kp_c.as<KeyOut>(), m, out_kp, capacity, ctx->rs_b))) return rc;
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (m > capacity) { ctx->set_error("orientation: output capacity too small"); return MB2_ERR_CAPACITY; }
+  return m;
+}
+
+int mb2_describe_sift(mb2_ctx* ctx, const float* pixels, int w, int h, const double* kp, int n, const mb2_sift_params* par,
+                      uint8_t* desc_u8, float* patches) {
+  if (!ctx || !pixels || !par || !desc_u8 || w <= 0 || h <= 0 || n < 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (n == 0) return 0;
+  ImgView img;
+  int rc;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  const void* d_in;
+  if ((rc = mb2_stage_in(ctx, kp, (size_t)n * MB2_KP * 8, ctx->rs_b, &d_in))) return rc;
+  MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)n * sizeof(KeyOut)));
+  LAUNCH1D(ctx, k_kp_from_doubles, n, (const double*)d_in, n, ctx->kp_b.as<KeyOut>());
+  float* d_patches = nullptr;
+  if (patches) { MB2_CUDA_CHECK(ctx, ctx->rs_c.reserve((size_t)n * 41 * 41 * 4)); d_patches = ctx->rs_c.as<float>(); }
+  if ((rc = describe_core(ctx, img, ctx->kp_b.as<KeyOut>(), n, *par, d_patches))) return rc;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(desc_u8, ctx->desc_u8.p, (size_t)n * 128, cudaMemcpyDeviceToHost, ctx->stream));
+  if (patches) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(patches, d_patches, (size_t)n * 41 * 41 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return n;
+}
+
+int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H, int orig_w, int orig_h,
+                             const mb2_hessaff_params* det, const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot,
+                             int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
+  if (!ctx || !pixels || !H || !det || !ori || !desc || slot < 0 || slot >= MB2_MAX_SLOTS) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView img;
+  int rc, n = 0, m = 0, k = 0;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  if ((rc = detect_core(ctx, img, *det, 1.0, 1.0, 1, &n))) return rc;
+  if ((rc = orient_core(ctx, img, n, *ori, &m))) return rc;
+  RegionSlot& rs = ctx->slots[slot];
+  if (!append) rs.n = 0;
+  if (m > 0) {
+    // ReprojectRegions (synth-detection.cpp:541-616): Hinv via cv::invert (closed form for 3x3)
+    double Hinv[9];
+    {
+      const double* S = H;
+      double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+      if (d == 0) { ctx->set_error("view: singular H"); return MB2_ERR_ARG; }
+      d = 1. / d;
+      Hinv[0] = (S[4] * S[8] - S[5] * S[7]) * d; Hinv[1] = (S[2] * S[7] - S[1] * S[8]) * d; Hinv[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+      Hinv[3] = (S[5] * S[6] - S[3] * S[8]) * d; Hinv[4] = (S[0] * S[8] - S[2] * S[6]) * d; Hinv[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+      Hinv[6] = (S[3] * S[7] - S[4] * S[6]) * d; Hinv[7] = (S[1] * S[6] - S[0] * S[7]) * d; Hinv[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+    }
+    const int is_eye = (std::fabs(H[0] - 1.0) + std::fabs(H[1]) + std::fabs(H[2]) + std::fabs(H[3]) + std::fabs(H[4] - 1.0) +
+                            std::fabs(H[5]) + std::fabs(H[6]) + std::fabs(H[7]) + std::fabs(H[8] - 1.0) < 0.01) ? 1 : 0;
+    MB2_CUDA_CHECK(ctx, ctx->rs_b.reserve(9 * 8));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->rs_b.p, Hinv, sizeof Hinv, cudaMemcpyHostToDevice, ctx->stream));
+    // oriented regions are in kp_c; reproj -> kp_a; compact both -> kp_b (det), kp_c... use rs_c for reproj
+    MB2_CUDA_CHECK(ctx, ctx->kp_a.reserve((size_t)m * sizeof(KeyOut)));
+    mb2_launch_reproject(ctx, ctx->kp_c.as<KeyOut>(), m, ctx->rs_b.as<double>(), is_eye, orig_w, orig_h, ctx->kp_a.as<KeyOut>());
+    MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)m * sizeof(KeyOut)));
+    MB2_CUDA_CHECK(ctx, ctx->rs_c.reserve((size_t)m * sizeof(KeyOut)));
+    if ((rc = compact(ctx, ctx->kp_c.as<KeyOut>(), ctx->kp_a.as<KeyOut>(), m, ctx->kp_b.as<KeyOut>(), ctx->rs_c.as<KeyOut>(), ctx->misc, &k)))
+      return rc;
+  }
+  if (k > 0) {
+    if ((rc = describe_core(ctx, img, ctx->kp_b.as<KeyOut>(), k, *desc, nullptr))) return rc;
+    // keep on device for matching
+    const int base = rs.n;
+    {
+      DevBuf nd, nx;
+      if (base > 0) {  // grow-preserving append
+        MB2_CUDA_CHECK(ctx, nd.reserve((size_t)(base + k) * 128));
+        MB2_CUDA_CHECK(ctx, nx.reserve((size_t)(base + k) * 16));
+        MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(nd.p, rs.desc.p, (size_t)base * 128, cudaMemcpyDeviceToDevice, ctx->stream));
+        MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(nx.p, rs.xy.p, (size_t)base * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+        MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        rs.desc.release(); rs.xy.release();
+        rs.desc = nd; rs.xy = nx;
+      } else {
+        MB2_CUDA_CHECK(ctx, rs.desc.reserve((size_t)k * 128));
+        MB2_CUDA_CHECK(ctx, rs.xy.reserve((size_t)k * 16));
+      }
+    }
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(rs.desc.as<uint8_t>() + (size_t)base * 128, ctx->desc_u8.p, (size_t)k * 128, cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+    LAUNCH1D(ctx, k_xy_from_keys, k, ctx->rs_c.as<KeyOut>(), k, rs.xy.as<double>() + (size_t)base * 2);
+    rs.n = base + k;
+    // results to the host
+    const int mcap = std::min(k, capacity);
+    if (det_kp && (rc = download_keys(ctx, ctx->kp_b.as<KeyOut>(), k, det_kp, capacity, ctx->rs_a))) return rc;
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (reproj_kp && (rc = download_keys(ctx, ctx->rs_c.as<KeyOut>(), k, reproj_kp, capacity, ctx->rs_a))) return rc;
+    if (desc_u8 && mcap > 0)
+      MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(desc_u8, ctx->desc_u8.p, (size_t)mcap * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (k > capacity && (det_kp || reproj_kp || desc_u8)) { ctx->set_error("view: output capacity too small"); return MB2_ERR_CAPACITY; }
+  }
+  return k;
+}
+
+int mb2_match_fginn(mb2_ctx* ctx, const uint8_t* q_desc, int nq, const uint8_t* t_desc, int nt, const double* t_xy, double matchRatio,
+                    double contradDist, int nn, double* out, int capacity) {
+  if (!ctx || nq < 0 || nt < 0 || !out) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (nq == 0 || nt == 0) return 0;
+  const void *dq, *dt, *dxy;
+  int rc;
+  if ((rc = mb2_stage_in(ctx, q_desc, (size_t)nq * 128, ctx->rs_a, &dq))) return rc;
+  if ((rc = mb2_stage_in(ctx, t_desc, (size_t)nt * 128, ctx->rs_b, &dt))) return rc;
+  if ((rc = mb2_stage_in(ctx, t_xy, (size_t)nt * 16, ctx->rs_c, &dxy))) return rc;
+  return match_core(ctx, (const uint8_t*)dq, nq, (const uint8_t*)dt, nt, (const double*)dxy, matchRatio, contradDist, nn, out, capacity);
+}
+
+int mb2_match_slots(mb2_ctx* ctx, int q_slot, int t_slot, double matchRatio, double contradDist, int nn, double* out, int capacity) {
+  if (!ctx || q_slot < 0 || q_slot >= MB2_MAX_SLOTS || t_slot < 0 || t_slot >= MB2_MAX_SLOTS || !out) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RegionSlot &q = ctx->slots[q_slot], &t = ctx->slots[t_slot];
+  return match_core(ctx, q.desc.as<uint8_t>(), q.n, t.desc.as<uint8_t>(), t.n, t.xy.as<double>(), matchRatio, contradDist, nn, out, capacity);
+}
+
+int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const double* models, int K, double th, double* resid, int* I,
+                     double* J) {
+  if (!ctx || !u || !models || len < 0 || K < 0 || which < 0 || which > 4) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (len == 0 || K == 0) return 0;
+  const void *du, *dm;
+  int rc;
+  if ((rc = mb2_stage_in(ctx, u, (size_t)len * 48, ctx->rs_a, &du))) return rc;
+  if ((rc = mb2_stage_in(ctx, models, (size_t)K * 72, ctx->rs_b, &dm))) return rc;
+  const size_t rbytes = resid ? (size_t)K * len * 8 : 0;
+  MB2_CUDA_CHECK(ctx, ctx->rs_c.reserve(rbytes + (size_t)K * 16 + 64));
+  double* d_J = ctx->rs_c.as<double>();
+  int* d_I = (int*)(d_J + K);
+  double* d_res = resid ? (double*)(((uintptr_t)(d_I + K) + 15) & ~(uintptr_t)15) : nullptr;
+  mb2_launch_score(ctx, which, (const double*)du, len, (const double*)dm, K, th, d_res, d_I, d_J);
+  if (J) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(J, d_J, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (I) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(I, d_I, (size_t)K * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (resid) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(resid, d_res, rbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return K;
+}
+
+int mb2_debug_pyramid_level(mb2_ctx* ctx, int octave, int level, int want_resp, float* out, int* rows, int* cols) {
+  if (!ctx) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  std::vector<OctaveLevels>& o = priv(ctx)->last_octaves;
+  if (octave < 0 || octave >= (int)o.size() || level < 0 || level >= o[octave].nlevels) return MB2_ERR_ARG;
+  const ImgView v = want_resp ? o[octave].resp[level] : o[octave].blur[level];
+  if (rows) *rows = v.rows;
+  if (cols) *cols = v.cols;
+  if (out) {
+    MB2_CUDA_CHECK(ctx, cudaMemcpy2DAsync(out, (size_t)v.cols * 4, v.p, (size_t)v.pitch * 4, (size_t)v.cols * 4, v.rows,
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return (int)o.size();
+}
+
+int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed,
+                 double* H, unsigned char* inl, int* data_out, double* J) {
+  (void)u; (void)len; (void)th; (void)conf; (void)max_sam; (void)errorType; (void)doSymCheck; (void)seed; (void)H; (void)inl;
+  (void)data_out; (void)J;
+  if (!ctx) return MB2_ERR_ARG;
+  ctx->set_error("mb2_ransac_h: LO-RANSAC driver not built yet (use mb2_score_models)");
+  return MB2_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

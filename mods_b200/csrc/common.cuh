@@ -1,0 +1,193 @@
+// mods_b200: shared device/host helpers.
+//
+// Floating-point contract: the reference is compiled without -march, so it
+// never executes an FMA; every parity-critical kernel is built with -fmad=false and writes the
+// reference's evaluation order out explicitly.  Where an FMA is provably exact (integer-valued
+// descriptor arithmetic) it is requested explicitly with __fmaf_rn.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/mods_b200.h"
+
+#define MB2_CUDA_CHECK(ctx, expr)                                                              \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+      return MB2_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T> T* as() { return (T*)p; }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {  // grow-only pinned staging
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T> T* as() { return (T*)p; }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// A device-resident set of described regions (what RegionVectorMap[det][desc] holds on the host
+// side of the reference, imagerepresentation.h:66) -- enough of it for MatchFlannFGINN.
+struct RegionSlot {
+  DevBuf desc;   // n x 128 u8
+  DevBuf xy;     // n x 2 f64  (reproj_kp.x, reproj_kp.y)
+  int n = 0;
+};
+
+struct mb2_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  int num_sms = 148;
+  // scratch, reused across calls
+  DevBuf img, pyr, resp, cand, misc, kp_a, kp_b, kp_c, desc_u8, patch_scratch, nn_a, nn_b, nn_c, nn_d, rs_a, rs_b, rs_c;
+  DevBuf octmap;
+  HostBuf h_a, h_b, h_c;
+  RegionSlot slots[MB2_MAX_SLOTS];
+  void* tmap_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime
+  void set_error(const std::string& s) { err = s; }
+};
+
+// ---- exact (non-contracted) float helpers ---------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double d_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double d_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double d_div(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---- device image view ----------------------------------------------------------------------
+struct ImgView {
+  const float* p;
+  int rows, cols, pitch;  // pitch in floats
+  __device__ __forceinline__ float at(int r, int c) const { return p[(size_t)r * pitch + c]; }
+};
+
+// atan2LUTff table (detectors/helpers.cpp:30-72), uploaded once per process by capi.cu.
+// The library is built as ONE translation unit (mods_b200.cu includes every kernel file), so this
+// is the single definition.
+__constant__ double c_atan_lut[256];
+
+// detectors/helpers.cpp:160-207
+__device__ __forceinline__ float atan2LUTff_dev(float y, float x) {
+  const float PI_2f = 1.57079632679489661923f, PIf = 3.14159265358979323846f;
+  if (x > 0.f) {
+    if (y > 0.f) {
+      if (x > y) return (float)c_atan_lut[(int)(fdiv(fmul(255.f, y), x))];
+      else return (float)d_sub((double)PI_2f, c_atan_lut[(int)(fdiv(fmul(255.f, x), y))]);
+    } else {
+      float absy = fabsf(y);
+      if (x > absy) return (float)(-c_atan_lut[(int)(fdiv(fmul(255.f, absy), x))]);
+      else return (float)d_add((double)(-PI_2f), c_atan_lut[(int)(fdiv(fmul(255.f, x), absy))]);
+    }
+  } else if (y > 0.f) {
+    float absx = fabsf(x);
+    if (absx > y) return (float)d_sub((double)PIf, c_atan_lut[(int)(fdiv(fmul(255.f, y), absx))]);
+    else return (float)d_add((double)PI_2f, c_atan_lut[(int)(fdiv(fmul(255.f, absx), y))]);
+  } else {
+    float absx = fabsf(x), absy = fabsf(y);
+    if (absx > absy) return (float)d_add((double)(-PIf), c_atan_lut[(int)(fdiv(fmul(255.f, absy), absx))]);
+    else {
+      if (x == 0.f) return 0.f;
+      return (float)d_sub((double)(-PI_2f), c_atan_lut[(int)(fdiv(fmul(255.f, absx), absy))]);
+    }
+  }
+}
+
+// detectors/helpers.cpp:524-549
+__device__ __forceinline__ bool interpolateCheckBorders_dev(int orig_w, int orig_h, float ofsx, float ofsy, float a11, float a12,
+                                                            float a21, float a22, int res_w, int res_h) {
+  const int width = orig_w - 2, height = orig_h - 2;
+  const float halfWidth = (float)ceil((double)(float)res_w / 2.0);
+  const float halfHeight = (float)ceil((double)(float)res_h / 2.0);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float xs = (i < 2) ? -halfWidth : halfWidth;
+    const float ys = (i & 1) ? halfHeight : -halfHeight;
+    float imx = fadd(fadd(ofsx, fmul(xs, a11)), fmul(ys, a12));
+    float imy = fadd(fadd(ofsy, fmul(xs, a21)), fmul(ys, a22));
+    if (floorf(imx) <= 0 || floorf(imy) <= 0 || ceilf(imx) >= width || ceilf(imy) >= height) return true;
+  }
+  return false;
+}
+
+// One output row of interpolate() (detectors/helpers.cpp:551-626).  The reference advances the
+// sample position with running float sums; `row` (0-based from the top) is reached by `row`
+// additions of (a12, a22) starting at (ofs - halfHeight*a12, ofs - halfHeight*a22), then the row is
+// walked with `+= (a11, a21)`.  im may live in global or shared memory.
+template <class Out>
+__device__ __forceinline__ void interpolate_row(const float* __restrict__ im, int im_rows, int im_cols, int im_pitch,
+                                                float ofsx, float ofsy, float a11, float a12, float a21, float a22,
+                                                int rw, int rh, bool touch, int row, Out out /* out(i, value) */) {
+  const int halfWidth = rw >> 1, halfHeight = rh >> 1;
+  float rx = fsub(ofsx, fmul((float)halfHeight, a12));
+  float ry = fsub(ofsy, fmul((float)halfHeight, a22));
+  for (int j = 0; j < row; ++j) { rx = fadd(rx, a12); ry = fadd(ry, a22); }
+  float WX = fsub(rx, fmul((float)halfWidth, a11));
+  float WY = fsub(ry, fmul((float)halfWidth, a21));
+  const int width = im_cols - 1, height = im_rows - 1;
+  for (int i = 0; i < rw; ++i) {
+    float v;
+    if (!touch) {
+      const int x = (int)WX, y = (int)WY;
+      const float wx = fsub(WX, (float)x);
+      const float* R0 = im + (size_t)y * im_pitch;
+      const float* R1 = R0 + im_pitch;
+      const float I1 = fadd(fmul(wx, fsub(R0[x + 1], R0[x])), R0[x]);
+      v = fadd(fmul(fsub(WY, (float)y), fsub(fadd(fmul(wx, fsub(R1[x + 1], R1[x])), R1[x]), I1)), I1);
+    } else {
+      const int x = (int)floorf(WX), y = (int)floorf(WY);
+      if (WX >= 0 && WY >= 0 && x < width && y < height) {
+        const float wx = fsub(WX, (float)x);
+        const float* R0 = im + (size_t)y * im_pitch;
+        const float* R1 = R0 + im_pitch;
+        const float I1 = fadd(fmul(wx, fsub(R0[x + 1], R0[x])), R0[x]);
+        v = fadd(fmul(fsub(WY, (float)y), fsub(fadd(fmul(wx, fsub(R1[x + 1], R1[x])), R1[x]), I1)), I1);
+      } else v = 0.f;
+    }
+    out(i, v);
+    WX = fadd(WX, a11); WY = fadd(WY, a21);
+  }
+}
+
+// Launch bookkeeping
+#define MB2_LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
+  do {                                                                     \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
+    (ctx)->launches++;                                                     \
+  } while (0)
+
+// host-side helpers implemented in capi.cu
+int mb2_stage_in(mb2_ctx* ctx, const void* src, size_t bytes, DevBuf& dst, const void** dev_ptr);
+bool mb2_is_device_ptr(const void* p);

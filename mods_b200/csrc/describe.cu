@@ -1,0 +1,313 @@
+// Affine-normalised 41x41 patch extraction + SIFT / RootSIFT, one CTA per region.
+//
+// Reference: DescribeRegions<> (synth-detection.hpp:169-255): sample a (P+2)^2 patch with the
+// det-1 affine frame, blur it with sigma = 1.5*P/41 (helpers.cpp:726-731 -> OpenCV GaussianBlur,
+// restated in oracle/cvmath.h), resample to 41x41, photometricallyNormalize (helpers.cpp:666-715);
+// SIFTDescriptor (matching/siftdesc.cpp:22-71 bins, :73-131 samplePatch, :133-159 normalize,
+// :199-278 SIFTnorm/RootSIFTnorm, :290-381 gradients).
+//
+// Design notes
+//  * The final 41x41 bilinear resample reads the blurred patch at <= 82 distinct rows x 82 distinct
+//    columns (the resampling matrix is diagonal), so the row pass is evaluated only at those
+//    columns and the column pass only at those 82x82 points -- same values, O(P*82*taps) instead of
+//    O(P^2*taps) work for large regions.
+//  * Gaussian taps depend only on the integer half-size m = ceil(s*mrSize) and are built on the
+//    host with libm (exactly the reference's arithmetic), one table per context.
+//  * Bit parity: sample positions use the reference's running float sums; photometric sums are
+//    serial float sums in raster order; every SIFT bin is accumulated in double by one thread
+//    walking the patch in raster order (the reference touches a bin at most once per pixel).
+#include "common.cuh"
+#undef MB2_NS
+#define MB2_NS mb2_describe_detail
+#include "pyramid.cuh"
+#include "describe.cuh"
+
+namespace MB2_NS {
+
+constexpr int PS = 41, NPIX = PS * PS, DT = 128;  // threads per CTA
+constexpr int NEED = 2 * PS;                      // needed rows / columns of the blurred patch
+
+struct KpGeom {  // per-region geometry shared by the planning and the describe kernels
+  int m;          // int(ceil(s * mrSize))
+  int P2;         // patchImageSize + 2 (0 => direct path)
+  float scale;    // imageToPatchScale
+};
+
+__device__ __forceinline__ KpGeom kp_geom(const KeyOut& k, const DescribeParams& dp) {
+  KpGeom g;
+  if (!dp.fast) {
+    const float mrScale = (float)ceil(k.v[6] * dp.mrSize);
+    g.m = (int)mrScale;
+    const int patchImageSize = 2 * g.m + 1;
+    g.scale = fdiv((float)patchImageSize, (float)dp.patchSize);
+    g.P2 = ((double)g.scale > 0.4) ? patchImageSize + 2 : 0;
+  } else {
+    const double mrScale = dp.mrSize * k.v[6];
+    g.m = (int)mrScale;
+    const int patchImageSize = 2 * g.m + 1;
+    g.scale = (float)((double)patchImageSize / (double)dp.patchSize);
+    g.P2 = 0;
+  }
+  return g;
+}
+
+// scratch floats needed by region i: (P2*P2) sampled patch + (P2*NEED) row-pass columns
+__global__ void k_plan(const KeyOut* __restrict__ kps, int n, DescribeParams dp, int max_m, unsigned long long* __restrict__ need,
+                       int* __restrict__ too_big) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  KpGeom g = kp_geom(kps[i], dp);
+  if (g.P2 > 0 && g.m > max_m) { atomicMax(too_big, g.m); }
+  need[i] = g.P2 > 0 ? (unsigned long long)g.P2 * (unsigned long long)(g.P2 + NEED) : 0ull;
+}
+
+__global__ void __launch_bounds__(DT)
+k_describe(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp, const DescTables* __restrict__ tab,
+           const TapTable taps, const unsigned long long* __restrict__ scratch_off, float* __restrict__ scratch,
+           uint8_t* __restrict__ desc_out, float* __restrict__ patch_out) {
+  __shared__ float s_patch[NPIX];
+  __shared__ float s_small[NEED * NEED]; // blurred patch at the needed rows x columns (extraction phase)
+  // the SIFT phase re-uses s_small: mask*grad, orientation-bin fraction, orientation bin
+  float* s_v0 = s_small;
+  float* s_wo1 = s_small + NPIX;
+  unsigned char* s_bo0 = (unsigned char*)(s_small + 2 * NPIX);
+  __shared__ int s_cols[NEED], s_rows[NEED];
+  __shared__ double s_vec[128];
+  __shared__ float s_stat[2];
+
+  const int kidx = blockIdx.x, tid = threadIdx.x;
+  if (kidx >= n) return;
+  const KeyOut k = kps[kidx];
+  const KpGeom g = kp_geom(k, dp);
+  const float x = (float)k.v[0], y = (float)k.v[1];
+  const float a11 = (float)k.v[2], a12 = (float)k.v[3], a21 = (float)k.v[4], a22 = (float)k.v[5];
+
+  if (g.P2 == 0) {
+    // heavy oversampling (or fast extraction): affine-normalise straight from the image
+    const float A11 = fmul(a11, g.scale), A12 = fmul(a12, g.scale), A21 = fmul(a21, g.scale), A22 = fmul(a22, g.scale);
+    const bool touch = interpolateCheckBorders_dev(img.cols, img.rows, x, y, A11, A12, A21, A22, PS, PS);
+    if (tid < PS)
+      interpolate_row(img.p, img.rows, img.cols, img.pitch, x, y, A11, A12, A21, A22, PS, PS, touch, tid,
+                      [&](int i, float v) { s_patch[tid * PS + i] = v; });
+    __syncthreads();
+  } else {
+    const int P2 = g.P2;
+    float* bufA = scratch + scratch_off[kidx];          // P2 x P2 sampled patch
+    float* bufB = bufA + (size_t)P2 * P2;               // P2 x NEED row pass at the needed columns
+    // A. sample with the det-1 frame, one thread per output row
+    {
+      const bool touch = interpolateCheckBorders_dev(img.cols, img.rows, x, y, a11, a12, a21, a22, P2, P2);
+      for (int row = tid; row < P2; row += DT)
+        interpolate_row(img.p, img.rows, img.cols, img.pitch, x, y, a11, a12, a21, a22, P2, P2, touch, row,
+                        [&](int i, float v) { bufA[(size_t)row * P2 + i] = v; });
+    }
+    // positions of the second interpolate(): ofs = P2>>1, A = diag(scale); the reference's running sums
+    const float ofs = (float)(P2 >> 1), sc = g.scale;
+    const bool touch2 = interpolateCheckBorders_dev(P2, P2, ofs, ofs, sc, 0.f, 0.f, sc, PS, PS);
+    if (tid == 0) {
+      // columns: WX starts at rx - 20*a11 with rx = ofs - 20*a12 = ofs - 0, then += a11
+      float rx = fsub(ofs, fmul((float)(PS >> 1), 0.f));
+      float WX = fsub(rx, fmul((float)(PS >> 1), sc));
+      for (int i = 0; i < PS; i++) {
+        int xi = touch2 ? (int)floorf(WX) : (int)WX;
+        s_cols[2 * i] = xi; s_cols[2 * i + 1] = xi + 1;
+        WX = fadd(WX, sc);
+      }
+    } else if (tid == 32) {
+      // rows: ry starts at ofs - 20*a22, += a22 per row; WY = ry - 20*a21 = ry - 0
+      float ry = fsub(ofs, fmul((float)(PS >> 1), sc));
+      for (int j = 0; j < PS; j++) {
+        float WY = fsub(ry, fmul((float)(PS >> 1), 0.f));
+        int yi = touch2 ? (int)floorf(WY) : (int)WY;
+        s_rows[2 * j] = yi; s_rows[2 * j + 1] = yi + 1;
+        ry = fadd(ry, sc);
+      }
+    }
+    __syncthreads();
+    // B. row pass (left-to-right accumulation, replicate border) at the needed columns, all rows
+    const int nt = taps.n[g.m], h = nt >> 1;
+    const float* kw = taps.w + taps.off[g.m];
+    for (int idx = tid; idx < P2 * NEED; idx += DT) {
+      const int r = idx / NEED, ci = idx - r * NEED;
+      const int c = s_cols[ci];
+      float acc = 0.f;
+      if (c >= 0 && c < P2) {
+        const float* rowp = bufA + (size_t)r * P2;
+        int cc = c - h; cc = cc < 0 ? 0 : cc;
+        acc = fmul(kw[0], rowp[cc]);
+        for (int j = 1; j < nt; j++) {
+          cc = c - h + j; cc = cc < 0 ? 0 : (cc > P2 - 1 ? P2 - 1 : cc);
+          acc = fadd(acc, fmul(kw[j], rowp[cc]));
+        }
+      }
+      bufB[idx] = acc;
+    }
+    __syncthreads();
+    // C. column pass (symmetric pairs) at the needed rows x needed columns
+    for (int idx = tid; idx < NEED * NEED; idx += DT) {
+      const int ri = idx / NEED, ci = idx - ri * NEED;
+      const int r = s_rows[ri], c = s_cols[ci];
+      float acc = 0.f;
+      if (r >= 0 && r < P2 && c >= 0 && c < P2) {
+        acc = fmul(kw[h], bufB[(size_t)r * NEED + ci]);
+        for (int j = 1; j <= h; j++) {
+          int rp = r + j; rp = rp > P2 - 1 ? P2 - 1 : rp;
+          int rm = r - j; rm = rm < 0 ? 0 : rm;
+          acc = fadd(acc, fmul(kw[h + j], fadd(bufB[(size_t)rp * NEED + ci], bufB[(size_t)rm * NEED + ci])));
+        }
+      }
+      s_small[idx] = acc;
+    }
+    __syncthreads();
+    // D. bilinear resample to 41x41 (interpolate(), helpers.cpp:551-626, with the same running sums)
+    if (tid < PS) {
+      const int j = tid;
+      float ry = fsub(ofs, fmul((float)(PS >> 1), sc));
+      for (int q = 0; q < j; q++) ry = fadd(ry, sc);
+      float rx = fsub(ofs, fmul((float)(PS >> 1), 0.f));
+      for (int q = 0; q < j; q++) rx = fadd(rx, 0.f);
+      float WX = fsub(rx, fmul((float)(PS >> 1), sc));
+      float WY = fsub(ry, fmul((float)(PS >> 1), 0.f));
+      const int width = P2 - 1, height = P2 - 1;
+      for (int i = 0; i < PS; i++) {
+        const int xi = s_cols[2 * i], yi = s_rows[2 * j];
+        float v = 0.f;
+        const bool inside = touch2 ? (WX >= 0 && WY >= 0 && xi < width && yi < height) : true;
+        if (inside) {
+          const float wx = fsub(WX, (float)xi);
+          const float r0x = s_small[(2 * j) * NEED + 2 * i], r0x1 = s_small[(2 * j) * NEED + 2 * i + 1];
+          const float r1x = s_small[(2 * j + 1) * NEED + 2 * i], r1x1 = s_small[(2 * j + 1) * NEED + 2 * i + 1];
+          const float I1 = fadd(fmul(wx, fsub(r0x1, r0x)), r0x);
+          v = fadd(fmul(fsub(WY, (float)yi), fsub(fadd(fmul(wx, fsub(r1x1, r1x)), r1x), I1)), I1);
+        }
+        s_patch[j * PS + i] = v;
+        WX = fadd(WX, sc); WY = fadd(WY, 0.f);
+      }
+    }
+    __syncthreads();
+  }
+
+  // photometricallyNormalize (helpers.cpp:666-715): serial float sums in raster order
+  if (dp.photoNorm) {
+    if (tid == 0) {
+      float sum = 0.f, gsum = 0.f;
+      for (int p = 0; p < NPIX; p++) if (tab->mask[p] > 0) { sum = fadd(sum, s_patch[p]); gsum = fadd(gsum, 1.f); }
+      sum = fdiv(sum, gsum);
+      float var = 0.f;
+      for (int p = 0; p < NPIX; p++) if (tab->mask[p] > 0) { const float d = fsub(sum, s_patch[p]); var = fadd(var, fmul(d, d)); }
+      var = sqrtf(fdiv(var, gsum));
+      s_stat[0] = sum; s_stat[1] = var;
+    }
+    __syncthreads();
+    const float sum = s_stat[0], var = s_stat[1];
+    if (!((double)var < 0.0001)) {
+      const float fac = fdiv(50.0f, var);
+      for (int p = tid; p < NPIX; p += DT) {
+        float v = fadd(128.f, fmul(fac, fsub(s_patch[p], sum)));
+        if (v > 255) v = 255;
+        if (v < 0) v = 0;
+        s_patch[p] = v;
+      }
+    }
+    __syncthreads();
+  }
+  if (patch_out) for (int p = tid; p < NPIX; p += DT) patch_out[(size_t)kidx * NPIX + p] = s_patch[p];
+
+  // gradients (siftdesc.cpp:290-345), orientation-bin split per pixel (siftdesc.cpp:99-107)
+  for (int p = tid; p < NPIX; p += DT) {
+    const int r = p / PS, c = p - r * PS;
+    float xg, yg;
+    if (c == 0) xg = fsub(s_patch[p + 1], s_patch[p]);
+    else if (c == PS - 1) xg = fsub(s_patch[p], s_patch[p - 1]);
+    else xg = fsub(s_patch[p + 1], s_patch[p - 1]);
+    if (r == 0) yg = fsub(s_patch[p + PS], s_patch[p]);
+    else if (r == PS - 1) yg = fsub(s_patch[p], s_patch[p - PS]);
+    else yg = fsub(s_patch[p + PS], s_patch[p - PS]);
+    const float grad = sqrtf(fadd(fmul(xg, xg), fmul(yg, yg)));
+    const float ori = atan2LUTff_dev(yg, xg);
+    s_v0[p] = fmul(tab->mask[p], grad);
+    const double M_PI_DOUBLED = 6.28318530718;
+    const float o = (float)(8.0 * ((double)ori + M_PI_DOUBLED) / M_PI_DOUBLED);
+    int bo0 = (int)o;
+    s_wo1[p] = fsub(o, (float)bo0);
+    s_bo0[p] = (unsigned char)(bo0 % 8);
+  }
+  __syncthreads();
+  // one thread per descriptor bin (rb, cb, bo), raster-order accumulation in double
+  {
+    const int rb = tid >> 5, cb = (tid >> 3) & 3, bo = tid & 7;
+    double acc = 0.0;
+    for (int r = 8 * rb; r < 8 * rb + 16 && r < PS; r++) {
+      float wr;  // at most one of the two row contributions has a non-zero weight for a given bin
+      if (tab->bin0[r] == rb * 8 && tab->w0[r] > 0) wr = tab->w0[r];
+      else if (tab->bin1[r] == rb * 8 && tab->w1[r] > 0) wr = tab->w1[r];
+      else continue;
+      for (int c = 8 * cb; c < 8 * cb + 16 && c < PS; c++) {
+        float wcw;
+        if (tab->bin0[c] == cb * 8 && tab->w0[c] > 0) wcw = tab->w0[c];
+        else if (tab->bin1[c] == cb * 8 && tab->w1[c] > 0) wcw = tab->w1[c];
+        else continue;
+        const int p = r * PS + c;
+        const float wc = fmul(wcw, s_v0[p]);
+        const float val = fmul(wr, wc);
+        if (val > 0) {
+          const int bo0 = s_bo0[p], bo1 = (bo0 + 1) & 7;
+          const float wo1 = s_wo1[p];
+          if (bo0 == bo) acc += (double)fmul(val, fsub(1.0f, wo1));
+          else if (bo1 == bo) acc += (double)fmul(val, wo1);
+        }
+      }
+    }
+    s_vec[tid] = acc;
+  }
+  __syncthreads();
+  // SIFTnorm / RootSIFTnorm on the double vector (siftdesc.cpp:133-159, 199-222, 247-262)
+  if (tid == 0) {
+    const double maxBinValue = (double)0.2f;
+    for (int pass = 0; pass < 2; pass++) {
+      double len = 0.0;
+      for (int i = 0; i < 128; i += 4) {
+        const double sq0 = s_vec[i] * s_vec[i], sq1 = s_vec[i + 1] * s_vec[i + 1], sq2 = s_vec[i + 2] * s_vec[i + 2],
+                     sq3 = s_vec[i + 3] * s_vec[i + 3];
+        len += sq0 + sq1 + sq2 + sq3;
+      }
+      len = sqrt(len);
+      const double fac = 1.0 / len;
+      for (int i = 0; i < 128; i++) s_vec[i] *= fac;
+      if (pass == 1) break;
+      bool changed = false;
+      for (int i = 0; i < 128; i++) if (s_vec[i] > maxBinValue) { s_vec[i] = maxBinValue; changed = true; }
+      if (!changed) break;
+    }
+    if (dp.rootSIFT) {
+      double sum = 0.;
+      for (int i = 0; i < 128; i++) sum += fabs(s_vec[i]);
+      for (int i = 0; i < 128; i++) s_vec[i] = sqrt(s_vec[i] / sum);
+    }
+  }
+  __syncthreads();
+  {
+    // (int)(512.0 * v + 0.5) for RootSIFT, (int)(512.0f * v + 0.5) for SIFT: identical in double
+    int b = (int)(512.0 * s_vec[tid] + 0.5);
+    b = b < 0 ? 0 : (b > 255 ? 255 : b);
+    desc_out[(size_t)kidx * 128 + tid] = (uint8_t)b;
+  }
+}
+
+}  // namespace
+using namespace MB2_NS;
+
+int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribeParams& dp, int max_m, unsigned long long* d_need,
+                      int* d_too_big) {
+  if (!n) return MB2_OK;
+  MB2_LAUNCH(ctx, k_plan, (n + 127) / 128, 128, 0, kps, n, dp, max_m, d_need, d_too_big);
+  return MB2_OK;
+}
+
+int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
+                               const DescTables* d_tables, const TapTable& taps, const unsigned long long* d_off, float* d_scratch,
+                               uint8_t* d_desc, float* d_patches) {
+  if (!n) return MB2_OK;
+  MB2_LAUNCH(ctx, k_describe, n, DT, 0, img, kps, n, dp, d_tables, taps, d_off, d_scratch, d_desc, d_patches);
+  return MB2_OK;
+}

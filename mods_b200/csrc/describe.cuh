@@ -1,0 +1,19 @@
+// Records shared between describe.cu and capi.cu.
+#pragma once
+#include "common.cuh"
+#include "pyramid.cuh"
+
+// Gaussian taps of the per-region pre-blur, indexed by m = int(ceil(s*mrSize)):
+// sigma = 1.5f * float(2m+1)/41, kernel as oracle/cvmath.h / OpenCV 2.4.9 getGaussianKernel.
+struct TapTable {
+  const int* n;      // taps per m (0 when the region takes the direct path)
+  const int* off;    // offset into w
+  const float* w;
+  int max_m;
+};
+
+int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribeParams& dp, int max_m, unsigned long long* d_need,
+                      int* d_too_big);
+int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
+                               const DescTables* d_tables, const TapTable& taps, const unsigned long long* d_off, float* d_scratch,
+                               uint8_t* d_desc, float* d_patches);

@@ -1,0 +1,466 @@
+// Exact all-pairs squared-L2 nearest neighbours over 128-D u8 descriptors with the FGINN
+// (first geometrically inconsistent) ratio test -- MatchFlannFGINN (matching/matching.cpp:357-461)
+// for vector_matcher = linear.
+//
+// Arithmetic: descriptors are integers 0..255 (siftdesc.cpp:218,242,258,274), exact in bf16;
+// products <= 65025 and 128-term sums <= 8.4e6 < 2^24 are exact in fp32, so
+// d(q,t) = |q|^2 + |t|^2 - 2 q.t from a bf16 x bf16 -> fp32 tensor-core contraction is bit-exact
+// and independent of accumulation order.
+//
+// Instead of materialising the reference's 50-NN table, the decision is evaluated exactly in two
+// streaming passes over the N1 x N2 distance matrix (distances never leave the SM):
+//   pass 1: (d0, idx0) = min over trains, ties -> lower index.
+//   between: thr(q) = the smallest integer distance dJ for which the reference's float test
+//            (double)(d0 / dJ) <= ratio^2 holds (monotone in dJ).
+//   pass 2: "failers" are trains with d < thr (they precede every "passer" in the sorted kNN list):
+//            count them, flag any failer farther than contradDist from idx0 in the image, keep the
+//            closest failer != idx0 (2nd NN) and the closest passer (the neighbour the loop accepts).
+//   accept  <=> no inconsistent failer, #failers <= min(nn, N2) - 1, a passer exists.
+//
+// The contraction runs on tcgen05 (UMMA 128x128x16, bf16 -> fp32 in TMEM), operands staged by TMA
+// with 128B swizzle; a SIMT dp4a kernel computes the same per-(query, chunk) partials and is used
+// as the on-GPU cross-check (MB2_NN_IMPL=simt) -- both feed the same merge + finalize kernels.
+#include "common.cuh"
+#undef MB2_NS
+#define MB2_NS mb2_nn_detail
+#include "nn.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace MB2_NS {
+
+constexpr unsigned long long KEY_INIT = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ unsigned long long make_key(float d, int idx) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;  // d >= 0: bit pattern is monotone
+}
+
+// ---------------------------------------------------------------------------------------------
+// preparation: u8 -> bf16 rows (padded to a multiple of 256 rows) + squared norms
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prepare(const uint8_t* __restrict__ desc, int n, int n_pad, __nv_bfloat16* __restrict__ out,
+                          float* __restrict__ norms, float pad_norm) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_pad) return;
+  unsigned w = 0;
+  if (row < n) w = ((const unsigned*)(desc + (size_t)row * 128))[lane];
+  const int b0 = w & 255, b1 = (w >> 8) & 255, b2 = (w >> 16) & 255, b3 = w >> 24;
+  __nv_bfloat162 lo = __floats2bfloat162_rn((float)b0, (float)b1), hi = __floats2bfloat162_rn((float)b2, (float)b3);
+  __nv_bfloat162* o = (__nv_bfloat162*)(out + (size_t)row * 128 + lane * 4);
+  o[0] = lo; o[1] = hi;
+  int s = b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) norms[row] = row < n ? (float)s : pad_norm;
+}
+
+__global__ void k_init_state(NNState st, int nq) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  st.best0[i] = KEY_INIT; st.best1[i] = KEY_INIT; st.bestP[i] = KEY_INIT; st.cnt[i] = 0; st.incons[i] = 0;
+}
+
+// thr(q): smallest integer dJ >= 1 with (double)(float(d0) / float(dJ)) <= sqminratio  (matching.cpp:435-437)
+__global__ void k_threshold(NNState st, int nq, const float* __restrict__ qn, double sqminratio) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const unsigned long long k = st.best0[i];
+  const float d0 = __uint_as_float((unsigned)(k >> 32));
+  st.d0[i] = d0; st.idx0[i] = (int)(unsigned)k;
+  double guess = floor((double)d0 / sqminratio);
+  if (guess < 1) guess = 1;
+  float t = (float)guess;
+  // walk to the exact boundary of the float test (a couple of steps at most)
+  while (t > 1.f && (double)__fdiv_rn(d0, t - 1.f) <= sqminratio) t -= 1.f;
+  while (!((double)__fdiv_rn(d0, t) <= sqminratio)) t += 1.f;
+  st.thr[i] = t;
+  st.thr_rel[i] = t - qn[i];  // compared against |t|^2 - 2 q.t (exact: all integers < 2^24)
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-thread accumulators of one query row over a range of trains
+// ---------------------------------------------------------------------------------------------
+struct Pass1Acc {
+  float best; int idx;
+  __device__ __forceinline__ void init() { best = 3.0e38f; idx = -1; }
+  __device__ __forceinline__ void add(float v, int col) { if (v < best) { best = v; idx = col; } }
+};
+
+struct Pass2Acc {
+  float bestP; int idxP; float best1; int idx1; int cnt; int incons;
+  __device__ __forceinline__ void init() { bestP = 3.0e38f; idxP = -1; best1 = 3.0e38f; idx1 = -1; cnt = 0; incons = 0; }
+  __device__ __forceinline__ void add(float v, int col, float thr_rel, int idx0, const double* __restrict__ txy, double contr2) {
+    if (v < thr_rel) {
+      cnt++;
+      if (col != idx0) {
+        if (v < best1) { best1 = v; idx1 = col; }
+        const double dx = txy[2 * idx0] - txy[2 * col], dy = txy[2 * idx0 + 1] - txy[2 * col + 1];
+        if (dx * dx + dy * dy > contr2) incons = 1;   // distanceSq, matching.cpp:174-179
+      }
+    } else if (v < bestP) { bestP = v; idxP = col; }
+  }
+};
+
+__device__ __forceinline__ void merge_pass1(NNState& st, int q, float qn, const Pass1Acc& a) {
+  if (a.idx >= 0) atomicMin(&st.best0[q], make_key(a.best + qn, a.idx));
+}
+__device__ __forceinline__ void merge_pass2(NNState& st, int q, float qn, const Pass2Acc& a) {
+  if (a.cnt) atomicAdd(&st.cnt[q], a.cnt);
+  if (a.incons) atomicOr(&st.incons[q], 1);
+  if (a.idx1 >= 0) atomicMin(&st.best1[q], make_key(a.best1 + qn, a.idx1));
+  if (a.idxP >= 0) atomicMin(&st.bestP[q], make_key(a.bestP + qn, a.idxP));
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT cross-check kernel: one thread per query, __dp4a on the raw u8 descriptors
+// ---------------------------------------------------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(128)
+k_nn_simt(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt, const float* __restrict__ qn,
+          const float* __restrict__ tn, NNState st, const double* __restrict__ txy, double contr2, int chunk) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t0 = blockIdx.y * chunk, t1 = min(nt, t0 + chunk);
+  if (qi >= nq) return;
+  unsigned qa[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) qa[i] = ((const unsigned*)(q + (size_t)qi * 128))[i];
+  Pass1Acc a1; Pass2Acc a2; a1.init(); a2.init();
+  float thr_rel = 0.f; int idx0 = -1;
+  if (PASS == 2) { thr_rel = st.thr_rel[qi]; idx0 = st.idx0[qi]; }
+  for (int j = t0; j < t1; j++) {
+    const unsigned* tp = (const unsigned*)(t + (size_t)j * 128);
+    unsigned dot = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) dot = __dp4a(qa[i], tp[i], dot);
+    const float v = __fmaf_rn(-2.f, (float)dot, tn[j]);
+    if (PASS == 1) a1.add(v, j); else a2.add(v, j, thr_rel, idx0, txy, contr2);
+  }
+  if (PASS == 1) merge_pass1(st, qi, qn[qi], a1); else merge_pass2(st, qi, qn[qi], a2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 256;            // queries per work item (two UMMA M=128 halves)
+constexpr int BN = 128;            // trains per tile (UMMA N)
+constexpr int BK = 64;             // bf16 per swizzle-128B row
+constexpr int KBLOCKS = 2;         // 128 / BK
+constexpr int STAGES = 3;          // B-operand smem ring
+constexpr int TSTAGES = 2;         // TMEM accumulator ring (2 x 256 columns)
+constexpr int TILE_BYTES = 128 * BK * 2;          // one [128 x 64] bf16 box = 16 KB
+constexpr int A_BYTES = 2 * KBLOCKS * TILE_BYTES; // 64 KB
+constexpr int B_STAGE_BYTES = KBLOCKS * TILE_BYTES;  // 32 KB
+constexpr int NN_THREADS = 32 * 10;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int SMEM_BYTES = A_BYTES + STAGES * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile [rows][64 bf16]: start address, SBO = 1024 B (8 rows), version 1 (sm_100),
+// layout type 2 (SWIZZLE_128B).  (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // bits [0,14)  start address >> 4
+  d |= (uint64_t)0 << 16;                            // bits [16,30) leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // bits [32,46) stride byte offset
+  d |= (uint64_t)1 << 46;                            // bits [46,48) descriptor version
+  d |= (uint64_t)2 << 61;                            // bits [61,64) SWIZZLE_128B
+  return d;
+}
+// kind::f16, BF16 x BF16 -> F32, K-major A and B, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(NN_THREADS, 1)
+k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, int nq, int nt_pad,
+        const float* __restrict__ qn, const float* __restrict__ tn, NNState st, const double* __restrict__ txy, double contr2,
+        int tiles_per_chunk, int n_qblocks, int n_chunks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                          // [half][kblock] 16 KB tiles
+  uint8_t* sB = smem + A_BYTES;                // [stage][kblock]
+  uint64_t* bars = (uint64_t*)(smem + A_BYTES + STAGES * B_STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]   TMA -> MMA
+  uint64_t* empty = bars + STAGES;             // [STAGES]   MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;         // [TSTAGES]  MMA -> epilogue
+  uint64_t* tempty = tfull + TSTAGES;          // [TSTAGES]  epilogue -> MMA
+  uint64_t* a_full = tempty + TSTAGES;         // A tile landed
+  uint64_t* a_empty = a_full + 1;              // A tile no longer read by the tensor core
+  uint32_t* tmem_slot = (uint32_t*)(a_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = n_qblocks * n_chunks;
+  const int total_tiles = nt_pad / BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < TSTAGES; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (2 stages x 2 halves x 128 fp32 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int qb = item / n_chunks, ch = item - qb * n_chunks;
+        const int tile0 = ch * tiles_per_chunk, tile1 = min(total_tiles, tile0 + tiles_per_chunk);
+        mbar_wait(a_empty, a_phase ^ 1);
+        mbar_expect_tx(a_full, A_BYTES);
+        for (int half = 0; half < 2; half++)
+          for (int kb = 0; kb < KBLOCKS; kb++)
+            tma_load_2d(&tmap_q, a_full, sA + (half * KBLOCKS + kb) * TILE_BYTES, kb * BK, qb * BM + half * 128);
+        a_phase ^= 1;
+        for (int tile = tile0; tile < tile1; tile++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], B_STAGE_BYTES);
+          for (int kb = 0; kb < KBLOCKS; kb++)
+            tma_load_2d(&tmap_t, &full[stage], sB + (stage * KBLOCKS + kb) * TILE_BYTES, kb * BK, tile * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, tstage = 0, tphase = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int qb = item / n_chunks, ch = item - qb * n_chunks;
+        const int tile0 = ch * tiles_per_chunk, tile1 = min(total_tiles, tile0 + tiles_per_chunk);
+        (void)qb;
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        for (int tile = tile0; tile < tile1; tile++) {
+          mbar_wait(&tempty[tstage], tphase ^ 1);
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int half = 0; half < 2; half++) {
+            const uint32_t d_tmem = tmem_base + tstage * 256 + half * 128;
+            for (int kb = 0; kb < KBLOCKS; kb++) {
+              const uint64_t da0 = umma_desc(smem_u32(sA + (half * KBLOCKS + kb) * TILE_BYTES));
+              const uint64_t db0 = umma_desc(smem_u32(sB + (stage * KBLOCKS + kb) * TILE_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / 16; k++)  // +32 B per UMMA_K step inside the swizzle atom
+                umma_bf16(d_tmem, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), (kb | k) != 0);
+            }
+          }
+          umma_commit(&empty[stage]);   // B slot reusable once these MMAs have read it
+          umma_commit(&tfull[tstage]);  // accumulators ready
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++tstage == TSTAGES) { tstage = 0; tphase ^= 1; }
+        }
+        umma_commit(a_empty);           // A tile reusable
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..9; TMEM lane group = warp % 4, query half = (warp - 2) / 4 =====
+    const int lg = warp & 3, half = (warp - 2) >> 2;
+    uint32_t tstage = 0, tphase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qb = item / n_chunks, ch = item - qb * n_chunks;
+      const int tile0 = ch * tiles_per_chunk, tile1 = min(total_tiles, tile0 + tiles_per_chunk);
+      const int q = qb * BM + half * 128 + lg * 32 + lane;
+      const bool qvalid = q < nq;
+      Pass1Acc a1; Pass2Acc a2; a1.init(); a2.init();
+      float thr_rel = 0.f; int idx0 = -1;
+      if (PASS == 2 && qvalid) { thr_rel = st.thr_rel[q]; idx0 = st.idx0[q]; }
+      for (int tile = tile0; tile < tile1; tile++) {
+        mbar_wait(&tfull[tstage], tphase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + tstage * 256 + half * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          const int col0 = tile * BN + c0;
+          float tnv[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = __ldg((const float4*)(tn + col0 + j));
+            tnv[j] = t4.x; tnv[j + 1] = t4.y; tnv[j + 2] = t4.z; tnv[j + 3] = t4.w;
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float v = __fmaf_rn(-2.f, __uint_as_float(r[j]), tnv[j]);
+            if (PASS == 1) a1.add(v, col0 + j); else a2.add(v, col0 + j, thr_rel, idx0, txy, contr2);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[tstage]);
+        if (++tstage == TSTAGES) { tstage = 0; tphase ^= 1; }
+      }
+      if (qvalid) {
+        if (PASS == 1) merge_pass1(st, q, qn[q], a1); else merge_pass2(st, q, qn[q], a2);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: one row per accepted query, in query order (stable compaction done by the caller)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_finalize(NNState st, int nq, int nt, int nn, MatchRow* __restrict__ rows, int* __restrict__ accept) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int k = nn < nt ? nn : nt;
+  const unsigned long long kp = st.bestP[i], k1 = st.best1[i];
+  const int cnt = st.cnt[i];  // failers incl. the NN itself == rank of the first passer
+  const bool ok = (st.incons[i] == 0) && (kp != KEY_INIT) && (cnt >= 1) && (cnt <= k - 1);
+  accept[i] = ok ? 1 : 0;
+  MatchRow r;
+  r.q = i; r.idx0 = st.idx0[i]; r.d0 = st.d0[i];
+  r.idxJ = (int)(unsigned)kp; r.dJ = __uint_as_float((unsigned)(kp >> 32));
+  const unsigned long long second = cnt > 1 ? k1 : kp;   // indices[1], dists[1]
+  r.idx1 = (int)(unsigned)second; r.d1 = __uint_as_float((unsigned)(second >> 32));
+  r.pad = 0;
+  rows[i] = r;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap(mb2_ctx* ctx, CUtensorMap* m, const void* base, int rows) {
+  if (!ctx->tmap_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return MB2_ERR_CUDA; }
+    ctx->tmap_encode = fn;
+  }
+  cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128 * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((PFN_encodeTiled)ctx->tmap_encode)(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return MB2_ERR_CUDA; }
+  return MB2_OK;
+}
+
+}  // namespace
+using namespace MB2_NS;
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+void mb2_nn_prepare(mb2_ctx* ctx, const uint8_t* d_desc, int n, int n_pad, void* d_bf16, float* d_norms, float pad_norm) {
+  MB2_LAUNCH(ctx, k_prepare, (n_pad + 3) / 4, 128, 0, d_desc, n, n_pad, (__nv_bfloat16*)d_bf16, d_norms, pad_norm);
+}
+void mb2_nn_init_state(mb2_ctx* ctx, const NNState& st, int nq) {
+  MB2_LAUNCH(ctx, k_init_state, (nq + 255) / 256, 256, 0, st, nq);
+}
+void mb2_nn_threshold(mb2_ctx* ctx, const NNState& st, int nq, const float* qn, double sqminratio) {
+  MB2_LAUNCH(ctx, k_threshold, (nq + 255) / 256, 256, 0, st, nq, qn, sqminratio);
+}
+void mb2_nn_finalize(mb2_ctx* ctx, const NNState& st, int nq, int nt, int nn, MatchRow* rows, int* accept) {
+  MB2_LAUNCH(ctx, k_finalize, (nq + 255) / 256, 256, 0, st, nq, nt, nn, rows, accept);
+}
+void mb2_nn_pass_simt(mb2_ctx* ctx, int pass, const uint8_t* q, int nq, const uint8_t* t, int nt, const float* qn, const float* tn,
+                      const NNState& st, const double* txy, double contr2) {
+  const int chunk = 4096;
+  dim3 grid((nq + 127) / 128, (nt + chunk - 1) / chunk);
+  if (pass == 1) MB2_LAUNCH(ctx, k_nn_simt<1>, grid, 128, 0, q, nq, t, nt, qn, tn, st, txy, contr2, chunk);
+  else MB2_LAUNCH(ctx, k_nn_simt<2>, grid, 128, 0, q, nq, t, nt, qn, tn, st, txy, contr2, chunk);
+}
+int mb2_nn_pass_tc(mb2_ctx* ctx, int pass, const void* q_bf16, int nq, int nq_pad, const void* t_bf16, int nt_pad, const float* qn,
+                   const float* tn, const NNState& st, const double* txy, double contr2) {
+  CUtensorMap mq, mt;
+  int rc = make_tmap(ctx, &mq, q_bf16, nq_pad);
+  if (rc) return rc;
+  rc = make_tmap(ctx, &mt, t_bf16, nt_pad);
+  if (rc) return rc;
+  const int n_qblocks = nq_pad / BM, total_tiles = nt_pad / BN;
+  // aim for ~8 work items per SM so the persistent CTAs stay balanced
+  int n_chunks = (8 * ctx->num_sms + n_qblocks - 1) / n_qblocks;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > total_tiles) n_chunks = total_tiles;
+  const int tiles_per_chunk = (total_tiles + n_chunks - 1) / n_chunks;
+  n_chunks = (total_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+  const int n_items = n_qblocks * n_chunks;
+  const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_nn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_nn_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr = true;
+  }
+  if (pass == 1)
+    MB2_LAUNCH(ctx, k_nn_tc<1>, grid, NN_THREADS, SMEM_BYTES, mq, mt, nq, nt_pad, qn, tn, st, txy, contr2, tiles_per_chunk, n_qblocks,
+               n_chunks);
+  else
+    MB2_LAUNCH(ctx, k_nn_tc<2>, grid, NN_THREADS, SMEM_BYTES, mq, mt, nq, nt_pad, qn, tn, st, txy, contr2, tiles_per_chunk, n_qblocks,
+               n_chunks);
+  return MB2_OK;
+}

@@ -1,0 +1,377 @@
+// Scale-space pyramid for the Hessian-Affine detector: separable Gaussian blur fused with the
+// Hessian response, 2x2 decimation, 3x3x3 non-maximum suppression, sub-pixel localisation and the
+// per-octave "first come" de-duplication.
+//
+// Reference: detectors/affinedetectors/pyramid.cpp (detectPyramidKeypoints :540-573,
+// detectOctaveKeypoints :455-538, HessianResponse :223-281, findLevelKeypoints :432-452,
+// localizeKeypoint :308-430), detectors/helpers.cpp (gaussianBlur :717-731, solveLinear3x3
+// :309-368).  The OpenCV 2.4.9 GaussianBlur / resize arithmetic is the definition restated in
+// oracle/cvmath.h (row pass left-to-right, column pass symmetric pairs, no FMA).
+//
+// All planes are f32 with a row pitch that is a multiple of 32 floats (128 B).
+#include "common.cuh"
+#undef MB2_NS
+#define MB2_NS mb2_pyramid_detail
+#include "pyramid.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Blur (+ optional Hessian response of the blurred image) -- one pass over HBM per level:
+// reads the source level once (halo re-reads are L2 hits), writes blur and response.
+// Tile = 64 x 32 output pixels per CTA of 256 threads; halo = taps/2 (+1 for the 3x3 Hessian).
+// ---------------------------------------------------------------------------------------------
+namespace MB2_NS {
+
+constexpr int TW = 64, TH = 32, BLUR_THREADS = 256;
+
+template <int NT>  // number of taps (odd)
+__global__ void __launch_bounds__(BLUR_THREADS)
+k_blur_hess(ImgView src, float* __restrict__ dst_blur, float* __restrict__ dst_resp, int dst_pitch, BlurTaps taps,
+            float norm2, int want_resp) {
+  constexpr int H = NT / 2;
+  constexpr int IN_W = TW + 2 * H + 2, IN_H = TH + 2 * H + 2;   // source tile incl. halo
+  constexpr int RP_W = TW + 2;                                   // row-pass result: IN_H x RP_W
+  constexpr int CP_W = TW + 2, CP_H = TH + 2;                    // col-pass result
+  extern __shared__ float smem[];
+  float* s_in = smem;                        // IN_H * IN_W
+  float* s_rp = s_in + IN_H * IN_W;          // IN_H * RP_W
+  float* s_cp = s_rp + IN_H * RP_W;          // CP_H * CP_W
+
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  // 1. load with clamped (replicated) coordinates
+  for (int i = tid; i < IN_H * IN_W; i += BLUR_THREADS) {
+    int ly = i / IN_W, lx = i - ly * IN_W;
+    int gy = min(max(y0 + ly - H - 1, 0), src.rows - 1);
+    int gx = min(max(x0 + lx - H - 1, 0), src.cols - 1);
+    s_in[i] = src.at(gy, gx);
+  }
+  __syncthreads();
+  // 2. row pass: out(ly, lx) for lx in [0, RP_W) is centred on source column lx + H
+  for (int i = tid; i < IN_H * RP_W; i += BLUR_THREADS) {
+    int ly = i / RP_W, lx = i - ly * RP_W;
+    const float* p = s_in + ly * IN_W + lx;
+    float acc = fmul(taps.k[0], p[0]);
+#pragma unroll
+    for (int j = 1; j < NT; j++) acc = fadd(acc, fmul(taps.k[j], p[j]));
+    s_rp[i] = acc;
+  }
+  __syncthreads();
+  // 3. column pass (symmetric pairs): out(ly, lx) for ly in [0, CP_H) centred on row ly + H
+  for (int i = tid; i < CP_H * CP_W; i += BLUR_THREADS) {
+    int ly = i / CP_W, lx = i - ly * CP_W;
+    const float* p = s_rp + (ly + H) * RP_W + lx;
+    float acc = fmul(taps.k[H], p[0]);
+#pragma unroll
+    for (int j = 1; j <= H; j++) acc = fadd(acc, fmul(taps.k[H + j], fadd(p[j * RP_W], p[-j * RP_W])));
+    s_cp[i] = acc;
+  }
+  __syncthreads();
+  // 4. write blur + Hessian response (pyramid.cpp:223-281; 1-px frame of the response is left 0)
+  for (int i = tid; i < TH * TW; i += BLUR_THREADS) {
+    int ly = i / TW, lx = i - ly * TW;
+    int gy = y0 + ly, gx = x0 + lx;
+    if (gy >= src.rows || gx >= src.cols) continue;
+    const float* c = s_cp + (ly + 1) * CP_W + (lx + 1);
+    dst_blur[(size_t)gy * dst_pitch + gx] = c[0];
+    if (want_resp) {
+      float r = 0.f;
+      if (gy >= 1 && gy < src.rows - 1 && gx >= 1 && gx < src.cols - 1) {
+        const float v11 = c[-CP_W - 1], v12 = c[-CP_W], v13 = c[-CP_W + 1];
+        const float v21 = c[-1], v22 = c[0], v23 = c[1];
+        const float v31 = c[CP_W - 1], v32 = c[CP_W], v33 = c[CP_W + 1];
+        const float Lxx = fadd(fsub(v21, fmul(2.f, v22)), v23);
+        const float Lyy = fadd(fsub(v12, fmul(2.f, v22)), v32);
+        const float Lxy = fdiv(fsub(fadd(fsub(v13, v11), v31), v33), 4.0f);
+        r = fmul(fsub(fmul(Lxx, Lyy), fmul(Lxy, Lxy)), norm2);
+      }
+      dst_resp[(size_t)gy * dst_pitch + gx] = r;
+    }
+  }
+}
+
+// Hessian response of an existing level (first level of every octave after the 0th).
+__global__ void k_hessian(ImgView src, float* __restrict__ dst, int dst_pitch, float norm2) {
+  int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (gx >= src.cols || gy >= src.rows) return;
+  float r = 0.f;
+  if (gy >= 1 && gy < src.rows - 1 && gx >= 1 && gx < src.cols - 1) {
+    const float v11 = src.at(gy - 1, gx - 1), v12 = src.at(gy - 1, gx), v13 = src.at(gy - 1, gx + 1);
+    const float v21 = src.at(gy, gx - 1), v22 = src.at(gy, gx), v23 = src.at(gy, gx + 1);
+    const float v31 = src.at(gy + 1, gx - 1), v32 = src.at(gy + 1, gx), v33 = src.at(gy + 1, gx + 1);
+    const float Lxx = fadd(fsub(v21, fmul(2.f, v22)), v23);
+    const float Lyy = fadd(fsub(v12, fmul(2.f, v22)), v32);
+    const float Lxy = fdiv(fsub(fadd(fsub(v13, v11), v31), v33), 4.0f);
+    r = fmul(fsub(fmul(Lxx, Lyy), fmul(Lxy, Lxy)), norm2);
+  }
+  dst[(size_t)gy * dst_pitch + gx] = r;
+}
+
+// cv::resize(x0.5, INTER_LINEAR) == fast INTER_AREA 2x2 mean (oracle/cvmath.h resize_half).
+__global__ void k_resize_half(ImgView src, float* __restrict__ dst, int orows, int ocols, int dst_pitch) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= ocols || r >= orows) return;
+  int r0 = 2 * r, c0 = 2 * c;
+  float v;
+  if (r0 + 1 < src.rows && c0 + 1 < src.cols) {
+    float sum = 0.f;
+    sum = fadd(sum, src.at(r0, c0)); sum = fadd(sum, src.at(r0, c0 + 1));
+    sum = fadd(sum, src.at(r0 + 1, c0)); sum = fadd(sum, src.at(r0 + 1, c0 + 1));
+    v = fmul(sum, 0.25f);
+  } else {
+    float sum = 0.f; int count = 0;
+    for (int sy = 0; sy < 2; sy++) {
+      if (r0 + sy >= src.rows) break;
+      for (int sx = 0; sx < 2; sx++) {
+        if (c0 + sx >= src.cols) break;
+        sum = fadd(sum, src.at(r0 + sy, c0 + sx)); count++;
+      }
+    }
+    v = fdiv(sum, (float)count);
+  }
+  dst[(size_t)r * dst_pitch + c] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3x3 extrema (pyramid.cpp:42-64, 432-452).  Non-strict: ties pass.  Candidates are appended
+// unordered; `key` = level * rows*cols + r*cols + c restores the reference's processing order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_max9(const ImgView& im, float val, int r, int c) {
+#pragma unroll
+  for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+    for (int dc = -1; dc <= 1; dc++)
+      if (im.at(r + dr, c + dc) > val) return false;
+  return true;
+}
+__device__ __forceinline__ bool is_min9(const ImgView& im, float val, int r, int c) {
+#pragma unroll
+  for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+    for (int dc = -1; dc <= 1; dc++)
+      if (im.at(r + dr, c + dc) < val) return false;
+  return true;
+}
+
+__global__ void k_nms(ImgView low, ImgView cur, ImgView high, int border, float posThr, float negThr, int level,
+                      Candidate* __restrict__ out, int* __restrict__ count, int capacity) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x + border, r = blockIdx.y * blockDim.y + threadIdx.y + border;
+  bool hit = false;
+  if (r < cur.rows - border && c < cur.cols - border) {
+    const float val = cur.at(r, c);
+    if (val > posThr) hit = is_max9(cur, val, r, c) && is_max9(low, val, r, c) && is_max9(high, val, r, c);
+    else if (val < negThr) hit = is_min9(cur, val, r, c) && is_min9(low, val, r, c) && is_min9(high, val, r, c);
+  }
+  // warp-aggregated append
+  unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (m) {
+    int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+    int leader = __ffs(m) - 1, base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit) {
+      int slot = base + __popc(m & ((1u << lane) - 1));
+      if (slot < capacity) out[slot] = Candidate{r, c, level, 0};
+    }
+  }
+}
+
+// helpers.cpp:309-368
+__device__ __forceinline__ void swapf(float& a, float& b) { float t = a; a = b; b = t; }
+__device__ void solveLinear3x3_dev(float* A, float* b) {
+  int i = 0, pr = 0;
+  float vp = fabsf(A[0]);
+  float tmp = fabsf(A[3]);
+  if (tmp > vp) { pr = 3; i = 1; vp = tmp; }
+  if (fabsf(A[6]) > vp) { pr = 6; i = 2; }
+  if (pr != 0) { swapf(A[pr], A[0]); swapf(A[pr + 1], A[1]); swapf(A[pr + 2], A[2]); swapf(b[i], b[0]); }
+  vp = fdiv(A[3], A[0]);
+  A[4] = fsub(A[4], fmul(vp, A[1])); A[5] = fsub(A[5], fmul(vp, A[2])); b[1] = fsub(b[1], fmul(vp, b[0]));
+  vp = fdiv(A[6], A[0]);
+  A[7] = fsub(A[7], fmul(vp, A[1])); A[8] = fsub(A[8], fmul(vp, A[2])); b[2] = fsub(b[2], fmul(vp, b[0]));
+  if (fabsf(A[4]) < fabsf(A[7])) { swapf(A[7], A[4]); swapf(A[8], A[5]); swapf(b[2], b[1]); }
+  vp = fdiv(A[7], A[4]);
+  A[8] = fsub(A[8], fmul(vp, A[5])); b[2] = fsub(b[2], fmul(vp, b[1]));
+  b[2] = fdiv(b[2], A[8]);
+  b[1] = fdiv(fsub(b[1], fmul(A[5], b[2])), A[4]);
+  b[0] = fdiv(fsub(fsub(b[0], fmul(A[2], b[2])), fmul(A[1], b[1])), A[0]);
+}
+
+// localizeKeypoint (pyramid.cpp:308-430) up to, not including, the octaveMap test.  Survivors
+// claim their final cell with atomicMin(key): the earliest candidate in the reference's processing
+// order (level, then raster) wins, exactly what the sequential octaveMap does.
+__global__ void k_localize(OctaveLevels oct, Candidate* __restrict__ cand, int n, LocalizeParams lp,
+                           unsigned long long* __restrict__ octmap, Localized* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Candidate cd = cand[i];
+  const ImgView low = oct.resp[cd.level - 1], cur = oct.resp[cd.level], high = oct.resp[cd.level + 1];
+  const int cols = cur.cols, rows = cur.rows;
+  int r = cd.r, c = cd.c, nr = r, nc = c;
+  float b[3] = {0.f, 0.f, 0.f};
+  float val = 0.f;
+  Localized L;
+  L.valid = 0;
+  L.key = (unsigned long long)cd.level * (unsigned long long)(rows * cols) + (unsigned long long)(cd.r * cols + cd.c);
+  bool ok = true;
+  for (int iter = 0; iter < 5 && ok; iter++) {
+    r = nr; c = nc;
+    const float c00 = cur.at(r - 1, c - 1), c01 = cur.at(r - 1, c), c02 = cur.at(r - 1, c + 1);
+    const float c10 = cur.at(r, c - 1), c11 = cur.at(r, c), c12 = cur.at(r, c + 1);
+    const float c20 = cur.at(r + 1, c - 1), c21 = cur.at(r + 1, c), c22 = cur.at(r + 1, c + 1);
+    const float l01 = low.at(r - 1, c), l10 = low.at(r, c - 1), l11 = low.at(r, c), l12 = low.at(r, c + 1), l21 = low.at(r + 1, c);
+    const float h01 = high.at(r - 1, c), h10 = high.at(r, c - 1), h11 = high.at(r, c), h12 = high.at(r, c + 1), h21 = high.at(r + 1, c);
+    float dxx = fadd(fsub(c10, fmul(2.0f, c11)), c12);
+    float dyy = fadd(fsub(c01, fmul(2.0f, c11)), c21);
+    float dss = fadd(fsub(l11, fmul(2.0f, c11)), h11);
+    float dxy = fmul(0.25f, fadd(fsub(fsub(c22, c20), c02), c00));
+    if (iter == 0) {
+      float s = fadd(dxx, dyy);
+      float edgeScore = fdiv(fmul(s, s), fsub(fmul(dxx, dyy), fmul(dxy, dxy)));
+      if ((double)edgeScore >= lp.edgeScoreThreshold || edgeScore < 0) { ok = false; break; }
+    }
+    float dxs = fmul(0.25f, fadd(fsub(fsub(h12, h10), l12), l10));
+    float dys = fmul(0.25f, fadd(fsub(fsub(h21, h01), l21), l01));
+    float A[9] = {dxx, dxy, dxs, dxy, dyy, dys, dxs, dys, dss};
+    float dx = fmul(0.5f, fsub(c12, c10));
+    float dy = fmul(0.5f, fsub(c21, c01));
+    float ds = fmul(0.5f, fsub(h11, l11));
+    b[0] = -dx; b[1] = -dy; b[2] = -ds;
+    solveLinear3x3_dev(A, b);
+    if (isnan(b[0]) || isnan(b[1]) || isnan(b[2])) { ok = false; break; }
+    val = fadd(c11, fmul(0.5f, fadd(fadd(fmul(dx, b[0]), fmul(dy, b[1])), fmul(ds, b[2]))));
+    // MAX_SUBPIXEL_SHIFT is the double literal 0.6; POINT_SAFETY_BORDER = 3
+    if ((double)b[0] > 0.6) { if (c < cols - 3) nc++; else { ok = false; break; } }
+    if ((double)b[1] > 0.6) { if (r < rows - 3) nr++; else { ok = false; break; } }
+    if ((double)b[0] < -0.6) { if (c > 3) nc--; else { ok = false; break; } }
+    if ((double)b[1] < -0.6) { if (r > 3) nr--; else { ok = false; break; } }
+    if (nr == r && nc == c) break;
+  }
+  if (ok) {
+    if (fabs((double)b[0]) > 1.5 || fabs((double)b[1]) > 1.5 || fabs((double)b[2]) > 1.5 || fabsf(val) < lp.finalThreshold) ok = false;
+  }
+  if (ok) {
+    L.valid = 1; L.r = r; L.c = c; L.level = cd.level;
+    L.b0 = b[0]; L.b1 = b[1]; L.b2 = b[2]; L.val = val;
+    atomicMin(&octmap[(size_t)r * cols + c], L.key);
+  }
+  out[i] = L;
+}
+
+// Winners of the octaveMap race become keypoints (pyramid.cpp:420-429): scale, blob type, and the
+// arguments of onKeypointDetected (x, y, s in pixels of the original view).
+__global__ void k_emit_keypoints(OctaveLevels oct, const Localized* __restrict__ loc, int n,
+                                 const unsigned long long* __restrict__ octmap, LocalizeParams lp, int octave,
+                                 KeypointRec* __restrict__ out, int* __restrict__ count, int capacity) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Localized L = loc[i];
+  if (!L.valid) return;
+  const int cols = oct.resp[0].cols;
+  if (octmap[(size_t)L.r * cols + L.c] != L.key) return;
+  // curScale * pow(2.0f, b[2] / numberOfScales): glibc powf is correctly rounded in all but
+  // ~1e-8 of cases; exp2 in double rounded once to float is the same function of the input.
+  const float e = fdiv(L.b2, (float)lp.numberOfScales);
+  const float p2 = (float)exp2((double)e);
+  const float scale = fmul(lp.levelSigma[L.level], p2);
+  int type;
+  if (L.val < 0) type = 2;
+  else {
+    const ImgView blur = oct.blur[L.level];
+    const float Lxx = fadd(fsub(blur.at(L.r, L.c - 1), fmul(2.f, blur.at(L.r, L.c))), blur.at(L.r, L.c + 1));
+    type = (Lxx < 0) ? 0 : 1;
+  }
+  int slot = atomicAdd(count, 1);
+  if (slot >= capacity) return;
+  KeypointRec k;
+  const float pd = lp.pixelDistance;
+  k.x = fmul(pd, fadd((float)L.c, L.b0));
+  k.y = fmul(pd, fadd((float)L.r, L.b1));
+  k.s = fmul(pd, scale);
+  k.pixelDistance = pd;
+  k.response = L.val;
+  k.type = type;
+  k.octave = octave;
+  k.level = L.level;
+  k.order = ((unsigned long long)octave << 56) | L.key;
+  k.a11 = 1.f; k.a12 = 0.f; k.a21 = 0.f; k.a22 = 1.f;
+  k.ok = 0;
+  out[slot] = k;
+}
+
+__global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+template <int NT>
+void launch_blur_nt(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps,
+                    float norm2, int want_resp) {
+  constexpr int H = NT / 2;
+  constexpr int IN_W = TW + 2 * H + 2, IN_H = TH + 2 * H + 2;
+  size_t smem = sizeof(float) * (IN_H * IN_W + IN_H * (TW + 2) + (TH + 2) * (TW + 2));
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_blur_hess<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  dim3 grid((src.cols + TW - 1) / TW, (src.rows + TH - 1) / TH);
+  MB2_LAUNCH(ctx, k_blur_hess<NT>, grid, BLUR_THREADS, smem, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp);
+}
+
+}  // namespace
+using namespace MB2_NS;
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+int mb2_launch_blur(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps,
+                    float norm2, int want_resp) {
+  switch (taps.n) {
+    case 3: launch_blur_nt<3>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 5: launch_blur_nt<5>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 7: launch_blur_nt<7>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 9: launch_blur_nt<9>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 11: launch_blur_nt<11>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 13: launch_blur_nt<13>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 15: launch_blur_nt<15>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 17: launch_blur_nt<17>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 19: launch_blur_nt<19>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    case 21: launch_blur_nt<21>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp); break;
+    default:
+      ctx->set_error("pyramid blur: unsupported tap count " + std::to_string(taps.n));
+      return MB2_ERR_UNSUPPORTED;
+  }
+  return MB2_OK;
+}
+
+void mb2_launch_hessian(mb2_ctx* ctx, const ImgView& src, float* dst, int dst_pitch, float norm2) {
+  dim3 block(32, 8), grid((src.cols + 31) / 32, (src.rows + 7) / 8);
+  MB2_LAUNCH(ctx, k_hessian, grid, block, 0, src, dst, dst_pitch, norm2);
+}
+
+void mb2_launch_resize_half(mb2_ctx* ctx, const ImgView& src, float* dst, int orows, int ocols, int dst_pitch) {
+  dim3 block(32, 8), grid((ocols + 31) / 32, (orows + 7) / 8);
+  MB2_LAUNCH(ctx, k_resize_half, grid, block, 0, src, dst, orows, ocols, dst_pitch);
+}
+
+void mb2_launch_nms(mb2_ctx* ctx, const ImgView& low, const ImgView& cur, const ImgView& high, int border, float posThr,
+                    float negThr, int level, Candidate* out, int* count, int capacity) {
+  int w = cur.cols - 2 * border, h = cur.rows - 2 * border;
+  if (w <= 0 || h <= 0) return;
+  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  MB2_LAUNCH(ctx, k_nms, grid, block, 0, low, cur, high, border, posThr, negThr, level, out, count, capacity);
+}
+
+void mb2_launch_fill_u64(mb2_ctx* ctx, unsigned long long* p, size_t n, unsigned long long v) {
+  if (!n) return;
+  MB2_LAUNCH(ctx, k_fill_u64, (unsigned)((n + 255) / 256), 256, 0, p, n, v);
+}
+
+void mb2_launch_localize(mb2_ctx* ctx, const OctaveLevels& oct, Candidate* cand, int n, const LocalizeParams& lp,
+                         unsigned long long* octmap, Localized* out) {
+  if (!n) return;
+  MB2_LAUNCH(ctx, k_localize, (n + 127) / 128, 128, 0, oct, cand, n, lp, octmap, out);
+}
+
+void mb2_launch_emit(mb2_ctx* ctx, const OctaveLevels& oct, const Localized* loc, int n, const unsigned long long* octmap,
+                     const LocalizeParams& lp, int octave, KeypointRec* out, int* count, int capacity) {
+  if (!n) return;
+  MB2_LAUNCH(ctx, k_emit_keypoints, (n + 127) / 128, 128, 0, oct, loc, n, octmap, lp, octave, out, count, capacity);
+}

@@ -1,0 +1,78 @@
+// Shared records of the detection kernels (pyramid.cu, affine.cu, orient.cu, describe.cu).
+#pragma once
+#include "common.cuh"
+
+struct BlurTaps { int n; float k[33]; };
+
+struct Candidate { int r, c, level, pad; };
+
+struct Localized {
+  unsigned long long key;  // level*rows*cols + r0*cols + c0 : the reference's processing order inside an octave
+  int valid, r, c, level;
+  float b0, b1, b2, val;
+};
+
+// A localized scale-space point on its way through Baumberg (affine.cu).
+struct KeypointRec {
+  unsigned long long order;  // (octave << 56) | Localized::key  == detection order of the reference
+  float x, y, s, pixelDistance, response;
+  float a11, a12, a21, a22;
+  int type, octave, level, ok;
+};
+
+#define MB2_MAX_LEVELS 8
+struct OctaveLevels {
+  ImgView blur[MB2_MAX_LEVELS];
+  ImgView resp[MB2_MAX_LEVELS];
+  int nlevels;
+};
+
+struct LocalizeParams {
+  double edgeScoreThreshold;
+  float finalThreshold;
+  float pixelDistance;
+  int numberOfScales;
+  float levelSigma[MB2_MAX_LEVELS];
+};
+
+int mb2_launch_blur(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps,
+                    float norm2, int want_resp);
+void mb2_launch_hessian(mb2_ctx* ctx, const ImgView& src, float* dst, int dst_pitch, float norm2);
+void mb2_launch_resize_half(mb2_ctx* ctx, const ImgView& src, float* dst, int orows, int ocols, int dst_pitch);
+void mb2_launch_nms(mb2_ctx* ctx, const ImgView& low, const ImgView& cur, const ImgView& high, int border, float posThr,
+                    float negThr, int level, Candidate* out, int* count, int capacity);
+void mb2_launch_fill_u64(mb2_ctx* ctx, unsigned long long* p, size_t n, unsigned long long v);
+void mb2_launch_localize(mb2_ctx* ctx, const OctaveLevels& oct, Candidate* cand, int n, const LocalizeParams& lp,
+                         unsigned long long* octmap, Localized* out);
+void mb2_launch_emit(mb2_ctx* ctx, const OctaveLevels& oct, const Localized* loc, int n, const unsigned long long* octmap,
+                     const LocalizeParams& lp, int octave, KeypointRec* out, int* count, int capacity);
+
+// affine.cu
+struct AffineParams {
+  int maxIterations, smmWindowSize, doBaumberg;
+  float convergenceThreshold, initialSigma;
+};
+void mb2_launch_affine_shape(mb2_ctx* ctx, const OctaveLevels* d_octaves, int n_octaves, KeypointRec* kps, int n,
+                             const AffineParams& ap, const float* d_smm_mask);
+
+// final keypoint record (doubles) as the C ABI returns it
+struct KeyOut { double v[MB2_KP]; unsigned long long order; int keep; int pad; };
+void mb2_launch_export(mb2_ctx* ctx, const KeypointRec* kps, int n, KeyOut* out, int as_regions);
+
+// orient.cu
+struct OrientParams { double mrSize; int patchSize; int maxAngles; double threshold; };
+void mb2_launch_orientation(mb2_ctx* ctx, const ImgView& img, const KeyOut* in, int n, const OrientParams& op,
+                            const float* d_orimask, KeyOut* out /* n * maxAngles */, int* out_count_per_kp);
+
+// describe.cu
+struct DescribeParams { double mrSize; int patchSize; int photoNorm; int rootSIFT; int fast; };
+struct DescTables {      // precomputed on the host exactly as the reference's constructors do
+  float mask[41 * 41];   // computeCircularGaussMask(41), siftdesc.h:87 / synth-detection.hpp:181
+  int bin0[41], bin1[41];
+  float w0[41], w1[41];  // floats stored in doubles by the reference (siftdesc.cpp:44-45)
+};
+int mb2_launch_describe(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
+                        const DescTables* d_tables, uint8_t* d_desc, float* d_patches /* may be null */);
+// reprojection + boundary filter (synth-detection.cpp:541-616)
+void mb2_launch_reproject(mb2_ctx* ctx, const KeyOut* det, int n, const double* Hinv9, int h_is_eye, int orig_w, int orig_h,
+                          KeyOut* reproj /* keep flag set */);

@@ -1,0 +1,197 @@
+// Batched-hypothesis scorer for DEGENSAC / LO-RANSAC: K models x n correspondences in one launch.
+//
+// Reference scorers (all closed form, f64): HDs (degensac/Htools.c:158-196) with lin_hg (:17-55) and
+// pinvJ (:132-156) fused so the n x 18 `lin` matrix is never built; HDsSym (:199-240), HDsSymMax
+// (:241-282) with ccmath minv (matutls/minv.c) for the 3x3 inverse; FDs / FDsSym
+// (degensac/Ftools.c:82-123); inlier count d <= th and MSAC gain truncQuad (rtools.c:228-236).
+// Built with -fmad=false: residuals are bit-identical to the CPU scorers; the MSAC sum J is a
+// fixed-order tree sum (deterministic, differs from the serial CPU sum only in the last bits).
+#include "common.cuh"
+#undef MB2_NS
+#define MB2_NS mb2_ransac_detail
+#include "ransac.cuh"
+
+// matutls/minv.c for n = 3, restated with indices (column-wise LU with row pivoting, in place).
+__host__ __device__ bool mb2_minv3(double* a) {
+  const int n = 3;
+  int le[3];
+  double q0[3], tq = 0., zr = 1.e-15;
+#define A_(r, c) a[(r) * n + (c)]
+  for (int j = 0; j < n; ++j) {
+    if (j > 0) {
+      for (int i = 0; i < n; ++i) q0[i] = A_(i, j);
+      for (int i = 1; i < n; ++i) {
+        int lc = i < j ? i : j;
+        double t = 0.;
+        for (int k = 0; k < lc; ++k) t += A_(i, k) * q0[k];
+        q0[i] -= t;
+      }
+      for (int i = 0; i < n; ++i) A_(i, j) = q0[i];
+    }
+    double s = fabs(A_(j, j));
+    int lc = j;
+    for (int k = j + 1; k < n; ++k) { double t = fabs(A_(k, j)); if (t > s) { s = t; lc = k; } }
+    tq = tq > s ? tq : s;
+    if (s < zr * tq) return false;
+    le[j] = lc;
+    if (lc != j) for (int k = 0; k < n; ++k) { double t = A_(j, k); A_(j, k) = A_(lc, k); A_(lc, k) = t; }
+    double t = 1. / A_(j, j);
+    for (int k = j + 1; k < n; ++k) A_(k, j) *= t;
+    A_(j, j) = t;
+  }
+  for (int j = 1; j < n; ++j) for (int k = 0; k < j; ++k) A_(k, j) *= A_(j, j);
+  for (int j = 1; j < n; ++j) {
+    for (int i = 0; i < j; ++i) q0[i] = A_(i, j);
+    for (int k = 0; k < j; ++k) { double t = 0.; for (int i = k; i < j; ++i) t -= A_(k, i) * q0[i]; q0[k] = t; }
+    for (int i = 0; i < j; ++i) A_(i, j) = q0[i];
+  }
+  for (int j = n - 2; j >= 0; --j) {
+    int m = n - j - 1;
+    for (int i = 0; i < m; ++i) q0[i] = A_(j + 1 + i, j);
+    for (int k = n - 1; k > j; --k) {
+      double t = -A_(k, j);
+      for (int i = j + 1, q = 0; i < k; ++i, ++q) t -= A_(k, i) * q0[q];
+      q0[--m] = t;
+    }
+    m = n - j - 1;
+    for (int i = 0; i < m; ++i) A_(j + 1 + i, j) = q0[i];
+  }
+  for (int k = 0; k < n - 1; ++k) {
+    for (int i = 0; i < n; ++i) q0[i] = A_(i, k);
+    for (int j = 0; j < n; ++j) {
+      double t; int i;
+      if (j > k) { t = 0.; i = j; } else { t = q0[j]; i = k + 1; }
+      for (; i < n; ++i) t += A_(j, i) * q0[i];
+      q0[j] = t;
+    }
+    for (int i = 0; i < n; ++i) A_(i, k) = q0[i];
+  }
+  for (int j = n - 2; j >= 0; --j)
+    for (int k = 0; k < n; ++k) { double t = A_(k, j); A_(k, j) = A_(k, le[j]); A_(k, le[j]) = t; }
+#undef A_
+  return true;
+}
+
+namespace MB2_NS {
+
+__device__ __forceinline__ double score_HDs(const double* u, const double* H) {
+  const double x1 = u[0], y1 = u[1];
+  const double z1[9] = {u[3], 0, -x1 * u[3], u[4], 0, -x1 * u[4], u[5], 0, -x1 * u[5]};
+  const double z2[9] = {0, u[3], -y1 * u[3], 0, u[4], -y1 * u[4], 0, u[5], -y1 * u[5]};
+  double r1 = 0, r2 = 0;
+#pragma unroll
+  for (int j = 0; j < 9; j++) { r1 += H[j] * z1[j]; r2 += H[j] * z2[j]; }
+  const double a = H[0] - H[2] * u[0];
+  const double b = H[3] - H[5] * u[0];
+  const double c = -H[8] - H[2] * u[3] - H[5] * u[4];
+  const double d = H[1] - H[2] * u[1];
+  const double e = H[4] - H[5] * u[1];
+  double pJ[8];
+  const double a2 = a * a, b2 = b * b, c2 = c * c, d2 = d * d, e2 = e * e;
+  const double c2pd2 = c2 + d2, ab = a * b, de = d * e;
+  const double Q = c * (c2pd2 + e2);
+  pJ[0] = -b * de + a * (c2 + e2);
+  pJ[1] = b * c2pd2 - a * de;
+  pJ[2] = Q;
+  pJ[3] = -c * (a * d + b * e);
+  pJ[4] = d * (b2 + c2) - ab * e;
+  pJ[5] = -ab * d + e * (a2 + c2);
+  pJ[6] = pJ[3];
+  pJ[7] = c * (a2 + b2 + c2);
+  const double N = a * pJ[0] + b * pJ[1] + c * pJ[2];
+#pragma unroll
+  for (int q = 0; q < 8; q++) pJ[q] /= N;
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) { const double v = pJ[j] * r1 + pJ[j + 4] * r2; s += v * v; }
+  return s;
+}
+
+__device__ __forceinline__ double score_HDsSym(const double* u, const double* Hinv, const double* H1, bool useMax) {
+  const double a = H1[6] * u[0] + H1[7] * u[1] + H1[8];
+  const double b = Hinv[6] * u[3] + Hinv[7] * u[4] + Hinv[8];
+  double xa = (H1[0] * u[0] + H1[1] * u[1] + H1[2]) / a;
+  double ya = (H1[3] * u[0] + H1[4] * u[1] + H1[5]) / a;
+  double xdiff = u[3] - xa, ydiff = u[4] - ya;
+  const double d1 = xdiff * xdiff + ydiff * ydiff;
+  xa = (Hinv[0] * u[3] + Hinv[1] * u[4] + Hinv[2]) / b;
+  ya = (Hinv[3] * u[3] + Hinv[4] * u[4] + Hinv[5]) / b;
+  xdiff = u[0] - xa; ydiff = u[1] - ya;
+  const double d2 = xdiff * xdiff + ydiff * ydiff;
+  return useMax ? (d1 < d2 ? d2 : d1) : d1 + d2;
+}
+
+__device__ __forceinline__ double score_FDs(const double* u, const double* F, bool sym) {
+  const double u1 = u[0], u2 = u[1], u4 = u[3], u5 = u[4];
+  const double rxc = F[0] * u4 + F[3] * u5 + F[6];
+  const double ryc = F[1] * u4 + F[4] * u5 + F[7];
+  const double rwc = F[2] * u4 + F[5] * u5 + F[8];
+  const double r = (u1 * rxc + u2 * ryc + rwc);
+  const double rx = F[0] * u1 + F[1] * u2 + F[2];
+  const double ry = F[3] * u1 + F[4] * u2 + F[5];
+  if (!sym) return r * r / (rxc * rxc + ryc * ryc + rx * rx + ry * ry);
+  const double a = rxc * rxc + ryc * ryc, b = rx * rx + ry * ry;
+  return r * r * (a + b) / (a * b);
+}
+
+// rtools.c:228-236
+__device__ __forceinline__ double truncQuad_dev(double epsilon, double thr) {
+  if (thr == 0) return 0;
+  if (epsilon >= thr * 9 / 4) return 0;
+  return 1 - (epsilon / (thr * 9 / 4));
+}
+
+constexpr int ST = 256;
+
+// grid = (K models); each CTA walks all n correspondences (coalesced on the 6-double records).
+__global__ void __launch_bounds__(ST)
+k_score(int which, const double* __restrict__ u, int len, const double* __restrict__ models, double th,
+        double* __restrict__ resid, int* __restrict__ I_out, double* __restrict__ J_out) {
+  __shared__ double sM[9], sHinv[9], sH1[9];
+  __shared__ double sJ[ST];
+  __shared__ int sI[ST];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  if (tid < 9) sM[tid] = models[(size_t)k * 9 + tid];
+  __syncthreads();
+  if (tid == 0 && (which == 1 || which == 2)) {
+    const double t[9] = {sM[0], sM[3], sM[6], sM[1], sM[4], sM[7], sM[2], sM[5], sM[8]};
+    double inv[9];
+    for (int i = 0; i < 9; i++) { sHinv[i] = t[i]; inv[i] = t[i]; }
+    mb2_minv3(inv);
+    for (int i = 0; i < 9; i++) sH1[i] = inv[i];
+  }
+  __syncthreads();
+  double J = 0; int I = 0;
+  for (int i = tid; i < len; i += ST) {
+    double p[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) p[j] = u[(size_t)i * 6 + j];
+    double d;
+    switch (which) {
+      case 0: d = score_HDs(p, sM); break;
+      case 1: d = score_HDsSym(p, sHinv, sH1, false); break;
+      case 2: d = score_HDsSym(p, sHinv, sH1, true); break;
+      case 3: d = score_FDs(p, sM, false); break;
+      default: d = score_FDs(p, sM, true); break;
+    }
+    if (resid) resid[(size_t)k * len + i] = d;
+    if (d <= th) I++;
+    J += truncQuad_dev(d, th);
+  }
+  sJ[tid] = J; sI[tid] = I;
+  __syncthreads();
+  for (int s = ST / 2; s > 0; s >>= 1) {
+    if (tid < s) { sJ[tid] += sJ[tid + s]; sI[tid] += sI[tid + s]; }
+    __syncthreads();
+  }
+  if (tid == 0) { if (I_out) I_out[k] = sI[0]; if (J_out) J_out[k] = sJ[0]; }
+}
+
+}  // namespace
+using namespace MB2_NS;
+
+void mb2_launch_score(mb2_ctx* ctx, int which, const double* d_u, int len, const double* d_models, int K, double th, double* d_resid,
+                      int* d_I, double* d_J) {
+  if (K <= 0) return;
+  MB2_LAUNCH(ctx, k_score, K, ST, 0, which, d_u, len, d_models, th, d_resid, d_I, d_J);
+}
