@@ -393,6 +393,32 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
   if (n_kp > kp_cap) { ctx->set_error("hessaff: keypoint list overflow"); return MB2_ERR_CAPACITY; }
   if (n_kp == 0) return MB2_OK;
 
+  // ---- host leg: keypoint scale through the host libm (pyramid.cpp:421) ----------------------------
+  {
+    MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)n_kp * (sizeof(ScaleReq) + 4) + 64));
+    ScaleReq* d_req = ctx->rs_a.as<ScaleReq>();
+    float* d_s = (float*)(d_req + n_kp);
+    MB2_CUDA_CHECK(ctx, ctx->h_a.reserve((size_t)n_kp * sizeof(ScaleReq)));
+    MB2_CUDA_CHECK(ctx, ctx->h_b.reserve((size_t)n_kp * 4));
+    mb2_launch_scale_requests(ctx, d_kp, n_kp, d_req);
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_a.p, d_req, (size_t)n_kp * sizeof(ScaleReq), cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const ScaleReq* req = ctx->h_a.as<ScaleReq>();
+    float* hs = ctx->h_b.as<float>();
+    float lvlSigma[MB2_MAX_LEVELS];
+    { float cs = par.initialSigma; for (int l = 0; l < NL; l++) { lvlSigma[l] = cs; cs *= sigmaStep; } }
+    const int nscales = par.numberOfScales;
+#pragma omp parallel for schedule(static) if (n_kp > 4096)
+    for (int i = 0; i < n_kp; i++) {
+      const float scale = lvlSigma[req[i].level] * std::pow(2.0f, req[i].b2 / nscales);
+      float pd = 1.0f;
+      for (int o = 0; o < req[i].octave; o++) pd *= 2.0f;
+      hs[i] = pd * scale;
+    }
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(d_s, hs, (size_t)n_kp * 4, cudaMemcpyHostToDevice, ctx->stream));
+    mb2_launch_set_scales(ctx, d_kp, n_kp, d_s);
+  }
+
   // ---- Baumberg, export, ordering ---------------------------------------------------------------
   AffineParams ap;
   ap.maxIterations = par.maxIterations; ap.smmWindowSize = par.smmWindowSize; ap.doBaumberg = par.doBaumberg;
@@ -431,12 +457,33 @@ int orient_core(mb2_ctx* ctx, const ImgView& img, int n, const mb2_orientation_p
   if (maxA > 36) { ctx->set_error("orientation: maxAngles > 36"); return MB2_ERR_ARG; }
   const size_t slots = (size_t)n * maxA;
   MB2_CUDA_CHECK(ctx, ctx->kp_a.reserve(slots * sizeof(KeyOut) + (size_t)n * 4 + 64));
+
   KeyOut* d_slots = ctx->kp_a.as<KeyOut>();
   int* d_cnt = (int*)(d_slots + slots);
   OrientParams p{op.mrSize, op.patchSize, maxA, op.threshold};
   mb2_launch_orientation(ctx, img, ctx->kp_b.as<KeyOut>(), n, p, priv(ctx)->t.orimask.as<float>(), d_slots, d_cnt);
   MB2_CUDA_CHECK(ctx, ctx->kp_c.reserve(slots * sizeof(KeyOut)));
-  return compact(ctx, d_slots, nullptr, (int)slots, ctx->kp_c.as<KeyOut>(), nullptr, ctx->misc, n_out);
+  if ((rc = compact(ctx, d_slots, nullptr, (int)slots, ctx->kp_c.as<KeyOut>(), nullptr, ctx->misc, n_out))) return rc;
+  const int m = *n_out;
+  if (m > 0) {
+    // host leg: ci = cos(-angle), si = sin(-angle) in float through the host libm, exactly as
+    // DetectOrientation does (synth-detection.cpp:902-903); the device finishes A <- A R.
+    MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)m * (4 + 16) + 64));
+    float* d_ang = ctx->rs_a.as<float>();
+    double* d_cs = (double*)(((uintptr_t)(d_ang + m) + 15) & ~(uintptr_t)15);
+    MB2_CUDA_CHECK(ctx, ctx->h_a.reserve((size_t)m * 4));
+    MB2_CUDA_CHECK(ctx, ctx->h_b.reserve((size_t)m * 16));
+    mb2_launch_extract_angles(ctx, ctx->kp_c.as<KeyOut>(), m, d_ang);
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_a.p, d_ang, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const float* ang = ctx->h_a.as<float>();
+    double* cs = ctx->h_b.as<double>();
+#pragma omp parallel for schedule(static) if (m > 4096)
+    for (int i = 0; i < m; i++) { cs[2 * i] = std::cos(-ang[i]); cs[2 * i + 1] = std::sin(-ang[i]); }
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cs, cs, (size_t)m * 16, cudaMemcpyHostToDevice, ctx->stream));
+    mb2_launch_apply_rotation(ctx, ctx->kp_c.as<KeyOut>(), d_cs, m);
+  }
+  return MB2_OK;
 }
 
 // describe the n records at d_keys; descriptors -> ctx->desc_u8 (device)

@@ -101,19 +101,38 @@ k_orientation(ImgView img, const KeyOut* __restrict__ in, int n, OrientParams op
       if (h[b] >= thresh && h[b] > h[a] && h[b] > h[c]) {
         const float pp = fdiv(fdiv(fsub(h[a], h[c]), fadd(fsub(h[a], fmul(2.0f, h[b])), h[c])), 2.0f);
         const float ang = fsub(fdiv(fmul(fmul(2.0f, PIf), fadd(fadd((float)b, 0.5f), pp)), 36.f), PIf);
-        const double ci = cos(-(double)ang), si = sin(-(double)ang);
+        // The rotation needs cos(-ang), sin(-ang), which the reference takes from the host libm in
+        // FLOAT (std::cos(float), synth-detection.cpp:902-903); libm's cosf/sinf are not correctly
+        // rounded and differ between libm builds, so the host adapter evaluates them
+        // and k_apply_rotation finishes the frame.
         KeyOut o = k;
-        o.v[2] = k.v[2] * ci - k.v[3] * si;
-        o.v[3] = k.v[2] * si + k.v[3] * ci;
-        o.v[4] = k.v[4] * ci - k.v[5] * si;
-        o.v[5] = k.v[4] * si + k.v[5] * ci;
         o.keep = 1;
         o.order = k.order;  // peak rank is implied by the slot index
+        o.pad = __float_as_int(ang);
         dst[cnt++] = o;
       }
     }
     out_count[kidx] = cnt;
   }
+}
+
+// A <- A * R(-theta) with (ci, si) = (cos(-theta), sin(-theta)) from the host (synth-detection.cpp:902-910)
+__global__ void k_extract_angles(const KeyOut* __restrict__ keys, int n, float* __restrict__ ang) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ang[i] = __int_as_float(keys[i].pad);
+}
+__global__ void k_apply_rotation(KeyOut* __restrict__ keys, const double* __restrict__ cs, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ci = cs[2 * i], si = cs[2 * i + 1];
+  KeyOut k = keys[i];
+  const double a11 = k.v[2], a12 = k.v[3], a21 = k.v[4], a22 = k.v[5];
+  k.v[2] = a11 * ci - a12 * si;
+  k.v[3] = a11 * si + a12 * ci;
+  k.v[4] = a21 * ci - a22 * si;
+  k.v[5] = a21 * si + a22 * ci;
+  k.pad = 0;
+  keys[i] = k;
 }
 
 // ReprojectRegions (synth-detection.cpp:541-616): reproj_kp = Hinv (affine part) applied to centre
@@ -155,6 +174,16 @@ void mb2_launch_orientation(mb2_ctx* ctx, const ImgView& img, const KeyOut* in, 
                             const float* d_orimask, KeyOut* out, int* out_count_per_kp) {
   if (!n) return;
   MB2_LAUNCH(ctx, k_orientation, (n + OW - 1) / OW, OW * 32, 0, img, in, n, op, d_orimask, out, out_count_per_kp);
+}
+
+void mb2_launch_extract_angles(mb2_ctx* ctx, const KeyOut* keys, int n, float* d_ang) {
+  if (!n) return;
+  MB2_LAUNCH(ctx, k_extract_angles, (n + 127) / 128, 128, 0, keys, n, d_ang);
+}
+
+void mb2_launch_apply_rotation(mb2_ctx* ctx, KeyOut* keys, const double* d_cs, int n) {
+  if (!n) return;
+  MB2_LAUNCH(ctx, k_apply_rotation, (n + 127) / 128, 128, 0, keys, d_cs, n);
 }
 
 void mb2_launch_reproject(mb2_ctx* ctx, const KeyOut* det, int n, const double* Hinv9, int h_is_eye, int orig_w, int orig_h,

@@ -268,11 +268,9 @@ __global__ void k_emit_keypoints(OctaveLevels oct, const Localized* __restrict__
   if (!L.valid) return;
   const int cols = oct.resp[0].cols;
   if (octmap[(size_t)L.r * cols + L.c] != L.key) return;
-  // curScale * pow(2.0f, b[2] / numberOfScales): glibc powf is correctly rounded in all but
-  // ~1e-8 of cases; exp2 in double rounded once to float is the same function of the input.
-  const float e = fdiv(L.b2, (float)lp.numberOfScales);
-  const float p2 = (float)exp2((double)e);
-  const float scale = fmul(lp.levelSigma[L.level], p2);
+  // scale = curScale * pow(2.0f, b[2] / numberOfScales) (pyramid.cpp:421) goes through the host libm:
+  // glibc powf is not correctly rounded (and has FMA / non-FMA builds), so the host adapter
+  // evaluates it -- see detect_core; here we only carry b2.
   int type;
   if (L.val < 0) type = 2;
   else {
@@ -286,7 +284,8 @@ __global__ void k_emit_keypoints(OctaveLevels oct, const Localized* __restrict__
   const float pd = lp.pixelDistance;
   k.x = fmul(pd, fadd((float)L.c, L.b0));
   k.y = fmul(pd, fadd((float)L.r, L.b1));
-  k.s = fmul(pd, scale);
+  k.s = 0.f;
+  k.b2 = L.b2;
   k.pixelDistance = pd;
   k.response = L.val;
   k.type = type;
@@ -296,6 +295,15 @@ __global__ void k_emit_keypoints(OctaveLevels oct, const Localized* __restrict__
   k.a11 = 1.f; k.a12 = 0.f; k.a21 = 0.f; k.a22 = 1.f;
   k.ok = 0;
   out[slot] = k;
+}
+
+__global__ void k_scale_requests(const KeypointRec* __restrict__ kps, int n, ScaleReq* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ScaleReq{kps[i].b2, kps[i].level, kps[i].octave};
+}
+__global__ void k_set_scales(KeypointRec* __restrict__ kps, int n, const float* __restrict__ s) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) kps[i].s = s[i];
 }
 
 __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
@@ -357,6 +365,15 @@ void mb2_launch_nms(mb2_ctx* ctx, const ImgView& low, const ImgView& cur, const 
   if (w <= 0 || h <= 0) return;
   dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
   MB2_LAUNCH(ctx, k_nms, grid, block, 0, low, cur, high, border, posThr, negThr, level, out, count, capacity);
+}
+
+void mb2_launch_scale_requests(mb2_ctx* ctx, const KeypointRec* kps, int n, ScaleReq* out) {
+  if (!n) return;
+  MB2_LAUNCH(ctx, k_scale_requests, (n + 255) / 256, 256, 0, kps, n, out);
+}
+void mb2_launch_set_scales(mb2_ctx* ctx, KeypointRec* kps, int n, const float* d_s) {
+  if (!n) return;
+  MB2_LAUNCH(ctx, k_set_scales, (n + 255) / 256, 256, 0, kps, n, d_s);
 }
 
 void mb2_launch_fill_u64(mb2_ctx* ctx, unsigned long long* p, size_t n, unsigned long long v) {

@@ -17,6 +17,7 @@ struct KeypointRec {
   unsigned long long order;  // (octave << 56) | Localized::key  == detection order of the reference
   float x, y, s, pixelDistance, response;
   float a11, a12, a21, a22;
+  float b2;                  // scale offset of the quadratic fit; s is filled in by the host leg (powf)
   int type, octave, level, ok;
 };
 
@@ -47,6 +48,10 @@ void mb2_launch_localize(mb2_ctx* ctx, const OctaveLevels& oct, Candidate* cand,
 void mb2_launch_emit(mb2_ctx* ctx, const OctaveLevels& oct, const Localized* loc, int n, const unsigned long long* octmap,
                      const LocalizeParams& lp, int octave, KeypointRec* out, int* count, int capacity);
 
+struct ScaleReq { float b2; int level; int octave; };
+void mb2_launch_scale_requests(mb2_ctx* ctx, const KeypointRec* kps, int n, ScaleReq* out);
+void mb2_launch_set_scales(mb2_ctx* ctx, KeypointRec* kps, int n, const float* d_s);
+
 // affine.cu
 struct AffineParams {
   int maxIterations, smmWindowSize, doBaumberg;
@@ -62,7 +67,9 @@ void mb2_launch_export(mb2_ctx* ctx, const KeypointRec* kps, int n, KeyOut* out,
 // orient.cu
 struct OrientParams { double mrSize; int patchSize; int maxAngles; double threshold; };
 void mb2_launch_orientation(mb2_ctx* ctx, const ImgView& img, const KeyOut* in, int n, const OrientParams& op,
-                            const float* d_orimask, KeyOut* out /* n * maxAngles */, int* out_count_per_kp);
+                            const float* d_orimask, KeyOut* out /* n * maxAngles; .pad = float bits of the angle */, int* out_count_per_kp);
+void mb2_launch_extract_angles(mb2_ctx* ctx, const KeyOut* keys, int n, float* d_ang);
+void mb2_launch_apply_rotation(mb2_ctx* ctx, KeyOut* keys, const double* d_cs, int n);
 
 // describe.cu
 struct DescribeParams { double mrSize; int patchSize; int photoNorm; int rootSIFT; int fast; };

@@ -183,6 +183,7 @@ class Reference(Lib):
         path = os.path.join(HERE, "_ref", "libmods_ref.so")
         if not os.path.exists(path):
             raise FileNotFoundError(path)
+        _preload_blas_deps()
         super().__init__(path, "ref_")
 
     def exp_ransacH(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1):
@@ -197,6 +198,21 @@ class Reference(Lib):
         u = _f64(u); idx = np.ascontiguousarray(idx, np.int32); H = np.zeros(9)
         self.fn("u2h", None)(_p(u), _p(idx), C.c_int(len(idx)), _p(H))
         return H
+
+
+def _preload_blas_deps():
+    """The reference links LAPACK from the OpenBLAS bundled with opencv-python-headless; that
+    library needs its sibling libgfortran / libquadmath, which are not on the loader path."""
+    import glob
+    import site
+    for sp in site.getsitepackages():
+        d = os.path.join(sp, "opencv_python_headless.libs")
+        for pat in ("libquadmath*.so*", "libgfortran*.so*", "libopenblas*.so*"):
+            for f in sorted(glob.glob(os.path.join(d, pat))):
+                try:
+                    C.CDLL(f, mode=C.RTLD_GLOBAL)
+                except OSError:
+                    pass
 
 
 def have_reference():

@@ -1,0 +1,233 @@
+"""Parity of the CUDA path (through the C ABI, libmods_b200.so) against the CPU oracle and the
+committed reference vectors.  Bit-exact for keypoints, patches, descriptors, tentatives and
+residuals; the MSAC sum J to 1e-9 (fixed-order tree sum vs serial sum)."""
+import os
+
+import numpy as np
+import pytest
+
+import mods_b200 as mb
+import synth
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def img():
+    return synth.blob_image(640, 480, seed=3)
+
+
+# ---- detection ---------------------------------------------------------------------------------
+def test_pyramid_levels_bit_exact(ctx, oracle, img):
+    ctx.hessaff_detect(img, as_regions=False)
+    P = oracle.pyramid(img)
+    assert len(P["levels"]) >= 25
+    for lv in P["levels"]:
+        g, _ = ctx.pyramid_level(lv["octave"], lv["level"], False)
+        r, _ = ctx.pyramid_level(lv["octave"], lv["level"], True)
+        assert np.array_equal(g, lv["blur"]), (lv["octave"], lv["level"])
+        assert np.array_equal(r[1:-1, 1:-1], lv["resp"][1:-1, 1:-1]), (lv["octave"], lv["level"])
+
+
+@pytest.mark.parametrize("as_regions", [False, True])
+def test_hessaff_keys_bit_exact(ctx, oracle, img, as_regions):
+    g = ctx.hessaff_detect(img, as_regions=as_regions)
+    o = oracle.hessaff_detect(img, raw=not as_regions)
+    assert len(o) > 1000 and np.array_equal(g, o)
+
+
+@pytest.mark.parametrize("wh", [(135, 101), (299, 150), (64, 37), (33, 200), (13, 13), (12, 40)])
+def test_hessaff_odd_and_tiny_sizes(ctx, oracle, wh):
+    """cv::resize rounding (135 -> 68, 299 -> 150), ragged tiles, images too small for one octave."""
+    im = synth.blob_image(wh[0], wh[1], seed=wh[0])
+    assert np.array_equal(ctx.hessaff_detect(im), oracle.hessaff_detect(im))
+
+
+def test_hessaff_flat_image_yields_nothing(ctx):
+    assert len(ctx.hessaff_detect(np.full((200, 300), 77.0, np.float32))) == 0
+
+
+def test_hessaff_matches_reference_golden(ctx):
+    im = synth.blob_image(320, 240, seed=int(G["s_seed"]))
+    assert np.array_equal(ctx.hessaff_detect(im, as_regions=False), G["s_raw"])
+    assert np.array_equal(ctx.hessaff_detect(im, as_regions=True), G["s_reg"])
+
+
+def test_hessaff_no_baumberg(ctx, oracle, img):
+    from oracle.pyoracle import HessParams
+    p = mb.HessaffParams.default(); p.doBaumberg = 0
+    po = HessParams.default(); po.doBaumberg = 0
+    assert np.array_equal(ctx.hessaff_detect(img, p), oracle.hessaff_detect(img, po))
+
+
+# ---- orientation -------------------------------------------------------------------------------
+@pytest.mark.parametrize("max_angles", [1, 3, 5])
+def test_orientation_bit_exact(ctx, oracle, img, max_angles):
+    k = oracle.hessaff_detect(img)
+    g = ctx.detect_orientation(img, k, mb.OrientationParams(1.0, 41, max_angles, 0.8))
+    o = oracle.detect_orientation(img, k, maxAngles=max_angles)
+    assert len(o) > 1000 and np.array_equal(g, o)
+
+
+def test_orientation_empty_and_zero_angles(ctx, img):
+    assert len(ctx.detect_orientation(img, np.zeros((0, 9)))) == 0
+    k = np.array([[320.0, 240.0, 1, 0, 0, 1, 3.0, 50.0, 1]])
+    assert len(ctx.detect_orientation(img, k, mb.OrientationParams(1.0, 41, 0, 0.8))) == 0
+
+
+# ---- description -------------------------------------------------------------------------------
+@pytest.mark.parametrize("root", [1, 0])
+def test_describe_bit_exact(ctx, oracle, img, root):
+    k = oracle.detect_orientation(img, oracle.hessaff_detect(img))
+    k = oracle.reproject(k, np.eye(3), img.shape[1], img.shape[0], 0)[0]
+    gd, gp = ctx.describe_sift(img, k, mb.SiftParams(5.1962, 41, 1, root, 0), want_patches=True)
+    od, op = oracle.describe(img, k, rootsift=bool(root), want_patches=True)
+    assert np.array_equal(gp, op)
+    assert np.array_equal(gd.astype(np.float32), od)
+
+
+def test_describe_large_and_tiny_regions(ctx, oracle):
+    """Direct path (P/41 <= 0.4), the 82x82 'needed samples' path up to P ~ 400, no photoNorm, fast extraction."""
+    im = synth.blob_image(900, 700, seed=9)
+    rng = np.random.default_rng(0)
+    ks = []
+    for s in (0.4, 0.9, 1.4, 2.0, 3.7, 8.0, 15.0, 24.0, 38.0):
+        a = rng.uniform(0, np.pi); r = rng.uniform(1.0, 2.0)
+        A = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]) @ np.diag([r, 1 / r])
+        ks.append([450.0 + rng.uniform(-20, 20), 350.0 + rng.uniform(-20, 20), A[0, 0], A[0, 1], A[1, 0], A[1, 1], s, 10.0, 1])
+    ks.append([5.0, 6.0, 1, 0, 0, 1, 4.0, 10.0, 0])        # sticks out of the image: zero-filled samples
+    k = np.array(ks)
+    for par, kw in ((mb.SiftParams(5.1962, 41, 1, 1, 0), dict(rootsift=True)),
+                    (mb.SiftParams(5.1962, 41, 0, 0, 0), dict(rootsift=False, photoNorm=False)),
+                    (mb.SiftParams(5.1962, 41, 1, 1, 1), dict(rootsift=True, fast=True))):
+        gd, gp = ctx.describe_sift(im, k, par, want_patches=True)
+        od, op = oracle.describe(im, k, want_patches=True, **kw)
+        assert np.array_equal(gp, op)
+        assert np.array_equal(gd.astype(np.float32), od)
+
+
+# ---- one view end to end -----------------------------------------------------------------------
+def test_view_pipeline_bit_exact(ctx, oracle, img):
+    g = ctx.detect_describe_view(img)
+    o = oracle.view_pipeline(img)
+    assert len(o[0]) > 1000
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1])
+    assert np.array_equal(g[2].astype(np.float32), o[2])
+
+
+def test_view_pipeline_matches_reference_golden(ctx):
+    im = synth.blob_image(320, 240, seed=int(G["s_seed"]))
+    det, rep, desc = ctx.detect_describe_view(im)
+    assert np.array_equal(det, G["s_det"]) and np.array_equal(rep, G["s_rep"]) and np.array_equal(desc, G["s_desc"])
+    if "cat_gray" in G:
+        det, rep, desc = ctx.detect_describe_view(G["cat_gray"])
+        assert np.array_equal(det, G["cat_det"]) and np.array_equal(rep, G["cat_rep"]) and np.array_equal(desc, G["cat_desc"])
+
+
+def test_view_pipeline_is_deterministic_at_scale(ctx):
+    """1920x1080 (BASELINE config 2 size): run twice, identical; descriptors are valid RootSIFT."""
+    im = synth.blob_image(1920, 1080, seed=5, n_blobs=6000)
+    a = ctx.detect_describe_view(im)
+    b = ctx.detect_describe_view(im)
+    assert len(a[0]) > 3000
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    n2 = (a[2].astype(np.float64) ** 2).sum(1)
+    assert np.all(np.abs(np.sqrt(n2) - 512.0) < 12.0)  # sqrt(L1-normalised) has unit L2 norm, x512, rounded
+
+
+# ---- matching ----------------------------------------------------------------------------------
+def _match_case(nq, nt, seed):
+    t_desc, _ = synth.random_descriptors(nt, seed)
+    q_desc, _ = synth.random_descriptors(nq, seed + 100, dup_of=t_desc, dup_frac=0.5)
+    rng = np.random.default_rng(seed)
+    txy = rng.uniform(0, 1000, size=(nt, 2))
+    for i in range(0, nt - 1, 7):  # near-duplicate trains close in the image: consistent 2nd NNs
+        t_desc[i + 1] = np.clip(t_desc[i].astype(int) + rng.integers(-2, 3, 128), 0, 255)
+        txy[i + 1] = txy[i] + rng.uniform(-5, 5, 2)
+    for i in range(3, nt - 1, 11):  # exact duplicates far apart: ties + inconsistent neighbours
+        t_desc[i + 1] = t_desc[i]
+    return q_desc, t_desc, txy
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("shape", [(300, 257, 1), (1000, 1500, 2), (2500, 3100, 3), (1, 60, 4), (40, 7, 5)])
+def test_fginn_bit_exact(ctx, oracle, impl, shape, monkeypatch):
+    nq, nt, seed = shape
+    q, t, txy = _match_case(nq, nt, seed)
+    monkeypatch.setenv("MB2_NN_IMPL", impl)
+    g = ctx.match_fginn(q, t, txy)
+    o = oracle.match_fginn(q.astype(np.float32), t.astype(np.float32), txy)
+    assert np.array_equal(g, o)
+
+
+@pytest.mark.parametrize("ratio,cd", [(0.8, 30.0), (0.85, 10.0), (0.6, 1e9), (0.95, 0.0)])
+def test_fginn_thresholds(ctx, oracle, ratio, cd):
+    q, t, txy = _match_case(800, 900, 9)
+    g = ctx.match_fginn(q, t, txy, ratio=ratio, contradDist=cd)
+    o = oracle.match_fginn(q.astype(np.float32), t.astype(np.float32), txy, ratio=ratio, contradDist=cd)
+    assert np.array_equal(g, o)
+
+
+def test_fginn_empty_and_unsupported(ctx):
+    q, t, txy = _match_case(10, 20, 1)
+    assert len(ctx.match_fginn(q[:0], t, txy)) == 0
+    assert len(ctx.match_fginn(q, t[:0], txy[:0])) == 0
+    with pytest.raises(mb.Mb2Error):
+        ctx.match_fginn(q, t, txy, ratio=1.0)
+
+
+def test_fginn_full_size_properties(ctx):
+    """30k x 30k (BASELINE config 3 size), where the CPU oracle would take minutes: tcgen05 and the
+    SIMT cross-check kernel must agree exactly, planted matches must be found, indices are valid."""
+    nt = nq = 30000
+    t_desc, _ = synth.random_descriptors(nt, 1)
+    q_desc, src = synth.random_descriptors(nq, 2, dup_of=t_desc, dup_frac=0.4, jitter=4)
+    txy = np.random.default_rng(3).uniform(0, 4096, size=(nt, 2))
+    a = ctx.match_fginn(q_desc, t_desc, txy)
+    os.environ["MB2_NN_IMPL"] = "simt"
+    try:
+        b = ctx.match_fginn(q_desc, t_desc, txy)
+    finally:
+        os.environ.pop("MB2_NN_IMPL", None)
+    assert np.array_equal(a, b)
+    planted = np.flatnonzero(src >= 0)
+    found = {int(r[0]): int(r[1]) for r in a}
+    hits = sum(1 for qi in planted if found.get(int(qi)) == int(src[qi]))
+    assert hits > 0.9 * len(planted)
+    assert a[:, 1].max() < nt and a[:, 2].max() < nt and np.all(a[:, 4] <= a[:, 6]) and np.all(a[:, 6] <= a[:, 5])
+
+
+def test_match_slots_equals_host_path(ctx):
+    A = synth.blob_image(640, 480, seed=3)
+    B = synth.warp_image(A, synth.gt_homography(640, 480))
+    da, ra, ua = ctx.detect_describe_view(A, slot=0)
+    db, rb, ub = ctx.detect_describe_view(B, slot=1)
+    g = ctx.match_slots(0, 1)
+    h = ctx.match_fginn(ua, ub, np.ascontiguousarray(rb[:, :2]))
+    assert len(g) > 50 and np.array_equal(g, h)
+
+
+# ---- verification ------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", range(5))
+def test_batched_scorer(ctx, oracle, which):
+    rng = np.random.default_rng(5)
+    n, K = 3000, 33
+    u = np.zeros((n, 6)); u[:, 0:2] = rng.random((n, 2)) * 1000; u[:, 2] = 1; u[:, 5] = 1
+    Hgt = synth.gt_homography(1000, 1000)
+    p = (Hgt @ u[:, 0:3].T).T; u[:, 3:5] = p[:, :2] / p[:, 2:3] + rng.normal(size=(n, 2))
+    u[n // 2:, 3:5] = rng.random((n - n // 2, 2)) * 1000
+    M0 = np.linalg.inv(Hgt).T.ravel()
+    models = np.stack([M0 * (1 + 1e-3 * rng.normal(size=9)) for _ in range(K)])
+    I, J, R = ctx.score_models(which, u, models, 9.0, want_resid=True)
+    Ro = np.stack([oracle.score(which, u, m) for m in models])
+    assert np.array_equal(R, Ro)                                   # residuals: bit-exact f64
+    assert np.array_equal(I, (Ro <= 9.0).sum(1))                   # inlier counts: exact
+    Jo = np.where(Ro >= 9.0 * 9 / 4, 0.0, 1 - (Ro / (9.0 * 9 / 4))).sum(1)
+    assert np.allclose(J, Jo, rtol=1e-12, atol=1e-9)               # MSAC sum: summation order only
+
+
+def test_scorer_matches_reference_golden(ctx):
+    for which in range(5):
+        _, _, R = ctx.score_models(which, G["r_u"], G["r_M"][None, :], 9.0, want_resid=True)
+        assert np.array_equal(R[0], G["r_scores"][which])

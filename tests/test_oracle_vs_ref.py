@@ -1,0 +1,93 @@
+"""Restatement vs the reference compiled in place, on fresh inputs (only where oracle/_ref exists:
+the build container, and the GPU box through the prebuilt .so)."""
+import numpy as np
+import pytest
+
+import synth
+
+
+@pytest.fixture(scope="module")
+def img():
+    return synth.blob_image(400, 300, seed=21)
+
+
+@pytest.mark.parametrize("sigma", [0.8, 1.2262737, 1.5198685, 1.545008, 1.946588, 2.4525473, 5.3])
+def test_gaussian_blur(oracle, reference, img, sigma):
+    assert np.array_equal(oracle.gaussian_blur(img, sigma), reference.gaussian_blur(img, sigma))
+
+
+def test_hessian_response(oracle, reference, img):
+    a, b = oracle.hessian_response(img, 2.56), reference.hessian_response(img, 2.56)
+    assert np.array_equal(a[1:-1, 1:-1], b[1:-1, 1:-1])  # the reference leaves the frame uninitialised
+
+
+def test_atan2_lut(oracle, reference):
+    rng = np.random.default_rng(1)
+    for i in range(20000):
+        y, x = rng.normal(size=2).astype(np.float32) * rng.choice([1e-3, 1.0, 100.0])
+        if i % 97 == 0:
+            x = np.float32(0)
+        if i % 101 == 0:
+            y = np.float32(0)
+        assert oracle.atan2(y, x) == reference.atan2(y, x)
+
+
+def test_interpolate_inside_and_touching(oracle, reference, img):
+    for (ox, oy, a) in ((200.3, 150.7, (0.9, 0.2, -0.1, 1.1)), (3.2, 4.1, (1.5, 0.0, 0.3, 1.2)), (396.0, 297.0, (2.0, 0.5, 0.5, 2.0))):
+        a_, ra = oracle.interpolate(img, ox, oy, *a, 19, 19)
+        b_, rb = reference.interpolate(img, ox, oy, *a, 19, 19)
+        assert ra == rb and np.array_equal(a_, b_)
+
+
+@pytest.mark.parametrize("raw", [True, False])
+def test_hessaff(oracle, reference, img, raw):
+    a, b = oracle.hessaff_detect(img, raw=raw), reference.hessaff_detect(img, raw=raw)
+    assert len(a) > 100 and np.array_equal(a, b)
+
+
+def test_hessaff_odd_sizes(oracle, reference):
+    for (w, h) in ((135, 101), (299, 150), (64, 37)):
+        im = synth.blob_image(w, h, seed=w)
+        assert np.array_equal(oracle.hessaff_detect(im), reference.hessaff_detect(im))
+
+
+@pytest.mark.parametrize("max_angles", [1, 5])
+def test_orientation(oracle, reference, img, max_angles):
+    k = reference.hessaff_detect(img)
+    a = oracle.detect_orientation(img, k, maxAngles=max_angles)
+    b = reference.detect_orientation(img, k, maxAngles=max_angles)
+    assert len(a) > 50 and np.array_equal(a, b)
+
+
+def test_reproject(oracle, reference, img):
+    k = reference.detect_orientation(img, reference.hessaff_detect(img))
+    H = np.array([[0.5, 0.1, 3.0], [-0.05, 1.0, 7.0], [0, 0, 1.0]])
+    for which in (0, 1):
+        for HH in (np.eye(3), H):
+            a = oracle.reproject(k, HH, 400, 300, which)
+            b = reference.reproject(k, HH, 400, 300, which)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("root", [True, False])
+def test_describe(oracle, reference, img, root):
+    k = reference.detect_orientation(img, reference.hessaff_detect(img))
+    k = reference.reproject(k, np.eye(3), 400, 300, 0)[0]
+    a, b = oracle.describe(img, k, rootsift=root), reference.describe(img, k, rootsift=root)
+    assert np.array_equal(a, b)
+
+
+def test_view_pipeline(oracle, reference, img):
+    a, b = oracle.view_pipeline(img), reference.view_pipeline(img)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 100
+
+
+def test_scorers(oracle, reference):
+    rng = np.random.default_rng(3)
+    n = 300
+    u = np.zeros((n, 6)); u[:, 0:2] = rng.random((n, 2)) * 500; u[:, 2] = 1; u[:, 5] = 1
+    u[:, 3:5] = rng.random((n, 2)) * 500
+    for trial in range(5):
+        M = rng.normal(size=9); M[8] = 1.0
+        for which in range(5):
+            assert np.array_equal(oracle.score(which, u, M), reference.score(which, u, M))
