@@ -27,6 +27,7 @@ struct CtxTables {
 struct CtxPriv {
   CtxTables t;
   std::vector<OctaveLevels> last_octaves;  // geometry of the most recent pyramid (diagnostics)
+  float* last_patches = nullptr;           // n x 41 x 41 normalised patches of the most recent describe
 };
 std::mutex g_lut_mutex;
 bool g_lut_uploaded[64] = {false};
@@ -487,7 +488,7 @@ int orient_core(mb2_ctx* ctx, const ImgView& img, int n, const mb2_orientation_p
 }
 
 // describe the n records at d_keys; descriptors -> ctx->desc_u8 (device)
-int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n, const mb2_sift_params& sp, float* d_patches) {
+int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n, const mb2_sift_params& sp) {
   if (n <= 0) return MB2_OK;
   if (sp.patchSize != 41) { ctx->set_error("describe: patchSize must be 41"); return MB2_ERR_ARG; }
   int rc;
@@ -518,10 +519,16 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   if (toobig) { ctx->set_error("describe: region larger than the tap table (m=" + std::to_string(toobig) + ")"); return MB2_ERR_CAPACITY; }
   if (total > ((size_t)24 << 30) / 4) { ctx->set_error("describe: patch scratch would exceed 24 GiB"); return MB2_ERR_CAPACITY; }
-  MB2_CUDA_CHECK(ctx, ctx->patch_scratch.reserve((size_t)total * 4 + 64));
+  // scratch = per-region sampling buffers, then n normalised 41x41 patches, photometric stats, bin-major votes
+  const size_t f_patches = ((size_t)total + 31) & ~(size_t)31;
+  const size_t f_stats = f_patches + (size_t)n * 41 * 41;
+  const size_t f_vec = (f_stats + (size_t)n * 2 + 1) & ~(size_t)1;
+  MB2_CUDA_CHECK(ctx, ctx->patch_scratch.reserve((f_vec + (size_t)n * 128 * 2) * 4 + 64));
   MB2_CUDA_CHECK(ctx, ctx->desc_u8.reserve((size_t)n * 128));
-  return mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, d_off,
-                                    ctx->patch_scratch.as<float>(), ctx->desc_u8.as<uint8_t>(), d_patches);
+  float* base = ctx->patch_scratch.as<float>();
+  priv(ctx)->last_patches = base + f_patches;
+  return mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, d_off, base,
+                                    ctx->desc_u8.as<uint8_t>(), base + f_patches, (float2*)(base + f_stats), (double*)(base + f_vec));
 }
 
 // FGINN on device-resident data.  out rows on host.
@@ -681,11 +688,10 @@ int mb2_describe_sift(mb2_ctx* ctx, const float* pixels, int w, int h, const dou
   if ((rc = mb2_stage_in(ctx, kp, (size_t)n * MB2_KP * 8, ctx->rs_b, &d_in))) return rc;
   MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)n * sizeof(KeyOut)));
   LAUNCH1D(ctx, k_kp_from_doubles, n, (const double*)d_in, n, ctx->kp_b.as<KeyOut>());
-  float* d_patches = nullptr;
-  if (patches) { MB2_CUDA_CHECK(ctx, ctx->rs_c.reserve((size_t)n * 41 * 41 * 4)); d_patches = ctx->rs_c.as<float>(); }
-  if ((rc = describe_core(ctx, img, ctx->kp_b.as<KeyOut>(), n, *par, d_patches))) return rc;
+  if ((rc = describe_core(ctx, img, ctx->kp_b.as<KeyOut>(), n, *par))) return rc;
   MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(desc_u8, ctx->desc_u8.p, (size_t)n * 128, cudaMemcpyDeviceToHost, ctx->stream));
-  if (patches) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(patches, d_patches, (size_t)n * 41 * 41 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (patches)
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(patches, priv(ctx)->last_patches, (size_t)n * 41 * 41 * 4, cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return n;
 }
@@ -727,7 +733,7 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
       return rc;
   }
   if (k > 0) {
-    if ((rc = describe_core(ctx, img, ctx->kp_b.as<KeyOut>(), k, *desc, nullptr))) return rc;
+    if ((rc = describe_core(ctx, img, ctx->kp_b.as<KeyOut>(), k, *desc))) return rc;
     // keep on device for matching
     const int base = rs.n;
     {
@@ -818,15 +824,6 @@ int mb2_debug_pyramid_level(mb2_ctx* ctx, int octave, int level, int want_resp, 
     MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return (int)o.size();
-}
-
-int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed,
-                 double* H, unsigned char* inl, int* data_out, double* J) {
-  (void)u; (void)len; (void)th; (void)conf; (void)max_sam; (void)errorType; (void)doSymCheck; (void)seed; (void)H; (void)inl;
-  (void)data_out; (void)J;
-  if (!ctx) return MB2_ERR_ARG;
-  ctx->set_error("mb2_ransac_h: LO-RANSAC driver not built yet (use mb2_score_models)");
-  return MB2_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

@@ -62,18 +62,11 @@ __global__ void k_plan(const KeyOut* __restrict__ kps, int n, DescribeParams dp,
 }
 
 __global__ void __launch_bounds__(DT)
-k_describe(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp, const DescTables* __restrict__ tab,
-           const TapTable taps, const unsigned long long* __restrict__ scratch_off, float* __restrict__ scratch,
-           uint8_t* __restrict__ desc_out, float* __restrict__ patch_out) {
+k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp, const TapTable taps,
+          const unsigned long long* __restrict__ scratch_off, float* __restrict__ scratch, float* __restrict__ patch_out) {
   __shared__ float s_patch[NPIX];
-  __shared__ float s_small[NEED * NEED]; // blurred patch at the needed rows x columns (extraction phase)
-  // the SIFT phase re-uses s_small: mask*grad, orientation-bin fraction, orientation bin
-  float* s_v0 = s_small;
-  float* s_wo1 = s_small + NPIX;
-  unsigned char* s_bo0 = (unsigned char*)(s_small + 2 * NPIX);
+  __shared__ float s_small[NEED * NEED]; // blurred patch at the needed rows x columns
   __shared__ int s_cols[NEED], s_rows[NEED];
-  __shared__ double s_vec[128];
-  __shared__ float s_stat[2];
 
   const int kidx = blockIdx.x, tid = threadIdx.x;
   if (kidx >= n) return;
@@ -187,32 +180,73 @@ k_describe(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp
     __syncthreads();
   }
 
-  // photometricallyNormalize (helpers.cpp:666-715): serial float sums in raster order
-  if (dp.photoNorm) {
-    if (tid == 0) {
-      float sum = 0.f, gsum = 0.f;
-      for (int p = 0; p < NPIX; p++) if (tab->mask[p] > 0) { sum = fadd(sum, s_patch[p]); gsum = fadd(gsum, 1.f); }
-      sum = fdiv(sum, gsum);
-      float var = 0.f;
-      for (int p = 0; p < NPIX; p++) if (tab->mask[p] > 0) { const float d = fsub(sum, s_patch[p]); var = fadd(var, fmul(d, d)); }
-      var = sqrtf(fdiv(var, gsum));
-      s_stat[0] = sum; s_stat[1] = var;
+  for (int p = tid; p < NPIX; p += DT) patch_out[(size_t)kidx * NPIX + p] = s_patch[p];
+}
+
+// photometricallyNormalize statistics (helpers.cpp:666-694): two serial float sums over the masked
+// pixels in raster order.  Float addition is not associative, so the sums stay serial, but 128
+// regions are summed side by side: one thread per region, the patches of a CTA's 128 regions are
+// staged through shared memory in coalesced 32-pixel slabs (padded rows: conflict-free columns).
+constexpr int PN_T = 128, PN_SLAB = 32;
+__global__ void __launch_bounds__(PN_T)
+k_photonorm_stats(const float* __restrict__ patches, int n, const DescTables* __restrict__ tab, float2* __restrict__ stats) {
+  __shared__ float s_tile[PN_T][PN_SLAB + 1];
+  __shared__ float s_mask[NPIX];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * PN_T;
+  for (int p = tid; p < NPIX; p += PN_T) s_mask[p] = tab->mask[p];
+  float sum = 0.f, gsum = 0.f, var = 0.f;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int p0 = 0; p0 < NPIX; p0 += PN_SLAB) {
+      __syncthreads();
+      for (int rr = warp; rr < PN_T; rr += PN_T / 32) {
+        const int region = r0 + rr, p = p0 + lane;
+        s_tile[rr][lane] = (region < n && p < NPIX) ? patches[(size_t)region * NPIX + p] : 0.f;
+      }
+      __syncthreads();
+      const int lim = min(PN_SLAB, NPIX - p0);
+      if (pass == 0) {
+        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { sum = fadd(sum, s_tile[tid][k]); gsum = fadd(gsum, 1.f); }
+      } else {
+        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { const float d = fsub(sum, s_tile[tid][k]); var = fadd(var, fmul(d, d)); }
+      }
     }
-    __syncthreads();
-    const float sum = s_stat[0], var = s_stat[1];
-    if (!((double)var < 0.0001)) {
+    if (pass == 0) sum = fdiv(sum, gsum);
+  }
+  var = sqrtf(fdiv(var, gsum));
+  if (r0 + tid < n) stats[r0 + tid] = make_float2(sum, var);
+}
+
+// Normalisation apply + gradients + 4x4x8 votes, one CTA (128 threads = 128 bins) per region.
+__global__ void __launch_bounds__(DT)
+k_sift_votes(float* __restrict__ patches, int n, DescribeParams dp, const DescTables* __restrict__ tab,
+             const float2* __restrict__ stats, double* __restrict__ vecT /* [128][n] */) {
+  __shared__ float s_patch[NPIX];
+  __shared__ float s_v0[NPIX];           // mask*grad
+  __shared__ float s_wo1[NPIX];
+  __shared__ unsigned char s_bo0[NPIX + 3];
+  const int kidx = blockIdx.x, tid = threadIdx.x;
+  if (kidx >= n) return;
+  float* gp = patches + (size_t)kidx * NPIX;
+  if (dp.photoNorm) {
+    const float2 st = stats[kidx];
+    const float sum = st.x, var = st.y;
+    if (!((double)var < 0.0001)) {   // helpers.cpp:695-697
       const float fac = fdiv(50.0f, var);
       for (int p = tid; p < NPIX; p += DT) {
-        float v = fadd(128.f, fmul(fac, fsub(s_patch[p], sum)));
+        float v = fadd(128.f, fmul(fac, fsub(gp[p], sum)));
         if (v > 255) v = 255;
         if (v < 0) v = 0;
         s_patch[p] = v;
+        gp[p] = v;   // the normalised patch is what DescribeRegions hands to the descriptor
       }
+    } else {
+      for (int p = tid; p < NPIX; p += DT) s_patch[p] = gp[p];
     }
-    __syncthreads();
+  } else {
+    for (int p = tid; p < NPIX; p += DT) s_patch[p] = gp[p];
   }
-  if (patch_out) for (int p = tid; p < NPIX; p += DT) patch_out[(size_t)kidx * NPIX + p] = s_patch[p];
-
+  __syncthreads();
   // gradients (siftdesc.cpp:290-345), orientation-bin split per pixel (siftdesc.cpp:99-107)
   for (int p = tid; p < NPIX; p += DT) {
     const int r = p / PS, c = p - r * PS;
@@ -258,39 +292,45 @@ k_describe(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp
         }
       }
     }
-    s_vec[tid] = acc;
+    vecT[(size_t)tid * n + kidx] = acc;
   }
-  __syncthreads();
-  // SIFTnorm / RootSIFTnorm on the double vector (siftdesc.cpp:133-159, 199-222, 247-262)
-  if (tid == 0) {
-    const double maxBinValue = (double)0.2f;
-    for (int pass = 0; pass < 2; pass++) {
-      double len = 0.0;
-      for (int i = 0; i < 128; i += 4) {
-        const double sq0 = s_vec[i] * s_vec[i], sq1 = s_vec[i + 1] * s_vec[i + 1], sq2 = s_vec[i + 2] * s_vec[i + 2],
-                     sq3 = s_vec[i + 3] * s_vec[i + 3];
-        len += sq0 + sq1 + sq2 + sq3;
-      }
-      len = sqrt(len);
-      const double fac = 1.0 / len;
-      for (int i = 0; i < 128; i++) s_vec[i] *= fac;
-      if (pass == 1) break;
-      bool changed = false;
-      for (int i = 0; i < 128; i++) if (s_vec[i] > maxBinValue) { s_vec[i] = maxBinValue; changed = true; }
-      if (!changed) break;
+}
+
+// SIFTnorm / RootSIFTnorm (siftdesc.cpp:133-159, 199-222, 247-262) + quantisation, one thread per
+// region (serial double sums in index order, as the reference); vecT is bin-major so the 128 reads
+// of neighbouring threads coalesce.
+__global__ void __launch_bounds__(128)
+k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __restrict__ desc_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double maxBinValue = (double)0.2f;
+  for (int pass = 0; pass < 2; pass++) {
+    double len = 0.0;
+    for (int i = 0; i < 128; i += 4) {
+      const double v0 = vecT[(size_t)i * n + r], v1 = vecT[(size_t)(i + 1) * n + r], v2 = vecT[(size_t)(i + 2) * n + r],
+                   v3 = vecT[(size_t)(i + 3) * n + r];
+      const double sq0 = v0 * v0, sq1 = v1 * v1, sq2 = v2 * v2, sq3 = v3 * v3;
+      len += sq0 + sq1 + sq2 + sq3;
     }
-    if (dp.rootSIFT) {
-      double sum = 0.;
-      for (int i = 0; i < 128; i++) sum += fabs(s_vec[i]);
-      for (int i = 0; i < 128; i++) s_vec[i] = sqrt(s_vec[i] / sum);
+    len = sqrt(len);
+    const double fac = 1.0 / len;
+    bool changed = false;
+    for (int i = 0; i < 128; i++) {
+      double v = vecT[(size_t)i * n + r] * fac;
+      if (pass == 0 && v > maxBinValue) { v = maxBinValue; changed = true; }
+      vecT[(size_t)i * n + r] = v;
     }
+    if (pass == 1 || !changed) break;
   }
-  __syncthreads();
-  {
+  double sum = 0.;
+  if (dp.rootSIFT) for (int i = 0; i < 128; i++) sum += fabs(vecT[(size_t)i * n + r]);
+  for (int i = 0; i < 128; i++) {
+    double v = vecT[(size_t)i * n + r];
+    if (dp.rootSIFT) v = sqrt(v / sum);
     // (int)(512.0 * v + 0.5) for RootSIFT, (int)(512.0f * v + 0.5) for SIFT: identical in double
-    int b = (int)(512.0 * s_vec[tid] + 0.5);
+    int b = (int)(512.0 * v + 0.5);
     b = b < 0 ? 0 : (b > 255 ? 255 : b);
-    desc_out[(size_t)kidx * 128 + tid] = (uint8_t)b;
+    desc_out[(size_t)r * 128 + i] = (uint8_t)b;
   }
 }
 
@@ -306,8 +346,11 @@ int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribePara
 
 int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
                                const DescTables* d_tables, const TapTable& taps, const unsigned long long* d_off, float* d_scratch,
-                               uint8_t* d_desc, float* d_patches) {
+                               uint8_t* d_desc, float* d_patches, float2* d_stats, double* d_vecT) {
   if (!n) return MB2_OK;
-  MB2_LAUNCH(ctx, k_describe, n, DT, 0, img, kps, n, dp, d_tables, taps, d_off, d_scratch, d_desc, d_patches);
+  MB2_LAUNCH(ctx, k_extract, n, DT, 0, img, kps, n, dp, taps, d_off, d_scratch, d_patches);
+  if (dp.photoNorm) MB2_LAUNCH(ctx, k_photonorm_stats, (n + PN_T - 1) / PN_T, PN_T, 0, d_patches, n, d_tables, d_stats);
+  MB2_LAUNCH(ctx, k_sift_votes, n, DT, 0, d_patches, n, dp, d_tables, d_stats, d_vecT);
+  MB2_LAUNCH(ctx, k_sift_finish, (n + 127) / 128, 128, 0, d_vecT, n, dp, d_desc);
   return MB2_OK;
 }

@@ -7,3 +7,4 @@
 #include "nn.cu"
 #include "ransac.cu"
 #include "capi.cu"
+#include "ransac_host.cu"

@@ -100,6 +100,24 @@ struct Pass2Acc {
   }
 };
 
+// Rare path of pass 2, kept out of line so the unrolled streaming loop stays small: replay the
+// failers of one 32-column slab in column order.
+__device__ __noinline__ void pass2_failers(Pass2Acc& a, const uint32_t* vals, unsigned failmask, int col0, int idx0,
+                                           const double* __restrict__ txy, double contr2) {
+  while (failmask) {
+    const int j = __ffs(failmask) - 1;
+    failmask &= failmask - 1;
+    const float v = __uint_as_float(vals[j]);
+    const int col = col0 + j;
+    a.cnt++;
+    if (col != idx0) {
+      if (v < a.best1) { a.best1 = v; a.idx1 = col; }
+      const double dx = txy[2 * idx0] - txy[2 * col], dy = txy[2 * idx0 + 1] - txy[2 * col + 1];
+      if (dx * dx + dy * dy > contr2) a.incons = 1;   // distanceSq, matching.cpp:174-179
+    }
+  }
+}
+
 __device__ __forceinline__ void merge_pass1(NNState& st, int q, float qn, const Pass1Acc& a) {
   if (a.idx >= 0) atomicMin(&st.best0[q], make_key(a.best + qn, a.idx));
 }
@@ -342,10 +360,25 @@ k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUte
             tnv[j] = t4.x; tnv[j + 1] = t4.y; tnv[j + 2] = t4.z; tnv[j + 3] = t4.w;
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (PASS == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const float v = __fmaf_rn(-2.f, __uint_as_float(r[j]), tnv[j]);
-            if (PASS == 1) a1.add(v, col0 + j); else a2.add(v, col0 + j, thr_rel, idx0, txy, contr2);
+            for (int j = 0; j < 32; j++) a1.add(__fmaf_rn(-2.f, __uint_as_float(r[j]), tnv[j]), col0 + j);
+          } else {
+            unsigned failmask = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float v = __fmaf_rn(-2.f, __uint_as_float(r[j]), tnv[j]);
+              r[j] = __float_as_uint(v);
+              const bool f = v < thr_rel;
+              failmask |= (unsigned)f << j;
+              if (!f && v < a2.bestP) { a2.bestP = v; a2.idxP = col0 + j; }
+            }
+            if (failmask) {
+              uint32_t tmp[32];
+#pragma unroll
+              for (int j = 0; j < 32; j++) tmp[j] = r[j];
+              pass2_failers(a2, tmp, failmask, col0, idx0, txy, contr2);
+            }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -14,21 +14,19 @@
 
 namespace MB2_NS {
 
-constexpr int PS = 41, NPIX = PS * PS, OW = 2;  // warps per block
+constexpr int PS = 41, NPIX = PS * PS, OW = 4;  // warps per block
 constexpr double K_SIGMA = 2 * 3.0 * 1.7320508075688772;  // synth-detection.cpp:28
 
 __global__ void __launch_bounds__(OW * 32)
 k_orientation(ImgView img, const KeyOut* __restrict__ in, int n, OrientParams op, const float* __restrict__ orimask,
               KeyOut* __restrict__ out, int* __restrict__ out_count) {
   __shared__ float s_patch[OW][NPIX];
-  __shared__ float s_wgt[OW][NPIX];
-  __shared__ unsigned char s_bin[OW][NPIX + 3];
   __shared__ float s_hist[OW][40];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kidx = blockIdx.x * OW + warp;
   if (kidx >= n) return;
   const KeyOut k = in[kidx];
-  float* patch = s_patch[warp]; float* wgt = s_wgt[warp]; unsigned char* bin = s_bin[warp]; float* hist = s_hist[warp];
+  float* patch = s_patch[warp]; float* hist = s_hist[warp];
   const int maxA = op.maxAngles;
   KeyOut* dst = out + (size_t)kidx * maxA;
   for (int j = lane; j < maxA; j += 32) dst[j].keep = 0;
@@ -51,33 +49,39 @@ k_orientation(ImgView img, const KeyOut* __restrict__ in, int n, OrientParams op
     interpolate_row(img.p, img.rows, img.cols, img.pitch, x, y, A11, A12, A21, A22, PS, PS, touch, row,
                     [&](int i, float v) { patch[row * PS + i] = v; });
   __syncwarp();
-  // gradient magnitude / orientation on the inner 39x39; weight and bin per pixel
+  // Gradient magnitude / orientation on the inner 39x39 (helpers.cpp:840-863), then the 36-bin
+  // histogram: bin b is a float sum over its pixels in raster order.  Lane L owns bins L and L+32;
+  // each slab of 32 consecutive pixels is evaluated one pixel per lane and then replayed in pixel
+  // order through shuffles, so every bin sees its contributions in the reference's order.
   const float PIf = 3.14159265358979323846f;
-  for (int p = lane; p < NPIX; p += 32) {
-    const int r = p / PS, c = p - r * PS;
-    unsigned char b = 255; float w = 0.f;
-    if (r >= 1 && r < PS - 1 && c >= 1 && c < PS - 1) {
-      const float xg = fsub(patch[p + 1], patch[p - 1]);
-      const float yg = fsub(patch[p + PS], patch[p - PS]);
-      const float mag = sqrtf(fadd(fmul(xg, xg), fmul(yg, yg)));
-      const float m = orimask[p];
-      if (m > 0 && (double)mag > 1.0) {
-        const float ori = atan2LUTff_dev(yg, xg);
-        const int bi = (int)fdiv(fmul(36.f, fadd(fdiv(ori, PIf), 1.0f)), 2.0f);
-        b = (unsigned char)bi;  // bi == 36 (ori == +pi) falls into a slot the reference never reads
-        w = fmul(mag, m);
-      }
-    }
-    bin[p] = b; wgt[p] = w;
-  }
-  __syncwarp();
   {
     float h0 = 0.f, h1 = 0.f;
     const int b0 = lane, b1 = lane + 32;
-    for (int p = PS; p < NPIX - PS; ++p) {
-      const int b = bin[p];
-      if (b == b0) h0 = fadd(h0, wgt[p]);
-      else if (b == b1) h1 = fadd(h1, wgt[p]);
+    for (int p0 = PS; p0 < NPIX - PS; p0 += 32) {
+      const int p = p0 + lane;
+      int b = 255; float w = 0.f;
+      if (p < NPIX - PS) {
+        const int r = p / PS, c = p - r * PS;
+        if (c >= 1 && c < PS - 1) {
+          const float xg = fsub(patch[p + 1], patch[p - 1]);
+          const float yg = fsub(patch[p + PS], patch[p - PS]);
+          const float mag = sqrtf(fadd(fmul(xg, xg), fmul(yg, yg)));
+          const float m = orimask[p];
+          if (m > 0 && (double)mag > 1.0) {
+            const float ori = atan2LUTff_dev(yg, xg);
+            b = (int)fdiv(fmul(36.f, fadd(fdiv(ori, PIf), 1.0f)), 2.0f);  // 36 (ori == +pi): a slot the reference never reads
+            w = fmul(mag, m);
+          }
+        }
+      }
+      if (__ballot_sync(0xffffffffu, b != 255) == 0) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int bj = __shfl_sync(0xffffffffu, b, j);
+        const float wj = __shfl_sync(0xffffffffu, w, j);
+        if (bj == b0) h0 = fadd(h0, wj);
+        else if (bj == b1) h1 = fadd(h1, wj);
+      }
     }
     hist[b0] = h0;
     if (b1 < 36) hist[b1] = h1;

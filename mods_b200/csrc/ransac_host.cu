@@ -1,0 +1,570 @@
+// LO-RANSAC homography (DEGENSAC, exp_ransacHcustom) with GPU-batched hypothesis scoring.
+//
+// Reference: degensac/exp_ranH.c:796-1236 (main loop, iter_type 4 = LSQ-before-LO + inner RANSAC),
+// exp_inHranicustom (:741-793), exp_iterHcustom (:617-737); rtools.c (sample :12-23, randsubset
+// :25-39, multirsampleT :136-156, inlidxs :160-171, nsamples :202-225, truncQuad :228-236,
+// scoreLess :238-250); Htools.c (lin_hg :17-55, lin_hgN :57-96, u2h :98-130, all_Hori_valid
+// :543-569); utools.c (normu :7-50, denormH :70-89, nullspace :97-167, cov_mat :170-185, det3
+// :196-202); hash.c (SuperFastHash, htContains / htInsert).
+//
+// What is restructured, and why it is the same computation:
+//  * The reference draws sample k with `srand(seed_k); 4 x random(); seed_{k+1} = rand()` and a pool
+//    permutation that never depends on scores, so the hypothesis sequence is a pure function of the
+//    initial seed.  We generate hypotheses in batches on the host with exactly those calls
+//    (glibc random_r with a private state: same stream as srand/rand, but re-entrant), score a whole
+//    batch in ONE launch (I = #inliers, J = MSAC sum per hypothesis), and then replay the reference's
+//    sequential best-so-far / symmetric-check / LO / adaptive-stop logic over the scores.
+//  * The reference keeps residual vectors in four rotating buffers (errs[0..3], errs[4] aliases one
+//    of them).  A buffer is modelled as "the residuals of hypothesis h": it is only materialised
+//    (one GPU launch) when the reference would actually read it (symmetric check, LO, final mask),
+//    including the reference's aliasing quirk where errs[4] may point at a buffer that later samples
+//    overwrite.
+//  * The 9x9 symmetric eigenproblem of the normalised DLT (u2h) uses a cyclic Jacobi solver instead
+//    of LAPACK dsyev (the reference links an unpinned system LAPACK): H agrees to ~1e-13 relative up
+//    to sign, decisions agree unless a residual sits within that distance of a threshold.
+#include "common.cuh"
+#undef MB2_NS
+#define MB2_NS mb2_ransac_host_detail
+#include "ransac.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace MB2_NS {
+
+struct Score { unsigned I; double J; };
+
+constexpr int ITER_SAM = 50, RAN_REP = 10, ILSQ_ITERS = 4, TC = 4, MWM = (9 / 4);  // rtools.h:7-35 (MWM is an int: 2)
+constexpr int MAX_SAMPLES = 1000000;
+constexpr double DEGENSAC_EPS = 2.2204e-16;
+constexpr double CHECK_COEF = 9.0;
+constexpr int MIN_GOOD_SYM_PTS = 5;
+
+inline double truncQuad(double epsilon, double thr) {
+  if (thr == 0) return 0;
+  if (epsilon >= thr * 9 / 4) return 0;
+  return 1 - (epsilon / (thr * 9 / 4));
+}
+inline int scoreLess(const Score a, const Score b) { return a.J < b.J; }  // __SCORE__ == SC_M
+inline Score inlidxs(const double* err, int len, double th, int* inl) {
+  Score s = {0, 0};
+  for (int i = 0; i < len; ++i) {
+    s.J += truncQuad(err[i], th);
+    if (err[i] <= th) { inl[s.I] = i; ++(s.I); }
+  }
+  return s;
+}
+inline int nsamples(int ninl, int ptNum, int samsiz, double conf) {
+  double a = 1, b = 1;
+  for (int i = 0; i < samsiz; i++) { a *= ninl - i; b *= ptNum - i; }
+  a = a / b;
+  if (a < DEGENSAC_EPS) return MAX_SAMPLES;
+  a = 1 - a;
+  if (a < DEGENSAC_EPS) return 1;
+  b = std::log(1 - conf) / std::log(a);
+  if (b > MAX_SAMPLES) return MAX_SAMPLES;
+  return (int)std::ceil(b);
+}
+inline double det3(const double* A) {
+  double r = (A[0] * A[4] * A[8] + A[2] * A[3] * A[7] + A[1] * A[5] * A[6]);
+  r -= (A[2] * A[4] * A[6] + A[0] * A[5] * A[7] + A[1] * A[3] * A[8]);
+  return r;
+}
+
+// glibc rand()/srand() stream with private state (TYPE_3, 128-byte state, same as the default generator)
+struct LibcRand {
+  struct random_data buf;
+  char state[128];
+  LibcRand() { std::memset(&buf, 0, sizeof buf); std::memset(state, 0, sizeof state); initstate_r(1, state, sizeof state, &buf); }
+  void seed(unsigned s) { srandom_r(s, &buf); }
+  int next() { int32_t r; random_r(&buf, &r); return (int)r; }
+};
+
+// rows 2q, 2q+1 of lin_hg's matrix (Htools.c:17-55) for correspondence q
+inline void lin_rows(const double* u, int q, double* r0, double* r1) {
+  const double* s = u + 6 * q;
+  r0[0] = s[3]; r0[1] = 0; r0[2] = -s[0] * s[3]; r0[3] = s[4]; r0[4] = 0; r0[5] = -s[0] * s[4]; r0[6] = s[5]; r0[7] = 0; r0[8] = -s[0] * s[5];
+  r1[0] = 0; r1[1] = s[3]; r1[2] = -s[1] * s[3]; r1[3] = 0; r1[4] = s[4]; r1[5] = -s[1] * s[4]; r1[6] = 0; r1[7] = s[5]; r1[8] = -s[1] * s[5];
+}
+
+// utools.c:97-167 (Gauss-Jordan with column pivoting bookkeeping; matrix row-wise)
+int nullspace(double* matrix, double* nullsp, int n, int* buffer) {
+  int* pnopivot = buffer; int nonpivot = 0;
+  int* ppivot = buffer + n;
+  int i = 0;
+  const double tol = 1e-12;
+  for (int j = 0; j < n; j++) {
+    double pivot = std::fabs(matrix[n * i + j]); int max = i;
+    for (int k = i + 1; k < n; k++) { double t = std::fabs(matrix[n * k + j]); if (pivot < t) { pivot = t; max = k; } }
+    if (pivot < tol) {
+      *(pnopivot++) = j; nonpivot++;
+      for (int k = i; k < n; k++) matrix[n * k + j] = 0;
+    } else {
+      *(ppivot++) = j;
+      for (int k = j; k < n; k++) { double t = matrix[i * n + k]; matrix[i * n + k] = matrix[max * n + k]; matrix[max * n + k] = t; }
+      pivot = matrix[i * n + j];
+      for (int k = j; k < n; k++) matrix[i * n + k] /= pivot;
+      for (int k = 0; k < i; k++) { pivot = -matrix[k * n + j]; for (int l = j; l < n; l++) matrix[k * n + l] += pivot * matrix[i * n + l]; }
+      for (int k = i + 1; k < n; k++) { pivot = matrix[k * n + j]; for (int l = j; l < n; l++) matrix[k * n + l] -= pivot * matrix[i * n + l]; }
+      i++;
+    }
+  }
+  for (int k = 0; k < nonpivot; k++) {
+    int j = buffer[k];
+    for (int l = 0; l < n - nonpivot; l++) nullsp[k * n + buffer[n + l]] = -matrix[l * n + j];
+    for (int l = 0; l < nonpivot; l++) nullsp[k * n + buffer[l]] = (j == buffer[l]) ? 1 : 0;
+  }
+  return nonpivot;
+}
+
+// Htools.c:543-569
+inline void cross3(double* out, const double* a, const double* b) {
+  out[0] = a[1] * b[2] - a[2] * b[1]; out[1] = a[2] * b[0] - a[0] * b[2]; out[2] = a[0] * b[1] - a[1] * b[0];
+}
+int all_Hori_valid(const double* us, const int* idx) {
+  double p[3], q[3];
+  const double *a = us + 6 * idx[0], *b = us + 6 * idx[1], *c = us + 6 * idx[2], *d = us + 6 * idx[3];
+  cross3(p, a, b); cross3(q, a + 3, b + 3);
+  if ((p[0] * c[0] + p[1] * c[1] + p[2] * c[2]) * (q[0] * c[3] + q[1] * c[4] + q[2] * c[5]) < 0) return 0;
+  if ((p[0] * d[0] + p[1] * d[1] + p[2] * d[2]) * (q[0] * d[3] + q[1] * d[4] + q[2] * d[5]) < 0) return 0;
+  cross3(p, c, d); cross3(q, c + 3, d + 3);
+  if ((p[0] * a[0] + p[1] * a[1] + p[2] * a[2]) * (q[0] * a[3] + q[1] * a[4] + q[2] * a[5]) < 0) return 0;
+  if ((p[0] * b[0] + p[1] * b[1] + p[2] * b[2]) * (q[0] * b[3] + q[1] * b[4] + q[2] * b[5]) < 0) return 0;
+  return 1;
+}
+
+// Smallest eigenvector of a symmetric 9x9 (stands in for LAPACK dsyev in lap_eig, lapwrap.c:67-97)
+void smallest_eigvec9(const double* C, double* v) {
+  const int n = 9;
+  double A[81], V[81];
+  std::memcpy(A, C, sizeof A);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < n; i++) { diag += A[i * n + i] * A[i * n + i]; for (int j = i + 1; j < n; j++) off += A[i * n + j] * A[i * n + j]; }
+    if (off <= 1e-32 * diag || off == 0) break;
+    for (int p = 0; p < n - 1; p++)
+      for (int q = p + 1; q < n; q++) {
+        const double apq = A[p * n + q];
+        if (apq == 0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < n; k++) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int best = 0;
+  for (int i = 1; i < n; i++) if (A[i * n + i] < A[best * n + best]) best = i;
+  for (int k = 0; k < n; k++) v[k] = V[k * n + best];
+}
+
+// utools.c:7-50
+void normu(const double* u, const int* inl, int len, double* A1, double* A2) {
+  for (int j = 0; j < 3; j++) { A1[j] = 0; A2[j] = 0; }
+  for (int j = 0; j < len; j++) { const double* p = u + 6 * inl[j]; A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[3]; A2[2] += p[4]; }
+  if (len > 0) for (int i = 1; i < 3; i++) { A1[i] /= len; A2[i] /= len; }
+  for (int j = 0; j < len; j++) {
+    const double* p = u + 6 * inl[j];
+    double a = p[0] - A1[1], b = p[1] - A1[2];
+    A1[0] += std::sqrt(a * a + b * b);
+    a = p[3] - A2[1]; b = p[4] - A2[2];
+    A2[0] += std::sqrt(a * a + b * b);
+  }
+  if (A1[0] != 0) A1[0] = len * std::sqrt(2) / A1[0];
+  if (A2[0] != 0) A2[0] = len * std::sqrt(2) / A2[0];
+  A1[1] *= -A1[0]; A1[2] *= -A1[0];
+  A2[1] *= -A2[0]; A2[2] *= -A2[0];
+}
+// utools.c:70-89
+void denormH(double* F, const double* A1, const double* A2) {
+  double r = A2[0], x = A2[1], y = A2[2];
+  F[6] += x * F[0] + y * F[3];
+  F[7] += x * F[1] + y * F[4];
+  F[8] += x * F[2] + y * F[5];
+  F[0] *= r; F[1] *= r; F[2] *= r; F[3] *= r; F[4] *= r; F[5] *= r;
+  r = 1 / A1[0]; x = -A1[1] * r; y = -A1[2] * r;
+  for (int i = 0; i < 9; i += 3) { F[i] = r * F[i] + x * F[i + 2]; F[i + 1] = r * F[i + 1] + y * F[i + 2]; }
+}
+// Htools.c:98-130 (u2h): exact 4-point nullspace or normalised-DLT least squares
+void u2h(const double* u, const int* inl, int len, double* H) {
+  if (len < 4) return;
+  if (len == 4) {
+    double Z2[81], V[81];
+    int nb[18];
+    for (int i = 0; i < 4; i++) lin_rows(u, inl[i], Z2 + (2 * i) * 9, Z2 + (2 * i + 1) * 9);
+    for (int i = 72; i < 81; ++i) Z2[i] = 0.0;
+    std::memset(V, 0, sizeof V);
+    nullspace(Z2, V, 9, nb);
+    std::memcpy(H, V, 9 * sizeof(double));
+    return;
+  }
+  double A1[3], A2[3], C[81];
+  normu(u, inl, len, A1, A2);
+  // lin_hgN (Htools.c:57-96) rows, accumulated straight into the 9x9 covariance (cov_mat, utools.c:170-185:
+  // C[i][j] = sum_k Z[k][i] * Z[k][j], k in row order)
+  std::vector<double> Z((size_t)2 * len * 9);
+  for (int i = 0; i < len; i++) {
+    const double* s = u + 6 * inl[i];
+    double a[3], b[3];
+    a[2] = 1; b[2] = 1;
+    a[0] = s[0] * A1[0] + A1[1]; a[1] = s[1] * A1[0] + A1[2];
+    b[0] = s[3] * A2[0] + A2[1]; b[1] = s[4] * A2[0] + A2[2];
+    double* r0 = Z.data() + (size_t)(2 * i) * 9; double* r1 = r0 + 9;
+    for (int j = 0; j < 3; j++) {
+      r0[3 * j] = b[j]; r0[3 * j + 1] = 0; r0[3 * j + 2] = -a[0] * b[j];
+      r1[3 * j] = 0; r1[3 * j + 1] = b[j]; r1[3 * j + 2] = -a[1] * b[j];
+    }
+  }
+  for (int i = 0; i < 9; i++)
+    for (int j = 0; j <= i; j++) {
+      double val = 0;
+      for (int k = 0; k < 2 * len; k++) val += Z[(size_t)k * 9 + i] * Z[(size_t)k * 9 + j];
+      C[9 * i + j] = val; C[i + 9 * j] = val;
+    }
+  smallest_eigvec9(C, H);
+  denormH(H, A1, A2);
+}
+
+// hash.c
+uint32_t SuperFastHash(const char* data, int len) {
+  uint32_t hash = len, tmp;
+  if (len <= 0 || data == 0) return 0;
+  auto get16 = [](const char* d) { return (uint32_t)(((uint32_t)((const uint8_t*)d)[1]) << 8) + (uint32_t)((const uint8_t*)d)[0]; };
+  int rem = len & 3;
+  len >>= 2;
+  for (; len > 0; len--) {
+    hash += get16(data);
+    tmp = (get16(data + 2) << 11) ^ hash;
+    hash = (hash << 16) ^ tmp;
+    data += 4;
+    hash += hash >> 11;
+  }
+  switch (rem) {
+    case 3: hash += get16(data); hash ^= hash << 16; hash ^= ((signed char)data[2]) << 18; hash += hash >> 11; break;
+    case 2: hash += get16(data); hash ^= hash << 11; hash += hash >> 17; break;
+    case 1: hash += (signed char)*data; hash ^= hash << 10; hash += hash >> 1;
+  }
+  hash ^= hash << 3; hash += hash >> 5; hash ^= hash << 4; hash += hash >> 17; hash ^= hash << 25; hash += hash >> 6;
+  return hash;
+}
+struct HashTable {
+  struct Field { uint32_t hash; int length, iterID; };
+  std::vector<Field> f[64];  // newest last; the reference prepends, so scan backwards
+  void insert(uint32_t h, int len, int id) { f[h % 64].push_back({h, len, id}); }
+  int contains(uint32_t h, int len, int id) const {
+    const auto& b = f[h % 64];
+    for (size_t i = b.size(); i-- > 0;) if (b[i].hash == h && b[i].length == len && b[i].iterID == id) return id;
+    for (size_t i = b.size(); i-- > 0;) if (b[i].hash == h && b[i].length == len) return b[i].iterID;
+    return -1;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+struct RansacH {
+  mb2_ctx* ctx;
+  const double* u; int len; double th; int which, doSymCheck;
+  const double* d_u = nullptr;
+  // residual buffers: errs[0..3] are buffer ids, errs[4] aliases one of them
+  struct Buf { std::vector<double> d; double h[9]; bool valid = false; bool tagged = false; };
+  Buf bufs[4];
+  int errs[5] = {0, 1, 2, 3, 3};
+  HashTable ht;
+  LibcRand rng;
+  int rc = MB2_OK;
+
+  // ---- GPU services
+  int gpu_resid(int which_, const double* h, double* out, Score* S, double th_) {
+    int I = 0; double J = 0;
+    int r = mb2_score_models(ctx, which_, d_u, len, h, 1, th_, out, &I, &J);
+    if (r < 0) { rc = r; return r; }
+    if (S) { S->I = (unsigned)I; S->J = J; }
+    return MB2_OK;
+  }
+  // eager "HDS1(Z, u, h, d, len)" into buffer id b
+  void eval_into(int b, const double* h) {
+    Buf& B = bufs[b];
+    B.d.resize(len);
+    gpu_resid(which, h, B.d.data(), nullptr, th);
+    std::memcpy(B.h, h, sizeof B.h); B.valid = true; B.tagged = true;
+  }
+  // lazy form used by the main sampling loop
+  void tag(int b, const double* h) { Buf& B = bufs[b]; std::memcpy(B.h, h, sizeof B.h); B.valid = false; B.tagged = true; }
+  const double* data(int b) {
+    Buf& B = bufs[b];
+    if (!B.valid) {
+      B.d.assign(len, 0.0);
+      if (B.tagged) gpu_resid(which, B.h, B.d.data(), nullptr, th);
+      B.valid = true;
+    }
+    return B.d.data();
+  }
+  bool sym_check_bad(const double* h) {  // exp_ranH.c:917-927
+    Score S = {0, 0};
+    gpu_resid(1 /*HDsSym*/, h, nullptr, &S, CHECK_COEF * th);
+    return S.I <= (unsigned)MIN_GOOD_SYM_PTS;
+  }
+
+  // rtools.c:25-39
+  int* randsubset(int* pool, int max_sz, int siz) {
+    for (int i = 0; i < siz; i++) {
+      int s = rng.next() % (max_sz - i), j = max_sz - i - 1;
+      int q = pool[s]; pool[s] = pool[j]; pool[j] = q;
+    }
+    return pool + max_sz - siz;
+  }
+
+  // exp_ranH.c:617-737
+  Score iterH(int* inliers, double ths, int steps, double* H, int iterID) {
+    int dbuf = errs[1];
+    double h[9] = {0};
+    Score maxS = {0, 0}, S = {0, 0}, Ss;
+    const double dth = (ths - th) / (steps);
+    maxS = inlidxs(data(errs[4]), len, th, inliers);
+    if (maxS.I < 4) return S;
+    S = inlidxs(data(errs[4]), len, th * MWM, inliers);
+    u2h(u, inliers, S.I, h);  // __D3__ with D3_H_RATIO 1 and an unlimited inlLimit: all inliers
+    for (int it = 0; it < steps; it++) {
+      eval_into(dbuf, h);
+      Ss = inlidxs(bufs[dbuf].d.data(), len, th, inliers);
+      const uint32_t hash = SuperFastHash((const char*)inliers, Ss.I * sizeof(*inliers));
+      const int ret = ht.contains(hash, Ss.I, iterID);
+      if (ret != -1 && ret != iterID) { S.I = 0; S.J = 0; return S; }
+      if (ret == -1) ht.insert(hash, Ss.I, iterID);
+      S = inlidxs(bufs[dbuf].d.data(), len, ths * MWM, inliers);
+      if (scoreLess(maxS, Ss)) {
+        maxS = Ss;
+        errs[1] = errs[0]; errs[0] = dbuf; dbuf = errs[1];
+        std::memcpy(H, h, 9 * sizeof(double));
+      }
+      if (S.I < 4) return maxS;
+      u2h(u, inliers, S.I, h);
+      ths -= dth;
+    }
+    eval_into(dbuf, h);
+    S = inlidxs(bufs[dbuf].d.data(), len, th, inliers);
+    if (scoreLess(maxS, S)) {
+      maxS = S;
+      errs[1] = errs[0]; errs[0] = dbuf;
+      std::memcpy(H, h, 9 * sizeof(double));
+    }
+    return maxS;
+  }
+
+  // exp_ranH.c:741-793
+  Score inHrani(int* inliers, int ninl, double* H, int rep, int* iterID) {
+    Score S, maxS = {0, 0};
+    double h[9] = {0};
+    std::vector<int> intbuff(len);
+    if (ninl < 8) return maxS;
+    int ssiz = ninl / 2;
+    if (ssiz > 12) ssiz = 12;
+    std::swap(errs[2], errs[0]);
+    for (int i = 0; i < rep; i++) {
+      int* sample = randsubset(inliers, ninl, ssiz);
+      u2h(u, sample, ssiz, h);
+      eval_into(errs[0], h);
+      errs[4] = errs[0];
+      S = iterH(intbuff.data(), TC * th, ILSQ_ITERS, h, ++*iterID);
+      if (scoreLess(maxS, S)) {
+        maxS = S;
+        std::swap(errs[2], errs[0]);
+        std::memcpy(H, h, 9 * sizeof(double));
+      }
+    }
+    std::swap(errs[2], errs[0]);
+    return maxS;
+  }
+
+  // case 4 of the iteration switch (exp_ranH.c:1012-1035 / 1151-1174)
+  Score local_optimisation(int* inliers, double* h, int* iterID) {
+    const int d = errs[0];
+    Score S = inlidxs(data(errs[4]), len, TC * th * MWM, inliers);
+    u2h(u, inliers, S.I, h);
+    eval_into(d, h);
+    S = inlidxs(bufs[d].d.data(), len, th, inliers);
+    return inHrani(inliers, S.I, h, RAN_REP, iterID);
+  }
+};
+
+}  // namespace
+using namespace MB2_NS;
+
+extern "C" int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck,
+                            long seed, double* H, unsigned char* inl, int* data_out, double* Jout) {
+  if (!ctx || !u || len < 0 || !H || !inl) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 9; i++) H[i] = 0;
+  for (int i = 0; i < len; i++) inl[i] = 0;
+  if (data_out) data_out[0] = data_out[1] = data_out[2] = 0;
+  if (Jout) *Jout = 0;
+  if (len < 4) return 0;
+  if (mb2_is_device_ptr(u)) { ctx->set_error("ransac_h: u must be a host pointer (the LO logic runs on the host)"); return MB2_ERR_ARG; }
+
+  RansacH R;
+  R.ctx = ctx; R.u = u; R.len = len; R.th = th; R.doSymCheck = doSymCheck;
+  R.which = errorType == 0 ? 0 : (errorType == 1 ? 2 : 1);  // Sampson -> HDs, SymmMax -> HDsSymMax, SymmSum -> HDsSym
+  // correspondences stay resident on the device for the whole run
+  static thread_local DevBuf d_u_buf;  // per thread; freed at process exit
+  if (d_u_buf.reserve((size_t)len * 48) != cudaSuccess) { ctx->set_error("ransac_h: cudaMalloc failed"); return MB2_ERR_CUDA; }
+  if (cudaMemcpyAsync(d_u_buf.p, u, (size_t)len * 48, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return MB2_ERR_CUDA;
+  R.d_u = d_u_buf.as<double>();
+
+  std::vector<int> pool(len), inliers(len);
+  for (int i = 0; i < len; i++) pool[i] = i;
+  int* samidx = pool.data() + len - 4;
+  int bestsamidx[4] = {0, 0, 0, 0};
+  double sol[81], *h = sol, M[81];
+  int nullspace_buff[18];
+  Score maxS = {0, 0}, maxSs = {0, 0}, S = {0, 0};
+  int no_sam = 0, iter_cnt = 0, no_rej = 0, iterID = 0;
+  bool new_max = false, bad_model = false;
+  std::memset(sol, 0, sizeof sol);
+
+  R.rng.seed((unsigned)seed);           // srand(time(NULL)) in the reference (exp_ranH.c:823)
+  unsigned cur_seed = (unsigned)R.rng.next();  // seed = rand()
+
+  // ---- batched hypothesis generation -------------------------------------------------------------
+  struct Hyp { double h[9]; unsigned seed_before; int sam[4]; int status; /* 0 ok, 1 orientation reject, 2 skipped */ };
+  std::vector<Hyp> batch;
+  std::vector<double> models;
+  std::vector<int> bI; std::vector<double> bJ;
+  size_t bpos = 0;
+  int batch_size = 64;
+  auto refill = [&](int want) -> int {
+    batch.clear(); models.clear(); bpos = 0;
+    for (int k = 0; k < want; k++) {
+      Hyp hy; hy.status = 0; hy.seed_before = cur_seed;
+      R.rng.seed(cur_seed);
+      // multirsampleT(Z, 9, 2, pool, 4, len, M): 4 x sample() (rtools.c:12-23), rows of Z into M
+      for (int i = 0; i < 4; i++) {
+        int s = R.rng.next() % (len - i), j = len - i - 1;
+        int q = pool[s]; pool[s] = pool[j]; pool[j] = q;
+        lin_rows(u, q, M + (2 * i) * 9, M + (2 * i + 1) * 9);
+      }
+      cur_seed = (unsigned)R.rng.next();
+      std::memcpy(hy.sam, samidx, sizeof hy.sam);
+      if (!all_Hori_valid(u, samidx)) hy.status = 1;
+      else {
+        for (int i = 72; i < 81; ++i) M[i] = 0.0;
+        double hs[81];
+        std::memset(hs, 0, sizeof hs);
+        int nullsize = nullspace(M, hs, 9, nullspace_buff);
+        if (nullsize != 1) hy.status = 2;
+        else {
+          double v = det3(hs), tol = hs[8];
+          if (tol == 0) { for (int i = 0; i < 9; ++i) tol += hs[i] * hs[i]; tol = std::sqrt(tol); tol *= 0.001; }
+          tol = tol * tol * tol;
+          if (std::fabs(v / tol) < 10e-2) hy.status = 2;
+          else std::memcpy(hy.h, hs, sizeof hy.h);
+        }
+      }
+      if (hy.status == 0) models.insert(models.end(), hy.h, hy.h + 9);
+      batch.push_back(hy);
+    }
+    const int K = (int)(models.size() / 9);
+    bI.assign(std::max(K, 1), 0); bJ.assign(std::max(K, 1), 0.0);
+    if (K > 0) {
+      int r = mb2_score_models(ctx, R.which, R.d_u, len, models.data(), K, th, nullptr, bI.data(), bJ.data());
+      if (r < 0) return r;
+    }
+    return MB2_OK;
+  };
+
+  auto tol_of = [](const double* hh) {
+    double tol = hh[8];
+    if (tol == 0) { for (int i = 0; i < 9; ++i) tol += hh[i] * hh[i]; tol = std::sqrt(tol); tol *= 0.001; }
+    return tol * tol * tol;
+  };
+
+  size_t model_idx = 0;
+  unsigned last_seed_before = cur_seed;
+  bool any_sample = false;
+  while (no_sam < max_sam) {
+    if (bpos >= batch.size()) {
+      int want = std::min(batch_size, std::max(1, max_sam - no_sam));
+      int r = refill(want);
+      if (r < 0) return r;
+      model_idx = 0;
+      if (batch_size < 4096) batch_size *= 2;
+    }
+    const Hyp& hy = batch[bpos++];
+    no_sam++;
+    last_seed_before = hy.seed_before; any_sample = true;
+    if (hy.status == 1) { no_rej++; continue; }
+    if (hy.status == 2) continue;
+    std::memcpy(h, hy.h, 9 * sizeof(double));
+    const int dbuf = R.errs[0];
+    R.tag(dbuf, h);                                   // d = errs[0]; HDS1(Z, u, h, d, len)
+    S.I = (unsigned)bI[model_idx]; S.J = bJ[model_idx]; model_idx++;
+    bool do_iterate;
+    if (scoreLess(maxS, S)) {
+      if (doSymCheck) bad_model = R.sym_check_bad(h);
+      if (bad_model) continue;
+      R.errs[0] = R.errs[3]; R.errs[3] = dbuf;
+      maxS = S; new_max = true;
+      std::memcpy(H, h, 9 * sizeof(double));
+    }
+    if (scoreLess(maxSs, S)) {
+      do_iterate = no_sam > ITER_SAM;
+      maxSs = S;
+      R.errs[4] = dbuf;
+      std::memcpy(bestsamidx, hy.sam, sizeof bestsamidx);
+    } else do_iterate = false;
+    if ((no_sam >= ITER_SAM) && (iter_cnt == 0) && (maxSs.I > 4)) do_iterate = true;
+    if (do_iterate) {
+      iter_cnt++;
+      // the reference's generator state here: srand(seed_k); 4 draws; 1 draw for the next seed
+      R.rng.seed(hy.seed_before);
+      for (int i = 0; i < 5; i++) R.rng.next();
+      S = R.local_optimisation(inliers.data(), h, &iterID);
+      if (R.rc < 0) return R.rc;
+      if (scoreLess(maxS, S) && (std::fabs(det3(h) / tol_of(h)) > 10e-2)) {
+        if (doSymCheck) bad_model = R.sym_check_bad(h);
+        if (!bad_model) {
+          const int d0 = R.errs[0];
+          R.errs[0] = R.errs[3]; R.errs[3] = d0;
+          maxS = S; new_max = true;
+          std::memcpy(H, h, 9 * sizeof(double));
+        }
+      }
+    }
+    if (new_max) {
+      const int new_sam = nsamples(maxS.I + 1, len, 4, conf);
+      if (new_sam < max_sam) max_sam = new_sam;
+      new_max = false;
+    }
+  }
+  if (iter_cnt == 0) {  // "If there were no LOs, do at least one NOW!" (exp_ranH.c:1124-1204)
+    iter_cnt++;
+    if (any_sample) { R.rng.seed(last_seed_before); for (int i = 0; i < 5; i++) R.rng.next(); }
+    S = R.local_optimisation(inliers.data(), h, &iterID);
+    if (R.rc < 0) return R.rc;
+    if (scoreLess(maxS, S) && (std::fabs(det3(h) / tol_of(h)) > 10e-2)) {
+      if (doSymCheck) bad_model = R.sym_check_bad(h);
+      if (!bad_model) {
+        const int d0 = R.errs[0];
+        R.errs[0] = R.errs[3]; R.errs[3] = d0;
+        maxS = S;
+        std::memcpy(H, h, 9 * sizeof(double));
+      }
+    }
+  }
+  const double* d = R.data(R.errs[3]);
+  if (R.rc < 0) return R.rc;
+  for (int j = 0; j < len; j++) inl[j] = (maxS.J > 0 || maxS.I > 0) ? (d[j] <= th ? 1 : 0) : 0;
+  if (data_out) { data_out[0] = no_sam; data_out[1] = iter_cnt; data_out[2] = no_rej; }
+  if (Jout) *Jout = maxS.J;
+  return (int)maxS.I;
+}

@@ -231,3 +231,42 @@ def test_scorer_matches_reference_golden(ctx):
     for which in range(5):
         _, _, R = ctx.score_models(which, G["r_u"], G["r_M"][None, :], 9.0, want_resid=True)
         assert np.array_equal(R[0], G["r_scores"][which])
+
+
+# ---- LO-RANSAC homography ----------------------------------------------------------------------
+def _h_close(a, b):
+    a = np.asarray(a) / np.linalg.norm(a); b = np.asarray(b) / np.linalg.norm(b)
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+def test_ransac_h_matches_reference_golden(ctx):
+    """exp_ransacHcustom of the reference (seed 12345 through its srand(time(NULL)) hook) on a planted
+    homography: same hypothesis sequence => same sample / LO / rejection counts, same inlier mask."""
+    res = ctx.ransac_h(G["r_u"], seed=12345)
+    I, samples, lo, rej = [int(v) for v in G["r_stats"]]
+    assert (res["I"], res["samples"], res["lo"], res["rejected"]) == (I, samples, lo, rej)
+    assert np.array_equal(res["inl"], G["r_inl"])
+    assert _h_close(res["H"], G["r_H"]) < 1e-9
+    assert abs(res["J"] - float(G["r_J"])) < 1e-9
+
+
+@pytest.mark.parametrize("seed,inl_frac,n", [(1, 0.6, 500), (2, 0.3, 800), (3, 0.9, 200), (7, 0.15, 1500), (11, 0.5, 20)])
+def test_ransac_h_vs_reference_build(ctx, reference, seed, inl_frac, n):
+    rng = np.random.default_rng(seed)
+    u = np.zeros((n, 6)); u[:, 0:2] = rng.random((n, 2)) * 800; u[:, 2] = 1; u[:, 5] = 1
+    Hgt = synth.gt_homography(800, 800)
+    p = (Hgt @ u[:, 0:3].T).T; u[:, 3:5] = p[:, :2] / p[:, 2:3] + rng.normal(size=(n, 2))
+    k = int(n * inl_frac)
+    u[k:, 3:5] = rng.random((n - k, 2)) * 800
+    for et in (0, 2):
+        r = reference.exp_ransacH(u, seed=seed * 17, errorType=et)
+        g = ctx.ransac_h(u, seed=seed * 17, errorType=et)
+        assert (g["I"], g["samples"], g["lo"], g["rejected"]) == (r["I"], r["samples"], r["lo"], r["rejected"])
+        assert np.array_equal(g["inl"], r["inl"])
+        assert _h_close(g["H"], r["H"]) < 1e-8
+
+
+def test_ransac_h_degenerate_inputs(ctx):
+    assert ctx.ransac_h(np.zeros((0, 6)))["I"] == 0
+    u = np.zeros((3, 6)); u[:, 2] = 1; u[:, 5] = 1
+    assert ctx.ransac_h(u)["I"] == 0
