@@ -83,6 +83,13 @@ void* mb2_ctx_stream(mb2_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long mb2_ctx_launch_count(const mb2_ctx* ctx);
 
+/* Per-kernel timing for bench.py's roofline: between begin and end every kernel launch of this context
+ * is bracketed by CUDA events on the context's stream.  end() writes "name\tlaunches\ttotal_ms\n" lines
+ * (plus "__extract_gather_bytes__", the algorithmic gather bytes of the patch extraction) into buf and
+ * returns the number of distinct kernels. */
+int mb2_ctx_profile_begin(mb2_ctx* ctx);
+int mb2_ctx_profile_end(mb2_ctx* ctx, char* buf, int buflen);
+
 /* ---- detection ------------------------------------------------------------------------- */
 /* Replaces the detector hook `int DetectAffineKeypoints(cv::Mat&, vector<AffineKeypoint>&,
  * ScaleSpaceDetectorParams, ScalePyramid&, tilt, zoom)` (scale-space-detector.hpp:231,

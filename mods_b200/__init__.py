@@ -12,11 +12,12 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmods_b200.so")
+HOST_LIB_PATH = os.path.join(HERE, "libmods_host.so")
 KP = 9
 EXPORTS = [
     "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view",
-    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level",
+    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end",
 ]
 
 
@@ -58,7 +59,7 @@ def build(force=False):
     """Compile libmods_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     if force and os.path.exists(LIB_PATH):
         os.remove(LIB_PATH)
-    subprocess.check_call(["make", "-C", HERE, "libmods_b200.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", HERE, "all"], stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 
@@ -76,6 +77,40 @@ def lib():
         _lib.mb2_ctx_stream.restype = C.c_void_p
         _lib.mb2_ctx_launch_count.restype = C.c_longlong
     return _lib
+
+
+_host = None
+
+
+def host_lib():
+    """libmods_host.so: the C++ mirror of the reference's plugin surface (mods_b200/host)."""
+    global _host
+    if _host is None:
+        lib()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise Mb2Error("libmods_host.so is not built")
+        _host = C.CDLL(HOST_LIB_PATH)
+    return _host
+
+
+class PairConfig(C.Structure):
+    _fields_ = [("det", HessaffParams), ("ori", OrientationParams), ("desc", SiftParams),
+                ("matchRatio", C.c_double), ("contradDist", C.c_double), ("duplicateDist", C.c_double),
+                ("err_threshold", C.c_double), ("confidence", C.c_double), ("HLAFCoef", C.c_double),
+                ("max_samples", C.c_int), ("errorType", C.c_int), ("doSymmCheck", C.c_int), ("seed", C.c_long)]
+
+    @staticmethod
+    def default():
+        c = PairConfig()
+        host_lib().mb2_pair_config_default(C.byref(c))
+        return c
+
+
+class PairResult(C.Structure):
+    _fields_ = [("regions1", C.c_int), ("regions2", C.c_int), ("tentatives", C.c_int), ("unique_tentatives", C.c_int),
+                ("ransac_inliers", C.c_int), ("verified", C.c_int), ("H", C.c_double * 9),
+                ("ms_detect_describe", C.c_double), ("ms_match", C.c_double), ("ms_duplicate", C.c_double),
+                ("ms_ransac", C.c_double), ("ms_total", C.c_double)]
 
 
 def _ptr(a):
@@ -125,6 +160,18 @@ class Context:
     @property
     def launches(self):
         return lib().mb2_ctx_launch_count(self.h)
+
+    def profile_begin(self):
+        self._check(lib().mb2_ctx_profile_begin(self.h), "profile_begin")
+
+    def profile_end(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._check(lib().mb2_ctx_profile_end(self.h, buf, C.c_int(len(buf))), "profile_end")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split("\t")
+            out[name] = (int(n), float(ms))
+        return out
 
     def pyramid_level(self, octave, level, want_resp=False):
         r, c = C.c_int(), C.c_int()
@@ -209,6 +256,17 @@ class Context:
         self._check(lib().mb2_score_models(self.h, C.c_int(which), _ptr(u), C.c_int(n), _ptr(models), C.c_int(K), C.c_double(th),
                                            _ptr(resid), _ptr(I), _ptr(J)), "score_models")
         return (I[:K], J[:K], resid) if want_resid else (I[:K], J[:K])
+
+    def mods_pair(self, img1, img2, cfg=None, shape1=None, shape2=None, capacity=0):
+        """One MODS iteration (mods.cpp:229-415) on a pair through the C++ host mirror."""
+        h1, w1 = shape1 if shape1 is not None else img1.shape
+        h2, w2 = shape2 if shape2 is not None else img2.shape
+        cfg = cfg or PairConfig.default()
+        res = PairResult()
+        out = np.zeros((max(1, capacity), 4)) if capacity else None
+        n = self._check(host_lib().mb2_mods_pair(self.h, _ptr(img1), C.c_int(w1), C.c_int(h1), _ptr(img2), C.c_int(w2), C.c_int(h2),
+                                                 C.byref(cfg), C.byref(res), _ptr(out), C.c_int(capacity)), "mods_pair")
+        return res, (out[:min(n, capacity)] if capacity else None)
 
     def ransac_h(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1):
         u = np.ascontiguousarray(u, np.float64)

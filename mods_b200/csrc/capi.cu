@@ -505,23 +505,26 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
   MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)n * 16 + 64 + cub_bytes + 64));
   unsigned long long* d_need = ctx->rs_a.as<unsigned long long>();
   unsigned long long* d_off = d_need + n;
-  unsigned long long* d_total = d_off + n;
-  int* d_toobig = (int*)(d_total + 1);
+  unsigned long long* d_total = d_off + n;        // [0] scratch floats, [1] sum of P2^2
+  int* d_toobig = (int*)(d_total + 2);
   void* cub_tmp = (void*)(((uintptr_t)(d_toobig + 2) + 15) & ~(uintptr_t)15);
-  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_toobig, 0, 8, ctx->stream));
-  mb2_describe_plan(ctx, d_keys, n, dp, taps.max_m, d_need, d_toobig);
+  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_total, 0, 16 + 8, ctx->stream));
+  mb2_describe_plan(ctx, d_keys, n, dp, taps.max_m, d_need, d_toobig, d_total + 1);
   MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, d_need, d_off, n, ctx->stream));
   ctx->launches += 1;
   MB2_LAUNCH(ctx, k_scan_offsets_total, 1, 32, 0, d_need, d_off, n, d_total);
-  unsigned long long total = 0; int toobig = 0;
-  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long total = 0, tot2[2] = {0, 0}; int toobig = 0;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(tot2, d_total, 16, cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&toobig, d_toobig, 4, cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  total = tot2[0];
+  // SURVEY 8d gather model: 4 bilinear taps x 4 B per sampled pixel ((P+2)^2 + 41^2 per region) + 128 B out
+  if (ctx->profiling) ctx->prof_extract_bytes += tot2[1] * 16ull + (unsigned long long)n * (1681ull * 16ull + 128ull);
   if (toobig) { ctx->set_error("describe: region larger than the tap table (m=" + std::to_string(toobig) + ")"); return MB2_ERR_CAPACITY; }
   if (total > ((size_t)24 << 30) / 4) { ctx->set_error("describe: patch scratch would exceed 24 GiB"); return MB2_ERR_CAPACITY; }
   // scratch = per-region sampling buffers, then n normalised 41x41 patches, photometric stats, bin-major votes
   const size_t f_patches = ((size_t)total + 31) & ~(size_t)31;
-  const size_t f_stats = f_patches + (size_t)n * 41 * 41;
+  const size_t f_stats = (f_patches + (size_t)n * 41 * 41 + 1) & ~(size_t)1;
   const size_t f_vec = (f_stats + (size_t)n * 2 + 1) & ~(size_t)1;
   MB2_CUDA_CHECK(ctx, ctx->patch_scratch.reserve((f_vec + (size_t)n * 128 * 2) * 4 + 64));
   MB2_CUDA_CHECK(ctx, ctx->desc_u8.reserve((size_t)n * 128));
@@ -642,6 +645,40 @@ const char* mb2_last_error(const mb2_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int mb2_ctx_sync(mb2_ctx* ctx) { MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return MB2_OK; }
 void* mb2_ctx_stream(mb2_ctx* ctx) { return (void*)ctx->stream; }
 long long mb2_ctx_launch_count(const mb2_ctx* ctx) { return ctx->launches; }
+
+int mb2_ctx_profile_begin(mb2_ctx* ctx) {
+  if (!ctx) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof.clear(); ctx->prof_extract_bytes = 0; ctx->profiling = true;
+  return MB2_OK;
+}
+
+int mb2_ctx_profile_end(mb2_ctx* ctx, char* buf, int buflen) {
+  if (!ctx || !buf || buflen <= 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ctx->profiling = false;
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<std::pair<std::string, std::pair<int, double> > > agg;
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    std::string name = r.name;
+    size_t lt = name.find('<');
+    bool found = false;
+    for (auto& a : agg) if (a.first == name) { a.second.first++; a.second.second += ms; found = true; break; }
+    if (!found) agg.push_back({name, {1, (double)ms}});
+    (void)lt;
+  }
+  ctx->prof.clear();
+  std::string out;
+  for (auto& a : agg) out += a.first + "\t" + std::to_string(a.second.first) + "\t" + std::to_string(a.second.second) + "\n";
+  out += "__extract_gather_bytes__\t1\t" + std::to_string((double)ctx->prof_extract_bytes) + "\n";
+  if ((int)out.size() + 1 > buflen) { ctx->set_error("profile_end: buffer too small"); return MB2_ERR_CAPACITY; }
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)agg.size();
+}
 
 int mb2_hessaff_detect(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_hessaff_params* par, double tilt, double zoom,
                        int as_regions, double* out_kp, int capacity) {

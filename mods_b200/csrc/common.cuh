@@ -74,6 +74,11 @@ struct mb2_ctx {
   HostBuf h_a, h_b, h_c;
   RegionSlot slots[MB2_MAX_SLOTS];
   void* tmap_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime
+  // optional per-kernel timing (mb2_ctx_profile_begin/end): CUDA events around every launch, on `stream`
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  unsigned long long prof_extract_bytes = 0;  // algorithmic gather bytes of the patch-extraction launches
   void set_error(const std::string& s) { err = s; }
 };
 
@@ -184,7 +189,13 @@ __device__ __forceinline__ void interpolate_row(const float* __restrict__ im, in
 // Launch bookkeeping
 #define MB2_LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
   do {                                                                     \
+    mb2_ctx::ProfRec _pr{#kernel, nullptr, nullptr};                       \
+    if ((ctx)->profiling) {                                                \
+      cudaEventCreate(&_pr.a); cudaEventCreate(&_pr.b);                    \
+      cudaEventRecord(_pr.a, (ctx)->stream);                               \
+    }                                                                      \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
+    if ((ctx)->profiling) { cudaEventRecord(_pr.b, (ctx)->stream); (ctx)->prof.push_back(_pr); } \
     (ctx)->launches++;                                                     \
   } while (0)
 

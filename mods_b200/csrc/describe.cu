@@ -53,12 +53,13 @@ __device__ __forceinline__ KpGeom kp_geom(const KeyOut& k, const DescribeParams&
 
 // scratch floats needed by region i: (P2*P2) sampled patch + (P2*NEED) row-pass columns
 __global__ void k_plan(const KeyOut* __restrict__ kps, int n, DescribeParams dp, int max_m, unsigned long long* __restrict__ need,
-                       int* __restrict__ too_big) {
+                       int* __restrict__ too_big, unsigned long long* __restrict__ sum_p2sq) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   KpGeom g = kp_geom(kps[i], dp);
   if (g.P2 > 0 && g.m > max_m) { atomicMax(too_big, g.m); }
   need[i] = g.P2 > 0 ? (unsigned long long)g.P2 * (unsigned long long)(g.P2 + NEED) : 0ull;
+  if (g.P2 > 0) atomicAdd(sum_p2sq, (unsigned long long)g.P2 * (unsigned long long)g.P2);
 }
 
 __global__ void __launch_bounds__(DT)
@@ -68,8 +69,10 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
   __shared__ float s_small[NEED * NEED]; // blurred patch at the needed rows x columns
   __shared__ int s_cols[NEED], s_rows[NEED];
 
-  const int kidx = blockIdx.x, tid = threadIdx.x;
-  if (kidx >= n) return;
+  // Regions arrive in detection order (fine octaves first), so the expensive large regions sit at the
+  // end of the list: walk it backwards so they are scheduled first and do not form a tail.
+  const int kidx = n - 1 - (int)blockIdx.x, tid = threadIdx.x;
+  if (kidx < 0) return;
   const KeyOut k = kps[kidx];
   const KpGeom g = kp_geom(k, dp);
   const float x = (float)k.v[0], y = (float)k.v[1];
@@ -338,9 +341,9 @@ k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __re
 using namespace MB2_NS;
 
 int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribeParams& dp, int max_m, unsigned long long* d_need,
-                      int* d_too_big) {
+                      int* d_too_big, unsigned long long* d_sum_p2sq) {
   if (!n) return MB2_OK;
-  MB2_LAUNCH(ctx, k_plan, (n + 127) / 128, 128, 0, kps, n, dp, max_m, d_need, d_too_big);
+  MB2_LAUNCH(ctx, k_plan, (n + 127) / 128, 128, 0, kps, n, dp, max_m, d_need, d_too_big, d_sum_p2sq);
   return MB2_OK;
 }
 

@@ -13,7 +13,7 @@ struct TapTable {
 };
 
 int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribeParams& dp, int max_m, unsigned long long* d_need,
-                      int* d_too_big);
+                      int* d_too_big, unsigned long long* d_sum_p2sq);
 int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
                                const DescTables* d_tables, const TapTable& taps, const unsigned long long* d_off, float* d_scratch,
                                uint8_t* d_desc, float* d_patches /* n x 41 x 41, required */, float2* d_stats /* n */,

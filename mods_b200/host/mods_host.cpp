@@ -1,0 +1,428 @@
+// Host-side mirror of the reference's plugin surface (see mods_host.hpp).  Everything numeric runs
+// in libmods_b200.so through the C ABI; what stays here is what the reference also does in host C++:
+// region bookkeeping, the O(T) (grid-accelerated, same result) duplicate filter and the small
+// post-RANSAC checks.
+#include "mods_host.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <ctime>
+#include <unordered_map>
+
+namespace mods {
+
+namespace {
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+const char* kDetectorNames[] = {"HessianAffine", "DoG", "HarrisAffine", "MSER"};  // detectors/structures.hpp:39-44 (prefix)
+AffineKeypoint kp_from(const double* v) {
+  AffineKeypoint k;
+  k.x = v[0]; k.y = v[1]; k.a11 = v[2]; k.a12 = v[3]; k.a21 = v[4]; k.a22 = v[5]; k.s = v[6]; k.response = v[7];
+  k.sub_type = (int)v[8]; k.octave_number = 0; k.pyramid_scale = 0;
+  return k;
+}
+}  // namespace
+
+DetectorsParameters::DetectorsParameters() {
+  // [HessianAffine] of config_iter_mods_cviu.ini
+  HessParam = mb2_hessaff_params{5.3333f, 3, 1.6f, 10.0f, 5, 16, 0.05f, 19, 1, 0, 2000, -1.f, -1.f, 41, 3.0f * std::sqrt(3.0f)};
+}
+DescriptorsParameters::DescriptorsParameters() {
+  SIFTParam = mb2_sift_params{5.1962, 41, 1, 0, 0};
+  RootSIFTParam = mb2_sift_params{5.1962, 41, 1, 1, 0};
+}
+
+// ---- ImageRepresentation ------------------------------------------------------------------------
+ImageRepresentation::ImageRepresentation(mb2_ctx* c, GrayImage img, std::string name, int device_slot)
+    : OriginalImg(img), ctx(c), Name(name), slot(device_slot) {}
+
+descriptor_type ImageRepresentation::GetDescriptorType(std::string n) const {
+  if (n == "SIFT") return DESC_SIFT;
+  if (n == "RootSIFT") return DESC_ROOT_SIFT;
+  return DESC_UNKNOWN;
+}
+detector_type ImageRepresentation::GetDetectorType(std::string n) const {
+  for (int i = 0; i < 4; i++) if (n == kDetectorNames[i]) return (detector_type)i;
+  return DET_UNKNOWN;
+}
+int ImageRepresentation::GetRegionsNumber(std::string det_name) const {  // imagerepresentation.cpp:264-283
+  int n = 0;
+  for (auto& d : RegionVectorMap) {
+    if (det_name != "All" && d.first != det_name) continue;
+    auto it = d.second.find("None");
+    if (it != d.second.end()) n += (int)it->second.size();
+  }
+  return n;
+}
+int ImageRepresentation::GetDescriptorsNumber(std::string desc_name, std::string det_name) const {  // :284-330
+  int n = 0;
+  for (auto& d : RegionVectorMap) {
+    if (det_name != "All" && d.first != det_name) continue;
+    for (auto& e : d.second) if (desc_name == "All" || e.first == desc_name) n += (int)e.second.size();
+  }
+  return n;
+}
+AffineRegionVector ImageRepresentation::GetAffineRegionVector(std::string desc_name, std::string det_name) const {  // :420-437
+  auto d = RegionVectorMap.find(det_name);
+  if (d == RegionVectorMap.end()) return AffineRegionVector();
+  auto e = d->second.find(desc_name);
+  if (e == d->second.end()) return AffineRegionVector();
+  return e->second;
+}
+void ImageRepresentation::AddRegions(AffineRegionVector& add, std::string det_name, std::string desc_name) {  // :566-600
+  AffineRegionVector& dst = RegionVectorMap[det_name][desc_name];
+  const int size = (int)dst.size();
+  dst.reserve(dst.size() + add.size());
+  for (AffineRegion r : add) { r.id += size; r.parent_id += size; dst.push_back(std::move(r)); }
+}
+
+void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisParam& synth_par, DetectorsParameters& det_par,
+                                                       DescriptorsParameters& desc_par, DominantOrientationParams& dom_ori_par) {
+  // imagerepresentation.cpp:603-2047, HessianAffine branch (:717-720) with SIFT-like descriptors (:1254-1341).
+  // Views other than the identity need GenerateSynthImageCorr (not built): skipped.
+  for (int det = 0; det < 4; det++) {
+    const std::string curr_det = kDetectorNames[det];
+    auto it = synth_par.find(curr_det);
+    if (it == synth_par.end() || curr_det != "HessianAffine") continue;
+    std::vector<AffineRegionVectorMap> perView(it->second.size());
+    for (size_t synth = 0; synth < it->second.size(); synth++) {
+      const ViewSynthParameters& v = it->second[synth];
+      const bool identity = (std::fabs(v.tilt - 1.) <= 0.1) && (std::fabs(v.phi) <= 0.2) && (std::fabs(v.zoom - 1.) <= 0.1);  // synth-detection.cpp:278
+      if (!identity) continue;
+      const double H[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      for (const std::string& curr_desc : v.descriptors) {
+        const descriptor_type dt = GetDescriptorType(curr_desc);
+        if (dt == DESC_UNKNOWN) continue;
+        mb2_sift_params sp = (dt == DESC_ROOT_SIFT) ? desc_par.RootSIFTParam : desc_par.SIFTParam;
+        mb2_orientation_params op{dom_ori_par.mrSize, dom_ori_par.patchSize, dom_ori_par.maxAngles, (double)dom_ori_par.threshold};
+        const double t0 = now_ms();
+        const int cap = std::max(4096, OriginalImg.rows * OriginalImg.cols / 16);
+        std::vector<double> det_kp((size_t)cap * MB2_KP), rep_kp((size_t)cap * MB2_KP);
+        std::vector<uint8_t> desc((size_t)cap * MB2_DESC_DIM);
+        const bool use_slot = slot >= 0 && (slot_desc.empty() || slot_desc == curr_desc);
+        int n = mb2_detect_describe_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
+                                         &det_par.HessParam, &op, &sp, use_slot ? slot : MB2_MAX_SLOTS - 1, use_slot && slot_count > 0,
+                                         det_kp.data(), rep_kp.data(), desc.data(), cap);
+        if (n < 0) continue;  // failures are silent, like the reference (empty lists)
+        if (use_slot) { slot_desc = curr_desc; slot_count += n; }
+        AffineRegionVector regs((size_t)n);
+        for (int i = 0; i < n; i++) {
+          AffineRegion& r = regs[i];
+          r.img_id = (int)synth; r.img_reproj_id = 0; r.id = 0; r.parent_id = 0; r.type = DET_HESSIAN;  // ids carry no information
+          r.det_kp = kp_from(&det_kp[(size_t)i * MB2_KP]);
+          r.reproj_kp = kp_from(&rep_kp[(size_t)i * MB2_KP]);
+          r.desc.type = dt;
+          r.desc.vec.assign(desc.begin() + (size_t)i * 128, desc.begin() + (size_t)(i + 1) * 128);
+        }
+        perView[synth][curr_desc] = std::move(regs);
+        TimeSpent.DetectTime += (now_ms() - t0) / 1000.0;  // detect + orient + describe are one fused call here
+      }
+    }
+    for (auto& m : perView) for (auto& e : m) AddRegions(e.second, curr_det, e.first);
+  }
+}
+
+// ---- matching ---------------------------------------------------------------------------------
+namespace {
+void fill_tentatives(const double* rows, int n, const AffineRegionList& list1, const AffineRegionList& list2, TentativeCorrespListExt& out) {
+  out.TCList.reserve(out.TCList.size() + n);
+  auto light = [](const AffineRegion& r) { AffineRegion c; c.img_id = r.img_id; c.img_reproj_id = r.img_reproj_id; c.id = r.id;
+                                           c.parent_id = r.parent_id; c.type = r.type; c.det_kp = r.det_kp; c.reproj_kp = r.reproj_kp;
+                                           c.desc.type = r.desc.type; return c; };
+  for (int i = 0; i < n; i++) {
+    const double* r = rows + (size_t)i * 7;
+    TentativeCorrespExt t;
+    t.first = light(list1[(int)r[0]]);
+    t.second = light(list2[(int)r[1]]);
+    t.secondbad = light(list2[(int)r[2]]);
+    t.secondbadby2ndcl = light(list2[(int)r[3]]);
+    t.d1 = r[4]; t.d2 = r[5]; t.d2by2ndcl = r[6];
+    t.ratio = std::sqrt((double)((float)r[4] / (float)r[5]));  // sqrt(ratio), ratio = float d0 / float dJ (matching.cpp:435,448)
+    out.TCList.push_back(std::move(t));
+  }
+}
+}  // namespace
+
+int MatchFlannFGINN(mb2_ctx* ctx, const AffineRegionList& list1, const AffineRegionList& list2, TentativeCorrespListExt& corresp,
+                    const MatchPars& par, const int nn) {
+  if (list1.empty() || list2.empty()) return 0;
+  std::vector<uint8_t> q(list1.size() * 128), t(list2.size() * 128);
+  std::vector<double> txy(list2.size() * 2);
+  for (size_t i = 0; i < list1.size(); i++) for (int j = 0; j < 128; j++) q[i * 128 + j] = (uint8_t)list1[i].desc.vec[j];
+  for (size_t i = 0; i < list2.size(); i++) {
+    for (int j = 0; j < 128; j++) t[i * 128 + j] = (uint8_t)list2[i].desc.vec[j];
+    txy[2 * i] = list2[i].reproj_kp.x; txy[2 * i + 1] = list2[i].reproj_kp.y;
+  }
+  std::vector<double> rows(list1.size() * 7);
+  int n = mb2_match_fginn(ctx, q.data(), (int)list1.size(), t.data(), (int)list2.size(), txy.data(), par.currMatchRatio, par.contradDist, nn,
+                          rows.data(), (int)list1.size());
+  if (n < 0) return 0;
+  fill_tentatives(rows.data(), n, list1, list2, corresp);
+  return n;
+}
+
+int CorrespondenceBank::GetCorrespondencesNumber(std::string desc_name, std::string det_name) const {
+  int n = 0;
+  for (auto& d : CorrespondencesMapMap) {
+    if (desc_name != "All" && d.first != desc_name) continue;
+    for (auto& e : d.second) if (det_name == "All" || e.first == det_name) n += (int)e.second.TCList.size();
+  }
+  return n;
+}
+TentativeCorrespListExt CorrespondenceBank::GetCorresponcesVector(std::string desc_name, std::string det_name) const {
+  TentativeCorrespListExt out;
+  for (auto& d : CorrespondencesMapMap) {
+    if (desc_name != "All" && d.first != desc_name) continue;
+    for (auto& e : d.second)
+      if (det_name == "All" || e.first == det_name) out.TCList.insert(out.TCList.end(), e.second.TCList.begin(), e.second.TCList.end());
+  }
+  return out;
+}
+void CorrespondenceBank::ClearCorrespondences(std::string det_name, std::string desc_name) {
+  auto d = CorrespondencesMapMap.find(desc_name);
+  if (d == CorrespondencesMapMap.end()) return;
+  auto e = d->second.find(det_name);
+  if (e != d->second.end()) e->second.TCList.clear();
+}
+
+int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresentation& imgrep2, IterationViewsynthesisParam& synth_par,
+                                     const WhatToMatch WhatToMatchNow, const MatchPars& par, const DescriptorsParameters&) {
+  // correspondencebank.cpp:237-351, "individual detectors" loop (:291-347); the grouped loop (:248-289)
+  // matches concatenated lists the same way.
+  for (const std::string& curr_det : WhatToMatchNow.separate_detectors) {
+    auto vs = synth_par.find(curr_det);
+    if (vs == synth_par.end() || vs->second.empty()) continue;
+    const ViewSynthParameters& current_VS_params = vs->second[0];
+    for (const std::string& curr_desc : WhatToMatchNow.separate_descriptors) {
+      ClearCorrespondences(curr_det, curr_desc);
+      MatchPars cur = par;
+      auto th = current_VS_params.FGINNThreshold.find(curr_desc);
+      cur.currMatchRatio = th != current_VS_params.FGINNThreshold.end() ? th->second : 0;
+      if (!(cur.currMatchRatio > 0)) continue;
+      TentativeCorrespListExt tents;
+      auto d1 = imgrep1.RegionVectorMap.find(curr_det), d2 = imgrep2.RegionVectorMap.find(curr_det);
+      if (d1 == imgrep1.RegionVectorMap.end() || d2 == imgrep2.RegionVectorMap.end()) continue;
+      const AffineRegionVector& queries = d1->second[curr_desc];
+      const AffineRegionVector& trains = d2->second[curr_desc];
+      const bool resident = curr_det == "HessianAffine" && imgrep1.slot >= 0 && imgrep2.slot >= 0 && imgrep1.slot_desc == curr_desc &&
+                            imgrep2.slot_desc == curr_desc && imgrep1.slot_count == (int)queries.size() &&
+                            imgrep2.slot_count == (int)trains.size();
+      if (resident) {  // descriptors are still on the device in exactly this order: no re-upload
+        std::vector<double> rows(std::max<size_t>(1, queries.size()) * 7);
+        int n = mb2_match_slots(ctx, imgrep1.slot, imgrep2.slot, cur.currMatchRatio, cur.contradDist, 50, rows.data(), (int)queries.size());
+        if (n > 0) fill_tentatives(rows.data(), n, queries, trains, tents);
+      } else {
+        MatchFlannFGINN(ctx, queries, trains, tents, cur);
+      }
+      CorrespondencesMapMap[curr_desc][curr_det] = std::move(tents);
+    }
+  }
+  return 0;
+}
+
+// ---- DuplicateFiltering (matching.cpp:2983-3047) -------------------------------------------------
+// The reference's O(T^2) double loop keeps i and drops every later j whose endpoints are both within r
+// of i's.  The kept set is decided greedily in list order, so a uniform grid over the first image's
+// coordinates (cell = r) gives the identical result in O(T).  (std::sort in the reference is unstable;
+// ties in the sort key keep their input order here.)
+void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, const int mode) {
+  if (r <= 0) return;
+  std::vector<TentativeCorrespExt>& L = in_corresp.TCList;
+  switch (mode) {
+    case MODE_FGINN: std::stable_sort(L.begin(), L.end(), [](const TentativeCorrespExt& a, const TentativeCorrespExt& b) { return std::fabs(a.ratio) < std::fabs(b.ratio); }); break;
+    case MODE_DISTANCE: std::stable_sort(L.begin(), L.end(), [](const TentativeCorrespExt& a, const TentativeCorrespExt& b) { return std::fabs(a.d1) < std::fabs(b.d1); }); break;
+    case MODE_BIGGER_REGION: std::stable_sort(L.begin(), L.end(), [](const TentativeCorrespExt& a, const TentativeCorrespExt& b) { return std::fabs(a.first.reproj_kp.s) < std::fabs(b.first.reproj_kp.s); }); break;
+    default: break;
+  }
+  const double r_sq = r * r;
+  std::unordered_map<long long, std::vector<int> > grid;
+  grid.reserve(L.size() * 2);
+  auto cell = [&](double x, double y) { return ((long long)std::floor(x / r) << 32) ^ ((long long)std::floor(y / r) & 0xffffffffLL); };
+  std::vector<char> keep(L.size(), 1);
+  for (size_t j = 0; j < L.size(); j++) {
+    const double x1 = L[j].first.reproj_kp.x, y1 = L[j].first.reproj_kp.y, x2 = L[j].second.reproj_kp.x, y2 = L[j].second.reproj_kp.y;
+    const long long cx = (long long)std::floor(x1 / r), cy = (long long)std::floor(y1 / r);
+    bool dup = false;
+    for (long long dx = -1; dx <= 1 && !dup; dx++)
+      for (long long dy = -1; dy <= 1 && !dup; dy++) {
+        auto it = grid.find(((cx + dx) << 32) ^ ((cy + dy) & 0xffffffffLL));
+        if (it == grid.end()) continue;
+        for (int i : it->second) {
+          double ddx = L[i].first.reproj_kp.x - x1, ddy = L[i].first.reproj_kp.y - y1;
+          if (ddx * ddx + ddy * ddy > r_sq) continue;
+          ddx = L[i].second.reproj_kp.x - x2; ddy = L[i].second.reproj_kp.y - y2;
+          if (ddx * ddx + ddy * ddy <= r_sq) { dup = true; break; }
+        }
+      }
+    if (dup) keep[j] = 0; else grid[cell(x1, y1)].push_back((int)j);
+  }
+  size_t w = 0;
+  for (size_t j = 0; j < L.size(); j++) if (keep[j]) { if (w != j) L[w] = std::move(L[j]); w++; }
+  L.resize(w);
+}
+
+// ---- LORANSACFiltering (matching.cpp:806-980), homography mode -------------------------------------
+namespace {
+bool invert3(const double* S, double* D) {  // cv::invert, 3x3 closed form
+  double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+  if (d == 0) { for (int i = 0; i < 9; i++) D[i] = 0; return false; }
+  d = 1. / d;
+  D[0] = (S[4] * S[8] - S[5] * S[7]) * d; D[1] = (S[2] * S[7] - S[1] * S[8]) * d; D[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+  D[3] = (S[5] * S[6] - S[3] * S[8]) * d; D[4] = (S[0] * S[8] - S[2] * S[6]) * d; D[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+  D[6] = (S[3] * S[7] - S[4] * S[6]) * d; D[7] = (S[1] * S[6] - S[0] * S[7]) * d; D[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+  return true;
+}
+int NaiveHCheck(const TentativeCorrespListExt& corresp, const double* H, const double error) {  // matching.cpp:1171-1200
+  const double err_sq = error * error;
+  double Hinv[9];
+  invert3(H, Hinv);
+  int corr_numb = 0;
+  for (const TentativeCorrespExt& t : corresp.TCList) {
+    const double x1 = t.first.reproj_kp.x, y1 = t.first.reproj_kp.y, x2 = t.second.reproj_kp.x, y2 = t.second.reproj_kp.y;
+    double xa = (H[0] * x1 + H[1] * y1 + H[2]) / (H[6] * x1 + H[7] * y1 + H[8]);
+    double ya = (H[3] * x1 + H[4] * y1 + H[5]) / (H[6] * x1 + H[7] * y1 + H[8]);
+    const double d1 = (x2 - xa) * (x2 - xa) + (y2 - ya) * (y2 - ya);
+    xa = (Hinv[0] * x2 + Hinv[1] * y2 + Hinv[2]) / (Hinv[6] * x2 + Hinv[7] * y2 + Hinv[8]);
+    ya = (Hinv[3] * x2 + Hinv[4] * y2 + Hinv[5]) / (Hinv[6] * x2 + Hinv[7] * y2 + Hinv[8]);
+    const double d2 = (x1 - xa) * (x1 - xa) + (y1 - ya) * (y1 - ya);
+    if ((d1 <= err_sq) && (d2 <= (err_sq))) corr_numb++;
+  }
+  return corr_numb;
+}
+}  // namespace
+
+int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp, double* H,
+                      const RANSACPars pars) {
+  const int MIN_POINTS = 8;
+  const unsigned tent_size = (unsigned)in_corresp.TCList.size();
+  ransac_corresp.TCList.clear();
+  int max_samples = pars.max_samples;
+  if (tent_size <= 20) max_samples = 1000;
+  if (pars.useF) return 0;  // epipolar mode (exp_ransacFcustom) is not built: empty output, like a failed run
+  if (tent_size < (unsigned)MIN_POINTS) return 0;
+  std::vector<double> u((size_t)tent_size * 6);
+  for (unsigned i = 0; i < tent_size; i++) {
+    const TentativeCorrespExt& t = in_corresp.TCList[i];
+    double* p = &u[(size_t)i * 6];
+    p[0] = t.first.reproj_kp.x; p[1] = t.first.reproj_kp.y; p[2] = 1.; p[3] = t.second.reproj_kp.x; p[4] = t.second.reproj_kp.y; p[5] = 1.;
+  }
+  double Hloran[9];
+  std::vector<unsigned char> inl(tent_size);
+  int data_out[3];
+  double J = 0;
+  const long seed = pars.seed ? pars.seed : (long)time(NULL);
+  int I = mb2_ransac_h(ctx, u.data(), (int)tent_size, pars.err_threshold * pars.err_threshold, pars.confidence, max_samples,
+                       (int)pars.errorType, pars.doSymmCheck, seed, Hloran, inl.data(), data_out, &J);
+  if (I < 0) return 0;
+  for (unsigned i = 0; i < tent_size; i++) {
+    in_corresp.TCList[i].isTrue = inl[i];
+    if (inl[i] || pars.justMarkOutliers) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
+  }
+  // H = inv(Hloran^T) (matching.cpp:920-938)
+  const double Ht[9] = {Hloran[0], Hloran[3], Hloran[6], Hloran[1], Hloran[4], Hloran[7], Hloran[2], Hloran[5], Hloran[8]};
+  double Hinv[9];
+  invert3(Ht, Hinv);
+  bool nonzero = false;
+  for (int i = 0; i < 9; i++) nonzero = nonzero || (Hinv[i] != 0.0);
+  if (!nonzero) { ransac_corresp.TCList.clear(); return 0; }
+  for (int i = 0; i < 9; i++) { ransac_corresp.H[i] = Hinv[i]; H[i] = Hinv[i]; }
+  if (NaiveHCheck(ransac_corresp, ransac_corresp.H, 10.0) < MIN_POINTS) ransac_corresp.TCList.clear();  // DO_TRANSFER_H_CHECK
+  // H_LAF_check (matching.cpp:251-309): three points per local affine frame scored with HDsSymMax in one batch
+  const double affineFerror = 3.0 * pars.HLAFCoef * pars.err_threshold;
+  if (affineFerror > 0 && !ransac_corresp.TCList.empty()) {
+    const double k_sigma = 3.0;  // matching.cpp:172
+    const size_t n = ransac_corresp.TCList.size();
+    std::vector<double> u3(n * 18), err(n * 3);
+    for (size_t l = 0; l < n; l++) {
+      const TentativeCorrespExt& t = ransac_corresp.TCList[l];
+      double* q = &u3[l * 18];
+      q[0] = t.first.reproj_kp.x; q[1] = t.first.reproj_kp.y; q[2] = 1.0;
+      q[3] = t.second.reproj_kp.x; q[4] = t.second.reproj_kp.y; q[5] = 1.0;
+      q[6] = q[0] + k_sigma * t.first.reproj_kp.a12 * t.first.reproj_kp.s; q[7] = q[1] + k_sigma * t.first.reproj_kp.a22 * t.first.reproj_kp.s; q[8] = 1.0;
+      q[9] = q[3] + k_sigma * t.second.reproj_kp.a12 * t.second.reproj_kp.s; q[10] = q[4] + k_sigma * t.second.reproj_kp.a22 * t.second.reproj_kp.s; q[11] = 1.0;
+      q[12] = q[0] + k_sigma * t.first.reproj_kp.a11 * t.first.reproj_kp.s; q[13] = q[1] + k_sigma * t.first.reproj_kp.a21 * t.first.reproj_kp.s; q[14] = 1.0;
+      q[15] = q[3] + k_sigma * t.second.reproj_kp.a11 * t.second.reproj_kp.s; q[16] = q[4] + k_sigma * t.second.reproj_kp.a21 * t.second.reproj_kp.s; q[17] = 1.0;
+    }
+    if (mb2_score_models(ctx, 2 /*HDsSymMax*/, u3.data(), (int)(n * 3), Hloran, 1, 0.0, err.data(), nullptr, nullptr) < 0) return 0;
+    std::vector<TentativeCorrespExt> good;
+    good.reserve(n);
+    for (size_t l = 0; l < n; l++) {
+      const double sumErr = std::sqrt(err[3 * l] + err[3 * l + 1] + err[3 * l + 2]);
+      if (!(sumErr > affineFerror)) good.push_back(ransac_corresp.TCList[l]);
+    }
+    ransac_corresp.TCList.swap(good);
+  }
+  if ((int)ransac_corresp.TCList.size() < MIN_POINTS) ransac_corresp.TCList.clear();
+  return (int)ransac_corresp.TCList.size();
+}
+
+}  // namespace mods
+
+// ---- one MODS iteration on one pair ---------------------------------------------------------------
+extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
+  mods::DetectorsParameters dp; mods::DescriptorsParameters sp;
+  c->det = dp.HessParam;
+  c->ori = mb2_orientation_params{1.0, 41, 1, 0.8};
+  c->desc = sp.RootSIFTParam;
+  c->matchRatio = 0.8; c->contradDist = 30.0; c->duplicateDist = 2.0;              // iters_mods_cviu.ini:62, config_iter_mods_cviu.ini:151,157
+  c->err_threshold = 3.0; c->confidence = 0.99; c->HLAFCoef = 12.0;                // config_iter_mods_cviu.ini:163-172
+  c->max_samples = 100000; c->errorType = 0; c->doSymmCheck = 1;
+  c->seed = 1;
+}
+
+extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
+                             const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity) {
+  using namespace mods;
+  if (!ctx || !img1 || !img2 || !cfg || !res) return MB2_ERR_ARG;
+  std::memset(res, 0, sizeof *res);
+  const double t_start = now_ms();
+  // Config (what getCLIparam would read from config_iter_mods_cviu.ini / an iters file with one HessianAffine tier)
+  DetectorsParameters det_par; det_par.HessParam = cfg->det;
+  DescriptorsParameters desc_par; desc_par.RootSIFTParam = cfg->desc; desc_par.SIFTParam = cfg->desc;
+  DominantOrientationParams dom; dom.maxAngles = cfg->ori.maxAngles; dom.threshold = (float)cfg->ori.threshold; dom.mrSize = cfg->ori.mrSize;
+  dom.patchSize = cfg->ori.patchSize;
+  const std::string desc_name = cfg->desc.rootSIFT ? "RootSIFT" : "SIFT";
+  IterationViewsynthesisParam iters;
+  ViewSynthParameters v; v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = cfg->matchRatio;
+  iters["HessianAffine"].push_back(v);
+  WhatToMatch wtm; wtm.separate_detectors.push_back("HessianAffine"); wtm.separate_descriptors.push_back(desc_name);
+  MatchPars mp; mp.contradDist = cfg->contradDist;
+  RANSACPars rp; rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
+  rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
+
+  // mods.cpp:229-415, one step
+  ImageRepresentation ImgRep1(ctx, GrayImage{img1, h1, w1}, "img1", 0), ImgRep2(ctx, GrayImage{img2, h2, w2}, "img2", 1);
+  double t0 = now_ms();
+  ImgRep1.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+  ImgRep2.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+  res->ms_detect_describe = now_ms() - t0;
+  res->regions1 = ImgRep1.GetDescriptorsNumber(desc_name); res->regions2 = ImgRep2.GetDescriptorsNumber(desc_name);
+  t0 = now_ms();
+  CorrespondenceBank Tentatives(ctx);
+  Tentatives.MatchImgReps(ImgRep1, ImgRep2, iters, wtm, mp, desc_par);
+  TentativeCorrespListExt tentatives = Tentatives.GetCorresponcesVector();
+  res->ms_match = now_ms() - t0;
+  res->tentatives = (int)tentatives.TCList.size();
+  t0 = now_ms();
+  DuplicateFiltering(tentatives, cfg->duplicateDist, MODE_FGINN);   // whichCorrespondenceRemains=bestFGINN
+  res->ms_duplicate = now_ms() - t0;
+  res->unique_tentatives = (int)tentatives.TCList.size();
+  t0 = now_ms();
+  TentativeCorrespListExt verified;
+  int n = LORANSACFiltering(ctx, tentatives, verified, verified.H, rp);
+  res->ms_ransac = now_ms() - t0;
+  for (const auto& t : tentatives.TCList) res->ransac_inliers += t.isTrue;
+  res->verified = n;
+  for (int i = 0; i < 9; i++) res->H[i] = verified.H[i];
+  if (verified_out)
+    for (int i = 0; i < n && i < capacity; i++) {
+      const auto& t = verified.TCList[i];
+      verified_out[4 * i] = t.first.reproj_kp.x; verified_out[4 * i + 1] = t.first.reproj_kp.y;
+      verified_out[4 * i + 2] = t.second.reproj_kp.x; verified_out[4 * i + 3] = t.second.reproj_kp.y;
+    }
+  res->ms_total = now_ms() - t_start;
+  return n;
+}

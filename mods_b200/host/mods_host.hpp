@@ -1,0 +1,173 @@
+// Host-side mirror of the reference's plugin surface for the hot path, on top of the C ABI
+// (include/mods_b200.h).  Same type / method names, argument meaning and error behaviour as the
+// reference, so that mods.cpp's iteration loop (mods.cpp:229-415) reads the same:
+//
+//   ImageRepresentation::SynthDetectDescribeKeypoints   imagerepresentation.h:44-47, .cpp:603-2047
+//   CorrespondenceBank::MatchImgReps                    correspondencebank.h:29-31, .cpp:237-351
+//   MatchFlannFGINN                                     matching/matching.hpp:268-269, .cpp:357-461
+//   DuplicateFiltering                                  matching/matching.hpp:300, .cpp:2983-3047
+//   LORANSACFiltering (+ NaiveHCheck, H_LAF_check)      matching/matching.hpp:284-286, .cpp:806-980, 1171-1200, 251-309
+//
+// cv::Mat is replaced by a plain float image; everything else keeps the reference's layout
+// (detectors/structures.hpp:187-245).  Only the HessianAffine detector and the SIFT / RootSIFT
+// descriptors are wired (the other branches are out of scope); unknown detector or
+// descriptor names are skipped silently, exactly as the reference skips detectors that have no
+// views configured.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mods_b200.h"
+
+namespace mods {
+
+enum detector_type { DET_HESSIAN = 0, DET_DOG = 1, DET_HARRIS = 2, DET_MSER = 3, DET_UNKNOWN = 1000 };
+enum descriptor_type { DESC_SIFT = 0, DESC_ROOT_SIFT = 1, DESC_UNKNOWN = 1000 };
+enum RANSAC_error_t { SAMPSON, SYMM_MAX, SYMM_SUM };
+const int MODE_RANDOM = 0, MODE_FGINN = 1, MODE_DISTANCE = 2, MODE_BIGGER_REGION = 3;  // configuration.hpp:31-34
+
+struct GrayImage {  // stands in for the CV_32F cv::Mat OriginalImg (gray = (B+G+R)/3, synth-detection.cpp:256-263)
+  const float* data = nullptr;  // host or device pointer, row-major, cols floats per row
+  int rows = 0, cols = 0;
+};
+
+struct AffineKeypoint {  // detectors/structures.hpp:187-196
+  double x, y;
+  double a11, a12, a21, a22;
+  double s;
+  double response;
+  int octave_number;
+  double pyramid_scale;
+  int sub_type;
+};
+struct ViewSynthParameters {  // detectors/structures.hpp:198-211
+  double zoom = 1.0, tilt = 1.0, phi = 0.0, InitSigma = 0.5;
+  int doBlur = 1, DSPlevels = 0;
+  double minSigma = 1.0, maxSigma = 1.0;
+  std::vector<std::string> descriptors;
+  std::map<std::string, double> FGINNThreshold;
+  std::map<std::string, double> DistanceThreshold;
+};
+typedef std::map<std::string, std::vector<ViewSynthParameters> > IterationViewsynthesisParam;
+struct Descriptor { descriptor_type type = DESC_UNKNOWN; std::vector<float> vec; };
+struct AffineRegion {  // detectors/structures.hpp:219-230
+  int img_id = 0, img_reproj_id = 0, id = 0, parent_id = 0;
+  detector_type type = DET_UNKNOWN;
+  AffineKeypoint det_kp, reproj_kp;
+  Descriptor desc;
+};
+typedef std::vector<AffineRegion> AffineRegionVector;
+typedef std::vector<AffineRegion> AffineRegionList;
+typedef std::map<std::string, AffineRegionVector> AffineRegionVectorMap;
+
+struct WhatToMatch {  // detectors/structures.hpp:247-253
+  std::vector<std::string> group_detectors, group_descriptors, separate_detectors, separate_descriptors;
+};
+struct TimeLog {  // detectors/structures.hpp:51-74
+  double SynthTime = 0, DetectTime = 0, OrientTime = 0, DescTime = 0, MatchingTime = 0, RANSACTime = 0, MiscTime = 0, TotalTime = 0;
+};
+
+struct DetectorsParameters { mb2_hessaff_params HessParam; DetectorsParameters(); };
+struct DescriptorsParameters { mb2_sift_params SIFTParam, RootSIFTParam; DescriptorsParameters(); };
+struct DominantOrientationParams {  // descriptors_parameters.hpp:23-36 + [DominantOrientation]
+  int maxAngles = 1; float threshold = 0.8f; bool addUpRight = false; bool halfSIFTMode = false;
+  double mrSize = 1.0; int patchSize = 41;
+};
+
+struct TentativeCorrespExt {  // matching/matching.hpp:35-52.  Regions are carried WITHOUT their descriptor payload.
+  AffineRegion first, second, secondbadby2ndcl, secondbad;
+  double d1 = 0, d2 = 0, d2by2ndcl = 0, d2byDB = 0, ratio = 0;
+  int isTrue = 0;
+};
+struct TentativeCorrespListExt {
+  std::vector<TentativeCorrespExt> TCList;
+  double H[9];
+  TentativeCorrespListExt() { for (int i = 0; i < 9; i++) H[i] = -1; }
+};
+struct MatchPars {  // matching/matching.hpp:99-144 (the fields the float path reads)
+  std::map<std::string, double> FGINNThreshold, DistanceThreshold;
+  double currMatchRatio = -1.0, matchDistanceThreshold = 0, contradDist = 10.0;
+  int minMatches = 15, maxSteps = 4;
+};
+struct RANSACPars {  // matching/matching.hpp:146-171
+  int useF = 0;
+  double err_threshold = 2.0, confidence = 0.99;
+  int max_samples = 100000, localOptimization = 1;
+  double LAFCoef = 3.0, HLAFCoef = 10.0;
+  RANSAC_error_t errorType = SYMM_SUM;
+  int doSymmCheck = 0, justMarkOutliers = 0;
+  long seed = 0;  // 0 => time(NULL) like the reference (exp_ranH.c:823); anything else is used as the srand seed
+};
+
+class CorrespondenceBank;
+
+class ImageRepresentation {
+ public:
+  ImageRepresentation(mb2_ctx* ctx, GrayImage img, std::string name, int device_slot);
+  descriptor_type GetDescriptorType(std::string desc_name) const;
+  detector_type GetDetectorType(std::string det_name) const;
+  TimeLog GetTimeSpent() const { return TimeSpent; }
+  int GetRegionsNumber(std::string det_name = "All") const;
+  int GetDescriptorsNumber(std::string desc_name = "All", std::string det_name = "All") const;
+  AffineRegionVector GetAffineRegionVector(std::string desc_name, std::string det_name) const;
+  void SynthDetectDescribeKeypoints(IterationViewsynthesisParam& synth_par, DetectorsParameters& det_par,
+                                    DescriptorsParameters& desc_par, DominantOrientationParams& dom_ori_par);
+  GrayImage OriginalImg;
+
+ protected:
+  friend class CorrespondenceBank;
+  void AddRegions(AffineRegionVector& RegionsToAdd, std::string det_name, std::string desc_name);
+  mb2_ctx* ctx;
+  TimeLog TimeSpent;
+  std::map<std::string, AffineRegionVectorMap> RegionVectorMap;
+  std::string Name;
+  int slot;                 // device-resident copy of RegionVectorMap["HessianAffine"][desc] for the matcher
+  std::string slot_desc;    // which descriptor the slot currently holds ("" = none)
+  int slot_count = 0;
+};
+
+class CorrespondenceBank {
+ public:
+  explicit CorrespondenceBank(mb2_ctx* ctx) : ctx(ctx) {}
+  int GetCorrespondencesNumber(std::string desc_name = "All", std::string det_name = "All") const;
+  TentativeCorrespListExt GetCorresponcesVector(std::string desc_name = "All", std::string det_name = "All") const;
+  int MatchImgReps(ImageRepresentation& imgrep1, ImageRepresentation& imgrep2, IterationViewsynthesisParam& synth_par,
+                   const WhatToMatch WhatToMatchNow, const MatchPars& par, const DescriptorsParameters& desc_pars);
+  void ClearCorrespondences(std::string det_name, std::string desc_name);
+
+ protected:
+  mb2_ctx* ctx;
+  std::map<std::string, std::map<std::string, TentativeCorrespListExt> > CorrespondencesMapMap;  // [desc][det]
+};
+
+int MatchFlannFGINN(mb2_ctx* ctx, const AffineRegionList& list1, const AffineRegionList& list2, TentativeCorrespListExt& corresp,
+                    const MatchPars& par, const int nn = 50);
+void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r = 3.0, const int mode = MODE_RANDOM);
+int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& out_corresp, double* H,
+                      const RANSACPars pars);
+
+}  // namespace mods
+
+// ---- C door for bench.py / tests: one MODS iteration on one image pair (mods.cpp:229-415, step 0 of
+// an iters file that has a single HessianAffine view tier with the identity view) --------------------
+extern "C" {
+typedef struct {
+  mb2_hessaff_params det;
+  mb2_orientation_params ori;
+  mb2_sift_params desc;
+  double matchRatio, contradDist, duplicateDist;
+  double err_threshold, confidence, HLAFCoef;
+  int max_samples, errorType, doSymmCheck;
+  long seed;
+} mb2_pair_config;
+typedef struct {
+  int regions1, regions2, tentatives, unique_tentatives, ransac_inliers, verified;
+  double H[9];
+  double ms_detect_describe, ms_match, ms_duplicate, ms_ransac, ms_total;
+} mb2_pair_result;
+void mb2_pair_config_default(mb2_pair_config* c);
+/* images: gray f32 [H|D].  verified_out (optional): capacity rows of 4 doubles (x1 y1 x2 y2).  Returns verified count or < 0. */
+int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2, const mb2_pair_config* cfg,
+                  mb2_pair_result* res, double* verified_out, int capacity);
+}
