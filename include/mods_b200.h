@@ -127,6 +127,10 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
                              int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8,
                              int capacity);
 
+/* Copies the regions of the most recent mb2_detect_describe_view (which may be called with NULL
+ * outputs to learn the count first) to the host.  Returns that count. */
+int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
+
 /* ---- matching -------------------------------------------------------------------------- */
 /* Replaces `int MatchFlannFGINN(const AffineRegionList& q, const AffineRegionList& t,
  * TentativeCorrespListExt&, const MatchPars&, int nn = 50)` (matching/matching.cpp:357-461) for

@@ -740,6 +740,7 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
   cudaSetDevice(ctx->device);
   ImgView img;
   int rc, n = 0, m = 0, k = 0;
+  ctx->last_view_n = 0;
   if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
   if ((rc = detect_core(ctx, img, *det, 1.0, 1.0, 1, &n))) return rc;
   if ((rc = orient_core(ctx, img, n, *ori, &m))) return rc;
@@ -792,6 +793,7 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
                                         ctx->stream));
     LAUNCH1D(ctx, k_xy_from_keys, k, ctx->rs_c.as<KeyOut>(), k, rs.xy.as<double>() + (size_t)base * 2);
     rs.n = base + k;
+    ctx->last_view_n = k;
     // results to the host
     const int mcap = std::min(k, capacity);
     if (det_kp && (rc = download_keys(ctx, ctx->kp_b.as<KeyOut>(), k, det_kp, capacity, ctx->rs_a))) return rc;
@@ -802,6 +804,19 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
     MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (k > capacity && (det_kp || reproj_kp || desc_u8)) { ctx->set_error("view: output capacity too small"); return MB2_ERR_CAPACITY; }
   }
+  return k;
+}
+
+int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
+  if (!ctx) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const int k = ctx->last_view_n, m = std::min(k, capacity);
+  if (m <= 0) return k;
+  int rc;
+  if (det_kp && (rc = download_keys(ctx, ctx->kp_b.as<KeyOut>(), m, det_kp, m, ctx->rs_a))) return rc;
+  if (reproj_kp && (rc = download_keys(ctx, ctx->rs_c.as<KeyOut>(), m, reproj_kp, m, ctx->rs_b))) return rc;
+  if (desc_u8) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(desc_u8, ctx->desc_u8.p, (size_t)m * 128, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return k;
 }
 

@@ -74,6 +74,7 @@ struct mb2_ctx {
   HostBuf h_a, h_b, h_c;
   RegionSlot slots[MB2_MAX_SLOTS];
   void* tmap_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime
+  int last_view_n = 0;          // regions of the most recent mb2_detect_describe_view (still in kp_b / rs_c / desc_u8)
   // optional per-kernel timing (mb2_ctx_profile_begin/end): CUDA events around every launch, on `stream`
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   bool profiling = false;

@@ -220,6 +220,13 @@ k_photonorm_stats(const float* __restrict__ patches, int n, const DescTables* __
   if (r0 + tid < n) stats[r0 + tid] = make_float2(sum, var);
 }
 
+__device__ __forceinline__ float wrow_at(const float (&w)[16], int i) {  // register array, dynamic index without local memory
+  float r = w[0];
+#pragma unroll
+  for (int k = 1; k < 16; k++) r = (i == k) ? w[k] : r;
+  return r;
+}
+
 // Normalisation apply + gradients + 4x4x8 votes, one CTA (128 threads = 128 bins) per region.
 __global__ void __launch_bounds__(DT)
 k_sift_votes(float* __restrict__ patches, int n, DescribeParams dp, const DescTables* __restrict__ tab,
@@ -270,21 +277,37 @@ k_sift_votes(float* __restrict__ patches, int n, DescribeParams dp, const DescTa
     s_bo0[p] = (unsigned char)(bo0 % 8);
   }
   __syncthreads();
-  // one thread per descriptor bin (rb, cb, bo), raster-order accumulation in double
+  // one thread per descriptor bin (rb, cb, bo), raster-order accumulation in double.  Bin rb collects
+  // rows 8rb..8rb+7 through (bin1, w1) and rows 8rb+8..8rb+15 through (bin0, w0) (siftdesc.cpp:22-71); the
+  // 16 + 16 weights of this thread's row / column bins are fetched once into registers.
   {
     const int rb = tid >> 5, cb = (tid >> 3) & 3, bo = tid & 7;
+    float wrow[16], wcol[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+      const int r = 8 * rb + t, c = 8 * cb + t;
+      float a = 0.f, b = 0.f;
+      if (r < PS) {
+        if (tab->bin0[r] == rb * 8 && tab->w0[r] > 0) a = tab->w0[r];
+        else if (tab->bin1[r] == rb * 8 && tab->w1[r] > 0) a = tab->w1[r];
+      }
+      if (c < PS) {
+        if (tab->bin0[c] == cb * 8 && tab->w0[c] > 0) b = tab->w0[c];
+        else if (tab->bin1[c] == cb * 8 && tab->w1[c] > 0) b = tab->w1[c];
+      }
+      wrow[t] = a; wcol[t] = b;
+    }
     double acc = 0.0;
-    for (int r = 8 * rb; r < 8 * rb + 16 && r < PS; r++) {
-      float wr;  // at most one of the two row contributions has a non-zero weight for a given bin
-      if (tab->bin0[r] == rb * 8 && tab->w0[r] > 0) wr = tab->w0[r];
-      else if (tab->bin1[r] == rb * 8 && tab->w1[r] > 0) wr = tab->w1[r];
-      else continue;
-      for (int c = 8 * cb; c < 8 * cb + 16 && c < PS; c++) {
-        float wcw;
-        if (tab->bin0[c] == cb * 8 && tab->w0[c] > 0) wcw = tab->w0[c];
-        else if (tab->bin1[c] == cb * 8 && tab->w1[c] > 0) wcw = tab->w1[c];
-        else continue;
-        const int p = r * PS + c;
+#pragma unroll 1
+    for (int tr = 0; tr < 16; tr++) {
+      const float wr = wrow_at(wrow, tr);
+      if (!(wr > 0)) continue;
+      const int rbase = (8 * rb + tr) * PS + 8 * cb;
+#pragma unroll
+      for (int tc = 0; tc < 16; tc++) {
+        const float wcw = wcol[tc];
+        if (!(wcw > 0)) continue;
+        const int p = rbase + tc;
         const float wc = fmul(wcw, s_v0[p]);
         const float val = fmul(wr, wc);
         if (val > 0) {

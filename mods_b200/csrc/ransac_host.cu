@@ -212,27 +212,32 @@ void u2h(const double* u, const int* inl, int len, double* H) {
   }
   double A1[3], A2[3], C[81];
   normu(u, inl, len, A1, A2);
-  // lin_hgN (Htools.c:57-96) rows, accumulated straight into the 9x9 covariance (cov_mat, utools.c:170-185:
-  // C[i][j] = sum_k Z[k][i] * Z[k][j], k in row order)
-  std::vector<double> Z((size_t)2 * len * 9);
+  // lin_hgN (Htools.c:57-96) rows folded straight into the 9x9 covariance.  cov_mat (utools.c:170-185)
+  // computes C[i][j] = sum_k Z[k][i] * Z[k][j] with k running over the rows in order; adding row 2i and
+  // then row 2i+1 of every point to all 45 accumulators performs exactly those additions in exactly that
+  // order, in one pass over the correspondences instead of 45 strided passes over a 2n x 9 matrix.
+  double acc[45];
+  for (int t = 0; t < 45; t++) acc[t] = 0;
   for (int i = 0; i < len; i++) {
     const double* s = u + 6 * inl[i];
     double a[3], b[3];
     a[2] = 1; b[2] = 1;
     a[0] = s[0] * A1[0] + A1[1]; a[1] = s[1] * A1[0] + A1[2];
     b[0] = s[3] * A2[0] + A2[1]; b[1] = s[4] * A2[0] + A2[2];
-    double* r0 = Z.data() + (size_t)(2 * i) * 9; double* r1 = r0 + 9;
+    double r0[9], r1[9];
     for (int j = 0; j < 3; j++) {
       r0[3 * j] = b[j]; r0[3 * j + 1] = 0; r0[3 * j + 2] = -a[0] * b[j];
       r1[3 * j] = 0; r1[3 * j + 1] = b[j]; r1[3 * j + 2] = -a[1] * b[j];
     }
+    int t = 0;
+    for (int p = 0; p < 9; p++)
+      for (int q = 0; q <= p; q++, t++) { acc[t] += r0[p] * r0[q]; acc[t] += r1[p] * r1[q]; }
   }
-  for (int i = 0; i < 9; i++)
-    for (int j = 0; j <= i; j++) {
-      double val = 0;
-      for (int k = 0; k < 2 * len; k++) val += Z[(size_t)k * 9 + i] * Z[(size_t)k * 9 + j];
-      C[9 * i + j] = val; C[i + 9 * j] = val;
-    }
+  {
+    int t = 0;
+    for (int p = 0; p < 9; p++)
+      for (int q = 0; q <= p; q++, t++) { C[9 * p + q] = acc[t]; C[p + 9 * q] = acc[t]; }
+  }
   smallest_eigvec9(C, H);
   denormH(H, A1, A2);
 }

@@ -48,35 +48,40 @@ detector_type ImageRepresentation::GetDetectorType(std::string n) const {
   for (int i = 0; i < 4; i++) if (n == kDetectorNames[i]) return (detector_type)i;
   return DET_UNKNOWN;
 }
-int ImageRepresentation::GetRegionsNumber(std::string det_name) const {  // imagerepresentation.cpp:264-283
+AffineRegion ImageRepresentation::RegionBlock::region(int i, bool with_desc) const {
+  AffineRegion r;
+  r.img_id = img_id[i]; r.img_reproj_id = 0; r.id = i; r.parent_id = 0; r.type = det;  // ids carry no information
+  r.det_kp = kp_from(&det_kp[(size_t)i * MB2_KP]);
+  r.reproj_kp = kp_from(&reproj_kp[(size_t)i * MB2_KP]);
+  r.desc.type = desc;
+  if (with_desc) r.desc.vec.assign(desc_u8.begin() + (size_t)i * 128, desc_u8.begin() + (size_t)(i + 1) * 128);
+  return r;
+}
+int ImageRepresentation::GetRegionsNumber(std::string det_name) const {  // imagerepresentation.cpp:264-283 ("None" lists)
   int n = 0;
-  for (auto& d : RegionVectorMap) {
+  for (auto& d : Blocks) {
     if (det_name != "All" && d.first != det_name) continue;
-    auto it = d.second.find("None");
-    if (it != d.second.end()) n += (int)it->second.size();
+    for (auto& e : d.second) { n += e.second.n; break; }
   }
   return n;
 }
 int ImageRepresentation::GetDescriptorsNumber(std::string desc_name, std::string det_name) const {  // :284-330
   int n = 0;
-  for (auto& d : RegionVectorMap) {
+  for (auto& d : Blocks) {
     if (det_name != "All" && d.first != det_name) continue;
-    for (auto& e : d.second) if (desc_name == "All" || e.first == desc_name) n += (int)e.second.size();
+    for (auto& e : d.second) if (desc_name == "All" || e.first == desc_name) n += e.second.n;
   }
   return n;
 }
 AffineRegionVector ImageRepresentation::GetAffineRegionVector(std::string desc_name, std::string det_name) const {  // :420-437
-  auto d = RegionVectorMap.find(det_name);
-  if (d == RegionVectorMap.end()) return AffineRegionVector();
+  AffineRegionVector out;
+  auto d = Blocks.find(det_name);
+  if (d == Blocks.end()) return out;
   auto e = d->second.find(desc_name);
-  if (e == d->second.end()) return AffineRegionVector();
-  return e->second;
-}
-void ImageRepresentation::AddRegions(AffineRegionVector& add, std::string det_name, std::string desc_name) {  // :566-600
-  AffineRegionVector& dst = RegionVectorMap[det_name][desc_name];
-  const int size = (int)dst.size();
-  dst.reserve(dst.size() + add.size());
-  for (AffineRegion r : add) { r.id += size; r.parent_id += size; dst.push_back(std::move(r)); }
+  if (e == d->second.end()) return out;
+  out.reserve(e->second.n);
+  for (int i = 0; i < e->second.n; i++) out.push_back(e->second.region(i, true));
+  return out;
 }
 
 void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisParam& synth_par, DetectorsParameters& det_par,
@@ -87,8 +92,7 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
     const std::string curr_det = kDetectorNames[det];
     auto it = synth_par.find(curr_det);
     if (it == synth_par.end() || curr_det != "HessianAffine") continue;
-    std::vector<AffineRegionVectorMap> perView(it->second.size());
-    for (size_t synth = 0; synth < it->second.size(); synth++) {
+    for (size_t synth = 0; synth < it->second.size(); synth++) {   // views are appended in view-index order (:2044-2045)
       const ViewSynthParameters& v = it->second[synth];
       const bool identity = (std::fabs(v.tilt - 1.) <= 0.1) && (std::fabs(v.phi) <= 0.2) && (std::fabs(v.zoom - 1.) <= 0.1);  // synth-detection.cpp:278
       if (!identity) continue;
@@ -99,29 +103,23 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
         mb2_sift_params sp = (dt == DESC_ROOT_SIFT) ? desc_par.RootSIFTParam : desc_par.SIFTParam;
         mb2_orientation_params op{dom_ori_par.mrSize, dom_ori_par.patchSize, dom_ori_par.maxAngles, (double)dom_ori_par.threshold};
         const double t0 = now_ms();
-        const int cap = std::max(4096, OriginalImg.rows * OriginalImg.cols / 16);
-        std::vector<double> det_kp((size_t)cap * MB2_KP), rep_kp((size_t)cap * MB2_KP);
-        std::vector<uint8_t> desc((size_t)cap * MB2_DESC_DIM);
         const bool use_slot = slot >= 0 && (slot_desc.empty() || slot_desc == curr_desc);
         int n = mb2_detect_describe_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
                                          &det_par.HessParam, &op, &sp, use_slot ? slot : MB2_MAX_SLOTS - 1, use_slot && slot_count > 0,
-                                         det_kp.data(), rep_kp.data(), desc.data(), cap);
+                                         nullptr, nullptr, nullptr, 0);
         if (n < 0) continue;  // failures are silent, like the reference (empty lists)
         if (use_slot) { slot_desc = curr_desc; slot_count += n; }
-        AffineRegionVector regs((size_t)n);
-        for (int i = 0; i < n; i++) {
-          AffineRegion& r = regs[i];
-          r.img_id = (int)synth; r.img_reproj_id = 0; r.id = 0; r.parent_id = 0; r.type = DET_HESSIAN;  // ids carry no information
-          r.det_kp = kp_from(&det_kp[(size_t)i * MB2_KP]);
-          r.reproj_kp = kp_from(&rep_kp[(size_t)i * MB2_KP]);
-          r.desc.type = dt;
-          r.desc.vec.assign(desc.begin() + (size_t)i * 128, desc.begin() + (size_t)(i + 1) * 128);
-        }
-        perView[synth][curr_desc] = std::move(regs);
+        RegionBlock& B = Blocks[curr_det][curr_desc];
+        B.det = DET_HESSIAN; B.desc = dt;
+        const size_t base = (size_t)B.n;
+        B.det_kp.resize((base + n) * MB2_KP); B.reproj_kp.resize((base + n) * MB2_KP); B.desc_u8.resize((base + n) * 128);
+        B.img_id.resize(base + n, (int)synth);
+        if (n > 0 && mb2_view_fetch(ctx, &B.det_kp[base * MB2_KP], &B.reproj_kp[base * MB2_KP], &B.desc_u8[base * 128], n) < 0) n = 0;
+        B.n = (int)base + n;
+        B.det_kp.resize((size_t)B.n * MB2_KP); B.reproj_kp.resize((size_t)B.n * MB2_KP); B.desc_u8.resize((size_t)B.n * 128); B.img_id.resize(B.n);
         TimeSpent.DetectTime += (now_ms() - t0) / 1000.0;  // detect + orient + describe are one fused call here
       }
     }
-    for (auto& m : perView) for (auto& e : m) AddRegions(e.second, curr_det, e.first);
   }
 }
 
@@ -142,6 +140,20 @@ void fill_tentatives(const double* rows, int n, const AffineRegionList& list1, c
     t.d1 = r[4]; t.d2 = r[5]; t.d2by2ndcl = r[6];
     t.ratio = std::sqrt((double)((float)r[4] / (float)r[5]));  // sqrt(ratio), ratio = float d0 / float dJ (matching.cpp:435,448)
     out.TCList.push_back(std::move(t));
+  }
+}
+template <class Get1, class Get2>
+void fill_tentatives_from(const double* rows, int n, Get1 get1, Get2 get2, TentativeCorrespListExt& out) {
+  out.TCList.resize(n);
+  for (int i = 0; i < n; i++) {
+    const double* r = rows + (size_t)i * 7;
+    TentativeCorrespExt& t = out.TCList[i];
+    t.first = get1((int)r[0]);
+    t.second = get2((int)r[1]);
+    t.secondbad = get2((int)r[2]);
+    t.secondbadby2ndcl = get2((int)r[3]);
+    t.d1 = r[4]; t.d2 = r[5]; t.d2by2ndcl = r[6];
+    t.ratio = std::sqrt((double)((float)r[4] / (float)r[5]));
   }
 }
 }  // namespace
@@ -181,6 +193,15 @@ TentativeCorrespListExt CorrespondenceBank::GetCorresponcesVector(std::string de
   }
   return out;
 }
+TentativeCorrespListExt CorrespondenceBank::TakeCorrespondences() {
+  TentativeCorrespListExt out;
+  for (auto& d : CorrespondencesMapMap)
+    for (auto& e : d.second) {
+      if (out.TCList.empty()) out.TCList.swap(e.second.TCList);
+      else { out.TCList.insert(out.TCList.end(), std::make_move_iterator(e.second.TCList.begin()), std::make_move_iterator(e.second.TCList.end())); e.second.TCList.clear(); }
+    }
+  return out;
+}
 void CorrespondenceBank::ClearCorrespondences(std::string det_name, std::string desc_name) {
   auto d = CorrespondencesMapMap.find(desc_name);
   if (d == CorrespondencesMapMap.end()) return;
@@ -203,20 +224,26 @@ int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresen
       cur.currMatchRatio = th != current_VS_params.FGINNThreshold.end() ? th->second : 0;
       if (!(cur.currMatchRatio > 0)) continue;
       TentativeCorrespListExt tents;
-      auto d1 = imgrep1.RegionVectorMap.find(curr_det), d2 = imgrep2.RegionVectorMap.find(curr_det);
-      if (d1 == imgrep1.RegionVectorMap.end() || d2 == imgrep2.RegionVectorMap.end()) continue;
-      const AffineRegionVector& queries = d1->second[curr_desc];
-      const AffineRegionVector& trains = d2->second[curr_desc];
+      auto d1 = imgrep1.Blocks.find(curr_det), d2 = imgrep2.Blocks.find(curr_det);
+      if (d1 == imgrep1.Blocks.end() || d2 == imgrep2.Blocks.end()) continue;
+      auto b1 = d1->second.find(curr_desc), b2 = d2->second.find(curr_desc);
+      if (b1 == d1->second.end() || b2 == d2->second.end()) continue;
+      const ImageRepresentation::RegionBlock& Q = b1->second;
+      const ImageRepresentation::RegionBlock& T = b2->second;
+      if (Q.n == 0 || T.n == 0) continue;
+      std::vector<double> rows((size_t)Q.n * 7);
       const bool resident = curr_det == "HessianAffine" && imgrep1.slot >= 0 && imgrep2.slot >= 0 && imgrep1.slot_desc == curr_desc &&
-                            imgrep2.slot_desc == curr_desc && imgrep1.slot_count == (int)queries.size() &&
-                            imgrep2.slot_count == (int)trains.size();
+                            imgrep2.slot_desc == curr_desc && imgrep1.slot_count == Q.n && imgrep2.slot_count == T.n;
+      int n;
       if (resident) {  // descriptors are still on the device in exactly this order: no re-upload
-        std::vector<double> rows(std::max<size_t>(1, queries.size()) * 7);
-        int n = mb2_match_slots(ctx, imgrep1.slot, imgrep2.slot, cur.currMatchRatio, cur.contradDist, 50, rows.data(), (int)queries.size());
-        if (n > 0) fill_tentatives(rows.data(), n, queries, trains, tents);
+        n = mb2_match_slots(ctx, imgrep1.slot, imgrep2.slot, cur.currMatchRatio, cur.contradDist, 50, rows.data(), Q.n);
       } else {
-        MatchFlannFGINN(ctx, queries, trains, tents, cur);
+        std::vector<double> txy((size_t)T.n * 2);
+        for (int i = 0; i < T.n; i++) { txy[2 * i] = T.reproj_kp[(size_t)i * MB2_KP]; txy[2 * i + 1] = T.reproj_kp[(size_t)i * MB2_KP + 1]; }
+        n = mb2_match_fginn(ctx, Q.desc_u8.data(), Q.n, T.desc_u8.data(), T.n, txy.data(), cur.currMatchRatio, cur.contradDist, 50, rows.data(), Q.n);
       }
+      if (n > 0)
+        fill_tentatives_from(rows.data(), n, [&](int i) { return Q.region(i, false); }, [&](int i) { return T.region(i, false); }, tents);
       CorrespondencesMapMap[curr_desc][curr_det] = std::move(tents);
     }
   }
@@ -230,13 +257,22 @@ int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresen
 // ties in the sort key keep their input order here.)
 void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, const int mode) {
   if (r <= 0) return;
-  std::vector<TentativeCorrespExt>& L = in_corresp.TCList;
-  switch (mode) {
-    case MODE_FGINN: std::stable_sort(L.begin(), L.end(), [](const TentativeCorrespExt& a, const TentativeCorrespExt& b) { return std::fabs(a.ratio) < std::fabs(b.ratio); }); break;
-    case MODE_DISTANCE: std::stable_sort(L.begin(), L.end(), [](const TentativeCorrespExt& a, const TentativeCorrespExt& b) { return std::fabs(a.d1) < std::fabs(b.d1); }); break;
-    case MODE_BIGGER_REGION: std::stable_sort(L.begin(), L.end(), [](const TentativeCorrespExt& a, const TentativeCorrespExt& b) { return std::fabs(a.first.reproj_kp.s) < std::fabs(b.first.reproj_kp.s); }); break;
-    default: break;
-  }
+  std::vector<TentativeCorrespExt>& L0 = in_corresp.TCList;
+  std::vector<int> order(L0.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+  auto key = [&](int i) -> double {
+    switch (mode) {
+      case MODE_FGINN: return std::fabs(L0[i].ratio);
+      case MODE_DISTANCE: return std::fabs(L0[i].d1);
+      case MODE_BIGGER_REGION: return std::fabs(L0[i].first.reproj_kp.s);
+      default: return 0.0;
+    }
+  };
+  if (mode == MODE_FGINN || mode == MODE_DISTANCE || mode == MODE_BIGGER_REGION)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+  std::vector<TentativeCorrespExt> L;
+  L.reserve(L0.size());
+  for (int i : order) L.push_back(std::move(L0[i]));
   const double r_sq = r * r;
   std::unordered_map<long long, std::vector<int> > grid;
   grid.reserve(L.size() * 2);
@@ -262,6 +298,7 @@ void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, con
   size_t w = 0;
   for (size_t j = 0; j < L.size(); j++) if (keep[j]) { if (w != j) L[w] = std::move(L[j]); w++; }
   L.resize(w);
+  L0.swap(L);
 }
 
 // ---- LORANSACFiltering (matching.cpp:806-980), homography mode -------------------------------------
@@ -403,7 +440,7 @@ extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, co
   t0 = now_ms();
   CorrespondenceBank Tentatives(ctx);
   Tentatives.MatchImgReps(ImgRep1, ImgRep2, iters, wtm, mp, desc_par);
-  TentativeCorrespListExt tentatives = Tentatives.GetCorresponcesVector();
+  TentativeCorrespListExt tentatives = Tentatives.TakeCorrespondences();  // == GetCorresponcesVector() without the deep copy
   res->ms_match = now_ms() - t0;
   res->tentatives = (int)tentatives.TCList.size();
   t0 = now_ms();

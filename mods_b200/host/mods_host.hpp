@@ -117,10 +117,19 @@ class ImageRepresentation {
 
  protected:
   friend class CorrespondenceBank;
-  void AddRegions(AffineRegionVector& RegionsToAdd, std::string det_name, std::string desc_name);
+  // Regions live as the SoA blocks the C ABI returns; the AoS AffineRegionVector the reference keeps in
+  // RegionVectorMap[det][desc] (imagerepresentation.h:66) is materialised on demand (GetAffineRegionVector).
+  struct RegionBlock {
+    int n = 0;
+    detector_type det = DET_UNKNOWN; descriptor_type desc = DESC_UNKNOWN;
+    std::vector<double> det_kp, reproj_kp;  // n x MB2_KP
+    std::vector<uint8_t> desc_u8;           // n x 128
+    std::vector<int> img_id;                // view index per region
+    AffineRegion region(int i, bool with_desc) const;
+  };
   mb2_ctx* ctx;
   TimeLog TimeSpent;
-  std::map<std::string, AffineRegionVectorMap> RegionVectorMap;
+  std::map<std::string, std::map<std::string, RegionBlock> > Blocks;  // [det][desc]
   std::string Name;
   int slot;                 // device-resident copy of RegionVectorMap["HessianAffine"][desc] for the matcher
   std::string slot_desc;    // which descriptor the slot currently holds ("" = none)
@@ -132,6 +141,8 @@ class CorrespondenceBank {
   explicit CorrespondenceBank(mb2_ctx* ctx) : ctx(ctx) {}
   int GetCorrespondencesNumber(std::string desc_name = "All", std::string det_name = "All") const;
   TentativeCorrespListExt GetCorresponcesVector(std::string desc_name = "All", std::string det_name = "All") const;
+  // same content as GetCorresponcesVector("All","All") but hands the lists over instead of deep-copying them
+  TentativeCorrespListExt TakeCorrespondences();
   int MatchImgReps(ImageRepresentation& imgrep1, ImageRepresentation& imgrep2, IterationViewsynthesisParam& synth_par,
                    const WhatToMatch WhatToMatchNow, const MatchPars& par, const DescriptorsParameters& desc_pars);
   void ClearCorrespondences(std::string det_name, std::string desc_name);
