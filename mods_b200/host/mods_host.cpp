@@ -258,46 +258,59 @@ int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresen
 void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, const int mode) {
   if (r <= 0) return;
   std::vector<TentativeCorrespExt>& L0 = in_corresp.TCList;
-  std::vector<int> order(L0.size());
-  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-  auto key = [&](int i) -> double {
+  const int T = (int)L0.size();
+  std::vector<int> order(T);
+  std::vector<double> key(T);
+  for (int i = 0; i < T; i++) {
+    order[i] = i;
     switch (mode) {
-      case MODE_FGINN: return std::fabs(L0[i].ratio);
-      case MODE_DISTANCE: return std::fabs(L0[i].d1);
-      case MODE_BIGGER_REGION: return std::fabs(L0[i].first.reproj_kp.s);
-      default: return 0.0;
+      case MODE_FGINN: key[i] = std::fabs(L0[i].ratio); break;
+      case MODE_DISTANCE: key[i] = std::fabs(L0[i].d1); break;
+      case MODE_BIGGER_REGION: key[i] = std::fabs(L0[i].first.reproj_kp.s); break;
+      default: key[i] = 0.0;
     }
-  };
+  }
   if (mode == MODE_FGINN || mode == MODE_DISTANCE || mode == MODE_BIGGER_REGION)
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
-  std::vector<TentativeCorrespExt> L;
-  L.reserve(L0.size());
-  for (int i : order) L.push_back(std::move(L0[i]));
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  // coordinates in processing order
+  std::vector<double> xy((size_t)T * 4);
+  for (int j = 0; j < T; j++) {
+    const TentativeCorrespExt& t = L0[order[j]];
+    xy[4 * j] = t.first.reproj_kp.x; xy[4 * j + 1] = t.first.reproj_kp.y; xy[4 * j + 2] = t.second.reproj_kp.x; xy[4 * j + 3] = t.second.reproj_kp.y;
+  }
   const double r_sq = r * r;
-  std::unordered_map<long long, std::vector<int> > grid;
-  grid.reserve(L.size() * 2);
-  auto cell = [&](double x, double y) { return ((long long)std::floor(x / r) << 32) ^ ((long long)std::floor(y / r) & 0xffffffffLL); };
-  std::vector<char> keep(L.size(), 1);
-  for (size_t j = 0; j < L.size(); j++) {
-    const double x1 = L[j].first.reproj_kp.x, y1 = L[j].first.reproj_kp.y, x2 = L[j].second.reproj_kp.x, y2 = L[j].second.reproj_kp.y;
+  // open-addressing hash of grid cells (cell = r) -> singly linked list of kept entries
+  int cap = 1; while (cap < 4 * std::max(T, 1)) cap <<= 1;
+  std::vector<long long> cell_key(cap, -1);
+  std::vector<int> cell_head(cap, -1), next(T, -1);
+  auto cell_of = [&](long long cx, long long cy) { return ((cx & 0x7fffffffLL) << 31) | (cy & 0x7fffffffLL); };
+  auto find_slot = [&](long long k) { size_t h = (size_t)(k * 0x9E3779B97F4A7C15ULL) & (cap - 1); while (cell_key[h] != -1 && cell_key[h] != k) h = (h + 1) & (cap - 1); return h; };
+  std::vector<char> keep(T, 1);
+  for (int j = 0; j < T; j++) {
+    const double x1 = xy[4 * j], y1 = xy[4 * j + 1], x2 = xy[4 * j + 2], y2 = xy[4 * j + 3];
     const long long cx = (long long)std::floor(x1 / r), cy = (long long)std::floor(y1 / r);
     bool dup = false;
     for (long long dx = -1; dx <= 1 && !dup; dx++)
       for (long long dy = -1; dy <= 1 && !dup; dy++) {
-        auto it = grid.find(((cx + dx) << 32) ^ ((cy + dy) & 0xffffffffLL));
-        if (it == grid.end()) continue;
-        for (int i : it->second) {
-          double ddx = L[i].first.reproj_kp.x - x1, ddy = L[i].first.reproj_kp.y - y1;
+        const size_t h = find_slot(cell_of(cx + dx, cy + dy));
+        if (cell_key[h] == -1) continue;
+        for (int i = cell_head[h]; i >= 0; i = next[i]) {
+          double ddx = xy[4 * i] - x1, ddy = xy[4 * i + 1] - y1;
           if (ddx * ddx + ddy * ddy > r_sq) continue;
-          ddx = L[i].second.reproj_kp.x - x2; ddy = L[i].second.reproj_kp.y - y2;
+          ddx = xy[4 * i + 2] - x2; ddy = xy[4 * i + 3] - y2;
           if (ddx * ddx + ddy * ddy <= r_sq) { dup = true; break; }
         }
       }
-    if (dup) keep[j] = 0; else grid[cell(x1, y1)].push_back((int)j);
+    if (dup) { keep[j] = 0; continue; }
+    const long long k = cell_of(cx, cy);
+    const size_t h = find_slot(k);
+    cell_key[h] = k; next[j] = cell_head[h]; cell_head[h] = j;
   }
-  size_t w = 0;
-  for (size_t j = 0; j < L.size(); j++) if (keep[j]) { if (w != j) L[w] = std::move(L[j]); w++; }
-  L.resize(w);
+  std::vector<TentativeCorrespExt> L;
+  size_t kept = 0;
+  for (int j = 0; j < T; j++) kept += keep[j];
+  L.reserve(kept);
+  for (int j = 0; j < T; j++) if (keep[j]) L.push_back(std::move(L0[order[j]]));
   L0.swap(L);
 }
 
@@ -397,6 +410,21 @@ int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, Tentati
 }
 
 }  // namespace mods
+
+// ---- test door: DuplicateFiltering on plain arrays (CPU-only logic, used by tests/test_host_logic.py) ------
+extern "C" int mb2_host_duplicate_filter(const double* xy /* n x 4: x1 y1 x2 y2 */, const double* ratio, int n, double r, int mode,
+                                         int* kept_out /* original indices, in output order */) {
+  mods::TentativeCorrespListExt L;
+  L.TCList.resize(n);
+  for (int i = 0; i < n; i++) {
+    mods::TentativeCorrespExt& t = L.TCList[i];
+    t.first.reproj_kp.x = xy[4 * i]; t.first.reproj_kp.y = xy[4 * i + 1]; t.second.reproj_kp.x = xy[4 * i + 2]; t.second.reproj_kp.y = xy[4 * i + 3];
+    t.ratio = ratio[i]; t.first.id = i;
+  }
+  mods::DuplicateFiltering(L, r, mode);
+  for (size_t i = 0; i < L.TCList.size(); i++) kept_out[i] = L.TCList[i].first.id;
+  return (int)L.TCList.size();
+}
 
 // ---- one MODS iteration on one pair ---------------------------------------------------------------
 extern "C" void mb2_pair_config_default(mb2_pair_config* c) {

@@ -33,3 +33,9 @@ os.environ["MB2_NN_IMPL"] = "simt"
 m2 = timed("match_slots simt", lambda: ctx.match_slots(0, 1), reps=1)
 print("simt equal:", np.array_equal(m, m2))
 print("launches", ctx.launches)
+os.environ.pop("MB2_NN_IMPL", None)
+for i in range(REPS):
+    res, _ = ctx.mods_pair(A, B)
+    print("  mods_pair run %d: total %.1f ms  dd %.1f match %.1f dup %.1f ransac %.1f | regions %d %d tent %d uniq %d inl %d ver %d"
+          % (i, res.ms_total, res.ms_detect_describe, res.ms_match, res.ms_duplicate, res.ms_ransac, res.regions1, res.regions2,
+             res.tentatives, res.unique_tentatives, res.ransac_inliers, res.verified))
