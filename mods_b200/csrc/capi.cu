@@ -526,12 +526,14 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
   const size_t f_patches = ((size_t)total + 31) & ~(size_t)31;
   const size_t f_stats = (f_patches + (size_t)n * 41 * 41 + 1) & ~(size_t)1;
   const size_t f_vec = (f_stats + (size_t)n * 2 + 1) & ~(size_t)1;
-  MB2_CUDA_CHECK(ctx, ctx->patch_scratch.reserve((f_vec + (size_t)n * 128 * 2) * 4 + 64));
+  const size_t f_rec = f_vec + (size_t)n * 128 * 2;
+  MB2_CUDA_CHECK(ctx, ctx->patch_scratch.reserve((f_rec + (size_t)n * 41 * 41 * 2) * 4 + 64));
   MB2_CUDA_CHECK(ctx, ctx->desc_u8.reserve((size_t)n * 128));
   float* base = ctx->patch_scratch.as<float>();
   priv(ctx)->last_patches = base + f_patches;
   return mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, d_off, base,
-                                    ctx->desc_u8.as<uint8_t>(), base + f_patches, (float2*)(base + f_stats), (double*)(base + f_vec));
+                                    ctx->desc_u8.as<uint8_t>(), base + f_patches, (float2*)(base + f_stats), (double*)(base + f_vec),
+                                    (float2*)(base + f_rec));
 }
 
 // FGINN on device-resident data.  out rows on host.

@@ -148,43 +148,55 @@ __device__ __forceinline__ bool interpolateCheckBorders_dev(int orig_w, int orig
   return false;
 }
 
-// One output row of interpolate() (detectors/helpers.cpp:551-626).  The reference advances the
-// sample position with running float sums; `row` (0-based from the top) is reached by `row`
-// additions of (a12, a22) starting at (ofs - halfHeight*a12, ofs - halfHeight*a22), then the row is
-// walked with `+= (a11, a21)`.  im may live in global or shared memory.
+// A run of `cnt` samples starting at column i0 of output row `row` of interpolate()
+// (detectors/helpers.cpp:551-626).  The reference advances the sample position with running float
+// sums: row `row` is reached by `row` additions of (a12, a22) starting at (ofs - halfHeight*a12,
+// ofs - halfHeight*a22), column i by i additions of (a11, a21) from the row start; a thread that starts
+// in the middle of a row first replays those additions (2 FADDs per skipped sample), so any split of the
+// patch over threads yields the reference's positions bit for bit.  im may be global or shared memory.
 template <class Out>
-__device__ __forceinline__ void interpolate_row(const float* __restrict__ im, int im_rows, int im_cols, int im_pitch,
+__device__ __forceinline__ void interpolate_seg(const float* __restrict__ im, int im_rows, int im_cols, int im_pitch,
                                                 float ofsx, float ofsy, float a11, float a12, float a21, float a22,
-                                                int rw, int rh, bool touch, int row, Out out /* out(i, value) */) {
+                                                int rw, int rh, bool touch, int row, int i0, int cnt, Out out /* out(i, value) */) {
   const int halfWidth = rw >> 1, halfHeight = rh >> 1;
   float rx = fsub(ofsx, fmul((float)halfHeight, a12));
   float ry = fsub(ofsy, fmul((float)halfHeight, a22));
   for (int j = 0; j < row; ++j) { rx = fadd(rx, a12); ry = fadd(ry, a22); }
   float WX = fsub(rx, fmul((float)halfWidth, a11));
   float WY = fsub(ry, fmul((float)halfWidth, a21));
+  for (int i = 0; i < i0; ++i) { WX = fadd(WX, a11); WY = fadd(WY, a21); }
   const int width = im_cols - 1, height = im_rows - 1;
-  for (int i = 0; i < rw; ++i) {
+  const int i1 = min(rw, i0 + cnt);
+  for (int i = i0; i < i1; ++i) {
     float v;
     if (!touch) {
       const int x = (int)WX, y = (int)WY;
       const float wx = fsub(WX, (float)x);
-      const float* R0 = im + (size_t)y * im_pitch;
+      const float* R0 = im + y * im_pitch + x;
       const float* R1 = R0 + im_pitch;
-      const float I1 = fadd(fmul(wx, fsub(R0[x + 1], R0[x])), R0[x]);
-      v = fadd(fmul(fsub(WY, (float)y), fsub(fadd(fmul(wx, fsub(R1[x + 1], R1[x])), R1[x]), I1)), I1);
+      const float I1 = fadd(fmul(wx, fsub(R0[1], R0[0])), R0[0]);
+      v = fadd(fmul(fsub(WY, (float)y), fsub(fadd(fmul(wx, fsub(R1[1], R1[0])), R1[0]), I1)), I1);
     } else {
       const int x = (int)floorf(WX), y = (int)floorf(WY);
       if (WX >= 0 && WY >= 0 && x < width && y < height) {
         const float wx = fsub(WX, (float)x);
-        const float* R0 = im + (size_t)y * im_pitch;
+        const float* R0 = im + y * im_pitch + x;
         const float* R1 = R0 + im_pitch;
-        const float I1 = fadd(fmul(wx, fsub(R0[x + 1], R0[x])), R0[x]);
-        v = fadd(fmul(fsub(WY, (float)y), fsub(fadd(fmul(wx, fsub(R1[x + 1], R1[x])), R1[x]), I1)), I1);
+        const float I1 = fadd(fmul(wx, fsub(R0[1], R0[0])), R0[0]);
+        v = fadd(fmul(fsub(WY, (float)y), fsub(fadd(fmul(wx, fsub(R1[1], R1[0])), R1[0]), I1)), I1);
       } else v = 0.f;
     }
     out(i, v);
     WX = fadd(WX, a11); WY = fadd(WY, a21);
   }
+}
+
+// One whole output row.
+template <class Out>
+__device__ __forceinline__ void interpolate_row(const float* __restrict__ im, int im_rows, int im_cols, int im_pitch,
+                                                float ofsx, float ofsy, float a11, float a12, float a21, float a22,
+                                                int rw, int rh, bool touch, int row, Out out /* out(i, value) */) {
+  interpolate_seg(im, im_rows, im_cols, im_pitch, ofsx, ofsy, a11, a12, a21, a22, rw, rh, touch, row, 0, rw, out);
 }
 
 // Launch bookkeeping

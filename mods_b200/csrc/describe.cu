@@ -62,12 +62,15 @@ __global__ void k_plan(const KeyOut* __restrict__ kps, int n, DescribeParams dp,
   if (g.P2 > 0) atomicAdd(sum_p2sq, (unsigned long long)g.P2 * (unsigned long long)g.P2);
 }
 
+constexpr int MAXT_SMEM = 384;   // Gaussian taps kept in shared memory (larger kernels read them from global)
+
 __global__ void __launch_bounds__(DT)
 k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp, const TapTable taps,
           const unsigned long long* __restrict__ scratch_off, float* __restrict__ scratch, float* __restrict__ patch_out) {
   __shared__ float s_patch[NPIX];
   __shared__ float s_small[NEED * NEED]; // blurred patch at the needed rows x columns
   __shared__ int s_cols[NEED], s_rows[NEED];
+  __shared__ float s_taps[MAXT_SMEM];
 
   // Regions arrive in detection order (fine octaves first), so the expensive large regions sit at the
   // end of the list: walk it backwards so they are scheduled first and do not form a tail.
@@ -79,23 +82,33 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
   const float a11 = (float)k.v[2], a12 = (float)k.v[3], a21 = (float)k.v[4], a22 = (float)k.v[5];
 
   if (g.P2 == 0) {
-    // heavy oversampling (or fast extraction): affine-normalise straight from the image
+    // heavy oversampling (or fast extraction): affine-normalise straight from the image, 3 threads per row
     const float A11 = fmul(a11, g.scale), A12 = fmul(a12, g.scale), A21 = fmul(a21, g.scale), A22 = fmul(a22, g.scale);
     const bool touch = interpolateCheckBorders_dev(img.cols, img.rows, x, y, A11, A12, A21, A22, PS, PS);
-    if (tid < PS)
-      interpolate_row(img.p, img.rows, img.cols, img.pitch, x, y, A11, A12, A21, A22, PS, PS, touch, tid,
-                      [&](int i, float v) { s_patch[tid * PS + i] = v; });
+    if (tid < 3 * PS) {
+      const int row = tid / 3, sg = tid - row * 3;
+      interpolate_seg(img.p, img.rows, img.cols, img.pitch, x, y, A11, A12, A21, A22, PS, PS, touch, row, sg * 14, 14,
+                      [&](int i, float v) { s_patch[row * PS + i] = v; });
+    }
     __syncthreads();
   } else {
     const int P2 = g.P2;
     float* bufA = scratch + scratch_off[kidx];          // P2 x P2 sampled patch
     float* bufB = bufA + (size_t)P2 * P2;               // P2 x NEED row pass at the needed columns
-    // A. sample with the det-1 frame, one thread per output row
+    const int nt = taps.n[g.m], h = nt >> 1;
+    const float* kw = taps.w + taps.off[g.m];
+    if (nt <= MAXT_SMEM) { for (int j = tid; j < nt; j += DT) s_taps[j] = kw[j]; kw = s_taps; }
+    // A. sample with the det-1 frame: rows are split into segments so that all threads sample
     {
       const bool touch = interpolateCheckBorders_dev(img.cols, img.rows, x, y, a11, a12, a21, a22, P2, P2);
-      for (int row = tid; row < P2; row += DT)
-        interpolate_row(img.p, img.rows, img.cols, img.pitch, x, y, a11, a12, a21, a22, P2, P2, touch, row,
-                        [&](int i, float v) { bufA[(size_t)row * P2 + i] = v; });
+      const int segs = P2 >= DT ? 1 : DT / P2;                 // segments per row
+      const int slen = (P2 + segs - 1) / segs;
+      for (int item = tid; item < P2 * segs; item += DT) {
+        const int row = item / segs, sg = item - row * segs;
+        float* orow = bufA + (size_t)row * P2;
+        interpolate_seg(img.p, img.rows, img.cols, img.pitch, x, y, a11, a12, a21, a22, P2, P2, touch, row, sg * slen, slen,
+                        [&](int i, float v) { orow[i] = v; });
+      }
     }
     // positions of the second interpolate(): ofs = P2>>1, A = diag(scale); the reference's running sums
     const float ofs = (float)(P2 >> 1), sc = g.scale;
@@ -120,52 +133,95 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
       }
     }
     __syncthreads();
-    // B. row pass (left-to-right accumulation, replicate border) at the needed columns, all rows
-    const int nt = taps.n[g.m], h = nt >> 1;
-    const float* kw = taps.w + taps.off[g.m];
-    for (int idx = tid; idx < P2 * NEED; idx += DT) {
-      const int r = idx / NEED, ci = idx - r * NEED;
-      const int c = s_cols[ci];
-      float acc = 0.f;
-      if (c >= 0 && c < P2) {
+    // B. row pass (left-to-right accumulation, replicate border) at the needed columns, all rows.  The needed
+    // columns come in adjacent pairs (x_i, x_i + 1): both are produced from one sliding window, one load per tap.
+    for (int idx = tid; idx < P2 * PS; idx += DT) {
+      const int r = idx / PS, i = idx - r * PS;
+      const int c = s_cols[2 * i];
+      float acc0 = 0.f, acc1 = 0.f;
+      if (c >= 0 && c + 1 < P2) {
         const float* rowp = bufA + (size_t)r * P2;
-        int cc = c - h; cc = cc < 0 ? 0 : cc;
-        acc = fmul(kw[0], rowp[cc]);
+        int cc = c - h;                                  // source column of tap 0 for output c
+        float a = rowp[cc < 0 ? 0 : cc];
+        float b = rowp[cc + 1 < 0 ? 0 : (cc + 1 > P2 - 1 ? P2 - 1 : cc + 1)];
+        acc0 = fmul(kw[0], a); acc1 = fmul(kw[0], b);
         for (int j = 1; j < nt; j++) {
-          cc = c - h + j; cc = cc < 0 ? 0 : (cc > P2 - 1 ? P2 - 1 : cc);
-          acc = fadd(acc, fmul(kw[j], rowp[cc]));
+          a = b;
+          const int cn = cc + j + 1;
+          b = rowp[cn < 0 ? 0 : (cn > P2 - 1 ? P2 - 1 : cn)];
+          const float kj = kw[j];
+          acc0 = fadd(acc0, fmul(kj, a)); acc1 = fadd(acc1, fmul(kj, b));
+        }
+      } else {
+        for (int q = 0; q < 2; q++) {                    // generic (never taken for in-range sample positions)
+          const int cq = c + q;
+          float acc = 0.f;
+          if (cq >= 0 && cq < P2) {
+            const float* rowp = bufA + (size_t)r * P2;
+            int cc = cq - h; cc = cc < 0 ? 0 : cc;
+            acc = fmul(kw[0], rowp[cc]);
+            for (int j = 1; j < nt; j++) {
+              cc = cq - h + j; cc = cc < 0 ? 0 : (cc > P2 - 1 ? P2 - 1 : cc);
+              acc = fadd(acc, fmul(kw[j], rowp[cc]));
+            }
+          }
+          if (q == 0) acc0 = acc; else acc1 = acc;
         }
       }
-      bufB[idx] = acc;
+      bufB[(size_t)r * NEED + 2 * i] = acc0;
+      bufB[(size_t)r * NEED + 2 * i + 1] = acc1;
     }
     __syncthreads();
-    // C. column pass (symmetric pairs) at the needed rows x needed columns
-    for (int idx = tid; idx < NEED * NEED; idx += DT) {
-      const int ri = idx / NEED, ci = idx - ri * NEED;
-      const int r = s_rows[ri], c = s_cols[ci];
-      float acc = 0.f;
-      if (r >= 0 && r < P2 && c >= 0 && c < P2) {
-        acc = fmul(kw[h], bufB[(size_t)r * NEED + ci]);
-        for (int j = 1; j <= h; j++) {
-          int rp = r + j; rp = rp > P2 - 1 ? P2 - 1 : rp;
-          int rm = r - j; rm = rm < 0 ? 0 : rm;
-          acc = fadd(acc, fmul(kw[h + j], fadd(bufB[(size_t)rp * NEED + ci], bufB[(size_t)rm * NEED + ci])));
+    // C. column pass (symmetric pairs) at the needed rows x needed columns; the needed rows also come in
+    // adjacent pairs (y_j, y_j + 1) that share all but two of their inputs.
+    for (int idx = tid; idx < PS * NEED; idx += DT) {
+      const int jr = idx / NEED, ci = idx - jr * NEED;
+      const int r = s_rows[2 * jr], c = s_cols[ci];
+      float acc0 = 0.f, acc1 = 0.f;
+      if (c >= 0 && c < P2) {
+        const float* col = bufB + ci;
+        auto at = [&](int rr) { rr = rr < 0 ? 0 : (rr > P2 - 1 ? P2 - 1 : rr); return col[(size_t)rr * NEED]; };
+        if (r >= 0 && r + 1 < P2) {
+          float up0 = at(r + 1), dn1 = at(r);            // out1 is centred on r + 1: its centre tap is up0, out0's centre is dn1
+          acc0 = fmul(kw[h], dn1); acc1 = fmul(kw[h], up0);
+          float dn0_prev = dn1;                          // B[r - (j-1)] for out0 == B[r + 1 - j] for out1
+          for (int j = 1; j <= h; j++) {
+            const float up1 = at(r + 1 + j);             // out1: B[r+1+j];  out0 at the next j: B[r+j+1]
+            const float dn0 = at(r - j);                 // out0: B[r-j]
+            const float kj = kw[h + j];
+            acc0 = fadd(acc0, fmul(kj, fadd(up0, dn0)));       // B[r+j] + B[r-j]
+            acc1 = fadd(acc1, fmul(kj, fadd(up1, dn0_prev)));  // B[r+1+j] + B[r+1-j]
+            up0 = up1; dn0_prev = dn0;
+          }
+        } else {
+          for (int q = 0; q < 2; q++) {
+            const int rq = r + q;
+            float acc = 0.f;
+            if (rq >= 0 && rq < P2) {
+              acc = fmul(kw[h], at(rq));
+              for (int j = 1; j <= h; j++) acc = fadd(acc, fmul(kw[h + j], fadd(at(rq + j), at(rq - j))));
+            }
+            if (q == 0) acc0 = acc; else acc1 = acc;
+          }
         }
       }
-      s_small[idx] = acc;
+      s_small[(2 * jr) * NEED + ci] = acc0;
+      s_small[(2 * jr + 1) * NEED + ci] = acc1;
     }
     __syncthreads();
-    // D. bilinear resample to 41x41 (interpolate(), helpers.cpp:551-626, with the same running sums)
-    if (tid < PS) {
-      const int j = tid;
+    // D. bilinear resample to 41x41 (interpolate(), helpers.cpp:551-626, with the same running sums), 3 threads per row
+    if (tid < 3 * PS) {
+      const int j = tid / 3, sg = tid - j * 3;
       float ry = fsub(ofs, fmul((float)(PS >> 1), sc));
       for (int q = 0; q < j; q++) ry = fadd(ry, sc);
       float rx = fsub(ofs, fmul((float)(PS >> 1), 0.f));
       for (int q = 0; q < j; q++) rx = fadd(rx, 0.f);
       float WX = fsub(rx, fmul((float)(PS >> 1), sc));
       float WY = fsub(ry, fmul((float)(PS >> 1), 0.f));
+      const int ib = sg * 14, ie = min(PS, ib + 14);
+      for (int i = 0; i < ib; i++) { WX = fadd(WX, sc); WY = fadd(WY, 0.f); }
       const int width = P2 - 1, height = P2 - 1;
-      for (int i = 0; i < PS; i++) {
+      for (int i = ib; i < ie; i++) {
         const int xi = s_cols[2 * i], yi = s_rows[2 * j];
         float v = 0.f;
         const bool inside = touch2 ? (WX >= 0 && WY >= 0 && xi < width && yi < height) : true;
@@ -187,77 +243,70 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
 }
 
 // photometricallyNormalize statistics (helpers.cpp:666-694): two serial float sums over the masked
-// pixels in raster order.  Float addition is not associative, so the sums stay serial, but 128
-// regions are summed side by side: one thread per region, the patches of a CTA's 128 regions are
-// staged through shared memory in coalesced 32-pixel slabs (padded rows: conflict-free columns).
-constexpr int PN_T = 128, PN_SLAB = 32;
+// pixels in raster order.  Float addition is not associative, so the sums stay serial, but 32 regions
+// are summed side by side by one warp: lane = region, the patches are staged through shared memory in
+// coalesced 32-pixel slabs (padded rows: conflict-free columns).
+constexpr int PN_T = 32, PN_SLAB = 32;
 __global__ void __launch_bounds__(PN_T)
 k_photonorm_stats(const float* __restrict__ patches, int n, const DescTables* __restrict__ tab, float2* __restrict__ stats) {
   __shared__ float s_tile[PN_T][PN_SLAB + 1];
   __shared__ float s_mask[NPIX];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lane = threadIdx.x;
   const int r0 = blockIdx.x * PN_T;
-  for (int p = tid; p < NPIX; p += PN_T) s_mask[p] = tab->mask[p];
+  for (int p = lane; p < NPIX; p += PN_T) s_mask[p] = tab->mask[p];
   float sum = 0.f, gsum = 0.f, var = 0.f;
   for (int pass = 0; pass < 2; pass++) {
     for (int p0 = 0; p0 < NPIX; p0 += PN_SLAB) {
-      __syncthreads();
-      for (int rr = warp; rr < PN_T; rr += PN_T / 32) {
-        const int region = r0 + rr, p = p0 + lane;
+      __syncwarp();
+      const int p = p0 + lane;
+#pragma unroll 8
+      for (int rr = 0; rr < PN_T; rr++) {
+        const int region = r0 + rr;
         s_tile[rr][lane] = (region < n && p < NPIX) ? patches[(size_t)region * NPIX + p] : 0.f;
       }
-      __syncthreads();
+      __syncwarp();
       const int lim = min(PN_SLAB, NPIX - p0);
       if (pass == 0) {
-        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { sum = fadd(sum, s_tile[tid][k]); gsum = fadd(gsum, 1.f); }
+        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { sum = fadd(sum, s_tile[lane][k]); gsum = fadd(gsum, 1.f); }
       } else {
-        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { const float d = fsub(sum, s_tile[tid][k]); var = fadd(var, fmul(d, d)); }
+        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { const float d = fsub(sum, s_tile[lane][k]); var = fadd(var, fmul(d, d)); }
       }
     }
     if (pass == 0) sum = fdiv(sum, gsum);
   }
   var = sqrtf(fdiv(var, gsum));
-  if (r0 + tid < n) stats[r0 + tid] = make_float2(sum, var);
+  if (r0 + lane < n) stats[r0 + lane] = make_float2(sum, var);
 }
 
-__device__ __forceinline__ float wrow_at(const float (&w)[16], int i) {  // register array, dynamic index without local memory
-  float r = w[0];
-#pragma unroll
-  for (int k = 1; k < 16; k++) r = (i == k) ? w[k] : r;
-  return r;
-}
-
-// Normalisation apply + gradients + 4x4x8 votes, one CTA (128 threads = 128 bins) per region.
+// Normalisation apply (helpers.cpp:695-714) + per-pixel gradient record of the SIFT descriptor
+// (siftdesc.cpp:290-345, 99-107): rec.x = mask * |grad|, rec.y = o = 8 * (ori + 2pi) / 2pi (its integer part
+// mod 8 is the lower orientation bin, its fraction the weight of the upper one).  One CTA per region.
 __global__ void __launch_bounds__(DT)
-k_sift_votes(float* __restrict__ patches, int n, DescribeParams dp, const DescTables* __restrict__ tab,
-             const float2* __restrict__ stats, double* __restrict__ vecT /* [128][n] */) {
+k_sift_grad(float* __restrict__ patches, int n, DescribeParams dp, const DescTables* __restrict__ tab,
+            const float2* __restrict__ stats, float2* __restrict__ rec) {
   __shared__ float s_patch[NPIX];
-  __shared__ float s_v0[NPIX];           // mask*grad
-  __shared__ float s_wo1[NPIX];
-  __shared__ unsigned char s_bo0[NPIX + 3];
   const int kidx = blockIdx.x, tid = threadIdx.x;
   if (kidx >= n) return;
   float* gp = patches + (size_t)kidx * NPIX;
+  bool normalise = false;
+  float sum = 0.f, fac = 0.f;
   if (dp.photoNorm) {
     const float2 st = stats[kidx];
-    const float sum = st.x, var = st.y;
-    if (!((double)var < 0.0001)) {   // helpers.cpp:695-697
-      const float fac = fdiv(50.0f, var);
-      for (int p = tid; p < NPIX; p += DT) {
-        float v = fadd(128.f, fmul(fac, fsub(gp[p], sum)));
-        if (v > 255) v = 255;
-        if (v < 0) v = 0;
-        s_patch[p] = v;
-        gp[p] = v;   // the normalised patch is what DescribeRegions hands to the descriptor
-      }
-    } else {
-      for (int p = tid; p < NPIX; p += DT) s_patch[p] = gp[p];
+    sum = st.x;
+    if (!((double)st.y < 0.0001)) { normalise = true; fac = fdiv(50.0f, st.y); }   // helpers.cpp:695-697
+  }
+  for (int p = tid; p < NPIX; p += DT) {
+    float v = gp[p];
+    if (normalise) {
+      v = fadd(128.f, fmul(fac, fsub(v, sum)));
+      if (v > 255) v = 255;
+      if (v < 0) v = 0;
+      gp[p] = v;   // the normalised patch is what DescribeRegions hands to the descriptor
     }
-  } else {
-    for (int p = tid; p < NPIX; p += DT) s_patch[p] = gp[p];
+    s_patch[p] = v;
   }
   __syncthreads();
-  // gradients (siftdesc.cpp:290-345), orientation-bin split per pixel (siftdesc.cpp:99-107)
+  float2* out = rec + (size_t)kidx * NPIX;
   for (int p = tid; p < NPIX; p += DT) {
     const int r = p / PS, c = p - r * PS;
     float xg, yg;
@@ -269,56 +318,70 @@ k_sift_votes(float* __restrict__ patches, int n, DescribeParams dp, const DescTa
     else yg = fsub(s_patch[p + PS], s_patch[p - PS]);
     const float grad = sqrtf(fadd(fmul(xg, xg), fmul(yg, yg)));
     const float ori = atan2LUTff_dev(yg, xg);
-    s_v0[p] = fmul(tab->mask[p], grad);
     const double M_PI_DOUBLED = 6.28318530718;
     const float o = (float)(8.0 * ((double)ori + M_PI_DOUBLED) / M_PI_DOUBLED);
-    int bo0 = (int)o;
-    s_wo1[p] = fsub(o, (float)bo0);
-    s_bo0[p] = (unsigned char)(bo0 % 8);
+    out[p] = make_float2(fmul(tab->mask[p], grad), o);
   }
-  __syncthreads();
-  // one thread per descriptor bin (rb, cb, bo), raster-order accumulation in double.  Bin rb collects
-  // rows 8rb..8rb+7 through (bin1, w1) and rows 8rb+8..8rb+15 through (bin0, w0) (siftdesc.cpp:22-71); the
-  // 16 + 16 weights of this thread's row / column bins are fetched once into registers.
-  {
-    const int rb = tid >> 5, cb = (tid >> 3) & 3, bo = tid & 7;
-    float wrow[16], wcol[16];
+}
+
+// 4x4x8 votes (siftdesc.cpp:73-131), one warp per region.  Lane = (rb, cb, h): spatial bin (rb, cb) and
+// one of its two 8-column segments (h = 0: columns 8cb..8cb+7 reach the bin through (bin1, w1); h = 1:
+// columns 8cb+8..8cb+15 through (bin0, w0)); every lane walks its 16 x 8 pixels in raster order and adds
+// into its own 8 orientation accumulators (double, in shared memory), then the two segments are summed.
+// (Sums are in double: the association differs from the reference's single raster chain only at 1e-16
+// relative, far below the 1/512 quantisation of the descriptor.)
+constexpr int VW = 4;  // warps (regions) per CTA
+__global__ void __launch_bounds__(VW * 32)
+k_sift_votes(const float2* __restrict__ rec, int n, const DescTables* __restrict__ tab, double* __restrict__ vecT /* [128][n] */) {
+  __shared__ double s_acc[VW][32][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kidx = blockIdx.x * VW + warp;
+  if (kidx >= n) return;
+  const int rb = lane >> 3, cb = (lane >> 1) & 3, h = lane & 1;
+  double* acc = s_acc[warp][lane];
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-      const int r = 8 * rb + t, c = 8 * cb + t;
-      float a = 0.f, b = 0.f;
-      if (r < PS) {
-        if (tab->bin0[r] == rb * 8 && tab->w0[r] > 0) a = tab->w0[r];
-        else if (tab->bin1[r] == rb * 8 && tab->w1[r] > 0) a = tab->w1[r];
-      }
-      if (c < PS) {
-        if (tab->bin0[c] == cb * 8 && tab->w0[c] > 0) b = tab->w0[c];
-        else if (tab->bin1[c] == cb * 8 && tab->w1[c] > 0) b = tab->w1[c];
-      }
-      wrow[t] = a; wcol[t] = b;
-    }
-    double acc = 0.0;
-#pragma unroll 1
-    for (int tr = 0; tr < 16; tr++) {
-      const float wr = wrow_at(wrow, tr);
-      if (!(wr > 0)) continue;
-      const int rbase = (8 * rb + tr) * PS + 8 * cb;
+  for (int b = 0; b < 8; b++) acc[b] = 0.0;
+  const float2* R = rec + (size_t)kidx * NPIX;
+  const int c_lo = 8 * cb + 8 * h;
+  float wcol[8];
 #pragma unroll
-      for (int tc = 0; tc < 16; tc++) {
-        const float wcw = wcol[tc];
-        if (!(wcw > 0)) continue;
-        const int p = rbase + tc;
-        const float wc = fmul(wcw, s_v0[p]);
-        const float val = fmul(wr, wc);
-        if (val > 0) {
-          const int bo0 = s_bo0[p], bo1 = (bo0 + 1) & 7;
-          const float wo1 = s_wo1[p];
-          if (bo0 == bo) acc += (double)fmul(val, fsub(1.0f, wo1));
-          else if (bo1 == bo) acc += (double)fmul(val, wo1);
-        }
+  for (int t = 0; t < 8; t++) {
+    const int c = c_lo + t;
+    float w = 0.f;
+    if (c < PS) {
+      if (h == 0) { if (tab->bin1[c] == cb * 8) w = tab->w1[c]; }
+      else { if (tab->bin0[c] == cb * 8) w = tab->w0[c]; }
+    }
+    wcol[t] = w;
+  }
+  for (int tr = 0; tr < 16; tr++) {
+    const int r = 8 * rb + tr;
+    if (r >= PS) break;
+    float wr = 0.f;
+    if (tr < 8) { if (tab->bin1[r] == rb * 8) wr = tab->w1[r]; }
+    else { if (tab->bin0[r] == rb * 8) wr = tab->w0[r]; }
+    if (!(wr > 0)) continue;
+    const float2* row = R + r * PS + c_lo;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      if (c_lo + t >= PS) break;
+      const float2 px = __ldg(row + t);
+      const float wc = fmul(wcol[t], px.x);
+      const float val = fmul(wr, wc);
+      if (val > 0) {
+        const int io = (int)px.y;
+        const float wo1 = fsub(px.y, (float)io);
+        const int bo0 = io & 7, bo1 = (bo0 + 1) & 7;   // io >= 0: io % 8 == io & 7
+        acc[bo0] += (double)fmul(val, fsub(1.0f, wo1));
+        acc[bo1] += (double)fmul(val, wo1);
       }
     }
-    vecT[(size_t)tid * n + kidx] = acc;
+  }
+  __syncwarp();
+  // lanes (rb, cb, 0) and (rb, cb, 1) are neighbours: h = 0 segment first (lower columns), as in a raster walk
+  for (int b = lane & 1 ? 4 : 0, e = b + 4; b < e; b++) {
+    const double v = s_acc[warp][lane & ~1][b] + s_acc[warp][lane | 1][b];
+    vecT[(size_t)((rb * 4 + cb) * 8 + b) * n + kidx] = v;
   }
 }
 
@@ -372,11 +435,12 @@ int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribePara
 
 int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
                                const DescTables* d_tables, const TapTable& taps, const unsigned long long* d_off, float* d_scratch,
-                               uint8_t* d_desc, float* d_patches, float2* d_stats, double* d_vecT) {
+                               uint8_t* d_desc, float* d_patches, float2* d_stats, double* d_vecT, float2* d_rec) {
   if (!n) return MB2_OK;
   MB2_LAUNCH(ctx, k_extract, n, DT, 0, img, kps, n, dp, taps, d_off, d_scratch, d_patches);
   if (dp.photoNorm) MB2_LAUNCH(ctx, k_photonorm_stats, (n + PN_T - 1) / PN_T, PN_T, 0, d_patches, n, d_tables, d_stats);
-  MB2_LAUNCH(ctx, k_sift_votes, n, DT, 0, d_patches, n, dp, d_tables, d_stats, d_vecT);
+  MB2_LAUNCH(ctx, k_sift_grad, n, DT, 0, d_patches, n, dp, d_tables, d_stats, d_rec);
+  MB2_LAUNCH(ctx, k_sift_votes, (n + VW - 1) / VW, VW * 32, 0, d_rec, n, d_tables, d_vecT);
   MB2_LAUNCH(ctx, k_sift_finish, (n + 127) / 128, 128, 0, d_vecT, n, dp, d_desc);
   return MB2_OK;
 }

@@ -17,4 +17,4 @@ int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribePara
 int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
                                const DescTables* d_tables, const TapTable& taps, const unsigned long long* d_off, float* d_scratch,
                                uint8_t* d_desc, float* d_patches /* n x 41 x 41, required */, float2* d_stats /* n */,
-                               double* d_vecT /* 128 x n */);
+                               double* d_vecT /* 128 x n */, float2* d_rec /* n x 1681 gradient records */);

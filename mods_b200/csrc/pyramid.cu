@@ -22,69 +22,107 @@
 namespace MB2_NS {
 
 constexpr int TW = 64, TH = 32, BLUR_THREADS = 256;
+constexpr int RS = 6;    // row-pass outputs per work item  (TW + 2 = 66 = 11 * 6)
+constexpr int CS = 12;   // column-pass outputs per work item (TH + 2 = 34 -> 12 + 12 + 10)
 
+// The kernel is instruction-bound unless the taps are applied from registers: every work item of the
+// row pass loads a window of RS + NT - 1 neighbours once and produces RS outputs from it; the column
+// pass does the same down a column.  Arithmetic order per output is unchanged (row: left-to-right
+// accumulation; column: centre tap, then symmetric pairs), so results are bit-identical to the oracle.
 template <int NT>  // number of taps (odd)
 __global__ void __launch_bounds__(BLUR_THREADS)
 k_blur_hess(ImgView src, float* __restrict__ dst_blur, float* __restrict__ dst_resp, int dst_pitch, BlurTaps taps,
             float norm2, int want_resp) {
   constexpr int H = NT / 2;
-  constexpr int IN_W = TW + 2 * H + 2, IN_H = TH + 2 * H + 2;   // source tile incl. halo
-  constexpr int RP_W = TW + 2;                                   // row-pass result: IN_H x RP_W
-  constexpr int CP_W = TW + 2, CP_H = TH + 2;                    // col-pass result
+  constexpr int IN_W = TW + 2 * H + 2, IN_H = TH + 2 * H + 2;   // source tile incl. halo (IN_W is even)
+  constexpr int IN_WP = IN_W + 2;                               // padded pitch (even, so float2 loads stay aligned)
+  constexpr int RP_W = TW + 2, RP_WP = RP_W + 2;                // row-pass result: IN_H x RP_W (pitch 68: conflict-free columns)
+  constexpr int CP_W = TW + 2, CP_H = TH + 2, CP_WP = RP_WP;    // col-pass result, aliases the source tile
   extern __shared__ float smem[];
-  float* s_in = smem;                        // IN_H * IN_W
-  float* s_rp = s_in + IN_H * IN_W;          // IN_H * RP_W
-  float* s_cp = s_rp + IN_H * RP_W;          // CP_H * CP_W
+  float* s_in = smem;                        // IN_H * IN_WP
+  float* s_rp = s_in + IN_H * IN_WP;         // IN_H * RP_WP
+  float* s_cp = s_in;                        // CP_H * CP_WP (the source tile is dead after the row pass)
+  static_assert(CP_H * CP_WP <= IN_H * IN_WP, "col-pass tile must fit in the source tile");
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  // 1. load with clamped (replicated) coordinates
-  for (int i = tid; i < IN_H * IN_W; i += BLUR_THREADS) {
-    int ly = i / IN_W, lx = i - ly * IN_W;
-    int gy = min(max(y0 + ly - H - 1, 0), src.rows - 1);
-    int gx = min(max(x0 + lx - H - 1, 0), src.cols - 1);
-    s_in[i] = src.at(gy, gx);
+  float k[NT];
+#pragma unroll
+  for (int j = 0; j < NT; j++) k[j] = taps.k[j];
+  // 1. load with clamped (replicated) coordinates, one warp per tile row
+  for (int ly = warp; ly < IN_H; ly += BLUR_THREADS / 32) {
+    const int gy = min(max(y0 + ly - H - 1, 0), src.rows - 1);
+    const float* row = src.p + (size_t)gy * src.pitch;
+    for (int lx = lane; lx < IN_W; lx += 32) {
+      const int gx = min(max(x0 + lx - H - 1, 0), src.cols - 1);
+      s_in[ly * IN_WP + lx] = row[gx];
+    }
   }
   __syncthreads();
-  // 2. row pass: out(ly, lx) for lx in [0, RP_W) is centred on source column lx + H
-  for (int i = tid; i < IN_H * RP_W; i += BLUR_THREADS) {
-    int ly = i / RP_W, lx = i - ly * RP_W;
-    const float* p = s_in + ly * IN_W + lx;
-    float acc = fmul(taps.k[0], p[0]);
+  // 2. row pass: item = (row ly, strip of RS outputs); output lx is centred on source column lx + H
+  for (int item = tid; item < IN_H * (RP_W / RS); item += BLUR_THREADS) {
+    const int ly = item / (RP_W / RS), st = item - ly * (RP_W / RS);
+    const float* p = s_in + ly * IN_WP + st * RS;
+    float w[RS + NT - 1];
 #pragma unroll
-    for (int j = 1; j < NT; j++) acc = fadd(acc, fmul(taps.k[j], p[j]));
-    s_rp[i] = acc;
+    for (int j = 0; j < RS + NT - 1; j += 2) {
+      const float2 v = *reinterpret_cast<const float2*>(p + j);
+      w[j] = v.x;
+      if (j + 1 < RS + NT - 1) w[j + 1] = v.y;
+    }
+    float* o = s_rp + ly * RP_WP + st * RS;
+#pragma unroll
+    for (int q = 0; q < RS; q++) {
+      float acc = fmul(k[0], w[q]);
+#pragma unroll
+      for (int j = 1; j < NT; j++) acc = fadd(acc, fmul(k[j], w[q + j]));
+      o[q] = acc;
+    }
   }
   __syncthreads();
-  // 3. column pass (symmetric pairs): out(ly, lx) for ly in [0, CP_H) centred on row ly + H
-  for (int i = tid; i < CP_H * CP_W; i += BLUR_THREADS) {
-    int ly = i / CP_W, lx = i - ly * CP_W;
-    const float* p = s_rp + (ly + H) * RP_W + lx;
-    float acc = fmul(taps.k[H], p[0]);
+  // 3. column pass (symmetric pairs): item = (column lx, strip of CS rows); output ly is centred on row ly + H
+  constexpr int NSTRIP = (CP_H + CS - 1) / CS;
+  for (int item = tid; item < CP_W * NSTRIP; item += BLUR_THREADS) {
+    const int st = item / CP_W, lx = item - st * CP_W;
+    const int ly0 = st * CS;
+    const float* p = s_rp + ly0 * RP_WP + lx;
+    float w[CS + 2 * H];
 #pragma unroll
-    for (int j = 1; j <= H; j++) acc = fadd(acc, fmul(taps.k[H + j], fadd(p[j * RP_W], p[-j * RP_W])));
-    s_cp[i] = acc;
+    for (int j = 0; j < CS + 2 * H; j++) w[j] = (ly0 + j < IN_H) ? p[j * RP_WP] : 0.f;
+#pragma unroll
+    for (int q = 0; q < CS; q++) {
+      if (ly0 + q < CP_H) {
+        float acc = fmul(k[H], w[q + H]);
+#pragma unroll
+        for (int j = 1; j <= H; j++) acc = fadd(acc, fmul(k[H + j], fadd(w[q + H + j], w[q + H - j])));
+        s_cp[(ly0 + q) * CP_WP + lx] = acc;
+      }
+    }
   }
   __syncthreads();
   // 4. write blur + Hessian response (pyramid.cpp:223-281; 1-px frame of the response is left 0)
-  for (int i = tid; i < TH * TW; i += BLUR_THREADS) {
-    int ly = i / TW, lx = i - ly * TW;
-    int gy = y0 + ly, gx = x0 + lx;
-    if (gy >= src.rows || gx >= src.cols) continue;
-    const float* c = s_cp + (ly + 1) * CP_W + (lx + 1);
-    dst_blur[(size_t)gy * dst_pitch + gx] = c[0];
-    if (want_resp) {
-      float r = 0.f;
-      if (gy >= 1 && gy < src.rows - 1 && gx >= 1 && gx < src.cols - 1) {
-        const float v11 = c[-CP_W - 1], v12 = c[-CP_W], v13 = c[-CP_W + 1];
-        const float v21 = c[-1], v22 = c[0], v23 = c[1];
-        const float v31 = c[CP_W - 1], v32 = c[CP_W], v33 = c[CP_W + 1];
-        const float Lxx = fadd(fsub(v21, fmul(2.f, v22)), v23);
-        const float Lyy = fadd(fsub(v12, fmul(2.f, v22)), v32);
-        const float Lxy = fdiv(fsub(fadd(fsub(v13, v11), v31), v33), 4.0f);
-        r = fmul(fsub(fmul(Lxx, Lyy), fmul(Lxy, Lxy)), norm2);
+  for (int ly = warp; ly < TH; ly += BLUR_THREADS / 32) {
+    const int gy = y0 + ly;
+    if (gy >= src.rows) break;
+#pragma unroll
+    for (int half = 0; half < TW / 32; half++) {
+      const int lx = lane + 32 * half, gx = x0 + lx;
+      if (gx >= src.cols) continue;
+      const float* c = s_cp + (ly + 1) * CP_WP + (lx + 1);
+      dst_blur[(size_t)gy * dst_pitch + gx] = c[0];
+      if (want_resp) {
+        float r = 0.f;
+        if (gy >= 1 && gy < src.rows - 1 && gx >= 1 && gx < src.cols - 1) {
+          const float v11 = c[-CP_WP - 1], v12 = c[-CP_WP], v13 = c[-CP_WP + 1];
+          const float v21 = c[-1], v22 = c[0], v23 = c[1];
+          const float v31 = c[CP_WP - 1], v32 = c[CP_WP], v33 = c[CP_WP + 1];
+          const float Lxx = fadd(fsub(v21, fmul(2.f, v22)), v23);
+          const float Lyy = fadd(fsub(v12, fmul(2.f, v22)), v32);
+          const float Lxy = fdiv(fsub(fadd(fsub(v13, v11), v31), v33), 4.0f);
+          r = fmul(fsub(fmul(Lxx, Lyy), fmul(Lxy, Lxy)), norm2);
+        }
+        dst_resp[(size_t)gy * dst_pitch + gx] = r;
       }
-      dst_resp[(size_t)gy * dst_pitch + gx] = r;
     }
   }
 }
@@ -152,26 +190,41 @@ __device__ __forceinline__ bool is_min9(const ImgView& im, float val, int r, int
   return true;
 }
 
-__global__ void k_nms(ImgView low, ImgView cur, ImgView high, int border, float posThr, float negThr, int level,
-                      Candidate* __restrict__ out, int* __restrict__ count, int capacity) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x + border, r = blockIdx.y * blockDim.y + threadIdx.y + border;
-  bool hit = false;
-  if (r < cur.rows - border && c < cur.cols - border) {
-    const float val = cur.at(r, c);
-    if (val > posThr) hit = is_max9(cur, val, r, c) && is_max9(low, val, r, c) && is_max9(high, val, r, c);
-    else if (val < negThr) hit = is_min9(cur, val, r, c) && is_min9(low, val, r, c) && is_min9(high, val, r, c);
+// Four pixels per thread from one aligned 16-byte load of the centre plane (the scan of `cur` is the
+// whole HBM cost: only the ~0.5% of pixels beyond the threshold ever touch their 26 neighbours).
+__global__ void __launch_bounds__(256)
+k_nms(ImgView low, ImgView cur, ImgView high, int border, float posThr, float negThr, int level,
+      Candidate* __restrict__ out, int* __restrict__ count, int capacity) {
+  const int c0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), r = blockIdx.y * blockDim.y + threadIdx.y + border;
+  const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+  unsigned hits = 0;
+  if (r < cur.rows - border && c0 < cur.cols) {
+    const float4 v4 = *reinterpret_cast<const float4*>(cur.p + (size_t)r * cur.pitch + c0);  // pitch and c0 are multiples of 4
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int c = c0 + q;
+      if (c < border || c >= cur.cols - border) continue;
+      const float val = v[q];
+      bool hit = false;
+      if (val > posThr) hit = is_max9(cur, val, r, c) && is_max9(low, val, r, c) && is_max9(high, val, r, c);
+      else if (val < negThr) hit = is_min9(cur, val, r, c) && is_min9(low, val, r, c) && is_min9(high, val, r, c);
+      hits |= (unsigned)hit << q;
+    }
   }
   // warp-aggregated append
-  unsigned m = __ballot_sync(0xffffffffu, hit);
-  if (m) {
-    int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
-    int leader = __ffs(m) - 1, base = 0;
-    if (lane == leader) base = atomicAdd(count, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (hit) {
-      int slot = base + __popc(m & ((1u << lane) - 1));
-      if (slot < capacity) out[slot] = Candidate{r, c, level, 0};
-    }
+  const int mine = __popc(hits);
+  int prefix = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) { int t = __shfl_up_sync(0xffffffffu, prefix, off); if (lane >= off) prefix += t; }
+  const int total = __shfl_sync(0xffffffffu, prefix, 31);
+  if (total) {
+    int base = 0;
+    if (lane == 31) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + prefix - mine;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (hits & (1u << q)) { if (base < capacity) out[base] = Candidate{r, c0 + q, level, 0}; base++; }
   }
 }
 
@@ -316,7 +369,7 @@ void launch_blur_nt(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* ds
                     float norm2, int want_resp) {
   constexpr int H = NT / 2;
   constexpr int IN_W = TW + 2 * H + 2, IN_H = TH + 2 * H + 2;
-  size_t smem = sizeof(float) * (IN_H * IN_W + IN_H * (TW + 2) + (TH + 2) * (TW + 2));
+  size_t smem = sizeof(float) * (IN_H * (IN_W + 2) + IN_H * (TW + 4));
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_blur_hess<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   dim3 grid((src.cols + TW - 1) / TW, (src.rows + TH - 1) / TH);
@@ -363,7 +416,7 @@ void mb2_launch_nms(mb2_ctx* ctx, const ImgView& low, const ImgView& cur, const 
                     float negThr, int level, Candidate* out, int* count, int capacity) {
   int w = cur.cols - 2 * border, h = cur.rows - 2 * border;
   if (w <= 0 || h <= 0) return;
-  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  dim3 block(32, 8), grid((cur.cols + 127) / 128, (h + 7) / 8);
   MB2_LAUNCH(ctx, k_nms, grid, block, 0, low, cur, high, border, posThr, negThr, level, out, count, capacity);
 }
 
