@@ -80,6 +80,8 @@ const char* mb2_last_error(const mb2_ctx* ctx);
 int mb2_ctx_sync(mb2_ctx* ctx);
 /* cudaStream_t of the context (for CUDA-event timing by the caller). */
 void* mb2_ctx_stream(mb2_ctx* ctx);
+int mb2_ctx_device(const mb2_ctx* ctx);
+int mb2_ctx_profiling(const mb2_ctx* ctx);   /* 1 between mb2_ctx_profile_begin and _end */
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long mb2_ctx_launch_count(const mb2_ctx* ctx);
 
@@ -130,6 +132,11 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
 /* Copies the regions of the most recent mb2_detect_describe_view (which may be called with NULL
  * outputs to learn the count first) to the host.  Returns that count. */
 int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
+
+/* Hands a device-resident region set over to another context on the same GPU (no copy).  Lets two host
+ * threads run mb2_detect_describe_view for the two images of a pair on two contexts (= two streams), the
+ * way mods.cpp:255-271 runs them as two OpenMP tasks, and match them afterwards on one. */
+int mb2_slot_move(mb2_ctx* dst, int dst_slot, mb2_ctx* src, int src_slot);
 
 /* ---- matching -------------------------------------------------------------------------- */
 /* Replaces `int MatchFlannFGINN(const AffineRegionList& q, const AffineRegionList& t,

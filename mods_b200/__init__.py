@@ -17,7 +17,7 @@ KP = 9
 EXPORTS = [
     "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
-    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end",
+    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
 ]
 
 
@@ -90,6 +90,10 @@ def host_lib():
         if not os.path.exists(HOST_LIB_PATH):
             raise Mb2Error("libmods_host.so is not built")
         _host = C.CDLL(HOST_LIB_PATH)
+        _host.mb2_mods_launch_count.restype = C.c_longlong
+        _host.mb2_mods_launch_count.argtypes = [C.c_void_p]
+        _host.mb2_mods_release.argtypes = [C.c_void_p]
+        _host.mb2_mods_release.restype = None
     return _host
 
 
@@ -136,6 +140,8 @@ class Context:
 
     def close(self):
         if self.h:
+            if _host is not None:
+                _host.mb2_mods_release(self.h)
             lib().mb2_ctx_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -159,6 +165,9 @@ class Context:
 
     @property
     def launches(self):
+        """Kernels launched so far (including the helper context mods_pair keeps for the second image)."""
+        if _host is not None:
+            return _host.mb2_mods_launch_count(self.h)
         return lib().mb2_ctx_launch_count(self.h)
 
     def profile_begin(self):
@@ -246,6 +255,10 @@ class Context:
         n = self._check(lib().mb2_match_slots(self.h, C.c_int(q_slot), C.c_int(t_slot), C.c_double(ratio), C.c_double(contradDist),
                                               C.c_int(nn), _ptr(out), C.c_int(capacity)), "match_slots")
         return out[:n].copy()
+
+    def slot_move_to(self, dst, dst_slot, src_slot):
+        """Hand the device-resident region set in self's src_slot over to context dst (no copy)."""
+        self._check(lib().mb2_slot_move(dst.h, C.c_int(dst_slot), self.h, C.c_int(src_slot)), "slot_move")
 
     # ---- verification
     def score_models(self, which, u, models, th, want_resid=False, len_=None, K=None):

@@ -646,6 +646,22 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
 const char* mb2_last_error(const mb2_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int mb2_ctx_sync(mb2_ctx* ctx) { MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return MB2_OK; }
 void* mb2_ctx_stream(mb2_ctx* ctx) { return (void*)ctx->stream; }
+int mb2_ctx_device(const mb2_ctx* ctx) { return ctx ? ctx->device : -1; }
+int mb2_ctx_profiling(const mb2_ctx* ctx) { return ctx && ctx->profiling ? 1 : 0; }
+
+int mb2_slot_move(mb2_ctx* dst, int dst_slot, mb2_ctx* src, int src_slot) {
+  if (!dst || !src || dst_slot < 0 || dst_slot >= MB2_MAX_SLOTS || src_slot < 0 || src_slot >= MB2_MAX_SLOTS || dst->device != src->device)
+    return MB2_ERR_ARG;
+  if (dst == src && dst_slot == src_slot) return MB2_OK;
+  cudaSetDevice(dst->device);
+  MB2_CUDA_CHECK(src, cudaStreamSynchronize(src->stream));
+  MB2_CUDA_CHECK(dst, cudaStreamSynchronize(dst->stream));
+  RegionSlot& d = dst->slots[dst_slot];
+  RegionSlot& s = src->slots[src_slot];
+  std::swap(d.desc, s.desc); std::swap(d.xy, s.xy); std::swap(d.n, s.n);   // buffers change owner, nothing is copied
+  s.n = 0;
+  return MB2_OK;
+}
 long long mb2_ctx_launch_count(const mb2_ctx* ctx) { return ctx->launches; }
 
 int mb2_ctx_profile_begin(mb2_ctx* ctx) {
@@ -850,17 +866,34 @@ int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const do
   const void *du, *dm;
   int rc;
   if ((rc = mb2_stage_in(ctx, u, (size_t)len * 48, ctx->rs_a, &du))) return rc;
-  if ((rc = mb2_stage_in(ctx, models, (size_t)K * 72, ctx->rs_b, &dm))) return rc;
+  // models and results go through pinned staging: these calls sit inside RANSAC's sequential loop, where a
+  // pageable cudaMemcpyAsync would cost more than the kernel
   const size_t rbytes = resid ? (size_t)K * len * 8 : 0;
+  const size_t out_bytes = (size_t)K * 16 + rbytes + 64;
+  MB2_CUDA_CHECK(ctx, ctx->h_c.reserve((size_t)K * 72 + out_bytes));
+  uint8_t* hp = ctx->h_c.as<uint8_t>();
+  double* h_models = (double*)hp;
+  double* h_J = (double*)(hp + (((size_t)K * 72 + 15) & ~(size_t)15));
+  int* h_I = (int*)(h_J + K);
+  double* h_res = (double*)(((uintptr_t)(h_I + K) + 15) & ~(uintptr_t)15);
+  if (mb2_is_device_ptr(models)) dm = models;
+  else {
+    std::memcpy(h_models, models, (size_t)K * 72);
+    MB2_CUDA_CHECK(ctx, ctx->rs_b.reserve((size_t)K * 72));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->rs_b.p, h_models, (size_t)K * 72, cudaMemcpyHostToDevice, ctx->stream));
+    dm = ctx->rs_b.p;
+  }
   MB2_CUDA_CHECK(ctx, ctx->rs_c.reserve(rbytes + (size_t)K * 16 + 64));
   double* d_J = ctx->rs_c.as<double>();
   int* d_I = (int*)(d_J + K);
   double* d_res = resid ? (double*)(((uintptr_t)(d_I + K) + 15) & ~(uintptr_t)15) : nullptr;
   mb2_launch_score(ctx, which, (const double*)du, len, (const double*)dm, K, th, d_res, d_I, d_J);
-  if (J) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(J, d_J, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (I) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(I, d_I, (size_t)K * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (resid) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(resid, d_res, rbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (J || I) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(h_J, d_J, (size_t)K * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  if (resid) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(h_res, d_res, rbytes, cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (J) std::memcpy(J, h_J, (size_t)K * 8);
+  if (I) std::memcpy(I, h_I, (size_t)K * 4);
+  if (resid) std::memcpy(resid, h_res, rbytes);
   return K;
 }
 

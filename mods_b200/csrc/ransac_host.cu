@@ -26,9 +26,13 @@
 #undef MB2_NS
 #define MB2_NS mb2_ransac_host_detail
 #include "ransac.cuh"
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 namespace MB2_NS {
@@ -216,23 +220,34 @@ void u2h(const double* u, const int* inl, int len, double* H) {
   // computes C[i][j] = sum_k Z[k][i] * Z[k][j] with k running over the rows in order; adding row 2i and
   // then row 2i+1 of every point to all 45 accumulators performs exactly those additions in exactly that
   // order, in one pass over the correspondences instead of 45 strided passes over a 2n x 9 matrix.
-  double acc[45];
-  for (int t = 0; t < 45; t++) acc[t] = 0;
-  for (int i = 0; i < len; i++) {
-    const double* s = u + 6 * inl[i];
-    double a[3], b[3];
-    a[2] = 1; b[2] = 1;
-    a[0] = s[0] * A1[0] + A1[1]; a[1] = s[1] * A1[0] + A1[2];
-    b[0] = s[3] * A2[0] + A2[1]; b[1] = s[4] * A2[0] + A2[2];
-    double r0[9], r1[9];
-    for (int j = 0; j < 3; j++) {
-      r0[3 * j] = b[j]; r0[3 * j + 1] = 0; r0[3 * j + 2] = -a[0] * b[j];
-      r1[3 * j] = 0; r1[3 * j + 1] = b[j]; r1[3 * j + 2] = -a[1] * b[j];
+  // Large inlier sets (LO on tens of thousands of points) are summed in fixed chunks on all host cores;
+  // the chunk boundaries do not depend on the thread count, so the result is machine-independent.  Short
+  // lists (one chunk) keep the reference's single serial chain bit for bit.
+  const int CH = 2048;
+  const int nchunks = len <= 2 * CH ? 1 : (len + CH - 1) / CH;
+  std::vector<double> part((size_t)nchunks * 45, 0.0);
+#pragma omp parallel for schedule(static) if (nchunks > 1)
+  for (int ck = 0; ck < nchunks; ck++) {
+    double* acc = part.data() + (size_t)ck * 45;
+    const int lo = nchunks == 1 ? 0 : ck * CH, hi = nchunks == 1 ? len : std::min(len, lo + CH);
+    for (int i = lo; i < hi; i++) {
+      const double* s = u + 6 * inl[i];
+      double a[3], b[3];
+      a[2] = 1; b[2] = 1;
+      a[0] = s[0] * A1[0] + A1[1]; a[1] = s[1] * A1[0] + A1[2];
+      b[0] = s[3] * A2[0] + A2[1]; b[1] = s[4] * A2[0] + A2[2];
+      double r0[9], r1[9];
+      for (int j = 0; j < 3; j++) {
+        r0[3 * j] = b[j]; r0[3 * j + 1] = 0; r0[3 * j + 2] = -a[0] * b[j];
+        r1[3 * j] = 0; r1[3 * j + 1] = b[j]; r1[3 * j + 2] = -a[1] * b[j];
+      }
+      int t = 0;
+      for (int p = 0; p < 9; p++)
+        for (int q = 0; q <= p; q++, t++) { acc[t] += r0[p] * r0[q]; acc[t] += r1[p] * r1[q]; }
     }
-    int t = 0;
-    for (int p = 0; p < 9; p++)
-      for (int q = 0; q <= p; q++, t++) { acc[t] += r0[p] * r0[q]; acc[t] += r1[p] * r1[q]; }
   }
+  double acc[45];
+  for (int t = 0; t < 45; t++) { acc[t] = part[t]; for (int ck = 1; ck < nchunks; ck++) acc[t] += part[(size_t)ck * 45 + t]; }
   {
     int t = 0;
     for (int p = 0; p < 9; p++)
@@ -277,8 +292,20 @@ struct HashTable {
 };
 
 // ---------------------------------------------------------------------------------------------
+struct Trace {  // MB2_RANSAC_TRACE=1: where the wall time of one mb2_ransac_h call goes (stderr)
+  bool on = std::getenv("MB2_RANSAC_TRACE") != nullptr;
+  double t[6] = {0, 0, 0, 0, 0, 0}; int n[6] = {0, 0, 0, 0, 0, 0};
+  static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+};
+struct TraceScope {
+  Trace& T; int k; double t0;
+  TraceScope(Trace& T, int k) : T(T), k(k), t0(T.on ? Trace::now() : 0) {}
+  ~TraceScope() { if (T.on) { T.t[k] += Trace::now() - t0; T.n[k]++; } }
+};
+
 struct RansacH {
   mb2_ctx* ctx;
+  Trace tr;
   const double* u; int len; double th; int which, doSymCheck;
   const double* d_u = nullptr;
   // residual buffers: errs[0..3] are buffer ids, errs[4] aliases one of them
@@ -291,6 +318,7 @@ struct RansacH {
 
   // ---- GPU services
   int gpu_resid(int which_, const double* h, double* out, Score* S, double th_) {
+    TraceScope ts(tr, 0);
     int I = 0; double J = 0;
     int r = mb2_score_models(ctx, which_, d_u, len, h, 1, th_, out, &I, &J);
     if (r < 0) { rc = r; return r; }
@@ -339,7 +367,7 @@ struct RansacH {
     maxS = inlidxs(data(errs[4]), len, th, inliers);
     if (maxS.I < 4) return S;
     S = inlidxs(data(errs[4]), len, th * MWM, inliers);
-    u2h(u, inliers, S.I, h);  // __D3__ with D3_H_RATIO 1 and an unlimited inlLimit: all inliers
+    { TraceScope ts(tr, 1); u2h(u, inliers, S.I, h); }  // __D3__ with D3_H_RATIO 1 and an unlimited inlLimit: all inliers
     for (int it = 0; it < steps; it++) {
       eval_into(dbuf, h);
       Ss = inlidxs(bufs[dbuf].d.data(), len, th, inliers);
@@ -354,7 +382,7 @@ struct RansacH {
         std::memcpy(H, h, 9 * sizeof(double));
       }
       if (S.I < 4) return maxS;
-      u2h(u, inliers, S.I, h);
+      { TraceScope ts(tr, 1); u2h(u, inliers, S.I, h); }
       ths -= dth;
     }
     eval_into(dbuf, h);
@@ -396,7 +424,7 @@ struct RansacH {
   Score local_optimisation(int* inliers, double* h, int* iterID) {
     const int d = errs[0];
     Score S = inlidxs(data(errs[4]), len, TC * th * MWM, inliers);
-    u2h(u, inliers, S.I, h);
+    { TraceScope ts(tr, 1); u2h(u, inliers, S.I, h); }
     eval_into(d, h);
     S = inlidxs(bufs[d].d.data(), len, th, inliers);
     return inHrani(inliers, S.I, h, RAN_REP, iterID);
@@ -448,6 +476,7 @@ extern "C" int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, d
   size_t bpos = 0;
   int batch_size = 64;
   auto refill = [&](int want) -> int {
+    TraceScope ts(R.tr, 2);
     batch.clear(); models.clear(); bpos = 0;
     for (int k = 0; k < want; k++) {
       Hyp hy; hy.status = 0; hy.seed_before = cur_seed;
@@ -481,6 +510,7 @@ extern "C" int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, d
     const int K = (int)(models.size() / 9);
     bI.assign(std::max(K, 1), 0); bJ.assign(std::max(K, 1), 0.0);
     if (K > 0) {
+      TraceScope ts2(R.tr, 3);
       int r = mb2_score_models(ctx, R.which, R.d_u, len, models.data(), K, th, nullptr, bI.data(), bJ.data());
       if (r < 0) return r;
     }
@@ -533,7 +563,7 @@ extern "C" int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, d
       // the reference's generator state here: srand(seed_k); 4 draws; 1 draw for the next seed
       R.rng.seed(hy.seed_before);
       for (int i = 0; i < 5; i++) R.rng.next();
-      S = R.local_optimisation(inliers.data(), h, &iterID);
+      { TraceScope ts(R.tr, 4); S = R.local_optimisation(inliers.data(), h, &iterID); }
       if (R.rc < 0) return R.rc;
       if (scoreLess(maxS, S) && (std::fabs(det3(h) / tol_of(h)) > 10e-2)) {
         if (doSymCheck) bad_model = R.sym_check_bad(h);
@@ -570,6 +600,10 @@ extern "C" int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, d
   if (R.rc < 0) return R.rc;
   for (int j = 0; j < len; j++) inl[j] = (maxS.J > 0 || maxS.I > 0) ? (d[j] <= th ? 1 : 0) : 0;
   if (data_out) { data_out[0] = no_sam; data_out[1] = iter_cnt; data_out[2] = no_rej; }
+  if (R.tr.on)
+    std::fprintf(stderr, "[mb2_ransac_h] len %d samples %d LOs %d I %u | resid %d x %.3f ms | u2h %d x %.3f ms | refill %d: %.2f ms (score %.2f) | LO total %.2f ms\n",
+                 len, no_sam, iter_cnt, maxS.I, R.tr.n[0], R.tr.n[0] ? R.tr.t[0] / R.tr.n[0] : 0., R.tr.n[1], R.tr.n[1] ? R.tr.t[1] / R.tr.n[1] : 0.,
+                 R.tr.n[2], R.tr.t[2], R.tr.t[3], R.tr.t[4]);
   if (Jout) *Jout = maxS.J;
   return (int)maxS.I;
 }

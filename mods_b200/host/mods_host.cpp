@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstring>
 #include <ctime>
+#include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace mods {
@@ -255,29 +257,14 @@ int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresen
 // of i's.  The kept set is decided greedily in list order, so a uniform grid over the first image's
 // coordinates (cell = r) gives the identical result in O(T).  (std::sort in the reference is unstable;
 // ties in the sort key keep their input order here.)
-void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, const int mode) {
-  if (r <= 0) return;
-  std::vector<TentativeCorrespExt>& L0 = in_corresp.TCList;
-  const int T = (int)L0.size();
+// Core on plain arrays: xy = n x (x1 y1 x2 y2), key = sort key (ignored when !sorted).  Returns the kept
+// original indices in processing order.
+std::vector<int> duplicate_filter_core(const double* xy_in, const double* key, int T, double r, bool sorted) {
   std::vector<int> order(T);
-  std::vector<double> key(T);
-  for (int i = 0; i < T; i++) {
-    order[i] = i;
-    switch (mode) {
-      case MODE_FGINN: key[i] = std::fabs(L0[i].ratio); break;
-      case MODE_DISTANCE: key[i] = std::fabs(L0[i].d1); break;
-      case MODE_BIGGER_REGION: key[i] = std::fabs(L0[i].first.reproj_kp.s); break;
-      default: key[i] = 0.0;
-    }
-  }
-  if (mode == MODE_FGINN || mode == MODE_DISTANCE || mode == MODE_BIGGER_REGION)
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
-  // coordinates in processing order
+  for (int i = 0; i < T; i++) order[i] = i;
+  if (sorted) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
   std::vector<double> xy((size_t)T * 4);
-  for (int j = 0; j < T; j++) {
-    const TentativeCorrespExt& t = L0[order[j]];
-    xy[4 * j] = t.first.reproj_kp.x; xy[4 * j + 1] = t.first.reproj_kp.y; xy[4 * j + 2] = t.second.reproj_kp.x; xy[4 * j + 3] = t.second.reproj_kp.y;
-  }
+  for (int j = 0; j < T; j++) std::memcpy(&xy[4 * (size_t)j], xy_in + 4 * (size_t)order[j], 4 * sizeof(double));
   const double r_sq = r * r;
   // open-addressing hash of grid cells (cell = r) -> singly linked list of kept entries
   int cap = 1; while (cap < 4 * std::max(T, 1)) cap <<= 1;
@@ -285,7 +272,8 @@ void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, con
   std::vector<int> cell_head(cap, -1), next(T, -1);
   auto cell_of = [&](long long cx, long long cy) { return ((cx & 0x7fffffffLL) << 31) | (cy & 0x7fffffffLL); };
   auto find_slot = [&](long long k) { size_t h = (size_t)(k * 0x9E3779B97F4A7C15ULL) & (cap - 1); while (cell_key[h] != -1 && cell_key[h] != k) h = (h + 1) & (cap - 1); return h; };
-  std::vector<char> keep(T, 1);
+  std::vector<int> kept;
+  kept.reserve(T);
   for (int j = 0; j < T; j++) {
     const double x1 = xy[4 * j], y1 = xy[4 * j + 1], x2 = xy[4 * j + 2], y2 = xy[4 * j + 3];
     const long long cx = (long long)std::floor(x1 / r), cy = (long long)std::floor(y1 / r);
@@ -301,16 +289,36 @@ void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, con
           if (ddx * ddx + ddy * ddy <= r_sq) { dup = true; break; }
         }
       }
-    if (dup) { keep[j] = 0; continue; }
+    if (dup) continue;
     const long long k = cell_of(cx, cy);
     const size_t h = find_slot(k);
     cell_key[h] = k; next[j] = cell_head[h]; cell_head[h] = j;
+    kept.push_back(order[j]);
   }
+  return kept;
+}
+
+void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, const int mode) {
+  if (r <= 0) return;
+  std::vector<TentativeCorrespExt>& L0 = in_corresp.TCList;
+  const int T = (int)L0.size();
+  std::vector<double> key(T), xy((size_t)T * 4);
+  for (int i = 0; i < T; i++) {
+    const TentativeCorrespExt& t = L0[i];
+    switch (mode) {
+      case MODE_FGINN: key[i] = std::fabs(t.ratio); break;
+      case MODE_DISTANCE: key[i] = std::fabs(t.d1); break;
+      case MODE_BIGGER_REGION: key[i] = std::fabs(t.first.reproj_kp.s); break;
+      default: key[i] = 0.0;
+    }
+    xy[4 * (size_t)i] = t.first.reproj_kp.x; xy[4 * (size_t)i + 1] = t.first.reproj_kp.y;
+    xy[4 * (size_t)i + 2] = t.second.reproj_kp.x; xy[4 * (size_t)i + 3] = t.second.reproj_kp.y;
+  }
+  const bool sorted = mode == MODE_FGINN || mode == MODE_DISTANCE || mode == MODE_BIGGER_REGION;
+  std::vector<int> kept = duplicate_filter_core(xy.data(), key.data(), T, r, sorted);
   std::vector<TentativeCorrespExt> L;
-  size_t kept = 0;
-  for (int j = 0; j < T; j++) kept += keep[j];
-  L.reserve(kept);
-  for (int j = 0; j < T; j++) if (keep[j]) L.push_back(std::move(L0[order[j]]));
+  L.reserve(kept.size());
+  for (int i : kept) L.push_back(std::move(L0[i]));
   L0.swap(L);
 }
 
@@ -325,88 +333,109 @@ bool invert3(const double* S, double* D) {  // cv::invert, 3x3 closed form
   D[6] = (S[3] * S[7] - S[4] * S[6]) * d; D[7] = (S[1] * S[6] - S[0] * S[7]) * d; D[8] = (S[0] * S[4] - S[1] * S[3]) * d;
   return true;
 }
-int NaiveHCheck(const TentativeCorrespListExt& corresp, const double* H, const double error) {  // matching.cpp:1171-1200
-  const double err_sq = error * error;
-  double Hinv[9];
-  invert3(H, Hinv);
-  int corr_numb = 0;
-  for (const TentativeCorrespExt& t : corresp.TCList) {
-    const double x1 = t.first.reproj_kp.x, y1 = t.first.reproj_kp.y, x2 = t.second.reproj_kp.x, y2 = t.second.reproj_kp.y;
-    double xa = (H[0] * x1 + H[1] * y1 + H[2]) / (H[6] * x1 + H[7] * y1 + H[8]);
-    double ya = (H[3] * x1 + H[4] * y1 + H[5]) / (H[6] * x1 + H[7] * y1 + H[8]);
-    const double d1 = (x2 - xa) * (x2 - xa) + (y2 - ya) * (y2 - ya);
-    xa = (Hinv[0] * x2 + Hinv[1] * y2 + Hinv[2]) / (Hinv[6] * x2 + Hinv[7] * y2 + Hinv[8]);
-    ya = (Hinv[3] * x2 + Hinv[4] * y2 + Hinv[5]) / (Hinv[6] * x2 + Hinv[7] * y2 + Hinv[8]);
-    const double d2 = (x1 - xa) * (x1 - xa) + (y1 - ya) * (y1 - ya);
-    if ((d1 <= err_sq) && (d2 <= (err_sq))) corr_numb++;
-  }
-  return corr_numb;
-}
 }  // namespace
 
-int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp, double* H,
-                      const RANSACPars pars) {
+// Core on plain arrays.  frames: n x 14 doubles = (x y a11 a12 a21 a22 s) of the first and of the second region
+// (reproj_kp).  inl[n] = DEGENSAC's inlier flags; verified = indices that survive NaiveHCheck / H_LAF_check.
+int loransac_core(mb2_ctx* ctx, const double* frames, int tent_size, const RANSACPars& pars, std::vector<unsigned char>& inl,
+                  std::vector<int>& verified, double* H) {
   const int MIN_POINTS = 8;
-  const unsigned tent_size = (unsigned)in_corresp.TCList.size();
-  ransac_corresp.TCList.clear();
+  inl.assign(std::max(tent_size, 0), 0);
+  verified.clear();
   int max_samples = pars.max_samples;
   if (tent_size <= 20) max_samples = 1000;
   if (pars.useF) return 0;  // epipolar mode (exp_ransacFcustom) is not built: empty output, like a failed run
-  if (tent_size < (unsigned)MIN_POINTS) return 0;
+  if (tent_size < MIN_POINTS) return 0;
   std::vector<double> u((size_t)tent_size * 6);
-  for (unsigned i = 0; i < tent_size; i++) {
-    const TentativeCorrespExt& t = in_corresp.TCList[i];
+  for (int i = 0; i < tent_size; i++) {
+    const double* f = frames + (size_t)i * 14;
     double* p = &u[(size_t)i * 6];
-    p[0] = t.first.reproj_kp.x; p[1] = t.first.reproj_kp.y; p[2] = 1.; p[3] = t.second.reproj_kp.x; p[4] = t.second.reproj_kp.y; p[5] = 1.;
+    p[0] = f[0]; p[1] = f[1]; p[2] = 1.; p[3] = f[7]; p[4] = f[8]; p[5] = 1.;
   }
   double Hloran[9];
-  std::vector<unsigned char> inl(tent_size);
   int data_out[3];
   double J = 0;
   const long seed = pars.seed ? pars.seed : (long)time(NULL);
-  int I = mb2_ransac_h(ctx, u.data(), (int)tent_size, pars.err_threshold * pars.err_threshold, pars.confidence, max_samples,
+  int I = mb2_ransac_h(ctx, u.data(), tent_size, pars.err_threshold * pars.err_threshold, pars.confidence, max_samples,
                        (int)pars.errorType, pars.doSymmCheck, seed, Hloran, inl.data(), data_out, &J);
   if (I < 0) return 0;
-  for (unsigned i = 0; i < tent_size; i++) {
-    in_corresp.TCList[i].isTrue = inl[i];
-    if (inl[i] || pars.justMarkOutliers) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
-  }
+  for (int i = 0; i < tent_size; i++) if (inl[i] || pars.justMarkOutliers) verified.push_back(i);
   // H = inv(Hloran^T) (matching.cpp:920-938)
   const double Ht[9] = {Hloran[0], Hloran[3], Hloran[6], Hloran[1], Hloran[4], Hloran[7], Hloran[2], Hloran[5], Hloran[8]};
   double Hinv[9];
   invert3(Ht, Hinv);
   bool nonzero = false;
   for (int i = 0; i < 9; i++) nonzero = nonzero || (Hinv[i] != 0.0);
-  if (!nonzero) { ransac_corresp.TCList.clear(); return 0; }
-  for (int i = 0; i < 9; i++) { ransac_corresp.H[i] = Hinv[i]; H[i] = Hinv[i]; }
-  if (NaiveHCheck(ransac_corresp, ransac_corresp.H, 10.0) < MIN_POINTS) ransac_corresp.TCList.clear();  // DO_TRANSFER_H_CHECK
+  if (!nonzero) { verified.clear(); return 0; }
+  for (int i = 0; i < 9; i++) H[i] = Hinv[i];
+  {  // NaiveHCheck (matching.cpp:1171-1200), DO_TRANSFER_H_CHECK
+    const double err_sq = 10.0 * 10.0;
+    double Hi[9];
+    invert3(H, Hi);
+    int corr_numb = 0;
+    for (int i : verified) {
+      const double* f = frames + (size_t)i * 14;
+      const double x1 = f[0], y1 = f[1], x2 = f[7], y2 = f[8];
+      double xa = (H[0] * x1 + H[1] * y1 + H[2]) / (H[6] * x1 + H[7] * y1 + H[8]);
+      double ya = (H[3] * x1 + H[4] * y1 + H[5]) / (H[6] * x1 + H[7] * y1 + H[8]);
+      const double d1 = (x2 - xa) * (x2 - xa) + (y2 - ya) * (y2 - ya);
+      xa = (Hi[0] * x2 + Hi[1] * y2 + Hi[2]) / (Hi[6] * x2 + Hi[7] * y2 + Hi[8]);
+      ya = (Hi[3] * x2 + Hi[4] * y2 + Hi[5]) / (Hi[6] * x2 + Hi[7] * y2 + Hi[8]);
+      const double d2 = (x1 - xa) * (x1 - xa) + (y1 - ya) * (y1 - ya);
+      if ((d1 <= err_sq) && (d2 <= (err_sq))) corr_numb++;
+    }
+    if (corr_numb < MIN_POINTS) verified.clear();
+  }
   // H_LAF_check (matching.cpp:251-309): three points per local affine frame scored with HDsSymMax in one batch
   const double affineFerror = 3.0 * pars.HLAFCoef * pars.err_threshold;
-  if (affineFerror > 0 && !ransac_corresp.TCList.empty()) {
+  if (affineFerror > 0 && !verified.empty()) {
     const double k_sigma = 3.0;  // matching.cpp:172
-    const size_t n = ransac_corresp.TCList.size();
+    const size_t n = verified.size();
     std::vector<double> u3(n * 18), err(n * 3);
     for (size_t l = 0; l < n; l++) {
-      const TentativeCorrespExt& t = ransac_corresp.TCList[l];
+      const double* f = frames + (size_t)verified[l] * 14;   // x y a11 a12 a21 a22 s | x y a11 a12 a21 a22 s
       double* q = &u3[l * 18];
-      q[0] = t.first.reproj_kp.x; q[1] = t.first.reproj_kp.y; q[2] = 1.0;
-      q[3] = t.second.reproj_kp.x; q[4] = t.second.reproj_kp.y; q[5] = 1.0;
-      q[6] = q[0] + k_sigma * t.first.reproj_kp.a12 * t.first.reproj_kp.s; q[7] = q[1] + k_sigma * t.first.reproj_kp.a22 * t.first.reproj_kp.s; q[8] = 1.0;
-      q[9] = q[3] + k_sigma * t.second.reproj_kp.a12 * t.second.reproj_kp.s; q[10] = q[4] + k_sigma * t.second.reproj_kp.a22 * t.second.reproj_kp.s; q[11] = 1.0;
-      q[12] = q[0] + k_sigma * t.first.reproj_kp.a11 * t.first.reproj_kp.s; q[13] = q[1] + k_sigma * t.first.reproj_kp.a21 * t.first.reproj_kp.s; q[14] = 1.0;
-      q[15] = q[3] + k_sigma * t.second.reproj_kp.a11 * t.second.reproj_kp.s; q[16] = q[4] + k_sigma * t.second.reproj_kp.a21 * t.second.reproj_kp.s; q[17] = 1.0;
+      q[0] = f[0]; q[1] = f[1]; q[2] = 1.0;
+      q[3] = f[7]; q[4] = f[8]; q[5] = 1.0;
+      q[6] = q[0] + k_sigma * f[3] * f[6]; q[7] = q[1] + k_sigma * f[5] * f[6]; q[8] = 1.0;
+      q[9] = q[3] + k_sigma * f[10] * f[13]; q[10] = q[4] + k_sigma * f[12] * f[13]; q[11] = 1.0;
+      q[12] = q[0] + k_sigma * f[2] * f[6]; q[13] = q[1] + k_sigma * f[4] * f[6]; q[14] = 1.0;
+      q[15] = q[3] + k_sigma * f[9] * f[13]; q[16] = q[4] + k_sigma * f[11] * f[13]; q[17] = 1.0;
     }
-    if (mb2_score_models(ctx, 2 /*HDsSymMax*/, u3.data(), (int)(n * 3), Hloran, 1, 0.0, err.data(), nullptr, nullptr) < 0) return 0;
-    std::vector<TentativeCorrespExt> good;
+    if (mb2_score_models(ctx, 2 /*HDsSymMax*/, u3.data(), (int)(n * 3), Hloran, 1, 0.0, err.data(), nullptr, nullptr) < 0) { verified.clear(); return 0; }
+    std::vector<int> good;
     good.reserve(n);
     for (size_t l = 0; l < n; l++) {
       const double sumErr = std::sqrt(err[3 * l] + err[3 * l + 1] + err[3 * l + 2]);
-      if (!(sumErr > affineFerror)) good.push_back(ransac_corresp.TCList[l]);
+      if (!(sumErr > affineFerror)) good.push_back(verified[l]);
     }
-    ransac_corresp.TCList.swap(good);
+    verified.swap(good);
   }
-  if ((int)ransac_corresp.TCList.size() < MIN_POINTS) ransac_corresp.TCList.clear();
-  return (int)ransac_corresp.TCList.size();
+  if ((int)verified.size() < MIN_POINTS) verified.clear();
+  return (int)verified.size();
+}
+
+namespace {
+void frame14(const AffineKeypoint& a, const AffineKeypoint& b, double* f) {
+  f[0] = a.x; f[1] = a.y; f[2] = a.a11; f[3] = a.a12; f[4] = a.a21; f[5] = a.a22; f[6] = a.s;
+  f[7] = b.x; f[8] = b.y; f[9] = b.a11; f[10] = b.a12; f[11] = b.a21; f[12] = b.a22; f[13] = b.s;
+}
+}  // namespace
+
+int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& ransac_corresp, double* H,
+                      const RANSACPars pars) {
+  const int n = (int)in_corresp.TCList.size();
+  ransac_corresp.TCList.clear();
+  std::vector<double> frames((size_t)n * 14);
+  for (int i = 0; i < n; i++) frame14(in_corresp.TCList[i].first.reproj_kp, in_corresp.TCList[i].second.reproj_kp, &frames[(size_t)i * 14]);
+  std::vector<unsigned char> inl;
+  std::vector<int> verified;
+  double Hout[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int k = loransac_core(ctx, frames.data(), n, pars, inl, verified, Hout);
+  for (int i = 0; i < n && i < (int)inl.size(); i++) in_corresp.TCList[i].isTrue = inl[i];
+  for (int i : verified) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
+  for (int i = 0; i < 9; i++) { ransac_corresp.H[i] = Hout[i]; H[i] = Hout[i]; }
+  return k;
 }
 
 }  // namespace mods
@@ -427,6 +456,34 @@ extern "C" int mb2_host_duplicate_filter(const double* xy /* n x 4: x1 y1 x2 y2 
 }
 
 // ---- one MODS iteration on one pair ---------------------------------------------------------------
+namespace {
+// second context (own stream) for the second image of a pair, created on first use, one per primary context
+std::mutex g_sib_mutex;
+std::unordered_map<mb2_ctx*, mb2_ctx*> g_siblings;
+mb2_ctx* sibling_ctx(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_sib_mutex);
+  auto it = g_siblings.find(ctx);
+  if (it != g_siblings.end()) return it->second;
+  mb2_ctx* c2 = nullptr;
+  if (mb2_ctx_create(mb2_ctx_device(ctx), &c2) != MB2_OK) c2 = nullptr;
+  g_siblings[ctx] = c2;
+  return c2;
+}
+}  // namespace
+
+extern "C" long long mb2_mods_launch_count(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_sib_mutex);
+  auto it = g_siblings.find(ctx);
+  return mb2_ctx_launch_count(ctx) + (it != g_siblings.end() && it->second ? mb2_ctx_launch_count(it->second) : 0);
+}
+extern "C" void mb2_mods_release(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_sib_mutex);
+  auto it = g_siblings.find(ctx);
+  if (it == g_siblings.end()) return;
+  if (it->second) mb2_ctx_destroy(it->second);
+  g_siblings.erase(it);
+}
+
 extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
   mods::DetectorsParameters dp; mods::DescriptorsParameters sp;
   c->det = dp.HessParam;
@@ -458,36 +515,67 @@ extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, co
   RANSACPars rp; rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
   rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
 
-  // mods.cpp:229-415, one step
-  ImageRepresentation ImgRep1(ctx, GrayImage{img1, h1, w1}, "img1", 0), ImgRep2(ctx, GrayImage{img2, h2, w2}, "img2", 1);
+  // mods.cpp:229-415, one step.  The two images go through SynthDetectDescribeKeypoints on two host threads
+  // (mods.cpp:255-271 runs them as two OpenMP tasks), each with its own context / stream; matching, duplicate
+  // filtering and verification then run on the region blocks and index lists directly (the AoS
+  // TentativeCorrespListExt of the reference is only materialised by the class API, not on this fast path).
+  mb2_ctx* ctx2 = mb2_ctx_profiling(ctx) ? nullptr : sibling_ctx(ctx);   // per-kernel profiling keeps everything on one stream
+  ImageRepresentation ImgRep1(ctx, GrayImage{img1, h1, w1}, "img1", 0), ImgRep2(ctx2 ? ctx2 : ctx, GrayImage{img2, h2, w2}, "img2", 1);
   double t0 = now_ms();
-  ImgRep1.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
-  ImgRep2.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+  if (ctx2) {
+    std::thread th([&] { ImgRep2.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom); });
+    ImgRep1.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+    th.join();
+    if (mb2_slot_move(ctx, 1, ctx2, 1) < 0) return MB2_ERR_CUDA;
+  } else {
+    ImgRep1.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+    ImgRep2.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+  }
   res->ms_detect_describe = now_ms() - t0;
   res->regions1 = ImgRep1.GetDescriptorsNumber(desc_name); res->regions2 = ImgRep2.GetDescriptorsNumber(desc_name);
-  t0 = now_ms();
-  CorrespondenceBank Tentatives(ctx);
-  Tentatives.MatchImgReps(ImgRep1, ImgRep2, iters, wtm, mp, desc_par);
-  TentativeCorrespListExt tentatives = Tentatives.TakeCorrespondences();  // == GetCorresponcesVector() without the deep copy
-  res->ms_match = now_ms() - t0;
-  res->tentatives = (int)tentatives.TCList.size();
-  t0 = now_ms();
-  DuplicateFiltering(tentatives, cfg->duplicateDist, MODE_FGINN);   // whichCorrespondenceRemains=bestFGINN
-  res->ms_duplicate = now_ms() - t0;
-  res->unique_tentatives = (int)tentatives.TCList.size();
-  t0 = now_ms();
-  TentativeCorrespListExt verified;
-  int n = LORANSACFiltering(ctx, tentatives, verified, verified.H, rp);
-  res->ms_ransac = now_ms() - t0;
-  for (const auto& t : tentatives.TCList) res->ransac_inliers += t.isTrue;
-  res->verified = n;
-  for (int i = 0; i < 9; i++) res->H[i] = verified.H[i];
-  if (verified_out)
-    for (int i = 0; i < n && i < capacity; i++) {
-      const auto& t = verified.TCList[i];
-      verified_out[4 * i] = t.first.reproj_kp.x; verified_out[4 * i + 1] = t.first.reproj_kp.y;
-      verified_out[4 * i + 2] = t.second.reproj_kp.x; verified_out[4 * i + 3] = t.second.reproj_kp.y;
+  const ImageRepresentation::RegionBlock* Q = ImgRep1.block("HessianAffine", desc_name);
+  const ImageRepresentation::RegionBlock* T = ImgRep2.block("HessianAffine", desc_name);
+  int n = 0;
+  if (Q && T && Q->n > 0 && T->n > 0) {
+    t0 = now_ms();
+    std::vector<double> rows((size_t)Q->n * 7);
+    int nt = mb2_match_slots(ctx, 0, 1, cfg->matchRatio, cfg->contradDist, 50, rows.data(), Q->n);   // MatchImgReps -> MatchFlannFGINN
+    if (nt < 0) return nt;
+    res->ms_match = now_ms() - t0;
+    res->tentatives = nt;
+    t0 = now_ms();
+    std::vector<double> xy((size_t)nt * 4), key(nt);
+    for (int i = 0; i < nt; i++) {
+      const double* r = &rows[(size_t)i * 7];
+      const double* a = &Q->reproj_kp[(size_t)r[0] * MB2_KP];
+      const double* b = &T->reproj_kp[(size_t)r[1] * MB2_KP];
+      xy[4 * (size_t)i] = a[0]; xy[4 * (size_t)i + 1] = a[1]; xy[4 * (size_t)i + 2] = b[0]; xy[4 * (size_t)i + 3] = b[1];
+      key[i] = std::fabs(std::sqrt((double)((float)r[4] / (float)r[5])));
     }
+    std::vector<int> kept = duplicate_filter_core(xy.data(), key.data(), nt, cfg->duplicateDist, true);  // DuplicateFiltering(.., MODE_FGINN)
+    res->ms_duplicate = now_ms() - t0;
+    res->unique_tentatives = (int)kept.size();
+    t0 = now_ms();
+    std::vector<double> frames(kept.size() * 14);
+    for (size_t i = 0; i < kept.size(); i++) {
+      const double* r = &rows[(size_t)kept[i] * 7];
+      const double* a = &Q->reproj_kp[(size_t)r[0] * MB2_KP];
+      const double* b = &T->reproj_kp[(size_t)r[1] * MB2_KP];
+      double* f = &frames[i * 14];
+      for (int j = 0; j < 7; j++) { f[j] = a[j]; f[7 + j] = b[j]; }   // KP layout starts with x y a11 a12 a21 a22 s
+    }
+    std::vector<unsigned char> inl;
+    std::vector<int> verified;
+    n = loransac_core(ctx, frames.data(), (int)kept.size(), rp, inl, verified, res->H);    // LORANSACFiltering
+    res->ms_ransac = now_ms() - t0;
+    for (unsigned char b : inl) res->ransac_inliers += b;
+    res->verified = n;
+    if (verified_out)
+      for (int i = 0; i < n && i < capacity; i++) {
+        const double* f = &frames[(size_t)verified[i] * 14];
+        verified_out[4 * i] = f[0]; verified_out[4 * i + 1] = f[1]; verified_out[4 * i + 2] = f[7]; verified_out[4 * i + 3] = f[8];
+      }
+  }
   res->ms_total = now_ms() - t_start;
   return n;
 }

@@ -114,9 +114,8 @@ class ImageRepresentation {
   void SynthDetectDescribeKeypoints(IterationViewsynthesisParam& synth_par, DetectorsParameters& det_par,
                                     DescriptorsParameters& desc_par, DominantOrientationParams& dom_ori_par);
   GrayImage OriginalImg;
-
- protected:
   friend class CorrespondenceBank;
+
   // Regions live as the SoA blocks the C ABI returns; the AoS AffineRegionVector the reference keeps in
   // RegionVectorMap[det][desc] (imagerepresentation.h:66) is materialised on demand (GetAffineRegionVector).
   struct RegionBlock {
@@ -127,6 +126,14 @@ class ImageRepresentation {
     std::vector<int> img_id;                // view index per region
     AffineRegion region(int i, bool with_desc) const;
   };
+ public:
+  const RegionBlock* block(const std::string& det, const std::string& desc) const {
+    auto d = Blocks.find(det);
+    if (d == Blocks.end()) return nullptr;
+    auto e = d->second.find(desc);
+    return e == d->second.end() ? nullptr : &e->second;
+  }
+ protected:
   mb2_ctx* ctx;
   TimeLog TimeSpent;
   std::map<std::string, std::map<std::string, RegionBlock> > Blocks;  // [det][desc]
@@ -157,6 +164,10 @@ int MatchFlannFGINN(mb2_ctx* ctx, const AffineRegionList& list1, const AffineReg
 void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r = 3.0, const int mode = MODE_RANDOM);
 int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& out_corresp, double* H,
                       const RANSACPars pars);
+// the same two steps on plain arrays (what the class API calls underneath)
+std::vector<int> duplicate_filter_core(const double* xy, const double* key, int n, double r, bool sorted);
+int loransac_core(mb2_ctx* ctx, const double* frames14, int n, const RANSACPars& pars, std::vector<unsigned char>& inl,
+                  std::vector<int>& verified, double* H);
 
 }  // namespace mods
 
@@ -181,4 +192,8 @@ void mb2_pair_config_default(mb2_pair_config* c);
 /* images: gray f32 [H|D].  verified_out (optional): capacity rows of 4 doubles (x1 y1 x2 y2).  Returns verified count or < 0. */
 int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2, const mb2_pair_config* cfg,
                   mb2_pair_result* res, double* verified_out, int capacity);
+/* kernels launched by ctx and by the helper context mb2_mods_pair keeps for the second image */
+long long mb2_mods_launch_count(mb2_ctx* ctx);
+/* destroys the helper context of ctx (call before mb2_ctx_destroy(ctx)) */
+void mb2_mods_release(mb2_ctx* ctx);
 }

@@ -270,3 +270,80 @@ def test_ransac_h_degenerate_inputs(ctx):
     assert ctx.ransac_h(np.zeros((0, 6)))["I"] == 0
     u = np.zeros((3, 6)); u[:, 2] = 1; u[:, 5] = 1
     assert ctx.ransac_h(u)["I"] == 0
+
+
+# ---- one mods.cpp iteration through the host mirror (libmods_host.so) -------------------------------
+def _dup_filter_bruteforce(xy, key, r):
+    """matching.cpp:2983-3047: stable sort by key, drop an entry when a kept one is within r in both images."""
+    order = np.argsort(key, kind="stable")
+    kept = []
+    for j in order:
+        ok = True
+        for i in kept:
+            if (xy[i, 0] - xy[j, 0]) ** 2 + (xy[i, 1] - xy[j, 1]) ** 2 <= r * r and (xy[i, 2] - xy[j, 2]) ** 2 + (xy[i, 3] - xy[j, 3]) ** 2 <= r * r:
+                ok = False
+                break
+        if ok:
+            kept.append(j)
+    return np.array(kept, dtype=np.int64)
+
+
+def test_mods_pair_equals_stage_composition(ctx, oracle):
+    import mods_b200 as mb
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(480, 360, seed=21, n_blobs=500)
+    B = warp_image(A, gt_homography(480, 360), seed=22)
+    cfg = mb.PairConfig.default()
+    cfg.seed = 4242
+    res, ver = ctx.mods_pair(A, B, cfg, capacity=4096)
+    oa, ob = oracle.view_pipeline(A), oracle.view_pipeline(B)
+    assert (res.regions1, res.regions2) == (len(oa[0]), len(ob[0]))
+    om = oracle.match_fginn(oa[2], ob[2], np.ascontiguousarray(ob[1][:, :2]), ratio=cfg.matchRatio, contradDist=cfg.contradDist)
+    assert res.tentatives == len(om)
+    qi, ti = om[:, 0].astype(int), om[:, 1].astype(int)
+    xy = np.concatenate([oa[1][qi, :2], ob[1][ti, :2]], axis=1)
+    key = np.abs(np.sqrt((om[:, 4].astype(np.float32) / om[:, 5].astype(np.float32)).astype(np.float64)))
+    kept = _dup_filter_bruteforce(xy, key, cfg.duplicateDist)
+    assert res.unique_tentatives == len(kept)
+    u = np.ones((len(kept), 6)); u[:, 0:2] = xy[kept, 0:2]; u[:, 3:5] = xy[kept, 2:4]
+    r = ctx.ransac_h(u, th=cfg.err_threshold ** 2, conf=cfg.confidence, max_sam=cfg.max_samples if len(kept) > 20 else 1000,
+                     errorType=cfg.errorType, doSymCheck=cfg.doSymmCheck, seed=cfg.seed)
+    assert res.ransac_inliers == int(r["inl"].sum())
+    assert 8 <= res.verified <= res.ransac_inliers
+    # verified pairs obey the ground-truth homography
+    Hgt = gt_homography(480, 360)
+    p = np.c_[ver[:, :2], np.ones(len(ver))] @ Hgt.T
+    assert np.median(np.hypot(p[:, 0] / p[:, 2] - ver[:, 2], p[:, 1] / p[:, 2] - ver[:, 3])) < 1.5
+
+
+def test_mods_pair_two_streams_equals_one(ctx):
+    """Both images on two contexts / host threads (default) == everything on one stream (profiling mode)."""
+    import mods_b200 as mb
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(640, 480, seed=31, n_blobs=900)
+    B = warp_image(A, gt_homography(640, 480), seed=32)
+    cfg = mb.PairConfig.default()
+    cfg.seed = 7
+    r2, v2 = ctx.mods_pair(A, B, cfg, capacity=8192)
+    ctx.profile_begin()
+    r1, v1 = ctx.mods_pair(A, B, cfg, capacity=8192)
+    prof = ctx.profile_end()
+    assert any("k_nn_tc" in k or "k_nn_simt" in k for k in prof)
+    for f in ("regions1", "regions2", "tentatives", "unique_tentatives", "ransac_inliers", "verified"):
+        assert getattr(r1, f) == getattr(r2, f), f
+    assert np.array_equal(v1, v2) and np.array_equal(np.array(r1.H[:]), np.array(r2.H[:]))
+
+
+def test_slot_move(ctx):
+    import mods_b200 as mb
+    from synth import blob_image
+    A = blob_image(320, 240, seed=11)
+    c2 = mb.Context(0)
+    try:
+        ga = ctx.detect_describe_view(A, slot=0)
+        gb = c2.detect_describe_view(A, slot=3)
+        c2.slot_move_to(ctx, 1, 3)
+        m = ctx.match_slots(0, 1, ratio=0.8, contradDist=0.0)
+        assert len(gb[0]) == len(ga[0]) and len(m) > 0 and np.array_equal(m[:, 0], m[:, 1])  # identical sets: every match is i -> i
+    finally:
+        c2.close()
