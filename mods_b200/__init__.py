@@ -281,6 +281,26 @@ class Context:
                                                  C.byref(cfg), C.byref(res), _ptr(out), C.c_int(capacity)), "mods_pair")
         return res, (out[:min(n, capacity)] if capacity else None)
 
+    def mods_pairs(self, pairs, cfg=None, shapes=None, capacity=0):
+        """A list of independent pairs through the pipelined driver (mb2_mods_pairs).  pairs: [(img1, img2), ...] (numpy
+        arrays, or torch tensors / device pointers together with shapes=[((h1, w1), (h2, w2)), ...]).
+        Returns ([PairResult], [verified arrays or None])."""
+        n = len(pairs)
+        cfg = cfg or PairConfig.default()
+        P = C.c_void_p * max(1, n); I = C.c_int * max(1, n)
+        p1, p2, w1, h1, w2, h2 = P(), P(), I(), I(), I(), I()
+        for k, (a, b) in enumerate(pairs):
+            (ha, wa), (hb, wb) = shapes[k] if shapes is not None else (a.shape, b.shape)
+            p1[k] = _ptr(a).value; p2[k] = _ptr(b).value
+            w1[k], h1[k], w2[k], h2[k] = wa, ha, wb, hb
+        res = (PairResult * max(1, n))()
+        outs = [np.zeros((capacity, 4)) for _ in range(n)] if capacity else None
+        vo = P(*[o.ctypes.data for o in outs]) if capacity and n else None
+        caps = I(*([capacity] * n)) if capacity and n else None
+        self._check(host_lib().mb2_mods_pairs(self.h, C.c_int(n), p1, w1, h1, p2, w2, h2, C.byref(cfg), res, vo, caps), "mods_pairs")
+        results = [res[k] for k in range(n)]
+        return results, ([outs[k][:min(results[k].verified, capacity)] for k in range(n)] if capacity else None)
+
     def ransac_h(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1):
         u = np.ascontiguousarray(u, np.float64)
         n = len(u)

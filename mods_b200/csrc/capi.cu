@@ -634,7 +634,7 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->img, &ctx->pyr, &ctx->resp, &ctx->cand, &ctx->misc, &ctx->kp_a, &ctx->kp_b, &ctx->kp_c, &ctx->desc_u8,
-                    &ctx->patch_scratch, &ctx->nn_a, &ctx->nn_b, &ctx->nn_c, &ctx->nn_d, &ctx->rs_a, &ctx->rs_b, &ctx->rs_c, &ctx->octmap};
+                    &ctx->patch_scratch, &ctx->nn_a, &ctx->nn_b, &ctx->nn_c, &ctx->nn_d, &ctx->rs_a, &ctx->rs_b, &ctx->rs_c, &ctx->rs_u, &ctx->octmap};
   for (DevBuf* b : bufs) b->release();
   for (auto& s : ctx->slots) { s.desc.release(); s.xy.release(); }
   ctx->h_a.release(); ctx->h_b.release(); ctx->h_c.release();
@@ -883,11 +883,14 @@ int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const do
     MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->rs_b.p, h_models, (size_t)K * 72, cudaMemcpyHostToDevice, ctx->stream));
     dm = ctx->rs_b.p;
   }
-  MB2_CUDA_CHECK(ctx, ctx->rs_c.reserve(rbytes + (size_t)K * 16 + 64));
+  const size_t pbytes = (J || I) ? mb2_score_partial_bytes(len, K) : 0;
+  MB2_CUDA_CHECK(ctx, ctx->rs_c.reserve(rbytes + (size_t)K * 16 + pbytes + 128));
   double* d_J = ctx->rs_c.as<double>();
   int* d_I = (int*)(d_J + K);
-  double* d_res = resid ? (double*)(((uintptr_t)(d_I + K) + 15) & ~(uintptr_t)15) : nullptr;
-  mb2_launch_score(ctx, which, (const double*)du, len, (const double*)dm, K, th, d_res, d_I, d_J);
+  double* d_res = (double*)(((uintptr_t)(d_I + K) + 15) & ~(uintptr_t)15);
+  void* d_part = (void*)(((uintptr_t)(d_res + (rbytes / 8)) + 15) & ~(uintptr_t)15);
+  mb2_launch_score(ctx, which, (const double*)du, len, (const double*)dm, K, th, resid ? d_res : nullptr, (J || I) ? d_I : nullptr,
+                   (J || I) ? d_J : nullptr, d_part);
   if (J || I) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(h_J, d_J, (size_t)K * 12, cudaMemcpyDeviceToHost, ctx->stream));
   if (resid) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(h_res, d_res, rbytes, cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -143,14 +143,10 @@ __device__ __forceinline__ double truncQuad_dev(double epsilon, double thr) {
 
 constexpr int ST = 256;
 
-// grid = (K models); each CTA walks all n correspondences (coalesced on the 6-double records).
-__global__ void __launch_bounds__(ST)
-k_score(int which, const double* __restrict__ u, int len, const double* __restrict__ models, double th,
-        double* __restrict__ resid, int* __restrict__ I_out, double* __restrict__ J_out) {
-  __shared__ double sM[9], sHinv[9], sH1[9];
-  __shared__ double sJ[ST];
-  __shared__ int sI[ST];
-  const int k = blockIdx.x, tid = threadIdx.x;
+struct Partial { double J; int I; int pad; };
+
+__device__ __forceinline__ void load_model(int which, const double* __restrict__ models, int k, double* sM, double* sHinv, double* sH1) {
+  const int tid = threadIdx.x;
   if (tid < 9) sM[tid] = models[(size_t)k * 9 + tid];
   __syncthreads();
   if (tid == 0 && (which == 1 || which == 2)) {
@@ -161,8 +157,22 @@ k_score(int which, const double* __restrict__ u, int len, const double* __restri
     for (int i = 0; i < 9; i++) sH1[i] = inv[i];
   }
   __syncthreads();
+}
+
+// grid = (K models, S segments of `chunk` correspondences).  A CTA walks its segment with coalesced loads of
+// the 6-double records, writes the residuals (optional) and one (I, J) partial; k_score_sum adds the S
+// partials of a model in segment order, so the MSAC sum is a fixed-order tree sum whatever the grid is.
+__global__ void __launch_bounds__(ST)
+k_score(int which, const double* __restrict__ u, int len, int chunk, const double* __restrict__ models, double th,
+        double* __restrict__ resid, Partial* __restrict__ part) {
+  __shared__ double sM[9], sHinv[9], sH1[9];
+  __shared__ double sJ[ST];
+  __shared__ int sI[ST];
+  const int k = blockIdx.x, seg = blockIdx.y, tid = threadIdx.x;
+  load_model(which, models, k, sM, sHinv, sH1);
+  const int lo = seg * chunk, hi = min(len, lo + chunk);
   double J = 0; int I = 0;
-  for (int i = tid; i < len; i += ST) {
+  for (int i = lo + tid; i < hi; i += ST) {
     double p[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) p[j] = u[(size_t)i * 6 + j];
@@ -178,20 +188,46 @@ k_score(int which, const double* __restrict__ u, int len, const double* __restri
     if (d <= th) I++;
     J += truncQuad_dev(d, th);
   }
+  if (!part) return;
   sJ[tid] = J; sI[tid] = I;
   __syncthreads();
   for (int s = ST / 2; s > 0; s >>= 1) {
     if (tid < s) { sJ[tid] += sJ[tid + s]; sI[tid] += sI[tid + s]; }
     __syncthreads();
   }
-  if (tid == 0) { if (I_out) I_out[k] = sI[0]; if (J_out) J_out[k] = sJ[0]; }
+  if (tid == 0) { Partial P; P.J = sJ[0]; P.I = sI[0]; P.pad = 0; part[(size_t)k * gridDim.y + seg] = P; }
+}
+
+__global__ void k_score_sum(const Partial* __restrict__ part, int K, int S, int* __restrict__ I_out, double* __restrict__ J_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double J = 0; int I = 0;
+  for (int s = 0; s < S; s++) { J += part[(size_t)k * S + s].J; I += part[(size_t)k * S + s].I; }
+  if (I_out) I_out[k] = I;
+  if (J_out) J_out[k] = J;
 }
 
 }  // namespace
 using namespace MB2_NS;
 
+// Segment plan: enough CTAs to fill the 148 SMs a few times over when there are few models.
+void mb2_score_plan(int len, int K, int* S, int* chunk) {
+  int s = (4 * 148 + K - 1) / K;
+  const int max_s = (len + ST - 1) / ST;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  int c = (len + s - 1) / s;
+  c = (c + ST - 1) / ST * ST;
+  *chunk = c; *S = (len + c - 1) / c;
+}
+size_t mb2_score_partial_bytes(int len, int K) { int S, c; mb2_score_plan(len, K, &S, &c); return (size_t)K * S * sizeof(Partial); }
+
 void mb2_launch_score(mb2_ctx* ctx, int which, const double* d_u, int len, const double* d_models, int K, double th, double* d_resid,
-                      int* d_I, double* d_J) {
-  if (K <= 0) return;
-  MB2_LAUNCH(ctx, k_score, K, ST, 0, which, d_u, len, d_models, th, d_resid, d_I, d_J);
+                      int* d_I, double* d_J, void* d_partials) {
+  if (K <= 0 || len <= 0) return;
+  int S, chunk;
+  mb2_score_plan(len, K, &S, &chunk);
+  const bool want = d_I || d_J;
+  MB2_LAUNCH(ctx, k_score, dim3(K, S), ST, 0, which, d_u, len, chunk, d_models, th, d_resid, want ? (Partial*)d_partials : (Partial*)nullptr);
+  if (want) MB2_LAUNCH(ctx, k_score_sum, (K + 127) / 128, 128, 0, (const Partial*)d_partials, K, S, d_I, d_J);
 }

@@ -59,6 +59,12 @@ inline Score inlidxs(const double* err, int len, double th, int* inl) {
   }
   return s;
 }
+// same index list and count, without the MSAC sum (for the call sites that only read S.I and the list)
+inline unsigned inlidxs_count(const double* err, int len, double th, int* inl) {
+  unsigned I = 0;
+  for (int i = 0; i < len; ++i) { inl[I] = i; I += err[i] <= th ? 1u : 0u; }
+  return I;
+}
 inline int nsamples(int ninl, int ptNum, int samsiz, double conf) {
   double a = 1, b = 1;
   for (int i = 0; i < samsiz; i++) { a *= ninl - i; b *= ptNum - i; }
@@ -241,9 +247,13 @@ void u2h(const double* u, const int* inl, int len, double* H) {
         r0[3 * j] = b[j]; r0[3 * j + 1] = 0; r0[3 * j + 2] = -a[0] * b[j];
         r1[3 * j] = 0; r1[3 * j + 1] = b[j]; r1[3 * j + 2] = -a[1] * b[j];
       }
+      // r0 is zero at columns 1, 4, 7 and r1 at 0, 3, 6: those products are +-0 and leave the sums unchanged
       int t = 0;
       for (int p = 0; p < 9; p++)
-        for (int q = 0; q <= p; q++, t++) { acc[t] += r0[p] * r0[q]; acc[t] += r1[p] * r1[q]; }
+        for (int q = 0; q <= p; q++, t++) {
+          if (p % 3 != 1 && q % 3 != 1) acc[t] += r0[p] * r0[q];
+          if (p % 3 != 0 && q % 3 != 0) acc[t] += r1[p] * r1[q];
+        }
     }
   }
   double acc[45];
@@ -366,7 +376,7 @@ struct RansacH {
     const double dth = (ths - th) / (steps);
     maxS = inlidxs(data(errs[4]), len, th, inliers);
     if (maxS.I < 4) return S;
-    S = inlidxs(data(errs[4]), len, th * MWM, inliers);
+    S.I = inlidxs_count(data(errs[4]), len, th * MWM, inliers);
     { TraceScope ts(tr, 1); u2h(u, inliers, S.I, h); }  // __D3__ with D3_H_RATIO 1 and an unlimited inlLimit: all inliers
     for (int it = 0; it < steps; it++) {
       eval_into(dbuf, h);
@@ -375,7 +385,7 @@ struct RansacH {
       const int ret = ht.contains(hash, Ss.I, iterID);
       if (ret != -1 && ret != iterID) { S.I = 0; S.J = 0; return S; }
       if (ret == -1) ht.insert(hash, Ss.I, iterID);
-      S = inlidxs(bufs[dbuf].d.data(), len, ths * MWM, inliers);
+      S.I = inlidxs_count(bufs[dbuf].d.data(), len, ths * MWM, inliers);
       if (scoreLess(maxS, Ss)) {
         maxS = Ss;
         errs[1] = errs[0]; errs[0] = dbuf; dbuf = errs[1];
@@ -423,11 +433,11 @@ struct RansacH {
   // case 4 of the iteration switch (exp_ranH.c:1012-1035 / 1151-1174)
   Score local_optimisation(int* inliers, double* h, int* iterID) {
     const int d = errs[0];
-    Score S = inlidxs(data(errs[4]), len, TC * th * MWM, inliers);
-    { TraceScope ts(tr, 1); u2h(u, inliers, S.I, h); }
+    unsigned I = inlidxs_count(data(errs[4]), len, TC * th * MWM, inliers);
+    { TraceScope ts(tr, 1); u2h(u, inliers, I, h); }
     eval_into(d, h);
-    S = inlidxs(bufs[d].d.data(), len, th, inliers);
-    return inHrani(inliers, S.I, h, RAN_REP, iterID);
+    I = inlidxs_count(bufs[d].d.data(), len, th, inliers);
+    return inHrani(inliers, I, h, RAN_REP, iterID);
   }
 };
 
@@ -449,7 +459,7 @@ extern "C" int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, d
   R.ctx = ctx; R.u = u; R.len = len; R.th = th; R.doSymCheck = doSymCheck;
   R.which = errorType == 0 ? 0 : (errorType == 1 ? 2 : 1);  // Sampson -> HDs, SymmMax -> HDsSymMax, SymmSum -> HDsSym
   // correspondences stay resident on the device for the whole run
-  static thread_local DevBuf d_u_buf;  // per thread; freed at process exit
+  DevBuf& d_u_buf = ctx->rs_u;
   if (d_u_buf.reserve((size_t)len * 48) != cudaSuccess) { ctx->set_error("ransac_h: cudaMalloc failed"); return MB2_ERR_CUDA; }
   if (cudaMemcpyAsync(d_u_buf.p, u, (size_t)len * 48, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return MB2_ERR_CUDA;
   R.d_u = d_u_buf.as<double>();

@@ -9,6 +9,9 @@
 #include <cmath>
 #include <cstring>
 #include <ctime>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -261,8 +264,13 @@ int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresen
 // original indices in processing order.
 std::vector<int> duplicate_filter_core(const double* xy_in, const double* key, int T, double r, bool sorted) {
   std::vector<int> order(T);
-  for (int i = 0; i < T; i++) order[i] = i;
-  if (sorted) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  if (sorted) {  // std::sort(TCList, CompareCorrespondenceByRatio) made stable: ties keep their input order
+    std::vector<std::pair<double, int> > ki(T);
+    for (int i = 0; i < T; i++) ki[i] = std::make_pair(key[i], i);
+    std::sort(ki.begin(), ki.end());
+    for (int i = 0; i < T; i++) order[i] = ki[i].second;
+  } else
+    for (int i = 0; i < T; i++) order[i] = i;
   std::vector<double> xy((size_t)T * 4);
   for (int j = 0; j < T; j++) std::memcpy(&xy[4 * (size_t)j], xy_in + 4 * (size_t)order[j], 4 * sizeof(double));
   const double r_sq = r * r;
@@ -457,30 +465,36 @@ extern "C" int mb2_host_duplicate_filter(const double* xy /* n x 4: x1 y1 x2 y2 
 
 // ---- one MODS iteration on one pair ---------------------------------------------------------------
 namespace {
-// second context (own stream) for the second image of a pair, created on first use, one per primary context
+// Helper contexts (own stream + scratch) kept per primary context, created on first use:
+//   [0] the second image of a pair (detected / described concurrently with the first),
+//   [1] verification (duplicate filter + LO-RANSAC) of pair k while pair k+1 is detected (mb2_mods_pairs).
 std::mutex g_sib_mutex;
-std::unordered_map<mb2_ctx*, mb2_ctx*> g_siblings;
-mb2_ctx* sibling_ctx(mb2_ctx* ctx) {
+struct Helpers { mb2_ctx* c[2] = {nullptr, nullptr}; bool tried[2] = {false, false}; };
+std::unordered_map<mb2_ctx*, Helpers> g_siblings;
+mb2_ctx* sibling_ctx(mb2_ctx* ctx, int which = 0) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
-  auto it = g_siblings.find(ctx);
-  if (it != g_siblings.end()) return it->second;
-  mb2_ctx* c2 = nullptr;
-  if (mb2_ctx_create(mb2_ctx_device(ctx), &c2) != MB2_OK) c2 = nullptr;
-  g_siblings[ctx] = c2;
-  return c2;
+  Helpers& h = g_siblings[ctx];
+  if (!h.tried[which]) {
+    h.tried[which] = true;
+    if (mb2_ctx_create(mb2_ctx_device(ctx), &h.c[which]) != MB2_OK) h.c[which] = nullptr;
+  }
+  return h.c[which];
 }
 }  // namespace
 
 extern "C" long long mb2_mods_launch_count(mb2_ctx* ctx) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
+  long long n = mb2_ctx_launch_count(ctx);
   auto it = g_siblings.find(ctx);
-  return mb2_ctx_launch_count(ctx) + (it != g_siblings.end() && it->second ? mb2_ctx_launch_count(it->second) : 0);
+  if (it != g_siblings.end())
+    for (mb2_ctx* c : it->second.c) if (c) n += mb2_ctx_launch_count(c);
+  return n;
 }
 extern "C" void mb2_mods_release(mb2_ctx* ctx) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
   auto it = g_siblings.find(ctx);
   if (it == g_siblings.end()) return;
-  if (it->second) mb2_ctx_destroy(it->second);
+  for (mb2_ctx* c : it->second.c) if (c) mb2_ctx_destroy(c);
   g_siblings.erase(it);
 }
 
@@ -495,55 +509,74 @@ extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
   c->seed = 1;
 }
 
-extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
-                             const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity) {
-  using namespace mods;
-  if (!ctx || !img1 || !img2 || !cfg || !res) return MB2_ERR_ARG;
-  std::memset(res, 0, sizeof *res);
-  const double t_start = now_ms();
-  // Config (what getCLIparam would read from config_iter_mods_cviu.ini / an iters file with one HessianAffine tier)
-  DetectorsParameters det_par; det_par.HessParam = cfg->det;
-  DescriptorsParameters desc_par; desc_par.RootSIFTParam = cfg->desc; desc_par.SIFTParam = cfg->desc;
-  DominantOrientationParams dom; dom.maxAngles = cfg->ori.maxAngles; dom.threshold = (float)cfg->ori.threshold; dom.mrSize = cfg->ori.mrSize;
-  dom.patchSize = cfg->ori.patchSize;
-  const std::string desc_name = cfg->desc.rootSIFT ? "RootSIFT" : "SIFT";
-  IterationViewsynthesisParam iters;
-  ViewSynthParameters v; v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = cfg->matchRatio;
-  iters["HessianAffine"].push_back(v);
-  WhatToMatch wtm; wtm.separate_detectors.push_back("HessianAffine"); wtm.separate_descriptors.push_back(desc_name);
-  MatchPars mp; mp.contradDist = cfg->contradDist;
-  RANSACPars rp; rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
-  rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
+namespace {
+using namespace mods;
 
-  // mods.cpp:229-415, one step.  The two images go through SynthDetectDescribeKeypoints on two host threads
-  // (mods.cpp:255-271 runs them as two OpenMP tasks), each with its own context / stream; matching, duplicate
-  // filtering and verification then run on the region blocks and index lists directly (the AoS
-  // TentativeCorrespListExt of the reference is only materialised by the class API, not on this fast path).
-  mb2_ctx* ctx2 = mb2_ctx_profiling(ctx) ? nullptr : sibling_ctx(ctx);   // per-kernel profiling keeps everything on one stream
-  ImageRepresentation ImgRep1(ctx, GrayImage{img1, h1, w1}, "img1", 0), ImgRep2(ctx2 ? ctx2 : ctx, GrayImage{img2, h2, w2}, "img2", 1);
+struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.ini / an iters file with one HessianAffine tier
+  DetectorsParameters det_par; DescriptorsParameters desc_par; DominantOrientationParams dom;
+  std::string desc_name; IterationViewsynthesisParam iters; RANSACPars rp;
+  explicit PairSetup(const mb2_pair_config* cfg) {
+    det_par.HessParam = cfg->det;
+    desc_par.RootSIFTParam = cfg->desc; desc_par.SIFTParam = cfg->desc;
+    dom.maxAngles = cfg->ori.maxAngles; dom.threshold = (float)cfg->ori.threshold; dom.mrSize = cfg->ori.mrSize; dom.patchSize = cfg->ori.patchSize;
+    desc_name = cfg->desc.rootSIFT ? "RootSIFT" : "SIFT";
+    ViewSynthParameters v; v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = cfg->matchRatio;
+    iters["HessianAffine"].push_back(v);
+    rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
+    rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
+  }
+};
+
+// Everything the verification stage needs from the detection / matching stage, on the host.
+struct PairFront {
+  std::unique_ptr<ImageRepresentation> rep1, rep2;
+  std::vector<double> rows;   // nt x 7 tentatives
+  int nt = 0, rc = MB2_OK;
+  double t_start = 0;
+};
+
+// mods.cpp:229-330 for one pair: SynthDetectDescribeKeypoints of both images on two host threads
+// (mods.cpp:255-271 runs them as two OpenMP tasks), each with its own context / stream, then MatchImgReps.
+void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2, const mb2_pair_config* cfg,
+                PairSetup& ps, mb2_pair_result* res, PairFront& out) {
+  out.t_start = now_ms();
+  mb2_ctx* ctx2 = mb2_ctx_profiling(ctx) ? nullptr : sibling_ctx(ctx, 0);   // per-kernel profiling keeps everything on one stream
+  out.rep1.reset(new ImageRepresentation(ctx, GrayImage{img1, h1, w1}, "img1", 0));
+  out.rep2.reset(new ImageRepresentation(ctx2 ? ctx2 : ctx, GrayImage{img2, h2, w2}, "img2", 1));
   double t0 = now_ms();
   if (ctx2) {
-    std::thread th([&] { ImgRep2.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom); });
-    ImgRep1.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+    std::thread th([&] { out.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom); });
+    out.rep1->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
     th.join();
-    if (mb2_slot_move(ctx, 1, ctx2, 1) < 0) return MB2_ERR_CUDA;
+    if (mb2_slot_move(ctx, 1, ctx2, 1) < 0) { out.rc = MB2_ERR_CUDA; return; }
   } else {
-    ImgRep1.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
-    ImgRep2.SynthDetectDescribeKeypoints(iters, det_par, desc_par, dom);
+    out.rep1->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
+    out.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
   }
   res->ms_detect_describe = now_ms() - t0;
-  res->regions1 = ImgRep1.GetDescriptorsNumber(desc_name); res->regions2 = ImgRep2.GetDescriptorsNumber(desc_name);
-  const ImageRepresentation::RegionBlock* Q = ImgRep1.block("HessianAffine", desc_name);
-  const ImageRepresentation::RegionBlock* T = ImgRep2.block("HessianAffine", desc_name);
-  int n = 0;
+  res->regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name); res->regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name);
+  const ImageRepresentation::RegionBlock* Q = out.rep1->block("HessianAffine", ps.desc_name);
+  const ImageRepresentation::RegionBlock* T = out.rep2->block("HessianAffine", ps.desc_name);
   if (Q && T && Q->n > 0 && T->n > 0) {
     t0 = now_ms();
-    std::vector<double> rows((size_t)Q->n * 7);
-    int nt = mb2_match_slots(ctx, 0, 1, cfg->matchRatio, cfg->contradDist, 50, rows.data(), Q->n);   // MatchImgReps -> MatchFlannFGINN
-    if (nt < 0) return nt;
+    out.rows.resize((size_t)Q->n * 7);
+    out.nt = mb2_match_slots(ctx, 0, 1, cfg->matchRatio, cfg->contradDist, 50, out.rows.data(), Q->n);   // MatchImgReps -> MatchFlannFGINN
+    if (out.nt < 0) { out.rc = out.nt; out.nt = 0; return; }
     res->ms_match = now_ms() - t0;
-    res->tentatives = nt;
-    t0 = now_ms();
+    res->tentatives = out.nt;
+  }
+}
+
+// mods.cpp:330-415: DuplicateFiltering(MODE_FGINN) + LORANSACFiltering on the region blocks and index lists
+// directly (the AoS TentativeCorrespListExt of the reference is only materialised by the class API).
+int pair_back(mb2_ctx* vctx, const mb2_pair_config* cfg, PairSetup& ps, PairFront& in, mb2_pair_result* res, double* verified_out, int capacity) {
+  int n = 0;
+  const ImageRepresentation::RegionBlock* Q = in.rep1->block("HessianAffine", ps.desc_name);
+  const ImageRepresentation::RegionBlock* T = in.rep2->block("HessianAffine", ps.desc_name);
+  const int nt = in.nt;
+  if (Q && T && nt > 0) {
+    const std::vector<double>& rows = in.rows;
+    double t0 = now_ms();
     std::vector<double> xy((size_t)nt * 4), key(nt);
     for (int i = 0; i < nt; i++) {
       const double* r = &rows[(size_t)i * 7];
@@ -552,7 +585,7 @@ extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, co
       xy[4 * (size_t)i] = a[0]; xy[4 * (size_t)i + 1] = a[1]; xy[4 * (size_t)i + 2] = b[0]; xy[4 * (size_t)i + 3] = b[1];
       key[i] = std::fabs(std::sqrt((double)((float)r[4] / (float)r[5])));
     }
-    std::vector<int> kept = duplicate_filter_core(xy.data(), key.data(), nt, cfg->duplicateDist, true);  // DuplicateFiltering(.., MODE_FGINN)
+    std::vector<int> kept = duplicate_filter_core(xy.data(), key.data(), nt, cfg->duplicateDist, true);
     res->ms_duplicate = now_ms() - t0;
     res->unique_tentatives = (int)kept.size();
     t0 = now_ms();
@@ -566,7 +599,7 @@ extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, co
     }
     std::vector<unsigned char> inl;
     std::vector<int> verified;
-    n = loransac_core(ctx, frames.data(), (int)kept.size(), rp, inl, verified, res->H);    // LORANSACFiltering
+    n = loransac_core(vctx, frames.data(), (int)kept.size(), ps.rp, inl, verified, res->H);
     res->ms_ransac = now_ms() - t0;
     for (unsigned char b : inl) res->ransac_inliers += b;
     res->verified = n;
@@ -576,6 +609,76 @@ extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, co
         verified_out[4 * i] = f[0]; verified_out[4 * i + 1] = f[1]; verified_out[4 * i + 2] = f[7]; verified_out[4 * i + 3] = f[8];
       }
   }
-  res->ms_total = now_ms() - t_start;
+  res->ms_total = res->ms_detect_describe + res->ms_match + res->ms_duplicate + res->ms_ransac;
   return n;
+}
+}  // namespace
+
+extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
+                             const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity) {
+  if (!ctx || !img1 || !img2 || !cfg || !res) return MB2_ERR_ARG;
+  std::memset(res, 0, sizeof *res);
+  PairSetup ps(cfg);
+  PairFront f;
+  pair_front(ctx, img1, w1, h1, img2, w2, h2, cfg, ps, res, f);
+  if (f.rc < 0) return f.rc;
+  const int n = pair_back(ctx, cfg, ps, f, res, verified_out, capacity);
+  res->ms_total = now_ms() - f.t_start;
+  return n;
+}
+
+// A list of independent pairs (a dataset run: mods.cpp is started once per pair by the EVD / WxBS scripts),
+// software-pipelined over two host threads: while pair k is being verified (duplicate filter + LO-RANSAC on
+// the helper context [1]), pair k+1 is already in detection / description / matching on the primary one.
+// Results are identical to calling mb2_mods_pair on every pair in turn.
+extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img1, const int* w1, const int* h1, const float* const* img2,
+                              const int* w2, const int* h2, const mb2_pair_config* cfg, mb2_pair_result* res, double* const* verified_out,
+                              const int* capacity) {
+  if (!ctx || n_pairs < 0 || !cfg || !res || (n_pairs > 0 && (!img1 || !img2 || !w1 || !h1 || !w2 || !h2))) return MB2_ERR_ARG;
+  mb2_ctx* vctx = mb2_ctx_profiling(ctx) ? nullptr : sibling_ctx(ctx, 1);
+  PairSetup ps(cfg);
+  if (!vctx) {  // no helper context: plain loop
+    for (int k = 0; k < n_pairs; k++) {
+      int r = mb2_mods_pair(ctx, img1[k], w1[k], h1[k], img2[k], w2[k], h2[k], cfg, &res[k], verified_out ? verified_out[k] : nullptr,
+                            capacity ? capacity[k] : 0);
+      if (r < 0) return r;
+    }
+    return n_pairs;
+  }
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<std::pair<int, std::unique_ptr<PairFront> > > q;
+  bool done = false;
+  int rc = MB2_OK;
+  std::thread back([&] {
+    PairSetup ps_back(cfg);
+    for (;;) {
+      std::pair<int, std::unique_ptr<PairFront> > item;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return done || !q.empty(); });
+        if (q.empty()) return;
+        item = std::move(q.front()); q.pop_front();
+      }
+      cv.notify_all();
+      const int k = item.first;
+      int r = pair_back(vctx, cfg, ps_back, *item.second, &res[k], verified_out ? verified_out[k] : nullptr, capacity ? capacity[k] : 0);
+      if (r < 0) { std::lock_guard<std::mutex> lk(m); rc = r; }
+    }
+  });
+  for (int k = 0; k < n_pairs; k++) {
+    std::memset(&res[k], 0, sizeof res[k]);
+    std::unique_ptr<PairFront> f(new PairFront);
+    pair_front(ctx, img1[k], w1[k], h1[k], img2[k], w2[k], h2[k], cfg, ps, &res[k], *f);
+    std::unique_lock<std::mutex> lk(m);
+    if (f->rc < 0) { rc = f->rc; break; }
+    cv.wait(lk, [&] { return q.size() < 2; });   // at most two pairs waiting for verification
+    q.emplace_back(k, std::move(f));
+    lk.unlock();
+    cv.notify_all();
+  }
+  { std::lock_guard<std::mutex> lk(m); done = true; }
+  cv.notify_all();
+  back.join();
+  return rc < 0 ? rc : n_pairs;
 }

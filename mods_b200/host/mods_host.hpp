@@ -192,7 +192,12 @@ void mb2_pair_config_default(mb2_pair_config* c);
 /* images: gray f32 [H|D].  verified_out (optional): capacity rows of 4 doubles (x1 y1 x2 y2).  Returns verified count or < 0. */
 int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2, const mb2_pair_config* cfg,
                   mb2_pair_result* res, double* verified_out, int capacity);
-/* kernels launched by ctx and by the helper context mb2_mods_pair keeps for the second image */
+/* n_pairs independent pairs, software-pipelined (verification of pair k overlaps detection of pair k+1);
+ * res[k] (and verified_out[k] / capacity[k] when given) are exactly what mb2_mods_pair returns for pair k. */
+int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img1, const int* w1, const int* h1, const float* const* img2,
+                   const int* w2, const int* h2, const mb2_pair_config* cfg, mb2_pair_result* res, double* const* verified_out,
+                   const int* capacity);
+/* kernels launched by ctx and by the helper contexts mb2_mods_pair(s) keep (second image, verification) */
 long long mb2_mods_launch_count(mb2_ctx* ctx);
 /* destroys the helper context of ctx (call before mb2_ctx_destroy(ctx)) */
 void mb2_mods_release(mb2_ctx* ctx);

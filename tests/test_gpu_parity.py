@@ -347,3 +347,22 @@ def test_slot_move(ctx):
         assert len(gb[0]) == len(ga[0]) and len(m) > 0 and np.array_equal(m[:, 0], m[:, 1])  # identical sets: every match is i -> i
     finally:
         c2.close()
+
+
+def test_mods_pairs_pipeline_equals_single_calls(ctx):
+    import mods_b200 as mb
+    from synth import blob_image, warp_image, gt_homography
+    pairs = []
+    for k in range(4):
+        A = blob_image(400 + 40 * k, 300 + 8 * k, seed=41 + k, n_blobs=350 + 50 * k)
+        pairs.append((A, warp_image(A, gt_homography(A.shape[1], A.shape[0]), seed=51 + k)))
+    cfg = mb.PairConfig.default()
+    cfg.seed = 99
+    single = [ctx.mods_pair(a, b, cfg, capacity=4096) for a, b in pairs]
+    res, ver = ctx.mods_pairs(pairs, cfg, capacity=4096)
+    assert len(res) == 4
+    for (r1, v1), r2, v2 in zip(single, res, ver):
+        for f in ("regions1", "regions2", "tentatives", "unique_tentatives", "ransac_inliers", "verified"):
+            assert getattr(r1, f) == getattr(r2, f), f
+        assert r1.verified >= 8 and np.array_equal(v1, v2) and np.array_equal(np.array(r1.H[:]), np.array(r2.H[:]))
+    assert ctx.mods_pairs([], cfg)[0] == []
