@@ -21,6 +21,7 @@ namespace MB2_NS {
 struct CtxTables {
   DevBuf smm_mask, orimask, desc_tables, tap_n, tap_off, tap_w, octaves;
   int smm_size = 0, tap_max_m = -1;
+  std::vector<int> tap_n_host;
   double tap_mrsize_key = -1;
   int tap_patch = 0;
 };
@@ -228,7 +229,7 @@ int ensure_taps(mb2_ctx* ctx, int max_m, int patchSize, TapTable* out) {
     MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(t.tap_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(t.tap_w.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    t.tap_max_m = want; t.tap_patch = patchSize;
+    t.tap_max_m = want; t.tap_patch = patchSize; t.tap_n_host = n;
   }
   out->n = t.tap_n.as<int>(); out->off = t.tap_off.as<int>(); out->w = t.tap_w.as<float>(); out->max_m = t.tap_max_m;
   return MB2_OK;
@@ -499,24 +500,34 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
   const int max_m = (int)std::ceil(std::sqrt((double)img.rows * img.rows + (double)img.cols * img.cols)) + 8;
   TapTable taps;
   if ((rc = ensure_taps(ctx, max_m, sp.patchSize, &taps))) return rc;
-  // scratch plan: need[i] floats per region, exclusive scan -> offsets
-  size_t cub_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, ctx->stream);
-  MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)n * 16 + 64 + cub_bytes + 64));
+  // plan: need[i] scratch floats per region (exclusive scan -> offsets) and the size-class lists (one radix sort)
+  size_t scan_bytes = 0, sort_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, ctx->stream);
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, ctx->stream);
+  const size_t cub_bytes = std::max(scan_bytes, sort_bytes);
+  MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)n * 32 + 128 + cub_bytes + 64));
   unsigned long long* d_need = ctx->rs_a.as<unsigned long long>();
   unsigned long long* d_off = d_need + n;
-  unsigned long long* d_total = d_off + n;        // [0] scratch floats, [1] sum of P2^2
-  int* d_toobig = (int*)(d_total + 2);
-  void* cub_tmp = (void*)(((uintptr_t)(d_toobig + 2) + 15) & ~(uintptr_t)15);
-  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_total, 0, 16 + 8, ctx->stream));
-  mb2_describe_plan(ctx, d_keys, n, dp, taps.max_m, d_need, d_toobig, d_total + 1);
-  MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, d_need, d_off, n, ctx->stream));
-  ctx->launches += 1;
+  unsigned long long* d_skeys = d_off + n;        // unsorted, then sorted class keys
+  unsigned long long* d_sorted = d_skeys + n;
+  unsigned long long* d_total = d_sorted + n;     // [0] scratch floats, [1] sum of P2^2
+  int* d_toobig = (int*)(d_total + 2);            // [0] too big, [1] pad, [2..7] class counts
+  int* d_cls = d_toobig + 2;
+  void* cub_tmp = (void*)(((uintptr_t)(d_cls + MB2_N_CLASSES) + 15) & ~(uintptr_t)15);
+  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_total, 0, 16 + 8 + 4 * MB2_N_CLASSES, ctx->stream));
+  mb2_describe_plan(ctx, d_keys, n, dp, taps.max_m, d_need, d_toobig, d_total + 1, d_skeys, d_cls);
+  MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, scan_bytes, d_need, d_off, n, ctx->stream));
   MB2_LAUNCH(ctx, k_scan_offsets_total, 1, 32, 0, d_need, d_off, n, d_total);
-  unsigned long long total = 0, tot2[2] = {0, 0}; int toobig = 0;
+  MB2_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortKeys(cub_tmp, sort_bytes, d_skeys, d_sorted, n, 0, 64, ctx->stream));
+  ctx->launches += 4;
+  unsigned long long total = 0, tot2[2] = {0, 0}; int hostc[2 + MB2_N_CLASSES] = {0};
   MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(tot2, d_total, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&toobig, d_toobig, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(hostc, d_toobig, sizeof hostc, cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int toobig = hostc[0];
+  ExtractPlan plan;
+  plan.sorted = d_sorted;
+  for (int c = 0; c < MB2_N_CLASSES; c++) plan.count[c] = hostc[2 + c];
   total = tot2[0];
   // SURVEY 8d gather model: 4 bilinear taps x 4 B per sampled pixel ((P+2)^2 + 41^2 per region) + 128 B out
   if (ctx->profiling) ctx->prof_extract_bytes += tot2[1] * 16ull + (unsigned long long)n * (1681ull * 16ull + 128ull);
@@ -531,7 +542,7 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
   MB2_CUDA_CHECK(ctx, ctx->desc_u8.reserve((size_t)n * 128));
   float* base = ctx->patch_scratch.as<float>();
   priv(ctx)->last_patches = base + f_patches;
-  return mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, d_off, base,
+  return mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, priv(ctx)->t.tap_n_host.data(), plan, d_off, base,
                                     ctx->desc_u8.as<uint8_t>(), base + f_patches, (float2*)(base + f_stats), (double*)(base + f_vec),
                                     (float2*)(base + f_rec));
 }
@@ -623,6 +634,9 @@ int mb2_ctx_create(int device, mb2_ctx** out) {
   mb2_ctx* c = new mb2_ctx();
   c->device = device;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MB2_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { mb2_ctx_destroy(c); return MB2_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
   *out = c;
@@ -639,6 +653,9 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
   for (auto& s : ctx->slots) { s.desc.release(); s.xy.release(); }
   ctx->h_a.release(); ctx->h_b.release(); ctx->h_c.release();
   drop_priv(ctx);
+  if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

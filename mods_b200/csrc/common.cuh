@@ -65,6 +65,8 @@ struct RegionSlot {
 struct mb2_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;            // forked from `stream` for launches that would otherwise leave a long tail
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   long long launches = 0;
   int num_sms = 148;
@@ -105,30 +107,24 @@ struct ImgView {
 // is the single definition.
 __constant__ double c_atan_lut[256];
 
-// detectors/helpers.cpp:160-207
-__device__ __forceinline__ float atan2LUTff_dev(float y, float x) {
-  const float PI_2f = 1.57079632679489661923f, PIf = 3.14159265358979323846f;
+// detectors/helpers.cpp:160-207.  The eight branches of the reference differ only in which of |x|, |y| is the
+// numerator and in the final affine map of the table value, so the table is read ONCE (index from the same
+// float multiply / divide as the taken branch) and the quadrant formula is selected afterwards: identical
+// results without eight divergent paths.  lut: 256 doubles (shared-memory copy of c_atan_lut in the hot kernels).
+__device__ __forceinline__ float atan2LUTff_dev(float y, float x, const double* __restrict__ lut) {
+  const double PI_2d = (double)1.57079632679489661923f, PId = (double)3.14159265358979323846f;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool big = ax > ay;                       // x > y, x > absy, absx > y, absx > absy in the four quadrants
+  const float num = big ? ay : ax, den = big ? ax : ay;
+  const double t = lut[(int)(fdiv(fmul(255.f, num), den))];
   if (x > 0.f) {
-    if (y > 0.f) {
-      if (x > y) return (float)c_atan_lut[(int)(fdiv(fmul(255.f, y), x))];
-      else return (float)d_sub((double)PI_2f, c_atan_lut[(int)(fdiv(fmul(255.f, x), y))]);
-    } else {
-      float absy = fabsf(y);
-      if (x > absy) return (float)(-c_atan_lut[(int)(fdiv(fmul(255.f, absy), x))]);
-      else return (float)d_add((double)(-PI_2f), c_atan_lut[(int)(fdiv(fmul(255.f, x), absy))]);
-    }
-  } else if (y > 0.f) {
-    float absx = fabsf(x);
-    if (absx > y) return (float)d_sub((double)PIf, c_atan_lut[(int)(fdiv(fmul(255.f, y), absx))]);
-    else return (float)d_add((double)PI_2f, c_atan_lut[(int)(fdiv(fmul(255.f, absx), y))]);
-  } else {
-    float absx = fabsf(x), absy = fabsf(y);
-    if (absx > absy) return (float)d_add((double)(-PIf), c_atan_lut[(int)(fdiv(fmul(255.f, absy), absx))]);
-    else {
-      if (x == 0.f) return 0.f;
-      return (float)d_sub((double)(-PI_2f), c_atan_lut[(int)(fdiv(fmul(255.f, absx), absy))]);
-    }
+    if (y > 0.f) return big ? (float)t : (float)d_sub(PI_2d, t);
+    return big ? (float)(-t) : (float)d_add(-PI_2d, t);
   }
+  if (y > 0.f) return big ? (float)d_sub(PId, t) : (float)d_add(PI_2d, t);
+  if (big) return (float)d_add(-PId, t);
+  if (x == 0.f) return 0.f;
+  return (float)d_sub(-PI_2d, t);
 }
 
 // detectors/helpers.cpp:524-549
@@ -200,17 +196,18 @@ __device__ __forceinline__ void interpolate_row(const float* __restrict__ im, in
 }
 
 // Launch bookkeeping
-#define MB2_LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
+#define MB2_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)           \
   do {                                                                     \
     mb2_ctx::ProfRec _pr{#kernel, nullptr, nullptr};                       \
     if ((ctx)->profiling) {                                                \
       cudaEventCreate(&_pr.a); cudaEventCreate(&_pr.b);                    \
-      cudaEventRecord(_pr.a, (ctx)->stream);                               \
+      cudaEventRecord(_pr.a, (strm));                                      \
     }                                                                      \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);       \
-    if ((ctx)->profiling) { cudaEventRecord(_pr.b, (ctx)->stream); (ctx)->prof.push_back(_pr); } \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);              \
+    if ((ctx)->profiling) { cudaEventRecord(_pr.b, (strm)); (ctx)->prof.push_back(_pr); } \
     (ctx)->launches++;                                                     \
   } while (0)
+#define MB2_LAUNCH(ctx, kernel, grid, block, smem, ...) MB2_LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, smem, __VA_ARGS__)
 
 // host-side helpers implemented in capi.cu
 int mb2_stage_in(mb2_ctx* ctx, const void* src, size_t bytes, DevBuf& dst, const void** dev_ptr);

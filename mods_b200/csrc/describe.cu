@@ -51,31 +51,53 @@ __device__ __forceinline__ KpGeom kp_geom(const KeyOut& k, const DescribeParams&
   return g;
 }
 
-// scratch floats needed by region i: (P2*P2) sampled patch + (P2*NEED) row-pass columns
+// Size classes of the blur path.  Small regions keep the whole (P+2)^2 patch in shared memory and blur it
+// densely; medium ones keep it in shared memory and blur only the <= 82 needed columns / rows; the rest
+// (and the direct path) go through the global-scratch kernel.  Bounds are on m = ceil(s * mrSize).
+constexpr int N_CLASSES = 6;
+// class order = launch order = sort order: big regions first
+enum { CLS_GLOBAL = 0, CLS_NEED_L = 1, CLS_NEED_S = 2, CLS_DENSE_L = 3, CLS_DENSE_M = 4, CLS_DENSE_S = 5 };
+__host__ __device__ __forceinline__ int size_class(int m, int P2) {
+  if (P2 == 0 || m > MB2_CLS_M_NEED_L) return CLS_GLOBAL;
+  if (m > MB2_CLS_M_NEED_S) return CLS_NEED_L;
+  if (m > MB2_CLS_M_DENSE_L) return CLS_NEED_S;
+  if (m > MB2_CLS_M_DENSE_M) return CLS_DENSE_L;
+  if (m > MB2_CLS_M_DENSE_S) return CLS_DENSE_M;
+  return CLS_DENSE_S;
+}
+
+// scratch floats needed by region i: (P2*P2) sampled patch + (P2*NEED) row-pass columns (global-scratch class only);
+// sort key = class | descending m | index, so that one radix sort yields the per-class lists, big regions first.
 __global__ void k_plan(const KeyOut* __restrict__ kps, int n, DescribeParams dp, int max_m, unsigned long long* __restrict__ need,
-                       int* __restrict__ too_big, unsigned long long* __restrict__ sum_p2sq) {
+                       int* __restrict__ too_big, unsigned long long* __restrict__ sum_p2sq, unsigned long long* __restrict__ keys,
+                       int* __restrict__ cls_cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   KpGeom g = kp_geom(kps[i], dp);
   if (g.P2 > 0 && g.m > max_m) { atomicMax(too_big, g.m); }
-  need[i] = g.P2 > 0 ? (unsigned long long)g.P2 * (unsigned long long)(g.P2 + NEED) : 0ull;
+  const int cls = size_class(g.m, g.P2);
+  need[i] = (g.P2 > 0 && cls == CLS_GLOBAL) ? (unsigned long long)g.P2 * (unsigned long long)(g.P2 + NEED) : 0ull;
   if (g.P2 > 0) atomicAdd(sum_p2sq, (unsigned long long)g.P2 * (unsigned long long)g.P2);
+  const int mm = g.m < 0 ? 0 : (g.m > 65535 ? 65535 : g.m);
+  keys[i] = ((unsigned long long)cls << 48) | ((unsigned long long)(65535 - mm) << 32) | (unsigned long long)(unsigned)i;
+  atomicAdd(&cls_cnt[cls], 1);
 }
 
 constexpr int MAXT_SMEM = 384;   // Gaussian taps kept in shared memory (larger kernels read them from global)
 
-__global__ void __launch_bounds__(DT)
-k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp, const TapTable taps,
-          const unsigned long long* __restrict__ scratch_off, float* __restrict__ scratch, float* __restrict__ patch_out) {
+__global__ void __launch_bounds__(512)
+k_extract(ImgView img, const KeyOut* __restrict__ kps, const unsigned long long* __restrict__ list, int n, DescribeParams dp,
+          const TapTable taps, const unsigned long long* __restrict__ scratch_off, float* __restrict__ scratch,
+          float* __restrict__ patch_out) {
   __shared__ float s_patch[NPIX];
   __shared__ float s_small[NEED * NEED]; // blurred patch at the needed rows x columns
   __shared__ int s_cols[NEED], s_rows[NEED];
   __shared__ float s_taps[MAXT_SMEM];
 
-  // Regions arrive in detection order (fine octaves first), so the expensive large regions sit at the
-  // end of the list: walk it backwards so they are scheduled first and do not form a tail.
-  const int kidx = n - 1 - (int)blockIdx.x, tid = threadIdx.x;
-  if (kidx < 0) return;
+  // list = this class's slice of the sorted keys (big regions first, so they do not form a tail)
+  const int tid = threadIdx.x, NT = blockDim.x;
+  if ((int)blockIdx.x >= n) return;
+  const int kidx = (int)(list[blockIdx.x] & 0xffffffffull);
   const KeyOut k = kps[kidx];
   const KpGeom g = kp_geom(k, dp);
   const float x = (float)k.v[0], y = (float)k.v[1];
@@ -97,13 +119,13 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
     float* bufB = bufA + (size_t)P2 * P2;               // P2 x NEED row pass at the needed columns
     const int nt = taps.n[g.m], h = nt >> 1;
     const float* kw = taps.w + taps.off[g.m];
-    if (nt <= MAXT_SMEM) { for (int j = tid; j < nt; j += DT) s_taps[j] = kw[j]; kw = s_taps; }
+    if (nt <= MAXT_SMEM) { for (int j = tid; j < nt; j += NT) s_taps[j] = kw[j]; kw = s_taps; }
     // A. sample with the det-1 frame: rows are split into segments so that all threads sample
     {
       const bool touch = interpolateCheckBorders_dev(img.cols, img.rows, x, y, a11, a12, a21, a22, P2, P2);
-      const int segs = P2 >= DT ? 1 : DT / P2;                 // segments per row
+      const int segs = P2 >= NT ? 1 : NT / P2;                 // segments per row
       const int slen = (P2 + segs - 1) / segs;
-      for (int item = tid; item < P2 * segs; item += DT) {
+      for (int item = tid; item < P2 * segs; item += NT) {
         const int row = item / segs, sg = item - row * segs;
         float* orow = bufA + (size_t)row * P2;
         interpolate_seg(img.p, img.rows, img.cols, img.pitch, x, y, a11, a12, a21, a22, P2, P2, touch, row, sg * slen, slen,
@@ -135,7 +157,7 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
     __syncthreads();
     // B. row pass (left-to-right accumulation, replicate border) at the needed columns, all rows.  The needed
     // columns come in adjacent pairs (x_i, x_i + 1): both are produced from one sliding window, one load per tap.
-    for (int idx = tid; idx < P2 * PS; idx += DT) {
+    for (int idx = tid; idx < P2 * PS; idx += NT) {
       const int r = idx / PS, i = idx - r * PS;
       const int c = s_cols[2 * i];
       float acc0 = 0.f, acc1 = 0.f;
@@ -174,7 +196,7 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
     __syncthreads();
     // C. column pass (symmetric pairs) at the needed rows x needed columns; the needed rows also come in
     // adjacent pairs (y_j, y_j + 1) that share all but two of their inputs.
-    for (int idx = tid; idx < PS * NEED; idx += DT) {
+    for (int idx = tid; idx < PS * NEED; idx += NT) {
       const int jr = idx / NEED, ci = idx - jr * NEED;
       const int r = s_rows[2 * jr], c = s_cols[ci];
       float acc0 = 0.f, acc1 = 0.f;
@@ -239,7 +261,265 @@ k_extract(ImgView img, const KeyOut* __restrict__ kps, int n, DescribeParams dp,
     __syncthreads();
   }
 
-  for (int p = tid; p < NPIX; p += DT) patch_out[(size_t)kidx * NPIX + p] = s_patch[p];
+  for (int p = tid; p < NPIX; p += NT) patch_out[(size_t)kidx * NPIX + p] = s_patch[p];
+}
+
+// ---- shared-memory variants --------------------------------------------------------------------------
+// Same arithmetic as k_extract (every output is the same chain of __fmul_rn / __fadd_rn), different staging:
+// the sampled patch A lives in shared memory with h replicated columns on both sides (row stride SA = P2 + 2h,
+// odd: conflict-free when consecutive lanes take consecutive rows), the row-pass result B with h replicated
+// rows above and below, so neither pass clamps an index.
+extern __shared__ float s_dyn[];
+
+struct ResamplePos {   // second interpolate() (ofs = P2 >> 1, A = diag(scale)): per output column / row
+  int xi[PS], yi[PS];
+  float wx[PS], wy[PS];
+};
+
+__device__ __forceinline__ void resample_positions(ResamplePos& rp, int P2, float sc, bool touch2, int tid) {
+  const float ofs = (float)(P2 >> 1);
+  if (tid == 0) {
+    // columns: WX starts at rx - 20*a11 with rx = ofs - 20*a12 = ofs - 0, then += a11
+    float rx = fsub(ofs, fmul((float)(PS >> 1), 0.f));
+    float WX = fsub(rx, fmul((float)(PS >> 1), sc));
+    for (int i = 0; i < PS; i++) { rp.xi[i] = touch2 ? (int)floorf(WX) : (int)WX; rp.wx[i] = WX; WX = fadd(WX, sc); }
+  } else if (tid == 32) {
+    // rows: ry starts at ofs - 20*a22, += a22 per row; WY = ry - 20*a21 = ry - 0
+    float ry = fsub(ofs, fmul((float)(PS >> 1), sc));
+    for (int j = 0; j < PS; j++) {
+      const float WY = fsub(ry, fmul((float)(PS >> 1), 0.f));
+      rp.yi[j] = touch2 ? (int)floorf(WY) : (int)WY; rp.wy[j] = WY;
+      ry = fadd(ry, sc);
+    }
+  }
+}
+
+// phase A: sample the P2 x P2 patch with the det-1 frame into A (padded rows), then replicate the borders
+__device__ __forceinline__ void sample_to_smem(const ImgView& img, float x, float y, float a11, float a12, float a21, float a22,
+                                               int P2, int h, int SA, float* A) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const bool touch = interpolateCheckBorders_dev(img.cols, img.rows, x, y, a11, a12, a21, a22, P2, P2);
+  const int segs = P2 >= NT ? 1 : NT / P2;                 // segments per row
+  const int slen = (P2 + segs - 1) / segs;
+  for (int item = tid; item < P2 * segs; item += NT) {
+    const int row = item / segs, sg = item - row * segs;
+    float* orow = A + row * SA + h;
+    interpolate_seg(img.p, img.rows, img.cols, img.pitch, x, y, a11, a12, a21, a22, P2, P2, touch, row, sg * slen, slen,
+                    [&](int i, float v) { orow[i] = v; });
+  }
+  __syncthreads();
+  const int h2 = 2 * h;
+  for (int t = tid; t < P2 * h2; t += NT) {
+    const int r = t / h2, q = t - r * h2;
+    float* row = A + r * SA;
+    if (q < h) row[q] = row[h]; else row[P2 + q] = row[h + P2 - 1];
+  }
+}
+
+// Dense variant (P2 <= ~83): every column / row of the blurred patch is produced, four adjacent outputs per
+// thread from one sliding window.  Shared memory: A [P2][SA] (+4), B [P2 + 2h][P2], taps.
+__global__ void __launch_bounds__(256)
+k_extract_dense(ImgView img, const KeyOut* __restrict__ kps, const unsigned long long* __restrict__ list, int n, DescribeParams dp,
+                const TapTable taps, float* __restrict__ patch_out) {
+  __shared__ ResamplePos rp;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  if ((int)blockIdx.x >= n) return;
+  const int kidx = (int)(list[blockIdx.x] & 0xffffffffull);
+  const KeyOut k = kps[kidx];
+  const KpGeom g = kp_geom(k, dp);
+  const int P2 = g.P2, nt = taps.n[g.m], h = nt >> 1, SA = P2 + 2 * h;
+  float* A = s_dyn;
+  float* B = A + P2 * SA + 4;
+  float* kw = B + (P2 + 2 * h) * P2;
+  float* S = A;   // blurred patch, P2 x P2, overwrites A after the row pass
+  for (int j = tid; j < nt; j += NT) kw[j] = taps.w[taps.off[g.m] + j];
+  const float sc = g.scale;
+  const bool touch2 = interpolateCheckBorders_dev(P2, P2, (float)(P2 >> 1), (float)(P2 >> 1), sc, 0.f, 0.f, sc, PS, PS);
+  resample_positions(rp, P2, sc, touch2, tid);
+  sample_to_smem(img, (float)k.v[0], (float)k.v[1], (float)k.v[2], (float)k.v[3], (float)k.v[4], (float)k.v[5], P2, h, SA, A);
+  __syncthreads();
+  // row pass (left-to-right accumulation): lanes -> consecutive rows, 4 adjacent columns per item
+  const int G = (P2 + 3) >> 2;
+  for (int item = tid; item < P2 * G; item += NT) {
+    const int g4 = item / P2, r = item - g4 * P2;
+    const int c0 = min(4 * g4, P2 - 4);                    // last group overlaps the previous one (same values)
+    const float* ap = A + r * SA + c0;                     // padded index of source column c0 - h
+    float v0 = ap[0], v1 = ap[1], v2 = ap[2], v3 = ap[3];
+    float kk = kw[0];
+    float a0 = fmul(kk, v0), a1 = fmul(kk, v1), a2 = fmul(kk, v2), a3 = fmul(kk, v3);
+#pragma unroll 4
+    for (int j = 1; j < nt; j++) {
+      v0 = v1; v1 = v2; v2 = v3; v3 = ap[j + 3];
+      kk = kw[j];
+      a0 = fadd(a0, fmul(kk, v0)); a1 = fadd(a1, fmul(kk, v1)); a2 = fadd(a2, fmul(kk, v2)); a3 = fadd(a3, fmul(kk, v3));
+    }
+    float* bp = B + (r + h) * P2 + c0;
+    bp[0] = a0; bp[1] = a1; bp[2] = a2; bp[3] = a3;
+  }
+  __syncthreads();
+  for (int t = tid; t < 2 * h * P2; t += NT) {            // replicate rows above / below
+    const int q = t / P2, c = t - q * P2;
+    if (q < h) B[q * P2 + c] = B[h * P2 + c]; else B[(P2 + q) * P2 + c] = B[(h + P2 - 1) * P2 + c];
+  }
+  __syncthreads();
+  // column pass (symmetric pairs): lanes -> consecutive columns, 4 adjacent rows per item
+  for (int item = tid; item < G * P2; item += NT) {
+    const int gr = item / P2, c = item - gr * P2;
+    const int r0 = min(4 * gr, P2 - 4);
+    const float* bp = B + (r0 + h) * P2 + c;
+    const float c0 = bp[0], c1 = bp[P2], c2 = bp[2 * P2], c3 = bp[3 * P2];
+    float kk = kw[h];
+    float a0 = fmul(kk, c0), a1 = fmul(kk, c1), a2 = fmul(kk, c2), a3 = fmul(kk, c3);
+    float u0 = c1, u1 = c2, u2 = c3, u3, d0, d1 = c0, d2 = c1, d3 = c2;
+#pragma unroll 4
+    for (int j = 1; j <= h; j++) {
+      u3 = bp[(3 + j) * P2]; d0 = bp[-j * P2];
+      kk = kw[h + j];
+      a0 = fadd(a0, fmul(kk, fadd(u0, d0))); a1 = fadd(a1, fmul(kk, fadd(u1, d1)));
+      a2 = fadd(a2, fmul(kk, fadd(u2, d2))); a3 = fadd(a3, fmul(kk, fadd(u3, d3)));
+      u0 = u1; u1 = u2; u2 = u3; d3 = d2; d2 = d1; d1 = d0;
+    }
+    float* sp = S + r0 * P2 + c;
+    sp[0] = a0; sp[P2] = a1; sp[2 * P2] = a2; sp[3 * P2] = a3;
+  }
+  __syncthreads();
+  // bilinear resample to 41x41 (interpolate(), helpers.cpp:551-626)
+  const int width = P2 - 1, height = P2 - 1;
+  for (int p = tid; p < NPIX; p += NT) {
+    const int j = p / PS, i = p - j * PS;
+    const int xi = rp.xi[i], yi = rp.yi[j];
+    const float WX = rp.wx[i], WY = rp.wy[j];
+    float v = 0.f;
+    const bool inside = touch2 ? (WX >= 0 && WY >= 0 && xi < width && yi < height) : true;
+    if (inside) {
+      const float* s0 = S + yi * P2 + xi;
+      const float wx = fsub(WX, (float)xi);
+      const float r0x = s0[0], r0x1 = s0[1], r1x = s0[P2], r1x1 = s0[P2 + 1];
+      const float I1 = fadd(fmul(wx, fsub(r0x1, r0x)), r0x);
+      v = fadd(fmul(fsub(WY, (float)yi), fsub(fadd(fmul(wx, fsub(r1x1, r1x)), r1x), I1)), I1);
+    }
+    patch_out[(size_t)kidx * NPIX + p] = v;
+  }
+}
+
+// Needed-columns variant (P2 up to ~150): A in shared memory, row pass only at the <= 82 columns the resample
+// reads (pairs (x_i, x_i + 1) from one sliding window, two rows per item), column pass at the 82 x 82 points.
+// Shared memory: A [P2][SA] (+4), B [P2 + 2h][SBN], taps;  the 82 x 82 result overwrites A.
+constexpr int SBN = NEED + 1;
+__global__ void __launch_bounds__(512)
+k_extract_needed(ImgView img, const KeyOut* __restrict__ kps, const unsigned long long* __restrict__ list, int n, DescribeParams dp,
+                 const TapTable taps, float* __restrict__ patch_out) {
+  __shared__ ResamplePos rp;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  if ((int)blockIdx.x >= n) return;
+  const int kidx = (int)(list[blockIdx.x] & 0xffffffffull);
+  const KeyOut k = kps[kidx];
+  const KpGeom g = kp_geom(k, dp);
+  const int P2 = g.P2, nt = taps.n[g.m], h = nt >> 1, SA = P2 + 2 * h;
+  float* A = s_dyn;
+  float* B = A + P2 * SA + 4;
+  float* kw = B + (P2 + 2 * h) * SBN;
+  float* S = A;   // 82 x 82 blurred values at the needed rows x columns (stride NEED)
+  for (int j = tid; j < nt; j += NT) kw[j] = taps.w[taps.off[g.m] + j];
+  const float sc = g.scale;
+  const bool touch2 = interpolateCheckBorders_dev(P2, P2, (float)(P2 >> 1), (float)(P2 >> 1), sc, 0.f, 0.f, sc, PS, PS);
+  resample_positions(rp, P2, sc, touch2, tid);
+  sample_to_smem(img, (float)k.v[0], (float)k.v[1], (float)k.v[2], (float)k.v[3], (float)k.v[4], (float)k.v[5], P2, h, SA, A);
+  __syncthreads();
+  // row pass: item = (column pair i, rows rr and rr + R2); lanes -> consecutive rows
+  const int R2 = (P2 + 1) >> 1;
+  for (int item = tid; item < PS * R2; item += NT) {
+    const int i = item / R2, rr = item - i * R2;
+    const int rA = rr, rB = min(rr + R2, P2 - 1);
+    const int c = rp.xi[i];
+    float A0 = 0.f, A1 = 0.f, B0 = 0.f, B1 = 0.f;
+    if (c >= 0 && c + 1 < P2) {
+      const float* pa = A + rA * SA + c;                   // padded index of source column c - h
+      const float* pb = A + rB * SA + c;
+      float a = pa[0], b = pa[1], e = pb[0], f = pb[1];
+      float kk = kw[0];
+      A0 = fmul(kk, a); A1 = fmul(kk, b); B0 = fmul(kk, e); B1 = fmul(kk, f);
+#pragma unroll 4
+      for (int j = 1; j < nt; j++) {
+        a = b; b = pa[j + 1]; e = f; f = pb[j + 1];
+        kk = kw[j];
+        A0 = fadd(A0, fmul(kk, a)); A1 = fadd(A1, fmul(kk, b)); B0 = fadd(B0, fmul(kk, e)); B1 = fadd(B1, fmul(kk, f));
+      }
+    } else {
+      for (int q = 0; q < 2; q++) {                        // generic (only for sample positions outside the patch)
+        const int cq = c + q;
+        if (cq < 0 || cq >= P2) continue;
+        const float* pa = A + rA * SA + cq;
+        const float* pb = A + rB * SA + cq;
+        float s0 = fmul(kw[0], pa[0]), s1 = fmul(kw[0], pb[0]);
+        for (int j = 1; j < nt; j++) { s0 = fadd(s0, fmul(kw[j], pa[j])); s1 = fadd(s1, fmul(kw[j], pb[j])); }
+        if (q == 0) { A0 = s0; B0 = s1; } else { A1 = s0; B1 = s1; }
+      }
+    }
+    float* ba = B + (rA + h) * SBN + 2 * i;
+    float* bb = B + (rB + h) * SBN + 2 * i;
+    ba[0] = A0; ba[1] = A1; bb[0] = B0; bb[1] = B1;
+  }
+  __syncthreads();
+  for (int t = tid; t < 2 * h * NEED; t += NT) {          // replicate rows above / below
+    const int q = t / NEED, c = t - q * NEED;
+    if (q < h) B[q * SBN + c] = B[h * SBN + c]; else B[(P2 + q) * SBN + c] = B[(h + P2 - 1) * SBN + c];
+  }
+  __syncthreads();
+  // column pass (symmetric pairs) at the needed rows (y_j, y_j + 1) x needed columns
+  for (int idx = tid; idx < PS * NEED; idx += NT) {
+    const int jr = idx / NEED, ci = idx - jr * NEED;
+    const int r = rp.yi[jr], c = rp.xi[ci >> 1] + (ci & 1);
+    float acc0 = 0.f, acc1 = 0.f;
+    if (c >= 0 && c < P2) {
+      const float* col = B + h * SBN + ci;                 // col[rr * SBN] = row-pass value of patch row rr, rr in [-h, P2 - 1 + h]
+      if (r >= 0 && r + 1 < P2) {
+        const float* bp = col + r * SBN;
+        float up0 = bp[SBN], dn1 = bp[0];                  // out1 is centred on r + 1, out0 on r
+        acc0 = fmul(kw[h], dn1); acc1 = fmul(kw[h], up0);
+        float dn0_prev = dn1;
+#pragma unroll 4
+        for (int j = 1; j <= h; j++) {
+          const float up1 = bp[(1 + j) * SBN];
+          const float dn0 = bp[-j * SBN];
+          const float kj = kw[h + j];
+          acc0 = fadd(acc0, fmul(kj, fadd(up0, dn0)));
+          acc1 = fadd(acc1, fmul(kj, fadd(up1, dn0_prev)));
+          up0 = up1; dn0_prev = dn0;
+        }
+      } else {
+        for (int q = 0; q < 2; q++) {
+          const int rq = r + q;
+          float acc = 0.f;
+          if (rq >= 0 && rq < P2) {
+            const float* bp = col + rq * SBN;
+            acc = fmul(kw[h], bp[0]);
+            for (int j = 1; j <= h; j++) acc = fadd(acc, fmul(kw[h + j], fadd(bp[j * SBN], bp[-j * SBN])));
+          }
+          if (q == 0) acc0 = acc; else acc1 = acc;
+        }
+      }
+    }
+    S[(2 * jr) * NEED + ci] = acc0;
+    S[(2 * jr + 1) * NEED + ci] = acc1;
+  }
+  __syncthreads();
+  const int width = P2 - 1, height = P2 - 1;
+  for (int p = tid; p < NPIX; p += NT) {
+    const int j = p / PS, i = p - j * PS;
+    const int xi = rp.xi[i], yi = rp.yi[j];
+    const float WX = rp.wx[i], WY = rp.wy[j];
+    float v = 0.f;
+    const bool inside = touch2 ? (WX >= 0 && WY >= 0 && xi < width && yi < height) : true;
+    if (inside) {
+      const float wx = fsub(WX, (float)xi);
+      const float r0x = S[(2 * j) * NEED + 2 * i], r0x1 = S[(2 * j) * NEED + 2 * i + 1];
+      const float r1x = S[(2 * j + 1) * NEED + 2 * i], r1x1 = S[(2 * j + 1) * NEED + 2 * i + 1];
+      const float I1 = fadd(fmul(wx, fsub(r0x1, r0x)), r0x);
+      v = fadd(fmul(fsub(WY, (float)yi), fsub(fadd(fmul(wx, fsub(r1x1, r1x)), r1x), I1)), I1);
+    }
+    patch_out[(size_t)kidx * NPIX + p] = v;
+  }
 }
 
 // photometricallyNormalize statistics (helpers.cpp:666-694): two serial float sums over the masked
@@ -285,8 +565,10 @@ __global__ void __launch_bounds__(DT)
 k_sift_grad(float* __restrict__ patches, int n, DescribeParams dp, const DescTables* __restrict__ tab,
             const float2* __restrict__ stats, float2* __restrict__ rec) {
   __shared__ float s_patch[NPIX];
+  __shared__ double s_lut[256];
   const int kidx = blockIdx.x, tid = threadIdx.x;
   if (kidx >= n) return;
+  for (int i = tid; i < 256; i += DT) s_lut[i] = c_atan_lut[i];
   float* gp = patches + (size_t)kidx * NPIX;
   bool normalise = false;
   float sum = 0.f, fac = 0.f;
@@ -317,7 +599,7 @@ k_sift_grad(float* __restrict__ patches, int n, DescribeParams dp, const DescTab
     else if (r == PS - 1) yg = fsub(s_patch[p], s_patch[p - PS]);
     else yg = fsub(s_patch[p + PS], s_patch[p - PS]);
     const float grad = sqrtf(fadd(fmul(xg, xg), fmul(yg, yg)));
-    const float ori = atan2LUTff_dev(yg, xg);
+    const float ori = atan2LUTff_dev(yg, xg, s_lut);
     const double M_PI_DOUBLED = 6.28318530718;
     const float o = (float)(8.0 * ((double)ori + M_PI_DOUBLED) / M_PI_DOUBLED);
     out[p] = make_float2(fmul(tab->mask[p], grad), o);
@@ -427,17 +709,76 @@ k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __re
 using namespace MB2_NS;
 
 int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribeParams& dp, int max_m, unsigned long long* d_need,
-                      int* d_too_big, unsigned long long* d_sum_p2sq) {
+                      int* d_too_big, unsigned long long* d_sum_p2sq, unsigned long long* d_keys, int* d_cls_cnt) {
   if (!n) return MB2_OK;
-  MB2_LAUNCH(ctx, k_plan, (n + 127) / 128, 128, 0, kps, n, dp, max_m, d_need, d_too_big, d_sum_p2sq);
+  MB2_LAUNCH(ctx, k_plan, (n + 127) / 128, 128, 0, kps, n, dp, max_m, d_need, d_too_big, d_sum_p2sq, d_keys, d_cls_cnt);
   return MB2_OK;
 }
 
+namespace {
+// dynamic shared memory of a class = the largest region it may hold
+size_t class_smem_bytes(int cls, const int* tap_n, int max_m) {
+  int lo, hi; bool dense;
+  switch (cls) {
+    case CLS_DENSE_S: lo = 0; hi = MB2_CLS_M_DENSE_S; dense = true; break;
+    case CLS_DENSE_M: lo = MB2_CLS_M_DENSE_S + 1; hi = MB2_CLS_M_DENSE_M; dense = true; break;
+    case CLS_DENSE_L: lo = MB2_CLS_M_DENSE_M + 1; hi = MB2_CLS_M_DENSE_L; dense = true; break;
+    case CLS_NEED_S: lo = MB2_CLS_M_DENSE_L + 1; hi = MB2_CLS_M_NEED_S; dense = false; break;
+    case CLS_NEED_L: lo = MB2_CLS_M_NEED_S + 1; hi = MB2_CLS_M_NEED_L; dense = false; break;
+    default: return 0;
+  }
+  size_t best = 0;
+  for (int m = lo; m <= hi && m <= max_m; m++) {
+    const int nt = tap_n[m];
+    if (!nt) continue;
+    const size_t P2 = 2 * (size_t)m + 3, h = nt >> 1, SA = P2 + 2 * h;
+    const size_t fl = P2 * SA + 4 + (P2 + 2 * h) * (dense ? P2 : (size_t)SBN) + nt + 4;
+    best = std::max(best, fl * 4);
+  }
+  return best;
+}
+}  // namespace
+
 int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int n, const DescribeParams& dp,
-                               const DescTables* d_tables, const TapTable& taps, const unsigned long long* d_off, float* d_scratch,
+                               const DescTables* d_tables, const TapTable& taps, const int* tap_n_host, const ExtractPlan& plan,
+                               const unsigned long long* d_off, float* d_scratch,
                                uint8_t* d_desc, float* d_patches, float2* d_stats, double* d_vecT, float2* d_rec) {
   if (!n) return MB2_OK;
-  MB2_LAUNCH(ctx, k_extract, n, DT, 0, img, kps, n, dp, taps, d_off, d_scratch, d_patches);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_extract_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_extract_needed, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr = true;
+  }
+  // The few very large regions of the global-scratch class take as long as thousands of small ones: they run on
+  // the side stream, next to the shared-memory classes (per-kernel profiling keeps one stream).
+  const bool fork = !ctx->profiling && plan.count[CLS_GLOBAL] > 0 && plan.count[CLS_GLOBAL] < n;
+  int first = 0;
+  for (int cls = 0; cls < N_CLASSES; cls++) {
+    const int cnt = plan.count[cls];
+    if (cnt > 0) {
+      const unsigned long long* list = plan.sorted + first;
+      const size_t smem = class_smem_bytes(cls, tap_n_host, taps.max_m);
+      switch (cls) {
+        case CLS_GLOBAL:
+          if (fork) {
+            cudaEventRecord(ctx->ev_fork, ctx->stream);
+            cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+            MB2_LAUNCH_ON(ctx, ctx->side, k_extract, cnt, 512, 0, img, kps, list, cnt, dp, taps, d_off, d_scratch, d_patches);
+            cudaEventRecord(ctx->ev_join, ctx->side);
+          } else {
+            MB2_LAUNCH(ctx, k_extract, cnt, 512, 0, img, kps, list, cnt, dp, taps, d_off, d_scratch, d_patches);
+          }
+          break;
+        case CLS_NEED_L: MB2_LAUNCH(ctx, k_extract_needed, cnt, 512, smem, img, kps, list, cnt, dp, taps, d_patches); break;
+        case CLS_NEED_S: MB2_LAUNCH(ctx, k_extract_needed, cnt, 256, smem, img, kps, list, cnt, dp, taps, d_patches); break;
+        case CLS_DENSE_L: MB2_LAUNCH(ctx, k_extract_dense, cnt, 256, smem, img, kps, list, cnt, dp, taps, d_patches); break;
+        default: MB2_LAUNCH(ctx, k_extract_dense, cnt, 128, smem, img, kps, list, cnt, dp, taps, d_patches); break;
+      }
+    }
+    first += cnt;
+  }
+  if (fork) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
   if (dp.photoNorm) MB2_LAUNCH(ctx, k_photonorm_stats, (n + PN_T - 1) / PN_T, PN_T, 0, d_patches, n, d_tables, d_stats);
   MB2_LAUNCH(ctx, k_sift_grad, n, DT, 0, d_patches, n, dp, d_tables, d_stats, d_rec);
   MB2_LAUNCH(ctx, k_sift_votes, (n + VW - 1) / VW, VW * 32, 0, d_rec, n, d_tables, d_vecT);
