@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE (oracle) -- see mods_oracle.hpp.  Out-of-line pieces + C API for ctypes.
 #include "mods_oracle.hpp"
+#include "mser_oracle.hpp"
 #include <cstdio>
 
 namespace mo {
@@ -195,12 +196,41 @@ void orc_sift_patch(const float* patch41, int rootsift, float* desc128) {
   SIFTDescriptor D(41, rootsift != 0);
   D(patch41, desc128);
 }
-int orc_view_pipeline(const float* img, int w, int h, int detector, const HessParamsC* hp, double, int, double,
+// MSER: DetectMSERs (extrema.cpp:284) -- raw keys, or regions after DetectAffineRegions (synth-detection.hpp:93)
+int orc_mser_detect(const float* img, int w, int h, double max_area, int min_size, double min_margin, int mode, int reg_number,
+                    int raw, double* out, int max_out) {
+  mser::Params mp; mp.max_area = max_area; mp.min_size = min_size; mp.min_margin = min_margin; mp.mode = mode; mp.reg_number = reg_number;
+  std::vector<mser::MKey> mk = mser::detectMSERs(img, w, h, mp, 1.0, 1.0);
+  std::vector<Key> keys;
+  for (const mser::MKey& k : mk) keys.push_back(Key{k.x, k.y, k.a11, k.a12, k.a21, k.a22, k.s, k.response, k.sub_type});
+  if (!raw) toRegions(keys);
+  for (size_t i = 0; i < keys.size() && (int)i < max_out; i++) kp_out(keys[i], out + i * KP);
+  return (int)keys.size();
+}
+// raw region list of getRLEExtrema (libExtrema.cpp:462): rows of 13 doubles
+//   polarity minI maxI threshold margin area border nruns cx cy sxx sxy syy
+int orc_mser_regions(const float* img, int w, int h, double max_area, int min_size, double min_margin, double* out, int max_out) {
+  mser::Params mp; mp.max_area = max_area; mp.min_size = min_size; mp.min_margin = min_margin;
+  std::vector<mser::OutRegion> regs;
+  mser::detectMSERs(img, w, h, mp, 1.0, 1.0, &regs);
+  for (size_t i = 0; i < regs.size() && (int)i < max_out; i++) {
+    const mser::OutRegion& r = regs[i]; double* o = out + i * 13;
+    o[0] = r.polarity; o[1] = r.minI; o[2] = r.maxI; o[3] = r.threshold; o[4] = r.margin; o[5] = r.area; o[6] = r.border;
+    o[7] = (double)r.rle.size(); o[8] = r.cx; o[9] = r.cy; o[10] = r.sxx; o[11] = r.sxy; o[12] = r.syy;
+  }
+  return (int)regs.size();
+}
+int orc_view_pipeline(const float* img, int w, int h, int detector, const HessParamsC* hp, double mser_max_area, int mser_min_size, double mser_min_margin,
                       double ori_mrSize, int ori_patch, int maxAngles, double ori_th, double desc_mrSize, int desc_patch,
                       int photoNorm, int rootsift, double* det_out, double* reproj_out, float* desc_out, int max_out) {
-  if (detector != 0) return -1;  // MSER restatement: not built yet
   Image im = image_in(img, w, h);
-  std::vector<Key> kp1 = detectAffineKeypoints(im, to_par(*hp), 1.0, 1.0);
+  std::vector<Key> kp1;
+  if (detector == 0) kp1 = detectAffineKeypoints(im, to_par(*hp), 1.0, 1.0);
+  else {
+    mser::Params mp; mp.max_area = mser_max_area; mp.min_size = mser_min_size; mp.min_margin = mser_min_margin;
+    for (const mser::MKey& k : mser::detectMSERs(img, w, h, mp, 1.0, 1.0))
+      kp1.push_back(Key{k.x, k.y, k.a11, k.a12, k.a21, k.a22, k.s, k.response, k.sub_type});
+  }
   toRegions(kp1);
   std::vector<Key> det = detectOrientation(kp1, im, ori_mrSize, ori_patch, maxAngles, ori_th), rep;
   const double H[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

@@ -84,6 +84,14 @@ class Lib:
                                    C.c_double(min_margin), C.c_int(mode), C.c_int(reg_number), C.c_int(int(raw)), _p(out), C.c_int(max_out))
         return out[:n].copy()
 
+    def mser_regions(self, img, max_area=0.05, min_size=30, min_margin=8.0, max_out=400000):
+        """rows: polarity minI maxI threshold margin area border nruns cx cy sxx sxy syy"""
+        img = _f32(img); out = np.zeros((max_out, 13))
+        n = self.fn("mser_regions")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_double(max_area), C.c_int(min_size),
+                                    C.c_double(min_margin), _p(out), C.c_int(max_out))
+        assert n <= max_out
+        return out[:n].copy()
+
     def detect_orientation(self, img, kps, mrSize=1.0, patchSize=41, maxAngles=1, th=0.8):
         img = _f32(img); kps = _f64(kps); n = len(kps)
         out = np.zeros((max(1, n * max(1, maxAngles) * 2), KP))

@@ -15,6 +15,7 @@
 #include "detectors/helpers.h"
 #include "detectors/affinedetectors/scale-space-detector.hpp"
 #include "detectors/mser/extrema/extrema.h"
+#include "detectors/mser/extrema/libExtrema.h"
 #include "matching/siftdesc.h"
 #include "synth-detection.hpp"
 
@@ -170,6 +171,30 @@ int ref_mser_detect(const float* img, int w, int h, double max_area, int min_siz
     DetectAffineRegions(view, regs, ep, DET_MSER, DetectMSERs);
     n = (int)regs.size();
     for (int i = 0; i < n && i < max_out; i++) kp_out(regs[i].det_kp, out + (size_t)i * KP);
+  }
+  return n;
+}
+
+// raw region list of getRLEExtrema (libExtrema.cpp:462) as DetectMSERs calls it (extrema.cpp:405): rows of 13 doubles
+//   polarity minI maxI threshold margin area border nruns cx cy sxx sxy syy
+int ref_mser_regions(const float* img, int w, int h, double max_area, int min_size, double min_margin, double* out, int max_out) {
+  extrema::ExtremaParams ep;
+  ep.max_area = max_area; ep.min_size = min_size; ep.min_margin = min_margin;
+  extrema::ExtremaImage im;
+  im.height = h; im.width = w; im.channels = 1;
+  std::vector<unsigned char> px((size_t)w * h);
+  for (size_t i = 0; i < px.size(); i++) px[i] = (unsigned char)img[i];    // extrema.cpp:401-403
+  im.data = px.data();
+  extrema::RLEExtrema res = extrema::getRLEExtrema(ep, im);
+  int n = 0;
+  for (int pol = 0; pol < 2; pol++) {
+    const std::vector<extrema::RLERegion>& v = pol ? res.MSERmin : res.MSERplus;
+    for (size_t i = 0; i < v.size(); i++, n++) {
+      if (n >= max_out) continue;
+      const extrema::RLERegion& r = v[i]; double* o = out + (size_t)n * 13;
+      o[0] = pol; o[1] = r.minI; o[2] = r.maxI; o[3] = r.threshold; o[4] = r.margin; o[5] = r.area; o[6] = r.border;
+      o[7] = (double)r.rle.size(); o[8] = r.cx; o[9] = r.cy; o[10] = r.sxx; o[11] = r.sxy; o[12] = r.syy;
+    }
   }
   return n;
 }

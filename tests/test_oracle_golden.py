@@ -43,3 +43,28 @@ def test_cat_crop_matches_reference(oracle):
 def test_scorers_match_reference(oracle, which):
     """HDs, HDsSym, HDsSymMax (Htools.c), FDs, FDsSym (Ftools.c): closed-form f64, bit-exact."""
     assert np.array_equal(oracle.score(which, G["r_u"], G["r_M"]), G["r_scores"][which])
+
+
+# ---- MSER (row a9): vectors from the reference's own detectors/mser sources (tests/golden/make_golden_mser.py)
+GM = np.load(os.path.join(os.path.dirname(__file__), "golden", "mser_vectors.npz"))
+
+
+def test_mser_cat_crop_matches_reference(oracle):
+    assert np.array_equal(oracle.mser_detect(G["cat_gray"]), G["cat_mser"])
+    assert np.array_equal(oracle.mser_regions(G["cat_gray"]), GM["cat_regions"])
+    assert np.array_equal(oracle.mser_detect(G["cat_gray"]), GM["cat_keys"])
+
+
+def test_mser_synthetic_matches_reference(oracle):
+    img = synth.blob_image(320, 240, seed=11)
+    assert np.array_equal(oracle.mser_regions(img), GM["s_regions"]) and len(GM["s_regions"]) > 100
+    assert np.array_equal(oracle.mser_detect(img), GM["s_keys"])
+
+
+def test_mser_plateaus_and_noise_match_reference(oracle):
+    """Equal-size merges, regions born inside a level, tiny min_size: the order-dependent corners of getExtrema.cpp."""
+    p = GM["p_img"].astype(np.float32)
+    assert np.array_equal(oracle.mser_regions(p, max_area=0.3, min_size=8, min_margin=1.0), GM["p_regions"])
+    assert np.array_equal(oracle.mser_detect(p, max_area=0.3, min_size=8, min_margin=1.0), GM["p_keys"])
+    n = GM["n_img"].astype(np.float32)
+    assert np.array_equal(oracle.mser_regions(n, min_size=5, min_margin=2.0), GM["n_regions"])

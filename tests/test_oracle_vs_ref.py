@@ -91,3 +91,38 @@ def test_scorers(oracle, reference):
         M = rng.normal(size=9); M[8] = 1.0
         for which in range(5):
             assert np.array_equal(oracle.score(which, u, M), reference.score(which, u, M))
+
+
+# ---- MSER (row a9)
+def test_mser_blobs(oracle, reference):
+    for seed in (3, 4):
+        im = synth.blob_image(400, 300, seed=seed)
+        a, b = oracle.mser_regions(im), reference.mser_regions(im)
+        assert len(a) > 100 and np.array_equal(a, b)
+        assert np.array_equal(oracle.mser_detect(im), reference.mser_detect(im))
+        assert np.array_equal(oracle.mser_detect(im, raw=True), reference.mser_detect(im, raw=True))
+
+
+def test_mser_noise_and_plateaus(oracle, reference):
+    rng = np.random.default_rng(9)
+    for k in range(4):
+        im = rng.integers(0, 256, (90, 130)).astype(np.float32)
+        assert np.array_equal(oracle.mser_regions(im, min_size=5, min_margin=2.0), reference.mser_regions(im, min_size=5, min_margin=2.0))
+        pl = (np.floor(np.kron(rng.random((30, 40)), np.ones((4, 4))) * 10) * 25).astype(np.float32)
+        kw = dict(max_area=0.3, min_size=8, min_margin=1.0)
+        assert np.array_equal(oracle.mser_regions(pl, **kw), reference.mser_regions(pl, **kw))
+
+
+@pytest.mark.parametrize("mode,regs", [(2, 50), (4, 2000), (4, 20)])
+def test_mser_detector_modes(oracle, reference, mode, regs):
+    """FIXED_REG_NUMBER / NOT_LESS_THAN_REGIONS (extrema.cpp:31-90): min_margin forced to 1, sort by margin, truncate."""
+    im = synth.blob_image(300, 200, seed=8)
+    a = oracle.mser_detect(im, mode=mode, reg_number=regs)
+    b = reference.mser_detect(im, mode=mode, reg_number=regs)
+    assert len(a) > 10 and np.array_equal(a, b)
+
+
+def test_mser_view_pipeline(oracle, reference):
+    im = synth.blob_image(400, 300, seed=21)
+    a, b = oracle.view_pipeline(im, detector=3), reference.view_pipeline(im, detector=3)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 50
