@@ -53,6 +53,18 @@ typedef struct {
   float mrSize;               /* 3*sqrt(3) */
 } mb2_hessaff_params;
 
+/* [MSER] section of config_iter_mods_cviu.ini == extrema::ExtremaParams (detectors/mser/extrema/extremaParams.h:56-93). */
+typedef struct {
+  double max_area;      /* 0.05 */
+  int min_size;         /* 30 (>= 2) */
+  double min_margin;    /* 8 */
+  int relative;         /* 0 (relative margins: unsupported) */
+  int mode;             /* detection_mode_t: 0 FIXED_TH .. 4 NOT_LESS_THAN_REGIONS */
+  int reg_number;
+  float rel_threshold;
+  float rel_reg_number;
+} mb2_mser_params;
+
 /* [DominantOrientation] (descriptors_parameters.hpp) as passed to DetectOrientation
  * (synth-detection.cpp:841-849). */
 typedef struct {
@@ -103,6 +115,18 @@ int mb2_ctx_profile_end(mb2_ctx* ctx, char* buf, int buflen);
 int mb2_hessaff_detect(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_hessaff_params* par,
                        double tilt, double zoom, int as_regions, double* out_kp, int capacity);
 
+/* Replaces the detector hook `int DetectMSERs(cv::Mat&, vector<AffineKeypoint>&, extrema::ExtremaParams, ScalePyramid&,
+ * tilt, zoom)` (detectors/mser/extrema/extrema.h:11, extrema.cpp:284-473; doOnNormal branch) and everything below it
+ * (getRLEExtrema, libExtrema.cpp:462) *plus* the post-step of DetectAffineRegions<> when `as_regions` != 0.
+ * MSER+ regions first, then MSER-, each in the reference's list order; response = margin, sub_type 21 / 20.
+ * Returns the number of keypoints; MB2_ERR_UNSUPPORTED when the reference itself leaves the defined behaviour of its
+ * packed label fields (a min_reg label absorbing >= 32768 pixels, getExtrema.cpp:322). */
+int mb2_mser_detect(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_mser_params* par, double tilt, double zoom,
+                    int as_regions, double* out_kp, int capacity);
+/* Diagnostics / parity: the raw region list of getRLEExtrema (libExtrema.cpp:462-482), one row of 13 doubles per
+ * (region, threshold): polarity minI maxI threshold margin area border nruns cx cy sxx sxy syy.  FIXED_TH semantics. */
+int mb2_mser_regions(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_mser_params* par, double* out_rows, int capacity);
+
 /* Replaces `int DetectOrientation(AffineRegionList&, AffineRegionList&, SynthImage&, mrSize,
  * patchSize, doHalfSIFT=0, maxAngNum, th, addUpRight=false)` (synth-detection.cpp:841-919). */
 int mb2_detect_orientation(mb2_ctx* ctx, const float* pixels, int w, int h, const double* in_kp, int n,
@@ -128,6 +152,13 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
                              const mb2_orientation_params* ori, const mb2_sift_params* desc,
                              int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8,
                              int capacity);
+
+/* Same pass with detector = MSER (imagerepresentation.cpp:1035-1038). */
+int mb2_detect_describe_view_mser(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H,
+                                  int orig_w, int orig_h, const mb2_mser_params* det,
+                                  const mb2_orientation_params* ori, const mb2_sift_params* desc,
+                                  int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8,
+                                  int capacity);
 
 /* Copies the regions of the most recent mb2_detect_describe_view (which may be called with NULL
  * outputs to learn the count first) to the host.  Returns that count. */

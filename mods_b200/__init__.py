@@ -18,6 +18,7 @@ EXPORTS = [
     "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
     "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
+    "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser",
 ]
 
 
@@ -36,6 +37,16 @@ class HessaffParams(C.Structure):
     @staticmethod
     def default():
         return HessaffParams(5.3333, 3, 1.6, 10.0, 5, 16, 0.05, 19, 1, 0, 2000, -1.0, -1.0, 41, 3.0 * 3.0 ** 0.5)
+
+
+class MserParams(C.Structure):
+    """mb2_mser_params == [MSER] of config_iter_mods_cviu.ini (extrema::ExtremaParams)."""
+    _fields_ = [("max_area", C.c_double), ("min_size", C.c_int), ("min_margin", C.c_double), ("relative", C.c_int),
+                ("mode", C.c_int), ("reg_number", C.c_int), ("rel_threshold", C.c_float), ("rel_reg_number", C.c_float)]
+
+    @staticmethod
+    def default():
+        return MserParams(0.05, 30, 8.0, 0, 0, -1, -1.0, -1.0)
 
 
 class OrientationParams(C.Structure):
@@ -201,6 +212,25 @@ class Context:
                                                  C.c_double(1.0), C.c_int(int(as_regions)), _ptr(out), C.c_int(capacity)), "hessaff_detect")
         return out[:n].copy()
 
+    def mser_detect(self, img, par=None, as_regions=True, capacity=None, shape=None, tilt=1.0, zoom=1.0):
+        h, w = shape if shape is not None else img.shape
+        par = par or MserParams.default()
+        capacity = capacity or max(4096, (h * w) // 16)
+        out = np.zeros((capacity, KP))
+        n = self._check(lib().mb2_mser_detect(self.h, _ptr(img), C.c_int(w), C.c_int(h), C.byref(par), C.c_double(tilt),
+                                              C.c_double(zoom), C.c_int(int(as_regions)), _ptr(out), C.c_int(capacity)), "mser_detect")
+        return out[:n].copy()
+
+    def mser_regions(self, img, par=None, capacity=None, shape=None):
+        """rows: polarity minI maxI threshold margin area border nruns cx cy sxx sxy syy"""
+        h, w = shape if shape is not None else img.shape
+        par = par or MserParams.default()
+        capacity = capacity or max(4096, (h * w) // 16)
+        out = np.zeros((capacity, 13))
+        n = self._check(lib().mb2_mser_regions(self.h, _ptr(img), C.c_int(w), C.c_int(h), C.byref(par), _ptr(out), C.c_int(capacity)),
+                        "mser_regions")
+        return out[:n].copy()
+
     def detect_orientation(self, img, kps, par=None, shape=None):
         h, w = shape if shape is not None else img.shape
         par = par or OrientationParams.default()
@@ -233,9 +263,10 @@ class Context:
             dk = np.zeros((capacity, KP)); rk = np.zeros((capacity, KP)); du = np.zeros((capacity, 128), np.uint8)
         else:
             dk = rk = du = None
-        n = self._check(lib().mb2_detect_describe_view(self.h, _ptr(img), C.c_int(w), C.c_int(h), _ptr(H), C.c_int(ow), C.c_int(oh),
-                                                       C.byref(det), C.byref(ori), C.byref(desc), C.c_int(slot), C.c_int(int(append)),
-                                                       _ptr(dk), _ptr(rk), _ptr(du), C.c_int(capacity)), "detect_describe_view")
+        fn = lib().mb2_detect_describe_view_mser if isinstance(det, MserParams) else lib().mb2_detect_describe_view
+        n = self._check(fn(self.h, _ptr(img), C.c_int(w), C.c_int(h), _ptr(H), C.c_int(ow), C.c_int(oh),
+                           C.byref(det), C.byref(ori), C.byref(desc), C.c_int(slot), C.c_int(int(append)),
+                           _ptr(dk), _ptr(rk), _ptr(du), C.c_int(capacity)), "detect_describe_view")
         if want_host:
             return dk[:n].copy(), rk[:n].copy(), du[:n].copy()
         return n

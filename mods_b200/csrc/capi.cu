@@ -652,6 +652,7 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   for (auto& s : ctx->slots) { s.desc.release(); s.xy.release(); }
   ctx->h_a.release(); ctx->h_b.release(); ctx->h_c.release();
+  mb2_mser_release(ctx);
   drop_priv(ctx);
   if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -768,16 +769,18 @@ int mb2_describe_sift(mb2_ctx* ctx, const float* pixels, int w, int h, const dou
   return n;
 }
 
-int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H, int orig_w, int orig_h,
-                             const mb2_hessaff_params* det, const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot,
-                             int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
-  if (!ctx || !pixels || !H || !det || !ori || !desc || slot < 0 || slot >= MB2_MAX_SLOTS) return MB2_ERR_ARG;
+// One (detector, view) pass; det_h != NULL: HessianAffine, det_m != NULL: MSER.
+static int view_core(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H, int orig_w, int orig_h,
+                     const mb2_hessaff_params* det_h, const mb2_mser_params* det_m, const mb2_orientation_params* ori, const mb2_sift_params* desc,
+                     int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
+  if (!ctx || !pixels || !H || (!det_h && !det_m) || !ori || !desc || slot < 0 || slot >= MB2_MAX_SLOTS) return MB2_ERR_ARG;
   cudaSetDevice(ctx->device);
   ImgView img;
   int rc, n = 0, m = 0, k = 0;
   ctx->last_view_n = 0;
   if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
-  if ((rc = detect_core(ctx, img, *det, 1.0, 1.0, 1, &n))) return rc;
+  if (det_h) { if ((rc = detect_core(ctx, img, *det_h, 1.0, 1.0, 1, &n))) return rc; }
+  else if ((rc = mb2_mser_core(ctx, img, *det_m, 1.0, 1.0, 1, &n, nullptr, 0))) return rc;
   if ((rc = orient_core(ctx, img, n, *ori, &m))) return rc;
   RegionSlot& rs = ctx->slots[slot];
   if (!append) rs.n = 0;
@@ -840,6 +843,46 @@ int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, co
     if (k > capacity && (det_kp || reproj_kp || desc_u8)) { ctx->set_error("view: output capacity too small"); return MB2_ERR_CAPACITY; }
   }
   return k;
+}
+
+int mb2_detect_describe_view(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H, int orig_w, int orig_h,
+                             const mb2_hessaff_params* det, const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot,
+                             int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
+  if (!det) return MB2_ERR_ARG;
+  return view_core(ctx, pixels, w, h, H, orig_w, orig_h, det, nullptr, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
+}
+int mb2_detect_describe_view_mser(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H, int orig_w, int orig_h,
+                                  const mb2_mser_params* det, const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot,
+                                  int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
+  if (!det) return MB2_ERR_ARG;
+  return view_core(ctx, pixels, w, h, H, orig_w, orig_h, nullptr, det, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
+}
+
+int mb2_mser_detect(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_mser_params* par, double tilt, double zoom, int as_regions,
+                    double* out_kp, int capacity) {
+  if (!ctx || !pixels || !par || w <= 0 || h <= 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView img;
+  int rc, n = 0;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  if ((rc = mb2_mser_core(ctx, img, *par, tilt, zoom, as_regions, &n, nullptr, 0))) return rc;
+  if ((rc = download_keys(ctx, ctx->kp_b.as<KeyOut>(), n, out_kp, capacity, ctx->rs_b))) return rc;
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n > capacity) { ctx->set_error("mser: output capacity too small"); return MB2_ERR_CAPACITY; }
+  return n;
+}
+int mb2_mser_regions(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_mser_params* par, double* out_rows, int capacity) {
+  if (!ctx || !pixels || !par || !out_rows || w <= 0 || h <= 0 || capacity <= 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView img;
+  int rc, n = 0;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  MB2_CUDA_CHECK(ctx, ctx->rs_u.reserve((size_t)capacity * 13 * 8));
+  mb2_mser_params p = *par; p.mode = 0;
+  if ((rc = mb2_mser_core(ctx, img, p, 1.0, 1.0, 0, &n, ctx->rs_u.as<double>(), capacity))) return rc;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(out_rows, ctx->rs_u.p, (size_t)std::min(n, capacity) * 13 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return n;
 }
 
 int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {

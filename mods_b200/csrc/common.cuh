@@ -81,6 +81,7 @@ struct mb2_ctx {
   struct ProfRec { const char* name; cudaEvent_t a, b; };
   bool profiling = false;
   std::vector<ProfRec> prof;
+  void* mser_state = nullptr;   // MserBufs (mser.cu), released by mb2_mser_release
   unsigned long long prof_extract_bytes = 0;  // algorithmic gather bytes of the patch-extraction launches
   void set_error(const std::string& s) { err = s; }
 };

@@ -6,5 +6,6 @@
 #include "describe.cu"
 #include "nn.cu"
 #include "ransac.cu"
+#include "mser.cu"
 #include "capi.cu"
 #include "ransac_host.cu"

@@ -83,3 +83,8 @@ int mb2_launch_describe(mb2_ctx* ctx, const ImgView& img, const KeyOut* kps, int
 // reprojection + boundary filter (synth-detection.cpp:541-616)
 void mb2_launch_reproject(mb2_ctx* ctx, const KeyOut* det, int n, const double* Hinv9, int h_is_eye, int orig_w, int orig_h,
                           KeyOut* reproj /* keep flag set */);
+
+// mser.cu: MSER+ / MSER- keys of the device image -> ctx->kp_b (reference order)
+int mb2_mser_core(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, double tilt, double zoom, int as_regions, int* n_out,
+                  double* d_table_out, int capacity);
+void mb2_mser_release(mb2_ctx* ctx);

@@ -1,0 +1,102 @@
+"""MSER on the GPU, through the C ABI, against the CPU oracle and the reference's golden
+vectors: region list (order, lifetimes, thresholds, margins, areas, borders, run counts) and f64 moments bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import mods_b200 as mb
+import synth
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+GM = np.load(os.path.join(os.path.dirname(__file__), "golden", "mser_vectors.npz"))
+
+
+def _par(max_area=0.05, min_size=30, min_margin=8.0, mode=0, reg_number=-1):
+    return mb.MserParams(max_area, min_size, min_margin, 0, mode, reg_number, -1.0, -1.0)
+
+
+def test_mser_regions_match_reference_golden(ctx):
+    assert np.array_equal(ctx.mser_regions(G["cat_gray"]), GM["cat_regions"])
+    assert np.array_equal(ctx.mser_detect(G["cat_gray"]), GM["cat_keys"])
+    img = synth.blob_image(320, 240, seed=11)
+    assert np.array_equal(ctx.mser_regions(img), GM["s_regions"])
+    assert np.array_equal(ctx.mser_detect(img), GM["s_keys"])
+
+
+def test_mser_order_dependent_corners_match_reference_golden(ctx):
+    """Plateaus (equal-size merges, births inside a level) and white noise with tiny min_size."""
+    p = GM["p_img"].astype(np.float32)
+    assert np.array_equal(ctx.mser_regions(p, _par(0.3, 8, 1.0)), GM["p_regions"])
+    assert np.array_equal(ctx.mser_detect(p, _par(0.3, 8, 1.0)), GM["p_keys"])
+    n = GM["n_img"].astype(np.float32)
+    assert np.array_equal(ctx.mser_regions(n, _par(0.05, 5, 2.0)), GM["n_regions"])
+
+
+@pytest.mark.parametrize("wh,seed", [((640, 480), 3), ((333, 257), 4), ((1280, 960), 5)])
+def test_mser_bit_exact_vs_oracle(ctx, oracle, wh, seed):
+    img = synth.blob_image(wh[0], wh[1], seed=seed)
+    g, o = ctx.mser_regions(img), oracle.mser_regions(img)
+    assert len(o) > 100 and np.array_equal(g, o)
+    assert np.array_equal(ctx.mser_detect(img, as_regions=False), oracle.mser_detect(img, raw=True))
+    assert np.array_equal(ctx.mser_detect(img, as_regions=True), oracle.mser_detect(img, raw=False))
+
+
+def test_mser_random_small_images(ctx, oracle):
+    rng = np.random.default_rng(17)
+    for k in range(24):
+        kind = k % 3
+        if kind == 0:
+            img = rng.integers(0, 256, (int(rng.integers(5, 60)), int(rng.integers(5, 60)))).astype(np.float32)
+            kw = dict(max_area=0.5, min_size=int(rng.integers(2, 12)), min_margin=float(rng.integers(1, 6)))
+        elif kind == 1:
+            k2 = int(rng.integers(1, 5))
+            img = (np.kron(rng.integers(0, 5, (int(rng.integers(2, 9)), int(rng.integers(2, 9)))), np.ones((k2, k2))) * int(rng.integers(1, 50))).astype(np.float32)
+            kw = dict(max_area=0.9, min_size=int(rng.integers(2, 10)), min_margin=float(rng.integers(1, 4)))
+        else:
+            img = (rng.integers(0, 8, (int(rng.integers(5, 40)), int(rng.integers(5, 40)))) * 30).astype(np.float32)
+            kw = dict(max_area=0.9, min_size=int(rng.integers(2, 20)), min_margin=1.0)
+        g = ctx.mser_regions(img, _par(kw["max_area"], kw["min_size"], kw["min_margin"]))
+        o = oracle.mser_regions(img, **kw)
+        assert np.array_equal(g, o), (k, img.shape, kw)
+
+
+def test_mser_degenerate_inputs(ctx):
+    assert len(ctx.mser_detect(np.full((50, 70), 128, np.float32))) == 0       # flat image: one component, never stable
+    assert len(ctx.mser_detect(np.zeros((3, 3), np.float32))) == 0
+    with pytest.raises(mb.Mb2Error):
+        ctx.mser_detect(np.zeros((20, 20), np.float32), _par(min_size=1))
+
+
+@pytest.mark.parametrize("mode,regs", [(2, 50), (4, 2000), (4, 20)])
+def test_mser_detector_modes(ctx, oracle, mode, regs):
+    im = synth.blob_image(300, 200, seed=8)
+    g = ctx.mser_detect(im, _par(mode=mode, reg_number=regs))
+    o = oracle.mser_detect(im, mode=mode, reg_number=regs)
+    assert len(o) > 10 and np.array_equal(g, o)
+
+
+def test_mser_view_pipeline_bit_exact(ctx, oracle):
+    """detector = MSER through detect -> orientation -> reprojection -> RootSIFT (imagerepresentation.cpp:1035-1038, 1254-1341)."""
+    img = synth.blob_image(640, 480, seed=3)
+    gd, gr, gu = ctx.detect_describe_view(img, det=mb.MserParams.default(), slot=2)
+    od, orp, ou = oracle.view_pipeline(img, detector=3)
+    assert len(od) > 100
+    assert np.array_equal(gd, od) and np.array_equal(gr, orp) and np.array_equal(gu.astype(np.float32), ou)
+
+
+def test_mser_full_size_properties(ctx):
+    """4096x3072 (BASELINE C3): deterministic, every region inside its size bounds, centroids inside the image, and the
+    moments of a region equal those recomputed from its area-consistent ellipse (det A = sqrt(det cov))."""
+    img = synth.blob_image(4096, 3072, seed=1, n_blobs=int(1.5e-3 * 4096 * 3072))
+    a = ctx.mser_regions(img, capacity=400000)
+    b = ctx.mser_regions(img, capacity=400000)
+    assert len(a) > 2000 and np.array_equal(a, b)
+    assert (a[:, 5] > 30).all() and (a[:, 5] <= 0.05 * 4096 * 3072).all() and (a[:, 4] > 8).all()
+    assert (a[:, 8] >= 0).all() and (a[:, 8] <= 4096).all() and (a[:, 9] >= 0).all() and (a[:, 9] <= 3072).all()
+    assert (a[:, 3] >= a[:, 1]).all() and (a[:, 3] < a[:, 2]).all()
+    k = ctx.mser_detect(img, as_regions=False, capacity=400000)
+    det_cov = a[:, 10] * a[:, 12] - a[:, 11] ** 2
+    det_A = k[:, 2] * k[:, 5] - k[:, 3] * k[:, 4]
+    assert np.allclose(det_A ** 2, det_cov, rtol=1e-9)
