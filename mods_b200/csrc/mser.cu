@@ -1,11 +1,13 @@
 // MSER detector on the GPU: replaces DetectMSERs (detectors/mser/extrema/extrema.cpp:284-473)
 // and everything below it (libExtrema.cpp, sortPixels.cpp, getExtrema.cpp, optThresh.cpp, boundary.cpp).
 //
-// The reference is sequential in (intensity, raster) order.  Here:
+// The reference is sequential in (intensity, raster) order.  Here both polarities are handled as ONE problem: the
+// inverted image (MSER-) is stacked under the image (MSER+) in one pixel index space of 2*W*H pixels whose halves are never
+// neighbours, so every level-synchronous phase below serves both at once:
 //   1. k_mser_prep / radix sort      u8 image of the polarity, pixels ordered by (level, raster)      [HBM streaming]
-//   2. k_mser_union / k_mser_final   component tree of the level sets, level by level: lock-free union-find with
-//                                    "larger (level, index) wins" hooking, so the representative of a component is
-//                                    its canonical pixel; every element that stops being a root is recorded once
+//   2. k_mser_tree (union / final)   component tree of the level sets, level by level: lock-free union-find with
+//                                    "larger (level, index) wins" hooking, so the representative of a component
+//                                    is a pixel of its top level; every element that stops being a root is recorded once
 //                                    (`hooked`, grouped by level), gets its canonical parent and adds its area / inner
 //                                    edge count to the new representative                              [L2 latency]
 //   3. k_mser_best .. k_mser_emulate survivor of every merge = largest tracked child; nodes where the reference's
@@ -22,19 +24,22 @@
 #include "pyramid.cuh"
 #include "mser_logic.cuh"
 
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 namespace MB2_NS {
 using namespace mser_logic;
+namespace cg = cooperative_groups;
 typedef unsigned long long u64;
 
 struct MserCounters {
   uint32_t hook_cnt, emu_nodes, own_keys, long_regions, n_sel, n_slots, n_starts, n_ends;
-  uint32_t overflow, thr_overflow, root, cap_overflow;
+  uint32_t overflow, thr_overflow, cap_overflow, root[2];
   uint32_t hist[256];
   uint32_t lvl_off[257];
   uint32_t hook_off[258];
@@ -60,33 +65,50 @@ struct MserBufs {
   }
 };
 
-// ---- union-find on zpar (L2-coherent accesses: other SMs hook concurrently) ---------------------------------------
+// ---- union-find on zpar ---------------------------------------------------------------------------------------------
+// In a level where a big component forms, every find ends on the same root: read through L2 (__ldcg) that one sector
+// becomes a hot spot that serialises the whole level.  The fast path therefore reads through L1 (possibly stale: a stale
+// pointer is still an ancestor, a stale "root" is caught by the CAS, which then falls back to L2-coherent reads).
+template <bool COHERENT>
+__device__ __forceinline__ uint32_t uf_load(const uint32_t* p) { return COHERENT ? __ldcg(p) : __ldca(p); }
+template <bool COHERENT>
 __device__ __forceinline__ uint32_t uf_find(uint32_t* zpar, uint32_t x) {
   for (;;) {
-    const uint32_t p = __ldcg(zpar + x);
+    const uint32_t p = uf_load<COHERENT>(zpar + x);
     if (p == x) return x;
-    const uint32_t g = __ldcg(zpar + p);
+    const uint32_t g = uf_load<COHERENT>(zpar + p);
     if (g != p) __stcg(zpar + x, g);  // path halving; values only ever move towards the root
     x = g;
   }
 }
+// Hooking order: a root of a lower level always goes under a pixel of the current level; inside a level the SMALLER
+// raster index wins.  Threads reach the pixels of a level in ascending order, so a late pixel hooks its own (uncontended)
+// root under the established one instead of dethroning it -- with "larger index wins" the root of a big component would
+// change once per joining pixel, one contended CAS after the other.  Which pixel of its level names a node is irrelevant
+// to every output (mser_logic.cuh).
 __device__ __forceinline__ bool key_less(const uint8_t* lev, uint32_t a, uint32_t b) {
   const int la = lev[a], lb = lev[b];
-  return la < lb || (la == lb && a < b);
+  return la < lb || (la == lb && a > b);
 }
-// joins the sets of a and b; returns the element that stopped being a root (NONE if already joined)
+// joins the sets of a and b; returns the element that stopped being a root (NONE if already joined).
+// A failed CAS returns the true parent of the element we took for a root: the search continues upwards from there (fresh
+// information every time, so it terminates) instead of re-reading the contended pointers through L2.  Hooking under an
+// element that has meanwhile stopped being a root itself is fine: its ancestors have larger keys, the forest stays ordered.
 __device__ __forceinline__ uint32_t uf_unite(uint32_t* zpar, const uint8_t* lev, uint32_t a, uint32_t b) {
+  uint32_t ra = uf_find<false>(zpar, a), rb = uf_find<false>(zpar, b);
   for (;;) {
-    uint32_t ra = uf_find(zpar, a), rb = uf_find(zpar, b);
     if (ra == rb) return NONE;
     if (key_less(lev, rb, ra)) { const uint32_t t = ra; ra = rb; rb = t; }
-    if (atomicCAS(zpar + ra, ra, rb) == ra) return ra;
+    const uint32_t old = atomicCAS(zpar + ra, ra, rb);
+    if (old == ra) return ra;
+    ra = uf_find<false>(zpar, old);
   }
 }
 
 // ---- 1. preparation ------------------------------------------------------------------------------------------------
-// float -> u8 as extrema.cpp:401-403 does ((unsigned char) of the float: truncation), inverted for MSER-
-__global__ void k_mser_prep(const float* __restrict__ img, int pitch, int W, int H, int pol, uint8_t* __restrict__ lev,
+// float -> u8 as extrema.cpp:401-403 does ((unsigned char) of the float: truncation); second half = inverted image
+// (InvertImageAndHistogram, sortPixels.cpp:131-153)
+__global__ void k_mser_prep(const float* __restrict__ img, int pitch, int W, int H, uint8_t* __restrict__ lev,
                             uint32_t* __restrict__ zpar, uint32_t* __restrict__ parent, uint32_t* __restrict__ area,
                             uint32_t* __restrict__ order_in, MserCounters* __restrict__ C) {
   __shared__ uint32_t h[256];
@@ -96,9 +118,10 @@ __global__ void k_mser_prep(const float* __restrict__ img, int pitch, int W, int
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     const int y = i / W, x = i - y * W;
     const int v = ((int)img[(size_t)y * pitch + x]) & 0xff;
-    const uint8_t l = (uint8_t)(pol ? 255 - v : v);
-    lev[i] = l; zpar[i] = i; parent[i] = i; area[i] = 1; order_in[i] = i;
-    atomicAdd(&h[l], 1u);
+    const uint32_t j = i + N;
+    lev[i] = (uint8_t)v; zpar[i] = i; parent[i] = i; area[i] = 1; order_in[i] = i;
+    lev[j] = (uint8_t)(255 - v); zpar[j] = j; parent[j] = j; area[j] = 1; order_in[j] = j;
+    atomicAdd(&h[v], 1u); atomicAdd(&h[255 - v], 1u);
   }
   __syncthreads();
   if (h[threadIdx.x]) atomicAdd(&C->hist[threadIdx.x], h[threadIdx.x]);
@@ -114,7 +137,10 @@ __global__ void k_mser_offsets(MserCounters* C) {
 // ---- 2. component tree, one level per launch pair ---------------------------------------------------------------------
 // A pixel joins every 4-neighbour that the reference has already labelled when it reaches the pixel: lower level, or the
 // same level and earlier in raster order (getExtrema.cpp:216-263).  nedge[p] counts them (border_num / 2).
-__global__ void k_mser_union(int L, int W, int H, const uint8_t* __restrict__ lev, const uint32_t* __restrict__ order, uint32_t* zpar,
+// The phase is latency bound (a chain of dependent L2 reads per pixel), so the four neighbour roots are chased together
+// and de-duplicated before anything is hooked; lanes of a warp hold raster neighbours of one level and mostly want to hook
+// the SAME lower root: one lane per distinct root issues the CAS, the others continue from its outcome.
+__device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint8_t* __restrict__ lev, const uint32_t* __restrict__ order, uint32_t* zpar,
                              uint32_t* __restrict__ nedge, uint32_t* __restrict__ hooked, MserCounters* C) {
   const uint32_t beg = C->lvl_off[L], end = C->lvl_off[L + 1];
   const int lane = threadIdx.x & 31;
@@ -122,25 +148,61 @@ __global__ void k_mser_union(int L, int W, int H, const uint8_t* __restrict__ le
   for (uint32_t base = beg + warp * 32; base < end; base += nwarps * 32) {
     const uint32_t k = base + lane;
     uint32_t hk[4]; int cnt = 0;
-    if (k < end) {
-      const uint32_t p = order[k];
-      const int y = p / W, x = p - y * W;
+    const bool act = k < end;
+    uint32_t p = 0, r[4]; bool valid[4] = {false, false, false, false};
+    if (act) {
+      p = order[k];
+      const int yy = p / W, x = p - yy * W, y = yy >= H ? yy - H : yy;
+      uint32_t q[4] = {p - W, p - 1, p + 1, p + W};
+      valid[0] = y > 0; valid[1] = x > 0; valid[2] = x < W - 1; valid[3] = y < H - 1;
+      int lq[4];
+#pragma unroll
+      for (int d = 0; d < 4; d++) lq[d] = valid[d] ? (int)lev[q[d]] : 256;
       uint32_t e = 0;
 #pragma unroll
-      for (int d = 0; d < 4; d++) {
-        uint32_t q;
-        if (d == 0) { if (y == 0) continue; q = p - W; }
-        else if (d == 1) { if (x == 0) continue; q = p - 1; }
-        else if (d == 2) { if (x == W - 1) continue; q = p + 1; }
-        else { if (y == H - 1) continue; q = p + W; }
-        const int lq = lev[q];
-        if (lq < L || (lq == L && q < p)) {
-          e++;
-          const uint32_t h = uf_unite(zpar, lev, p, q);
-          if (h != NONE) hk[cnt++] = h;
+      for (int d = 0; d < 4; d++) { valid[d] = lq[d] < L || (lq[d] == L && q[d] < p); e += valid[d] ? 1u : 0u; r[d] = q[d]; }
+      nedge[p] = e;
+      // the (up to) four root searches advance together: independent loads in flight instead of four serial chains
+      bool moving = true;
+      while (moving) {
+        uint32_t nx[4];
+#pragma unroll
+        for (int d = 0; d < 4; d++) nx[d] = valid[d] ? __ldca(zpar + r[d]) : r[d];
+        moving = false;
+#pragma unroll
+        for (int d = 0; d < 4; d++) if (nx[d] != r[d]) { r[d] = nx[d]; moving = true; }
+      }
+#pragma unroll
+      for (int d = 0; d < 4; d++) if (valid[d] && r[d] != q[d]) __stcg(zpar + q[d], r[d]);   // compress the start of the path
+      if (valid[1] && valid[0] && r[1] == r[0]) valid[1] = false;
+      if (valid[2] && ((valid[0] && r[2] == r[0]) || (valid[1] && r[2] == r[1]))) valid[2] = false;
+      if (valid[3] && ((valid[0] && r[3] == r[0]) || (valid[1] && r[3] == r[1]) || (valid[2] && r[3] == r[2]))) valid[3] = false;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      bool pend = act && valid[d];
+      uint32_t ra = 0, rb = 0;
+      if (pend) { ra = uf_find<false>(zpar, p); rb = r[d]; }
+      for (;;) {
+        if (pend) {
+          if (ra == rb) pend = false;
+          else if (key_less(lev, rb, ra)) { const uint32_t t = ra; ra = rb; rb = t; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pend);
+        if (!m) break;
+        if (pend) {
+          const unsigned grp = __match_any_sync(m, ra);
+          const int leader = __ffs(grp) - 1;
+          uint32_t old = 0;
+          if (lane == leader) old = atomicCAS(zpar + ra, ra, rb);
+          old = __shfl_sync(grp, old, leader);
+          const uint32_t rb_lead = __shfl_sync(grp, rb, leader);
+          if (old == ra) {                       // ra now hangs under the leader's rb
+            if (lane == leader) { hk[cnt++] = ra; pend = false; }
+            else ra = uf_find<false>(zpar, rb_lead);
+          } else ra = uf_find<false>(zpar, old);  // somebody else hooked ra first: go on from its true parent
         }
       }
-      nedge[p] = e;
     }
     __syncwarp();
     int incl = cnt;
@@ -155,10 +217,8 @@ __global__ void k_mser_union(int L, int W, int H, const uint8_t* __restrict__ le
 }
 // Every element hooked during level L now learns its canonical parent (the representative of the level-L node) and hands
 // its totals over; lanes that share a representative combine first.
-__global__ void k_mser_final(int L, uint32_t* zpar, uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge,
-                             const uint32_t* __restrict__ hooked, MserCounters* C) {
-  const uint32_t beg = C->hook_off[L], end = C->hook_cnt;
-  if (blockIdx.x == 0 && threadIdx.x == 0) C->hook_off[L + 1] = end;
+__device__ __forceinline__ void mser_final_phase(int L, uint32_t* zpar, uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge,
+                             const uint32_t* __restrict__ hooked, MserCounters* C, uint32_t beg, uint32_t end) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t base = beg + warp * 32; base < end; base += nwarps * 32) {
@@ -167,7 +227,7 @@ __global__ void k_mser_final(int L, uint32_t* zpar, uint32_t* __restrict__ paren
     const unsigned mask = __ballot_sync(0xffffffffu, act);
     if (act) {
       const uint32_t x = hooked[i];
-      const uint32_t r = uf_find(zpar, x);
+      const uint32_t r = uf_find<false>(zpar, x);   // no hooking during this kernel: every pointer read is a valid ancestor
       parent[x] = r;
       const uint32_t a = area[x], e = nedge[x];
       const unsigned grp = __match_any_sync(mask, r);
@@ -176,15 +236,34 @@ __global__ void k_mser_final(int L, uint32_t* zpar, uint32_t* __restrict__ paren
     }
   }
 }
-__global__ void k_mser_root(uint32_t* zpar, MserCounters* C) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { C->root = uf_find(zpar, 0); C->hook_off[257] = C->hook_cnt; }
+// The whole tree in ONE cooperative launch: levels in order, a grid barrier between the hooking phase and the hand-over
+// phase of every non-empty level (two launches per level would cost more than the levels themselves).
+__global__ void __launch_bounds__(256) k_mser_tree(int W, int H, const uint8_t* __restrict__ lev, const uint32_t* __restrict__ order, uint32_t* zpar,
+                                                   uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge, uint32_t* __restrict__ hooked, MserCounters* C,
+                                                   unsigned long long* dbg /* optional: 3 x 256 phase time stamps (ns) */) {
+  cg::grid_group grid = cg::this_grid();
+  uint32_t hook_beg = 0;
+  for (int L = 0; L < 256; L++) {
+    if (C->lvl_off[L] == C->lvl_off[L + 1]) { if (blockIdx.x == 0 && threadIdx.x == 0) C->hook_off[L + 1] = hook_beg; continue; }
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L] = t; }
+    mser_union_phase(L, W, H, lev, order, zpar, nedge, hooked, C);
+    grid.sync();
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L + 1] = t; }
+    const uint32_t hook_end = *(volatile uint32_t*)&C->hook_cnt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) C->hook_off[L + 1] = hook_end;
+    mser_final_phase(L, zpar, parent, area, nedge, hooked, C, hook_beg, hook_end);
+    hook_beg = hook_end;
+    grid.sync();
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L + 2] = t; }
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) { C->root[0] = uf_find<true>(zpar, 0); C->root[1] = uf_find<true>(zpar, (uint32_t)W * H); C->hook_off[257] = hook_beg; }
 }
 
 // ---- 3. survivors -------------------------------------------------------------------------------------------------------
-struct TreeDev {  // Tree with the root read from the counters block
-  int W, H; const uint8_t* lev; const uint32_t* parent; const uint32_t* area; const uint32_t* nedge; const MserCounters* C; int track_size;
+struct TreeDev {
+  int W, H; const uint8_t* lev; const uint32_t* parent; const uint32_t* area; const uint32_t* nedge; int track_size;
   __device__ __forceinline__ Tree get() const {
-    Tree t; t.W = W; t.H = H; t.lev = lev; t.parent = parent; t.area = area; t.nedge = nedge; t.root = C->root; t.track_size = track_size;
+    Tree t; t.W = W; t.H = H; t.lev = lev; t.parent = parent; t.area = area; t.nedge = nedge; t.track_size = track_size;
     return t;
   }
 };
@@ -192,7 +271,7 @@ struct TreeDev {  // Tree with the root read from the counters block
 __global__ void k_mser_best(TreeDev td, uint32_t N, u64* __restrict__ best) {
   const Tree t = td.get();
   for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < N; x += gridDim.x * blockDim.x) {
-    if (x == t.root || !is_rep(t, x) || !tracked(t, x)) continue;
+    if (is_root(t, x) || !is_rep(t, x) || !tracked(t, x)) continue;
     atomicMax(best + t.parent[x], ((u64)t.area[x] << 32) | (u64)(~x));
   }
 }
@@ -200,7 +279,7 @@ __global__ void k_mser_best(TreeDev td, uint32_t N, u64* __restrict__ best) {
 __global__ void k_mser_ties(TreeDev td, uint32_t N, const u64* __restrict__ best, uint8_t* __restrict__ flag) {
   const Tree t = td.get();
   for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < N; x += gridDim.x * blockDim.x) {
-    if (x == t.root || !is_rep(t, x) || !tracked(t, x)) continue;
+    if (is_root(t, x) || !is_rep(t, x) || !tracked(t, x)) continue;
     const u64 b = best[t.parent[x]];
     if ((uint32_t)(b >> 32) == t.area[x] && (uint32_t)(~b) != x) flag[t.parent[x]] = 2;
   }
@@ -271,7 +350,7 @@ __global__ void k_mser_regions_a(TreeDev td, const uint32_t* __restrict__ emu_no
 #define MSER_RB_THREADS 32
 #define MSER_MAX_T 128
 __global__ void __launch_bounds__(MSER_RB_THREADS) k_mser_regions_b(TreeDev td, const LongRegion* __restrict__ regs, uint32_t n, const uint32_t* __restrict__ surv,
-                                 const uint32_t* __restrict__ birth, double min_margin, int min_size, int max_size, uint32_t* slot_of_node,
+                                 const uint32_t* __restrict__ birth, uint32_t Nimg, double min_margin, int min_size, int max_size, uint32_t* slot_of_node,
                                  uint32_t* __restrict__ node_of_slot, SelRec* __restrict__ sel, uint32_t cap, MserCounters* C) {
   extern __shared__ int sm_hist[];  // cA[256][32], cB[256][32]
   const uint32_t i = blockIdx.x * MSER_RB_THREADS + threadIdx.x;
@@ -295,7 +374,7 @@ __global__ void __launch_bounds__(MSER_RB_THREADS) k_mser_regions_b(TreeDev td, 
     atomicMin(slot_of_node + node, o);
     const uint32_t slot = o;
     SelRec e;
-    e.key = ((u64)minI << 40) | ((u64)birth[r.v0] << 8) | (u64)k;
+    e.key = ((u64)(r.v0 >= Nimg ? 1 : 0) << 48) | ((u64)minI << 40) | ((u64)birth[r.v0] << 8) | (u64)k;
     e.node = node; e.slot = slot; e.minI = minI; e.maxI = r.maxI; e.thresh = T[k].thresh; e.margin = T[k].margin;
     e.area = cA[T[k].thresh * MSER_RB_THREADS]; e.border = cB[T[k].thresh * MSER_RB_THREADS];
     sel[o] = e;
@@ -308,24 +387,28 @@ __global__ void k_mser_selkeys(const SelRec* __restrict__ sel, uint32_t n, u64* 
 
 // ---- 5. selected components -> row runs ------------------------------------------------------------------------------------
 // sa[x] = slot of the nearest selected node on the path from x to the root (x included); levels from the top down.
-__global__ void k_mser_down_init(uint32_t* __restrict__ sa, const uint32_t* __restrict__ slot_of_node, const MserCounters* C) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) sa[C->root] = slot_of_node[C->root];
-}
-__global__ void k_mser_down(int L, const uint32_t* __restrict__ parent, const uint32_t* __restrict__ hooked, const uint32_t* __restrict__ slot_of_node,
-                            uint32_t* __restrict__ sa, const MserCounters* C) {
-  const uint32_t beg = C->hook_off[L], end = C->hook_off[L + 1];
-  for (uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
-    const uint32_t x = hooked[i];
-    const uint32_t s = slot_of_node[x];
-    sa[x] = (s != NONE) ? s : sa[parent[x]];
+__global__ void __launch_bounds__(256) k_mser_down(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ hooked, const uint32_t* __restrict__ slot_of_node,
+                                                   uint32_t* sa, const MserCounters* C) {
+  cg::grid_group grid = cg::this_grid();
+  if (threadIdx.x == 0 && blockIdx.x == 0) { sa[C->root[0]] = slot_of_node[C->root[0]]; sa[C->root[1]] = slot_of_node[C->root[1]]; }
+  grid.sync();
+  for (int L = 255; L >= 0; L--) {
+    const uint32_t beg = C->hook_off[L], end = C->hook_off[L + 1];
+    if (beg == end) continue;
+    for (uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+      const uint32_t x = hooked[i];
+      const uint32_t s = slot_of_node[x];
+      sa[x] = (s != NONE) ? s : __ldcg(sa + parent[x]);   // written by another block in an earlier phase
+    }
+    grid.sync();
   }
 }
 __global__ void k_mser_upsel(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ node_of_slot, uint32_t n_slots,
-                             const uint32_t* __restrict__ sa, uint32_t* __restrict__ up_sel, const MserCounters* C) {
+                             const uint32_t* __restrict__ sa, uint32_t* __restrict__ up_sel) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
   const uint32_t node = node_of_slot[s];
-  up_sel[s] = (node == C->root) ? NONE : sa[parent[node]];
+  up_sel[s] = (parent[node] == node) ? NONE : sa[parent[node]];
 }
 __device__ __forceinline__ bool in_slot(const uint32_t* sa, const uint32_t* up_sel, uint32_t q, uint32_t s) {
   uint32_t t = sa[q];
@@ -344,11 +427,11 @@ __device__ __forceinline__ void agg_append(u64* list, uint32_t* counter, uint32_
 // first / last pixel of every row run of every selected component: key = slot << 32 | line << 16 | column
 __global__ void k_mser_runs(int W, int H, const uint32_t* __restrict__ sa, const uint32_t* __restrict__ up_sel, u64* __restrict__ starts,
                             u64* __restrict__ ends, uint32_t cap, MserCounters* C) {
-  const uint32_t N = (uint32_t)W * H;
-  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+  const uint32_t N2 = 2u * (uint32_t)W * H;
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N2; p += gridDim.x * blockDim.x) {
     uint32_t s = sa[p];
     if (s == NONE) continue;
-    const int y = p / W, x = p - y * W;
+    const int yy = p / W, x = p - yy * W, y = yy >= H ? yy - H : yy;
     while (s != NONE) {
       const bool l = x > 0 && in_slot(sa, up_sel, p - 1, s);
       const bool r = x < W - 1 && in_slot(sa, up_sel, p + 1, s);
@@ -374,10 +457,11 @@ __global__ void k_mser_moments(const u64* __restrict__ starts, const u64* __rest
 }
 // AffineKeypoint as DetectMSERs fills it (extrema.cpp:409-433) [+ DetectAffineRegions' post-step, synth-detection.hpp:110-124]
 __global__ void k_mser_keys(const SelRec* __restrict__ sel, const uint32_t* __restrict__ order, uint32_t n, const SlotMoments* __restrict__ mom,
-                            const uint32_t* __restrict__ slot_of_node, int pol, int as_regions, KeyOut* __restrict__ out, double* __restrict__ table) {
+                            const uint32_t* __restrict__ slot_of_node, uint32_t Nimg, int as_regions, KeyOut* __restrict__ out, double* __restrict__ table) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const SelRec e = sel[order[i]];
+  const int pol = e.node >= Nimg ? 1 : 0;
   const SlotMoments sm = mom[slot_of_node[e.node]];
   double A[4];
   ellipse_to_A(sm.m.sxx, sm.m.sxy, sm.m.syy, A);
@@ -418,13 +502,14 @@ MserBufs* mser_bufs(mb2_ctx* ctx) {
     if (hc->cap_overflow) { ctx->set_error("mser: internal list capacity exceeded"); return MB2_ERR_CAPACITY; }               \
   } while (0)
 
-// One polarity.  Appends the keys (reference order) to d_out[*n_out ...]; table (optional) receives 13 doubles per region.
-int mser_polarity(mb2_ctx* ctx, const ImgView& img, int pol, const mb2_mser_params& par, double min_margin, int as_regions, KeyOut* d_out,
-                  int out_cap, int* n_out, double* d_table) {
+// Both polarities at once (stacked, see the header comment).  Writes the keys (MSER+ first, reference order inside each) to
+// d_out; table (optional) receives 13 doubles per region.
+int mser_both(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, double min_margin, int as_regions, KeyOut* d_out,
+              int out_cap, int* n_out, double* d_table) {
   MserBufs& B = *mser_bufs(ctx);
   cudaStream_t st = ctx->stream;
   const int W = img.cols, H = img.rows;
-  const uint32_t N = (uint32_t)W * H;
+  const uint32_t Nimg = (uint32_t)W * H, N = 2 * Nimg;
   const int G = ctx->num_sms * 8;
   const int track_size = std::min(10000, par.min_size);
   const int max_size = (int)((double)W * (double)H * par.max_area);
@@ -444,9 +529,9 @@ int mser_polarity(mb2_ctx* ctx, const ImgView& img, int pol, const mb2_mser_para
   uint32_t *order = B.order.as<uint32_t>(), *order_in = B.order_in.as<uint32_t>(), *hooked = B.hooked.as<uint32_t>();
   uint32_t *surv = B.surv.as<uint32_t>(), *birth = B.birth.as<uint32_t>(), *slot_of_node = B.slot_of_node.as<uint32_t>(), *sa = B.sa.as<uint32_t>();
 
-  // 1. u8 image, histogram, (level, raster) order
+  // 1. u8 images, histogram, (level, raster) order
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(dC, 0, sizeof(MserCounters), st));
-  MB2_LAUNCH(ctx, k_mser_prep, grid_for(N, 256, G), 256, 0, img.p, img.pitch, W, H, pol, lev, zpar, parent, area, order_in, dC);
+  MB2_LAUNCH(ctx, k_mser_prep, grid_for(Nimg, 256, G), 256, 0, img.p, img.pitch, W, H, lev, zpar, parent, area, order_in, dC);
   MB2_LAUNCH(ctx, k_mser_offsets, 1, 32, 0, dC);
   {
     size_t tmp = 0;
@@ -455,14 +540,35 @@ int mser_polarity(mb2_ctx* ctx, const ImgView& img, int pol, const mb2_mser_para
     cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, lev, B.keys8.as<uint8_t>(), order_in, order, (int)N, 0, 8, st);
     ctx->launches += 3;
   }
-  // 2. component tree
-  for (int L = 0; L < 256; L++) {
-    MB2_LAUNCH(ctx, k_mser_union, G, 256, 0, L, W, H, lev, order, zpar, nedge, hooked, dC);
-    MB2_LAUNCH(ctx, k_mser_final, G, 256, 0, L, zpar, parent, area, nedge, hooked, dC);
+  // 2. component trees
+  {
+    int occ = 0;
+    MB2_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mser_tree, 256, 0));
+    const int Gc = ctx->num_sms * std::max(1, std::min(occ, 4));   // co-resident by construction
+    int Wv = W, Hv = H;
+    static const bool level_prof = getenv("MB2_MSER_LEVEL_PROF") != nullptr;   // diagnostics: per-level phase times to stderr
+    unsigned long long* dbg = nullptr;
+    if (level_prof) { MB2_CUDA_CHECK(ctx, B.table.reserve(3 * 256 * 8)); dbg = B.table.as<unsigned long long>(); cudaMemsetAsync(dbg, 0, 3 * 256 * 8, st); }
+    void* args[] = {&Wv, &Hv, &lev, &order, &zpar, &parent, &area, &nedge, &hooked, &dC, &dbg};
+    mb2_ctx::ProfRec pr{"k_mser_tree", nullptr, nullptr};
+    if (ctx->profiling) { cudaEventCreate(&pr.a); cudaEventCreate(&pr.b); cudaEventRecord(pr.a, st); }
+    MB2_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_mser_tree, dim3(Gc), dim3(256), args, 0, st));
+    if (ctx->profiling) { cudaEventRecord(pr.b, st); ctx->prof.push_back(pr); }
+    ctx->launches++;
+    if (level_prof) {
+      std::vector<unsigned long long> t(3 * 256); std::vector<uint32_t> hist(256);
+      cudaMemcpyAsync(t.data(), dbg, 3 * 256 * 8, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(hist.data(), &dC->hist[0], 256 * 4, cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      double tu = 0, tf = 0;
+      for (int L = 0; L < 256; L++) if (t[3 * L]) { tu += (t[3 * L + 1] - t[3 * L]) * 1e-3; tf += (t[3 * L + 2] - t[3 * L + 1]) * 1e-3; }
+      fprintf(stderr, "[mser] grid %d x 256: union %.0f us, final %.0f us; per level (pixels: union us / final us):", Gc, tu, tf);
+      for (int L = 0; L < 256; L++) if (t[3 * L]) fprintf(stderr, " L%d(%u: %.0f/%.0f)", L, hist[L], (t[3 * L + 1] - t[3 * L]) * 1e-3, (t[3 * L + 2] - t[3 * L + 1]) * 1e-3);
+      fprintf(stderr, "\n");
+    }
   }
-  MB2_LAUNCH(ctx, k_mser_root, 1, 32, 0, zpar, dC);
   // 3. survivors
-  TreeDev td{W, H, lev, parent, area, nedge, dC, track_size};
+  TreeDev td{W, H, lev, parent, area, nedge, track_size};
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(B.best.p, 0, (size_t)N * 8, st));
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(B.flag.p, 0, N, st));
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(surv, 0xff, (size_t)N * 4, st));
@@ -510,32 +616,42 @@ int mser_polarity(mb2_ctx* ctx, const ImgView& img, int pol, const mb2_mser_para
       const size_t smem = (size_t)2 * 256 * MSER_RB_THREADS * sizeof(int);
       MB2_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_mser_regions_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       MB2_LAUNCH(ctx, k_mser_regions_b, (n_long + MSER_RB_THREADS - 1) / MSER_RB_THREADS, MSER_RB_THREADS, smem, td, B.longr.as<LongRegion>(), n_long, surv,
-                 birth, min_margin, par.min_size, max_size, slot_of_node, B.node_of_slot.as<uint32_t>(), B.sel.as<SelRec>(), sel_cap, dC);
+                 birth, Nimg, min_margin, par.min_size, max_size, slot_of_node, B.node_of_slot.as<uint32_t>(), B.sel.as<SelRec>(), sel_cap, dC);
       MSER_SYNC_COUNTERS();
       if (hc->thr_overflow) { ctx->set_error("mser: more than 128 stability thresholds in one region"); return MB2_ERR_CAPACITY; }
       n_sel = (int)hc->n_sel; n_slots = n_sel;
     }
   }
+  *n_out = n_sel;
   if (n_sel == 0) return MB2_OK;
-  if (*n_out + n_sel > out_cap) { ctx->set_error("mser: output capacity too small"); *n_out += n_sel; return MB2_ERR_CAPACITY; }
-  // reference list order
+  if (n_sel > out_cap) { ctx->set_error("mser: output capacity too small"); return MB2_ERR_CAPACITY; }
+  // reference list order (polarity, birth level, promotion time, threshold rank)
   MB2_CUDA_CHECK(ctx, B.selkey_a.reserve((size_t)n_sel * 8)); MB2_CUDA_CHECK(ctx, B.selkey_b.reserve((size_t)n_sel * 8));
   MB2_CUDA_CHECK(ctx, B.selidx_a.reserve((size_t)n_sel * 4)); MB2_CUDA_CHECK(ctx, B.selidx_b.reserve((size_t)n_sel * 4));
   MB2_LAUNCH(ctx, k_mser_selkeys, (n_sel + 255) / 256, 256, 0, B.sel.as<SelRec>(), (uint32_t)n_sel, B.selkey_a.as<u64>(), B.selidx_a.as<uint32_t>());
   {
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 48, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 49, st);
     MB2_CUDA_CHECK(ctx, B.cub_tmp.reserve(tmp));
-    cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 48, st);
+    cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 49, st);
     ctx->launches += 4;
   }
   // 5. runs of the selected components
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(sa, 0xff, (size_t)N * 4, st));
   MB2_CUDA_CHECK(ctx, B.up_sel.reserve((size_t)n_slots * 4));
-  MB2_LAUNCH(ctx, k_mser_down_init, 1, 32, 0, sa, slot_of_node, dC);
-  for (int L = 255; L >= 0; L--) MB2_LAUNCH(ctx, k_mser_down, G, 256, 0, L, parent, hooked, slot_of_node, sa, dC);
-  MB2_LAUNCH(ctx, k_mser_upsel, (n_slots + 255) / 256, 256, 0, parent, B.node_of_slot.as<uint32_t>(), (uint32_t)n_slots, sa, B.up_sel.as<uint32_t>(), dC);
-  const uint32_t run_cap = 2 * N + 1024;
+  {
+    int occ = 0;
+    MB2_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mser_down, 256, 0));
+    const int Gc = ctx->num_sms * std::max(1, std::min(occ, 4));
+    void* args[] = {&parent, &hooked, &slot_of_node, &sa, &dC};
+    mb2_ctx::ProfRec pr{"k_mser_down", nullptr, nullptr};
+    if (ctx->profiling) { cudaEventCreate(&pr.a); cudaEventCreate(&pr.b); cudaEventRecord(pr.a, st); }
+    MB2_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_mser_down, dim3(Gc), dim3(256), args, 0, st));
+    if (ctx->profiling) { cudaEventRecord(pr.b, st); ctx->prof.push_back(pr); }
+    ctx->launches++;
+  }
+  MB2_LAUNCH(ctx, k_mser_upsel, (n_slots + 255) / 256, 256, 0, parent, B.node_of_slot.as<uint32_t>(), (uint32_t)n_slots, sa, B.up_sel.as<uint32_t>());
+  const uint32_t run_cap = N + 1024;
   MB2_CUDA_CHECK(ctx, B.ev_a.reserve((size_t)run_cap * 8)); MB2_CUDA_CHECK(ctx, B.ev_b.reserve((size_t)run_cap * 8));
   MB2_LAUNCH(ctx, k_mser_runs, grid_for(N, 256, G), 256, 0, W, H, sa, B.up_sel.as<uint32_t>(), B.ev_a.as<u64>(), B.ev_b.as<u64>(), run_cap, dC);
   MSER_SYNC_COUNTERS();
@@ -554,9 +670,8 @@ int mser_polarity(mb2_ctx* ctx, const ImgView& img, int pol, const mb2_mser_para
   // 6. moments and keys
   MB2_CUDA_CHECK(ctx, B.mom.reserve((size_t)n_slots * sizeof(SlotMoments)));
   MB2_LAUNCH(ctx, k_mser_moments, (n_slots + 63) / 64, 64, 0, B.ev_c.as<u64>(), B.ev_d.as<u64>(), n_runs, (uint32_t)n_slots, B.mom.as<SlotMoments>());
-  MB2_LAUNCH(ctx, k_mser_keys, (n_sel + 127) / 128, 128, 0, B.sel.as<SelRec>(), B.selidx_b.as<uint32_t>(), (uint32_t)n_sel, B.mom.as<SlotMoments>(), slot_of_node, pol,
-             as_regions, d_out + *n_out, d_table ? d_table + (size_t)*n_out * 13 : nullptr);
-  *n_out += n_sel;
+  MB2_LAUNCH(ctx, k_mser_keys, (n_sel + 127) / 128, 128, 0, B.sel.as<SelRec>(), B.selidx_b.as<uint32_t>(), (uint32_t)n_sel, B.mom.as<SlotMoments>(), slot_of_node,
+             Nimg, as_regions, d_out, d_table);
   return MB2_OK;
 }
 
@@ -575,14 +690,13 @@ int mb2_mser_core(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, 
   *n_out = 0;
   if (par.min_size < 2) { ctx->set_error("mser: min_size < 2 is not supported"); return MB2_ERR_UNSUPPORTED; }
   if (par.relative) { ctx->set_error("mser: relative margins are not supported"); return MB2_ERR_UNSUPPORTED; }
-  if (img.cols > 65535 || img.rows > 65535 || (long long)img.cols * img.rows >= (1LL << 31)) { ctx->set_error("mser: image too large"); return MB2_ERR_ARG; }
+  if (img.cols > 65535 || img.rows > 65535 || (long long)img.cols * img.rows >= (1LL << 30)) { ctx->set_error("mser: image too large"); return MB2_ERR_ARG; }
   const double min_margin = par.mode != 0 ? 1.0 : par.min_margin;  // extrema.cpp:294-299
   const int cap = capacity > 0 ? capacity : (int)std::min<long long>((long long)img.cols * img.rows / 16 + 4096, 4000000);
   MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)cap * sizeof(KeyOut)));
   int rc;
   const bool sort_on_host = par.mode != 0;
-  for (int pol = 0; pol < 2; pol++)
-    if ((rc = mser_polarity(ctx, img, pol, par, min_margin, sort_on_host ? 0 : as_regions, ctx->kp_b.as<KeyOut>(), cap, n_out, d_table_out))) return rc;
+  if ((rc = mser_both(ctx, img, par, min_margin, sort_on_host ? 0 : as_regions, ctx->kp_b.as<KeyOut>(), cap, n_out, d_table_out))) return rc;
   if (sort_on_host && *n_out > 0) {
     // prepareKeysForExport (extrema.cpp:31-90): the reference's own (unstable) std::sort decides the order of equal margins,
     // so this step runs through the same library routine on the host.

@@ -12,7 +12,7 @@
 //
 // Tree representation (built by mser.cu on the GPU, by tests/native/mser_tree_cpu.cpp on the host for the logic
 // tests): one node per (component, level) that owns at least one pixel of that level; the node is named by its
-// representative pixel `rep` = the pixel of that level with the largest raster index in the component;
+// representative pixel `rep`, some pixel of that level in the component (which one does not matter);
 //   parent[x] = rep of x's node if x is not a rep, else rep of the parent node (root: itself);
 //   area[rep] = pixels in the component; nedge[rep] = 4-adjacent pixel pairs inside the component, so that the
 //   reference's border count (+4 - 2*labelled neighbours per pixel, :150-168) is 4*area - 2*nedge.
@@ -32,17 +32,20 @@ namespace mser_logic {
 
 static const uint32_t NONE = 0xffffffffu;
 
+// Several images of the same size may be stacked into one pixel index space (mser.cu stacks MSER+ on top of MSER-, the
+// inverted image): pixel p lies in image p / (W*H), and rows of different images are never neighbours.  Every image has
+// its own root (the only pixels with parent[x] == x).
 struct Tree {
-  int W, H;
-  const uint8_t* lev;      // intensity of this polarity (255 - I for MSER-)
+  int W, H;                // size of ONE image
+  const uint8_t* lev;      // intensity (255 - I in the MSER- image)
   const uint32_t* parent;
   const uint32_t* area;
   const uint32_t* nedge;
-  uint32_t root;
   int track_size;          // min(10000, min_size): promotion threshold (PrepareThresholds, getExtrema.cpp:372-381)
 };
 
-MB2_HD bool is_rep(const Tree& t, uint32_t x) { return x == t.root || t.lev[t.parent[x]] > t.lev[x]; }
+MB2_HD bool is_root(const Tree& t, uint32_t x) { return t.parent[x] == x; }
+MB2_HD bool is_rep(const Tree& t, uint32_t x) { const uint32_t p = t.parent[x]; return p == x || t.lev[p] > t.lev[x]; }
 MB2_HD uint32_t node_of(const Tree& t, uint32_t x) { return is_rep(t, x) ? x : t.parent[x]; }
 MB2_HD int border_of(const Tree& t, uint32_t rep) { return (int)(4u * t.area[rep] - 2u * t.nedge[rep]); }
 MB2_HD bool tracked(const Tree& t, uint32_t rep) { return (int)t.area[rep] >= t.track_size; }
@@ -90,13 +93,13 @@ MB2_HD void emu_add_pixel(const Tree& t, EmuScratch& s, uint32_t root, uint32_t 
   }
 }
 
-// own: the node's own pixels in raster order (the rep is the last one), as the low 32 bits of sorted (node<<32 | pixel) keys
+// own: the node's own pixels in raster order (the rep is one of them), as the low 32 bits of sorted (node<<32 | pixel) keys
 MB2_HD EmuResult emulate_node(const Tree& t, EmuScratch& s, uint32_t v, const unsigned long long* own, int n_own) {
   EmuResult res; res.survivor = NONE; res.birth = NONE; res.overflow = 0;
   const int L = t.lev[v], W = t.W;
   for (int k = 0; k < n_own; k++) {
     const uint32_t p = (uint32_t)own[k];
-    const int x = (int)(p % (uint32_t)W), y = (int)(p / (uint32_t)W);
+    const int x = (int)(p % (uint32_t)W), y = (int)((p / (uint32_t)W) % (uint32_t)t.H);   // row inside its own image
     uint32_t lab[4]; int n = 0;
     for (int d = 0; d < 4; d++) {  // up, left, right, down
       uint32_t q;
@@ -148,7 +151,7 @@ MB2_HD EmuResult emulate_node(const Tree& t, EmuScratch& s, uint32_t v, const un
 MB2_HD int region_extent(const Tree& t, const uint32_t* surv, uint32_t v0, bool* at_root, uint32_t* last) {
   uint32_t u = v0;
   for (;;) {
-    if (u == t.root) { *at_root = true; *last = u; return t.lev[u]; }
+    if (is_root(t, u)) { *at_root = true; *last = u; return t.lev[u]; }
     const uint32_t p = t.parent[u];
     if (surv[p] != u) { *at_root = false; *last = u; return t.lev[p]; }
     u = p;
@@ -224,7 +227,7 @@ MB2_HD void region_histograms(const Tree& t, const uint32_t* surv, uint32_t v0, 
   for (;;) {
     const int a = (int)t.area[u], b = border_of(t, u);
     int next_lv; uint32_t nu = NONE;
-    if (u == t.root) next_lv = 256;
+    if (is_root(t, u)) next_lv = 256;
     else { const uint32_t p = t.parent[u]; if (surv[p] == u) { nu = p; next_lv = t.lev[p]; } else next_lv = 256; }
     const int hi = (next_lv < maximum_int + 1) ? next_lv : maximum_int + 1;
     for (int i = lv; i < hi; i++) { cA[i * stride] = a; cB[i * stride] = b; }
@@ -238,7 +241,7 @@ MB2_HD void region_histograms(const Tree& t, const uint32_t* surv, uint32_t v0, 
 MB2_HD uint32_t region_node_at(const Tree& t, const uint32_t* surv, uint32_t v0, int thresh) {
   uint32_t u = v0;
   for (;;) {
-    if (u == t.root) return u;
+    if (is_root(t, u)) return u;
     const uint32_t p = t.parent[u];
     if (surv[p] != u || (int)t.lev[p] > thresh) return u;
     u = p;

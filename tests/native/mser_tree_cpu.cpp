@@ -23,7 +23,7 @@ struct Build {
     while (zpar[x] != x) { zpar[x] = zpar[zpar[x]]; x = zpar[x]; }
     return x;
   }
-  bool less(uint32_t a, uint32_t b) const { return lev[a] < lev[b] || (lev[a] == lev[b] && a < b); }
+  bool less(uint32_t a, uint32_t b) const { return lev[a] < lev[b] || (lev[a] == lev[b] && a > b); }  // same hooking order as mser.cu
   void run() {
     N = W * H;
     zpar.resize(N); parent.resize(N); area.assign(N, 1); nedge.assign(N, 0);
@@ -72,13 +72,13 @@ extern "C" int mser_tree_regions(const float* img, int w, int h, double max_area
     Build b; b.W = w; b.H = h; b.lev.resize(N);
     for (int i = 0; i < N; i++) { uint8_t v = (unsigned char)img[i]; b.lev[i] = pol ? (uint8_t)(255 - v) : v; }
     b.run();
-    Tree t; t.W = w; t.H = h; t.lev = b.lev.data(); t.parent = b.parent.data(); t.area = b.area.data(); t.nedge = b.nedge.data(); t.root = b.root;
+    Tree t; t.W = w; t.H = h; t.lev = b.lev.data(); t.parent = b.parent.data(); t.area = b.area.data(); t.nedge = b.nedge.data();
     t.track_size = std::min(10000, min_size);
     const int max_size = (int)((double)w * (double)h * max_area);
     // survivors: largest tracked child; ties and births are replayed
     std::vector<uint32_t> surv(N, NONE), bestArea(N, 0), nbest(N, 0);
     for (int x = 0; x < N; x++) {
-      if ((uint32_t)x == t.root || !is_rep(t, x) || !tracked(t, x)) continue;
+      if (is_root(t, x) || !is_rep(t, x) || !tracked(t, x)) continue;
       const uint32_t v = t.parent[x];
       if (t.area[x] > bestArea[v]) { bestArea[v] = t.area[x]; surv[v] = x; nbest[v] = 1; }
       else if (t.area[x] == bestArea[v]) nbest[v]++;
@@ -132,7 +132,7 @@ extern "C" int mser_tree_regions(const float* img, int w, int h, double max_area
       std::vector<uint8_t> in(N, 0);
       for (int x = 0; x < N; x++) {
         uint32_t u = node_of(t, x);
-        while (u != e.node && u != t.root && t.lev[u] <= t.lev[e.node]) u = t.parent[u];
+        while (u != e.node && !is_root(t, u) && t.lev[u] <= t.lev[e.node]) u = t.parent[u];
         in[x] = (u == e.node);
       }
       for (int y = 0; y < h; y++)
