@@ -2,11 +2,12 @@
 """bench.py -- the BASELINE.json metric on this repo's hot path.
 
 Metric: image-pairs/sec (and matched-kpts/sec) on a synthetic 4096x3072 pair at ~30k keypoints per image
-(BASELINE.json configs[2], "C3"), one pair = both images through HessianAffine detection (Gaussian
-pyramid, Hessian response, 3x3x3 NMS, localisation, Baumberg) -> dominant orientation -> RootSIFT
-description, then exact FGINN matching (tcgen05), duplicate filtering and LO-RANSAC homography + LAF
-check -- one iteration of mods.cpp's loop with the identity view (MSER and synthesised views are not
-built yet: see DESIGN.md "scope").
+(BASELINE.json configs[2], "C3": MSER + HessAff, tensor-core NN, DEGENSAC-H), one pair = both images through
+HessianAffine detection (Gaussian pyramid, Hessian response, 3x3x3 NMS, localisation, Baumberg) AND MSER detection
+(component tree of both polarities, stability thresholds, region moments) -> dominant orientation -> RootSIFT
+description, then exact FGINN matching per detector (tcgen05), duplicate filtering and LO-RANSAC homography + LAF
+check over the union -- one iteration of mods.cpp's loop with the identity view of both detectors (synthesised
+views are not built yet: see DESIGN.md "scope").  --no-mser gives the HessianAffine-only variant.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size WxH]
 
@@ -113,6 +114,7 @@ def run_ours(args, rank, world, local_rank):
     pairs = make_pairs(w, h, N_PAIRS, seed0=1 + 1000 * rank)
     ctx = mb.Context(local_rank)
     cfg = mb.PairConfig.default()
+    cfg.use_mser = 0 if args.no_mser else 1
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     dev_pairs = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in pairs]
     pin_pairs = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
@@ -182,8 +184,11 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (pyramid/patches), f64 (SIFT sums, RANSAC), bf16->f32 tcgen05 (NN, exact on u8 descriptors)",
         "data": "synthetic (numpy PCG64 blob images + ground-truth homography warp, mods_b200/synth.py)",
-        "config": {"workload": "C3: %dx%d synthetic pair, HessianAffine(FixedTh 5.3333)+Baumberg+orientation+RootSIFT, identity view, "
-                               "FGINN 0.8 exact NN, duplicate filter 2px, LO-RANSAC-H 3px + LAF check; MSER not built yet" % (w, h),
+        "config": {"workload": "C3: %dx%d synthetic pair, HessianAffine(FixedTh 5.3333)+Baumberg and %s, orientation+RootSIFT, identity view, "
+                               "FGINN 0.8 exact NN per detector, duplicate filter 2px, LO-RANSAC-H 3px + LAF check"
+                               % (w, h, "HessianAffine only (--no-mser)" if args.no_mser else "MSER(min_margin 8, min_size 30, max_area 0.05)"),
+                   "mser_regions_per_image": float(np.mean([r.mser_regions1 + r.mser_regions2 for r in res_dev])) / 2,
+                   "mser_tentatives": float(np.mean([r.mser_tentatives for r in res_dev])),
                    "pairs_in_rotation": N_PAIRS, "l2": "inputs cycle through %d pairs (%.0f MB) and the per-image pyramid working set (~1.3 GB) exceeds the 126 MB L2"
                    % (N_PAIRS, N_PAIRS * 2 * w * h * 4 / 1e6),
                    "regions_per_image": regions, "tentatives": tent, "verified": verified, "parallelism": "pairs sharded over ranks, no collective",
@@ -203,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
         out.update(roofline_from_profile(prof, w, h, regions, peaks, steps=min(args.steps, N_PAIRS)))
     else:
         out["roofline"] = None
-    out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1) if not args.no_cpu_baseline else None
+    out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1, with_mser=not args.no_mser) if not args.no_cpu_baseline else None
     print(json.dumps(out))
 
 
@@ -224,6 +229,13 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps):
         rl = {"bound": "hbm", "kernel": name, "achieved": gb / 1e9 / avg_s if gb else None, "peak": peaks["hbm"], "unit": "GB/s",
               "frac": (gb / 1e9 / avg_s / peaks["hbm"]) if gb else None, "traffic": None,
               "note": "L2-gather / FP32-ALU kernel: algorithmic bytes = bilinear taps read + patch written (SURVEY 8d), peak = %s HBM copy" % peaks["src"]}
+    elif "k_mser_tree" in name:
+        # ~30 B/px per polarity (u8 read + sorted offset + label R/W + boundary pass); both polarities in one launch
+        gb = 30.0 * 2 * w * h
+        rl = {"bound": "hbm", "kernel": name, "achieved": gb / 1e9 / avg_s, "peak": peaks["hbm"], "unit": "GB/s", "frac": gb / 1e9 / avg_s / peaks["hbm"],
+              "traffic": None, "algorithmic_bytes": gb,
+              "note": "component tree of both polarities: 256 level-synchronous phases, each a chain of dependent reads -- latency bound, not bandwidth bound "
+                      "(DESIGN.md); peak = %s HBM copy" % peaks["src"]}
     elif "k_blur_hess" in name or "k_nms" in name:
         rl = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
     elif "k_nn_tc" in name:
@@ -247,24 +259,26 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps):
     return dict(roofline=rl, kernels=kernels, **extra)
 
 
-def cpu_baseline(pair, cfg_seed=1, query_sample=600):
+def cpu_baseline(pair, cfg_seed=1, query_sample=600, with_mser=True):
     """The CPU oracle (port of the reference's algorithm, 1 thread) on a bounded sample of the same pair."""
     from oracle.pyoracle import Oracle
     O = Oracle()
     A, B = pair
-    t0 = time.perf_counter(); va = O.view_pipeline(A); t_view = time.perf_counter() - t0
-    vb = O.view_pipeline(B[: B.shape[0] // 4])  # trains for the matching sample (quarter image, not timed into t_view)
-    nq = min(query_sample, len(va[0]))
-    t0 = time.perf_counter()
-    O.match_fginn(va[2][:nq], vb[2], np.ascontiguousarray(vb[1][:, :2]))
-    t_match_sample = time.perf_counter() - t0
-    # one pair = 2 views + matching all queries against all trains (linear in queries x trains)
-    scale = (len(va[0]) / max(1, nq)) * (len(va[0]) / max(1, len(vb[0])))
-    t_pair = 2 * t_view + t_match_sample * scale
+    t_pair, notes = 0.0, []
+    for det, name in ((0, "HessianAffine"),) + (((3, "MSER"),) if with_mser else ()):
+        t0 = time.perf_counter(); va = O.view_pipeline(A, detector=det); t_view = time.perf_counter() - t0
+        vb = O.view_pipeline(B[: B.shape[0] // 4], detector=det)  # trains for the matching sample (quarter image, not timed into t_view)
+        nq = min(query_sample, len(va[0]))
+        t0 = time.perf_counter()
+        O.match_fginn(va[2][:nq], vb[2], np.ascontiguousarray(vb[1][:, :2]))
+        t_match_sample = time.perf_counter() - t0
+        # one pair = 2 views + matching all queries against all trains (linear in queries x trains)
+        scale = (len(va[0]) / max(1, nq)) * (len(va[0]) / max(1, len(vb[0])))
+        t_pair += 2 * t_view + t_match_sample * scale
+        notes.append("%s: view pipeline on one full image %.1f s (%d regions, x2 per pair) + exact FGINN of %d queries vs %d trains %.1f s "
+                     "extrapolated linearly to %d x %d" % (name, t_view, len(va[0]), nq, len(vb[0]), t_match_sample, len(va[0]), len(va[0])))
     return {"value": 1.0 / t_pair, "unit": "pairs/s", "cores": 1, "kind": "port",
-            "sample": "oracle view pipeline on one full 4096x3072 image (%.1f s, %d regions, x2 per pair) + exact FGINN of %d queries vs %d trains "
-                      "(%.1f s) extrapolated linearly to %d x %d; duplicate filter / RANSAC not included (small)"
-                      % (t_view, len(va[0]), nq, len(vb[0]), t_match_sample, len(va[0]), len(va[0]))}
+            "sample": "oracle (1 thread) on the same 4096x3072 pair; " + "; ".join(notes) + "; duplicate filter / RANSAC not included (small)"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -286,19 +300,24 @@ def run_reference(args, rank, world):
     a = np.ascontiguousarray(A[h // 4: h // 4 + ch, w // 4: w // 4 + cw]); b = np.ascontiguousarray(B[h // 4: h // 4 + ch, w // 4: w // 4 + cw])
     steps = max(1, min(args.steps, 3))
 
+    dets = (0,) if args.no_mser else (0, 3)
+
     def one_step():
-        out = [None, None]
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=lambda i=i, im=im: out.__setitem__(i, L.view_pipeline(im))) for i, im in enumerate((a, b))]
-        [t.start() for t in th]; [t.join() for t in th]
-        t_views = time.perf_counter() - t0
-        va, vb = out
-        nq = min(500, len(va[0]))
-        t0 = time.perf_counter()
-        O.match_fginn(va[2][:nq], vb[2], np.ascontiguousarray(vb[1][:, :2]))
-        t_match = time.perf_counter() - t0
-        # full-size pair: 4x the pixels per view; matching is (4 n1) x (4 n2) instead of nq x n2
-        return 4.0 * t_views + t_match * (len(va[0]) / max(1, nq)) * 16.0
+        t_total = 0.0
+        for det in dets:
+            out = [None, None]
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=lambda i=i, im=im: out.__setitem__(i, L.view_pipeline(im, detector=det))) for i, im in enumerate((a, b))]
+            [t.start() for t in th]; [t.join() for t in th]
+            t_views = time.perf_counter() - t0
+            va, vb = out
+            nq = min(500, len(va[0]))
+            t0 = time.perf_counter()
+            O.match_fginn(va[2][:nq], vb[2], np.ascontiguousarray(vb[1][:, :2]))
+            t_match = time.perf_counter() - t0
+            # full-size pair: 4x the pixels per view; matching is (4 n1) x (4 n2) instead of nq x n2
+            t_total += 4.0 * t_views + t_match * (len(va[0]) / max(1, nq)) * 16.0
+        return t_total
 
     for _ in range(min(args.warmup, 1)):
         one_step()
@@ -310,10 +329,11 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": "image-pairs/sec (4096x3072 synthetic pair, ~30k HessAff kpts/image)", "value": v, "unit": "pairs/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_pair, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)", "data": "synthetic (same generator and seeds as the GPU arm)",
-           "config": {"workload": "C3: %dx%d synthetic pair (reference CPU path)" % (w, h)},
+           "config": {"workload": "C3: %dx%d synthetic pair (reference CPU path, %s)" % (w, h, "HessianAffine only" if args.no_mser else "HessianAffine + MSER")},
            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": 2, "kind": "reference" if use_ref else "port",
-                            "sample": "centre %dx%d crop of the pair (1/4 area): %s view pipeline for both images on 2 threads, scaled x4; exact FGINN "
-                                      "(oracle port, 1 thread) of 500 queries vs all trains scaled to the full N1 x N2" % (cw, ch, "oracle/_ref" if use_ref else "oracle port")},
+                            "sample": "centre %dx%d crop of the pair (1/4 area): %s view pipeline (%s) for both images on 2 threads (mods.cpp's two OpenMP "
+                                      "tasks; one view per detector leaves nothing else to parallelise), scaled x4; exact FGINN (oracle port, 1 thread) of 500 queries vs "
+                                      "all trains scaled to the full N1 x N2" % (cw, ch, "oracle/_ref" if use_ref else "oracle port", "HessianAffine, then MSER" if len(dets) > 1 else "HessianAffine")},
            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -326,6 +346,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="4096x3072", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mser", action="store_true", help="HessianAffine-only variant of the workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

@@ -112,7 +112,8 @@ class PairConfig(C.Structure):
     _fields_ = [("det", HessaffParams), ("ori", OrientationParams), ("desc", SiftParams),
                 ("matchRatio", C.c_double), ("contradDist", C.c_double), ("duplicateDist", C.c_double),
                 ("err_threshold", C.c_double), ("confidence", C.c_double), ("HLAFCoef", C.c_double),
-                ("max_samples", C.c_int), ("errorType", C.c_int), ("doSymmCheck", C.c_int), ("seed", C.c_long)]
+                ("max_samples", C.c_int), ("errorType", C.c_int), ("doSymmCheck", C.c_int), ("seed", C.c_long),
+                ("use_mser", C.c_int), ("mser", MserParams), ("mserMatchRatio", C.c_double)]
 
     @staticmethod
     def default():
@@ -125,7 +126,8 @@ class PairResult(C.Structure):
     _fields_ = [("regions1", C.c_int), ("regions2", C.c_int), ("tentatives", C.c_int), ("unique_tentatives", C.c_int),
                 ("ransac_inliers", C.c_int), ("verified", C.c_int), ("H", C.c_double * 9),
                 ("ms_detect_describe", C.c_double), ("ms_match", C.c_double), ("ms_duplicate", C.c_double),
-                ("ms_ransac", C.c_double), ("ms_total", C.c_double)]
+                ("ms_ransac", C.c_double), ("ms_total", C.c_double),
+                ("mser_regions1", C.c_int), ("mser_regions2", C.c_int), ("mser_tentatives", C.c_int)]
 
 
 def _ptr(a):

@@ -34,6 +34,8 @@ AffineKeypoint kp_from(const double* v) {
 DetectorsParameters::DetectorsParameters() {
   // [HessianAffine] of config_iter_mods_cviu.ini
   HessParam = mb2_hessaff_params{5.3333f, 3, 1.6f, 10.0f, 5, 16, 0.05f, 19, 1, 0, 2000, -1.f, -1.f, 41, 3.0f * std::sqrt(3.0f)};
+  // [MSER] of config_iter_mods_cviu.ini
+  MSERParam = mb2_mser_params{0.05, 30, 8.0, 0, 0, -1, -1.f, -1.f};
 }
 DescriptorsParameters::DescriptorsParameters() {
   SIFTParam = mb2_sift_params{5.1962, 41, 1, 0, 0};
@@ -91,12 +93,14 @@ AffineRegionVector ImageRepresentation::GetAffineRegionVector(std::string desc_n
 
 void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisParam& synth_par, DetectorsParameters& det_par,
                                                        DescriptorsParameters& desc_par, DominantOrientationParams& dom_ori_par) {
-  // imagerepresentation.cpp:603-2047, HessianAffine branch (:717-720) with SIFT-like descriptors (:1254-1341).
-  // Views other than the identity need GenerateSynthImageCorr (not built): skipped.
+  // imagerepresentation.cpp:603-2047: HessianAffine branch (:717-720) and MSER branch (:1035-1038) with SIFT-like
+  // descriptors (:1254-1341).  Views other than the identity need GenerateSynthImageCorr (not built): skipped.
   for (int det = 0; det < 4; det++) {
     const std::string curr_det = kDetectorNames[det];
     auto it = synth_par.find(curr_det);
-    if (it == synth_par.end() || curr_det != "HessianAffine") continue;
+    if (it == synth_par.end() || (curr_det != "HessianAffine" && curr_det != "MSER")) continue;
+    const bool is_mser = curr_det == "MSER";
+    SlotState& ss = slot_state[curr_det];
     for (size_t synth = 0; synth < it->second.size(); synth++) {   // views are appended in view-index order (:2044-2045)
       const ViewSynthParameters& v = it->second[synth];
       const bool identity = (std::fabs(v.tilt - 1.) <= 0.1) && (std::fabs(v.phi) <= 0.2) && (std::fabs(v.zoom - 1.) <= 0.1);  // synth-detection.cpp:278
@@ -108,14 +112,16 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
         mb2_sift_params sp = (dt == DESC_ROOT_SIFT) ? desc_par.RootSIFTParam : desc_par.SIFTParam;
         mb2_orientation_params op{dom_ori_par.mrSize, dom_ori_par.patchSize, dom_ori_par.maxAngles, (double)dom_ori_par.threshold};
         const double t0 = now_ms();
-        const bool use_slot = slot >= 0 && (slot_desc.empty() || slot_desc == curr_desc);
-        int n = mb2_detect_describe_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
-                                         &det_par.HessParam, &op, &sp, use_slot ? slot : MB2_MAX_SLOTS - 1, use_slot && slot_count > 0,
-                                         nullptr, nullptr, nullptr, 0);
+        const bool use_slot = slot >= 0 && (ss.desc.empty() || ss.desc == curr_desc);
+        const int dev_slot = use_slot ? slot_of(curr_det) : MB2_MAX_SLOTS - 1;
+        int n = is_mser ? mb2_detect_describe_view_mser(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
+                                                        &det_par.MSERParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0)
+                        : mb2_detect_describe_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
+                                                   &det_par.HessParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0);
         if (n < 0) continue;  // failures are silent, like the reference (empty lists)
-        if (use_slot) { slot_desc = curr_desc; slot_count += n; }
+        if (use_slot) { ss.desc = curr_desc; ss.count += n; }
         RegionBlock& B = Blocks[curr_det][curr_desc];
-        B.det = DET_HESSIAN; B.desc = dt;
+        B.det = is_mser ? DET_MSER : DET_HESSIAN; B.desc = dt;
         const size_t base = (size_t)B.n;
         B.det_kp.resize((base + n) * MB2_KP); B.reproj_kp.resize((base + n) * MB2_KP); B.desc_u8.resize((base + n) * 128);
         B.img_id.resize(base + n, (int)synth);
@@ -237,11 +243,12 @@ int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresen
       const ImageRepresentation::RegionBlock& T = b2->second;
       if (Q.n == 0 || T.n == 0) continue;
       std::vector<double> rows((size_t)Q.n * 7);
-      const bool resident = curr_det == "HessianAffine" && imgrep1.slot >= 0 && imgrep2.slot >= 0 && imgrep1.slot_desc == curr_desc &&
-                            imgrep2.slot_desc == curr_desc && imgrep1.slot_count == Q.n && imgrep2.slot_count == T.n;
+      auto s1 = imgrep1.slot_state.find(curr_det), s2 = imgrep2.slot_state.find(curr_det);
+      const bool resident = imgrep1.slot >= 0 && imgrep2.slot >= 0 && s1 != imgrep1.slot_state.end() && s2 != imgrep2.slot_state.end() &&
+                            s1->second.desc == curr_desc && s2->second.desc == curr_desc && s1->second.count == Q.n && s2->second.count == T.n;
       int n;
       if (resident) {  // descriptors are still on the device in exactly this order: no re-upload
-        n = mb2_match_slots(ctx, imgrep1.slot, imgrep2.slot, cur.currMatchRatio, cur.contradDist, 50, rows.data(), Q.n);
+        n = mb2_match_slots(ctx, imgrep1.slot_of(curr_det), imgrep2.slot_of(curr_det), cur.currMatchRatio, cur.contradDist, 50, rows.data(), Q.n);
       } else {
         std::vector<double> txy((size_t)T.n * 2);
         for (int i = 0; i < T.n; i++) { txy[2 * i] = T.reproj_kp[(size_t)i * MB2_KP]; txy[2 * i + 1] = T.reproj_kp[(size_t)i * MB2_KP + 1]; }
@@ -507,6 +514,7 @@ extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
   c->err_threshold = 3.0; c->confidence = 0.99; c->HLAFCoef = 12.0;                // config_iter_mods_cviu.ini:163-172
   c->max_samples = 100000; c->errorType = 0; c->doSymmCheck = 1;
   c->seed = 1;
+  c->use_mser = 0; c->mser = dp.MSERParam; c->mserMatchRatio = 0.8;                 // iters_mods_cviu.ini:36 ([MSER0] FGINNThreshold)
 }
 
 namespace {
@@ -522,6 +530,11 @@ struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.in
     desc_name = cfg->desc.rootSIFT ? "RootSIFT" : "SIFT";
     ViewSynthParameters v; v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = cfg->matchRatio;
     iters["HessianAffine"].push_back(v);
+    if (cfg->use_mser) {
+      det_par.MSERParam = cfg->mser;
+      ViewSynthParameters m; m.descriptors.push_back(desc_name); m.FGINNThreshold[desc_name] = cfg->mserMatchRatio;
+      iters["MSER"].push_back(m);
+    }
     rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
     rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
   }
@@ -530,8 +543,11 @@ struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.in
 // Everything the verification stage needs from the detection / matching stage, on the host.
 struct PairFront {
   std::unique_ptr<ImageRepresentation> rep1, rep2;
-  std::vector<double> rows;   // nt x 7 tentatives
-  int nt = 0, rc = MB2_OK;
+  // tentatives per detector, in the order GetCorresponcesVector("All", "All") concatenates them
+  // (CorrespondencesMapMap[desc][det], std::map order: "HessianAffine" < "MSER")
+  struct Group { const char* det; std::vector<double> rows; int nt = 0; };
+  Group groups[2];
+  int n_groups = 0, nt = 0, rc = MB2_OK;
   double t_start = 0;
 };
 
@@ -549,41 +565,57 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
     out.rep1->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
     th.join();
     if (mb2_slot_move(ctx, 1, ctx2, 1) < 0) { out.rc = MB2_ERR_CUDA; return; }
+    if (cfg->use_mser && mb2_slot_move(ctx, 3, ctx2, 3) < 0) { out.rc = MB2_ERR_CUDA; return; }
   } else {
     out.rep1->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
     out.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
   }
   res->ms_detect_describe = now_ms() - t0;
   res->regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name); res->regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name);
-  const ImageRepresentation::RegionBlock* Q = out.rep1->block("HessianAffine", ps.desc_name);
-  const ImageRepresentation::RegionBlock* T = out.rep2->block("HessianAffine", ps.desc_name);
-  if (Q && T && Q->n > 0 && T->n > 0) {
-    t0 = now_ms();
-    out.rows.resize((size_t)Q->n * 7);
-    out.nt = mb2_match_slots(ctx, 0, 1, cfg->matchRatio, cfg->contradDist, 50, out.rows.data(), Q->n);   // MatchImgReps -> MatchFlannFGINN
-    if (out.nt < 0) { out.rc = out.nt; out.nt = 0; return; }
-    res->ms_match = now_ms() - t0;
-    res->tentatives = out.nt;
+  res->mser_regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name, "MSER"); res->mser_regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name, "MSER");
+  t0 = now_ms();
+  const char* dets[2] = {"HessianAffine", "MSER"};
+  for (int g = 0; g < (cfg->use_mser ? 2 : 1); g++) {   // MatchImgReps, separate detectors (correspondencebank.cpp:291-347)
+    PairFront::Group& G = out.groups[out.n_groups];
+    G.det = dets[g];
+    const ImageRepresentation::RegionBlock* Q = out.rep1->block(dets[g], ps.desc_name);
+    const ImageRepresentation::RegionBlock* T = out.rep2->block(dets[g], ps.desc_name);
+    out.n_groups++;
+    if (!(Q && T && Q->n > 0 && T->n > 0)) continue;
+    G.rows.resize((size_t)Q->n * 7);
+    G.nt = mb2_match_slots(ctx, g == 0 ? 0 : 2, g == 0 ? 1 : 3, g == 0 ? cfg->matchRatio : cfg->mserMatchRatio, cfg->contradDist, 50, G.rows.data(), Q->n);
+    if (G.nt < 0) { out.rc = G.nt; G.nt = 0; return; }
+    out.nt += G.nt;
+    if (g == 1) res->mser_tentatives = G.nt;
   }
+  res->ms_match = now_ms() - t0;
+  res->tentatives = out.nt;
 }
 
 // mods.cpp:330-415: DuplicateFiltering(MODE_FGINN) + LORANSACFiltering on the region blocks and index lists
 // directly (the AoS TentativeCorrespListExt of the reference is only materialised by the class API).
 int pair_back(mb2_ctx* vctx, const mb2_pair_config* cfg, PairSetup& ps, PairFront& in, mb2_pair_result* res, double* verified_out, int capacity) {
   int n = 0;
-  const ImageRepresentation::RegionBlock* Q = in.rep1->block("HessianAffine", ps.desc_name);
-  const ImageRepresentation::RegionBlock* T = in.rep2->block("HessianAffine", ps.desc_name);
   const int nt = in.nt;
-  if (Q && T && nt > 0) {
-    const std::vector<double>& rows = in.rows;
+  if (nt > 0) {
     double t0 = now_ms();
+    // tentatives["All"] = GetCorresponcesVector() (mods.cpp:298): the per-detector lists one after the other
     std::vector<double> xy((size_t)nt * 4), key(nt);
-    for (int i = 0; i < nt; i++) {
-      const double* r = &rows[(size_t)i * 7];
-      const double* a = &Q->reproj_kp[(size_t)r[0] * MB2_KP];
-      const double* b = &T->reproj_kp[(size_t)r[1] * MB2_KP];
-      xy[4 * (size_t)i] = a[0]; xy[4 * (size_t)i + 1] = a[1]; xy[4 * (size_t)i + 2] = b[0]; xy[4 * (size_t)i + 3] = b[1];
-      key[i] = std::fabs(std::sqrt((double)((float)r[4] / (float)r[5])));
+    std::vector<const double*> fa(nt), fb(nt);   // reproj_kp records of the two regions of every tentative
+    int o = 0;
+    for (int g = 0; g < in.n_groups; g++) {
+      const PairFront::Group& G = in.groups[g];
+      if (G.nt <= 0) continue;
+      const ImageRepresentation::RegionBlock* Q = in.rep1->block(G.det, ps.desc_name);
+      const ImageRepresentation::RegionBlock* T = in.rep2->block(G.det, ps.desc_name);
+      for (int i = 0; i < G.nt; i++, o++) {
+        const double* r = &G.rows[(size_t)i * 7];
+        const double* a = &Q->reproj_kp[(size_t)r[0] * MB2_KP];
+        const double* b = &T->reproj_kp[(size_t)r[1] * MB2_KP];
+        fa[o] = a; fb[o] = b;
+        xy[4 * (size_t)o] = a[0]; xy[4 * (size_t)o + 1] = a[1]; xy[4 * (size_t)o + 2] = b[0]; xy[4 * (size_t)o + 3] = b[1];
+        key[o] = std::fabs(std::sqrt((double)((float)r[4] / (float)r[5])));
+      }
     }
     std::vector<int> kept = duplicate_filter_core(xy.data(), key.data(), nt, cfg->duplicateDist, true);
     res->ms_duplicate = now_ms() - t0;
@@ -591,9 +623,8 @@ int pair_back(mb2_ctx* vctx, const mb2_pair_config* cfg, PairSetup& ps, PairFron
     t0 = now_ms();
     std::vector<double> frames(kept.size() * 14);
     for (size_t i = 0; i < kept.size(); i++) {
-      const double* r = &rows[(size_t)kept[i] * 7];
-      const double* a = &Q->reproj_kp[(size_t)r[0] * MB2_KP];
-      const double* b = &T->reproj_kp[(size_t)r[1] * MB2_KP];
+      const double* a = fa[kept[i]];
+      const double* b = fb[kept[i]];
       double* f = &frames[i * 14];
       for (int j = 0; j < 7; j++) { f[j] = a[j]; f[7 + j] = b[j]; }   // KP layout starts with x y a11 a12 a21 a22 s
     }

@@ -9,7 +9,7 @@
 //   LORANSACFiltering (+ NaiveHCheck, H_LAF_check)      matching/matching.hpp:284-286, .cpp:806-980, 1171-1200, 251-309
 //
 // cv::Mat is replaced by a plain float image; everything else keeps the reference's layout
-// (detectors/structures.hpp:187-245).  Only the HessianAffine detector and the SIFT / RootSIFT
+// (detectors/structures.hpp:187-245).  Only the HessianAffine and MSER detectors and the SIFT / RootSIFT
 // descriptors are wired (the other branches are out of scope); unknown detector or
 // descriptor names are skipped silently, exactly as the reference skips detectors that have no
 // views configured.
@@ -68,7 +68,7 @@ struct TimeLog {  // detectors/structures.hpp:51-74
   double SynthTime = 0, DetectTime = 0, OrientTime = 0, DescTime = 0, MatchingTime = 0, RANSACTime = 0, MiscTime = 0, TotalTime = 0;
 };
 
-struct DetectorsParameters { mb2_hessaff_params HessParam; DetectorsParameters(); };
+struct DetectorsParameters { mb2_hessaff_params HessParam; mb2_mser_params MSERParam; DetectorsParameters(); };
 struct DescriptorsParameters { mb2_sift_params SIFTParam, RootSIFTParam; DescriptorsParameters(); };
 struct DominantOrientationParams {  // descriptors_parameters.hpp:23-36 + [DominantOrientation]
   int maxAngles = 1; float threshold = 0.8f; bool addUpRight = false; bool halfSIFTMode = false;
@@ -138,9 +138,11 @@ class ImageRepresentation {
   TimeLog TimeSpent;
   std::map<std::string, std::map<std::string, RegionBlock> > Blocks;  // [det][desc]
   std::string Name;
-  int slot;                 // device-resident copy of RegionVectorMap["HessianAffine"][desc] for the matcher
-  std::string slot_desc;    // which descriptor the slot currently holds ("" = none)
-  int slot_count = 0;
+  // device-resident copies of RegionVectorMap[det][desc] for the matcher: HessianAffine in `slot`, MSER in `slot + 2`
+  int slot;
+  struct SlotState { std::string desc; int count = 0; };   // which descriptor the slot currently holds ("" = none)
+  std::map<std::string, SlotState> slot_state;              // per detector
+  int slot_of(const std::string& det) const { return slot < 0 ? -1 : (det == "MSER" ? slot + 2 : slot); }
 };
 
 class CorrespondenceBank {
@@ -182,11 +184,17 @@ typedef struct {
   double err_threshold, confidence, HLAFCoef;
   int max_samples, errorType, doSymmCheck;
   long seed;
+  /* second detector of the step ([MSER0] / [MSER1] tiers of iters_mods_cviu.ini), matched separately like the reference's
+   * "separate detectors" loop (correspondencebank.cpp:291-347) and verified together with the HessianAffine tentatives */
+  int use_mser;
+  mb2_mser_params mser;
+  double mserMatchRatio;
 } mb2_pair_config;
 typedef struct {
   int regions1, regions2, tentatives, unique_tentatives, ransac_inliers, verified;
   double H[9];
   double ms_detect_describe, ms_match, ms_duplicate, ms_ransac, ms_total;
+  int mser_regions1, mser_regions2, mser_tentatives;   /* the MSER share of regions1 / regions2 / tentatives */
 } mb2_pair_result;
 void mb2_pair_config_default(mb2_pair_config* c);
 /* images: gray f32 [H|D].  verified_out (optional): capacity rows of 4 doubles (x1 y1 x2 y2).  Returns verified count or < 0. */

@@ -100,3 +100,70 @@ def test_mser_full_size_properties(ctx):
     det_cov = a[:, 10] * a[:, 12] - a[:, 11] ** 2
     det_A = k[:, 2] * k[:, 5] - k[:, 3] * k[:, 4]
     assert np.allclose(det_A ** 2, det_cov, rtol=1e-9)
+
+
+def _dup_filter_bruteforce(xy, key, r):
+    """matching.cpp:2983-3047 with a stable sort (MODE_FGINN)."""
+    order = np.argsort(key, kind="stable")
+    kept = []
+    for j in order:
+        dup = False
+        for i in kept:
+            if (xy[i, 0] - xy[j, 0]) ** 2 + (xy[i, 1] - xy[j, 1]) ** 2 <= r * r and (xy[i, 2] - xy[j, 2]) ** 2 + (xy[i, 3] - xy[j, 3]) ** 2 <= r * r:
+                dup = True
+                break
+        if not dup:
+            kept.append(j)
+    return np.array(kept, dtype=np.int64)
+
+
+def test_mods_pair_with_mser_equals_stage_composition(ctx, oracle):
+    """One mods.cpp iteration with both detectors of the step (HessianAffine + MSER, separate matching, joint verification)
+    == the oracle's per-view pipelines, its FGINN matcher per detector, duplicate filter and the GPU RANSAC on the union."""
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(480, 360, seed=21, n_blobs=500)
+    B = warp_image(A, gt_homography(480, 360), seed=22)
+    cfg = mb.PairConfig.default()
+    cfg.seed = 4242
+    cfg.use_mser = 1
+    res, ver = ctx.mods_pair(A, B, cfg, capacity=8192)
+    xy, key = [], []
+    n1 = n2 = nt = 0
+    for det, ratio in ((0, cfg.matchRatio), (3, cfg.mserMatchRatio)):
+        oa, ob = oracle.view_pipeline(A, detector=det), oracle.view_pipeline(B, detector=det)
+        n1 += len(oa[0]); n2 += len(ob[0])
+        om = oracle.match_fginn(oa[2], ob[2], np.ascontiguousarray(ob[1][:, :2]), ratio=ratio, contradDist=cfg.contradDist)
+        nt += len(om)
+        if det == 3:
+            assert (res.mser_regions1, res.mser_regions2, res.mser_tentatives) == (len(oa[0]), len(ob[0]), len(om)) and len(om) > 5
+        qi, ti = om[:, 0].astype(int), om[:, 1].astype(int)
+        xy.append(np.concatenate([oa[1][qi, :2], ob[1][ti, :2]], axis=1))
+        key.append(np.abs(np.sqrt((om[:, 4].astype(np.float32) / om[:, 5].astype(np.float32)).astype(np.float64))))
+    xy, key = np.concatenate(xy), np.concatenate(key)
+    assert (res.regions1, res.regions2, res.tentatives) == (n1, n2, nt)
+    kept = _dup_filter_bruteforce(xy, key, cfg.duplicateDist)
+    assert res.unique_tentatives == len(kept)
+    u = np.ones((len(kept), 6)); u[:, 0:2] = xy[kept, 0:2]; u[:, 3:5] = xy[kept, 2:4]
+    r = ctx.ransac_h(u, th=cfg.err_threshold ** 2, conf=cfg.confidence, max_sam=cfg.max_samples if len(kept) > 20 else 1000,
+                     errorType=cfg.errorType, doSymCheck=cfg.doSymmCheck, seed=cfg.seed)
+    assert res.ransac_inliers == int(r["inl"].sum()) and 8 <= res.verified <= res.ransac_inliers
+    Hgt = gt_homography(480, 360)
+    p = np.c_[ver[:, :2], np.ones(len(ver))] @ Hgt.T
+    assert np.median(np.hypot(p[:, 0] / p[:, 2] - ver[:, 2], p[:, 1] / p[:, 2] - ver[:, 3])) < 1.5
+
+
+def test_mods_pairs_with_mser_pipeline_equals_single_calls(ctx):
+    from synth import blob_image, warp_image, gt_homography
+    pairs = []
+    for k in range(3):
+        A = blob_image(400 + 40 * k, 300 + 8 * k, seed=41 + k, n_blobs=350 + 50 * k)
+        pairs.append((A, warp_image(A, gt_homography(A.shape[1], A.shape[0]), seed=51 + k)))
+    cfg = mb.PairConfig.default()
+    cfg.seed = 99
+    cfg.use_mser = 1
+    single = [ctx.mods_pair(a, b, cfg, capacity=4096) for a, b in pairs]
+    res, ver = ctx.mods_pairs(pairs, cfg, capacity=4096)
+    for (r1, v1), r2, v2 in zip(single, res, ver):
+        for f in ("regions1", "regions2", "tentatives", "unique_tentatives", "ransac_inliers", "verified", "mser_regions1", "mser_tentatives"):
+            assert getattr(r1, f) == getattr(r2, f), f
+        assert r1.mser_regions1 > 0 and np.array_equal(v1, v2) and np.array_equal(np.array(r1.H[:]), np.array(r2.H[:]))
