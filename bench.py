@@ -205,14 +205,15 @@ def run_ours(args, rank, world, local_rank):
         "stage_ms": {k: float(np.mean([getattr(r, k) for r in res_lat])) for k in ("ms_detect_describe", "ms_match", "ms_duplicate", "ms_ransac", "ms_total")},
     }
     if prof:
-        out.update(roofline_from_profile(prof, w, h, regions, peaks, steps=min(args.steps, N_PAIRS)))
+        out.update(roofline_from_profile(prof, w, h, regions, peaks, steps=min(args.steps, N_PAIRS),
+                                         mser_regions=float(np.mean([r.mser_regions1 + r.mser_regions2 for r in res_dev])) / 2))
     else:
         out["roofline"] = None
     out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1, with_mser=not args.no_mser) if not args.no_cpu_baseline else None
     print(json.dumps(out))
 
 
-def roofline_from_profile(prof, w, h, regions, peaks, steps):
+def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
     """prof: {kernel name: (launches, total ms)} over `steps` pairs (2 images each)."""
     prof = dict(prof)
     gather_bytes = prof.pop("__extract_gather_bytes__", (1, 0.0))[1]
@@ -252,7 +253,8 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps):
     nn = [(k, v) for k, v in prof.items() if "k_nn_tc" in k]
     if nn:
         ms_nn = sum(v[1] for _, v in nn) / steps
-        flop = 2.0 * 2.0 * regions * regions * 128        # two streaming passes over the N1 x N2 x 128 contraction
+        nh = regions - mser_regions                        # matching is per detector: N_hess^2 + N_mser^2 distance pairs
+        flop = 2.0 * 2.0 * (nh * nh + mser_regions * mser_regions) * 128   # two streaming passes over each N1 x N2 x 128 contraction
         extra["roofline_nn"] = {"bound": "tensor", "achieved": flop / 1e12 / (ms_nn / 1e3), "peak": peaks["bf16"], "unit": "TFLOP/s",
                                 "frac": flop / 1e12 / (ms_nn / 1e3) / peaks["bf16"], "ms_per_pair": ms_nn, "flop": flop,
                                 "note": "2 passes (NN, then FGINN statistics); epilogue on CUDA cores is fused (distances never leave the SM)"}

@@ -178,11 +178,16 @@ __device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint
       if (valid[2] && ((valid[0] && r[2] == r[0]) || (valid[1] && r[2] == r[1]))) valid[2] = false;
       if (valid[3] && ((valid[0] && r[3] == r[0]) || (valid[1] && r[3] == r[1]) || (valid[2] && r[3] == r[2]))) valid[3] = false;
     }
+    // distinct roots packed to the front: most pixels have one, so the warp-synchronous rounds below are one or two, not four
+    uint32_t rr[4]; int nr = 0;
 #pragma unroll
-    for (int d = 0; d < 4; d++) {
-      bool pend = act && valid[d];
+    for (int d = 0; d < 4; d++) if (valid[d]) rr[nr++] = r[d];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      bool pend = act && j < nr;
+      if (!__ballot_sync(0xffffffffu, pend)) break;
       uint32_t ra = 0, rb = 0;
-      if (pend) { ra = uf_find<false>(zpar, p); rb = r[d]; }
+      if (pend) { ra = uf_find<false>(zpar, p); rb = rr[j]; }
       for (;;) {
         if (pend) {
           if (ra == rb) pend = false;
