@@ -160,6 +160,18 @@ int mb2_detect_describe_view_mser(mb2_ctx* ctx, const float* pixels, int w, int 
                                   int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8,
                                   int capacity);
 
+/* Batched form of the MSER detector hook for the two images of a pair (mods.cpp:255-271 runs the two images side by side):
+ * the component tree is built level by level and is latency bound, so two same-size images in ONE pass cost hardly more
+ * than one.  FIXED_TH only.  Detection only: the keys (as regions) stay on the device; *n1 / *n2 = regions per image.
+ * mb2_describe_view_of_pair then runs DetectOrientation -> ReprojectRegions -> DescribeRegions for image `which` (0 / 1)
+ * exactly as mb2_detect_describe_view_mser does after its detection (same outputs, same slot semantics); `src` is the
+ * context that ran mb2_mser_detect_pair (NULL = ctx itself), so the two images can be finished on two contexts at once. */
+int mb2_mser_detect_pair(mb2_ctx* ctx, const float* pixels1, const float* pixels2, int w, int h, const mb2_mser_params* par,
+                         int* n1, int* n2);
+int mb2_describe_view_of_pair(mb2_ctx* ctx, mb2_ctx* src, int which, const double* H, int orig_w, int orig_h,
+                              const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot, int append,
+                              double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
+
 /* Copies the regions of the most recent mb2_detect_describe_view (which may be called with NULL
  * outputs to learn the count first) to the host.  Returns that count. */
 int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);

@@ -18,7 +18,7 @@ EXPORTS = [
     "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
     "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
-    "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser",
+    "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair",
 ]
 
 
@@ -232,6 +232,25 @@ class Context:
         n = self._check(lib().mb2_mser_regions(self.h, _ptr(img), C.c_int(w), C.c_int(h), C.byref(par), _ptr(out), C.c_int(capacity)),
                         "mser_regions")
         return out[:n].copy()
+
+    def mser_pair_views(self, img1, img2, det=None, ori=None, desc=None, slots=(2, 3), shape=None):
+        """Both images of a pair through MSER detection in one pass, then orientation / reprojection / description per image.
+        Returns [(det_kp, reproj_kp, desc_u8), (...)]."""
+        h, w = shape if shape is not None else img1.shape
+        det = det or MserParams.default(); ori = ori or OrientationParams.default(); desc = desc or SiftParams.default()
+        n1, n2 = C.c_int(), C.c_int()
+        self._check(lib().mb2_mser_detect_pair(self.h, _ptr(img1), _ptr(img2), C.c_int(w), C.c_int(h), C.byref(det), C.byref(n1), C.byref(n2)),
+                    "mser_detect_pair")
+        H = np.ascontiguousarray(np.eye(3), np.float64)
+        out = []
+        for which, n in ((0, n1.value), (1, n2.value)):
+            cap = max(1, n * max(1, ori.maxAngles))
+            dk = np.zeros((cap, KP)); rk = np.zeros((cap, KP)); du = np.zeros((cap, 128), np.uint8)
+            k = self._check(lib().mb2_describe_view_of_pair(self.h, C.c_void_p(0), C.c_int(which), _ptr(H), C.c_int(w), C.c_int(h), C.byref(ori), C.byref(desc),
+                                                            C.c_int(slots[which]), C.c_int(0), _ptr(dk), _ptr(rk), _ptr(du), C.c_int(cap)),
+                            "describe_view_of_pair")
+            out.append((dk[:k].copy(), rk[:k].copy(), du[:k].copy()))
+        return out
 
     def detect_orientation(self, img, kps, par=None, shape=None):
         h, w = shape if shape is not None else img.shape

@@ -648,7 +648,8 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->img, &ctx->pyr, &ctx->resp, &ctx->cand, &ctx->misc, &ctx->kp_a, &ctx->kp_b, &ctx->kp_c, &ctx->desc_u8,
-                    &ctx->patch_scratch, &ctx->nn_a, &ctx->nn_b, &ctx->nn_c, &ctx->nn_d, &ctx->rs_a, &ctx->rs_b, &ctx->rs_c, &ctx->rs_u, &ctx->octmap};
+                    &ctx->patch_scratch, &ctx->nn_a, &ctx->nn_b, &ctx->nn_c, &ctx->nn_d, &ctx->rs_a, &ctx->rs_b, &ctx->rs_c, &ctx->rs_u, &ctx->octmap,
+                    &ctx->img2, &ctx->pair_keys};
   for (DevBuf* b : bufs) b->release();
   for (auto& s : ctx->slots) { s.desc.release(); s.xy.release(); }
   ctx->h_a.release(); ctx->h_b.release(); ctx->h_c.release();
@@ -769,6 +770,9 @@ int mb2_describe_sift(mb2_ctx* ctx, const float* pixels, int w, int h, const dou
   return n;
 }
 
+static int view_post(mb2_ctx* ctx, const ImgView& img, int n, const double* H, int orig_w, int orig_h, const mb2_orientation_params* ori,
+                     const mb2_sift_params* desc, int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
+
 // One (detector, view) pass; det_h != NULL: HessianAffine, det_m != NULL: MSER.
 static int view_core(mb2_ctx* ctx, const float* pixels, int w, int h, const double* H, int orig_w, int orig_h,
                      const mb2_hessaff_params* det_h, const mb2_mser_params* det_m, const mb2_orientation_params* ori, const mb2_sift_params* desc,
@@ -776,11 +780,19 @@ static int view_core(mb2_ctx* ctx, const float* pixels, int w, int h, const doub
   if (!ctx || !pixels || !H || (!det_h && !det_m) || !ori || !desc || slot < 0 || slot >= MB2_MAX_SLOTS) return MB2_ERR_ARG;
   cudaSetDevice(ctx->device);
   ImgView img;
-  int rc, n = 0, m = 0, k = 0;
+  int rc, n = 0;
   ctx->last_view_n = 0;
   if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
   if (det_h) { if ((rc = detect_core(ctx, img, *det_h, 1.0, 1.0, 1, &n))) return rc; }
   else if ((rc = mb2_mser_core(ctx, img, *det_m, 1.0, 1.0, 1, &n, nullptr, 0))) return rc;
+  return view_post(ctx, img, n, H, orig_w, orig_h, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
+}
+
+// DetectOrientation -> ReprojectRegions -> DescribeRegions on the n detected regions in ctx->kp_b (imagerepresentation.cpp:1254-1341)
+static int view_post(mb2_ctx* ctx, const ImgView& img, int n, const double* H, int orig_w, int orig_h, const mb2_orientation_params* ori,
+                     const mb2_sift_params* desc, int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
+  int rc, m = 0, k = 0;
+  ctx->last_view_n = 0;
   if ((rc = orient_core(ctx, img, n, *ori, &m))) return rc;
   RegionSlot& rs = ctx->slots[slot];
   if (!append) rs.n = 0;
@@ -856,6 +868,48 @@ int mb2_detect_describe_view_mser(mb2_ctx* ctx, const float* pixels, int w, int 
                                   int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
   if (!det) return MB2_ERR_ARG;
   return view_core(ctx, pixels, w, h, H, orig_w, orig_h, nullptr, det, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
+}
+
+int mb2_mser_detect_pair(mb2_ctx* ctx, const float* pixels1, const float* pixels2, int w, int h, const mb2_mser_params* par, int* n1, int* n2) {
+  if (!ctx || !pixels1 || !pixels2 || !par || !n1 || !n2 || w <= 0 || h <= 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView a, b;
+  int rc;
+  ctx->pair_n[0] = ctx->pair_n[1] = 0;
+  if ((rc = stage_image(ctx, pixels1, w, h, &a))) return rc;
+  {  // second image next to the first
+    const int pitch = pitch_of(w);
+    MB2_CUDA_CHECK(ctx, ctx->img2.reserve((size_t)pitch * h * 4));
+    cudaMemcpyKind kind = mb2_is_device_ptr(pixels2) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    MB2_CUDA_CHECK(ctx, cudaMemcpy2DAsync(ctx->img2.p, (size_t)pitch * 4, pixels2, (size_t)w * 4, (size_t)w * 4, h, kind, ctx->stream));
+    b.p = ctx->img2.as<float>(); b.rows = h; b.cols = w; b.pitch = pitch;
+  }
+  if ((rc = mb2_mser_core_pair(ctx, a, b, *par, 1, n1, n2))) return rc;
+  const int n = *n1 + *n2;
+  if (n > 0) {
+    MB2_CUDA_CHECK(ctx, ctx->pair_keys.reserve((size_t)n * sizeof(KeyOut)));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->pair_keys.p, ctx->kp_b.p, (size_t)n * sizeof(KeyOut), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  ctx->pair_n[0] = *n1; ctx->pair_n[1] = *n2; ctx->pair_w = w; ctx->pair_h = h;
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // the keys may be picked up by another context (mb2_describe_view_of_pair)
+  return n;
+}
+int mb2_describe_view_of_pair(mb2_ctx* ctx, mb2_ctx* src, int which, const double* H, int orig_w, int orig_h, const mb2_orientation_params* ori,
+                              const mb2_sift_params* desc, int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8,
+                              int capacity) {
+  if (!src) src = ctx;
+  if (!ctx || which < 0 || which > 1 || !H || !ori || !desc || slot < 0 || slot >= MB2_MAX_SLOTS || src->pair_w <= 0 || src->device != ctx->device)
+    return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView img;   // the staged images and the keys stay where mb2_mser_detect_pair left them (same device: readable from any context)
+  img.p = which ? src->img2.as<float>() : src->img.as<float>(); img.rows = src->pair_h; img.cols = src->pair_w; img.pitch = pitch_of(src->pair_w);
+  const int n = src->pair_n[which];
+  if (n > 0) {
+    MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)n * sizeof(KeyOut)));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->kp_b.p, src->pair_keys.as<KeyOut>() + (which ? src->pair_n[0] : 0), (size_t)n * sizeof(KeyOut),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return view_post(ctx, img, n, H, orig_w, orig_h, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
 }
 
 int mb2_mser_detect(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_mser_params* par, double tilt, double zoom, int as_regions,

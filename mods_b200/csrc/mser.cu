@@ -39,7 +39,7 @@ typedef unsigned long long u64;
 
 struct MserCounters {
   uint32_t hook_cnt, emu_nodes, own_keys, long_regions, n_sel, n_slots, n_starts, n_ends;
-  uint32_t overflow, thr_overflow, cap_overflow, root[2];
+  uint32_t overflow, thr_overflow, cap_overflow, n_stack, root[8], n_img[4];   // n_stack = 2 x images; n_img = regions per image
   uint32_t hist[256];
   uint32_t lvl_off[257];
   uint32_t hook_off[258];
@@ -108,23 +108,26 @@ __device__ __forceinline__ uint32_t uf_unite(uint32_t* zpar, const uint8_t* lev,
 // ---- 1. preparation ------------------------------------------------------------------------------------------------
 // float -> u8 as extrema.cpp:401-403 does ((unsigned char) of the float: truncation); second half = inverted image
 // (InvertImageAndHistogram, sortPixels.cpp:131-153)
-__global__ void k_mser_prep(const float* __restrict__ img, int pitch, int W, int H, uint8_t* __restrict__ lev,
+struct MserImages { const float* p[4]; int pitch[4]; int n; };   // same-size images processed together (a pair: n = 2)
+__global__ void k_mser_prep(MserImages im, int W, int H, uint8_t* __restrict__ lev,
                             uint32_t* __restrict__ zpar, uint32_t* __restrict__ parent, uint32_t* __restrict__ area,
                             uint32_t* __restrict__ order_in, MserCounters* __restrict__ C) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t N = (uint32_t)W * H;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-    const int y = i / W, x = i - y * W;
-    const int v = ((int)img[(size_t)y * pitch + x]) & 0xff;
-    const uint32_t j = i + N;
-    lev[i] = (uint8_t)v; zpar[i] = i; parent[i] = i; area[i] = 1; order_in[i] = i;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N * im.n; i += gridDim.x * blockDim.x) {
+    const uint32_t k = i / N, pi = i - k * N;
+    const int y = pi / W, x = pi - y * W;
+    const int v = ((int)im.p[k][(size_t)y * im.pitch[k] + x]) & 0xff;
+    const uint32_t a = 2 * k * N + pi, j = a + N;
+    lev[a] = (uint8_t)v; zpar[a] = a; parent[a] = a; area[a] = 1; order_in[a] = a;
     lev[j] = (uint8_t)(255 - v); zpar[j] = j; parent[j] = j; area[j] = 1; order_in[j] = j;
     atomicAdd(&h[v], 1u); atomicAdd(&h[255 - v], 1u);
   }
   __syncthreads();
   if (h[threadIdx.x]) atomicAdd(&C->hist[threadIdx.x], h[threadIdx.x]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) C->n_stack = 2 * im.n;
 }
 __global__ void k_mser_offsets(MserCounters* C) {
   if (threadIdx.x || blockIdx.x) return;
@@ -152,7 +155,7 @@ __device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint
     uint32_t p = 0, r[4]; bool valid[4] = {false, false, false, false};
     if (act) {
       p = order[k];
-      const int yy = p / W, x = p - yy * W, y = yy >= H ? yy - H : yy;
+      const int yy = p / W, x = p - yy * W, y = yy % H;
       uint32_t q[4] = {p - W, p - 1, p + 1, p + W};
       valid[0] = y > 0; valid[1] = x > 0; valid[2] = x < W - 1; valid[3] = y < H - 1;
       int lq[4];
@@ -261,7 +264,10 @@ __global__ void __launch_bounds__(256) k_mser_tree(int W, int H, const uint8_t* 
     grid.sync();
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L + 2] = t; }
   }
-  if (threadIdx.x == 0 && blockIdx.x == 0) { C->root[0] = uf_find<true>(zpar, 0); C->root[1] = uf_find<true>(zpar, (uint32_t)W * H); C->hook_off[257] = hook_beg; }
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (uint32_t i = 0; i < C->n_stack; i++) C->root[i] = uf_find<true>(zpar, i * (uint32_t)W * H);
+    C->hook_off[257] = hook_beg;
+  }
 }
 
 // ---- 3. survivors -------------------------------------------------------------------------------------------------------
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(MSER_RB_THREADS) k_mser_regions_b(TreeDev td, 
     atomicMin(slot_of_node + node, o);
     const uint32_t slot = o;
     SelRec e;
-    e.key = ((u64)(r.v0 >= Nimg ? 1 : 0) << 48) | ((u64)minI << 40) | ((u64)birth[r.v0] << 8) | (u64)k;
+    e.key = ((u64)(r.v0 / Nimg) << 48) | ((u64)minI << 40) | ((u64)birth[r.v0] << 8) | (u64)k;
     e.node = node; e.slot = slot; e.minI = minI; e.maxI = r.maxI; e.thresh = T[k].thresh; e.margin = T[k].margin;
     e.area = cA[T[k].thresh * MSER_RB_THREADS]; e.border = cB[T[k].thresh * MSER_RB_THREADS];
     sel[o] = e;
@@ -395,7 +401,8 @@ __global__ void k_mser_selkeys(const SelRec* __restrict__ sel, uint32_t n, u64* 
 __global__ void __launch_bounds__(256) k_mser_down(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ hooked, const uint32_t* __restrict__ slot_of_node,
                                                    uint32_t* sa, const MserCounters* C) {
   cg::grid_group grid = cg::this_grid();
-  if (threadIdx.x == 0 && blockIdx.x == 0) { sa[C->root[0]] = slot_of_node[C->root[0]]; sa[C->root[1]] = slot_of_node[C->root[1]]; }
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    for (uint32_t i = 0; i < C->n_stack; i++) sa[C->root[i]] = slot_of_node[C->root[i]];
   grid.sync();
   for (int L = 255; L >= 0; L--) {
     const uint32_t beg = C->hook_off[L], end = C->hook_off[L + 1];
@@ -432,11 +439,11 @@ __device__ __forceinline__ void agg_append(u64* list, uint32_t* counter, uint32_
 // first / last pixel of every row run of every selected component: key = slot << 32 | line << 16 | column
 __global__ void k_mser_runs(int W, int H, const uint32_t* __restrict__ sa, const uint32_t* __restrict__ up_sel, u64* __restrict__ starts,
                             u64* __restrict__ ends, uint32_t cap, MserCounters* C) {
-  const uint32_t N2 = 2u * (uint32_t)W * H;
+  const uint32_t N2 = C->n_stack * (uint32_t)W * H;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N2; p += gridDim.x * blockDim.x) {
     uint32_t s = sa[p];
     if (s == NONE) continue;
-    const int yy = p / W, x = p - yy * W, y = yy >= H ? yy - H : yy;
+    const int yy = p / W, x = p - yy * W, y = yy % H;
     while (s != NONE) {
       const bool l = x > 0 && in_slot(sa, up_sel, p - 1, s);
       const bool r = x < W - 1 && in_slot(sa, up_sel, p + 1, s);
@@ -462,11 +469,12 @@ __global__ void k_mser_moments(const u64* __restrict__ starts, const u64* __rest
 }
 // AffineKeypoint as DetectMSERs fills it (extrema.cpp:409-433) [+ DetectAffineRegions' post-step, synth-detection.hpp:110-124]
 __global__ void k_mser_keys(const SelRec* __restrict__ sel, const uint32_t* __restrict__ order, uint32_t n, const SlotMoments* __restrict__ mom,
-                            const uint32_t* __restrict__ slot_of_node, uint32_t Nimg, int as_regions, KeyOut* __restrict__ out, double* __restrict__ table) {
+                            const uint32_t* __restrict__ slot_of_node, uint32_t Nimg, int as_regions, KeyOut* __restrict__ out, double* __restrict__ table,
+                            uint32_t* __restrict__ n_img) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const SelRec e = sel[order[i]];
-  const int pol = e.node >= Nimg ? 1 : 0;
+  const int pol = (int)((e.node / Nimg) & 1u);
   const SlotMoments sm = mom[slot_of_node[e.node]];
   double A[4];
   ellipse_to_A(sm.m.sxx, sm.m.sxy, sm.m.syy, A);
@@ -483,6 +491,7 @@ __global__ void k_mser_keys(const SelRec* __restrict__ sel, const uint32_t* __re
   o.v[7] = (double)e.margin; o.v[8] = pol ? 20.0 : 21.0;
   o.order = i; o.keep = 1; o.pad = 0;
   out[i] = o;
+  atomicAdd(n_img + e.node / (2 * Nimg), 1u);   // regions per image (keys are image-major)
   if (table) {
     double* r = table + (size_t)i * 13;
     r[0] = pol; r[1] = e.minI; r[2] = e.maxI; r[3] = e.thresh; r[4] = e.margin; r[5] = e.area; r[6] = e.border; r[7] = sm.nruns;
@@ -507,14 +516,17 @@ MserBufs* mser_bufs(mb2_ctx* ctx) {
     if (hc->cap_overflow) { ctx->set_error("mser: internal list capacity exceeded"); return MB2_ERR_CAPACITY; }               \
   } while (0)
 
-// Both polarities at once (stacked, see the header comment).  Writes the keys (MSER+ first, reference order inside each) to
-// d_out; table (optional) receives 13 doubles per region.
-int mser_both(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, double min_margin, int as_regions, KeyOut* d_out,
-              int out_cap, int* n_out, double* d_table) {
+// K same-size images, both polarities each, at once (stacked, see the header comment).  Writes the keys image by image
+// (MSER+ first, reference order inside each) to d_out, n_per_img[k] of them for image k; table (optional) receives 13
+// doubles per region.
+int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& par, double min_margin, int as_regions, KeyOut* d_out,
+               int out_cap, int* n_per_img, double* d_table) {
   MserBufs& B = *mser_bufs(ctx);
   cudaStream_t st = ctx->stream;
-  const int W = img.cols, H = img.rows;
-  const uint32_t Nimg = (uint32_t)W * H, N = 2 * Nimg;
+  const int W = imgs[0].cols, H = imgs[0].rows;
+  const uint32_t Nimg = (uint32_t)W * H, N = 2 * Nimg * (uint32_t)K;
+  MserImages mi; mi.n = K;
+  for (int k = 0; k < K; k++) { mi.p[k] = imgs[k].p; mi.pitch[k] = imgs[k].pitch; n_per_img[k] = 0; }
   const int G = ctx->num_sms * 8;
   const int track_size = std::min(10000, par.min_size);
   const int max_size = (int)((double)W * (double)H * par.max_area);
@@ -536,7 +548,7 @@ int mser_both(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, doub
 
   // 1. u8 images, histogram, (level, raster) order
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(dC, 0, sizeof(MserCounters), st));
-  MB2_LAUNCH(ctx, k_mser_prep, grid_for(Nimg, 256, G), 256, 0, img.p, img.pitch, W, H, lev, zpar, parent, area, order_in, dC);
+  MB2_LAUNCH(ctx, k_mser_prep, grid_for(Nimg * K, 256, G), 256, 0, mi, W, H, lev, zpar, parent, area, order_in, dC);
   MB2_LAUNCH(ctx, k_mser_offsets, 1, 32, 0, dC);
   {
     size_t tmp = 0;
@@ -627,7 +639,6 @@ int mser_both(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, doub
       n_sel = (int)hc->n_sel; n_slots = n_sel;
     }
   }
-  *n_out = n_sel;
   if (n_sel == 0) return MB2_OK;
   if (n_sel > out_cap) { ctx->set_error("mser: output capacity too small"); return MB2_ERR_CAPACITY; }
   // reference list order (polarity, birth level, promotion time, threshold rank)
@@ -636,9 +647,9 @@ int mser_both(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, doub
   MB2_LAUNCH(ctx, k_mser_selkeys, (n_sel + 255) / 256, 256, 0, B.sel.as<SelRec>(), (uint32_t)n_sel, B.selkey_a.as<u64>(), B.selidx_a.as<uint32_t>());
   {
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 49, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 52, st);
     MB2_CUDA_CHECK(ctx, B.cub_tmp.reserve(tmp));
-    cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 49, st);
+    cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, B.selkey_a.as<u64>(), B.selkey_b.as<u64>(), B.selidx_a.as<uint32_t>(), B.selidx_b.as<uint32_t>(), n_sel, 0, 52, st);
     ctx->launches += 4;
   }
   // 5. runs of the selected components
@@ -676,7 +687,9 @@ int mser_both(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, doub
   MB2_CUDA_CHECK(ctx, B.mom.reserve((size_t)n_slots * sizeof(SlotMoments)));
   MB2_LAUNCH(ctx, k_mser_moments, (n_slots + 63) / 64, 64, 0, B.ev_c.as<u64>(), B.ev_d.as<u64>(), n_runs, (uint32_t)n_slots, B.mom.as<SlotMoments>());
   MB2_LAUNCH(ctx, k_mser_keys, (n_sel + 127) / 128, 128, 0, B.sel.as<SelRec>(), B.selidx_b.as<uint32_t>(), (uint32_t)n_sel, B.mom.as<SlotMoments>(), slot_of_node,
-             Nimg, as_regions, d_out, d_table);
+             Nimg, as_regions, d_out, d_table, &dC->n_img[0]);
+  MSER_SYNC_COUNTERS();
+  for (int k = 0; k < K; k++) n_per_img[k] = (int)hc->n_img[k];
   return MB2_OK;
 }
 
@@ -701,7 +714,7 @@ int mb2_mser_core(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, 
   MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)cap * sizeof(KeyOut)));
   int rc;
   const bool sort_on_host = par.mode != 0;
-  if ((rc = mser_both(ctx, img, par, min_margin, sort_on_host ? 0 : as_regions, ctx->kp_b.as<KeyOut>(), cap, n_out, d_table_out))) return rc;
+  if ((rc = mser_stack(ctx, &img, 1, par, min_margin, sort_on_host ? 0 : as_regions, ctx->kp_b.as<KeyOut>(), cap, n_out, d_table_out))) return rc;
   if (sort_on_host && *n_out > 0) {
     // prepareKeysForExport (extrema.cpp:31-90): the reference's own (unstable) std::sort decides the order of equal margins,
     // so this step runs through the same library routine on the host.
@@ -741,4 +754,21 @@ int mb2_mser_core(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, 
     }
   }
   return MB2_OK;
+}
+
+// Two same-size images in one pass (FIXED_TH): the level-synchronous tree kernel is latency bound, so a pair costs
+// hardly more than one image.  Keys of image 0 then image 1 in ctx->kp_b.
+int mb2_mser_core_pair(mb2_ctx* ctx, const ImgView& img1, const ImgView& img2, const mb2_mser_params& par, int as_regions, int* n1, int* n2) {
+  using namespace MB2_NS;
+  *n1 = *n2 = 0;
+  if (par.min_size < 2 || par.relative || par.mode != 0) { ctx->set_error("mser pair: FIXED_TH, absolute margins, min_size >= 2 only"); return MB2_ERR_UNSUPPORTED; }
+  if (img1.cols != img2.cols || img1.rows != img2.rows) { ctx->set_error("mser pair: images must have the same size"); return MB2_ERR_ARG; }
+  if (img1.cols > 65535 || img1.rows > 65535 || (long long)img1.cols * img1.rows >= (1LL << 29)) { ctx->set_error("mser: image too large"); return MB2_ERR_ARG; }
+  const int cap = (int)std::min<long long>((long long)img1.cols * img1.rows / 8 + 8192, 8000000);
+  MB2_CUDA_CHECK(ctx, ctx->kp_b.reserve((size_t)cap * sizeof(KeyOut)));
+  const ImgView imgs[2] = {img1, img2};
+  int n[2] = {0, 0};
+  const int rc = mser_stack(ctx, imgs, 2, par, par.min_margin, as_regions, ctx->kp_b.as<KeyOut>(), cap, n, nullptr);
+  *n1 = n[0]; *n2 = n[1];
+  return rc;
 }

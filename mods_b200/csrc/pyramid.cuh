@@ -87,4 +87,5 @@ void mb2_launch_reproject(mb2_ctx* ctx, const KeyOut* det, int n, const double* 
 // mser.cu: MSER+ / MSER- keys of the device image -> ctx->kp_b (reference order)
 int mb2_mser_core(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, double tilt, double zoom, int as_regions, int* n_out,
                   double* d_table_out, int capacity);
+int mb2_mser_core_pair(mb2_ctx* ctx, const ImgView& img1, const ImgView& img2, const mb2_mser_params& par, int as_regions, int* n1, int* n2);
 void mb2_mser_release(mb2_ctx* ctx);

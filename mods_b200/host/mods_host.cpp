@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <condition_variable>
@@ -132,6 +134,21 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
       }
     }
   }
+}
+
+void ImageRepresentation::AppendViewFrom(mb2_ctx* from, const std::string& det, const std::string& desc, int n, int synth) {
+  const descriptor_type dt = GetDescriptorType(desc);
+  if (dt == DESC_UNKNOWN || n < 0) return;
+  SlotState& ss = slot_state[det];
+  ss.desc = desc; ss.count += n;
+  RegionBlock& B = Blocks[det][desc];
+  B.det = GetDetectorType(det); B.desc = dt;
+  const size_t base = (size_t)B.n;
+  B.det_kp.resize((base + n) * MB2_KP); B.reproj_kp.resize((base + n) * MB2_KP); B.desc_u8.resize((base + n) * 128);
+  B.img_id.resize(base + n, synth);
+  if (n > 0 && mb2_view_fetch(from, &B.det_kp[base * MB2_KP], &B.reproj_kp[base * MB2_KP], &B.desc_u8[base * 128], n) < 0) n = 0;
+  B.n = (int)base + n;
+  B.det_kp.resize((size_t)B.n * MB2_KP); B.reproj_kp.resize((size_t)B.n * MB2_KP); B.desc_u8.resize((size_t)B.n * 128); B.img_id.resize(B.n);
 }
 
 // ---- matching ---------------------------------------------------------------------------------
@@ -474,9 +491,11 @@ extern "C" int mb2_host_duplicate_filter(const double* xy /* n x 4: x1 y1 x2 y2 
 namespace {
 // Helper contexts (own stream + scratch) kept per primary context, created on first use:
 //   [0] the second image of a pair (detected / described concurrently with the first),
-//   [1] verification (duplicate filter + LO-RANSAC) of pair k while pair k+1 is detected (mb2_mods_pairs).
+//   [1] verification (duplicate filter + LO-RANSAC) of pair k while pair k+1 is detected (mb2_mods_pairs),
+//   [2] the MSER pass of both images of a pair (one batched detection, mb2_mser_detect_pair), next to the two HessianAffine passes,
+//   [3] orientation + description of the second image's MSER regions while [2] does the first image's.
 std::mutex g_sib_mutex;
-struct Helpers { mb2_ctx* c[2] = {nullptr, nullptr}; bool tried[2] = {false, false}; };
+struct Helpers { mb2_ctx* c[4] = {nullptr, nullptr, nullptr, nullptr}; bool tried[4] = {false, false, false, false}; };
 std::unordered_map<mb2_ctx*, Helpers> g_siblings;
 mb2_ctx* sibling_ctx(mb2_ctx* ctx, int which = 0) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
@@ -560,12 +579,55 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
   out.rep1.reset(new ImageRepresentation(ctx, GrayImage{img1, h1, w1}, "img1", 0));
   out.rep2.reset(new ImageRepresentation(ctx2 ? ctx2 : ctx, GrayImage{img2, h2, w2}, "img2", 1));
   double t0 = now_ms();
+  // MSER of both images in ONE batched pass on a third context when the images have the same size (the component-tree
+  // kernel is latency bound: two images cost hardly more than one); otherwise per image, after HessianAffine.
+  mb2_ctx* ctx3 = (ctx2 && cfg->use_mser && w1 == w2 && h1 == h2) ? sibling_ctx(ctx, 2) : nullptr;
+  IterationViewsynthesisParam iters_here = ps.iters;
+  if (ctx3) {
+    iters_here.erase("MSER");
+    for (auto* r : {out.rep1.get(), out.rep2.get()}) { r->Prepare("HessianAffine", ps.desc_name); r->Prepare("MSER", ps.desc_name); }
+  }
+  int mser_rc = MB2_OK;
+  auto mser_post = [&](mb2_ctx* run, int which, int* rc_out) {   // orientation + description of one image's MSER regions
+    const double Hid[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    mb2_sift_params sp = cfg->desc.rootSIFT ? ps.desc_par.RootSIFTParam : ps.desc_par.SIFTParam;
+    mb2_orientation_params op{ps.dom.mrSize, ps.dom.patchSize, ps.dom.maxAngles, (double)ps.dom.threshold};
+    const int k = mb2_describe_view_of_pair(run, ctx3, which, Hid, w1, h1, &op, &sp, 2 + which, 0, nullptr, nullptr, nullptr, 0);
+    if (k < 0) { *rc_out = k; return; }
+    (which ? out.rep2 : out.rep1)->AppendViewFrom(run, "MSER", ps.desc_name, k, 0);
+  };
+  static const bool timing = getenv("MB2_PAIR_TIMING") != nullptr;   // diagnostics: where the front stage spends its time
+  double tm_detect = 0, tm_post = 0, th1 = 0, th2 = 0;
+  auto mser_pair = [&] {
+    int n1 = 0, n2 = 0;
+    const double ta = now_ms();
+    if ((mser_rc = mb2_mser_detect_pair(ctx3, img1, img2, w1, h1, &ps.det_par.MSERParam, &n1, &n2)) < 0) return;
+    tm_detect = now_ms() - ta;
+    struct PostTimer { double& t; double t0; ~PostTimer() { t = now_ms() - t0; } } post_timer{tm_post, now_ms()};
+    mser_rc = MB2_OK;
+    // the two images are finished side by side: image 1 here, image 2 on a fourth context
+    mb2_ctx* ctx4 = sibling_ctx(ctx, 3);
+    int rc2 = MB2_OK;
+    if (ctx4) {
+      std::thread t2([&] { mser_post(ctx4, 1, &rc2); });
+      mser_post(ctx3, 0, &mser_rc);
+      t2.join();
+      if (rc2 < 0) mser_rc = rc2;
+      if (mser_rc >= 0 && mb2_slot_move(ctx3, 3, ctx4, 3) < 0) mser_rc = MB2_ERR_CUDA;
+    } else { mser_post(ctx3, 0, &mser_rc); if (mser_rc >= 0) mser_post(ctx3, 1, &mser_rc); }
+  };
   if (ctx2) {
-    std::thread th([&] { out.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom); });
-    out.rep1->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
+    std::thread th([&] { const double ta = now_ms(); out.rep2->SynthDetectDescribeKeypoints(iters_here, ps.det_par, ps.desc_par, ps.dom); th2 = now_ms() - ta; });
+    std::thread tm;
+    if (ctx3) tm = std::thread(mser_pair);
+    { const double ta = now_ms(); out.rep1->SynthDetectDescribeKeypoints(iters_here, ps.det_par, ps.desc_par, ps.dom); th1 = now_ms() - ta; }
     th.join();
+    if (ctx3) tm.join();
+    if (timing) fprintf(stderr, "[pair front] hessaff img1 %.1f ms, img2 %.1f ms | mser detect (both) %.1f ms, orient+describe %.1f ms\n", th1, th2, tm_detect, tm_post);
+    if (mser_rc < 0) { out.rc = mser_rc; return; }
     if (mb2_slot_move(ctx, 1, ctx2, 1) < 0) { out.rc = MB2_ERR_CUDA; return; }
-    if (cfg->use_mser && mb2_slot_move(ctx, 3, ctx2, 3) < 0) { out.rc = MB2_ERR_CUDA; return; }
+    if (ctx3) { if (mb2_slot_move(ctx, 2, ctx3, 2) < 0 || mb2_slot_move(ctx, 3, ctx3, 3) < 0) { out.rc = MB2_ERR_CUDA; return; } }
+    else if (cfg->use_mser && mb2_slot_move(ctx, 3, ctx2, 3) < 0) { out.rc = MB2_ERR_CUDA; return; }
   } else {
     out.rep1->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
     out.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);

@@ -113,6 +113,12 @@ class ImageRepresentation {
   AffineRegionVector GetAffineRegionVector(std::string desc_name, std::string det_name) const;
   void SynthDetectDescribeKeypoints(IterationViewsynthesisParam& synth_par, DetectorsParameters& det_par,
                                     DescriptorsParameters& desc_par, DominantOrientationParams& dom_ori_par);
+  // Appends the n regions of the most recent view pass of context `from` (still resident there) as view `synth` of
+  // (det, desc): what SynthDetectDescribeKeypoints does after every view, for passes the caller ran itself (the pair
+  // driver batches the MSER detection of both images, mb2_mser_detect_pair).
+  // creates the (det, desc) entries up front, so that passes of different detectors may then fill them from different threads
+  void Prepare(const std::string& det, const std::string& desc) { Blocks[det][desc]; slot_state[det]; }
+  void AppendViewFrom(mb2_ctx* from, const std::string& det, const std::string& desc, int n, int synth);
   GrayImage OriginalImg;
   friend class CorrespondenceBank;
 

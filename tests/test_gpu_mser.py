@@ -167,3 +167,17 @@ def test_mods_pairs_with_mser_pipeline_equals_single_calls(ctx):
         for f in ("regions1", "regions2", "tentatives", "unique_tentatives", "ransac_inliers", "verified", "mser_regions1", "mser_tentatives"):
             assert getattr(r1, f) == getattr(r2, f), f
         assert r1.mser_regions1 > 0 and np.array_equal(v1, v2) and np.array_equal(np.array(r1.H[:]), np.array(r2.H[:]))
+
+
+def test_mser_pair_batch_equals_single_images(ctx):
+    """mb2_mser_detect_pair (both images of a pair in one stacked pass) + mb2_describe_view_of_pair == two single-image view passes."""
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(512, 384, seed=61, n_blobs=600)
+    B = warp_image(A, gt_homography(512, 384), seed=62)
+    (d1, r1, u1), (d2, r2, u2) = ctx.mser_pair_views(A, B, slots=(4, 5))
+    s1 = ctx.detect_describe_view(A, det=mb.MserParams.default(), slot=2)
+    s2 = ctx.detect_describe_view(B, det=mb.MserParams.default(), slot=3)
+    assert len(d1) > 50 and len(d2) > 50
+    for got, want in (((d1, r1, u1), s1), ((d2, r2, u2), s2)):
+        assert all(np.array_equal(g, w) for g, w in zip(got, want))
+    assert np.array_equal(ctx.match_slots(4, 5), ctx.match_slots(2, 3))
