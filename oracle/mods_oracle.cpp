@@ -243,6 +243,40 @@ int orc_view_pipeline(const float* img, int w, int h, int detector, const HessPa
   return n;
 }
 
+int orc_synth_view(const float* img, int w, int h, double tilt, double phi, double zoom, double InitSigma, int doBlur,
+                   float* out, int capacity, int* ow, int* oh, double* H) {
+  SynthView v;
+  generateSynthImage(image_in(img, w, h), tilt, phi, zoom, InitSigma, doBlur, v);
+  *ow = v.pixels.cols; *oh = v.pixels.rows;
+  for (int i = 0; i < 9; i++) H[i] = v.H[i];
+  if ((size_t)*ow * *oh <= (size_t)capacity) std::memcpy(out, v.pixels.px.data(), sizeof(float) * (size_t)*ow * *oh);
+  return v.identity ? 1 : 0;
+}
+int orc_view_pipeline_synth(const float* img, int w, int h, int detector, const HessParamsC* hp, double mser_max_area, int mser_min_size,
+                            double mser_min_margin, double ori_mrSize, int ori_patch, int maxAngles, double ori_th, double desc_mrSize,
+                            int desc_patch, int photoNorm, int rootsift, double tilt, double phi, double zoom, double InitSigma, int doBlur,
+                            double* det_out, double* reproj_out, float* desc_out, int max_out) {
+  SynthView v;
+  generateSynthImage(image_in(img, w, h), tilt, phi, zoom, InitSigma, doBlur, v);
+  const Image& im = v.pixels;
+  std::vector<Key> kp1;
+  if (detector == 0) kp1 = detectAffineKeypoints(im, to_par(*hp), v.tilt, v.zoom);
+  else {
+    mser::Params mp; mp.max_area = mser_max_area; mp.min_size = mser_min_size; mp.min_margin = mser_min_margin;
+    for (const mser::MKey& k : mser::detectMSERs(im.px.data(), im.cols, im.rows, mp, v.tilt, v.zoom))
+      kp1.push_back(Key{k.x, k.y, k.a11, k.a12, k.a21, k.a22, k.s, k.response, k.sub_type});
+  }
+  toRegions(kp1);
+  std::vector<Key> det = detectOrientation(kp1, im, ori_mrSize, ori_patch, maxAngles, ori_th), rep;
+  reprojectRegions(det, rep, v.H, w, h, 0, 0);
+  int n = (int)det.size();
+  if (n > max_out) return -n;
+  SIFTDescriptor D(desc_patch, rootsift != 0);
+  describeRegions(det, im, D, desc_mrSize, desc_patch, false, photoNorm != 0, desc_out);
+  for (int i = 0; i < n; i++) { kp_out(det[i], det_out + (size_t)i * KP); kp_out(rep[i], reproj_out + (size_t)i * KP); }
+  return n;
+}
+
 // which: 0 HDs, 1 HDsSym, 2 HDsSymMax, 3 FDs, 4 FDsSym
 void orc_score(int which, const double* u, const double* M, double* d, int len) {
   switch (which) {

@@ -556,6 +556,63 @@ inline void toRegions(std::vector<Key>& keys) {
 }
 
 // ------------------------------------------------------------------------------------------
+// synth-detection.cpp:236-430  GenerateSynthImageCorr (gray input; the (B+G+R)/3 conversion is the caller's)
+// ------------------------------------------------------------------------------------------
+struct SynthView { Image pixels; double H[9]; double tilt, zoom, rotation; bool identity; };
+inline void generateSynthImage(const Image& in, double tilt, double phi, double zoom, double InitSigma, int doBlur, SynthView& out) {
+  bool vertical_tilt = false;
+  if (tilt < 0) { tilt = -tilt; vertical_tilt = true; }
+  const int zoomed = std::fabs(zoom - 1.0f) >= 0.05 ? 1 : 0;
+  const int w = in.cols, h = in.rows;
+  const int wS1 = (int)(w * zoom), hS1 = (int)(h * zoom);
+  for (int i = 0; i < 9; i++) out.H[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  out.identity = false;
+  if ((std::fabs(tilt - 1.) <= 0.1) && (std::fabs(phi) <= 0.2) && (std::fabs(zoom - 1.) <= 0.1)) {   // :278 (abs is std::abs(double): `using namespace std`, :30)
+    out.rotation = 0; out.tilt = 1; out.zoom = 1; out.pixels = in; out.identity = true;
+    return;
+  }
+  double d, d2, w_new, h_new, kV = 1., kH = 1.;
+  if (zoomed) { kV = (double)w / (double)wS1; kH = (double)h / (double)hS1; }
+  const double c = std::cos(phi), s = std::sin(phi);
+  const bool q1 = (phi >= 0) && (phi < M_PI / 2);
+  const double sx = vertical_tilt ? kH : tilt * kH, sy = vertical_tilt ? tilt * kV : kV;   // :301-342
+  if (q1) {
+    w_new = std::floor((0.5 + c * w + s * h) / sx); h_new = std::floor((0.5 + s * w + c * h) / sy);
+    out.H[0] = c / sx; out.H[1] = s / sx; out.H[2] = 0;
+    out.H[3] = -s / sy; out.H[4] = c / sy; out.H[5] = std::floor(0.5 + s * w / sy);
+  } else {
+    w_new = std::floor((0.5 - c * w + s * h) / sx); h_new = std::floor((0.5 + s * w - c * h) / sy);
+    d = -std::floor(c * w / sx); d2 = std::floor(0.5 + (s * w - c * h) / sy);
+    out.H[0] = c / sx; out.H[1] = s / sx; out.H[2] = d;
+    out.H[3] = -s / sy; out.H[4] = c / sy; out.H[5] = d2;
+  }
+  out.H[6] = 0; out.H[7] = 0; out.H[8] = 1;
+  out.rotation = phi * 180 / M_PI; out.tilt = tilt; out.zoom = zoom;
+  const double sigma_aa_2 = zoomed ? InitSigma / (4.0 * zoom) : InitSigma / 2.0;
+  const double sigma_aa = InitSigma * tilt / (2.0 * zoom);
+  const double sigma_x = vertical_tilt ? sigma_aa_2 : sigma_aa, sigma_y = vertical_tilt ? sigma_aa : sigma_aa_2;
+  int w_new_rot, h_new_rot; double warpRot[6];
+  if (q1) {
+    w_new_rot = (int)std::floor(0.5 + c * w + s * h); h_new_rot = (int)std::floor(0.5 + s * w + c * h);
+    warpRot[0] = c; warpRot[1] = s; warpRot[2] = 0; warpRot[3] = -s; warpRot[4] = c; warpRot[5] = std::floor(0.5 + s * w);
+  } else {
+    w_new_rot = (int)std::floor(0.5 - c * w + s * h); h_new_rot = (int)std::floor(0.5 + s * w - c * h);
+    d = -std::floor(c * w); d2 = std::floor(0.5 + (s * w - c * h));
+    warpRot[0] = c; warpRot[1] = s; warpRot[2] = d; warpRot[3] = -s; warpRot[4] = c; warpRot[5] = d2;
+  }
+  Image rot(h_new_rot, w_new_rot);
+  cvmath::warp_affine_linear(in.px.data(), h, w, warpRot, rot.px.data(), h_new_rot, w_new_rot, 128.f);   // :385
+  if (doBlur) {                                                                                               // :398-412
+    int kx = (int)std::floor(2.0 * 3.0 * sigma_x + 1.0); if (kx % 2 == 0) kx++; if (kx < 3) kx = 3;
+    int ky = (int)std::floor(2.0 * 3.0 * sigma_y + 1.0); if (ky % 2 == 0) ky++; if (ky < 3) ky = 3;
+    cvmath::sep_filter_reflect101(rot.px.data(), rot.px.data(), rot.rows, rot.cols, cvmath::gauss_kernel(kx, sigma_x), cvmath::gauss_kernel(ky, sigma_y));
+  }
+  const double wtz[6] = {1.0 / sx, 0, 0, 0, 1.0 / sy, 0};                                                    // :415-427
+  out.pixels = Image((int)h_new, (int)w_new);
+  cvmath::warp_affine_linear(rot.px.data(), rot.rows, rot.cols, wtz, out.pixels.px.data(), (int)h_new, (int)w_new, 128.f);
+}
+
+// ------------------------------------------------------------------------------------------
 // synth-detection.cpp: orientation, reprojection;  synth-detection.hpp: DescribeRegions
 // ------------------------------------------------------------------------------------------
 const double k_sigma_sd = 2 * 3.0 * 1.7320508075688772;  // synth-detection.cpp:28  (2*3*sqrt(3))

@@ -134,6 +134,28 @@ class Lib:
         assert 0 <= n <= max_out, n
         return det[:n].copy(), rep[:n].copy(), d[:n].copy()
 
+    def synth_view(self, img, tilt, phi, zoom, InitSigma=0.5, doBlur=1):
+        """GenerateSynthImageCorr: returns (pixels, H, is_identity)."""
+        img = _f32(img); h, w = img.shape
+        cap = int((w + h) ** 2 * max(1.0, zoom) ** 2) + 16
+        out = np.zeros(cap, np.float32); ow, oh = C.c_int(), C.c_int(); H = np.zeros(9)
+        ident = self.fn("synth_view")(_p(img), C.c_int(w), C.c_int(h), C.c_double(tilt), C.c_double(phi), C.c_double(zoom), C.c_double(InitSigma),
+                                      C.c_int(doBlur), _p(out), C.c_int(cap), C.byref(ow), C.byref(oh), _p(H))
+        return out[: ow.value * oh.value].reshape(oh.value, ow.value).copy(), H.reshape(3, 3), bool(ident)
+
+    def view_pipeline_synth(self, img, tilt, phi, zoom, detector=0, hp=None, mser=(0.05, 30, 8.0), ori=(1.0, 41, 1, 0.8),
+                            desc=(5.1962, 41, True, True), InitSigma=0.5, doBlur=1, max_out=400000):
+        img = _f32(img); hp = hp or HessParams.default()
+        det = np.zeros((max_out, KP)); rep = np.zeros((max_out, KP)); d = np.zeros((max_out, 128), np.float32)
+        n = self.fn("view_pipeline_synth")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(detector), C.byref(hp),
+                                           C.c_double(mser[0]), C.c_int(mser[1]), C.c_double(mser[2]),
+                                           C.c_double(ori[0]), C.c_int(ori[1]), C.c_int(ori[2]), C.c_double(ori[3]),
+                                           C.c_double(desc[0]), C.c_int(desc[1]), C.c_int(int(desc[2])), C.c_int(int(desc[3])),
+                                           C.c_double(tilt), C.c_double(phi), C.c_double(zoom), C.c_double(InitSigma), C.c_int(doBlur),
+                                           _p(det), _p(rep), _p(d), C.c_int(max_out))
+        assert 0 <= n <= max_out, n
+        return det[:n].copy(), rep[:n].copy(), d[:n].copy()
+
     # ---- matching / verification
     def score(self, which, u, M):
         u = _f64(u); M = _f64(M).ravel(); n = len(u)

@@ -278,6 +278,57 @@ int ref_view_pipeline(const float* img, int w, int h, int detector, const HessPa
   return n;
 }
 
+// ---- view synthesis (synth-detection.cpp:236-430) ----------------------------------------------------
+// out: pixels of the synthesised view (capacity floats), its size and H (original -> view).  Returns 1 for the identity view.
+int ref_synth_view(const float* img, int w, int h, double tilt, double phi, double zoom, double InitSigma, int doBlur,
+                   float* out, int capacity, int* ow, int* oh, double* H) {
+  cv::Mat in(h, w, CV_32FC1);
+  std::memcpy(in.data, img, sizeof(float) * (size_t)w * h);
+  SynthImage view;
+  GenerateSynthImageCorr(in, view, "img", tilt, phi, zoom, InitSigma, doBlur, 1, false);
+  *ow = view.pixels.cols; *oh = view.pixels.rows;
+  for (int i = 0; i < 9; i++) H[i] = view.H[i];
+  if ((size_t)*ow * *oh <= (size_t)capacity)
+    for (int r = 0; r < *oh; r++) std::memcpy(out + (size_t)r * *ow, view.pixels.ptr<float>(r), sizeof(float) * *ow);
+  return view.id == 0 ? 1 : 0;
+}
+// One (detector, view) pass of SynthDetectDescribeKeypoints for a synthesised view (imagerepresentation.cpp:621-1341)
+int ref_view_pipeline_synth(const float* img, int w, int h, int detector, const HessParamsC* hp,
+                            double mser_max_area, int mser_min_size, double mser_min_margin,
+                            double ori_mrSize, int ori_patch, int maxAngles, double ori_th,
+                            double desc_mrSize, int desc_patch, int photoNorm, int rootsift,
+                            double tilt, double phi, double zoom, double InitSigma, int doBlur,
+                            double* det_out, double* reproj_out, float* desc_out, int max_out) {
+  cv::Mat in(h, w, CV_32FC1);
+  std::memcpy(in.data, img, sizeof(float) * (size_t)w * h);
+  SynthImage view;
+  GenerateSynthImageCorr(in, view, "img", tilt, phi, zoom, InitSigma, doBlur, 1, false);
+  AffineRegionList kp1;
+  if (detector == 0) {
+    ScaleSpaceDetectorParams sp = to_ref(*hp);
+    DetectAffineRegions(view, kp1, sp, DET_HESSIAN, DetectAffineKeypoints);
+  } else {
+    extrema::ExtremaParams ep;
+    ep.max_area = mser_max_area; ep.min_size = mser_min_size; ep.min_margin = mser_min_margin;
+    DetectAffineRegions(view, kp1, ep, DET_MSER, DetectMSERs);
+  }
+  AffineRegionList oriented;
+  DetectOrientation(kp1, oriented, view, ori_mrSize, ori_patch, false, maxAngles, ori_th, false);
+  AffineRegionList desc_list = oriented;
+  ReprojectRegions(desc_list, view.H, w, h);
+  SIFTDescriptorParams sp;
+  sp.useRootSIFT = rootsift; sp.PEParam.patchSize = desc_patch; sp.PEParam.mrSize = desc_mrSize;
+  SIFTDescriptor D(sp);
+  DescribeRegions(desc_list, view, D, desc_mrSize, desc_patch, false, photoNorm != 0);
+  int n = (int)desc_list.size();
+  for (int i = 0; i < n && i < max_out; i++) {
+    kp_out(desc_list[i].det_kp, det_out + (size_t)i * KP);
+    kp_out(desc_list[i].reproj_kp, reproj_out + (size_t)i * KP);
+    for (int j = 0; j < 128; j++) desc_out[(size_t)i * 128 + j] = desc_list[i].desc.vec[j];
+  }
+  return n;
+}
+
 // ---- DEGENSAC ------------------------------------------------------------------------------
 void ref_set_seed(long s) { mb2_ref_seed = s; }
 void ref_lin_hg(const double* u, double* Z, int len) {

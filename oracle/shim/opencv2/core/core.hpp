@@ -184,12 +184,13 @@ inline void SVDecomp(const Mat&, Mat&, Mat&, Mat&, int = 0) { shim_unsupported("
 inline void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0,
                          int borderType = BORDER_DEFAULT) {
   if (src.depth() != CV_32F || src.channels() != 1) shim_unsupported("GaussianBlur type");
-  if (borderType != BORDER_REPLICATE) shim_unsupported("GaussianBlur border (view synthesis is SURVEY 8f-1, not built yet)");
+  if (borderType != BORDER_REPLICATE && borderType != BORDER_REFLECT_101) shim_unsupported("GaussianBlur border");
   if (sigmaY <= 0) sigmaY = sigmaX;
   Mat out = (dst.data == src.data) ? src : Mat(src.rows, src.cols, src.type());
   std::vector<float> kx = cvmath::gauss_kernel(ksize.width, sigmaX);
   std::vector<float> ky = cvmath::gauss_kernel(ksize.height, sigmaY);
-  cvmath::sep_filter((const float*)src.data, (float*)out.data, src.rows, src.cols, kx, ky);
+  if (borderType == BORDER_REPLICATE) cvmath::sep_filter((const float*)src.data, (float*)out.data, src.rows, src.cols, kx, ky);
+  else cvmath::sep_filter_reflect101((const float*)src.data, (float*)out.data, src.rows, src.cols, kx, ky);
   dst = out;
 }
 
@@ -211,8 +212,13 @@ inline double invert(const Mat& src, Mat& dst, int = DECOMP_LU) {
   return ok ? 1.0 : 0.0;
 }
 
-inline void warpAffine(const Mat&, Mat&, const Mat&, Size, int = INTER_LINEAR, int = BORDER_CONSTANT, const Scalar& = Scalar()) {
-  shim_unsupported("warpAffine (view synthesis is SURVEY 8f-1, not built yet)");
+inline void warpAffine(const Mat& src, Mat& dst, const Mat& M, Size dsize, int flags = INTER_LINEAR, int border = BORDER_CONSTANT,
+                       const Scalar& bv = Scalar()) {
+  if (src.depth() != CV_32F || src.channels() != 1 || flags != INTER_LINEAR || border != BORDER_CONSTANT || M.depth() != CV_64F)
+    shim_unsupported("warpAffine other than CV_32FC1 / INTER_LINEAR / BORDER_CONSTANT");
+  Mat out(dsize.height, dsize.width, src.type());
+  cvmath::warp_affine_linear((const float*)src.data, src.rows, src.cols, (const double*)M.data, (float*)out.data, dsize.height, dsize.width, (float)bv.val[0]);
+  dst = out;
 }
 inline void warpPerspective(const Mat&, Mat&, const Mat&, Size, int = INTER_LINEAR, int = BORDER_CONSTANT, const Scalar& = Scalar()) {
   shim_unsupported("warpPerspective");

@@ -126,3 +126,22 @@ def test_mser_view_pipeline(oracle, reference):
     im = synth.blob_image(400, 300, seed=21)
     a, b = oracle.view_pipeline(im, detector=3), reference.view_pipeline(im, detector=3)
     assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 50
+
+
+# ---- view synthesis (row a2)
+@pytest.mark.parametrize("view", [(2, 0.0, 1.0), (2, 0.7, 1.0), (4, 2.2, 1.0), (1, 0.0, 0.5), (6, 1.2, 0.25), (-2, 0.5, 1.0), (1, 0.0, 1.0), (9, 3.0, 1.0)])
+def test_synth_view(oracle, reference, view):
+    """GenerateSynthImageCorr (synth-detection.cpp:236-430): size, H and pixels of the synthesised view."""
+    im = synth.blob_image(320, 240, seed=5)
+    a, Ha, ia = oracle.synth_view(im, *view)
+    b, Hb, ib = reference.synth_view(im, *view)
+    assert a.shape == b.shape and np.array_equal(a, b) and np.array_equal(Ha, Hb) and ia == ib
+
+
+@pytest.mark.parametrize("detector", [0, 3])
+def test_view_pipeline_synth(oracle, reference, detector):
+    im = synth.blob_image(400, 300, seed=21)
+    for view in ((2, 0.6, 1.0), (4, 2.0, 1.0), (1, 0.0, 0.5)):
+        a = oracle.view_pipeline_synth(im, *view, detector=detector)
+        b = reference.view_pipeline_synth(im, *view, detector=detector)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 5
