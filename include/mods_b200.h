@@ -65,6 +65,13 @@ typedef struct {
   float rel_reg_number;
 } mb2_mser_params;
 
+/* One synthesised view == ViewSynthParameters (detectors/structures.hpp:198-211) as passed to GenerateSynthImageCorr
+ * (synth-detection.cpp:236-245): tilt (< 0: vertical tilt), rotation phi in radians, zoom, anti-aliasing InitSigma. */
+typedef struct {
+  double tilt, phi, zoom, InitSigma;   /* 1, 0, 1, 0.5 */
+  int doBlur;                          /* 1 */
+} mb2_view_params;
+
 /* [DominantOrientation] (descriptors_parameters.hpp) as passed to DetectOrientation
  * (synth-detection.cpp:841-849). */
 typedef struct {
@@ -171,6 +178,22 @@ int mb2_mser_detect_pair(mb2_ctx* ctx, const float* pixels1, const float* pixels
 int mb2_describe_view_of_pair(mb2_ctx* ctx, mb2_ctx* src, int which, const double* H, int orig_w, int orig_h,
                               const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot, int append,
                               double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
+
+/* Replaces `void GenerateSynthImageCorr(const cv::Mat& in, SynthImage& out, name, tilt, phi, zoom, InitSigma, doBlur, img_id,
+ * convert2gray)` (synth-detection.cpp:236-430) for a gray f32 image [H|D]: rotation warp (border 128) -> anisotropic
+ * anti-aliasing blur -> tilt / zoom warp, with OpenCV 2.4.9's fixed-point bilinear warpAffine.  out (optional, [H]):
+ * capacity floats, receives the view row-major when it fits; *ow, *oh its size; H9 = SynthImage::H (original -> view).
+ * Returns 1 for the identity view (pixels untouched), 0 otherwise. */
+int mb2_synth_view(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_view_params* view, float* out, int capacity,
+                   int* ow, int* oh, double* H9);
+/* One (detector, view) pass of SynthDetectDescribeKeypoints for an arbitrary view (imagerepresentation.cpp:621-1341):
+ * GenerateSynthImageCorr -> detect on the view (detector 0 = HessianAffine with `hess`, 3 = MSER with `mser`) ->
+ * DetectOrientation -> ReprojectRegions to the original frame (regions leaving the original image are dropped) ->
+ * DescribeRegions on the view.  Outputs and slot semantics as mb2_detect_describe_view. */
+int mb2_detect_describe_synth_view(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_view_params* view, int detector,
+                                   const mb2_hessaff_params* hess, const mb2_mser_params* mser,
+                                   const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot, int append,
+                                   double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
 
 /* Copies the regions of the most recent mb2_detect_describe_view (which may be called with NULL
  * outputs to learn the count first) to the host.  Returns that count. */

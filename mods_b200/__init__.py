@@ -18,7 +18,7 @@ EXPORTS = [
     "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
     "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
-    "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair",
+    "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair", "mb2_synth_view", "mb2_detect_describe_synth_view",
 ]
 
 
@@ -47,6 +47,11 @@ class MserParams(C.Structure):
     @staticmethod
     def default():
         return MserParams(0.05, 30, 8.0, 0, 0, -1, -1.0, -1.0)
+
+
+class ViewParams(C.Structure):
+    """mb2_view_params == one ViewSynthParameters entry (tilt, rotation phi [rad], zoom, InitSigma, doBlur)."""
+    _fields_ = [("tilt", C.c_double), ("phi", C.c_double), ("zoom", C.c_double), ("InitSigma", C.c_double), ("doBlur", C.c_int)]
 
 
 class OrientationParams(C.Structure):
@@ -288,6 +293,35 @@ class Context:
         n = self._check(fn(self.h, _ptr(img), C.c_int(w), C.c_int(h), _ptr(H), C.c_int(ow), C.c_int(oh),
                            C.byref(det), C.byref(ori), C.byref(desc), C.c_int(slot), C.c_int(int(append)),
                            _ptr(dk), _ptr(rk), _ptr(du), C.c_int(capacity)), "detect_describe_view")
+        if want_host:
+            return dk[:n].copy(), rk[:n].copy(), du[:n].copy()
+        return n
+
+    def synth_view(self, img, tilt, phi, zoom, InitSigma=0.5, doBlur=1, shape=None):
+        """GenerateSynthImageCorr on the GPU: returns (pixels, H, is_identity)."""
+        h, w = shape if shape is not None else img.shape
+        vp = ViewParams(tilt, phi, zoom, InitSigma, doBlur)
+        cap = int((w + h) ** 2 * max(1.0, zoom) ** 2) + 16
+        out = np.zeros(cap, np.float32); ow, oh = C.c_int(), C.c_int(); H = np.zeros(9)
+        ident = self._check(lib().mb2_synth_view(self.h, _ptr(img), C.c_int(w), C.c_int(h), C.byref(vp), _ptr(out), C.c_int(cap), C.byref(ow),
+                                                 C.byref(oh), _ptr(H)), "synth_view")
+        return out[: ow.value * oh.value].reshape(oh.value, ow.value).copy(), H.reshape(3, 3), bool(ident)
+
+    def detect_describe_synth_view(self, img, tilt, phi, zoom, det=None, ori=None, desc=None, slot=0, append=False, capacity=None,
+                                   InitSigma=0.5, doBlur=1, shape=None, want_host=True):
+        h, w = shape if shape is not None else img.shape
+        vp = ViewParams(tilt, phi, zoom, InitSigma, doBlur)
+        det = det or HessaffParams.default(); ori = ori or OrientationParams.default(); desc = desc or SiftParams.default()
+        is_mser = isinstance(det, MserParams)
+        capacity = capacity or max(4096, (h * w) // 16)
+        if want_host:
+            dk = np.zeros((capacity, KP)); rk = np.zeros((capacity, KP)); du = np.zeros((capacity, 128), np.uint8)
+        else:
+            dk = rk = du = None
+        n = self._check(lib().mb2_detect_describe_synth_view(self.h, _ptr(img), C.c_int(w), C.c_int(h), C.byref(vp), C.c_int(3 if is_mser else 0),
+                                                             None if is_mser else C.byref(det), C.byref(det) if is_mser else None,
+                                                             C.byref(ori), C.byref(desc), C.c_int(slot), C.c_int(int(append)),
+                                                             _ptr(dk), _ptr(rk), _ptr(du), C.c_int(capacity)), "detect_describe_synth_view")
         if want_host:
             return dk[:n].copy(), rk[:n].copy(), du[:n].copy()
         return n

@@ -649,7 +649,7 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->img, &ctx->pyr, &ctx->resp, &ctx->cand, &ctx->misc, &ctx->kp_a, &ctx->kp_b, &ctx->kp_c, &ctx->desc_u8,
                     &ctx->patch_scratch, &ctx->nn_a, &ctx->nn_b, &ctx->nn_c, &ctx->nn_d, &ctx->rs_a, &ctx->rs_b, &ctx->rs_c, &ctx->rs_u, &ctx->octmap,
-                    &ctx->img2, &ctx->pair_keys};
+                    &ctx->img2, &ctx->pair_keys, &ctx->synth_a, &ctx->synth_b, &ctx->synth_c, &ctx->synth_k};
   for (DevBuf* b : bufs) b->release();
   for (auto& s : ctx->slots) { s.desc.release(); s.xy.release(); }
   ctx->h_a.release(); ctx->h_b.release(); ctx->h_c.release();
@@ -868,6 +868,41 @@ int mb2_detect_describe_view_mser(mb2_ctx* ctx, const float* pixels, int w, int 
                                   int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
   if (!det) return MB2_ERR_ARG;
   return view_core(ctx, pixels, w, h, H, orig_w, orig_h, nullptr, det, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
+}
+
+int mb2_synth_view(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_view_params* view, float* out, int capacity, int* ow, int* oh,
+                   double* H9) {
+  if (!ctx || !pixels || !view || !ow || !oh || !H9 || w <= 0 || h <= 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView img, v;
+  int rc;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  const int ident = mb2_synth_core(ctx, img, *view, &v, H9);
+  if (ident < 0) return ident;
+  *ow = v.cols; *oh = v.rows;
+  if (out && (long long)v.cols * v.rows <= capacity)
+    MB2_CUDA_CHECK(ctx, cudaMemcpy2DAsync(out, (size_t)v.cols * 4, v.p, (size_t)v.pitch * 4, (size_t)v.cols * 4, v.rows, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return ident;
+}
+int mb2_detect_describe_synth_view(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_view_params* view, int detector,
+                                   const mb2_hessaff_params* hess, const mb2_mser_params* mser, const mb2_orientation_params* ori,
+                                   const mb2_sift_params* desc, int slot, int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8,
+                                   int capacity) {
+  if (!ctx || !pixels || !view || !ori || !desc || slot < 0 || slot >= MB2_MAX_SLOTS || (detector == 0 && !hess) || (detector == 3 && !mser) ||
+      (detector != 0 && detector != 3))
+    return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  ImgView img, v;
+  int rc, n = 0;
+  double H[9];
+  ctx->last_view_n = 0;
+  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  if ((rc = mb2_synth_core(ctx, img, *view, &v, H)) < 0) return rc;
+  const double tilt = std::fabs(view->tilt), zoom = view->zoom;   // SynthImage::tilt / zoom as DetectAffineRegions passes them on
+  if (detector == 0) { if ((rc = detect_core(ctx, v, *hess, tilt, zoom, 1, &n))) return rc; }
+  else if ((rc = mb2_mser_core(ctx, v, *mser, tilt, zoom, 1, &n, nullptr, 0))) return rc;
+  return view_post(ctx, v, n, H, w, h, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
 }
 
 int mb2_mser_detect_pair(mb2_ctx* ctx, const float* pixels1, const float* pixels2, int w, int h, const mb2_mser_params* par, int* n1, int* n2) {

@@ -83,6 +83,7 @@ struct mb2_ctx {
   std::vector<ProfRec> prof;
   void* mser_state = nullptr;   // MserBufs (mser.cu), released by mb2_mser_release
   DevBuf img2, pair_keys;       // mb2_mser_detect_pair: second image, keys of both images
+  DevBuf synth_a, synth_b, synth_c, synth_k;   // view synthesis: rotated image, view, blur scratch, taps
   int pair_n[2] = {0, 0}, pair_w = 0, pair_h = 0;
   unsigned long long prof_extract_bytes = 0;  // algorithmic gather bytes of the patch-extraction launches
   void set_error(const std::string& s) { err = s; }

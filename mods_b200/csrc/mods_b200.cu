@@ -7,5 +7,6 @@
 #include "nn.cu"
 #include "ransac.cu"
 #include "mser.cu"
+#include "synth.cu"
 #include "capi.cu"
 #include "ransac_host.cu"

@@ -89,3 +89,6 @@ int mb2_mser_core(mb2_ctx* ctx, const ImgView& img, const mb2_mser_params& par, 
                   double* d_table_out, int capacity);
 int mb2_mser_core_pair(mb2_ctx* ctx, const ImgView& img1, const ImgView& img2, const mb2_mser_params& par, int as_regions, int* n1, int* n2);
 void mb2_mser_release(mb2_ctx* ctx);
+
+// synth.cu: GenerateSynthImageCorr on the device; returns 1 for the identity view (out = in), 0 otherwise, < 0 on error
+int mb2_synth_core(mb2_ctx* ctx, const ImgView& in, const mb2_view_params& vp, ImgView* out, double* H);
