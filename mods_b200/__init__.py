@@ -387,6 +387,16 @@ class Context:
         results = [res[k] for k in range(n)]
         return results, ([outs[k][:min(results[k].verified, capacity)] for k in range(n)] if capacity else None)
 
+    def verify(self, frames14, keys, cfg=None, capacity=0):
+        """DuplicateFiltering + LORANSACFiltering of gathered tentatives (mb2_host_verify).  Returns (PairResult, verified rows)."""
+        cfg = cfg or PairConfig.default()
+        frames14 = np.ascontiguousarray(frames14, np.float64); keys = np.ascontiguousarray(keys, np.float64)
+        res = PairResult()
+        out = np.zeros((max(1, capacity), 4)) if capacity else None
+        n = self._check(host_lib().mb2_host_verify(self.h, _ptr(frames14), _ptr(keys), C.c_int(len(keys)), C.byref(cfg), C.byref(res), _ptr(out),
+                                                   C.c_int(capacity)), "host_verify")
+        return res, (out[:min(n, capacity)] if capacity else None)
+
     def ransac_h(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1):
         u = np.ascontiguousarray(u, np.float64)
         n = len(u)

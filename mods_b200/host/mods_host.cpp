@@ -44,6 +44,48 @@ DescriptorsParameters::DescriptorsParameters() {
   RootSIFTParam = mb2_sift_params{5.1962, 41, 1, 1, 0};
 }
 
+// ---- SetVSPars (synth-detection.cpp:103-234) --------------------------------------------------------
+int SetVSPars(const std::vector<double>& scale_set, const std::vector<double>& tilt_set, const double phi_base,
+              const std::vector<double>& FGINNThreshold, const std::vector<double>& DistanceThreshold,
+              const std::vector<std::string> descriptors, std::vector<ViewSynthParameters>& par, std::vector<ViewSynthParameters>& prev_par,
+              const double InitSigma, const int doBlur, const int dsplevels, const double minSigma, const double maxSigma) {
+  const double eps1 = 0.01;   // synth-detection.cpp:29
+  par.clear();
+  std::vector<ViewSynthParameters> pars_tmp;
+  auto make = [&](double phi, double tilt, double zoom, int blur) {
+    ViewSynthParameters t;
+    t.phi = phi; t.tilt = tilt; t.zoom = zoom; t.InitSigma = InitSigma; t.doBlur = blur; t.DSPlevels = dsplevels;
+    t.minSigma = minSigma; t.maxSigma = maxSigma; t.descriptors = descriptors;
+    for (size_t d = 0; d < descriptors.size(); d++) {
+      t.DistanceThreshold[descriptors[d]] = d < DistanceThreshold.size() ? DistanceThreshold[d] : 0;
+      t.FGINNThreshold[descriptors[d]] = d < FGINNThreshold.size() ? FGINNThreshold[d] : 0;
+    }
+    return t;
+  };
+  if (scale_set.empty() || tilt_set.empty()) pars_tmp.push_back(make(0, 0, 0, 0));   // :120-136
+  for (size_t sc = 0; sc < scale_set.size(); sc++)
+    for (size_t t = 0; t < tilt_set.size(); t++) {
+      if (std::fabs(tilt_set[t] - 1) > eps1) {
+        int n_rot1 = (int)std::floor(180.0 * tilt_set[t] / phi_base);
+        double delta_phi = M_PI / n_rot1;
+        if (n_rot1 < 0) {   // no rotation mode if negative: one vertical tilt and one horizontal one (:144-169)
+          n_rot1 = 1; delta_phi = 0;
+          pars_tmp.push_back(make(0, -tilt_set[t], scale_set[sc], doBlur));
+        }
+        for (int r = 0; r < n_rot1; r++) pars_tmp.push_back(make(delta_phi * r, tilt_set[t], scale_set[sc], doBlur));
+      } else
+        pars_tmp.push_back(make(0, tilt_set[t], scale_set[sc], doBlur));
+    }
+  for (const ViewSynthParameters& p : pars_tmp) {
+    bool unique = true;
+    for (const ViewSynthParameters& q : prev_par)
+      if ((std::fabs(p.zoom - q.zoom) <= eps1) && (std::fabs(p.tilt - q.tilt) <= eps1) && (std::fabs(p.phi - q.phi) <= eps1)) { unique = false; break; }
+    if (unique) par.push_back(p);
+  }
+  for (const ViewSynthParameters& p : par) prev_par.push_back(p);
+  return (int)par.size();
+}
+
 // ---- ImageRepresentation ------------------------------------------------------------------------
 ImageRepresentation::ImageRepresentation(mb2_ctx* c, GrayImage img, std::string name, int device_slot)
     : OriginalImg(img), ctx(c), Name(name), slot(device_slot) {}
@@ -96,7 +138,7 @@ AffineRegionVector ImageRepresentation::GetAffineRegionVector(std::string desc_n
 void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisParam& synth_par, DetectorsParameters& det_par,
                                                        DescriptorsParameters& desc_par, DominantOrientationParams& dom_ori_par) {
   // imagerepresentation.cpp:603-2047: HessianAffine branch (:717-720) and MSER branch (:1035-1038) with SIFT-like
-  // descriptors (:1254-1341).  Views other than the identity need GenerateSynthImageCorr (not built): skipped.
+  // descriptors (:1254-1341); every view goes through GenerateSynthImageCorr on the device (mb2_detect_describe_synth_view).
   for (int det = 0; det < 4; det++) {
     const std::string curr_det = kDetectorNames[det];
     auto it = synth_par.find(curr_det);
@@ -106,8 +148,8 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
     for (size_t synth = 0; synth < it->second.size(); synth++) {   // views are appended in view-index order (:2044-2045)
       const ViewSynthParameters& v = it->second[synth];
       const bool identity = (std::fabs(v.tilt - 1.) <= 0.1) && (std::fabs(v.phi) <= 0.2) && (std::fabs(v.zoom - 1.) <= 0.1);  // synth-detection.cpp:278
-      if (!identity) continue;
       const double H[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      const mb2_view_params vp{v.tilt, v.phi, v.zoom, v.InitSigma, v.doBlur};
       for (const std::string& curr_desc : v.descriptors) {
         const descriptor_type dt = GetDescriptorType(curr_desc);
         if (dt == DESC_UNKNOWN) continue;
@@ -116,10 +158,15 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
         const double t0 = now_ms();
         const bool use_slot = slot >= 0 && (ss.desc.empty() || ss.desc == curr_desc);
         const int dev_slot = use_slot ? slot_of(curr_det) : MB2_MAX_SLOTS - 1;
-        int n = is_mser ? mb2_detect_describe_view_mser(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
-                                                        &det_par.MSERParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0)
-                        : mb2_detect_describe_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
-                                                   &det_par.HessParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0);
+        int n;
+        if (!identity)
+          n = mb2_detect_describe_synth_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, &vp, is_mser ? 3 : 0, &det_par.HessParam,
+                                             &det_par.MSERParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0);
+        else
+          n = is_mser ? mb2_detect_describe_view_mser(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
+                                                      &det_par.MSERParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0)
+                      : mb2_detect_describe_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
+                                                 &det_par.HessParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0);
         if (n < 0) continue;  // failures are silent, like the reference (empty lists)
         if (use_slot) { ss.desc = curr_desc; ss.count += n; }
         RegionBlock& B = Blocks[curr_det][curr_desc];
@@ -487,6 +534,16 @@ extern "C" int mb2_host_duplicate_filter(const double* xy /* n x 4: x1 y1 x2 y2 
   return (int)L.TCList.size();
 }
 
+extern "C" int mb2_host_set_vs_pars(const double* scales, int n_scales, const double* tilts, int n_tilts, double phi_base, const double* prev,
+                                    int n_prev, double* out, int capacity) {
+  std::vector<mods::ViewSynthParameters> par, prev_par(n_prev);
+  for (int i = 0; i < n_prev; i++) { prev_par[i].zoom = prev[3 * i]; prev_par[i].tilt = prev[3 * i + 1]; prev_par[i].phi = prev[3 * i + 2]; }
+  const int n = mods::SetVSPars(std::vector<double>(scales, scales + n_scales), std::vector<double>(tilts, tilts + n_tilts), phi_base, {}, {}, {}, par,
+                                prev_par);
+  for (int i = 0; i < n && i < capacity; i++) { out[3 * i] = par[i].zoom; out[3 * i + 1] = par[i].tilt; out[3 * i + 2] = par[i].phi; }
+  return n;
+}
+
 // ---- one MODS iteration on one pair ---------------------------------------------------------------
 namespace {
 // Helper contexts (own stream + scratch) kept per primary context, created on first use:
@@ -706,6 +763,37 @@ int pair_back(mb2_ctx* vctx, const mb2_pair_config* cfg, PairSetup& ps, PairFron
   return n;
 }
 }  // namespace
+
+extern "C" int mb2_host_verify(mb2_ctx* ctx, const double* frames14, const double* key, int n, const mb2_pair_config* cfg, mb2_pair_result* res,
+                               double* verified_out, int capacity) {
+  if (!ctx || !cfg || !res || n < 0 || (n > 0 && (!frames14 || !key))) return MB2_ERR_ARG;
+  PairSetup ps(cfg);
+  std::vector<double> xy((size_t)n * 4);
+  for (int i = 0; i < n; i++) {
+    const double* f = frames14 + (size_t)i * 14;
+    xy[4 * (size_t)i] = f[0]; xy[4 * (size_t)i + 1] = f[1]; xy[4 * (size_t)i + 2] = f[7]; xy[4 * (size_t)i + 3] = f[8];
+  }
+  double t0 = now_ms();
+  std::vector<int> kept = duplicate_filter_core(xy.data(), key, n, cfg->duplicateDist, true);
+  res->ms_duplicate = now_ms() - t0;
+  res->tentatives = n; res->unique_tentatives = (int)kept.size();
+  t0 = now_ms();
+  std::vector<double> frames(kept.size() * 14);
+  for (size_t i = 0; i < kept.size(); i++) std::memcpy(&frames[i * 14], frames14 + (size_t)kept[i] * 14, 14 * sizeof(double));
+  std::vector<unsigned char> inl;
+  std::vector<int> verified;
+  const int k = loransac_core(ctx, frames.data(), (int)kept.size(), ps.rp, inl, verified, res->H);
+  res->ms_ransac = now_ms() - t0;
+  res->ransac_inliers = 0;
+  for (unsigned char b : inl) res->ransac_inliers += b;
+  res->verified = k;
+  if (verified_out)
+    for (int i = 0; i < k && i < capacity; i++) {
+      const double* f = &frames[(size_t)verified[i] * 14];
+      verified_out[4 * i] = f[0]; verified_out[4 * i + 1] = f[1]; verified_out[4 * i + 2] = f[7]; verified_out[4 * i + 3] = f[8];
+    }
+  return k;
+}
 
 extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
                              const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity) {

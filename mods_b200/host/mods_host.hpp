@@ -100,6 +100,13 @@ struct RANSACPars {  // matching/matching.hpp:146-171
   long seed = 0;  // 0 => time(NULL) like the reference (exp_ranH.c:823); anything else is used as the srand seed
 };
 
+// SetVSPars (synth-detection.cpp:103-234): expands ScaleSet x TiltSet x rotations (n = floor(180 t / Phi), delta = pi / n) into
+// view parameters, drops the views already generated in earlier steps (prev_par, tolerance 0.01) and appends the new ones to it.
+int SetVSPars(const std::vector<double>& scale_set, const std::vector<double>& tilt_set, const double phi_base,
+              const std::vector<double>& FGINNThreshold, const std::vector<double>& DistanceThreshold,
+              const std::vector<std::string> descriptors, std::vector<ViewSynthParameters>& par, std::vector<ViewSynthParameters>& prev_par,
+              const double InitSigma = 0.5, const int doBlur = 1, const int dsplevels = 0, const double minSigma = 1.0, const double maxSigma = 1.0);
+
 class CorrespondenceBank;
 
 class ImageRepresentation {
@@ -211,6 +218,14 @@ int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* 
 int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img1, const int* w1, const int* h1, const float* const* img2,
                    const int* w2, const int* h2, const mb2_pair_config* cfg, mb2_pair_result* res, double* const* verified_out,
                    const int* capacity);
+/* mods.cpp:298-415 on plain arrays: DuplicateFiltering(MODE_FGINN) + LORANSACFiltering of n tentatives.  frames: n rows of 14 doubles
+ * (reproj_kp x y a11 a12 a21 a22 s of the first region, then of the second), key[n] = sqrt(d1/d2) ratios.  Used by the view-sharded
+ * driver (mods_b200/sharding.py), where rank 0 verifies the tentatives gathered from all ranks.  Returns the verified count. */
+int mb2_host_verify(mb2_ctx* ctx, const double* frames14, const double* key, int n, const mb2_pair_config* cfg, mb2_pair_result* res,
+                    double* verified_out, int capacity);
+/* test door: SetVSPars for one step; out rows = (zoom, tilt, phi); prev (n_prev rows, same layout) = views of earlier steps */
+int mb2_host_set_vs_pars(const double* scales, int n_scales, const double* tilts, int n_tilts, double phi_base, const double* prev, int n_prev,
+                         double* out, int capacity);
 /* kernels launched by ctx and by the helper contexts mb2_mods_pair(s) keep (second image, verification) */
 long long mb2_mods_launch_count(mb2_ctx* ctx);
 /* destroys the helper context of ctx (call before mb2_ctx_destroy(ctx)) */

@@ -34,3 +34,30 @@ def test_duplicate_filter_equals_reference_double_loop():
         k = H.mb2_host_duplicate_filter(xy.ctypes.data_as(C.c_void_p), ratio.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_double(2.0),
                                         C.c_int(1), out.ctypes.data_as(C.c_void_p))
         assert np.array_equal(out[:k], _brute(xy, ratio, 2.0))
+
+
+def _set_vs_pars(H, scales, tilts, phi, prev):
+    scales = np.asarray(scales, np.float64); tilts = np.asarray(tilts, np.float64)
+    prev = np.ascontiguousarray(np.asarray(prev, np.float64).reshape(-1, 3))
+    out = np.zeros((512, 3))
+    n = H.mb2_host_set_vs_pars(scales.ctypes.data_as(C.c_void_p), C.c_int(len(scales)), tilts.ctypes.data_as(C.c_void_p), C.c_int(len(tilts)),
+                               C.c_double(phi), prev.ctypes.data_as(C.c_void_p), C.c_int(len(prev)), out.ctypes.data_as(C.c_void_p), C.c_int(512))
+    return out[:n].copy()
+
+
+def test_set_vs_pars_view_counts_of_iters_mods_cviu():
+    """SetVSPars (synth-detection.cpp:103-234) on the [MSER2], [MSER3], [HessianAffine4..6] tiers of build/iters_mods_cviu.ini:
+    3, 24, 11, 20, 30 new views per step after the de-duplication against earlier steps."""
+    mb.build()
+    H = mb.host_lib()
+    m2 = _set_vs_pars(H, [1, 0.25, 0.125], [1], 360, [])
+    m3 = _set_vs_pars(H, [1, 0.25, 0.125], [1, 3, 6, 9], 360, m2)
+    assert (len(m2), len(m3)) == (3, 24)
+    h4 = _set_vs_pars(H, [1], [1, 2, 4, 6, 8], 360, [])
+    h5 = _set_vs_pars(H, [1], [1, 2, 4, 6, 8], 120, h4)
+    h6 = _set_vs_pars(H, [1], [1, 2, 4, 6, 8], 60, np.concatenate([h4, h5]))
+    assert (len(h4), len(h5), len(h6)) == (11, 20, 30)
+    # rows are (zoom, tilt, phi): tilt t gets floor(180 t / Phi) rotations spaced pi / n apart, the un-tilted view none
+    assert np.allclose(h4[0], (1, 1, 0)) and np.allclose(h4[1], (1, 2, 0)) and np.allclose(h4[2:4, 2], (0, np.pi / 2))
+    v = _set_vs_pars(H, [1], [-3], 360, [])   # negative tilt in the set: floor(180 * -3 / 360) < 0 -> "no rotation" mode, two views (:144-169)
+    assert len(v) == 2 and np.allclose(v[0], (1, 3, 0)) and np.allclose(v[1], (1, -3, 0))

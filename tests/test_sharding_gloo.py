@@ -64,3 +64,61 @@ def test_assignment_is_balanced_and_complete():
         assert sorted(i for r in a for i in r) == list(range(len(costs)))
         loads = [sum(costs[i] for i in r) for r in a]
         assert max(loads) <= sum(costs) / world + max(costs)
+
+
+# ---- view-sharded pair (BASELINE C4): two gloo ranks, oracle as the per-view worker --------------------------------
+def _pair_units():
+    A = synth.blob_image(200, 150, seed=71, n_blobs=120)
+    B = synth.warp_image(A, synth.gt_homography(200, 150), seed=72)
+    views = [(1.0, 0.0, 1.0), (2.0, 0.0, 1.0), (2.0, 1.5707963, 1.0)]
+    units = [(im, det, vi, v) for im in (0, 1) for det in ("HessianAffine", "MSER") for vi, v in enumerate(views if det == "HessianAffine" else views[:1])]
+    costs = [sharding.view_cost(200, 150, abs(u[3][0]), u[3][2]) for u in units]
+    return (A, B), units, costs
+
+
+def _oracle_workers():
+    from oracle.pyoracle import Oracle
+    O = Oracle()
+    (A, B), units, costs = _pair_units()
+
+    def compute(u):
+        img = (A, B)[u[0]]
+        det, rep, desc = O.view_pipeline_synth(img, *u[3], detector=0 if u[1] == "HessianAffine" else 3)
+        return det, rep, desc.astype(np.uint8)
+
+    def match(det_name, q_rep, q_desc, t_rep, t_desc, lo, hi):
+        rows = O.match_fginn(q_desc[lo:hi].astype(np.float32), t_desc.astype(np.float32), np.ascontiguousarray(t_rep[:, :2]))
+        rows[:, 0] += lo
+        return rows
+    return compute, match, units, costs
+
+
+def _pair_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    compute, match, units, costs = _oracle_workers()
+    out = sharding.pair_views_sharded(compute, match, units, costs, dist=dist, device="cpu")
+    if rank == 1:   # every rank ends with the same data: check on the non-zero one
+        q.put({k: tuple(np.array(a) for a in v) for k, v in out.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_view_sharded_pair_equals_serial():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pair_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    got = q.get(timeout=300)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    compute, match, units, costs = _oracle_workers()
+    want = sharding.pair_views_sharded(compute, match, units, costs)
+    assert sorted(got) == ["HessianAffine", "MSER"]
+    for det in want:
+        assert all(np.array_equal(a, b) for a, b in zip(got[det], want[det])), det
+        assert len(want[det][0]) > 10
+    assert len(want["HessianAffine"][4]) > 5
+    frames, keys = sharding.frames_and_keys(got)
+    assert frames.shape[1] == 14 and len(frames) == len(keys) == sum(len(v[4]) for v in got.values())
