@@ -125,11 +125,11 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(buffers, steps, pipelined=True):
-        """K steps = K pairs.  pipelined: ONE mb2_mods_pairs call over the K pairs (the dataset entry point: verification of
+    def timed(buffers, steps, pipelined=True, collective=True):
+        """K steps = K pairs.  collective=False: rank-local (the profiling pass runs on rank 0 only -- no barrier, no all-reduce).  pipelined: ONE mb2_mods_pairs call over the K pairs (the dataset entry point: verification of
         pair k overlaps detection of pair k+1); otherwise K separate mb2_mods_pair calls (per-pair latency)."""
         results = []
-        barrier()
+        barrier() if collective else torch.cuda.synchronize()
         l0 = ctx.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -142,10 +142,10 @@ def run_ours(args, rank, world, local_rank):
                 res, _ = ctx.mods_pair(a, b, cfg, shape1=(h, w), shape2=(h, w))
                 results.append(res)
         e1.record(stream)
-        barrier()
+        barrier() if collective else torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
-        if world > 1:
+        if world > 1 and collective:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
@@ -166,9 +166,12 @@ def run_ours(args, rank, world, local_rank):
     prof = None
     if rank == 0 and hasattr(ctx, "profile_begin"):
         ctx.profile_begin()
-        timed(dev_pairs, min(args.steps, N_PAIRS), pipelined=False)
+        timed(dev_pairs, min(args.steps, N_PAIRS), pipelined=False, collective=False)
         prof = ctx.profile_end()
 
+    if world > 1:   # every rank: the other ranks wait here while rank 0 finishes its (rank-local) profiling pass
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = load_peaks()
@@ -237,8 +240,16 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
               "traffic": None, "algorithmic_bytes": gb,
               "note": "component tree of both polarities: 256 level-synchronous phases, each a chain of dependent reads -- latency bound, not bandwidth bound "
                       "(DESIGN.md); peak = %s HBM copy" % peaks["src"]}
-    elif "k_blur_hess" in name or "k_nms" in name:
-        rl = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+    elif "k_blur_hess" in name:
+        # per image: every octave runs 4 incremental blurs with the Hessian fused (read 4 B + write blur 4 B + write response 4 B per pixel
+        # of the octave, octaves sum to 4/3 W H) plus the initial blur of octave 0 (read 4 B + write 4 B): DESIGN.md, kernel table
+        gb = (12.0 * 4 * (4.0 / 3.0) + 8.0) * w * h * 2 * steps   # bytes over all launches of the profiled steps (2 images per pair)
+        rl = {"bound": "hbm", "kernel": name, "achieved": gb / 1e9 / (ms / 1e3), "peak": peaks["hbm"], "unit": "GB/s",
+              "frac": gb / 1e9 / (ms / 1e3) / peaks["hbm"], "traffic": None, "algorithmic_bytes_per_launch": gb / max(1, n_launch)}
+    elif "k_nms" in name:
+        gb = 12.0 * 3 * (4.0 / 3.0) * w * h * 2 * steps            # 3 detection levels per octave, 3 response planes read per level
+        rl = {"bound": "hbm", "kernel": name, "achieved": gb / 1e9 / (ms / 1e3), "peak": peaks["hbm"], "unit": "GB/s",
+              "frac": gb / 1e9 / (ms / 1e3) / peaks["hbm"], "traffic": None, "algorithmic_bytes_per_launch": gb / max(1, n_launch)}
     elif "k_nn_tc" in name:
         rl = {"bound": "tensor", "kernel": name, "achieved": None, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": None, "traffic": None}
     # the two kernels the north star names, always reported
@@ -341,6 +352,9 @@ def run_reference(args, rank, world):
 
 
 def main():
+    if os.environ.get("MB2_DUMP_AFTER"):   # diagnostics: Python stacks of all threads if the run is still alive after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["MB2_DUMP_AFTER"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
