@@ -255,9 +255,8 @@ struct PyramidLayout {
 // ---- detection core: pixels on device -> ordered KeyOut list on device --------------------------
 // Result: ctx->kp_b holds n KeyOut (ordered like the reference's key vector, keep == 1 for all).
 int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par, double tilt, double zoom, int as_regions, int* n_out) {
-  (void)tilt; (void)zoom;  // reg_number rescale only matters for the non-FIXED_TH modes
   *n_out = 0;
-  if (par.mode != 0) { ctx->set_error("hessaff: only DetectorMode FIXED_TH is built so far"); return MB2_ERR_UNSUPPORTED; }
+  if (par.mode < 0 || par.mode > 4) { ctx->set_error("hessaff: unknown DetectorMode"); return MB2_ERR_ARG; }
   if (par.numberOfScales + 2 > MB2_MAX_LEVELS || par.smmWindowSize != 19 || par.border < 2) {
     ctx->set_error("hessaff: unsupported numberOfScales / smmWindowSize / border"); return MB2_ERR_ARG;
   }
@@ -316,8 +315,9 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
   MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(T.octaves.p, octs.data(), sizeof(OctaveLevels) * L.n_octaves, cudaMemcpyHostToDevice, ctx->stream));
 
   // thresholds (pyramid.h:46-69)
-  const float finalThreshold = par.threshold * par.threshold;
-  const float positiveThreshold = (float)(0.8 * par.threshold), negativeThreshold = -positiveThreshold;
+  // every mode but FIXED_TH opens all response gates: every 3x3x3 extremum is localised and goes through Baumberg (pyramid.h:59-60)
+  const float finalThreshold = par.mode != 0 ? 0.0f : par.threshold * par.threshold;
+  const float positiveThreshold = par.mode != 0 ? 0.0f : (float)(0.8 * par.threshold), negativeThreshold = -positiveThreshold;
   const double er = par.edgeEigenValueRatio;
   const double edgeScoreThreshold = (er + 1.0f) * (er + 1.0f) / er;
 
@@ -434,6 +434,41 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
   if ((rc = compact(ctx, ctx->kp_b.as<KeyOut>(), nullptr, n_kp, ctx->kp_c.as<KeyOut>(), nullptr, ctx->misc, &n_keep))) return rc;
   std::swap(ctx->kp_b, ctx->kp_c);
   *n_out = n_keep;
+  if (par.mode != 0 && n_keep > 0) {
+    // prepareKeysForExport (scale-space-detector.hpp:127-198): sort by |response| with the reference's own (unstable) std::sort and
+    // truncate.  Host leg: only the same library routine on the same input order reproduces the order of equal responses.
+    int reg_number = par.reg_number;
+    if ((tilt > 2.0) || (zoom < 0.5)) reg_number = (int)std::floor(zoom * (double)reg_number / tilt);   // scale-space-detector.cpp:50-51
+    std::vector<KeyOut> keys(n_keep);
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(keys.data(), ctx->kp_b.p, (size_t)n_keep * sizeof(KeyOut), cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    auto cmp = [](const KeyOut& a, const KeyOut& b) { return std::fabs(a.v[7]) > std::fabs(b.v[7]); };
+    std::sort(keys.begin(), keys.end(), cmp);
+    const int regNumber = n_keep;
+    KeyOut probe = keys[0];
+    switch (par.mode) {
+      case 1: probe.v[7] = std::fabs(keys[0].v[7]) * par.rel_threshold; keys.resize(std::lower_bound(keys.begin(), keys.end(), probe, cmp) - keys.begin()); break;
+      case 2: {
+        int n = reg_number;
+        if (par.doBaumberg) n = (int)std::floor(3.0 * (double)n);
+        if (n < regNumber && n >= 0) keys.resize(n);
+        break; }
+      case 3: keys.resize((int)std::floor(par.rel_reg_number * (double)keys.size())); break;
+      case 4: {
+        probe.v[7] = par.threshold;
+        const int fix = (int)(std::lower_bound(keys.begin(), keys.end(), probe, cmp) - keys.begin());
+        keys.resize(fix < reg_number ? std::min(reg_number, regNumber) : std::min(fix, regNumber));
+        break; }
+      default: break;
+    }
+    if (par.mode == 2 && (int)keys.size() > reg_number) keys.resize(std::max(reg_number, 0));
+    for (size_t i = 0; i < keys.size(); i++) keys[i].order = i;
+    *n_out = (int)keys.size();
+    if (*n_out > 0) {
+      MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->kp_b.p, keys.data(), keys.size() * sizeof(KeyOut), cudaMemcpyHostToDevice, ctx->stream));
+      MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
   return MB2_OK;
 }
 

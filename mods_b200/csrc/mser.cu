@@ -561,7 +561,8 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
   {
     int occ = 0;
     MB2_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mser_tree, 256, 0));
-    const int Gc = ctx->num_sms * std::max(1, std::min(occ, 4));   // co-resident by construction
+    static const int gmul = getenv("MB2_MSER_GRID") ? atoi(getenv("MB2_MSER_GRID")) : 4;   // CTAs per SM of the persistent kernel
+    const int Gc = ctx->num_sms * std::max(1, std::min(occ, gmul));   // co-resident by construction
     int Wv = W, Hv = H;
     static const bool level_prof = getenv("MB2_MSER_LEVEL_PROF") != nullptr;   // diagnostics: per-level phase times to stderr
     unsigned long long* dbg = nullptr;

@@ -505,9 +505,9 @@ struct HessianAffineDetector {
   // scale-space-detector.hpp:127-198 (prepareKeysForExport)
   void prepareKeysForExport() {
     if (keys.empty() || par.mode == 0) return;
-    // NB the reference uses std::sort (unstable) on |response|; ties are implementation-defined
-    // there.  We use a stable sort, so ties keep detection order.
-    std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return std::fabs(a.response) > std::fabs(b.response); });
+    // sortKeys (:115-118): the reference's own std::sort (unstable) with responseCompareInvOrder -- the same library routine on the
+    // same input order is the only way to reproduce the order of equal responses
+    std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return std::fabs(a.response) > std::fabs(b.response); });
     int regNumber = (int)keys.size();
     auto lower = [&](double thr) {
       int lo = 0;  // first index whose |response| is NOT > thr  (std::lower_bound with responseCompareInvOrder)

@@ -54,6 +54,19 @@ def test_hessaff_matches_reference_golden(ctx):
     assert np.array_equal(ctx.hessaff_detect(im, as_regions=True), G["s_reg"])
 
 
+@pytest.mark.parametrize("mode,regs,rel", [(2, 100, -1.0), (4, 2000, -1.0), (4, 50, -1.0), (1, -1, 0.3), (3, -1, 0.25)])
+def test_hessaff_detector_modes(ctx, oracle, mode, regs, rel):
+    """DetectorMode != FIXED_TH (scale-space-detector.hpp:127-198): all extrema localised + Baumberg, std::sort by |response|, truncation."""
+    from oracle.pyoracle import HessParams
+    im = synth.blob_image(300, 200, seed=8)
+    gp = mb.HessaffParams.default(); gp.mode = mode; gp.reg_number = regs; gp.rel_threshold = rel; gp.rel_reg_number = rel if mode == 3 else -1.0
+    hp = HessParams.default(); hp.mode = mode; hp.reg_number = regs; hp.rel_threshold = rel; hp.rel_reg_number = rel if mode == 3 else -1.0
+    for as_regions in (False, True):
+        g = ctx.hessaff_detect(im, gp, as_regions=as_regions)
+        o = oracle.hessaff_detect(im, hp, raw=not as_regions)
+        assert len(o) > 20 and np.array_equal(g, o)
+
+
 def test_hessaff_no_baumberg(ctx, oracle, img):
     from oracle.pyoracle import HessParams
     p = mb.HessaffParams.default(); p.doBaumberg = 0

@@ -145,3 +145,14 @@ def test_view_pipeline_synth(oracle, reference, detector):
         a = oracle.view_pipeline_synth(im, *view, detector=detector)
         b = reference.view_pipeline_synth(im, *view, detector=detector)
         assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[0]) > 5
+
+
+@pytest.mark.parametrize("mode,regs,rel", [(2, 100, -1.0), (4, 2000, -1.0), (4, 50, -1.0), (1, -1, 0.3), (3, -1, 0.25)])
+def test_hessaff_detector_modes(oracle, reference, mode, regs, rel):
+    """prepareKeysForExport (scale-space-detector.hpp:127-198): every mode but FIXED_TH opens the response gates, sorts by |response|
+    with std::sort and truncates."""
+    from oracle.pyoracle import HessParams
+    im = synth.blob_image(300, 200, seed=8)
+    hp = HessParams.default(); hp.mode = mode; hp.reg_number = regs; hp.rel_threshold = rel; hp.rel_reg_number = rel if mode == 3 else -1.0
+    a, b = oracle.hessaff_detect(im, hp, raw=True), reference.hessaff_detect(im, hp, raw=True)
+    assert len(a) > 20 and np.array_equal(a, b)
