@@ -195,6 +195,13 @@ int mb2_detect_describe_synth_view(mb2_ctx* ctx, const float* pixels, int w, int
                                    const mb2_orientation_params* ori, const mb2_sift_params* desc, int slot, int append,
                                    double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
 
+/* Scheduling aid for callers that run several contexts on one GPU: the MSER component-tree kernel is bound by memory latency
+ * and slows down badly next to bandwidth-hungry kernels.  mb2_ctx_tree_epoch(src) = number of tree kernels `src` has launched so
+ * far (safe to poll from another host thread); mb2_ctx_wait_tree(ctx, src) makes everything submitted to ctx from now on wait for
+ * the most recent tree kernel of src (stream-ordered, no host block). */
+long long mb2_ctx_tree_epoch(const mb2_ctx* ctx);
+int mb2_ctx_wait_tree(mb2_ctx* ctx, mb2_ctx* src);
+
 /* Copies the regions of the most recent mb2_detect_describe_view (which may be called with NULL
  * outputs to learn the count first) to the host.  Returns that count. */
 int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);

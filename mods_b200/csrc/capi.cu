@@ -671,7 +671,8 @@ int mb2_ctx_create(int device, mb2_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MB2_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { mb2_ctx_destroy(c); return MB2_ERR_CUDA; }
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_tree, cudaEventDisableTiming) != cudaSuccess) { mb2_ctx_destroy(c); return MB2_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
   *out = c;
@@ -693,6 +694,7 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
   if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_tree) cudaEventDestroy(ctx->ev_tree);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -903,6 +905,14 @@ int mb2_detect_describe_view_mser(mb2_ctx* ctx, const float* pixels, int w, int 
                                   int append, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity) {
   if (!det) return MB2_ERR_ARG;
   return view_core(ctx, pixels, w, h, H, orig_w, orig_h, nullptr, det, ori, desc, slot, append, det_kp, reproj_kp, desc_u8, capacity);
+}
+
+long long mb2_ctx_tree_epoch(const mb2_ctx* ctx) { return ctx ? ctx->tree_epoch : 0; }
+int mb2_ctx_wait_tree(mb2_ctx* ctx, mb2_ctx* src) {
+  if (!ctx || !src || ctx->device != src->device || !src->ev_tree) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  MB2_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, src->ev_tree, 0));
+  return MB2_OK;
 }
 
 int mb2_synth_view(mb2_ctx* ctx, const float* pixels, int w, int h, const mb2_view_params* view, float* out, int capacity, int* ow, int* oh,

@@ -85,6 +85,10 @@ struct mb2_ctx {
   DevBuf img2, pair_keys;       // mb2_mser_detect_pair: second image, keys of both images
   DevBuf synth_a, synth_b, synth_c, synth_k;   // view synthesis: rotated image, view, blur scratch, taps
   int pair_n[2] = {0, 0}, pair_w = 0, pair_h = 0;
+  // the component-tree kernel is latency bound and suffers badly from bandwidth-hungry neighbours: other contexts can order their
+  // work behind it (mb2_ctx_wait_tree).  tree_epoch counts the tree kernels launched so far (read by other host threads).
+  cudaEvent_t ev_tree = nullptr;
+  volatile long long tree_epoch = 0;
   unsigned long long prof_extract_bytes = 0;  // algorithmic gather bytes of the patch-extraction launches
   void set_error(const std::string& s) { err = s; }
 };

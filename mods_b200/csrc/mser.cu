@@ -176,6 +176,7 @@ __device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint
         for (int d = 0; d < 4; d++) if (nx[d] != r[d]) { r[d] = nx[d]; moving = true; }
       }
 #pragma unroll
+#pragma unroll
       for (int d = 0; d < 4; d++) if (valid[d] && r[d] != q[d]) __stcg(zpar + q[d], r[d]);   // compress the start of the path
       if (valid[1] && valid[0] && r[1] == r[0]) valid[1] = false;
       if (valid[2] && ((valid[0] && r[2] == r[0]) || (valid[1] && r[2] == r[1]))) valid[2] = false;
@@ -573,6 +574,7 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
     MB2_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_mser_tree, dim3(Gc), dim3(256), args, 0, st));
     if (ctx->profiling) { cudaEventRecord(pr.b, st); ctx->prof.push_back(pr); }
     ctx->launches++;
+    if (ctx->ev_tree) { cudaEventRecord(ctx->ev_tree, st); __sync_synchronize(); ctx->tree_epoch = ctx->tree_epoch + 1; }
     if (level_prof) {
       std::vector<unsigned long long> t(3 * 256); std::vector<uint32_t> hist(256);
       cudaMemcpyAsync(t.data(), dbg, 3 * 256 * 8, cudaMemcpyDeviceToHost, st);

@@ -674,10 +674,20 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
     } else { mser_post(ctx3, 0, &mser_rc); if (mser_rc >= 0) mser_post(ctx3, 1, &mser_rc); }
   };
   if (ctx2) {
-    std::thread th([&] { const double ta = now_ms(); out.rep2->SynthDetectDescribeKeypoints(iters_here, ps.det_par, ps.desc_par, ps.dom); th2 = now_ms() - ta; });
+    // The tree kernel of the MSER pass goes first and alone: the HessianAffine streams are ordered behind it (they then overlap
+    // with the rest of the MSER pass), because next to their bandwidth-hungry kernels the latency-bound tree kernel takes 2-3x longer.
+    static const bool tree_first = getenv("MB2_NO_TREE_FIRST") == nullptr;
+    const long long epoch0 = ctx3 ? mb2_ctx_tree_epoch(ctx3) : 0;
+    auto wait_tree = [&](mb2_ctx* c) {
+      if (!ctx3 || !tree_first) return;
+      const double t_give_up = now_ms() + 200.0;   // the MSER thread reaches the launch within a few ms; never block for good
+      while (mb2_ctx_tree_epoch(ctx3) == epoch0 && mser_rc >= 0 && now_ms() < t_give_up) std::this_thread::yield();
+      if (mb2_ctx_tree_epoch(ctx3) != epoch0) mb2_ctx_wait_tree(c, ctx3);
+    };
     std::thread tm;
     if (ctx3) tm = std::thread(mser_pair);
-    { const double ta = now_ms(); out.rep1->SynthDetectDescribeKeypoints(iters_here, ps.det_par, ps.desc_par, ps.dom); th1 = now_ms() - ta; }
+    std::thread th([&] { wait_tree(ctx2); const double ta = now_ms(); out.rep2->SynthDetectDescribeKeypoints(iters_here, ps.det_par, ps.desc_par, ps.dom); th2 = now_ms() - ta; });
+    { wait_tree(ctx); const double ta = now_ms(); out.rep1->SynthDetectDescribeKeypoints(iters_here, ps.det_par, ps.desc_par, ps.dom); th1 = now_ms() - ta; }
     th.join();
     if (ctx3) tm.join();
     if (timing) fprintf(stderr, "[pair front] hessaff img1 %.1f ms, img2 %.1f ms | mser detect (both) %.1f ms, orient+describe %.1f ms\n", th1, th2, tm_detect, tm_post);

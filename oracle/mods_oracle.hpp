@@ -888,28 +888,36 @@ inline std::vector<Tentative> matchFGINN(const float* q, int nq, const float* t,
   if (nq == 0 || nt == 0) return out;
   const double sqminratio = matchRatio * matchRatio, contrDistSq = contradDist * contradDist;
   const int k = std::min(nn, nt);
-  std::vector<std::pair<float, int>> d(nt);
-  for (int i = 0; i < nq; i++) {
-    const float* a = q + (size_t)i * 128;
-    for (int j = 0; j < nt; j++) {
-      const float* b = t + (size_t)j * 128;
-      float s = 0;
-      for (int e = 0; e < 128; e++) { float df = a[e] - b[e]; s += df * df; }
-      d[j] = std::make_pair(s, j);
-    }
-    std::partial_sort(d.begin(), d.begin() + k, d.end());
-    for (int j = 1; j < k; j++) {
-      double ratio = d[0].first / d[j].first;  // float / float, as in the reference
-      double dx = txy[2 * d[0].second] - txy[2 * d[j].second], dy = txy[2 * d[0].second + 1] - txy[2 * d[j].second + 1];
-      double dist1 = dx * dx + dy * dy;
-      if (sqminratio >= 1.0) {
-        if ((j == nn - 1) || (dist1 > contrDistSq)) { out.push_back({i, d[0].second, d[j].second, d[1].second, d[0].first, d[j].first, d[1].first}); break; }
-      } else {
-        if (ratio <= sqminratio) { out.push_back({i, d[0].second, d[j].second, d[1].second, d[0].first, d[j].first, d[1].first}); break; }
-        if (dist1 > contrDistSq) break;
+  // queries are independent: all host threads (OpenMP), results put back in query order -- the same list as the serial loop
+  std::vector<Tentative> per_q(nq);
+  std::vector<char> has(nq, 0);
+#pragma omp parallel
+  {
+    std::vector<std::pair<float, int>> d(nt);
+#pragma omp for schedule(dynamic, 16)
+    for (int i = 0; i < nq; i++) {
+      const float* a = q + (size_t)i * 128;
+      for (int j = 0; j < nt; j++) {
+        const float* b = t + (size_t)j * 128;
+        float s = 0;
+        for (int e = 0; e < 128; e++) { float df = a[e] - b[e]; s += df * df; }
+        d[j] = std::make_pair(s, j);
+      }
+      std::partial_sort(d.begin(), d.begin() + k, d.end());
+      for (int j = 1; j < k; j++) {
+        double ratio = d[0].first / d[j].first;  // float / float, as in the reference
+        double dx = txy[2 * d[0].second] - txy[2 * d[j].second], dy = txy[2 * d[0].second + 1] - txy[2 * d[j].second + 1];
+        double dist1 = dx * dx + dy * dy;
+        if (sqminratio >= 1.0) {
+          if ((j == nn - 1) || (dist1 > contrDistSq)) { per_q[i] = {i, d[0].second, d[j].second, d[1].second, d[0].first, d[j].first, d[1].first}; has[i] = 1; break; }
+        } else {
+          if (ratio <= sqminratio) { per_q[i] = {i, d[0].second, d[j].second, d[1].second, d[0].first, d[j].first, d[1].first}; has[i] = 1; break; }
+          if (dist1 > contrDistSq) break;
+        }
       }
     }
   }
+  for (int i = 0; i < nq; i++) if (has[i]) out.push_back(per_q[i]);
   return out;
 }
 

@@ -17,6 +17,8 @@ else:
     np.savez(cache, A=A, B=B)
 ctx = mb.Context(0)
 ctx.profile_begin()          # keeps both images on one stream (the capture is serialised anyway)
-res, _ = ctx.mods_pair(A, B)
+cfg = mb.PairConfig.default()
+cfg.use_mser = 0 if os.environ.get("NCU_NO_MSER") else 1   # the C3 workload: HessianAffine + MSER
+res, _ = ctx.mods_pair(A, B, cfg)
 ctx.profile_end()
 print("regions %d %d tentatives %d verified %d" % (res.regions1, res.regions2, res.tentatives, res.verified))
