@@ -93,6 +93,9 @@ typedef struct {
 
 /* ---- context --------------------------------------------------------------------------- */
 int mb2_ctx_create(int device, mb2_ctx** out);
+/* Same, with the context's streams at the device's highest priority when high_priority != 0: for the context whose work sits on the
+ * critical path when several contexts share one GPU (its pending blocks are scheduled ahead of the others'). */
+int mb2_ctx_create_prio(int device, int high_priority, mb2_ctx** out);
 void mb2_ctx_destroy(mb2_ctx* ctx);
 const char* mb2_last_error(const mb2_ctx* ctx);
 /* Blocks until everything queued on the context's stream has finished. */

@@ -660,7 +660,8 @@ int mb2_stage_in(mb2_ctx* ctx, const void* src, size_t bytes, DevBuf& dst, const
 // =================================================================================================
 extern "C" {
 
-int mb2_ctx_create(int device, mb2_ctx** out) {
+int mb2_ctx_create(int device, mb2_ctx** out) { return mb2_ctx_create_prio(device, 0, out); }
+int mb2_ctx_create_prio(int device, int high_priority, mb2_ctx** out) {
   if (!out) return MB2_ERR_ARG;
   *out = nullptr;
   int count = 0;
@@ -668,8 +669,11 @@ int mb2_ctx_create(int device, mb2_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return MB2_ERR_CUDA;
   mb2_ctx* c = new mb2_ctx();
   c->device = device;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MB2_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // numerically lower = higher priority
+  const int prio = high_priority ? prio_hi : prio_lo;
+  if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio) != cudaSuccess) { delete c; return MB2_ERR_CUDA; }
+  if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_tree, cudaEventDisableTiming) != cudaSuccess) { mb2_ctx_destroy(c); return MB2_ERR_CUDA; }

@@ -559,7 +559,9 @@ mb2_ctx* sibling_ctx(mb2_ctx* ctx, int which = 0) {
   Helpers& h = g_siblings[ctx];
   if (!h.tried[which]) {
     h.tried[which] = true;
-    if (mb2_ctx_create(mb2_ctx_device(ctx), &h.c[which]) != MB2_OK) h.c[which] = nullptr;
+    // [2] and [3] carry the MSER chain, the critical path of a pair: their kernels go ahead of the HessianAffine ones
+    static const bool prio = getenv("MB2_NO_PRIO") == nullptr;
+    if (mb2_ctx_create_prio(mb2_ctx_device(ctx), (which >= 2 && prio) ? 1 : 0, &h.c[which]) != MB2_OK) h.c[which] = nullptr;
   }
   return h.c[which];
 }
