@@ -212,7 +212,7 @@ def run_ours(args, rank, world, local_rank):
                                          mser_regions=float(np.mean([r.mser_regions1 + r.mser_regions2 for r in res_dev])) / 2))
     else:
         out["roofline"] = None
-    out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1, with_mser=not args.no_mser) if not args.no_cpu_baseline else None
+    out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1, with_mser=not args.no_mser) if (not args.no_cpu_baseline and world == 1) else None   # rank 0 at N=1 only
     print(json.dumps(out))
 
 

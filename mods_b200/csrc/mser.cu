@@ -15,7 +15,7 @@
 //                                    thread each (mser_logic.cuh: emulate_node)
 //   4. k_mser_regions_*              one thread per tracked region: lifetime, cumulative area/border histograms,
 //                                    stability thresholds (FastSetOptThresholds4StableRegion)
-//   5. k_mser_down / k_mser_runs     selected components -> row runs (start / end events), sorted per region
+//   5. k_mser_sa / k_mser_runs       selected components -> row runs (start / end events), sorted per region
 //   6. k_mser_moments / k_mser_keys  RLE2Ellipse in the reference's summation order, sqrtm, AffineKeypoint record
 // Integer / index work is bit-exact by construction; the f64 moment sums follow the reference's order run by run.
 #include "common.cuh"
@@ -398,22 +398,23 @@ __global__ void k_mser_selkeys(const SelRec* __restrict__ sel, uint32_t n, u64* 
 }
 
 // ---- 5. selected components -> row runs ------------------------------------------------------------------------------------
-// sa[x] = slot of the nearest selected node on the path from x to the root (x included); levels from the top down.
-__global__ void __launch_bounds__(256) k_mser_down(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ hooked, const uint32_t* __restrict__ slot_of_node,
-                                                   uint32_t* sa, const MserCounters* C) {
-  cg::grid_group grid = cg::this_grid();
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    for (uint32_t i = 0; i < C->n_stack; i++) sa[C->root[i]] = slot_of_node[C->root[i]];
-  grid.sync();
-  for (int L = 255; L >= 0; L--) {
-    const uint32_t beg = C->hook_off[L], end = C->hook_off[L + 1];
-    if (beg == end) continue;
-    for (uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
-      const uint32_t x = hooked[i];
-      const uint32_t s = slot_of_node[x];
-      sa[x] = (s != NONE) ? s : __ldcg(sa + parent[x]);   // written by another block in an earlier phase
+// sa[x] = slot of the nearest selected node on the path from x's node to the root (the node included).  Selected components are
+// at most max_size pixels large and areas only grow towards the root, so every pixel simply walks up until it meets a selected
+// node or a component that is too large to have selected ancestors: background pixels stop at once, pixels inside a blob after a few
+// levels.  (A level-synchronous top-down pass costs a grid barrier per level instead.)
+__global__ void k_mser_sa(TreeDev td, uint32_t N, const uint32_t* __restrict__ slot_of_node, uint32_t max_size, uint32_t* __restrict__ sa) {
+  const Tree t = td.get();
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+    uint32_t u = node_of(t, p), s = NONE;
+    for (;;) {
+      if (t.area[u] > max_size) break;
+      s = slot_of_node[u];
+      if (s != NONE) break;
+      const uint32_t up = t.parent[u];
+      if (up == u) break;
+      u = up;
     }
-    grid.sync();
+    sa[p] = s;
   }
 }
 __global__ void k_mser_upsel(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ node_of_slot, uint32_t n_slots,
@@ -656,19 +657,8 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
     ctx->launches += 4;
   }
   // 5. runs of the selected components
-  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(sa, 0xff, (size_t)N * 4, st));
   MB2_CUDA_CHECK(ctx, B.up_sel.reserve((size_t)n_slots * 4));
-  {
-    int occ = 0;
-    MB2_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mser_down, 256, 0));
-    const int Gc = ctx->num_sms * std::max(1, std::min(occ, 4));
-    void* args[] = {&parent, &hooked, &slot_of_node, &sa, &dC};
-    mb2_ctx::ProfRec pr{"k_mser_down", nullptr, nullptr};
-    if (ctx->profiling) { cudaEventCreate(&pr.a); cudaEventCreate(&pr.b); cudaEventRecord(pr.a, st); }
-    MB2_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_mser_down, dim3(Gc), dim3(256), args, 0, st));
-    if (ctx->profiling) { cudaEventRecord(pr.b, st); ctx->prof.push_back(pr); }
-    ctx->launches++;
-  }
+  MB2_LAUNCH(ctx, k_mser_sa, grid_for(N, 256, G), 256, 0, td, N, slot_of_node, (uint32_t)max_size, sa);
   MB2_LAUNCH(ctx, k_mser_upsel, (n_slots + 255) / 256, 256, 0, parent, B.node_of_slot.as<uint32_t>(), (uint32_t)n_slots, sa, B.up_sel.as<uint32_t>());
   const uint32_t run_cap = N + 1024;
   MB2_CUDA_CHECK(ctx, B.ev_a.reserve((size_t)run_cap * 8)); MB2_CUDA_CHECK(ctx, B.ev_b.reserve((size_t)run_cap * 8));
