@@ -683,7 +683,7 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
     auto wait_tree = [&](mb2_ctx* c) {
       if (!ctx3 || !tree_first) return;
       const double t_give_up = now_ms() + 200.0;   // the MSER thread reaches the launch within a few ms; never block for good
-      while (mb2_ctx_tree_epoch(ctx3) == epoch0 && mser_rc >= 0 && now_ms() < t_give_up) std::this_thread::yield();
+      while (mb2_ctx_tree_epoch(ctx3) == epoch0 && mser_rc >= 0 && now_ms() < t_give_up) std::this_thread::sleep_for(std::chrono::microseconds(50));
       if (mb2_ctx_tree_epoch(ctx3) != epoch0) mb2_ctx_wait_tree(c, ctx3);
     };
     std::thread tm;
