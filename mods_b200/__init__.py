@@ -118,7 +118,18 @@ class PairConfig(C.Structure):
                 ("matchRatio", C.c_double), ("contradDist", C.c_double), ("duplicateDist", C.c_double),
                 ("err_threshold", C.c_double), ("confidence", C.c_double), ("HLAFCoef", C.c_double),
                 ("max_samples", C.c_int), ("errorType", C.c_int), ("doSymmCheck", C.c_int), ("seed", C.c_long),
-                ("use_mser", C.c_int), ("mser", MserParams), ("mserMatchRatio", C.c_double)]
+                ("use_mser", C.c_int), ("mser", MserParams), ("mserMatchRatio", C.c_double),
+                ("n_hess_views", C.c_int), ("n_mser_views", C.c_int), ("hess_views", ViewParams * 32), ("mser_views", ViewParams * 32)]
+
+    def set_views(self, hess=None, mser=None):
+        """View tiers of the step: lists of (tilt, phi, zoom[, InitSigma]) as SetVSPars produces them; None = identity view only."""
+        for name, views in (("hess", hess), ("mser", mser)):
+            views = views or []
+            assert len(views) <= 32
+            setattr(self, "n_%s_views" % name, len(views))
+            arr = getattr(self, "%s_views" % name)
+            for i, v in enumerate(views):
+                arr[i] = ViewParams(v[0], v[1], v[2], v[3] if len(v) > 3 else 0.5, 1)
 
     @staticmethod
     def default():

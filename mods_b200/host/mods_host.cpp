@@ -593,6 +593,8 @@ extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
   c->max_samples = 100000; c->errorType = 0; c->doSymmCheck = 1;
   c->seed = 1;
   c->use_mser = 0; c->mser = dp.MSERParam; c->mserMatchRatio = 0.8;                 // iters_mods_cviu.ini:36 ([MSER0] FGINNThreshold)
+  c->n_hess_views = c->n_mser_views = 0;
+  std::memset(c->hess_views, 0, sizeof c->hess_views); std::memset(c->mser_views, 0, sizeof c->mser_views);
 }
 
 namespace {
@@ -601,17 +603,27 @@ using namespace mods;
 struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.ini / an iters file with one HessianAffine tier
   DetectorsParameters det_par; DescriptorsParameters desc_par; DominantOrientationParams dom;
   std::string desc_name; IterationViewsynthesisParam iters; RANSACPars rp;
+  bool mser_identity_only = true;   // the batched two-image MSER pass covers the identity view only
   explicit PairSetup(const mb2_pair_config* cfg) {
     det_par.HessParam = cfg->det;
     desc_par.RootSIFTParam = cfg->desc; desc_par.SIFTParam = cfg->desc;
     dom.maxAngles = cfg->ori.maxAngles; dom.threshold = (float)cfg->ori.threshold; dom.mrSize = cfg->ori.mrSize; dom.patchSize = cfg->ori.patchSize;
     desc_name = cfg->desc.rootSIFT ? "RootSIFT" : "SIFT";
-    ViewSynthParameters v; v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = cfg->matchRatio;
-    iters["HessianAffine"].push_back(v);
+    auto tier = [&](const char* det, double ratio, int n, const mb2_view_params* views) {
+      if (n <= 0) { ViewSynthParameters v; v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = ratio; iters[det].push_back(v); return; }
+      for (int i = 0; i < n && i < MB2_MAX_PAIR_VIEWS; i++) {
+        ViewSynthParameters v; v.tilt = views[i].tilt; v.phi = views[i].phi; v.zoom = views[i].zoom; v.InitSigma = views[i].InitSigma; v.doBlur = views[i].doBlur;
+        v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = ratio;
+        iters[det].push_back(v);
+      }
+    };
+    tier("HessianAffine", cfg->matchRatio, cfg->n_hess_views, cfg->hess_views);
+    mser_identity_only = true;
     if (cfg->use_mser) {
       det_par.MSERParam = cfg->mser;
-      ViewSynthParameters m; m.descriptors.push_back(desc_name); m.FGINNThreshold[desc_name] = cfg->mserMatchRatio;
-      iters["MSER"].push_back(m);
+      tier("MSER", cfg->mserMatchRatio, cfg->n_mser_views, cfg->mser_views);
+      const std::vector<ViewSynthParameters>& mv = iters["MSER"];
+      mser_identity_only = mv.size() == 1 && std::fabs(mv[0].tilt - 1.) <= 0.1 && std::fabs(mv[0].phi) <= 0.2 && std::fabs(mv[0].zoom - 1.) <= 0.1;
     }
     rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
     rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
@@ -640,7 +652,7 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
   double t0 = now_ms();
   // MSER of both images in ONE batched pass on a third context when the images have the same size (the component-tree
   // kernel is latency bound: two images cost hardly more than one); otherwise per image, after HessianAffine.
-  mb2_ctx* ctx3 = (ctx2 && cfg->use_mser && w1 == w2 && h1 == h2) ? sibling_ctx(ctx, 2) : nullptr;
+  mb2_ctx* ctx3 = (ctx2 && cfg->use_mser && ps.mser_identity_only && w1 == w2 && h1 == h2) ? sibling_ctx(ctx, 2) : nullptr;
   IterationViewsynthesisParam iters_here = ps.iters;
   if (ctx3) {
     iters_here.erase("MSER");

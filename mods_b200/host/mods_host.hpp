@@ -189,6 +189,7 @@ int loransac_core(mb2_ctx* ctx, const double* frames14, int n, const RANSACPars&
 // ---- C door for bench.py / tests: one MODS iteration on one image pair (mods.cpp:229-415, step 0 of
 // an iters file that has a single HessianAffine view tier with the identity view) --------------------
 extern "C" {
+#define MB2_MAX_PAIR_VIEWS 32
 typedef struct {
   mb2_hessaff_params det;
   mb2_orientation_params ori;
@@ -202,6 +203,10 @@ typedef struct {
   int use_mser;
   mb2_mser_params mser;
   double mserMatchRatio;
+  /* view tiers of the step (rows of SetVSPars; iters_mods_cviu.ini [HessianAffine4] has 11, [MSER2] 3): n == 0 means the identity view
+   * only.  The views of one detector are appended in this order (imagerepresentation.cpp:2044-2045). */
+  int n_hess_views, n_mser_views;
+  mb2_view_params hess_views[MB2_MAX_PAIR_VIEWS], mser_views[MB2_MAX_PAIR_VIEWS];
 } mb2_pair_config;
 typedef struct {
   int regions1, regions2, tentatives, unique_tentatives, ransac_inliers, verified;

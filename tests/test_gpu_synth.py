@@ -48,3 +48,34 @@ def test_synth_view_full_size_properties(ctx):
     c, s = np.cos(0.5), np.sin(0.5)
     assert a.shape == (int(np.floor(0.5 + s * 4096 + c * 3072)), int(np.floor((0.5 + c * 4096 + s * 3072) / 2.0)))
     assert np.array_equal(a, b) and a[0, 0] == 128.0 and a[-1, -1] == 128.0 and 0 <= a.min() and a.max() <= 255.0
+
+
+def test_mods_pair_with_view_tiers_equals_per_view_composition(ctx):
+    """One mods.cpp step with view tiers (HessianAffine: identity + two tilted views, MSER: identity + a zoomed-out view) through the
+    C++ host mirror (SynthDetectDescribeKeypoints appends the views of a detector in view order, MatchImgReps per detector, joint
+    verification) == the same step composed from per-view C-ABI calls by the view-sharded driver (world size 1)."""
+    from mods_b200 import sharding
+    A = synth.blob_image(480, 360, seed=21, n_blobs=500)
+    B = synth.warp_image(A, synth.gt_homography(480, 360), seed=22)
+    hess = [(1.0, 0.0, 1.0, 0.2), (2.0, 0.0, 1.0, 0.2), (2.0, 1.5707963267948966, 1.0, 0.2)]
+    mser = [(1.0, 0.0, 1.0, 0.8), (1.0, 0.0, 0.5, 0.8)]
+    cfg = mb.PairConfig.default()
+    cfg.seed = 77
+    cfg.use_mser = 1
+    cfg.set_views(hess, mser)
+    res, ver = ctx.mods_pair(A, B, cfg, capacity=8192)
+    tiers = {"HessianAffine": [(v[2], v[0], v[1], v[3]) for v in hess], "MSER": [(v[2], v[0], v[1], v[3]) for v in mser]}   # rows (zoom, tilt, phi, sigma)
+    units, costs = sharding.iters_units(480, 360, tiers)
+    compute, match = sharding.gpu_workers(ctx, A, B, cfg)
+    groups = sharding.pair_views_sharded(compute, match, units, costs)
+    n1 = sum(len(g[0]) for g in groups.values()); n2 = sum(len(g[2]) for g in groups.values())
+    assert (res.regions1, res.regions2) == (n1, n2) and res.mser_regions1 == len(groups["MSER"][0]) > 20
+    assert res.tentatives == sum(len(g[4]) for g in groups.values()) and res.mser_tentatives == len(groups["MSER"][4])
+    frames, keys = sharding.frames_and_keys(groups)
+    r2, v2 = ctx.verify(frames, keys, cfg, capacity=8192)
+    assert (res.unique_tentatives, res.ransac_inliers, res.verified) == (r2.unique_tentatives, r2.ransac_inliers, r2.verified)
+    assert np.array_equal(ver, v2) and res.verified >= 8
+    # more views than the identity alone must have added regions
+    cfg1 = mb.PairConfig.default(); cfg1.seed = 77; cfg1.use_mser = 1
+    res1, _ = ctx.mods_pair(A, B, cfg1)
+    assert res.regions1 > res1.regions1 and res.tentatives > res1.tentatives
