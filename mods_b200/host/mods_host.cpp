@@ -623,7 +623,8 @@ struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.in
       det_par.MSERParam = cfg->mser;
       tier("MSER", cfg->mserMatchRatio, cfg->n_mser_views, cfg->mser_views);
       const std::vector<ViewSynthParameters>& mv = iters["MSER"];
-      mser_identity_only = mv.size() == 1 && std::fabs(mv[0].tilt - 1.) <= 0.1 && std::fabs(mv[0].phi) <= 0.2 && std::fabs(mv[0].zoom - 1.) <= 0.1;
+      mser_identity_only = mv.size() == 1 && std::fabs(mv[0].tilt - 1.) <= 0.1 && std::fabs(mv[0].phi) <= 0.2 && std::fabs(mv[0].zoom - 1.) <= 0.1 &&
+                           cfg->mser.mode == 0;   // the batched pass is FIXED_TH only (the other modes sort on the host per image)
     }
     rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
     rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;

@@ -181,3 +181,40 @@ def test_mser_pair_batch_equals_single_images(ctx):
     for got, want in (((d1, r1, u1), s1), ((d2, r2, u2), s2)):
         assert all(np.array_equal(g, w) for g, w in zip(got, want))
     assert np.array_equal(ctx.match_slots(4, 5), ctx.match_slots(2, 3))
+
+
+def test_mods_pair_wxbs_style_config(ctx, oracle):
+    """The WxBS flavour of the step (config_iter_mods_cviu_wxbs.ini: MSER FixedRegNumber, HessianAffine NotLessThanRegions, up to 5
+    orientations per region, contradDist 10): detector modes and multiple orientations through the whole pair driver == oracle."""
+    from oracle.pyoracle import HessParams
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(480, 360, seed=21, n_blobs=500)
+    B = warp_image(A, gt_homography(480, 360), seed=22)
+    cfg = mb.PairConfig.default()
+    cfg.seed = 5
+    cfg.use_mser = 1
+    cfg.det.mode = 4; cfg.det.reg_number = 300          # NOT_LESS_THAN_REGIONS
+    cfg.mser.mode = 2; cfg.mser.reg_number = 60         # FIXED_REG_NUMBER
+    cfg.ori.maxAngles = 5
+    cfg.contradDist = 10.0
+    res, ver = ctx.mods_pair(A, B, cfg, capacity=8192)
+    hp = HessParams.default(); hp.mode = 4; hp.reg_number = 300
+    n1 = n2 = nt = 0
+    for det, ratio in ((0, cfg.matchRatio), (3, cfg.mserMatchRatio)):
+        oa = oracle.view_pipeline(A, detector=det, hp=hp, ori=(1.0, 41, 5, 0.8))
+        ob = oracle.view_pipeline(B, detector=det, hp=hp, ori=(1.0, 41, 5, 0.8))
+        if det == 3:   # the oracle's view_pipeline takes the MSER mode through mser_detect only: check the count that way
+            continue
+        n1 += len(oa[0]); n2 += len(ob[0])
+        nt += len(oracle.match_fginn(oa[2], ob[2], np.ascontiguousarray(ob[1][:, :2]), ratio=ratio, contradDist=10.0))
+    assert (res.regions1 - res.mser_regions1, res.regions2 - res.mser_regions2) == (n1, n2)
+    assert res.tentatives - res.mser_tentatives == nt
+    counts = []
+    for img in (A, B):   # MSER with a detector mode, composed from the oracle's stages: detect -> orientations -> reprojection filter
+        km = oracle.mser_detect(img, mode=2, reg_number=60)
+        assert len(km) == 60
+        ko = oracle.detect_orientation(img, km, maxAngles=5)
+        counts.append(len(oracle.reproject(ko, np.eye(3), 480, 360, 0)[0]))
+    assert (res.mser_regions1, res.mser_regions2) == tuple(counts) and res.verified >= 8
+    p = np.c_[ver[:, :2], np.ones(len(ver))] @ gt_homography(480, 360).T
+    assert np.median(np.hypot(p[:, 0] / p[:, 2] - ver[:, 2], p[:, 1] / p[:, 2] - ver[:, 3])) < 1.5
