@@ -13,6 +13,8 @@
 #include <ctime>
 #include <condition_variable>
 #include <deque>
+#include <fstream>
+#include <iostream>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -181,6 +183,73 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
       }
     }
   }
+}
+
+// ---- feature cache (imagerepresentation.cpp:34-37 saveKP, :89-99 saveAR, :124-147 loadKP / loadAR, :2139-2215) ----------------
+void ImageRepresentation::SaveRegions(std::string fname, int mode) const {
+  if (mode != 0) return;   // the reference's binary branch is empty (:2141-2143)
+  std::ofstream kpfile(fname);
+  if (!kpfile.is_open()) { std::cerr << "Cannot open file " << fname << " to save keypoints" << std::endl; return; }
+  auto saveKP = [&](const double* v) {   // x y a11 a12 a21 a22 pyramid_scale octave_number s sub_type  (response is not stored)
+    kpfile << v[0] << " " << v[1] << " " << v[2] << " " << v[3] << " " << v[4] << " " << v[5] << " ";
+    kpfile << 0.0 << " " << 0 << " " << v[6] << " " << (int)v[8] << " ";
+  };
+  kpfile << Blocks.size() << std::endl;
+  for (auto& d : Blocks) {
+    kpfile << d.first << " " << d.second.size() << std::endl;
+    for (auto& e : d.second) {
+      const RegionBlock& B = e.second;
+      kpfile << e.first << " " << B.n << std::endl;
+      if (B.n > 0) kpfile << 128 << std::endl;
+      for (int i = 0; i < B.n; i++) {
+        kpfile << i << " " << B.img_id[i] << " " << 0 << " " << 0 << " ";   // id img_id img_reproj_id parent_id
+        saveKP(&B.det_kp[(size_t)i * MB2_KP]);
+        saveKP(&B.reproj_kp[(size_t)i * MB2_KP]);
+        kpfile << " " << 128 << " ";
+        for (int j = 0; j < 128; j++) kpfile << (float)B.desc_u8[(size_t)i * 128 + j] << " ";
+        kpfile << std::endl;
+      }
+    }
+  }
+}
+void ImageRepresentation::LoadRegions(std::string fname) {
+  std::ifstream kpfile(fname);
+  if (!kpfile.is_open()) { std::cerr << "Cannot open file " << fname << " to load keypoints" << std::endl; return; }
+  int numberOfDetectors = 0;
+  kpfile >> numberOfDetectors;
+  for (int det = 0; det < numberOfDetectors && kpfile; det++) {
+    std::string det_name; int num_of_descs = 0;
+    kpfile >> det_name >> num_of_descs;
+    for (int desc = 0; desc < num_of_descs && kpfile; desc++) {
+      std::string desc_name; int num_of_kp = 0, desc_size = 0;
+      kpfile >> desc_name >> num_of_kp;
+      if (num_of_kp > 0) kpfile >> desc_size;
+      const descriptor_type dt = GetDescriptorType(desc_name);
+      RegionBlock tmp;
+      RegionBlock& B = (dt != DESC_UNKNOWN) ? Blocks[det_name][desc_name] : tmp;   // "None" and foreign descriptors are parsed and dropped
+      B.det = GetDetectorType(det_name); B.desc = dt;
+      for (int kp = 0; kp < num_of_kp && kpfile; kp++) {
+        int id, img_id, img_reproj_id, parent_id, size1 = 0;
+        kpfile >> id >> img_id >> img_reproj_id >> parent_id;
+        double k[2][MB2_KP];
+        for (int w = 0; w < 2; w++) {   // loadKP: x y a11 a12 a21 a22 pyramid_scale octave_number s sub_type
+          double ps; int oct, st;
+          kpfile >> k[w][0] >> k[w][1] >> k[w][2] >> k[w][3] >> k[w][4] >> k[w][5] >> ps >> oct >> k[w][6] >> st;
+          k[w][7] = 0; k[w][8] = st;
+        }
+        kpfile >> size1;
+        std::vector<float> vec(size1 > 0 ? size1 : 0);
+        for (int j = 0; j < size1; j++) kpfile >> vec[j];
+        if (!kpfile) break;
+        B.det_kp.insert(B.det_kp.end(), k[0], k[0] + MB2_KP);
+        B.reproj_kp.insert(B.reproj_kp.end(), k[1], k[1] + MB2_KP);
+        for (int j = 0; j < 128; j++) B.desc_u8.push_back(j < size1 ? (uint8_t)std::max(0.f, std::min(255.f, vec[j])) : 0);
+        B.img_id.push_back(img_id);
+        B.n++;
+      }
+    }
+  }
+  slot_state.clear();   // nothing of this is resident on the device
 }
 
 void ImageRepresentation::AppendViewFrom(mb2_ctx* from, const std::string& det, const std::string& desc, int n, int synth) {
@@ -532,6 +601,31 @@ extern "C" int mb2_host_duplicate_filter(const double* xy /* n x 4: x1 y1 x2 y2 
   mods::DuplicateFiltering(L, r, mode);
   for (size_t i = 0; i < L.TCList.size(); i++) kept_out[i] = L.TCList[i].first.id;
   return (int)L.TCList.size();
+}
+
+extern "C" int mb2_host_save_regions(const char* fname, const char* det, const char* desc, int n, const double* det_kp, const double* reproj_kp,
+                                     const uint8_t* desc_u8) {
+  struct Rep : mods::ImageRepresentation {
+    Rep() : mods::ImageRepresentation(nullptr, mods::GrayImage(), "cache", -1) {}
+    RegionBlock& blk(const std::string& d, const std::string& e) { return Blocks[d][e]; }
+  } rep;
+  mods::ImageRepresentation::RegionBlock& B = rep.blk(det, desc);
+  B.n = n; B.det = rep.GetDetectorType(det); B.desc = rep.GetDescriptorType(desc);
+  B.det_kp.assign(det_kp, det_kp + (size_t)n * MB2_KP); B.reproj_kp.assign(reproj_kp, reproj_kp + (size_t)n * MB2_KP);
+  B.desc_u8.assign(desc_u8, desc_u8 + (size_t)n * 128); B.img_id.assign(n, 0);
+  rep.SaveRegions(fname);
+  return n;
+}
+extern "C" int mb2_host_load_regions(const char* fname, const char* det, const char* desc, int capacity, double* det_kp, double* reproj_kp,
+                                     uint8_t* desc_u8) {
+  mods::ImageRepresentation rep(nullptr, mods::GrayImage(), "cache", -1);
+  rep.LoadRegions(fname);
+  const mods::ImageRepresentation::RegionBlock* B = rep.block(det, desc);
+  if (!B) return 0;
+  const int m = std::min(B->n, capacity);
+  std::memcpy(det_kp, B->det_kp.data(), (size_t)m * MB2_KP * 8); std::memcpy(reproj_kp, B->reproj_kp.data(), (size_t)m * MB2_KP * 8);
+  std::memcpy(desc_u8, B->desc_u8.data(), (size_t)m * 128);
+  return B->n;
 }
 
 extern "C" int mb2_host_set_vs_pars(const double* scales, int n_scales, const double* tilts, int n_tilts, double phi_base, const double* prev,

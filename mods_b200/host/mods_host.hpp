@@ -125,6 +125,11 @@ class ImageRepresentation {
   // driver batches the MSER detection of both images, mb2_mser_detect_pair).
   // creates the (det, desc) entries up front, so that passes of different detectors may then fill them from different threads
   void Prepare(const std::string& det, const std::string& desc) { Blocks[det][desc]; slot_state[det]; }
+  // Feature cache, text format of the reference (imagerepresentation.cpp:2139-2215; record = saveAR, :89-99): files written here are
+  // read by the reference's `read_pre_extracted` flow and by build/read_features.m, and vice versa.  Loaded regions live on the host
+  // only (MatchImgReps then uploads them; the device-resident fast path needs regions detected in this process).
+  void SaveRegions(std::string fname, int mode = 0) const;
+  void LoadRegions(std::string fname);
   void AppendViewFrom(mb2_ctx* from, const std::string& det, const std::string& desc, int n, int synth);
   GrayImage OriginalImg;
   friend class CorrespondenceBank;
@@ -228,6 +233,9 @@ int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img1, const in
  * driver (mods_b200/sharding.py), where rank 0 verifies the tentatives gathered from all ranks.  Returns the verified count. */
 int mb2_host_verify(mb2_ctx* ctx, const double* frames14, const double* key, int n, const mb2_pair_config* cfg, mb2_pair_result* res,
                     double* verified_out, int capacity);
+/* test doors: feature cache of one (detector, descriptor) set through ImageRepresentation::SaveRegions / LoadRegions */
+int mb2_host_save_regions(const char* fname, const char* det, const char* desc, int n, const double* det_kp, const double* reproj_kp, const uint8_t* desc_u8);
+int mb2_host_load_regions(const char* fname, const char* det, const char* desc, int capacity, double* det_kp, double* reproj_kp, uint8_t* desc_u8);
 /* test door: SetVSPars for one step; out rows = (zoom, tilt, phi); prev (n_prev rows, same layout) = views of earlier steps */
 int mb2_host_set_vs_pars(const double* scales, int n_scales, const double* tilts, int n_tilts, double phi_base, const double* prev, int n_prev,
                          double* out, int capacity);

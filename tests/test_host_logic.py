@@ -61,3 +61,42 @@ def test_set_vs_pars_view_counts_of_iters_mods_cviu():
     assert np.allclose(h4[0], (1, 1, 0)) and np.allclose(h4[1], (1, 2, 0)) and np.allclose(h4[2:4, 2], (0, np.pi / 2))
     v = _set_vs_pars(H, [1], [-3], 360, [])   # negative tilt in the set: floor(180 * -3 / 360) < 0 -> "no rotation" mode, two views (:144-169)
     assert len(v) == 2 and np.allclose(v[0], (1, 3, 0)) and np.allclose(v[1], (1, -3, 0))
+
+
+def test_feature_cache_format_and_round_trip(tmp_path):
+    """ImageRepresentation::SaveRegions / LoadRegions (imagerepresentation.cpp:2139-2215): the reference's text format, record by
+    record (saveAR :89-99 = ids, det_kp, reproj_kp as `x y a11 a12 a21 a22 pyramid_scale octave_number s sub_type`, descriptor size,
+    descriptor values; C++ default stream formatting = %g with 6 significant digits), and the values survive a round trip."""
+    mb.build()
+    H = mb.host_lib()
+    rng = np.random.default_rng(3)
+    n = 7
+    det = np.zeros((n, 9)); rep = np.zeros((n, 9))
+    for a in (det, rep):
+        a[:, 0:2] = rng.random((n, 2)) * 4000; a[:, 2:6] = rng.normal(size=(n, 4)); a[:, 6] = rng.random(n) * 30 + 1
+        a[:, 7] = rng.normal(size=n) * 100; a[:, 8] = rng.integers(0, 22, n)
+    desc = rng.integers(0, 256, (n, 128)).astype(np.uint8)
+    f = str(tmp_path / "regions.txt").encode()
+    assert H.mb2_host_save_regions(f, b"MSER", b"RootSIFT", C.c_int(n), det.ctypes.data_as(C.c_void_p), rep.ctypes.data_as(C.c_void_p),
+                                   desc.ctypes.data_as(C.c_void_p)) == n
+    lines = open(f.decode()).read().split("\n")
+    assert lines[0] == "1" and lines[1] == "MSER 1" and lines[2] == "RootSIFT %d" % n and lines[3] == "128"
+
+    def kp(v):
+        return " ".join("%g" % x for x in v[:6]) + " 0 0 " + "%g" % v[6] + " %d " % int(v[8])
+    for i in range(n):
+        want = "%d 0 0 0 " % i + kp(det[i]) + kp(rep[i]) + " 128 " + " ".join("%d" % d for d in desc[i]) + " "
+        assert lines[4 + i] == want, i
+    d2 = np.zeros((n, 9)); r2 = np.zeros((n, 9)); u2 = np.zeros((n, 128), np.uint8)
+    assert H.mb2_host_load_regions(f, b"MSER", b"RootSIFT", C.c_int(n), d2.ctypes.data_as(C.c_void_p), r2.ctypes.data_as(C.c_void_p),
+                                   u2.ctypes.data_as(C.c_void_p)) == n
+    assert np.array_equal(u2, desc)
+    for got, src in ((d2, det), (r2, rep)):
+        assert np.allclose(got[:, :7], src[:, :7], rtol=1e-5) and np.array_equal(got[:, 8], src[:, 8]) and np.all(got[:, 7] == 0)   # response is not in the format
+    # a file as the reference writes it: a "None" list without descriptors next to the described one
+    txt = "1\nHessianAffine 2\nNone 1\n0\n0 0 0 0 1 2 1 0 0 1 0 0 3 1 1 2 1 0 0 1 0 0 3 1  0 \nRootSIFT 1\n128\n" + lines[4] + "\n"
+    g = str(tmp_path / "ref_style.txt")
+    open(g, "w").write(txt)
+    assert H.mb2_host_load_regions(g.encode(), b"HessianAffine", b"RootSIFT", C.c_int(n), d2.ctypes.data_as(C.c_void_p), r2.ctypes.data_as(C.c_void_p),
+                                   u2.ctypes.data_as(C.c_void_p)) == 1
+    assert np.array_equal(u2[0], desc[0])
