@@ -38,6 +38,12 @@ void HDsidx(const double*, const double*, const double*, double*, int, int*, int
 void HDsSymidx(const double*, const double*, const double*, double*, int, int*, int);
 void HDsSymidxMax(const double*, const double*, const double*, double*, int, int*, int);
 void FDs(const double* u, const double* F, double* p, int len);
+typedef void (*FDsPtr)(const double*, const double*, double*, int);                  // Fcustomdef.h:3
+typedef void (*exFDsPtr)(const double*, const double*, double*, double*, int);      // Fcustomdef.h:4
+void exFDs(const double* u, const double* F, double* p, double* w, int len);
+void exFDsSym(const double* u, const double* F, double* p, double* w, int len);
+int exp_ransacFcustom(double* u, int len, double th, double conf, int max_sam, double* F, unsigned char* inl, int* data_out, int do_lo,
+                      unsigned inlLimit, double** resids, double* H_best, int* Ih, exFDsPtr EXFDS1, FDsPtr FDS1, int doSymCheck);   // exp_ranF.h:70-72
 void FDsSym(const double* u, const double* F, double* p, int len);
 int nsamples(int ninl, int ptNum, int samsiz, double conf);
 Score exp_ransacHcustom(double* u, int len, double th, double conf, int max_sam, double* H, unsigned char* inl,
@@ -367,6 +373,23 @@ double ref_exp_ransacH(const double* u, int len, double th, double conf, int max
   free(resids);
   out4[0] = (int)s.I; out4[1] = data_out[0]; out4[2] = data_out[1]; out4[3] = data_out[2];
   return s.J;
+}
+
+// exp_ransacFcustom (exp_ranF.c:795) exactly as LORANSACFiltering calls it in F mode (matching.cpp:883): 7-point LO-RANSAC with the
+// DEGENSAC plane-and-parallax branch; srand(time(NULL)) sees mb2_ref_seed.  errorType: 0 Sampson, otherwise symmetric epipolar.
+// out4: I, samples, LO count, Ih (inliers of the best homography met on the way).
+int ref_exp_ransacF(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, double* F,
+                    unsigned char* inl, int* out4) {
+  mb2_ref_seed = seed;
+  std::vector<double> uc(u, u + (size_t)len * 6);
+  std::vector<int> data_out((size_t)len * 18 + 8, 0);
+  double* resids = 0; double Hbest[9] = {0}; int Ih = 0;
+  FDsPtr a = errorType == 0 ? &FDs : &FDsSym;
+  exFDsPtr b = errorType == 0 ? &exFDs : &exFDsSym;
+  const int I = exp_ransacFcustom(uc.data(), len, th, conf, max_sam, F, inl, data_out.data(), 1, (unsigned)len, &resids, Hbest, &Ih, b, a, doSymCheck);
+  free(resids);
+  out4[0] = I; out4[1] = data_out[0]; out4[2] = data_out[1]; out4[3] = Ih;
+  return I;
 }
 
 }  // extern "C"

@@ -156,3 +156,16 @@ def test_hessaff_detector_modes(oracle, reference, mode, regs, rel):
     hp = HessParams.default(); hp.mode = mode; hp.reg_number = regs; hp.rel_threshold = rel; hp.rel_reg_number = rel if mode == 3 else -1.0
     a, b = oracle.hessaff_detect(im, hp, raw=True), reference.hessaff_detect(im, hp, raw=True)
     assert len(a) > 20 and np.array_equal(a, b)
+
+
+def test_reference_f_ransac_is_pinned_by_golden_vectors(reference):
+    """exp_ransacFcustom (exp_ranF.c:795, DEGENSAC on) of the compiled reference with a fixed seed reproduces the committed vectors: the
+    target the F driver (row a19, not built yet) will be held to."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ransac_f_vectors.npz"))
+    for seed in (1, 2):
+        for et in (0, 1):
+            r = reference.exp_ransacF(G["u"], seed=seed, errorType=et)
+            assert np.array_equal(r["inl"], G["inl_s%d_e%d" % (seed, et)])
+            assert [r["I"], r["samples"], r["lo"], r["Ih"]] == G["stats_s%d_e%d" % (seed, et)].tolist()
+            assert np.allclose(r["F"], G["F_s%d_e%d" % (seed, et)], rtol=1e-9, atol=1e-12)
