@@ -237,7 +237,8 @@ int mb2_match_slots(mb2_ctx* ctx, int q_slot, int t_slot, double matchRatio, dou
  * HDsSym :199-240, HDsSymMax :241-282) and `FDsPtr` (degensac/Fcustomdef.h:3; FDs Ftools.c:82-100,
  * FDsSym :102-123).  u: len*6 doubles (x1 y1 1 x2 y2 1) [H|D]; models: K*9 doubles (h stored as in
  * DEGENSAC, column-wise, 2nd image -> 1st) [H|D].  which: 0 HDs, 1 HDsSym, 2 HDsSymMax, 3 FDs,
- * 4 FDsSym.  Outputs [H], each may be NULL: resid K*len doubles; I[K] = #{d <= th};
+ * 4 FDsSym, 5 the residual of exFDsSym (Ftools.c:172-196; same quantity as FDsSym, formed as r^2 / (ab/(a+b)), which is what the
+ * F-matrix LO thresholds).  Outputs [H], each may be NULL: resid K*len doubles; I[K] = #{d <= th};
  * J[K] = sum truncQuad(d, th) (rtools.c:228-236). */
 int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const double* models, int K,
                      double th, double* resid, int* I, double* J);
@@ -254,6 +255,22 @@ int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const do
 int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, double conf, int max_sam,
                  int errorType, int doSymCheck, long seed, double* H, unsigned char* inl, int* data_out,
                  double* J);
+
+/* Replaces `int exp_ransacFcustom(double* u, int len, double th, double conf, int max_sam, double* F,
+ * unsigned char* inl, int* data_out, int do_lo, unsigned inlLimit, double** resids, double* H_best, int* Ih,
+ * exFDsPtr EXFDS1, FDsPtr FDS1, int doSymCheck)` (degensac/exp_ranF.h:70-72, exp_ranF.c:795-1192) as
+ * LORANSACFiltering calls it in F mode (matching/matching.cpp:883, which passes inlLimit = 0 and
+ * do_lo = pars.localOptimization): 7-point LO-RANSAC with MSAC scoring, oriented-epipolar and symmetric-distance
+ * checks, the DEGENSAC test of every so-far-the-best sample (checksample -> innerH -> plane-and-parallax rFtH)
+ * and the inner-RANSAC + iterated weighted LSQ local optimisation.  The 7-point models (up to 3 per sample) are
+ * generated on the host from the reference's rand() stream (`seed` stands in for time(NULL)), scored in batches
+ * on the GPU and replayed through the reference's sequential logic; all later residual vectors are GPU launches
+ * too.  errorType: 0 Sampson (FDs / exFDs), otherwise symmetric epipolar (FDsSym / exFDsSym).
+ * u [H]: len*6 doubles; F [H]: 9 doubles; inl [H]: len flags.  data_out[0..3] = samples, LO count, Ih (inliers of
+ * the best homography met by the degeneracy test), scorer launches.  Returns #inliers (maxS.I), < 0 on error. */
+int mb2_ransac_f(mb2_ctx* ctx, const double* u, int len, double th, double conf, int max_sam,
+                 int errorType, int doSymCheck, int do_lo, unsigned inlLimit, long seed, double* F,
+                 unsigned char* inl, int* data_out, double* J);
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
 /* Copies one plane of the most recent scale-space pyramid (ScalePyramid / Octave::blurs,

@@ -17,7 +17,7 @@ KP = 9
 EXPORTS = [
     "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
-    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
+    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_ransac_f", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
     "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair", "mb2_synth_view", "mb2_detect_describe_synth_view", "mb2_ctx_tree_epoch", "mb2_ctx_wait_tree", "mb2_ctx_create_prio",
 ]
 
@@ -119,7 +119,8 @@ class PairConfig(C.Structure):
                 ("err_threshold", C.c_double), ("confidence", C.c_double), ("HLAFCoef", C.c_double),
                 ("max_samples", C.c_int), ("errorType", C.c_int), ("doSymmCheck", C.c_int), ("seed", C.c_long),
                 ("use_mser", C.c_int), ("mser", MserParams), ("mserMatchRatio", C.c_double),
-                ("n_hess_views", C.c_int), ("n_mser_views", C.c_int), ("hess_views", ViewParams * 32), ("mser_views", ViewParams * 32)]
+                ("n_hess_views", C.c_int), ("n_mser_views", C.c_int), ("hess_views", ViewParams * 32), ("mser_views", ViewParams * 32),
+                ("useF", C.c_int), ("localOptimization", C.c_int), ("LAFCoef", C.c_double)]
 
     def set_views(self, hess=None, mser=None):
         """View tiers of the step: lists of (tilt, phi, zoom[, InitSigma]) as SetVSPars produces them; None = identity view only."""
@@ -407,6 +408,16 @@ class Context:
         n = self._check(host_lib().mb2_host_verify(self.h, _ptr(frames14), _ptr(keys), C.c_int(len(keys)), C.byref(cfg), C.byref(res), _ptr(out),
                                                    C.c_int(capacity)), "host_verify")
         return res, (out[:min(n, capacity)] if capacity else None)
+
+    def ransac_f(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1, do_lo=1, inlLimit=None):
+        """exp_ransacFcustom (degensac/exp_ranF.c:795).  inlLimit None = len (no limit); LORANSACFiltering passes 0."""
+        u = np.ascontiguousarray(u, np.float64)
+        n = len(u)
+        F = np.zeros(9); inl = np.zeros(max(1, n), np.uint8); data = np.zeros(4, np.int32); J = C.c_double()
+        I = self._check(lib().mb2_ransac_f(self.h, _ptr(u), C.c_int(n), C.c_double(th), C.c_double(conf), C.c_int(max_sam),
+                                           C.c_int(errorType), C.c_int(doSymCheck), C.c_int(do_lo), C.c_uint(n if inlLimit is None else inlLimit),
+                                           C.c_long(seed), _ptr(F), _ptr(inl), _ptr(data), C.byref(J)), "ransac_f")
+        return dict(F=F, inl=inl[:n], I=I, samples=int(data[0]), lo=int(data[1]), Ih=int(data[2]), launches=int(data[3]), J=J.value)
 
     def ransac_h(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1):
         u = np.ascontiguousarray(u, np.float64)

@@ -1058,7 +1058,7 @@ int mb2_match_slots(mb2_ctx* ctx, int q_slot, int t_slot, double matchRatio, dou
 
 int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const double* models, int K, double th, double* resid, int* I,
                      double* J) {
-  if (!ctx || !u || !models || len < 0 || K < 0 || which < 0 || which > 4) return MB2_ERR_ARG;
+  if (!ctx || !u || !models || len < 0 || K < 0 || which < 0 || which > 5) return MB2_ERR_ARG;
   cudaSetDevice(ctx->device);
   if (len == 0 || K == 0) return 0;
   const void *du, *dm;

@@ -10,3 +10,4 @@
 #include "synth.cu"
 #include "capi.cu"
 #include "ransac_host.cu"
+#include "ransac_f_host.cu"

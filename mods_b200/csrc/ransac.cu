@@ -11,66 +11,8 @@
 #define MB2_NS mb2_ransac_detail
 #include "ransac.cuh"
 
-// matutls/minv.c for n = 3, restated with indices (column-wise LU with row pivoting, in place).
-__host__ __device__ bool mb2_minv3(double* a) {
-  const int n = 3;
-  int le[3];
-  double q0[3], tq = 0., zr = 1.e-15;
-#define A_(r, c) a[(r) * n + (c)]
-  for (int j = 0; j < n; ++j) {
-    if (j > 0) {
-      for (int i = 0; i < n; ++i) q0[i] = A_(i, j);
-      for (int i = 1; i < n; ++i) {
-        int lc = i < j ? i : j;
-        double t = 0.;
-        for (int k = 0; k < lc; ++k) t += A_(i, k) * q0[k];
-        q0[i] -= t;
-      }
-      for (int i = 0; i < n; ++i) A_(i, j) = q0[i];
-    }
-    double s = fabs(A_(j, j));
-    int lc = j;
-    for (int k = j + 1; k < n; ++k) { double t = fabs(A_(k, j)); if (t > s) { s = t; lc = k; } }
-    tq = tq > s ? tq : s;
-    if (s < zr * tq) return false;
-    le[j] = lc;
-    if (lc != j) for (int k = 0; k < n; ++k) { double t = A_(j, k); A_(j, k) = A_(lc, k); A_(lc, k) = t; }
-    double t = 1. / A_(j, j);
-    for (int k = j + 1; k < n; ++k) A_(k, j) *= t;
-    A_(j, j) = t;
-  }
-  for (int j = 1; j < n; ++j) for (int k = 0; k < j; ++k) A_(k, j) *= A_(j, j);
-  for (int j = 1; j < n; ++j) {
-    for (int i = 0; i < j; ++i) q0[i] = A_(i, j);
-    for (int k = 0; k < j; ++k) { double t = 0.; for (int i = k; i < j; ++i) t -= A_(k, i) * q0[i]; q0[k] = t; }
-    for (int i = 0; i < j; ++i) A_(i, j) = q0[i];
-  }
-  for (int j = n - 2; j >= 0; --j) {
-    int m = n - j - 1;
-    for (int i = 0; i < m; ++i) q0[i] = A_(j + 1 + i, j);
-    for (int k = n - 1; k > j; --k) {
-      double t = -A_(k, j);
-      for (int i = j + 1, q = 0; i < k; ++i, ++q) t -= A_(k, i) * q0[q];
-      q0[--m] = t;
-    }
-    m = n - j - 1;
-    for (int i = 0; i < m; ++i) A_(j + 1 + i, j) = q0[i];
-  }
-  for (int k = 0; k < n - 1; ++k) {
-    for (int i = 0; i < n; ++i) q0[i] = A_(i, k);
-    for (int j = 0; j < n; ++j) {
-      double t; int i;
-      if (j > k) { t = 0.; i = j; } else { t = q0[j]; i = k + 1; }
-      for (; i < n; ++i) t += A_(j, i) * q0[i];
-      q0[j] = t;
-    }
-    for (int i = 0; i < n; ++i) A_(i, k) = q0[i];
-  }
-  for (int j = n - 2; j >= 0; --j)
-    for (int k = 0; k < n; ++k) { double t = A_(k, j); A_(k, j) = A_(k, le[j]); A_(k, le[j]) = t; }
-#undef A_
-  return true;
-}
+#include "minv3.hpp"
+__host__ __device__ bool mb2_minv3(double* a) { return mb2_minv3_impl(a); }
 
 namespace MB2_NS {
 
@@ -121,7 +63,8 @@ __device__ __forceinline__ double score_HDsSym(const double* u, const double* Hi
   return useMax ? (d1 < d2 ? d2 : d1) : d1 + d2;
 }
 
-__device__ __forceinline__ double score_FDs(const double* u, const double* F, bool sym) {
+// sym: 0 FDs, 1 FDsSym, 2 the residual exFDsSym returns (Ftools.c:172-196: r^2 / (a b / (a + b)), used inside the F-matrix LO)
+__device__ __forceinline__ double score_FDs(const double* u, const double* F, int sym) {
   const double u1 = u[0], u2 = u[1], u4 = u[3], u5 = u[4];
   const double rxc = F[0] * u4 + F[3] * u5 + F[6];
   const double ryc = F[1] * u4 + F[4] * u5 + F[7];
@@ -131,7 +74,9 @@ __device__ __forceinline__ double score_FDs(const double* u, const double* F, bo
   const double ry = F[3] * u1 + F[4] * u2 + F[5];
   if (!sym) return r * r / (rxc * rxc + ryc * ryc + rx * rx + ry * ry);
   const double a = rxc * rxc + ryc * ryc, b = rx * rx + ry * ry;
-  return r * r * (a + b) / (a * b);
+  if (sym == 1) return r * r * (a + b) / (a * b);
+  const double w = (a * b) / (a + b);
+  return r * r / w;
 }
 
 // rtools.c:228-236
@@ -181,8 +126,9 @@ k_score(int which, const double* __restrict__ u, int len, int chunk, const doubl
       case 0: d = score_HDs(p, sM); break;
       case 1: d = score_HDsSym(p, sHinv, sH1, false); break;
       case 2: d = score_HDsSym(p, sHinv, sH1, true); break;
-      case 3: d = score_FDs(p, sM, false); break;
-      default: d = score_FDs(p, sM, true); break;
+      case 3: d = score_FDs(p, sM, 0); break;
+      case 4: d = score_FDs(p, sM, 1); break;
+      default: d = score_FDs(p, sM, 2); break;
     }
     if (resid) resid[(size_t)k * len + i] = d;
     if (d <= th) I++;

@@ -1,0 +1,289 @@
+// Host-side numerics shared by the LO-RANSAC drivers (H: ransac_host.cu, F: ransac_f_logic.hpp).  Plain C++ (no CUDA), so the same
+// code is compiled into the library and into tests/native/ransac_f_cpu.cpp.
+// Reference: degensac/rtools.c, utools.c, Htools.c, hash.c (line numbers at each function).
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+
+namespace mb2_ransac_common {
+struct Score { unsigned I; double J; };
+
+constexpr int ITER_SAM = 50, RAN_REP = 10, ILSQ_ITERS = 4, TC = 4, MWM = (9 / 4);  // rtools.h:7-35 (MWM is an int: 2)
+constexpr int MAX_SAMPLES = 1000000;
+constexpr double DEGENSAC_EPS = 2.2204e-16;
+constexpr double CHECK_COEF = 9.0;
+constexpr int MIN_GOOD_SYM_PTS = 5;
+
+inline double truncQuad(double epsilon, double thr) {
+  if (thr == 0) return 0;
+  if (epsilon >= thr * 9 / 4) return 0;
+  return 1 - (epsilon / (thr * 9 / 4));
+}
+inline int scoreLess(const Score a, const Score b) { return a.J < b.J; }  // __SCORE__ == SC_M
+inline Score inlidxs(const double* err, int len, double th, int* inl) {
+  Score s = {0, 0};
+  for (int i = 0; i < len; ++i) {
+    s.J += truncQuad(err[i], th);
+    if (err[i] <= th) { inl[s.I] = i; ++(s.I); }
+  }
+  return s;
+}
+// same index list and count, without the MSAC sum (for the call sites that only read S.I and the list)
+inline unsigned inlidxs_count(const double* err, int len, double th, int* inl) {
+  unsigned I = 0;
+  for (int i = 0; i < len; ++i) { inl[I] = i; I += err[i] <= th ? 1u : 0u; }
+  return I;
+}
+inline int nsamples(int ninl, int ptNum, int samsiz, double conf) {
+  double a = 1, b = 1;
+  for (int i = 0; i < samsiz; i++) { a *= ninl - i; b *= ptNum - i; }
+  a = a / b;
+  if (a < DEGENSAC_EPS) return MAX_SAMPLES;
+  a = 1 - a;
+  if (a < DEGENSAC_EPS) return 1;
+  b = std::log(1 - conf) / std::log(a);
+  if (b > MAX_SAMPLES) return MAX_SAMPLES;
+  return (int)std::ceil(b);
+}
+inline double det3(const double* A) {
+  double r = (A[0] * A[4] * A[8] + A[2] * A[3] * A[7] + A[1] * A[5] * A[6]);
+  r -= (A[2] * A[4] * A[6] + A[0] * A[5] * A[7] + A[1] * A[3] * A[8]);
+  return r;
+}
+
+// glibc rand()/srand() stream with private state (TYPE_3, 128-byte state, same as the default generator)
+struct LibcRand {
+  struct random_data buf;
+  char state[128];
+  LibcRand() { std::memset(&buf, 0, sizeof buf); std::memset(state, 0, sizeof state); initstate_r(1, state, sizeof state, &buf); }
+  LibcRand(const LibcRand& o) { copy_from(o); }
+  LibcRand& operator=(const LibcRand& o) { if (this != &o) copy_from(o); return *this; }
+  void seed(unsigned s) { srandom_r(s, &buf); }
+  int next() { int32_t r; random_r(&buf, &r); return (int)r; }
+ private:
+  void copy_from(const LibcRand& o) {  // random_data holds pointers into `state`: rebase them
+    std::memcpy(state, o.state, sizeof state);
+    buf = o.buf;
+    const ptrdiff_t shift = state - o.state;
+    buf.fptr = (int32_t*)((char*)o.buf.fptr + shift); buf.rptr = (int32_t*)((char*)o.buf.rptr + shift);
+    buf.state = (int32_t*)((char*)o.buf.state + shift); buf.end_ptr = (int32_t*)((char*)o.buf.end_ptr + shift);
+  }
+};
+
+// rows 2q, 2q+1 of lin_hg's matrix (Htools.c:17-55) for correspondence q
+inline void lin_rows(const double* u, int q, double* r0, double* r1) {
+  const double* s = u + 6 * q;
+  r0[0] = s[3]; r0[1] = 0; r0[2] = -s[0] * s[3]; r0[3] = s[4]; r0[4] = 0; r0[5] = -s[0] * s[4]; r0[6] = s[5]; r0[7] = 0; r0[8] = -s[0] * s[5];
+  r1[0] = 0; r1[1] = s[3]; r1[2] = -s[1] * s[3]; r1[3] = 0; r1[4] = s[4]; r1[5] = -s[1] * s[4]; r1[6] = 0; r1[7] = s[5]; r1[8] = -s[1] * s[5];
+}
+
+// utools.c:97-167 (Gauss-Jordan with column pivoting bookkeeping; matrix row-wise)
+inline int nullspace(double* matrix, double* nullsp, int n, int* buffer) {
+  int* pnopivot = buffer; int nonpivot = 0;
+  int* ppivot = buffer + n;
+  int i = 0;
+  const double tol = 1e-12;
+  for (int j = 0; j < n; j++) {
+    double pivot = std::fabs(matrix[n * i + j]); int max = i;
+    for (int k = i + 1; k < n; k++) { double t = std::fabs(matrix[n * k + j]); if (pivot < t) { pivot = t; max = k; } }
+    if (pivot < tol) {
+      *(pnopivot++) = j; nonpivot++;
+      for (int k = i; k < n; k++) matrix[n * k + j] = 0;
+    } else {
+      *(ppivot++) = j;
+      for (int k = j; k < n; k++) { double t = matrix[i * n + k]; matrix[i * n + k] = matrix[max * n + k]; matrix[max * n + k] = t; }
+      pivot = matrix[i * n + j];
+      for (int k = j; k < n; k++) matrix[i * n + k] /= pivot;
+      for (int k = 0; k < i; k++) { pivot = -matrix[k * n + j]; for (int l = j; l < n; l++) matrix[k * n + l] += pivot * matrix[i * n + l]; }
+      for (int k = i + 1; k < n; k++) { pivot = matrix[k * n + j]; for (int l = j; l < n; l++) matrix[k * n + l] -= pivot * matrix[i * n + l]; }
+      i++;
+    }
+  }
+  for (int k = 0; k < nonpivot; k++) {
+    int j = buffer[k];
+    for (int l = 0; l < n - nonpivot; l++) nullsp[k * n + buffer[n + l]] = -matrix[l * n + j];
+    for (int l = 0; l < nonpivot; l++) nullsp[k * n + buffer[l]] = (j == buffer[l]) ? 1 : 0;
+  }
+  return nonpivot;
+}
+
+// Htools.c:543-569
+inline void cross3(double* out, const double* a, const double* b) {
+  out[0] = a[1] * b[2] - a[2] * b[1]; out[1] = a[2] * b[0] - a[0] * b[2]; out[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline int all_Hori_valid(const double* us, const int* idx) {
+  double p[3], q[3];
+  const double *a = us + 6 * idx[0], *b = us + 6 * idx[1], *c = us + 6 * idx[2], *d = us + 6 * idx[3];
+  cross3(p, a, b); cross3(q, a + 3, b + 3);
+  if ((p[0] * c[0] + p[1] * c[1] + p[2] * c[2]) * (q[0] * c[3] + q[1] * c[4] + q[2] * c[5]) < 0) return 0;
+  if ((p[0] * d[0] + p[1] * d[1] + p[2] * d[2]) * (q[0] * d[3] + q[1] * d[4] + q[2] * d[5]) < 0) return 0;
+  cross3(p, c, d); cross3(q, c + 3, d + 3);
+  if ((p[0] * a[0] + p[1] * a[1] + p[2] * a[2]) * (q[0] * a[3] + q[1] * a[4] + q[2] * a[5]) < 0) return 0;
+  if ((p[0] * b[0] + p[1] * b[1] + p[2] * b[2]) * (q[0] * b[3] + q[1] * b[4] + q[2] * b[5]) < 0) return 0;
+  return 1;
+}
+
+// Smallest eigenvector of a symmetric 9x9 (stands in for LAPACK dsyev in lap_eig, lapwrap.c:67-97)
+inline void smallest_eigvec9(const double* C, double* v) {
+  const int n = 9;
+  double A[81], V[81];
+  std::memcpy(A, C, sizeof A);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < n; i++) { diag += A[i * n + i] * A[i * n + i]; for (int j = i + 1; j < n; j++) off += A[i * n + j] * A[i * n + j]; }
+    if (off <= 1e-32 * diag || off == 0) break;
+    for (int p = 0; p < n - 1; p++)
+      for (int q = p + 1; q < n; q++) {
+        const double apq = A[p * n + q];
+        if (apq == 0) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < n; k++) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          const double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int best = 0;
+  for (int i = 1; i < n; i++) if (A[i * n + i] < A[best * n + best]) best = i;
+  for (int k = 0; k < n; k++) v[k] = V[k * n + best];
+}
+
+// utools.c:7-50
+inline void normu(const double* u, const int* inl, int len, double* A1, double* A2) {
+  for (int j = 0; j < 3; j++) { A1[j] = 0; A2[j] = 0; }
+  for (int j = 0; j < len; j++) { const double* p = u + 6 * inl[j]; A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[3]; A2[2] += p[4]; }
+  if (len > 0) for (int i = 1; i < 3; i++) { A1[i] /= len; A2[i] /= len; }
+  for (int j = 0; j < len; j++) {
+    const double* p = u + 6 * inl[j];
+    double a = p[0] - A1[1], b = p[1] - A1[2];
+    A1[0] += std::sqrt(a * a + b * b);
+    a = p[3] - A2[1]; b = p[4] - A2[2];
+    A2[0] += std::sqrt(a * a + b * b);
+  }
+  if (A1[0] != 0) A1[0] = len * std::sqrt(2) / A1[0];
+  if (A2[0] != 0) A2[0] = len * std::sqrt(2) / A2[0];
+  A1[1] *= -A1[0]; A1[2] *= -A1[0];
+  A2[1] *= -A2[0]; A2[2] *= -A2[0];
+}
+// utools.c:70-89
+inline void denormH(double* F, const double* A1, const double* A2) {
+  double r = A2[0], x = A2[1], y = A2[2];
+  F[6] += x * F[0] + y * F[3];
+  F[7] += x * F[1] + y * F[4];
+  F[8] += x * F[2] + y * F[5];
+  F[0] *= r; F[1] *= r; F[2] *= r; F[3] *= r; F[4] *= r; F[5] *= r;
+  r = 1 / A1[0]; x = -A1[1] * r; y = -A1[2] * r;
+  for (int i = 0; i < 9; i += 3) { F[i] = r * F[i] + x * F[i + 2]; F[i + 1] = r * F[i + 1] + y * F[i + 2]; }
+}
+// Htools.c:98-130 (u2h): exact 4-point nullspace or normalised-DLT least squares
+inline void u2h(const double* u, const int* inl, int len, double* H) {
+  if (len < 4) return;
+  if (len == 4) {
+    double Z2[81], V[81];
+    int nb[18];
+    for (int i = 0; i < 4; i++) lin_rows(u, inl[i], Z2 + (2 * i) * 9, Z2 + (2 * i + 1) * 9);
+    for (int i = 72; i < 81; ++i) Z2[i] = 0.0;
+    std::memset(V, 0, sizeof V);
+    nullspace(Z2, V, 9, nb);
+    std::memcpy(H, V, 9 * sizeof(double));
+    return;
+  }
+  double A1[3], A2[3], C[81];
+  normu(u, inl, len, A1, A2);
+  // lin_hgN (Htools.c:57-96) rows folded straight into the 9x9 covariance.  cov_mat (utools.c:170-185)
+  // computes C[i][j] = sum_k Z[k][i] * Z[k][j] with k running over the rows in order; adding row 2i and
+  // then row 2i+1 of every point to all 45 accumulators performs exactly those additions in exactly that
+  // order, in one pass over the correspondences instead of 45 strided passes over a 2n x 9 matrix.
+  // Large inlier sets (LO on tens of thousands of points) are summed in fixed chunks on all host cores;
+  // the chunk boundaries do not depend on the thread count, so the result is machine-independent.  Short
+  // lists (one chunk) keep the reference's single serial chain bit for bit.
+  const int CH = 2048;
+  const int nchunks = len <= 2 * CH ? 1 : (len + CH - 1) / CH;
+  std::vector<double> part((size_t)nchunks * 45, 0.0);
+#pragma omp parallel for schedule(static) if (nchunks > 1)
+  for (int ck = 0; ck < nchunks; ck++) {
+    double* acc = part.data() + (size_t)ck * 45;
+    const int lo = nchunks == 1 ? 0 : ck * CH, hi = nchunks == 1 ? len : std::min(len, lo + CH);
+    for (int i = lo; i < hi; i++) {
+      const double* s = u + 6 * inl[i];
+      double a[3], b[3];
+      a[2] = 1; b[2] = 1;
+      a[0] = s[0] * A1[0] + A1[1]; a[1] = s[1] * A1[0] + A1[2];
+      b[0] = s[3] * A2[0] + A2[1]; b[1] = s[4] * A2[0] + A2[2];
+      double r0[9], r1[9];
+      for (int j = 0; j < 3; j++) {
+        r0[3 * j] = b[j]; r0[3 * j + 1] = 0; r0[3 * j + 2] = -a[0] * b[j];
+        r1[3 * j] = 0; r1[3 * j + 1] = b[j]; r1[3 * j + 2] = -a[1] * b[j];
+      }
+      // r0 is zero at columns 1, 4, 7 and r1 at 0, 3, 6: those products are +-0 and leave the sums unchanged
+      int t = 0;
+      for (int p = 0; p < 9; p++)
+        for (int q = 0; q <= p; q++, t++) {
+          if (p % 3 != 1 && q % 3 != 1) acc[t] += r0[p] * r0[q];
+          if (p % 3 != 0 && q % 3 != 0) acc[t] += r1[p] * r1[q];
+        }
+    }
+  }
+  double acc[45];
+  for (int t = 0; t < 45; t++) { acc[t] = part[t]; for (int ck = 1; ck < nchunks; ck++) acc[t] += part[(size_t)ck * 45 + t]; }
+  {
+    int t = 0;
+    for (int p = 0; p < 9; p++)
+      for (int q = 0; q <= p; q++, t++) { C[9 * p + q] = acc[t]; C[p + 9 * q] = acc[t]; }
+  }
+  smallest_eigvec9(C, H);
+  denormH(H, A1, A2);
+}
+
+// hash.c
+inline uint32_t SuperFastHash(const char* data, int len) {
+  uint32_t hash = len, tmp;
+  if (len <= 0 || data == 0) return 0;
+  auto get16 = [](const char* d) { return (uint32_t)(((uint32_t)((const uint8_t*)d)[1]) << 8) + (uint32_t)((const uint8_t*)d)[0]; };
+  int rem = len & 3;
+  len >>= 2;
+  for (; len > 0; len--) {
+    hash += get16(data);
+    tmp = (get16(data + 2) << 11) ^ hash;
+    hash = (hash << 16) ^ tmp;
+    data += 4;
+    hash += hash >> 11;
+  }
+  switch (rem) {
+    case 3: hash += get16(data); hash ^= hash << 16; hash ^= ((signed char)data[2]) << 18; hash += hash >> 11; break;
+    case 2: hash += get16(data); hash ^= hash << 11; hash += hash >> 17; break;
+    case 1: hash += (signed char)*data; hash ^= hash << 10; hash += hash >> 1;
+  }
+  hash ^= hash << 3; hash += hash >> 5; hash ^= hash << 4; hash += hash >> 17; hash ^= hash << 25; hash += hash >> 6;
+  return hash;
+}
+struct HashTable {
+  struct Field { uint32_t hash; int length, iterID; };
+  std::vector<Field> f[64];  // newest last; the reference prepends, so scan backwards
+  void insert(uint32_t h, int len, int id) { f[h % 64].push_back({h, len, id}); }
+  int contains(uint32_t h, int len, int id) const {
+    const auto& b = f[h % 64];
+    for (size_t i = b.size(); i-- > 0;) if (b[i].hash == h && b[i].length == len && b[i].iterID == id) return id;
+    for (size_t i = b.size(); i-- > 0;) if (b[i].hash == h && b[i].length == len) return b[i].iterID;
+    return -1;
+  }
+};
+
+}  // namespace mb2_ransac_common

@@ -470,7 +470,7 @@ void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r, con
   L0.swap(L);
 }
 
-// ---- LORANSACFiltering (matching.cpp:806-980), homography mode -------------------------------------
+// ---- LORANSACFiltering (matching.cpp:806-980), homography and epipolar modes -------------------------------------
 namespace {
 bool invert3(const double* S, double* D) {  // cv::invert, 3x3 closed form
   double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
@@ -492,7 +492,6 @@ int loransac_core(mb2_ctx* ctx, const double* frames, int tent_size, const RANSA
   verified.clear();
   int max_samples = pars.max_samples;
   if (tent_size <= 20) max_samples = 1000;
-  if (pars.useF) return 0;  // epipolar mode (exp_ransacFcustom) is not built: empty output, like a failed run
   if (tent_size < MIN_POINTS) return 0;
   std::vector<double> u((size_t)tent_size * 6);
   for (int i = 0; i < tent_size; i++) {
@@ -501,9 +500,43 @@ int loransac_core(mb2_ctx* ctx, const double* frames, int tent_size, const RANSA
     p[0] = f[0]; p[1] = f[1]; p[2] = 1.; p[3] = f[7]; p[4] = f[8]; p[5] = 1.;
   }
   double Hloran[9];
-  int data_out[3];
+  int data_out[4];
   double J = 0;
   const long seed = pars.seed ? pars.seed : (long)time(NULL);
+  if (pars.useF) {  // epipolar mode (matching.cpp:875-887, 959-971): exp_ransacFcustom with inlLimit 0, then F_LAF_check
+    const int I = mb2_ransac_f(ctx, u.data(), tent_size, pars.err_threshold * pars.err_threshold, pars.confidence, pars.max_samples,
+                               pars.errorType == SAMPSON ? 0 : 1, pars.doSymmCheck, pars.localOptimization, 0u, seed, Hloran, inl.data(), data_out, &J);
+    if (I < 0) return 0;
+    for (int i = 0; i < tent_size; i++) if (inl[i] || pars.justMarkOutliers) verified.push_back(i);
+    for (int i = 0; i < 9; i++) H[i] = Hloran[i];
+    // F_LAF_check (matching.cpp:193-250): the three points of each local affine frame against F, sum of the three distances
+    const double affineFerror = pars.LAFCoef * pars.err_threshold;
+    if (affineFerror > 0 && !verified.empty()) {
+      const double k_sigma = 3.0;  // matching.cpp:172
+      const size_t n = verified.size();
+      std::vector<double> u3(n * 18), err(n * 3);
+      for (size_t l = 0; l < n; l++) {
+        const double* f = frames + (size_t)verified[l] * 14;
+        double* q = &u3[l * 18];
+        q[0] = f[0]; q[1] = f[1]; q[2] = 1.0;
+        q[3] = f[7]; q[4] = f[8]; q[5] = 1.0;
+        q[6] = q[0] + k_sigma * f[3] * f[6]; q[7] = q[1] + k_sigma * f[5] * f[6]; q[8] = 1.0;
+        q[9] = q[3] + k_sigma * f[10] * f[13]; q[10] = q[4] + k_sigma * f[12] * f[13]; q[11] = 1.0;
+        q[12] = q[0] + k_sigma * f[2] * f[6]; q[13] = q[1] + k_sigma * f[4] * f[6]; q[14] = 1.0;
+        q[15] = q[3] + k_sigma * f[9] * f[13]; q[16] = q[4] + k_sigma * f[11] * f[13]; q[17] = 1.0;
+      }
+      if (mb2_score_models(ctx, pars.errorType == SAMPSON ? 3 : 4, u3.data(), (int)(n * 3), Hloran, 1, 0.0, err.data(), nullptr, nullptr) < 0) { verified.clear(); return 0; }
+      std::vector<int> good;
+      good.reserve(n);
+      for (size_t l = 0; l < n; l++) {
+        const double sumErr = std::sqrt(err[3 * l]) + std::sqrt(err[3 * l + 1]) + std::sqrt(err[3 * l + 2]);
+        if (!(sumErr > affineFerror)) good.push_back(verified[l]);
+      }
+      verified.swap(good);
+    }
+    if ((int)verified.size() < MIN_POINTS) verified.clear();
+    return (int)verified.size();
+  }
   int I = mb2_ransac_h(ctx, u.data(), tent_size, pars.err_threshold * pars.err_threshold, pars.confidence, max_samples,
                        (int)pars.errorType, pars.doSymmCheck, seed, Hloran, inl.data(), data_out, &J);
   if (I < 0) return 0;
@@ -582,7 +615,8 @@ int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, Tentati
   const int k = loransac_core(ctx, frames.data(), n, pars, inl, verified, Hout);
   for (int i = 0; i < n && i < (int)inl.size(); i++) in_corresp.TCList[i].isTrue = inl[i];
   for (int i : verified) ransac_corresp.TCList.push_back(in_corresp.TCList[i]);
-  for (int i = 0; i < 9; i++) { ransac_corresp.H[i] = Hout[i]; H[i] = Hout[i]; }
+  // homography mode writes both; epipolar mode leaves the caller's H alone and stores F in the list (matching.cpp:932-936, 969-970)
+  for (int i = 0; i < 9; i++) { ransac_corresp.H[i] = Hout[i]; if (!pars.useF) H[i] = Hout[i]; }
   return k;
 }
 
@@ -689,6 +723,7 @@ extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
   c->use_mser = 0; c->mser = dp.MSERParam; c->mserMatchRatio = 0.8;                 // iters_mods_cviu.ini:36 ([MSER0] FGINNThreshold)
   c->n_hess_views = c->n_mser_views = 0;
   std::memset(c->hess_views, 0, sizeof c->hess_views); std::memset(c->mser_views, 0, sizeof c->mser_views);
+  c->useF = 0; c->localOptimization = 1; c->LAFCoef = 2.0;                           // config_iter_mods_cviu.ini:168-169
 }
 
 namespace {
@@ -722,6 +757,7 @@ struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.in
     }
     rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
     rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
+    rp.useF = cfg->useF; rp.localOptimization = cfg->localOptimization; rp.LAFCoef = cfg->LAFCoef;
   }
 };
 

@@ -212,6 +212,10 @@ typedef struct {
    * only.  The views of one detector are appended in this order (imagerepresentation.cpp:2044-2045). */
   int n_hess_views, n_mser_views;
   mb2_view_params hess_views[MB2_MAX_PAIR_VIEWS], mser_views[MB2_MAX_PAIR_VIEWS];
+  /* verification model (RANSACPars, matching.hpp:146-171): useF = 1 runs the epipolar branch of LORANSACFiltering
+   * (exp_ransacFcustom + F_LAF_check) instead of the homography one */
+  int useF, localOptimization;
+  double LAFCoef;
 } mb2_pair_config;
 typedef struct {
   int regions1, regions2, tentatives, unique_tentatives, ransac_inliers, verified;

@@ -277,14 +277,15 @@ int orc_view_pipeline_synth(const float* img, int w, int h, int detector, const 
   return n;
 }
 
-// which: 0 HDs, 1 HDsSym, 2 HDsSymMax, 3 FDs, 4 FDsSym
+// which: 0 HDs, 1 HDsSym, 2 HDsSymMax, 3 FDs, 4 FDsSym, 5 exFDsSym's residual
 void orc_score(int which, const double* u, const double* M, double* d, int len) {
   switch (which) {
     case 0: HDs(u, M, d, len); break;
     case 1: HDsSymImpl(u, M, d, len, false); break;
     case 2: HDsSymImpl(u, M, d, len, true); break;
-    case 3: FDsImpl(u, M, d, len, false); break;
-    default: FDsImpl(u, M, d, len, true); break;
+    case 3: FDsImpl(u, M, d, len, 0); break;
+    case 4: FDsImpl(u, M, d, len, 1); break;
+    default: FDsImpl(u, M, d, len, 2); break;
   }
 }
 // out rows of 7 doubles: q idx0 idxJ idx1 d0 dJ d1

@@ -984,7 +984,8 @@ inline void HDsSymImpl(const double* u, const double* H, double* p, int len, boo
   }
 }
 
-inline void FDsImpl(const double* u, const double* F, double* p, int len, bool sym) {  // Ftools.c:82-123
+// sym: 0 FDs (Ftools.c:82-100), 1 FDsSym (:102-123), 2 the residual exFDsSym returns (:172-196: r^2 / (ab / (a + b)))
+inline void FDsImpl(const double* u, const double* F, double* p, int len, int sym) {
   for (int i = 0; i < len; i++, u += 6) {
     const double u1 = u[0], u2 = u[1], u4 = u[3], u5 = u[4];
     double rxc = F[0] * u4 + F[3] * u5 + F[6];
@@ -994,7 +995,11 @@ inline void FDsImpl(const double* u, const double* F, double* p, int len, bool s
     double rx = F[0] * u1 + F[1] * u2 + F[2];
     double ry = F[3] * u1 + F[4] * u2 + F[5];
     if (!sym) p[i] = r * r / (rxc * rxc + ryc * ryc + rx * rx + ry * ry);
-    else { double a = rxc * rxc + ryc * ryc, b = rx * rx + ry * ry; p[i] = r * r * (a + b) / (a * b); }
+    else {
+      double a = rxc * rxc + ryc * ryc, b = rx * rx + ry * ry;
+      if (sym == 1) p[i] = r * r * (a + b) / (a * b);
+      else { const double w = (a * b) / (a + b); p[i] = r * r / w; }
+    }
   }
 }
 

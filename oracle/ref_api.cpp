@@ -49,6 +49,10 @@ int nsamples(int ninl, int ptNum, int samsiz, double conf);
 Score exp_ransacHcustom(double* u, int len, double th, double conf, int max_sam, double* H, unsigned char* inl,
                         int iter_type, int* data_out, int oriented_constraint, unsigned inlLimit, double** resids,
                         HDsPtr HDS1, HDsiPtr HDSi1, HDsidxPtr HDSidx1, int doSymCheck);   // exp_ranH.h:32
+int svduv(double* d, double* a, double* u, int m, double* v, int n);                                    // matutls/svduv.c
+void u2f(const double* u, const int* inl, int len, double* F, double* buffer);                          // Ftools.c:311
+void u2fw(const double* u, const int* inl, const double* w, int len, double* F, double* buffer);        // Ftools.c:363
+int checksample(double* F, double* u7, double th, double* H);                                           // DegUtils.c:42
 long mb2_ref_seed = 1;
 }
 
@@ -378,18 +382,36 @@ double ref_exp_ransacH(const double* u, int len, double th, double conf, int max
 // exp_ransacFcustom (exp_ranF.c:795) exactly as LORANSACFiltering calls it in F mode (matching.cpp:883): 7-point LO-RANSAC with the
 // DEGENSAC plane-and-parallax branch; srand(time(NULL)) sees mb2_ref_seed.  errorType: 0 Sampson, otherwise symmetric epipolar.
 // out4: I, samples, LO count, Ih (inliers of the best homography met on the way).
+// inlLimit: LORANSACFiltering passes 0 (every LSQ of the LO then runs on 8 random inliers); ref_exp_ransacF keeps the "no limit"
+// form (inlLimit = len) the first golden vectors were made with.
+int ref_exp_ransacF2(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, unsigned inlLimit,
+                     double* F, unsigned char* inl, int* out4);
 int ref_exp_ransacF(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, double* F,
                     unsigned char* inl, int* out4) {
+  return ref_exp_ransacF2(u, len, th, conf, max_sam, errorType, doSymCheck, seed, (unsigned)len, F, inl, out4);
+}
+int ref_exp_ransacF2(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, unsigned inlLimit,
+                     double* F, unsigned char* inl, int* out4) {
   mb2_ref_seed = seed;
   std::vector<double> uc(u, u + (size_t)len * 6);
   std::vector<int> data_out((size_t)len * 18 + 8, 0);
   double* resids = 0; double Hbest[9] = {0}; int Ih = 0;
   FDsPtr a = errorType == 0 ? &FDs : &FDsSym;
   exFDsPtr b = errorType == 0 ? &exFDs : &exFDsSym;
-  const int I = exp_ransacFcustom(uc.data(), len, th, conf, max_sam, F, inl, data_out.data(), 1, (unsigned)len, &resids, Hbest, &Ih, b, a, doSymCheck);
+  const int I = exp_ransacFcustom(uc.data(), len, th, conf, max_sam, F, inl, data_out.data(), 1, inlLimit, &resids, Hbest, &Ih, b, a, doSymCheck);
   free(resids);
   out4[0] = I; out4[1] = data_out[0]; out4[2] = data_out[1]; out4[3] = Ih;
   return I;
+}
+// pieces of the F path on their own (unit comparisons of the restated numerics)
+void ref_svduv3_V(const double* A, double* V) { double a[9], d[3], U[9]; std::memcpy(a, A, sizeof a); svduv(d, a, U, 3, V, 3); }
+void ref_u2f(const double* u, const int* inl, const double* w, int len, double* F) {
+  std::vector<double> buf((size_t)9 * (len < 9 ? 9 : len));
+  if (w) u2fw(u, inl, w, len, F, buf.data()); else u2f(u, inl, len, F, buf.data());
+}
+int ref_checksample(const double* F, const double* u7, double th, double* H) {
+  double f[9], uu[42]; std::memcpy(f, F, sizeof f); std::memcpy(uu, u7, sizeof uu);
+  return checksample(f, uu, th, H);
 }
 
 }  // extern "C"

@@ -7,4 +7,12 @@
 extern long mb2_ref_seed;
 static inline time_t mb2_ref_time(void) { return (time_t)mb2_ref_seed; }
 #define time(x) mb2_ref_time()
+/* degensac/lapwrap.h:12 declares `typedef ptrdiff_t lapack_int` and passes pointers to such 64-bit integers to an LP64 LAPACK
+ * (32-bit INTEGER): sizes work by little-endian accident, but `info` keeps an UNINITIALISED upper half, so lap_SVD / lap_eig
+ * report failure depending on stack garbage (singulF then silently returns the identity, Ftools.c:294-297).  The oracle build
+ * pins the evidently intended behaviour -- LAPACK's own 32-bit info decides -- by making lapack_int a 32-bit int. */
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#define ptrdiff_t int
 #endif

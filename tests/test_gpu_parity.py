@@ -2,6 +2,7 @@
 committed reference vectors.  Bit-exact for keypoints, patches, descriptors, tentatives and
 residuals; the MSAC sum J to 1e-9 (fixed-order tree sum vs serial sum)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -222,7 +223,7 @@ def test_match_slots_equals_host_path(ctx):
 
 
 # ---- verification ------------------------------------------------------------------------------
-@pytest.mark.parametrize("which", range(5))
+@pytest.mark.parametrize("which", range(6))
 def test_batched_scorer(ctx, oracle, which):
     rng = np.random.default_rng(5)
     n, K = 3000, 33
@@ -285,6 +286,60 @@ def test_ransac_h_degenerate_inputs(ctx):
     assert ctx.ransac_h(u)["I"] == 0
 
 
+# ---- LO-RANSAC fundamental matrix (DEGENSAC) -------------------------------------------------------
+def _load_f_golden():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_f
+    return make_golden_f, np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ransac_f_vectors.npz"))
+
+
+def test_ransac_f_matches_reference_golden(ctx):
+    """exp_ransacFcustom of the reference on four scenes x seeds x error types x inlLimit forms (tests/golden/make_golden_f.py): same
+    inlier count, sample count, LO count, best-homography support, inlier mask; F up to scale."""
+    mg, GF = _load_f_golden()
+    for name, seed, et, lim in mg.CASES:
+        key = "%s_s%d_e%d_l%s" % (name, seed, et, lim)
+        u = GF["u_" + name]
+        r = ctx.ransac_f(u, seed=seed, errorType=et, inlLimit=None if lim == "n" else 0)
+        assert [r["I"], r["samples"], r["lo"], r["Ih"]] == GF["stats_" + key].tolist(), key
+        assert np.array_equal(r["inl"], np.unpackbits(GF["inl_" + key])[:len(u)]), key
+        assert _h_close(r["F"], GF["F_" + key]) < 1e-7, key
+        assert r["launches"] > 0
+
+
+@pytest.mark.parametrize("cfg", [dict(n=300, n_out=200, noise=1.0), dict(n=600, n_out=200, planar_frac=0.8), dict(n=2000, n_out=1200), dict(n=30, n_out=8)])
+def test_ransac_f_vs_reference_build(ctx, reference, cfg):
+    mg, _ = _load_f_golden()
+    u = mg.general_scene(21, **cfg)
+    for seed in (5, 6):
+        for et in (0, 1):
+            for lim in (None, 0):
+                a = reference.exp_ransacF(u, seed=seed, errorType=et, inlLimit=lim); b = ctx.ransac_f(u, seed=seed, errorType=et, inlLimit=lim)
+                assert [a[k] for k in ("I", "samples", "lo", "Ih")] == [b[k] for k in ("I", "samples", "lo", "Ih")], (cfg, seed, et, lim)
+                assert np.array_equal(a["inl"], b["inl"]) and _h_close(a["F"], b["F"]) < 1e-7
+
+
+def test_ransac_f_full_size_properties(ctx):
+    """BASELINE C3 size (30k tentatives, 40 % outliers): no oracle at this size in seconds, so size-independent properties -- the
+    mask is exactly {FDs(F) <= th} recomputed through the scorer, it recovers the planted inliers, F has rank 2 and the run is
+    repeatable."""
+    mg, _ = _load_f_golden()
+    n, n_out = 30000, 12000
+    u = mg.general_scene(4, n=n, n_out=n_out, noise=0.5)
+    r = ctx.ransac_f(u, seed=9, inlLimit=0)
+    _, _, R = ctx.score_models(3, u, r["F"][None, :], 9.0, want_resid=True)
+    assert np.array_equal(r["inl"], (R[0] <= 9.0).astype(np.uint8))
+    assert r["I"] == int(r["inl"].sum()) and r["I"] > 0.9 * (n - n_out)
+    assert np.linalg.svd(r["F"].reshape(3, 3))[1][2] < 1e-9 * np.linalg.svd(r["F"].reshape(3, 3))[1][0]
+    r2 = ctx.ransac_f(u, seed=9, inlLimit=0)
+    assert np.array_equal(r["inl"], r2["inl"]) and np.array_equal(r["F"], r2["F"])
+
+
+def test_ransac_f_degenerate_inputs(ctx):
+    assert ctx.ransac_f(np.zeros((0, 6)))["I"] == 0
+    assert ctx.ransac_f(np.ones((20, 6)))["inl"].sum() == 0
+
+
 # ---- one mods.cpp iteration through the host mirror (libmods_host.so) -------------------------------
 def _dup_filter_bruteforce(xy, key, r):
     """matching.cpp:2983-3047: stable sort by key, drop an entry when a kept one is within r in both images."""
@@ -327,6 +382,16 @@ def test_mods_pair_equals_stage_composition(ctx, oracle):
     Hgt = gt_homography(480, 360)
     p = np.c_[ver[:, :2], np.ones(len(ver))] @ Hgt.T
     assert np.median(np.hypot(p[:, 0] / p[:, 2] - ver[:, 2], p[:, 1] / p[:, 2] - ver[:, 3])) < 1.5
+    # the same pair verified in epipolar mode (RANSACPars.useF: exp_ransacFcustom with inlLimit 0 + F_LAF_check, matching.cpp:875-971)
+    cfg.useF = 1
+    resF, verF = ctx.mods_pair(A, B, cfg, capacity=4096)
+    assert (resF.tentatives, resF.unique_tentatives) == (res.tentatives, res.unique_tentatives)
+    rf = ctx.ransac_f(u, th=cfg.err_threshold ** 2, conf=cfg.confidence, max_sam=cfg.max_samples, errorType=0 if cfg.errorType == 0 else 1,
+                      doSymCheck=cfg.doSymmCheck, seed=cfg.seed, do_lo=cfg.localOptimization, inlLimit=0)
+    assert resF.ransac_inliers == int(rf["inl"].sum()) and _h_close(np.array(resF.H), rf["F"]) < 1e-12
+    assert 8 <= resF.verified <= resF.ransac_inliers
+    p = np.c_[verF[:, :2], np.ones(len(verF))] @ Hgt.T
+    assert np.median(np.hypot(p[:, 0] / p[:, 2] - verF[:, 2], p[:, 1] / p[:, 2] - verF[:, 3])) < 1.5
 
 
 def test_mods_pair_two_streams_equals_one(ctx):

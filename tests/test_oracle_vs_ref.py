@@ -159,13 +159,17 @@ def test_hessaff_detector_modes(oracle, reference, mode, regs, rel):
 
 
 def test_reference_f_ransac_is_pinned_by_golden_vectors(reference):
-    """exp_ransacFcustom (exp_ranF.c:795, DEGENSAC on) of the compiled reference with a fixed seed reproduces the committed vectors: the
-    target the F driver (row a19, not built yet) will be held to."""
+    """exp_ransacFcustom (exp_ranF.c:795, DEGENSAC on) of the compiled reference with a fixed seed reproduces the committed vectors the F
+    driver (row a19, mods_b200/csrc/ransac_f_logic.hpp) is held to in tests/test_ransac_f_logic.py and tests/test_gpu_parity.py."""
     import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_f import CASES
     G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ransac_f_vectors.npz"))
-    for seed in (1, 2):
-        for et in (0, 1):
-            r = reference.exp_ransacF(G["u"], seed=seed, errorType=et)
-            assert np.array_equal(r["inl"], G["inl_s%d_e%d" % (seed, et)])
-            assert [r["I"], r["samples"], r["lo"], r["Ih"]] == G["stats_s%d_e%d" % (seed, et)].tolist()
-            assert np.allclose(r["F"], G["F_s%d_e%d" % (seed, et)], rtol=1e-9, atol=1e-12)
+    for name, seed, et, lim in CASES:
+        key = "%s_s%d_e%d_l%s" % (name, seed, et, lim)
+        u = G["u_" + name]
+        r = reference.exp_ransacF(u, seed=seed, errorType=et, inlLimit=None if lim == "n" else 0)
+        assert np.array_equal(r["inl"], np.unpackbits(G["inl_" + key])[:len(u)]), key
+        assert [r["I"], r["samples"], r["lo"], r["Ih"]] == G["stats_" + key].tolist(), key
+        assert np.allclose(r["F"], G["F_" + key], rtol=1e-9, atol=1e-12), key

@@ -1,0 +1,96 @@
+"""Host logic of the F-matrix LO-RANSAC driver (mods_b200/csrc/ransac_f_logic.hpp: the code the library compiles) without a GPU:
+tests/native/ransac_f_cpu.cpp instantiates it with the ORACLE's residual functions as the scorer.  Held against (i) the committed golden
+vectors of the compiled reference (exp_ransacFcustom, tests/golden/ransac_f_vectors.npz) and (ii) the compiled reference itself on fresh
+scenes when oracle/_ref is present: same inlier count, sample count, LO count, best-homography support and inlier mask; F up to scale."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_f import CASES, general_scene  # noqa: E402
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+@pytest.fixture(scope="module")
+def flogic(oracle):
+    src = os.path.join(HERE, "native", "ransac_f_cpu.cpp")
+    so = os.path.join(HERE, "native", "libransac_f_cpu.so")
+    hdrs = [os.path.join(HERE, "..", "mods_b200", "csrc", h) for h in ("ransac_f_logic.hpp", "ransac_common.hpp", "minv3.hpp")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fopenmp", "-o", so, src])
+    lib = C.CDLL(so)
+    score = getattr(oracle.lib, oracle.prefix + "score")
+
+    def run(u, seed=1, errorType=0, inlLimit=None, th=9.0, conf=0.99, max_sam=100000, doSymCheck=1, do_lo=1):
+        u = np.ascontiguousarray(u, np.float64); n = len(u)
+        F = np.zeros(9); inl = np.zeros(max(n, 1), np.uint8); out = np.zeros(5, np.int32)
+        I = lib.t_ransac_f(score, _p(u), C.c_int(n), C.c_double(th), C.c_double(conf), C.c_int(max_sam), C.c_int(errorType), C.c_int(doSymCheck),
+                           C.c_int(do_lo), C.c_uint(n if inlLimit is None else inlLimit), C.c_long(seed), _p(F), _p(inl), _p(out))
+        return dict(F=F, inl=inl[:n], I=I, samples=int(out[1]), lo=int(out[2]), Ih=int(out[3]), calls=int(out[4]))
+    run.lib = lib
+    return run
+
+
+def same_F(a, b, tol=1e-7):
+    a = a / max(np.linalg.norm(a), 1e-300); b = b / max(np.linalg.norm(b), 1e-300)
+    return min(np.abs(a - b).max(), np.abs(a + b).max()) < tol
+
+
+def check_against_golden(run, G, name, seed, et, lim):
+    key = "%s_s%d_e%d_l%s" % (name, seed, et, lim)
+    u = G["u_" + name]
+    r = run(u, seed=seed, errorType=et, inlLimit=None if lim == "n" else 0)
+    assert [r["I"], r["samples"], r["lo"], r["Ih"]] == G["stats_" + key].tolist(), key
+    assert np.array_equal(r["inl"], np.unpackbits(G["inl_" + key])[:len(u)]), key
+    assert same_F(r["F"], G["F_" + key]), key
+
+
+def test_f_logic_reproduces_reference_golden_vectors(flogic):
+    G = np.load(os.path.join(HERE, "golden", "ransac_f_vectors.npz"))
+    for case in CASES:
+        check_against_golden(flogic, G, *case)
+
+
+def test_f_logic_vs_reference_build_on_fresh_scenes(flogic, reference):
+    for cfg in (dict(n=300, n_out=200, noise=1.0), dict(n=200, n_out=150, noise=0.3), dict(n=600, n_out=200, planar_frac=0.8), dict(n=30, n_out=8)):
+        u = general_scene(11, **cfg)
+        for seed in (5, 6):
+            for et in (0, 1):
+                for lim in (None, 0):
+                    a = reference.exp_ransacF(u, seed=seed, errorType=et, inlLimit=lim); b = flogic(u, seed=seed, errorType=et, inlLimit=lim)
+                    assert [a[k] for k in ("I", "samples", "lo", "Ih")] == [b[k] for k in ("I", "samples", "lo", "Ih")], (cfg, seed, et, lim)
+                    assert np.array_equal(a["inl"], b["inl"]) and same_F(a["F"], b["F"])
+
+
+def test_restated_numerics_vs_reference_pieces(flogic, reference):
+    """ccmath's unsorted 3x3 svduv (bit-exact right-singular matrix), u2f / u2fw incl. the 8-point branch with its stride-9 weighting."""
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        A = rng.normal(size=(3, 3))
+        if t % 2:
+            U, s, Vt = np.linalg.svd(A); s[2] = 0; A = (U * s) @ Vt
+        A = np.ascontiguousarray(A); V1 = np.zeros(9); V2 = np.zeros(9)
+        reference.fn("svduv3_V", None)(_p(A), _p(V1)); flogic.lib.t_svd3_ccmath_V(_p(A), _p(V2))
+        assert np.array_equal(V1, V2)
+    u = general_scene(3, n_out=0)
+    for n in (8, 9, 14, 100):
+        for weighted in (False, True):
+            idx = rng.permutation(300)[:n].astype(np.int32); w = rng.random(len(u)) + 0.5
+            F1 = np.zeros(9); F2 = np.zeros(9)
+            reference.fn("u2f", None)(_p(u), _p(idx), _p(w) if weighted else None, C.c_int(n), _p(F1))
+            flogic.lib.t_u2f(_p(u), _p(idx), _p(w) if weighted else None, C.c_int(n), _p(F2))
+            assert same_F(F1, F2, 1e-9), (n, weighted)
+
+
+def test_f_logic_degenerate_inputs(flogic):
+    assert flogic(np.zeros((0, 6)))["I"] == 0
+    r = flogic(np.ones((20, 6)))          # all correspondences identical: nothing acceptable, empty mask, no crash
+    assert r["inl"].sum() == 0
