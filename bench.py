@@ -212,6 +212,11 @@ def run_ours(args, rank, world, local_rank):
                                          mser_regions=float(np.mean([r.mser_regions1 + r.mser_regions2 for r in res_dev])) / 2))
     else:
         out["roofline"] = None
+    if world == 1:
+        try:
+            out["micro"] = micro_benchmarks(ctx)
+        except Exception as e:   # the micro-benchmarks never take the headline down
+            out["micro"] = {"error": repr(e)}
     out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1, with_mser=not args.no_mser) if (not args.no_cpu_baseline and world == 1) else None   # rank 0 at N=1 only
     print(json.dumps(out))
 
@@ -271,6 +276,52 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
                                 "frac": flop / 1e12 / (ms_nn / 1e3) / peaks["bf16"], "ms_per_pair": ms_nn, "flop": flop,
                                 "note": "2 passes (NN, then FGINN statistics); epilogue on CUDA cores is fused (distances never leave the SM)"}
     return dict(roofline=rl, kernels=kernels, **extra)
+
+
+def micro_benchmarks(ctx):
+    """SURVEY 8d micro-benchmarks of the verification rows (a17-a19): the batched scorer on n = 8192 correspondences x K = 4096
+    hypotheses (kernel time from the library's CUDA events), and the F-matrix LO-RANSAC driver on 30k tentatives."""
+    import mods_b200.synth as synth
+    rng = np.random.default_rng(1)
+    n, K = 8192, 4096
+    u = np.zeros((n, 6)); u[:, 0:2] = rng.random((n, 2)) * 1000; u[:, 2] = 1; u[:, 5] = 1
+    Hgt = synth.gt_homography(1000, 1000)
+    p = (Hgt @ u[:, 0:3].T).T; u[:, 3:5] = p[:, :2] / p[:, 2:3] + rng.normal(size=(n, 2))
+    u[int(0.6 * n):, 3:5] = rng.random((n - int(0.6 * n), 2)) * 1000
+    M0 = np.linalg.inv(Hgt).T.ravel()
+    models = np.stack([M0 * (1 + 1e-3 * rng.normal(size=9)) for _ in range(K)])
+    out = {}
+    for which, name, flop in ((0, "HDs", 120.0), (3, "FDs", 40.0)):
+        ctx.score_models(which, u, models, 9.0)
+        ctx.profile_begin()
+        for _ in range(5):
+            ctx.score_models(which, u, models, 9.0)
+        prof = ctx.profile_end()
+        ms = prof.get("k_score", (1, 0.0))[1] / 5
+        out["scorer_" + name] = {"n": n, "K": K, "kernel_ms": ms, "achieved": flop * n * K / 1e12 / (ms / 1e3) if ms else None, "unit": "TFLOP/s (f64)",
+                                 "peak": 40.0, "peak_src": "nominal B200 FP64 (MEASURED_PEAKS.json has no FP64 figure)",
+                                 "frac": (flop * n * K / 1e12 / (ms / 1e3) / 40.0) if ms else None, "flop_per_point_model": flop}
+    # F driver at C3 size: 30k tentatives, 40 % outliers, inlLimit 0 as LORANSACFiltering calls it
+    X = np.c_[rng.random((30000, 2)) * 6 - 3, rng.random(30000) * 10 + 2]
+    Km = np.array([[800, 0, 400], [0, 800, 300], [0, 0, 1.0]]); a = 0.15
+    Rm = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]); t = np.array([0.8, 0.1, 0.2])
+    x1 = (Km @ X.T).T; x1 = x1[:, :2] / x1[:, 2:]
+    x2 = (Km @ (Rm @ X.T + t[:, None])).T; x2 = x2[:, :2] / x2[:, 2:]
+    uf = np.ones((30000, 6)); uf[:, 0:2] = x1 + rng.normal(size=(30000, 2)) * 0.5; uf[:, 3:5] = x2 + rng.normal(size=(30000, 2)) * 0.5
+    uf[18000:, 3:5] = rng.random((12000, 2)) * 800
+    uf = np.ascontiguousarray(uf[rng.permutation(30000)])
+    ctx.ransac_f(uf, seed=9, inlLimit=0)
+    t0 = time.perf_counter(); r = ctx.ransac_f(uf, seed=9, inlLimit=0); dt = time.perf_counter() - t0
+    out["ransac_f"] = {"tentatives": 30000, "ms": 1e3 * dt, "inliers": int(r["I"]), "samples": r["samples"], "lo": r["lo"], "launches": r["launches"]}
+    try:
+        from oracle import pyoracle
+        if pyoracle.have_reference():
+            R = pyoracle.Reference()
+            t0 = time.perf_counter(); rr = R.exp_ransacF(uf, seed=9, inlLimit=0); dr = time.perf_counter() - t0
+            out["ransac_f"].update({"reference_cpu_ms": 1e3 * dr, "identical_to_reference": bool(np.array_equal(rr["inl"], r["inl"]) and rr["samples"] == r["samples"])})
+    except Exception:
+        pass
+    return out
 
 
 def cpu_baseline(pair, cfg_seed=1, query_sample=2000, with_mser=True):
