@@ -79,6 +79,9 @@ typedef struct {
   int patchSize;   /* 41 */
   int maxAngles;   /* 1 */
   double threshold;/* 0.8 */
+  int doHalfSIFT;  /* 0; 1 = orientations modulo pi for the Half* descriptors: the upper half of the smoothed histogram is folded onto
+                    * the lower one before the peak search (synth-detection.cpp:801-808) */
+  int reserved;
 } mb2_orientation_params;
 
 /* [SIFTDescriptor] as passed to DescribeRegions<SIFTDescriptor> (synth-detection.hpp:169-172,
@@ -89,6 +92,11 @@ typedef struct {
   int photoNorm;   /* 1 */
   int rootSIFT;    /* 1 = RootSIFT, 0 = SIFT */
   int fastPatchExtraction; /* 0 */
+  int doHalfSIFT;  /* 0; 1 with rootSIFT = HalfRootSIFT (siftdesc.cpp:401-442): opposite orientation bins summed -> 64-D, RootSIFT
+                    * normalisation on the 64 entries.  Rows of desc_u8 stay 128 wide: entries 0..63 hold the descriptor, 64..127 are 0
+                    * (L2 distances between such rows equal the 64-D distances).  doHalfSIFT without rootSIFT is refused: the reference's
+                    * SIFTnorm reads 128 entries of the 64-entry vector (siftdesc.cpp:251, 267). */
+  int reserved;
 } mb2_sift_params;
 
 /* ---- context --------------------------------------------------------------------------- */

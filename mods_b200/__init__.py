@@ -55,20 +55,21 @@ class ViewParams(C.Structure):
 
 
 class OrientationParams(C.Structure):
-    _fields_ = [("mrSize", C.c_double), ("patchSize", C.c_int), ("maxAngles", C.c_int), ("threshold", C.c_double)]
+    _fields_ = [("mrSize", C.c_double), ("patchSize", C.c_int), ("maxAngles", C.c_int), ("threshold", C.c_double),
+                ("doHalfSIFT", C.c_int), ("reserved", C.c_int)]
 
     @staticmethod
     def default():
-        return OrientationParams(1.0, 41, 1, 0.8)
+        return OrientationParams(1.0, 41, 1, 0.8, 0, 0)
 
 
 class SiftParams(C.Structure):
     _fields_ = [("mrSize", C.c_double), ("patchSize", C.c_int), ("photoNorm", C.c_int), ("rootSIFT", C.c_int),
-                ("fastPatchExtraction", C.c_int)]
+                ("fastPatchExtraction", C.c_int), ("doHalfSIFT", C.c_int), ("reserved", C.c_int)]
 
     @staticmethod
     def default():
-        return SiftParams(5.1962, 41, 1, 1, 0)
+        return SiftParams(5.1962, 41, 1, 1, 0, 0, 0)
 
 
 def build(force=False):

@@ -497,7 +497,7 @@ int orient_core(mb2_ctx* ctx, const ImgView& img, int n, const mb2_orientation_p
 
   KeyOut* d_slots = ctx->kp_a.as<KeyOut>();
   int* d_cnt = (int*)(d_slots + slots);
-  OrientParams p{op.mrSize, op.patchSize, maxA, op.threshold};
+  OrientParams p{op.mrSize, op.patchSize, maxA, op.threshold, op.doHalfSIFT != 0 ? 1 : 0};
   mb2_launch_orientation(ctx, img, ctx->kp_b.as<KeyOut>(), n, p, priv(ctx)->t.orimask.as<float>(), d_slots, d_cnt);
   MB2_CUDA_CHECK(ctx, ctx->kp_c.reserve(slots * sizeof(KeyOut)));
   if ((rc = compact(ctx, d_slots, nullptr, (int)slots, ctx->kp_c.as<KeyOut>(), nullptr, ctx->misc, n_out))) return rc;
@@ -530,7 +530,11 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
   int rc;
   if ((rc = upload_lut(ctx))) return rc;
   if ((rc = ensure_desc_tables(ctx))) return rc;
-  DescribeParams dp{sp.mrSize, sp.patchSize, sp.photoNorm, sp.rootSIFT, sp.fastPatchExtraction};
+  if (sp.doHalfSIFT && !sp.rootSIFT) {
+    ctx->set_error("describe: HalfSIFT without RootSIFT is undefined in the reference (SIFTnorm reads past the 64-entry vector)");
+    return MB2_ERR_UNSUPPORTED;
+  }
+  DescribeParams dp{sp.mrSize, sp.patchSize, sp.photoNorm, sp.rootSIFT, sp.fastPatchExtraction, sp.doHalfSIFT != 0 ? 1 : 0};
   // largest possible m: the region must fit in the image for the earlier boundary tests, bound by the image diagonal
   const int max_m = (int)std::ceil(std::sqrt((double)img.rows * img.rows + (double)img.cols * img.cols)) + 8;
   TapTable taps;

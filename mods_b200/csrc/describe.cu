@@ -675,9 +675,20 @@ k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __re
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const double maxBinValue = (double)0.2f;
+  int D = 128;
+  if (dp.half) {
+    // HalfSIFT (siftdesc.cpp:408-421): the raw votes (doNorm is off for this pass) of opposite orientations are summed,
+    // half_vec[i*4 + j] = vec[i*8 + j] + vec[i*8 + j + 4]; the normalisation below then runs on 64 entries
+    D = 64;
+    for (int i = 0; i < 16; i++)
+      for (int j = 0; j < 4; j++) {
+        const double h = vecT[(size_t)(i * 8 + j) * n + r] + vecT[(size_t)(i * 8 + j + 4) * n + r];
+        vecT[(size_t)(i * 4 + j) * n + r] = h;   // i*4+j <= i*8+j: entries still to be read are never overwritten
+      }
+  }
   for (int pass = 0; pass < 2; pass++) {
     double len = 0.0;
-    for (int i = 0; i < 128; i += 4) {
+    for (int i = 0; i < D; i += 4) {
       const double v0 = vecT[(size_t)i * n + r], v1 = vecT[(size_t)(i + 1) * n + r], v2 = vecT[(size_t)(i + 2) * n + r],
                    v3 = vecT[(size_t)(i + 3) * n + r];
       const double sq0 = v0 * v0, sq1 = v1 * v1, sq2 = v2 * v2, sq3 = v3 * v3;
@@ -686,7 +697,7 @@ k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __re
     len = sqrt(len);
     const double fac = 1.0 / len;
     bool changed = false;
-    for (int i = 0; i < 128; i++) {
+    for (int i = 0; i < D; i++) {
       double v = vecT[(size_t)i * n + r] * fac;
       if (pass == 0 && v > maxBinValue) { v = maxBinValue; changed = true; }
       vecT[(size_t)i * n + r] = v;
@@ -694,8 +705,8 @@ k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __re
     if (pass == 1 || !changed) break;
   }
   double sum = 0.;
-  if (dp.rootSIFT) for (int i = 0; i < 128; i++) sum += fabs(vecT[(size_t)i * n + r]);
-  for (int i = 0; i < 128; i++) {
+  if (dp.rootSIFT) for (int i = 0; i < D; i++) sum += fabs(vecT[(size_t)i * n + r]);
+  for (int i = 0; i < D; i++) {
     double v = vecT[(size_t)i * n + r];
     if (dp.rootSIFT) v = sqrt(v / sum);
     // (int)(512.0 * v + 0.5) for RootSIFT, (int)(512.0f * v + 0.5) for SIFT: identical in double
@@ -703,6 +714,7 @@ k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __re
     b = b < 0 ? 0 : (b > 255 ? 255 : b);
     desc_out[(size_t)r * 128 + i] = (uint8_t)b;
   }
+  for (int i = D; i < 128; i++) desc_out[(size_t)r * 128 + i] = 0;
 }
 
 }  // namespace

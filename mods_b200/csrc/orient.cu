@@ -158,6 +158,13 @@ k_orientation(ImgView img, const KeyOut* __restrict__ in, int n, OrientParams op
   for (int d = 16; d > 0; d >>= 1) thresh = fmaxf(thresh, __shfl_xor_sync(0xffffffffu, thresh, d));
   thresh = fmaxf(thresh, 0.0f);
   thresh = (float)((double)thresh * op.threshold);
+  if (op.half) {  // doHalfSIFT: hist[i] += hist[i + 18], upper half cleared (synth-detection.cpp:801-808), after the threshold is fixed
+    const float lo = lane < 18 ? fadd(hist[lane], hist[lane + 18]) : 0.0f;
+    __syncwarp();
+    hist[lane] = lo;              // lanes 18..31 clear bins 18..31
+    if (lane < 4) hist[32 + lane] = 0.0f;
+    __syncwarp();
+  }
   // peaks in the order of the reference's addPeakAngle calls: (35,0,1), (i-1,i,i+1) for i = 1..34, (34,35,0); first maxAngles
   auto is_peak = [&](int q) {
     const int a = (q == 0) ? 35 : q - 1, c = (q == 35) ? 0 : q + 1;

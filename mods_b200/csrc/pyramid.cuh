@@ -65,14 +65,14 @@ struct KeyOut { double v[MB2_KP]; unsigned long long order; int keep; int pad; }
 void mb2_launch_export(mb2_ctx* ctx, const KeypointRec* kps, int n, KeyOut* out, int as_regions);
 
 // orient.cu
-struct OrientParams { double mrSize; int patchSize; int maxAngles; double threshold; };
+struct OrientParams { double mrSize; int patchSize; int maxAngles; double threshold; int half; };
 void mb2_launch_orientation(mb2_ctx* ctx, const ImgView& img, const KeyOut* in, int n, const OrientParams& op,
                             const float* d_orimask, KeyOut* out /* n * maxAngles; .pad = float bits of the angle */, int* out_count_per_kp);
 void mb2_launch_extract_angles(mb2_ctx* ctx, const KeyOut* keys, int n, float* d_ang);
 void mb2_launch_apply_rotation(mb2_ctx* ctx, KeyOut* keys, const double* d_cs, int n);
 
 // describe.cu
-struct DescribeParams { double mrSize; int patchSize; int photoNorm; int rootSIFT; int fast; };
+struct DescribeParams { double mrSize; int patchSize; int photoNorm; int rootSIFT; int fast; int half; };
 struct DescTables {      // precomputed on the host exactly as the reference's constructors do
   float mask[41 * 41];   // computeCircularGaussMask(41), siftdesc.h:87 / synth-detection.hpp:181
   int bin0[41], bin1[41];

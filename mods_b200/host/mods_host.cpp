@@ -44,6 +44,8 @@ DetectorsParameters::DetectorsParameters() {
 DescriptorsParameters::DescriptorsParameters() {
   SIFTParam = mb2_sift_params{5.1962, 41, 1, 0, 0};
   RootSIFTParam = mb2_sift_params{5.1962, 41, 1, 1, 0};
+  HalfRootSIFTParam = RootSIFTParam; HalfRootSIFTParam.doHalfSIFT = 1;   // io_mods.cpp:752-753
+  HalfSIFTParam = HalfRootSIFTParam;                                     // io_mods.cpp:756 (HalfSIFT is HalfRootSIFT in the reference)
 }
 
 // ---- SetVSPars (synth-detection.cpp:103-234) --------------------------------------------------------
@@ -95,6 +97,8 @@ ImageRepresentation::ImageRepresentation(mb2_ctx* c, GrayImage img, std::string 
 descriptor_type ImageRepresentation::GetDescriptorType(std::string n) const {
   if (n == "SIFT") return DESC_SIFT;
   if (n == "RootSIFT") return DESC_ROOT_SIFT;
+  if (n == "HalfSIFT") return DESC_HALF_SIFT;
+  if (n == "HalfRootSIFT") return DESC_HALF_ROOT_SIFT;
   return DESC_UNKNOWN;
 }
 detector_type ImageRepresentation::GetDetectorType(std::string n) const {
@@ -152,11 +156,16 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
       const bool identity = (std::fabs(v.tilt - 1.) <= 0.1) && (std::fabs(v.phi) <= 0.2) && (std::fabs(v.zoom - 1.) <= 0.1);  // synth-detection.cpp:278
       const double H[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
       const mb2_view_params vp{v.tilt, v.phi, v.zoom, v.InitSigma, v.doBlur};
+      // HalfSIFT_like_desc is sticky over the view's descriptor list (imagerepresentation.cpp:693-714): one Half* name makes
+      // EVERY SIFT-like descriptor of the view use the regions oriented modulo pi (:1257-1262, :1288-1291)
+      bool half_like = false;
+      for (const std::string& d : v.descriptors) half_like = half_like || d.find("Half") != std::string::npos;
       for (const std::string& curr_desc : v.descriptors) {
         const descriptor_type dt = GetDescriptorType(curr_desc);
         if (dt == DESC_UNKNOWN) continue;
-        mb2_sift_params sp = (dt == DESC_ROOT_SIFT) ? desc_par.RootSIFTParam : desc_par.SIFTParam;
-        mb2_orientation_params op{dom_ori_par.mrSize, dom_ori_par.patchSize, dom_ori_par.maxAngles, (double)dom_ori_par.threshold};
+        mb2_sift_params sp = dt == DESC_ROOT_SIFT ? desc_par.RootSIFTParam : dt == DESC_HALF_ROOT_SIFT ? desc_par.HalfRootSIFTParam
+                             : dt == DESC_HALF_SIFT ? desc_par.HalfSIFTParam : desc_par.SIFTParam;
+        mb2_orientation_params op{dom_ori_par.mrSize, dom_ori_par.patchSize, dom_ori_par.maxAngles, (double)dom_ori_par.threshold, half_like ? 1 : 0, 0};
         const double t0 = now_ms();
         const bool use_slot = slot >= 0 && (ss.desc.empty() || ss.desc == curr_desc);
         const int dev_slot = use_slot ? slot_of(curr_det) : MB2_MAX_SLOTS - 1;

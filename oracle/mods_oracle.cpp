@@ -180,6 +180,12 @@ int orc_detect_orientation(const float* img, int w, int h, const double* kps, in
   for (size_t i = 0; i < res.size() && (int)i < max_out; i++) kp_out(res[i], out + i * KP);
   return (int)res.size();
 }
+int orc_detect_orientation_half(const float* img, int w, int h, const double* kps, int n, double mrSize, int patchSize, int maxAngles,
+                                double th, int doHalfSIFT, double* out, int max_out) {
+  std::vector<Key> res = detectOrientation(keys_in(kps, n), image_in(img, w, h), mrSize, patchSize, maxAngles, th, doHalfSIFT != 0);
+  for (size_t i = 0; i < res.size() && (int)i < max_out; i++) kp_out(res[i], out + i * KP);
+  return (int)res.size();
+}
 int orc_reproject(const double* kps, int n, const double* H, int w, int h, int which, double mrSize, double* out_det,
                   double* out_reproj) {
   std::vector<Key> det = keys_in(kps, n), rep;
@@ -189,11 +195,11 @@ int orc_reproject(const double* kps, int n, const double* H, int w, int h, int w
 }
 void orc_describe(const float* img, int w, int h, const double* kps, int n, double mrSize, int patchSize, int fast, int photoNorm,
                   int rootsift, float* desc, float* patches /* may be null */) {
-  SIFTDescriptor D(patchSize, rootsift != 0);
+  SIFTDescriptor D(patchSize, (rootsift & 1) != 0); D.doHalfSIFT = (rootsift & 2) != 0;   // flags: bit0 RootSIFT, bit1 Half descriptor
   describeRegions(keys_in(kps, n), image_in(img, w, h), D, mrSize, patchSize, fast != 0, photoNorm != 0, desc, patches);
 }
 void orc_sift_patch(const float* patch41, int rootsift, float* desc128) {
-  SIFTDescriptor D(41, rootsift != 0);
+  SIFTDescriptor D(41, (rootsift & 1) != 0); D.doHalfSIFT = (rootsift & 2) != 0;
   D(patch41, desc128);
 }
 // MSER: DetectMSERs (extrema.cpp:284) -- raw keys, or regions after DetectAffineRegions (synth-detection.hpp:93)
@@ -232,12 +238,12 @@ int orc_view_pipeline(const float* img, int w, int h, int detector, const HessPa
       kp1.push_back(Key{k.x, k.y, k.a11, k.a12, k.a21, k.a22, k.s, k.response, k.sub_type});
   }
   toRegions(kp1);
-  std::vector<Key> det = detectOrientation(kp1, im, ori_mrSize, ori_patch, maxAngles, ori_th), rep;
+  std::vector<Key> det = detectOrientation(kp1, im, ori_mrSize, ori_patch, maxAngles, ori_th, (rootsift & 4) != 0), rep;
   const double H[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   reprojectRegions(det, rep, H, w, h, 0, 0);
   int n = (int)det.size();
   if (n > max_out) return -n;
-  SIFTDescriptor D(desc_patch, rootsift != 0);
+  SIFTDescriptor D(desc_patch, (rootsift & 1) != 0); D.doHalfSIFT = (rootsift & 2) != 0;   // flags: bit0 RootSIFT, bit1 Half descriptor, bit2 orientation modulo pi
   describeRegions(det, im, D, desc_mrSize, desc_patch, false, photoNorm != 0, desc_out);
   for (int i = 0; i < n; i++) { kp_out(det[i], det_out + (size_t)i * KP); kp_out(rep[i], reproj_out + (size_t)i * KP); }
   return n;
@@ -267,11 +273,11 @@ int orc_view_pipeline_synth(const float* img, int w, int h, int detector, const 
       kp1.push_back(Key{k.x, k.y, k.a11, k.a12, k.a21, k.a22, k.s, k.response, k.sub_type});
   }
   toRegions(kp1);
-  std::vector<Key> det = detectOrientation(kp1, im, ori_mrSize, ori_patch, maxAngles, ori_th), rep;
+  std::vector<Key> det = detectOrientation(kp1, im, ori_mrSize, ori_patch, maxAngles, ori_th, (rootsift & 4) != 0), rep;
   reprojectRegions(det, rep, v.H, w, h, 0, 0);
   int n = (int)det.size();
   if (n > max_out) return -n;
-  SIFTDescriptor D(desc_patch, rootsift != 0);
+  SIFTDescriptor D(desc_patch, (rootsift & 1) != 0); D.doHalfSIFT = (rootsift & 2) != 0;   // flags: bit0 RootSIFT, bit1 Half descriptor, bit2 orientation modulo pi
   describeRegions(det, im, D, desc_mrSize, desc_patch, false, photoNorm != 0, desc_out);
   for (int i = 0; i < n; i++) { kp_out(det[i], det_out + (size_t)i * KP); kp_out(rep[i], reproj_out + (size_t)i * KP); }
   return n;

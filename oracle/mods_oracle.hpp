@@ -619,7 +619,7 @@ const double k_sigma_sd = 2 * 3.0 * 1.7320508075688772;  // synth-detection.cpp:
 
 // synth-detection.cpp:746-839.  img is patch x patch.
 inline void estimateDominantAngles(const float* img, int pS, const float* orimask, std::vector<float>& angles1, double max_th,
-                                   int maxAngles, std::vector<float>& gmag, std::vector<float>& gori) {
+                                   int maxAngles, std::vector<float>& gmag, std::vector<float>& gori, bool doHalfSIFT = false) {
   angles1.clear();
   if (maxAngles == 0) return;
   const int bins = 36;
@@ -652,6 +652,10 @@ inline void estimateDominantAngles(const float* img, int pS, const float* orimas
   float thresh = 0.0;
   for (int i = 0; i < bins; i++) if (hist[i] > thresh) thresh = hist[i];
   thresh *= max_th;
+  if (doHalfSIFT) {  // synth-detection.cpp:801-808: orientations modulo pi
+    const int halfbins = bins / 2;
+    for (int i = 0; i < halfbins; i++) { hist[i] += hist[i + halfbins]; hist[i + halfbins] = 0; }
+  }
   auto addPeak = [&](int a, int b, int c) {  // synth-detection.cpp:734-744
     if (hist[b] >= thresh && hist[b] > hist[a] && hist[b] > hist[c]) {
       float pp = (hist[a] - hist[c]) / (hist[a] - 2.0f * hist[b] + hist[c]) / 2.0f;
@@ -671,9 +675,9 @@ inline void estimateDominantAngles(const float* img, int pS, const float* orimas
   } else angles1.clear();
 }
 
-// synth-detection.cpp:841-919 (doHalfSIFT = 0, addUpRight = false)
+// synth-detection.cpp:841-919 (addUpRight = false)
 inline std::vector<Key> detectOrientation(const std::vector<Key>& in, const Image& img, double mrSize, int patchSize,
-                                          int maxAngNum, double th) {
+                                          int maxAngNum, double th, bool doHalfSIFT = false) {
   std::vector<Key> out;
   double mrScale = (double)mrSize;
   int patchImageSize = 2 * int(mrScale) + 1;
@@ -691,7 +695,7 @@ inline std::vector<Key> detectOrientation(const std::vector<Key>& in, const Imag
     if (maxAngNum > 0) {
       interpolate(img.px.data(), img.rows, img.cols, (float)k.x, (float)k.y, (float)k.a11 * curr_sc, (float)k.a12 * curr_sc,
                   (float)k.a21 * curr_sc, (float)k.a22 * curr_sc, patch.data(), patchSize, patchSize);
-      estimateDominantAngles(patch.data(), patchSize, orimask.data(), angles1, th, maxAngNum, gmag, gori);
+      estimateDominantAngles(patch.data(), patchSize, orimask.data(), angles1, th, maxAngNum, gmag, gori, doHalfSIFT);
       for (size_t j = 0; j < angles1.size(); j++) {
         double ci = std::cos(-angles1[j]), si = std::sin(-angles1[j]);
         Key t = k;
@@ -748,6 +752,7 @@ struct SIFTDescriptor {
   int patchSize = 41, spatialBins = 4, orientationBins = 8;
   double maxBinValue = 0.2f;  // siftdesc.h:56 (a float literal stored in a double)
   bool useRootSIFT = false;
+  bool doHalfSIFT = false;   // with useRootSIFT: HalfRootSIFT (64 entries; rows stay 128 wide, the upper 64 are 0)
   std::vector<float> mask, grad, ori;
   std::vector<int> bin0, bin1;
   std::vector<double> w0, w1, vec;
@@ -801,7 +806,7 @@ struct SIFTDescriptor {
     for (size_t i = 0; i < v.size(); i++) v[i] *= fac;
     return len;
   }
-  void finish() {  // SIFTnorm / RootSIFTnorm (double overloads), siftdesc.cpp:199-222, 247-262
+  void finish(std::vector<double>& vec) {  // SIFTnorm / RootSIFTnorm (double overloads), siftdesc.cpp:199-222, 247-262
     normalize(vec);
     bool changed = false;
     for (size_t i = 0; i < vec.size(); i++) if (vec[i] > maxBinValue) { vec[i] = maxBinValue; changed = true; }
@@ -831,7 +836,17 @@ struct SIFTDescriptor {
       }
     for (size_t i = 0; i < vec.size(); i++) vec[i] = 0;
     samplePatch();
-    finish();
+    if (doHalfSIFT) {  // siftdesc.cpp:408-431: the un-normalised votes of opposite orientation bins are summed, then RootSIFTnorm on 64 entries
+      const int spBins = spatialBins * spatialBins, oriHalf = orientationBins / 2;
+      std::vector<double> half_vec((size_t)spBins * oriHalf);
+      int b = 0;
+      for (int i = 0; i < spBins; i++)
+        for (int j = 0; j < oriHalf; j++) half_vec[b++] = vec[i * orientationBins + j] + vec[i * orientationBins + j + oriHalf];
+      finish(half_vec);
+      for (size_t i = 0; i < vec.size(); i++) desc[i] = i < half_vec.size() ? (float)half_vec[i] : 0.0f;
+      return;
+    }
+    finish(vec);
     for (size_t i = 0; i < vec.size(); i++) desc[i] = (float)vec[i];
   }
 };

@@ -92,11 +92,11 @@ class Lib:
         assert n <= max_out
         return out[:n].copy()
 
-    def detect_orientation(self, img, kps, mrSize=1.0, patchSize=41, maxAngles=1, th=0.8):
+    def detect_orientation(self, img, kps, mrSize=1.0, patchSize=41, maxAngles=1, th=0.8, doHalfSIFT=0):
         img = _f32(img); kps = _f64(kps); n = len(kps)
         out = np.zeros((max(1, n * max(1, maxAngles) * 2), KP))
-        m = self.fn("detect_orientation")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(kps), C.c_int(n), C.c_double(mrSize),
-                                          C.c_int(patchSize), C.c_int(maxAngles), C.c_double(th), _p(out), C.c_int(len(out)))
+        m = self.fn("detect_orientation_half")(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(kps), C.c_int(n), C.c_double(mrSize),
+                                               C.c_int(patchSize), C.c_int(maxAngles), C.c_double(th), C.c_int(doHalfSIFT), _p(out), C.c_int(len(out)))
         return out[:m].copy()
 
     def reproject(self, kps, H, w, h, which=0, mrSize=5.1962):

@@ -219,6 +219,15 @@ int ref_detect_orientation(const float* img, int w, int h, const double* kps, in
   for (int i = 0; i < m && i < max_out; i++) kp_out(res[i].det_kp, out + (size_t)i * KP);
   return m;
 }
+int ref_detect_orientation_half(const float* img, int w, int h, const double* kps, int n, double mrSize,
+                                int patchSize, int maxAngles, double th, int doHalfSIFT, double* out, int max_out) {
+  SynthImage view; identity_view(view, img, w, h);
+  AffineRegionList in = regions_in(kps, n), res;
+  DetectOrientation(in, res, view, mrSize, patchSize, doHalfSIFT, maxAngles, th, false);   // synth-detection.cpp:841
+  int m = (int)res.size();
+  for (int i = 0; i < m && i < max_out; i++) kp_out(res[i].det_kp, out + (size_t)i * KP);
+  return m;
+}
 // which=0: ReprojectRegions (synth-detection.cpp:541); which=1: ...AndRemoveTouchBoundary (:63)
 int ref_reproject(const double* kps, int n, const double* H, int w, int h, int which, double mrSize,
                   double* out_det, double* out_reproj) {
@@ -237,20 +246,20 @@ void ref_describe(const float* img, int w, int h, const double* kps, int n, doub
   SynthImage view; identity_view(view, img, w, h);
   AffineRegionList l = regions_in(kps, n);
   SIFTDescriptorParams sp;
-  sp.useRootSIFT = rootsift; sp.PEParam.patchSize = patchSize; sp.PEParam.mrSize = mrSize;
+  sp.useRootSIFT = rootsift & 1; sp.doHalfSIFT = (rootsift & 2) ? 1 : 0; sp.PEParam.patchSize = patchSize; sp.PEParam.mrSize = mrSize;
   SIFTDescriptor D(sp);
   DescribeRegions(l, view, D, mrSize, patchSize, fast != 0, photoNorm != 0);      // synth-detection.hpp:169
   for (int i = 0; i < n; i++)
-    for (int j = 0; j < 128; j++) desc[(size_t)i * 128 + j] = l[i].desc.vec[j];
+    for (int j = 0; j < 128; j++) desc[(size_t)i * 128 + j] = j < (int)l[i].desc.vec.size() ? l[i].desc.vec[j] : 0.f;
 }
 void ref_sift_patch(const float* patch41, int rootsift, float* desc128) {
-  SIFTDescriptorParams sp; sp.useRootSIFT = rootsift;
+  SIFTDescriptorParams sp; sp.useRootSIFT = rootsift & 1; sp.doHalfSIFT = (rootsift & 2) ? 1 : 0;
   SIFTDescriptor D(sp);
   cv::Mat p(41, 41, CV_32FC1);
   std::memcpy(p.data, patch41, sizeof(float) * 41 * 41);
   std::vector<float> v;
   D(p, v);                                                                         // siftdesc.cpp:401
-  for (int j = 0; j < 128; j++) desc128[j] = v[j];
+  for (int j = 0; j < 128; j++) desc128[j] = j < (int)v.size() ? v[j] : 0.f;
 }
 
 // One (detector, view) pass of SynthDetectDescribeKeypoints for the identity view with a
@@ -272,18 +281,18 @@ int ref_view_pipeline(const float* img, int w, int h, int detector, const HessPa
     DetectAffineRegions(view, kp1, ep, DET_MSER, DetectMSERs);
   }
   AffineRegionList oriented;
-  DetectOrientation(kp1, oriented, view, ori_mrSize, ori_patch, false, maxAngles, ori_th, false);
+  DetectOrientation(kp1, oriented, view, ori_mrSize, ori_patch, (rootsift & 4) ? 1 : 0, maxAngles, ori_th, false);
   AffineRegionList desc_list = oriented;
   ReprojectRegions(desc_list, view.H, w, h);
   SIFTDescriptorParams sp;
-  sp.useRootSIFT = rootsift; sp.PEParam.patchSize = desc_patch; sp.PEParam.mrSize = desc_mrSize;
+  sp.useRootSIFT = rootsift & 1; sp.doHalfSIFT = (rootsift & 2) ? 1 : 0; sp.PEParam.patchSize = desc_patch; sp.PEParam.mrSize = desc_mrSize;
   SIFTDescriptor D(sp);
   DescribeRegions(desc_list, view, D, desc_mrSize, desc_patch, false, photoNorm != 0);
   int n = (int)desc_list.size();
   for (int i = 0; i < n && i < max_out; i++) {
     kp_out(desc_list[i].det_kp, det_out + (size_t)i * KP);
     kp_out(desc_list[i].reproj_kp, reproj_out + (size_t)i * KP);
-    for (int j = 0; j < 128; j++) desc_out[(size_t)i * 128 + j] = desc_list[i].desc.vec[j];
+    for (int j = 0; j < 128; j++) desc_out[(size_t)i * 128 + j] = j < (int)desc_list[i].desc.vec.size() ? desc_list[i].desc.vec[j] : 0.f;
   }
   return n;
 }
@@ -323,18 +332,18 @@ int ref_view_pipeline_synth(const float* img, int w, int h, int detector, const 
     DetectAffineRegions(view, kp1, ep, DET_MSER, DetectMSERs);
   }
   AffineRegionList oriented;
-  DetectOrientation(kp1, oriented, view, ori_mrSize, ori_patch, false, maxAngles, ori_th, false);
+  DetectOrientation(kp1, oriented, view, ori_mrSize, ori_patch, (rootsift & 4) ? 1 : 0, maxAngles, ori_th, false);
   AffineRegionList desc_list = oriented;
   ReprojectRegions(desc_list, view.H, w, h);
   SIFTDescriptorParams sp;
-  sp.useRootSIFT = rootsift; sp.PEParam.patchSize = desc_patch; sp.PEParam.mrSize = desc_mrSize;
+  sp.useRootSIFT = rootsift & 1; sp.doHalfSIFT = (rootsift & 2) ? 1 : 0; sp.PEParam.patchSize = desc_patch; sp.PEParam.mrSize = desc_mrSize;
   SIFTDescriptor D(sp);
   DescribeRegions(desc_list, view, D, desc_mrSize, desc_patch, false, photoNorm != 0);
   int n = (int)desc_list.size();
   for (int i = 0; i < n && i < max_out; i++) {
     kp_out(desc_list[i].det_kp, det_out + (size_t)i * KP);
     kp_out(desc_list[i].reproj_kp, reproj_out + (size_t)i * KP);
-    for (int j = 0; j < 128; j++) desc_out[(size_t)i * 128 + j] = desc_list[i].desc.vec[j];
+    for (int j = 0; j < 128; j++) desc_out[(size_t)i * 128 + j] = j < (int)desc_list[i].desc.vec.size() ? desc_list[i].desc.vec[j] : 0.f;
   }
   return n;
 }

@@ -286,6 +286,41 @@ def test_ransac_h_degenerate_inputs(ctx):
     assert ctx.ransac_h(u)["I"] == 0
 
 
+# ---- HalfRootSIFT (WxBS tiers) -----------------------------------------------------------------------
+def test_half_root_sift_vs_oracle_and_golden(ctx, oracle):
+    """Orientations modulo pi (mb2_orientation_params.doHalfSIFT) and the folded 64-entry descriptor (mb2_sift_params.doHalfSIFT):
+    bit-exact against the oracle on a fresh image and against the reference's golden vectors; the per-view pass with both flags."""
+    GH = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "half_sift_vectors.npz"))
+    im = GH["image"].astype(np.float32)
+    for maxA in (1, 5):
+        op = mb.OrientationParams.default(); op.maxAngles = maxA; op.doHalfSIFT = 1
+        assert np.array_equal(ctx.detect_orientation(im, GH["kps"], op), GH["oriented_half_a%d" % maxA])
+    sp = mb.SiftParams.default(); sp.doHalfSIFT = 1
+    assert np.array_equal(ctx.describe_sift(im, GH["oriented_half_a1"], sp), GH["desc_half"])
+    op = mb.OrientationParams.default(); op.doHalfSIFT = 1
+    v = ctx.detect_describe_view(im, ori=op, desc=sp)
+    assert np.array_equal(v[0], GH["view_det"]) and np.array_equal(v[2], GH["view_desc"])
+    # fresh image, both detectors, and RootSIFT described on half-oriented regions (a view listing RootSIFT,HalfRootSIFT)
+    im2 = synth.blob_image(480, 360, seed=31)
+    for det, dflag in ((mb.HessaffParams.default(), 0), (mb.MserParams.default(), 3)):
+        for flags, half_desc in ((7, 1), (5, 0)):
+            sp = mb.SiftParams.default(); sp.doHalfSIFT = half_desc
+            g = ctx.detect_describe_view(im2, det=det, ori=op, desc=sp)
+            o = oracle.view_pipeline(im2, detector=dflag, desc=(5.1962, 41, True, flags))
+            assert len(g[0]) > 100 and np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2].astype(np.float32), o[2])
+    # HalfSIFT without RootSIFT is undefined in the reference (SIFTnorm reads past the 64-entry vector): refused
+    sp = mb.SiftParams.default(); sp.doHalfSIFT = 1; sp.rootSIFT = 0
+    with pytest.raises(mb.Mb2Error):
+        ctx.describe_sift(im, GH["oriented_half_a1"], sp)
+    # matching two HalfRootSIFT sets: the zero upper halves leave the L2 distances of the 64 entries unchanged
+    sp = mb.SiftParams.default(); sp.doHalfSIFT = 1
+    B = synth.warp_image(im2, synth.gt_homography(480, 360), seed=32)
+    ga = ctx.detect_describe_view(im2, ori=op, desc=sp, slot=0); gb = ctx.detect_describe_view(B, ori=op, desc=sp, slot=1)
+    gm = ctx.match_slots(0, 1)
+    om = oracle.match_fginn(ga[2].astype(np.float32), gb[2].astype(np.float32), np.ascontiguousarray(gb[1][:, :2]))
+    assert len(gm) > 20 and np.array_equal(gm, om)
+
+
 # ---- LO-RANSAC fundamental matrix (DEGENSAC) -------------------------------------------------------
 def _load_f_golden():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))

@@ -68,3 +68,14 @@ def test_mser_plateaus_and_noise_match_reference(oracle):
     assert np.array_equal(oracle.mser_detect(p, max_area=0.3, min_size=8, min_margin=1.0), GM["p_keys"])
     n = GM["n_img"].astype(np.float32)
     assert np.array_equal(oracle.mser_regions(n, min_size=5, min_margin=2.0), GM["n_regions"])
+
+
+def test_half_root_sift_matches_reference(oracle):
+    """HalfRootSIFT (orientations modulo pi + folded 64-entry descriptor): tests/golden/make_golden_half.py."""
+    GH = np.load(os.path.join(os.path.dirname(__file__), "golden", "half_sift_vectors.npz"))
+    im = GH["image"].astype(np.float32)
+    for maxA in (1, 5):
+        assert np.array_equal(oracle.detect_orientation(im, GH["kps"], maxAngles=maxA, doHalfSIFT=1), GH["oriented_half_a%d" % maxA])
+    assert np.array_equal(oracle.describe(im, GH["oriented_half_a1"], rootsift=3).astype(np.uint8), GH["desc_half"])
+    v = oracle.view_pipeline(im, detector=0, desc=(5.1962, 41, True, 7))
+    assert np.array_equal(v[0], GH["view_det"]) and np.array_equal(v[2].astype(np.uint8), GH["view_desc"])

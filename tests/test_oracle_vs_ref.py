@@ -173,3 +173,24 @@ def test_reference_f_ransac_is_pinned_by_golden_vectors(reference):
         assert np.array_equal(r["inl"], np.unpackbits(G["inl_" + key])[:len(u)]), key
         assert [r["I"], r["samples"], r["lo"], r["Ih"]] == G["stats_" + key].tolist(), key
         assert np.allclose(r["F"], G["F_" + key], rtol=1e-9, atol=1e-12), key
+
+
+def test_half_root_sift_oracle_vs_reference(oracle, reference):
+    """HalfRootSIFT (WxBS tiers: `Descriptors=RootSIFT,HalfRootSIFT`): orientations modulo pi (DetectOrientation doHalfSIFT = 1,
+    synth-detection.cpp:801-808) and the folded 64-entry descriptor (siftdesc.cpp:401-442).  desc flags: bit0 RootSIFT, bit1 Half
+    descriptor, bit2 orientation modulo pi (a RootSIFT descriptor in a view that also lists a Half* one gets flags 5)."""
+    im = synth.blob_image(320, 240, seed=5)
+    kps = oracle.hessaff_detect(im)
+    for maxA in (1, 5):
+        a, b = oracle.detect_orientation(im, kps, maxAngles=maxA, doHalfSIFT=1), reference.detect_orientation(im, kps, maxAngles=maxA, doHalfSIFT=1)
+        assert len(a) > 50 and np.array_equal(a, b)
+        assert not np.array_equal(a, oracle.detect_orientation(im, kps, maxAngles=maxA)[:len(a)])
+    da, db = oracle.describe(im, a, rootsift=3), reference.describe(im, a, rootsift=3)
+    assert np.array_equal(da, db) and da[:, :64].any() and not da[:, 64:].any()
+    for det in (0, 3):
+        for flags in (7, 5):
+            va = oracle.view_pipeline(im, detector=det, desc=(5.1962, 41, True, flags))
+            vb = reference.view_pipeline(im, detector=det, desc=(5.1962, 41, True, flags))
+            assert len(va[0]) > 20
+            for x, y in zip(va, vb):
+                assert np.array_equal(x, y)
