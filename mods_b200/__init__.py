@@ -121,7 +121,8 @@ class PairConfig(C.Structure):
                 ("max_samples", C.c_int), ("errorType", C.c_int), ("doSymmCheck", C.c_int), ("seed", C.c_long),
                 ("use_mser", C.c_int), ("mser", MserParams), ("mserMatchRatio", C.c_double),
                 ("n_hess_views", C.c_int), ("n_mser_views", C.c_int), ("hess_views", ViewParams * 32), ("mser_views", ViewParams * 32),
-                ("useF", C.c_int), ("localOptimization", C.c_int), ("LAFCoef", C.c_double)]
+                ("useF", C.c_int), ("localOptimization", C.c_int), ("LAFCoef", C.c_double),
+                ("halfRootSIFT", C.c_int), ("reserved", C.c_int)]
 
     def set_views(self, hess=None, mser=None):
         """View tiers of the step: lists of (tilt, phi, zoom[, InitSigma]) as SetVSPars produces them; None = identity view only."""

@@ -671,6 +671,12 @@ int mb2_ctx_create_prio(int device, int high_priority, mb2_ctx** out) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return MB2_ERR_CUDA; }
   if (cudaSetDevice(device) != cudaSuccess) return MB2_ERR_CUDA;
+  // MB2_SCHED=yield|block: how host threads wait in cudaStreamSynchronize.  A pair keeps ~5 host threads waiting on the GPU; with one
+  // rank per GPU and few host cores per rank the default spin-wait oversubscribes the cores.
+  if (const char* sched = getenv("MB2_SCHED")) {
+    const unsigned f = !strcmp(sched, "yield") ? cudaDeviceScheduleYield : !strcmp(sched, "block") ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto;
+    if (cudaSetDeviceFlags(f) != cudaSuccess) cudaGetLastError();   // best effort
+  }
   mb2_ctx* c = new mb2_ctx();
   c->device = device;
   int prio_lo = 0, prio_hi = 0;

@@ -732,6 +732,7 @@ extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
   c->use_mser = 0; c->mser = dp.MSERParam; c->mserMatchRatio = 0.8;                 // iters_mods_cviu.ini:36 ([MSER0] FGINNThreshold)
   c->n_hess_views = c->n_mser_views = 0;
   std::memset(c->hess_views, 0, sizeof c->hess_views); std::memset(c->mser_views, 0, sizeof c->mser_views);
+  c->halfRootSIFT = 0;
   c->useF = 0; c->localOptimization = 1; c->LAFCoef = 2.0;                           // config_iter_mods_cviu.ini:168-169
 }
 
@@ -741,18 +742,24 @@ using namespace mods;
 struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.ini / an iters file with one HessianAffine tier
   DetectorsParameters det_par; DescriptorsParameters desc_par; DominantOrientationParams dom;
   std::string desc_name; IterationViewsynthesisParam iters; RANSACPars rp;
+  // descriptors of every tier: {desc_name}, or {"RootSIFT", "HalfRootSIFT"} for the WxBS tiers (iters_mods_cviu_wxbs.ini:35,48,61)
+  std::vector<std::string> descs;
   bool mser_identity_only = true;   // the batched two-image MSER pass covers the identity view only
   explicit PairSetup(const mb2_pair_config* cfg) {
     det_par.HessParam = cfg->det;
     desc_par.RootSIFTParam = cfg->desc; desc_par.SIFTParam = cfg->desc;
+    desc_par.HalfRootSIFTParam = cfg->desc; desc_par.HalfRootSIFTParam.rootSIFT = 1; desc_par.HalfRootSIFTParam.doHalfSIFT = 1;
+    desc_par.HalfSIFTParam = desc_par.HalfRootSIFTParam;
     dom.maxAngles = cfg->ori.maxAngles; dom.threshold = (float)cfg->ori.threshold; dom.mrSize = cfg->ori.mrSize; dom.patchSize = cfg->ori.patchSize;
     desc_name = cfg->desc.rootSIFT ? "RootSIFT" : "SIFT";
+    descs.push_back(desc_name);
+    if (cfg->halfRootSIFT && cfg->desc.rootSIFT) descs.push_back("HalfRootSIFT");
     auto tier = [&](const char* det, double ratio, int n, const mb2_view_params* views) {
-      if (n <= 0) { ViewSynthParameters v; v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = ratio; iters[det].push_back(v); return; }
+      auto add = [&](ViewSynthParameters v) { for (const std::string& d : descs) { v.descriptors.push_back(d); v.FGINNThreshold[d] = ratio; } iters[det].push_back(v); };
+      if (n <= 0) { add(ViewSynthParameters()); return; }
       for (int i = 0; i < n && i < MB2_MAX_PAIR_VIEWS; i++) {
         ViewSynthParameters v; v.tilt = views[i].tilt; v.phi = views[i].phi; v.zoom = views[i].zoom; v.InitSigma = views[i].InitSigma; v.doBlur = views[i].doBlur;
-        v.descriptors.push_back(desc_name); v.FGINNThreshold[desc_name] = ratio;
-        iters[det].push_back(v);
+        add(v);
       }
     };
     tier("HessianAffine", cfg->matchRatio, cfg->n_hess_views, cfg->hess_views);
@@ -762,7 +769,8 @@ struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.in
       tier("MSER", cfg->mserMatchRatio, cfg->n_mser_views, cfg->mser_views);
       const std::vector<ViewSynthParameters>& mv = iters["MSER"];
       mser_identity_only = mv.size() == 1 && std::fabs(mv[0].tilt - 1.) <= 0.1 && std::fabs(mv[0].phi) <= 0.2 && std::fabs(mv[0].zoom - 1.) <= 0.1 &&
-                           cfg->mser.mode == 0;   // the batched pass is FIXED_TH only (the other modes sort on the host per image)
+                           cfg->mser.mode == 0 &&   // the batched pass is FIXED_TH only (the other modes sort on the host per image)
+                           descs.size() == 1;       // ... and describes one descriptor with plain orientations
     }
     rp.err_threshold = cfg->err_threshold; rp.confidence = cfg->confidence; rp.max_samples = cfg->max_samples;
     rp.HLAFCoef = cfg->HLAFCoef; rp.errorType = (RANSAC_error_t)cfg->errorType; rp.doSymmCheck = cfg->doSymmCheck; rp.seed = cfg->seed;
@@ -773,10 +781,10 @@ struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.in
 // Everything the verification stage needs from the detection / matching stage, on the host.
 struct PairFront {
   std::unique_ptr<ImageRepresentation> rep1, rep2;
-  // tentatives per detector, in the order GetCorresponcesVector("All", "All") concatenates them
-  // (CorrespondencesMapMap[desc][det], std::map order: "HessianAffine" < "MSER")
-  struct Group { const char* det; std::vector<double> rows; int nt = 0; };
-  Group groups[2];
+  // tentatives per (descriptor, detector), in the order GetCorresponcesVector("All", "All") concatenates them
+  // (CorrespondencesMapMap[desc][det], std::map order: "HalfRootSIFT" < "RootSIFT", "HessianAffine" < "MSER")
+  struct Group { const char* det; std::string desc; std::vector<double> rows; int nt = 0; };
+  Group groups[4];
   int n_groups = 0, nt = 0, rc = MB2_OK;
   double t_start = 0;
 };
@@ -858,19 +866,29 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
   res->mser_regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name, "MSER"); res->mser_regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name, "MSER");
   t0 = now_ms();
   const char* dets[2] = {"HessianAffine", "MSER"};
-  for (int g = 0; g < (cfg->use_mser ? 2 : 1); g++) {   // MatchImgReps, separate detectors (correspondencebank.cpp:291-347)
-    PairFront::Group& G = out.groups[out.n_groups];
-    G.det = dets[g];
-    const ImageRepresentation::RegionBlock* Q = out.rep1->block(dets[g], ps.desc_name);
-    const ImageRepresentation::RegionBlock* T = out.rep2->block(dets[g], ps.desc_name);
-    out.n_groups++;
-    if (!(Q && T && Q->n > 0 && T->n > 0)) continue;
-    G.rows.resize((size_t)Q->n * 7);
-    G.nt = mb2_match_slots(ctx, g == 0 ? 0 : 2, g == 0 ? 1 : 3, g == 0 ? cfg->matchRatio : cfg->mserMatchRatio, cfg->contradDist, 50, G.rows.data(), Q->n);
-    if (G.nt < 0) { out.rc = G.nt; G.nt = 0; return; }
-    out.nt += G.nt;
-    if (g == 1) res->mser_tentatives = G.nt;
-  }
+  std::vector<std::string> desc_order = ps.descs;
+  std::sort(desc_order.begin(), desc_order.end());
+  for (const std::string& desc : desc_order)
+    for (int g = 0; g < (cfg->use_mser ? 2 : 1); g++) {   // MatchImgReps, separate detectors x separate descriptors (correspondencebank.cpp:291-347)
+      PairFront::Group& G = out.groups[out.n_groups];
+      G.det = dets[g]; G.desc = desc;
+      const ImageRepresentation::RegionBlock* Q = out.rep1->block(dets[g], desc);
+      const ImageRepresentation::RegionBlock* T = out.rep2->block(dets[g], desc);
+      out.n_groups++;
+      if (!(Q && T && Q->n > 0 && T->n > 0)) continue;
+      G.rows.resize((size_t)Q->n * 7);
+      const double ratio = g == 0 ? cfg->matchRatio : cfg->mserMatchRatio;
+      if (desc == ps.desc_name)   // the first descriptor of the tier is the one left resident on the device
+        G.nt = mb2_match_slots(ctx, g == 0 ? 0 : 2, g == 0 ? 1 : 3, ratio, cfg->contradDist, 50, G.rows.data(), Q->n);
+      else {
+        std::vector<double> txy((size_t)T->n * 2);
+        for (int i = 0; i < T->n; i++) { txy[2 * i] = T->reproj_kp[(size_t)i * MB2_KP]; txy[2 * i + 1] = T->reproj_kp[(size_t)i * MB2_KP + 1]; }
+        G.nt = mb2_match_fginn(ctx, Q->desc_u8.data(), Q->n, T->desc_u8.data(), T->n, txy.data(), ratio, cfg->contradDist, 50, G.rows.data(), Q->n);
+      }
+      if (G.nt < 0) { out.rc = G.nt; G.nt = 0; return; }
+      out.nt += G.nt;
+      if (g == 1) res->mser_tentatives += G.nt;
+    }
   res->ms_match = now_ms() - t0;
   res->tentatives = out.nt;
 }
@@ -889,8 +907,8 @@ int pair_back(mb2_ctx* vctx, const mb2_pair_config* cfg, PairSetup& ps, PairFron
     for (int g = 0; g < in.n_groups; g++) {
       const PairFront::Group& G = in.groups[g];
       if (G.nt <= 0) continue;
-      const ImageRepresentation::RegionBlock* Q = in.rep1->block(G.det, ps.desc_name);
-      const ImageRepresentation::RegionBlock* T = in.rep2->block(G.det, ps.desc_name);
+      const ImageRepresentation::RegionBlock* Q = in.rep1->block(G.det, G.desc);
+      const ImageRepresentation::RegionBlock* T = in.rep2->block(G.det, G.desc);
       for (int i = 0; i < G.nt; i++, o++) {
         const double* r = &G.rows[(size_t)i * 7];
         const double* a = &Q->reproj_kp[(size_t)r[0] * MB2_KP];

@@ -216,6 +216,10 @@ typedef struct {
    * (exp_ransacFcustom + F_LAF_check) instead of the homography one */
   int useF, localOptimization;
   double LAFCoef;
+  /* 1: every tier describes `RootSIFT,HalfRootSIFT` (the WxBS tiers): orientations modulo pi for both (the Half* name is sticky,
+   * imagerepresentation.cpp:693-714), each (detector, descriptor) group matched separately, all tentatives verified together.
+   * regions1/2 and mser_regions1/2 count the RootSIFT regions; tentatives / mser_tentatives sum over both descriptors. */
+  int halfRootSIFT, reserved;
 } mb2_pair_config;
 typedef struct {
   int regions1, regions2, tentatives, unique_tentatives, ransac_inliers, verified;

@@ -218,3 +218,34 @@ def test_mods_pair_wxbs_style_config(ctx, oracle):
     assert (res.mser_regions1, res.mser_regions2) == tuple(counts) and res.verified >= 8
     p = np.c_[ver[:, :2], np.ones(len(ver))] @ gt_homography(480, 360).T
     assert np.median(np.hypot(p[:, 0] / p[:, 2] - ver[:, 2], p[:, 1] / p[:, 2] - ver[:, 3])) < 1.5
+
+
+def test_mods_pair_with_half_root_sift_descriptor_list(ctx, oracle):
+    """`Descriptors=RootSIFT,HalfRootSIFT` (WxBS tiers, iters_mods_cviu_wxbs.ini:35,48,61) through the pair driver: both descriptors on
+    regions oriented modulo pi, the four (descriptor, detector) groups matched separately == the oracle's stages composed."""
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(480, 360, seed=21, n_blobs=500)
+    B = warp_image(A, gt_homography(480, 360), seed=22)
+    cfg = mb.PairConfig.default()
+    cfg.seed = 5; cfg.use_mser = 1; cfg.halfRootSIFT = 1
+    res, ver = ctx.mods_pair(A, B, cfg, capacity=8192)
+    n1 = n2 = nt = nt_mser = 0
+    for det, ratio in ((0, cfg.matchRatio), (3, cfg.mserMatchRatio)):
+        for flags in (5, 7):   # RootSIFT on half-oriented regions, HalfRootSIFT
+            oa = oracle.view_pipeline(A, detector=det, desc=(5.1962, 41, True, flags))
+            ob = oracle.view_pipeline(B, detector=det, desc=(5.1962, 41, True, flags))
+            m = len(oracle.match_fginn(oa[2], ob[2], np.ascontiguousarray(ob[1][:, :2]), ratio=ratio, contradDist=cfg.contradDist))
+            nt += m
+            if det == 3:
+                nt_mser += m
+            if flags == 5:
+                n1 += len(oa[0]); n2 += len(ob[0])
+    assert (res.regions1, res.regions2) == (n1, n2)
+    assert (res.tentatives, res.mser_tentatives) == (nt, nt_mser)
+    assert res.verified >= 8
+    p = np.c_[ver[:, :2], np.ones(len(ver))] @ gt_homography(480, 360).T
+    assert np.median(np.hypot(p[:, 0] / p[:, 2] - ver[:, 2], p[:, 1] / p[:, 2] - ver[:, 3])) < 1.5
+    # the pipelined dataset call gives the same result
+    out, _ = ctx.mods_pairs([(A, B), (A, B)], cfg)
+    for r in out:
+        assert (r.regions1, r.tentatives, r.verified) == (res.regions1, res.tentatives, res.verified)
