@@ -51,6 +51,10 @@ typedef struct {
   float rel_reg_number;
   int patchSize;              /* 41 */
   float mrSize;               /* 3*sqrt(3) */
+  int detectorType;           /* detector_type (structures.hpp): 0 DET_HESSIAN, 1 DET_DOG -- the response of every level becomes
+                               * level - GaussianBlur(level, sigma = curSigma^2) (pyramid.cpp:176-181, Response() :132-175), the
+                               * threshold is used un-squared (pyramid.h:56-57) and the point type is the sign (DOG_DARK 10 /
+                               * DOG_BRIGHT 11, pyramid.cpp:92-99); everything else is the same scale-space detector */
 } mb2_hessaff_params;
 
 /* [MSER] section of config_iter_mods_cviu.ini == extrema::ExtremaParams (detectors/mser/extrema/extremaParams.h:56-93). */

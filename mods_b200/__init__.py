@@ -32,11 +32,16 @@ class HessaffParams(C.Structure):
                 ("edgeEigenValueRatio", C.c_float), ("border", C.c_int), ("maxIterations", C.c_int),
                 ("convergenceThreshold", C.c_float), ("smmWindowSize", C.c_int), ("doBaumberg", C.c_int),
                 ("mode", C.c_int), ("reg_number", C.c_int), ("rel_threshold", C.c_float),
-                ("rel_reg_number", C.c_float), ("patchSize", C.c_int), ("mrSize", C.c_float)]
+                ("rel_reg_number", C.c_float), ("patchSize", C.c_int), ("mrSize", C.c_float), ("detectorType", C.c_int)]
 
     @staticmethod
     def default():
-        return HessaffParams(5.3333, 3, 1.6, 10.0, 5, 16, 0.05, 19, 1, 0, 2000, -1.0, -1.0, 41, 3.0 * 3.0 ** 0.5)
+        return HessaffParams(5.3333, 3, 1.6, 10.0, 5, 16, 0.05, 19, 1, 0, 2000, -1.0, -1.0, 41, 3.0 * 3.0 ** 0.5, 0)
+
+    @staticmethod
+    def dog():
+        """[DoG] of config_iter_mods_cviu_wxbs.ini:45-59 with mode FixedTh: threshold 8, no Baumberg iteration."""
+        return HessaffParams(8.0, 3, 1.6, 10.0, 5, 16, 0.05, 19, 0, 0, 3000, 0.01, 0.5, 41, 3.0 * 3.0 ** 0.5, 1)
 
 
 class MserParams(C.Structure):

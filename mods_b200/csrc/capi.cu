@@ -257,6 +257,7 @@ struct PyramidLayout {
 int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par, double tilt, double zoom, int as_regions, int* n_out) {
   *n_out = 0;
   if (par.mode < 0 || par.mode > 4) { ctx->set_error("hessaff: unknown DetectorMode"); return MB2_ERR_ARG; }
+  if (par.detectorType < 0 || par.detectorType > 1) { ctx->set_error("scale-space detector: only DET_HESSIAN (0) and DET_DOG (1) are built"); return MB2_ERR_UNSUPPORTED; }
   if (par.numberOfScales + 2 > MB2_MAX_LEVELS || par.smmWindowSize != 19 || par.border < 2) {
     ctx->set_error("hessaff: unsupported numberOfScales / smmWindowSize / border"); return MB2_ERR_ARG;
   }
@@ -316,7 +317,8 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
 
   // thresholds (pyramid.h:46-69)
   // every mode but FIXED_TH opens all response gates: every 3x3x3 extremum is localised and goes through Baumberg (pyramid.h:59-60)
-  const float finalThreshold = par.mode != 0 ? 0.0f : par.threshold * par.threshold;
+  const bool dog = par.detectorType == 1;
+  const float finalThreshold = par.mode != 0 ? 0.0f : (dog ? par.threshold : par.threshold * par.threshold);   // squared for DET_HESSIAN only
   const float positiveThreshold = par.mode != 0 ? 0.0f : (float)(0.8 * par.threshold), negativeThreshold = -positiveThreshold;
   const double er = par.edgeEigenValueRatio;
   const double edgeScoreThreshold = (er + 1.0f) * (er + 1.0f) / er;
@@ -336,6 +338,26 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
   int* d_counts = ctx->misc.as<int>();  // [0] = candidates (per octave), [1] = keypoints (global)
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, 64, ctx->stream));
 
+  // DET_DOG: the response of level l is level - GaussianBlur(level, sigma = levelSigma[l]^2) in every octave: taps of the NL wide
+  // kernels on the device (ctx->dog_taps), one scratch plane for the row pass
+  std::vector<int> dog_n(NL, 0), dog_off(NL, 0);
+  if (dog) {
+    std::vector<float> all;
+    for (int l = 0; l < NL; l++) {
+      const float sg = levelSigma[l] * levelSigma[l];
+      dog_n[l] = mb2host::gauss_ksize(sg); dog_off[l] = (int)all.size();
+      const std::vector<float> k = mb2host::gauss_kernel(dog_n[l], sg);
+      all.insert(all.end(), k.begin(), k.end());
+    }
+    MB2_CUDA_CHECK(ctx, ctx->dog_taps.reserve(all.size() * 4));
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dog_taps.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // `all` is a host temporary
+    MB2_CUDA_CHECK(ctx, ctx->dog_tmp.reserve((size_t)L.pitch[0] * L.rows[0] * 4));
+  }
+  auto dog_response = [&](const OctaveLevels& oc, int l) {
+    mb2_launch_dog(ctx, oc.blur[l], (float*)oc.resp[l].p, oc.resp[l].pitch, ctx->dog_taps.as<float>() + dog_off[l], dog_n[l], ctx->dog_tmp.as<float>());
+  };
+
   // ---- scale space -----------------------------------------------------------------------------
   float pixelDistance = 1.0f;
   for (int o = 0; o < L.n_octaves; o++) {
@@ -346,24 +368,26 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
       float n0 = levelSigma[0] * levelSigma[0];
       if (par.initialSigma > curSigma0) {
         const float sigma = std::sqrt(par.initialSigma * par.initialSigma - curSigma0 * curSigma0);
-        rc = mb2_launch_blur(ctx, img, (float*)oc.blur[0].p, (float*)oc.resp[0].p, oc.blur[0].pitch, make_taps(sigma), n0 * n0, 1);
+        rc = mb2_launch_blur(ctx, img, (float*)oc.blur[0].p, (float*)oc.resp[0].p, oc.blur[0].pitch, make_taps(sigma), n0 * n0, dog ? 0 : 1);
         if (rc) return rc;
+        if (dog) dog_response(oc, 0);
       } else {
         MB2_CUDA_CHECK(ctx, cudaMemcpy2DAsync((void*)oc.blur[0].p, (size_t)oc.blur[0].pitch * 4, img.p, (size_t)img.pitch * 4,
                                               (size_t)img.cols * 4, img.rows, cudaMemcpyDeviceToDevice, ctx->stream));
-        mb2_launch_hessian(ctx, oc.blur[0], (float*)oc.resp[0].p, oc.resp[0].pitch, n0 * n0);
+        if (dog) dog_response(oc, 0); else mb2_launch_hessian(ctx, oc.blur[0], (float*)oc.resp[0].p, oc.resp[0].pitch, n0 * n0);
       }
     } else {
       // next octave = cv::resize(level S, 0.5) of the previous one (pyramid.cpp:517-520)
       mb2_launch_resize_half(ctx, octs[o - 1].blur[S], (float*)oc.blur[0].p, oc.blur[0].rows, oc.blur[0].cols, oc.blur[0].pitch);
       float n0 = levelSigma[0] * levelSigma[0];
-      mb2_launch_hessian(ctx, oc.blur[0], (float*)oc.resp[0].p, oc.resp[0].pitch, n0 * n0);
+      if (dog) dog_response(oc, 0); else mb2_launch_hessian(ctx, oc.blur[0], (float*)oc.resp[0].p, oc.resp[0].pitch, n0 * n0);
     }
     for (int i = 1; i < NL; i++) {
       float nrm = levelSigma[i] * levelSigma[i];  // Response(nextBlur, sigma*sigma); HessianResponse squares it again
       rc = mb2_launch_blur(ctx, oc.blur[i - 1], (float*)oc.blur[i].p, (float*)oc.resp[i].p, oc.blur[i].pitch, make_taps(incSigma[i]),
-                           nrm * nrm, 1);
+                           nrm * nrm, dog ? 0 : 1);
       if (rc) return rc;
+      if (dog) dog_response(oc, i);
     }
     // ---- extrema -> localisation -> de-duplication, levels 1..S in the reference's order --------
     MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int), ctx->stream));
@@ -377,7 +401,7 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
     if (n_cand > 0) {
       LocalizeParams lp;
       lp.edgeScoreThreshold = edgeScoreThreshold; lp.finalThreshold = finalThreshold; lp.pixelDistance = pixelDistance;
-      lp.numberOfScales = S;
+      lp.numberOfScales = S; lp.detectorType = dog ? 1 : 0;
       // findLevelKeypoints(curSigma): curSigma at level lv is initialSigma * sigmaStep^lv accumulated in float
       {
         float cs = par.initialSigma;

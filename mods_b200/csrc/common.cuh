@@ -71,7 +71,7 @@ struct mb2_ctx {
   long long launches = 0;
   int num_sms = 148;
   // scratch, reused across calls
-  DevBuf img, pyr, resp, cand, misc, kp_a, kp_b, kp_c, desc_u8, patch_scratch, nn_a, nn_b, nn_c, nn_d, rs_a, rs_b, rs_c, rs_u, rs_v;
+  DevBuf img, pyr, resp, cand, misc, kp_a, kp_b, kp_c, desc_u8, patch_scratch, nn_a, nn_b, nn_c, nn_d, rs_a, rs_b, rs_c, rs_u, rs_v, dog_taps, dog_tmp;
   DevBuf octmap;
   HostBuf h_a, h_b, h_c;
   RegionSlot slots[MB2_MAX_SLOTS];

@@ -325,7 +325,8 @@ __global__ void k_emit_keypoints(OctaveLevels oct, const Localized* __restrict__
   // glibc powf is not correctly rounded (and has FMA / non-FMA builds), so the host adapter
   // evaluates it -- see detect_core; here we only carry b2.
   int type;
-  if (L.val < 0) type = 2;
+  if (lp.detectorType == 1) type = L.val < 0 ? 11 : 10;   // DOG_BRIGHT : DOG_DARK
+  else if (L.val < 0) type = 2;
   else {
     const ImgView blur = oct.blur[L.level];
     const float Lxx = fadd(fsub(blur.at(L.r, L.c - 1), fmul(2.f, blur.at(L.r, L.c))), blur.at(L.r, L.c + 1));
@@ -380,8 +381,36 @@ void launch_blur_nt(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* ds
 using namespace MB2_NS;
 
 // ---------------------------------------------------------------------------------------------
+// DET_DOG response: wide separable Gaussian in OpenCV's order (generic row filter left to right, symmetric column filter centre
+// then pairs, BORDER_REPLICATE; oracle/cvmath.h sep_filter), the subtraction fused into the column pass.  Tap counts reach ~100
+// (sigma = curSigma^2), so the taps live in global memory and every thread walks its own window through L1/L2.
+__global__ void k_wide_rows(ImgView src, const float* __restrict__ k, int n, float* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.cols || y >= src.rows) return;
+  const float* s = src.p + (size_t)y * src.pitch;
+  const int h = n / 2, last = src.cols - 1;
+  float acc = fmul(k[0], s[max(x - h, 0)]);
+  for (int j = 1; j < n; j++) acc = fadd(acc, fmul(k[j], s[min(max(x - h + j, 0), last)]));
+  dst[(size_t)y * src.pitch + x] = acc;
+}
+__global__ void k_dog_cols(ImgView level, const float* __restrict__ tmp, const float* __restrict__ k, int n, float* __restrict__ resp, int resp_pitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= level.cols || y >= level.rows) return;
+  const int h = n / 2, last = level.rows - 1;
+  float d = fmul(k[h], tmp[(size_t)y * level.pitch + x]);
+  for (int j = 1; j <= h; j++)
+    d = fadd(d, fmul(k[h + j], fadd(tmp[(size_t)min(y + j, last) * level.pitch + x], tmp[(size_t)max(y - j, 0) * level.pitch + x])));
+  resp[(size_t)y * resp_pitch + x] = fsub(level.p[(size_t)y * level.pitch + x], d);
+}
+
 // host launchers
 // ---------------------------------------------------------------------------------------------
+void mb2_launch_dog(mb2_ctx* ctx, const ImgView& level, float* resp, int resp_pitch, const float* d_taps, int n, float* d_tmp) {
+  dim3 block(32, 8), grid((level.cols + 31) / 32, (level.rows + 7) / 8);
+  MB2_LAUNCH(ctx, k_wide_rows, grid, block, 0, level, d_taps, n, d_tmp);
+  MB2_LAUNCH(ctx, k_dog_cols, grid, block, 0, level, (const float*)d_tmp, d_taps, n, resp, resp_pitch);
+}
+
 int mb2_launch_blur(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps,
                     float norm2, int want_resp) {
   switch (taps.n) {

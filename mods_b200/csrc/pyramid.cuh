@@ -34,8 +34,12 @@ struct LocalizeParams {
   float pixelDistance;
   int numberOfScales;
   float levelSigma[MB2_MAX_LEVELS];
+  int detectorType;   // 0 DET_HESSIAN, 1 DET_DOG (getPointType, pyramid.cpp:66-130)
 };
 
+// DET_DOG response (pyramid.cpp:176-181): resp = level - GaussianBlur(level, ksize(sigma), sigma, BORDER_REPLICATE); d_taps: n taps on
+// the device, d_tmp: one plane of the level's size (row pass)
+void mb2_launch_dog(mb2_ctx* ctx, const ImgView& level, float* resp, int resp_pitch, const float* d_taps, int n, float* d_tmp);
 int mb2_launch_blur(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps,
                     float norm2, int want_resp);
 void mb2_launch_hessian(mb2_ctx* ctx, const ImgView& src, float* dst, int dst_pitch, float norm2);

@@ -96,6 +96,7 @@ struct HessParamsC {
   float threshold; int numberOfScales; float initialSigma; float edgeEigenValueRatio; int border;
   int maxIterations; float convergenceThreshold; int smmWindowSize; int doBaumberg;
   int mode; int reg_number; float rel_threshold; float rel_reg_number; int patchSize; float mrSize;
+  int detectorType;   // 0 DET_HESSIAN, 1 DET_DOG
 };
 HessParams to_par(const HessParamsC& c) {
   HessParams p;
@@ -103,7 +104,7 @@ HessParams to_par(const HessParamsC& c) {
   p.edgeEigenValueRatio = c.edgeEigenValueRatio; p.border = c.border; p.maxIterations = c.maxIterations;
   p.convergenceThreshold = c.convergenceThreshold; p.smmWindowSize = c.smmWindowSize; p.doBaumberg = c.doBaumberg;
   p.mode = c.mode; p.reg_number = c.reg_number; p.rel_threshold = c.rel_threshold; p.rel_reg_number = c.rel_reg_number;
-  p.patchSize = c.patchSize; p.mrSize = c.mrSize;
+  p.patchSize = c.patchSize; p.mrSize = c.mrSize; p.detectorType = c.detectorType;
   return p;
 }
 void kp_out(const Key& k, double* o) {

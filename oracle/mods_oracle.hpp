@@ -51,6 +51,7 @@ struct HessParams {  // [HessianAffine] of config_iter_mods_cviu.ini; structures
   int smmWindowSize = 19;
   int doBaumberg = 1;
   int mode = 0;  // FIXED_TH
+  int detectorType = 0;  // detector_type (structures.hpp): 0 DET_HESSIAN, 1 DET_DOG
   int reg_number = -1;
   float rel_threshold = -1;
   float rel_reg_number = -1;
@@ -303,6 +304,12 @@ inline Image hessianResponse(const Image& in, float norm) {  // pyramid.cpp:223-
   return out;
 }
 
+inline Image dogResponse(const Image& in, float norm) {  // pyramid.cpp:176-181: the level minus its own blur with sigma = norm (= curSigma^2)
+  Image nb = gaussianBlur(in, norm), out(in.rows, in.cols);
+  for (size_t i = 0; i < out.px.size(); i++) out.px[i] = in.px[i] - nb.px[i];
+  return out;
+}
+
 struct Candidate { int r, c; };  // 3x3x3 extremum before localisation
 
 struct HessianAffineDetector {
@@ -328,7 +335,7 @@ struct HessianAffineDetector {
     finalThreshold = par.threshold;
     positiveThreshold = (float)(0.8 * finalThreshold);
     negativeThreshold = -positiveThreshold;
-    finalThreshold = par.threshold * par.threshold;  // DET_HESSIAN
+    if (par.detectorType == 0) finalThreshold = par.threshold * par.threshold;  // DET_HESSIAN only (pyramid.h:56-57)
     if (par.mode != 0) finalThreshold = positiveThreshold = negativeThreshold = 0.0f;
     computeGaussMask(smmMask.data(), par.smmWindowSize);
   }
@@ -421,8 +428,9 @@ struct HessianAffineDetector {
       return;
     octaveMap[(size_t)r * cols + c] = 1;
     float scale = curScale * std::pow(2.0f, b[2] / par.numberOfScales);
-    int type;  // getPointType, pyramid.cpp:66-130 (DET_HESSIAN)
-    if (val < 0) type = 2;
+    int type;  // getPointType, pyramid.cpp:66-130
+    if (par.detectorType == 1) type = val < 0 ? 11 : 10;   // DOG_BRIGHT : DOG_DARK (pyramid.h:36-37)
+    else if (val < 0) type = 2;
     else {
       const float* p = blur.row(r) + c;
       float Lxx = (p[-1] - 2 * p[0] + p[1]);
@@ -450,13 +458,14 @@ struct HessianAffineDetector {
     float curSigma = par.initialSigma;
     int numLevels = 1;
     Image blur = firstLevel, prevBlur, low, cur, high;
-    cur = hessianResponse(blur, curSigma * curSigma);
+    auto response = [&](const Image& im, float norm) { return par.detectorType == 1 ? dogResponse(im, norm) : hessianResponse(im, norm); };   // pyramid.cpp:132-175
+    cur = response(blur, curSigma * curSigma);
     if (keep_levels) { dump_blur.push_back(blur); dump_resp.push_back(cur); dump_info.push_back({octave, 0, blur.rows, blur.cols, pixelDistance, curSigma}); }
     for (int i = 1; i < par.numberOfScales + 2; i++) {
       float sigma = curSigma * std::sqrt(sigmaStep * sigmaStep - 1.0f);
       Image nextBlur = gaussianBlur(blur, sigma);
       sigma = curSigma * sigmaStep;
-      high = hessianResponse(nextBlur, sigma * sigma);
+      high = response(nextBlur, sigma * sigma);
       if (keep_levels) { dump_blur.push_back(nextBlur); dump_resp.push_back(high); dump_info.push_back({octave, i, blur.rows, blur.cols, pixelDistance, sigma}); }
       numLevels++;
       if (numLevels == 3) {

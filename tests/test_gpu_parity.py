@@ -286,6 +286,32 @@ def test_ransac_h_degenerate_inputs(ctx):
     assert ctx.ransac_h(u)["I"] == 0
 
 
+# ---- DoG flavour of the scale-space detector -----------------------------------------------------------
+@pytest.mark.parametrize("mode,regs", [(0, 3000), (4, 200), (2, 150)])
+def test_dog_detector_vs_oracle_and_golden(ctx, oracle, mode, regs):
+    """mb2_hessaff_params.detectorType = 1 (DET_DOG): response = level - GaussianBlur(level, sigma^2) with up to ~100 taps, un-squared
+    threshold, sign point types; keys bit-exact against the oracle (== compiled reference) and the reference's golden vectors."""
+    from oracle.pyoracle import HessParams
+    im = synth.blob_image(480, 360, seed=33)
+    hp = HessParams.dog(); hp.mode = mode; hp.reg_number = regs
+    gp = mb.HessaffParams.dog(); gp.mode = mode; gp.reg_number = regs
+    a = ctx.hessaff_detect(im, gp, as_regions=False)
+    assert len(a) > 100 and np.array_equal(a, oracle.hessaff_detect(im, hp, raw=True)) and set(a[:, 8].astype(int)) <= {10, 11}
+    if mode == 0:
+        GD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dog_vectors.npz"))
+        img = GD["image"].astype(np.float32)
+        assert np.array_equal(ctx.hessaff_detect(img, mb.HessaffParams.dog(), as_regions=False), GD["raw_fixed_th"])
+        v = ctx.detect_describe_view(img, det=mb.HessaffParams.dog())
+        assert np.array_equal(v[0], GD["view_det"]) and np.array_equal(v[2], GD["view_desc"])
+        g, o = ctx.detect_describe_view(im, det=gp), oracle.view_pipeline(im, hp=hp)
+        assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2].astype(np.float32), o[2])
+        # pyramid levels: the response plane is the level minus its wide blur, bit for bit
+        p = oracle.pyramid(im, hp)
+        ctx.hessaff_detect(im, gp)
+        for lv in p["levels"][:7]:
+            assert np.array_equal(ctx.pyramid_level(lv["octave"], lv["level"], want_resp=True), lv["resp"])
+
+
 # ---- HalfRootSIFT (WxBS tiers) -----------------------------------------------------------------------
 def test_half_root_sift_vs_oracle_and_golden(ctx, oracle):
     """Orientations modulo pi (mb2_orientation_params.doHalfSIFT) and the folded 64-entry descriptor (mb2_sift_params.doHalfSIFT):

@@ -79,3 +79,16 @@ def test_half_root_sift_matches_reference(oracle):
     assert np.array_equal(oracle.describe(im, GH["oriented_half_a1"], rootsift=3).astype(np.uint8), GH["desc_half"])
     v = oracle.view_pipeline(im, detector=0, desc=(5.1962, 41, True, 7))
     assert np.array_equal(v[0], GH["view_det"]) and np.array_equal(v[2].astype(np.uint8), GH["view_desc"])
+
+
+def test_dog_detector_matches_reference(oracle):
+    """DET_DOG flavour of the scale-space detector: tests/golden/make_golden_dog.py."""
+    from oracle.pyoracle import HessParams
+    GD = np.load(os.path.join(os.path.dirname(__file__), "golden", "dog_vectors.npz"))
+    im = GD["image"].astype(np.float32)
+    hp = HessParams.dog()
+    assert np.array_equal(oracle.hessaff_detect(im, hp, raw=True), GD["raw_fixed_th"]) and len(GD["raw_fixed_th"]) > 50
+    hp.mode = 4; hp.reg_number = 80
+    assert np.array_equal(oracle.hessaff_detect(im, hp, raw=True), GD["raw_not_less_80"])
+    v = oracle.view_pipeline(im, hp=HessParams.dog())
+    assert np.array_equal(v[0], GD["view_det"]) and np.array_equal(v[2].astype(np.uint8), GD["view_desc"])

@@ -194,3 +194,15 @@ def test_half_root_sift_oracle_vs_reference(oracle, reference):
             assert len(va[0]) > 20
             for x, y in zip(va, vb):
                 assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("mode,regs", [(0, 3000), (4, 200), (2, 150), (1, 3000)])
+def test_dog_detector_oracle_vs_reference(oracle, reference, mode, regs):
+    from oracle.pyoracle import HessParams
+    im = synth.blob_image(320, 240, seed=5)
+    hp = HessParams.dog(); hp.mode = mode; hp.reg_number = regs
+    a, b = oracle.hessaff_detect(im, hp, raw=True), reference.hessaff_detect(im, hp, raw=True)
+    assert len(a) > 50 and np.array_equal(a, b) and set(a[:, 8].astype(int)) <= {10, 11}
+    if mode == 0:
+        va, vb = oracle.view_pipeline(im, hp=hp), reference.view_pipeline(im, hp=hp)
+        assert all(np.array_equal(x, y) for x, y in zip(va, vb))
