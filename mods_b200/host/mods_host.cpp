@@ -689,7 +689,9 @@ namespace {
 //   [2] the MSER pass of both images of a pair (one batched detection, mb2_mser_detect_pair), next to the two HessianAffine passes,
 //   [3] orientation + description of the second image's MSER regions while [2] does the first image's.
 std::mutex g_sib_mutex;
-struct Helpers { mb2_ctx* c[4] = {nullptr, nullptr, nullptr, nullptr}; bool tried[4] = {false, false, false, false}; };
+//   [4], [5] further MSER contexts: with MB2_MSER_AHEAD=n the dataset call (mb2_mods_pairs) runs the MSER detection of the next n pairs
+//   while the current pair is in its HessianAffine / description stage; a detection owns its context until it is described.
+struct Helpers { mb2_ctx* c[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; bool tried[6] = {false, false, false, false, false, false}; };
 std::unordered_map<mb2_ctx*, Helpers> g_siblings;
 mb2_ctx* sibling_ctx(mb2_ctx* ctx, int which = 0) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
@@ -791,8 +793,15 @@ struct PairFront {
 
 // mods.cpp:229-330 for one pair: SynthDetectDescribeKeypoints of both images on two host threads
 // (mods.cpp:255-271 runs them as two OpenMP tasks), each with its own context / stream, then MatchImgReps.
+// A MSER detection of both images of a pair started ahead of its pair_front (mb2_mods_pairs, MB2_MSER_AHEAD): mb2_mser_detect_pair
+// running on context `c` in its own thread.
+struct MserAhead {
+  mb2_ctx* c = nullptr; std::thread th; int rc = MB2_OK, n1 = 0, n2 = 0; double ms = 0;
+  ~MserAhead() { if (th.joinable()) th.join(); }
+};
+
 void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2, const mb2_pair_config* cfg,
-                PairSetup& ps, mb2_pair_result* res, PairFront& out) {
+                PairSetup& ps, mb2_pair_result* res, PairFront& out, MserAhead* pre = nullptr) {
   out.t_start = now_ms();
   mb2_ctx* ctx2 = mb2_ctx_profiling(ctx) ? nullptr : sibling_ctx(ctx, 0);   // per-kernel profiling keeps everything on one stream
   out.rep1.reset(new ImageRepresentation(ctx, GrayImage{img1, h1, w1}, "img1", 0));
@@ -800,7 +809,7 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
   double t0 = now_ms();
   // MSER of both images in ONE batched pass on a third context when the images have the same size (the component-tree
   // kernel is latency bound: two images cost hardly more than one); otherwise per image, after HessianAffine.
-  mb2_ctx* ctx3 = (ctx2 && cfg->use_mser && ps.mser_identity_only && w1 == w2 && h1 == h2) ? sibling_ctx(ctx, 2) : nullptr;
+  mb2_ctx* ctx3 = (ctx2 && cfg->use_mser && ps.mser_identity_only && w1 == w2 && h1 == h2) ? (pre ? pre->c : sibling_ctx(ctx, 2)) : nullptr;
   IterationViewsynthesisParam iters_here = ps.iters;
   if (ctx3) {
     iters_here.erase("MSER");
@@ -820,8 +829,15 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
   auto mser_pair = [&] {
     int n1 = 0, n2 = 0;
     const double ta = now_ms();
-    if ((mser_rc = mb2_mser_detect_pair(ctx3, img1, img2, w1, h1, &ps.det_par.MSERParam, &n1, &n2)) < 0) return;
-    tm_detect = now_ms() - ta;
+    if (pre) {   // started while the previous pair was in its HessianAffine / description stage
+      if (pre->th.joinable()) pre->th.join();
+      if ((mser_rc = pre->rc) < 0) return;
+      n1 = pre->n1; n2 = pre->n2;
+      tm_detect = pre->ms;
+    } else {
+      if ((mser_rc = mb2_mser_detect_pair(ctx3, img1, img2, w1, h1, &ps.det_par.MSERParam, &n1, &n2)) < 0) return;
+      tm_detect = now_ms() - ta;
+    }
     struct PostTimer { double& t; double t0; ~PostTimer() { t = now_ms() - t0; } } post_timer{tm_post, now_ms()};
     mser_rc = MB2_OK;
     // the two images are finished side by side: image 1 here, image 2 on a fourth context
@@ -838,7 +854,8 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
   if (ctx2) {
     // The tree kernel of the MSER pass goes first and alone: the HessianAffine streams are ordered behind it (they then overlap
     // with the rest of the MSER pass), because next to their bandwidth-hungry kernels the latency-bound tree kernel takes 2-3x longer.
-    static const bool tree_first = getenv("MB2_NO_TREE_FIRST") == nullptr;
+    static const bool tree_first_env = getenv("MB2_NO_TREE_FIRST") == nullptr;
+    const bool tree_first = tree_first_env && !pre;   // a detection started ahead belongs to another time window: nothing to order behind
     const long long epoch0 = ctx3 ? mb2_ctx_tree_epoch(ctx3) : 0;
     auto wait_tree = [&](mb2_ctx* c) {
       if (!ctx3 || !tree_first) return;
@@ -1029,10 +1046,41 @@ extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img
       if (r < 0) { std::lock_guard<std::mutex> lk(m); rc = r; }
     }
   });
+  // MB2_MSER_AHEAD=n (0..2): the MSER detection (component tree: latency bound, ~10 % SM use) of the next n pairs runs while the
+  // current pair is in its HessianAffine / description stage, each on its own context.  Same results, different schedule.
+  int ahead = 0;
+  if (const char* e = getenv("MB2_MSER_AHEAD")) ahead = std::max(0, std::min(2, atoi(e)));
+  bool same_size = true;
+  for (int k = 0; k < n_pairs; k++) same_size = same_size && w1[k] == w2[k] && h1[k] == h2[k];
+  if (!(cfg->use_mser && ps.mser_identity_only && same_size && sibling_ctx(ctx, 0))) ahead = 0;
+  mb2_ctx* pool[3] = {nullptr, nullptr, nullptr};
+  if (ahead > 0) {
+    static const int which[3] = {2, 4, 5};
+    for (int i = 0; i <= ahead; i++) if (!(pool[i] = sibling_ctx(ctx, which[i]))) ahead = 0;
+  }
+  std::deque<std::unique_ptr<MserAhead> > inflight;
+  int next_launch = 0;
+  auto launch_ahead = [&](int k) {
+    std::unique_ptr<MserAhead> a(new MserAhead);
+    a->c = pool[k % (ahead + 1)];
+    MserAhead* p = a.get();
+    p->th = std::thread([p, k, &ps, img1, img2, w1, h1] {
+      const double t0 = now_ms();
+      p->rc = mb2_mser_detect_pair(p->c, img1[k], img2[k], w1[k], h1[k], &ps.det_par.MSERParam, &p->n1, &p->n2);
+      p->ms = now_ms() - t0;
+    });
+    inflight.push_back(std::move(a));
+  };
   for (int k = 0; k < n_pairs; k++) {
     std::memset(&res[k], 0, sizeof res[k]);
     std::unique_ptr<PairFront> f(new PairFront);
-    pair_front(ctx, img1[k], w1[k], h1[k], img2[k], w2[k], h2[k], cfg, ps, &res[k], *f);
+    std::unique_ptr<MserAhead> pre;
+    if (ahead > 0) {
+      while (next_launch < n_pairs && next_launch <= k + ahead) launch_ahead(next_launch++);
+      pre = std::move(inflight.front()); inflight.pop_front();
+    }
+    pair_front(ctx, img1[k], w1[k], h1[k], img2[k], w2[k], h2[k], cfg, ps, &res[k], *f, pre.get());
+    pre.reset();
     std::unique_lock<std::mutex> lk(m);
     if (f->rc < 0) { rc = f->rc; break; }
     cv.wait(lk, [&] { return q.size() < 2; });   // at most two pairs waiting for verification
@@ -1040,6 +1088,7 @@ extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img
     lk.unlock();
     cv.notify_all();
   }
+  inflight.clear();   // joins detections that were started for pairs an error kept us from reaching
   { std::lock_guard<std::mutex> lk(m); done = true; }
   cv.notify_all();
   back.join();
