@@ -37,13 +37,13 @@ AffineKeypoint kp_from(const double* v) {
 
 DetectorsParameters::DetectorsParameters() {
   // [HessianAffine] of config_iter_mods_cviu.ini
-  HessParam = mb2_hessaff_params{5.3333f, 3, 1.6f, 10.0f, 5, 16, 0.05f, 19, 1, 0, 2000, -1.f, -1.f, 41, 3.0f * std::sqrt(3.0f)};
+  HessParam = mb2_hessaff_params{5.3333f, 3, 1.6f, 10.0f, 5, 16, 0.05f, 19, 1, 0, 2000, -1.f, -1.f, 41, 3.0f * std::sqrt(3.0f), 0};
   // [MSER] of config_iter_mods_cviu.ini
   MSERParam = mb2_mser_params{0.05, 30, 8.0, 0, 0, -1, -1.f, -1.f};
 }
 DescriptorsParameters::DescriptorsParameters() {
-  SIFTParam = mb2_sift_params{5.1962, 41, 1, 0, 0};
-  RootSIFTParam = mb2_sift_params{5.1962, 41, 1, 1, 0};
+  SIFTParam = mb2_sift_params{5.1962, 41, 1, 0, 0, 0, 0};
+  RootSIFTParam = mb2_sift_params{5.1962, 41, 1, 1, 0, 0, 0};
   HalfRootSIFTParam = RootSIFTParam; HalfRootSIFTParam.doHalfSIFT = 1;   // io_mods.cpp:752-753
   HalfSIFTParam = HalfRootSIFTParam;                                     // io_mods.cpp:756 (HalfSIFT is HalfRootSIFT in the reference)
 }
@@ -725,7 +725,7 @@ extern "C" void mb2_mods_release(mb2_ctx* ctx) {
 extern "C" void mb2_pair_config_default(mb2_pair_config* c) {
   mods::DetectorsParameters dp; mods::DescriptorsParameters sp;
   c->det = dp.HessParam;
-  c->ori = mb2_orientation_params{1.0, 41, 1, 0.8};
+  c->ori = mb2_orientation_params{1.0, 41, 1, 0.8, 0, 0};
   c->desc = sp.RootSIFTParam;
   c->matchRatio = 0.8; c->contradDist = 30.0; c->duplicateDist = 2.0;              // iters_mods_cviu.ini:62, config_iter_mods_cviu.ini:151,157
   c->err_threshold = 3.0; c->confidence = 0.99; c->HLAFCoef = 12.0;                // config_iter_mods_cviu.ini:163-172
@@ -819,7 +819,7 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
   auto mser_post = [&](mb2_ctx* run, int which, int* rc_out) {   // orientation + description of one image's MSER regions
     const double Hid[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     mb2_sift_params sp = cfg->desc.rootSIFT ? ps.desc_par.RootSIFTParam : ps.desc_par.SIFTParam;
-    mb2_orientation_params op{ps.dom.mrSize, ps.dom.patchSize, ps.dom.maxAngles, (double)ps.dom.threshold};
+    mb2_orientation_params op{ps.dom.mrSize, ps.dom.patchSize, ps.dom.maxAngles, (double)ps.dom.threshold, 0, 0};
     const int k = mb2_describe_view_of_pair(run, ctx3, which, Hid, w1, h1, &op, &sp, 2 + which, 0, nullptr, nullptr, nullptr, 0);
     if (k < 0) { *rc_out = k; return; }
     (which ? out.rep2 : out.rep1)->AppendViewFrom(run, "MSER", ps.desc_name, k, 0);
