@@ -69,15 +69,28 @@ struct MserBufs {
 // In a level where a big component forms, every find ends on the same root: read through L2 (__ldcg) that one sector
 // becomes a hot spot that serialises the whole level.  The fast path therefore reads through L1 (possibly stale: a stale
 // pointer is still an ancestor, a stale "root" is caught by the CAS, which then falls back to L2-coherent reads).
+// One 8-byte word per element: low half = parent pointer, bits 32..39 = level of THIS element (written once by k_mser_prep).  A
+// neighbour's level and pointer, and a root's level for the hooking order, come with the load that is needed anyway -- the separate
+// lev[] reads (one more 32-byte sector per neighbour row and two per hooking attempt) are gone.  Hooking swaps the pointer half with a
+// 64-bit CAS whose expected value carries the (immutable) level; path compression stores the pointer half only.
+typedef unsigned long long zp_t;
+__device__ __forceinline__ uint32_t zp_ptr(zp_t z) { return (uint32_t)z; }
+__device__ __forceinline__ int zp_lev(zp_t z) { return (int)(z >> 32); }
+__device__ __forceinline__ zp_t zp_make(uint32_t ptr, int lev) { return ((zp_t)(uint32_t)lev << 32) | ptr; }
+__device__ __forceinline__ void zp_set_ptr(zp_t* z, uint32_t ptr) { __stcg(reinterpret_cast<uint32_t*>(z), ptr); }   // little endian: low word
 template <bool COHERENT>
-__device__ __forceinline__ uint32_t uf_load(const uint32_t* p) { return COHERENT ? __ldcg(p) : __ldca(p); }
+__device__ __forceinline__ zp_t uf_load(const zp_t* p) { return COHERENT ? __ldcg(p) : __ldca(p); }
+// root of x; *lev_out (optional) = its level
 template <bool COHERENT>
-__device__ __forceinline__ uint32_t uf_find(uint32_t* zpar, uint32_t x) {
+__device__ __forceinline__ uint32_t uf_find(zp_t* zpar, uint32_t x, int* lev_out = nullptr) {
   for (;;) {
-    const uint32_t p = uf_load<COHERENT>(zpar + x);
-    if (p == x) return x;
-    const uint32_t g = uf_load<COHERENT>(zpar + p);
-    if (g != p) __stcg(zpar + x, g);  // path halving; values only ever move towards the root
+    const zp_t zx = uf_load<COHERENT>(zpar + x);
+    const uint32_t p = zp_ptr(zx);
+    if (p == x) { if (lev_out) *lev_out = zp_lev(zx); return x; }
+    const zp_t zp = uf_load<COHERENT>(zpar + p);
+    const uint32_t g = zp_ptr(zp);
+    if (g == p) { if (lev_out) *lev_out = zp_lev(zp); return p; }
+    zp_set_ptr(zpar + x, g);  // path halving; values only ever move towards the root
     x = g;
   }
 }
@@ -86,31 +99,14 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* zpar, uint32_t x) {
 // root under the established one instead of dethroning it -- with "larger index wins" the root of a big component would
 // change once per joining pixel, one contended CAS after the other.  Which pixel of its level names a node is irrelevant
 // to every output (mser_logic.cuh).
-__device__ __forceinline__ bool key_less(const uint8_t* lev, uint32_t a, uint32_t b) {
-  const int la = lev[a], lb = lev[b];
-  return la < lb || (la == lb && a > b);
-}
-// joins the sets of a and b; returns the element that stopped being a root (NONE if already joined).
-// A failed CAS returns the true parent of the element we took for a root: the search continues upwards from there (fresh
-// information every time, so it terminates) instead of re-reading the contended pointers through L2.  Hooking under an
-// element that has meanwhile stopped being a root itself is fine: its ancestors have larger keys, the forest stays ordered.
-__device__ __forceinline__ uint32_t uf_unite(uint32_t* zpar, const uint8_t* lev, uint32_t a, uint32_t b) {
-  uint32_t ra = uf_find<false>(zpar, a), rb = uf_find<false>(zpar, b);
-  for (;;) {
-    if (ra == rb) return NONE;
-    if (key_less(lev, rb, ra)) { const uint32_t t = ra; ra = rb; rb = t; }
-    const uint32_t old = atomicCAS(zpar + ra, ra, rb);
-    if (old == ra) return ra;
-    ra = uf_find<false>(zpar, old);
-  }
-}
+__device__ __forceinline__ bool key_less(int la, uint32_t a, int lb, uint32_t b) { return la < lb || (la == lb && a > b); }
 
 // ---- 1. preparation ------------------------------------------------------------------------------------------------
 // float -> u8 as extrema.cpp:401-403 does ((unsigned char) of the float: truncation); second half = inverted image
 // (InvertImageAndHistogram, sortPixels.cpp:131-153)
 struct MserImages { const float* p[4]; int pitch[4]; int n; };   // same-size images processed together (a pair: n = 2)
 __global__ void k_mser_prep(MserImages im, int W, int H, uint8_t* __restrict__ lev,
-                            uint32_t* __restrict__ zpar, uint32_t* __restrict__ parent, uint32_t* __restrict__ area,
+                            zp_t* __restrict__ zpar, uint32_t* __restrict__ parent, uint32_t* __restrict__ area,
                             uint32_t* __restrict__ order_in, MserCounters* __restrict__ C) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
@@ -121,8 +117,8 @@ __global__ void k_mser_prep(MserImages im, int W, int H, uint8_t* __restrict__ l
     const int y = pi / W, x = pi - y * W;
     const int v = ((int)im.p[k][(size_t)y * im.pitch[k] + x]) & 0xff;
     const uint32_t a = 2 * k * N + pi, j = a + N;
-    lev[a] = (uint8_t)v; zpar[a] = a; parent[a] = a; area[a] = 1; order_in[a] = a;
-    lev[j] = (uint8_t)(255 - v); zpar[j] = j; parent[j] = j; area[j] = 1; order_in[j] = j;
+    lev[a] = (uint8_t)v; zpar[a] = zp_make(a, v); parent[a] = a; area[a] = 1; order_in[a] = a;
+    lev[j] = (uint8_t)(255 - v); zpar[j] = zp_make(j, 255 - v); parent[j] = j; area[j] = 1; order_in[j] = j;
     atomicAdd(&h[v], 1u); atomicAdd(&h[255 - v], 1u);
   }
   __syncthreads();
@@ -143,7 +139,7 @@ __global__ void k_mser_offsets(MserCounters* C) {
 // The phase is latency bound (a chain of dependent L2 reads per pixel), so the four neighbour roots are chased together
 // and de-duplicated before anything is hooked; lanes of a warp hold raster neighbours of one level and mostly want to hook
 // the SAME lower root: one lane per distinct root issues the CAS, the others continue from its outcome.
-__device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint8_t* __restrict__ lev, const uint32_t* __restrict__ order, uint32_t* zpar,
+__device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint32_t* __restrict__ order, zp_t* zpar,
                              uint32_t* __restrict__ nedge, uint32_t* __restrict__ hooked, MserCounters* C) {
   const uint32_t beg = C->lvl_off[L], end = C->lvl_off[L + 1];
   const int lane = threadIdx.x & 31;
@@ -152,64 +148,69 @@ __device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint
     const uint32_t k = base + lane;
     uint32_t hk[4]; int cnt = 0;
     const bool act = k < end;
-    uint32_t p = 0, r[4]; bool valid[4] = {false, false, false, false};
+    uint32_t p = 0, r[4]; int rl[4] = {0, 0, 0, 0}; bool valid[4] = {false, false, false, false};
     if (act) {
       p = order[k];
       const int yy = p / W, x = p - yy * W, y = yy % H;
       uint32_t q[4] = {p - W, p - 1, p + 1, p + W};
       valid[0] = y > 0; valid[1] = x > 0; valid[2] = x < W - 1; valid[3] = y < H - 1;
-      int lq[4];
+      zp_t zq[4];
 #pragma unroll
-      for (int d = 0; d < 4; d++) lq[d] = valid[d] ? (int)lev[q[d]] : 256;
+      for (int d = 0; d < 4; d++) zq[d] = valid[d] ? __ldca(zpar + q[d]) : zp_make(q[d], 256);   // level and pointer of a neighbour in one access
       uint32_t e = 0;
+      bool moving = false;
 #pragma unroll
-      for (int d = 0; d < 4; d++) { valid[d] = lq[d] < L || (lq[d] == L && q[d] < p); e += valid[d] ? 1u : 0u; r[d] = q[d]; }
+      for (int d = 0; d < 4; d++) {
+        const int lq = zp_lev(zq[d]);
+        valid[d] = lq < L || (lq == L && q[d] < p); e += valid[d] ? 1u : 0u;
+        r[d] = q[d]; rl[d] = lq;
+        if (valid[d] && zp_ptr(zq[d]) != q[d]) { r[d] = zp_ptr(zq[d]); moving = true; }
+      }
       nedge[p] = e;
       // the (up to) four root searches advance together: independent loads in flight instead of four serial chains
-      bool moving = true;
       while (moving) {
-        uint32_t nx[4];
+        zp_t z[4];
 #pragma unroll
-        for (int d = 0; d < 4; d++) nx[d] = valid[d] ? __ldca(zpar + r[d]) : r[d];
+        for (int d = 0; d < 4; d++) z[d] = valid[d] ? __ldca(zpar + r[d]) : zp_make(r[d], 0);
         moving = false;
 #pragma unroll
-        for (int d = 0; d < 4; d++) if (nx[d] != r[d]) { r[d] = nx[d]; moving = true; }
+        for (int d = 0; d < 4; d++) if (valid[d]) { rl[d] = zp_lev(z[d]); if (zp_ptr(z[d]) != r[d]) { r[d] = zp_ptr(z[d]); moving = true; } }
       }
 #pragma unroll
-#pragma unroll
-      for (int d = 0; d < 4; d++) if (valid[d] && r[d] != q[d]) __stcg(zpar + q[d], r[d]);   // compress the start of the path
+      for (int d = 0; d < 4; d++) if (valid[d] && r[d] != q[d]) zp_set_ptr(zpar + q[d], r[d]);   // compress the start of the path
       if (valid[1] && valid[0] && r[1] == r[0]) valid[1] = false;
       if (valid[2] && ((valid[0] && r[2] == r[0]) || (valid[1] && r[2] == r[1]))) valid[2] = false;
       if (valid[3] && ((valid[0] && r[3] == r[0]) || (valid[1] && r[3] == r[1]) || (valid[2] && r[3] == r[2]))) valid[3] = false;
     }
     // distinct roots packed to the front: most pixels have one, so the warp-synchronous rounds below are one or two, not four
-    uint32_t rr[4]; int nr = 0;
+    uint32_t rr[4]; int rrl[4]; int nr = 0;
 #pragma unroll
-    for (int d = 0; d < 4; d++) if (valid[d]) rr[nr++] = r[d];
+    for (int d = 0; d < 4; d++) if (valid[d]) { rr[nr] = r[d]; rrl[nr] = rl[d]; nr++; }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       bool pend = act && j < nr;
       if (!__ballot_sync(0xffffffffu, pend)) break;
-      uint32_t ra = 0, rb = 0;
-      if (pend) { ra = uf_find<false>(zpar, p); rb = rr[j]; }
+      uint32_t ra = 0, rb = 0; int la = 0, lb = 0;
+      if (pend) { ra = uf_find<false>(zpar, p, &la); rb = rr[j]; lb = rrl[j]; }
       for (;;) {
         if (pend) {
           if (ra == rb) pend = false;
-          else if (key_less(lev, rb, ra)) { const uint32_t t = ra; ra = rb; rb = t; }
+          else if (key_less(lb, rb, la, ra)) { const uint32_t t = ra; ra = rb; rb = t; const int tl = la; la = lb; lb = tl; }
         }
         const unsigned m = __ballot_sync(0xffffffffu, pend);
         if (!m) break;
         if (pend) {
           const unsigned grp = __match_any_sync(m, ra);
           const int leader = __ffs(grp) - 1;
-          uint32_t old = 0;
-          if (lane == leader) old = atomicCAS(zpar + ra, ra, rb);
+          const zp_t expect = zp_make(ra, la);   // the level of ra is the same in every lane that holds ra
+          zp_t old = 0;
+          if (lane == leader) old = atomicCAS(zpar + ra, expect, zp_make(rb, la));
           old = __shfl_sync(grp, old, leader);
           const uint32_t rb_lead = __shfl_sync(grp, rb, leader);
-          if (old == ra) {                       // ra now hangs under the leader's rb
+          if (old == expect) {                   // ra now hangs under the leader's rb
             if (lane == leader) { hk[cnt++] = ra; pend = false; }
-            else ra = uf_find<false>(zpar, rb_lead);
-          } else ra = uf_find<false>(zpar, old);  // somebody else hooked ra first: go on from its true parent
+            else ra = uf_find<false>(zpar, rb_lead, &la);
+          } else ra = uf_find<false>(zpar, zp_ptr(old), &la);  // somebody else hooked ra first: go on from its true parent
         }
       }
     }
@@ -226,7 +227,7 @@ __device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint
 }
 // Every element hooked during level L now learns its canonical parent (the representative of the level-L node) and hands
 // its totals over; lanes that share a representative combine first.
-__device__ __forceinline__ void mser_final_phase(int L, uint32_t* zpar, uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge,
+__device__ __forceinline__ void mser_final_phase(int L, zp_t* zpar, uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge,
                              const uint32_t* __restrict__ hooked, MserCounters* C, uint32_t beg, uint32_t end) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -247,7 +248,7 @@ __device__ __forceinline__ void mser_final_phase(int L, uint32_t* zpar, uint32_t
 }
 // The whole tree in ONE cooperative launch: levels in order, a grid barrier between the hooking phase and the hand-over
 // phase of every non-empty level (two launches per level would cost more than the levels themselves).
-__global__ void __launch_bounds__(256) k_mser_tree(int W, int H, const uint8_t* __restrict__ lev, const uint32_t* __restrict__ order, uint32_t* zpar,
+__global__ void __launch_bounds__(256) k_mser_tree(int W, int H, const uint8_t* __restrict__ lev, const uint32_t* __restrict__ order, zp_t* zpar,
                                                    uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge, uint32_t* __restrict__ hooked, MserCounters* C,
                                                    unsigned long long* dbg /* optional: 3 x 256 phase time stamps (ns) */) {
   cg::grid_group grid = cg::this_grid();
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) k_mser_tree(int W, int H, const uint8_t* 
   for (int L = 0; L < 256; L++) {
     if (C->lvl_off[L] == C->lvl_off[L + 1]) { if (blockIdx.x == 0 && threadIdx.x == 0) C->hook_off[L + 1] = hook_beg; continue; }
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L] = t; }
-    mser_union_phase(L, W, H, lev, order, zpar, nedge, hooked, C);
+    mser_union_phase(L, W, H, order, zpar, nedge, hooked, C);
     grid.sync();
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L + 1] = t; }
     const uint32_t hook_end = *(volatile uint32_t*)&C->hook_cnt;
@@ -539,12 +540,14 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
   MserCounters* dC = B.counters.as<MserCounters>();
   MserCounters* hc = B.h_counters.as<MserCounters>();
   MB2_CUDA_CHECK(ctx, B.lev.reserve(N)); MB2_CUDA_CHECK(ctx, B.keys8.reserve(N));
-  DevBuf* u32bufs[] = {&B.zpar, &B.parent, &B.area, &B.nedge, &B.order, &B.order_in, &B.hooked, &B.surv, &B.birth, &B.slot_of_node, &B.sa};
+  MB2_CUDA_CHECK(ctx, B.zpar.reserve((size_t)N * 8));   // pointer + level per element (zp_t)
+  DevBuf* u32bufs[] = {&B.parent, &B.area, &B.nedge, &B.order, &B.order_in, &B.hooked, &B.surv, &B.birth, &B.slot_of_node, &B.sa};
   for (DevBuf* b : u32bufs) MB2_CUDA_CHECK(ctx, b->reserve((size_t)N * 4));
   MB2_CUDA_CHECK(ctx, B.best.reserve((size_t)N * 8));
   MB2_CUDA_CHECK(ctx, B.flag.reserve(N));
   uint8_t* lev = B.lev.as<uint8_t>();
-  uint32_t *zpar = B.zpar.as<uint32_t>(), *parent = B.parent.as<uint32_t>(), *area = B.area.as<uint32_t>(), *nedge = B.nedge.as<uint32_t>();
+  zp_t* zpar = B.zpar.as<zp_t>();
+  uint32_t *parent = B.parent.as<uint32_t>(), *area = B.area.as<uint32_t>(), *nedge = B.nedge.as<uint32_t>();
   uint32_t *order = B.order.as<uint32_t>(), *order_in = B.order_in.as<uint32_t>(), *hooked = B.hooked.as<uint32_t>();
   uint32_t *surv = B.surv.as<uint32_t>(), *birth = B.birth.as<uint32_t>(), *slot_of_node = B.slot_of_node.as<uint32_t>(), *sa = B.sa.as<uint32_t>();
 
