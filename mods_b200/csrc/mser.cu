@@ -345,6 +345,99 @@ __global__ void k_mser_emulate(TreeDev td, uint32_t N, const uint32_t* __restric
   birth[v] = r.birth;
 }
 
+// Warp-per-node form of the replay.  emulate_node (mser_logic.cuh) spends most of its time in loads that do NOT depend on the replay
+// state: the level of the four neighbours of every own pixel and, for a neighbour below the node's level, the walk up to the child
+// of v that contains it (child_containing) plus that child's area.  The 32 lanes do this for 32 consecutive own pixels at once; the
+// order-dependent part -- the small union-find over {children, own pixels} -- is then replayed by lane 0 pixel by pixel, in raster
+// order, from the shuffled results.  Same decisions as emulate_node, statement by statement.
+__global__ void __launch_bounds__(256)
+k_mser_emulate_warp(TreeDev td, uint32_t N, const uint32_t* __restrict__ emu_nodes, uint32_t n_nodes, const u64* __restrict__ keys, uint32_t n_keys,
+                    EmuScratch s, uint32_t* __restrict__ surv, uint32_t* __restrict__ birth, MserCounters* C) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= n_nodes) return;
+  const Tree t = td.get();
+  const uint32_t v = emu_nodes[wid];
+  const uint32_t lo = lower_bound_u64(keys, n_keys, (u64)v << 32), hi = lower_bound_u64(keys, n_keys, ((u64)v + 1) << 32);
+  const u64* own = keys + lo;
+  const int n_own = (int)(hi - lo);
+  const int L = t.lev[v], W = t.W;
+  EmuResult res; res.survivor = NONE; res.birth = NONE; res.overflow = 0;
+  for (int k0 = 0; k0 < n_own; k0 += 32) {
+    // ---- order-independent part, one own pixel per lane
+    const int k = k0 + lane;
+    uint32_t p = 0, id[4] = {0, 0, 0, 0}, ar[4] = {0, 0, 0, 0};
+    unsigned codes = 0;   // 2 bits per direction (up, left, right, down): 0 none, 1 child of v (id = its rep, ar = its area), 2 same-level pixel
+    if (k < n_own) {
+      p = (uint32_t)own[k];
+      const int x = (int)(p % (uint32_t)W), y = (int)((p / (uint32_t)W) % (uint32_t)t.H);
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        uint32_t q;
+        if (d == 0) { if (y == 0) continue; q = p - W; }
+        else if (d == 1) { if (x == 0) continue; q = p - 1; }
+        else if (d == 2) { if (x == W - 1) continue; q = p + 1; }
+        else { if (y == t.H - 1) continue; q = p + W; }
+        const int lq = t.lev[q];
+        if (lq < L) { const uint32_t c = child_containing(t, v, q); id[d] = c; ar[d] = t.area[c]; codes |= 1u << (2 * d); }
+        else if (lq == L && q < p) { id[d] = q; codes |= 2u << (2 * d); }
+      }
+    }
+    // ---- order-dependent part: lane 0 replays the chunk in raster order
+    const int cnt = min(32, n_own - k0);
+    for (int i = 0; i < cnt; i++) {
+      const uint32_t pi = __shfl_sync(0xffffffffu, p, i);
+      const unsigned ci = __shfl_sync(0xffffffffu, codes, i);
+      uint32_t idi[4], ari[4];
+#pragma unroll
+      for (int d = 0; d < 4; d++) { idi[d] = __shfl_sync(0xffffffffu, id[d], i); ari[d] = __shfl_sync(0xffffffffu, ar[d], i); }
+      if (lane != 0) continue;
+      uint32_t lab[4]; int n = 0;
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        const unsigned code = (ci >> (2 * d)) & 3u;
+        if (code == 0) continue;
+        uint32_t e;
+        if (code == 1) {
+          const uint32_t c = idi[d];
+          e = s.N + c;
+          if (s.uf[e] == NONE) {  // first contact with this child
+            s.uf[e] = e; s.size[e] = ari[d];
+            if ((int)ari[d] >= t.track_size) { s.kind[e] = 1; s.presize[e] = ari[d]; s.ident[e] = c; s.birth[e] = NONE; }
+            else s.kind[e] = 0;
+          }
+        } else e = idi[d];
+        const uint32_t r = emu_find(s, e);
+        bool dup = false;
+        for (int j = 0; j < n; j++) dup |= (lab[j] == r);
+        if (!dup) lab[n++] = r;
+      }
+      if (n == 0) { s.uf[pi] = pi; s.size[pi] = 1; s.kind[pi] = 0; continue; }       // ConsRegion :174-178
+      if (n == 1) { emu_add_pixel(t, s, lab[0], pi, res); continue; }
+      // MergeRegions :267-361
+      uint32_t maxSize = 0, maxLabel = lab[0];
+      for (int j = 0; j < n; j++)
+        if (s.kind[lab[j]] == 1 && s.presize[lab[j]] > maxSize) { maxSize = s.presize[lab[j]]; maxLabel = lab[j]; }
+      for (int j = 0; j < n; j++) {
+        const uint32_t l = lab[j];
+        if (l == maxLabel) continue;
+        s.size[maxLabel] += s.size[l];
+        s.uf[l] = maxLabel;
+      }
+      if (s.kind[maxLabel] == 0 && s.size[maxLabel] >= 32768u) res.overflow = 1;
+      emu_add_pixel(t, s, maxLabel, pi, res);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    const uint32_t r = emu_find(s, v);
+    if (s.kind[r] == 1) { res.survivor = s.ident[r]; res.birth = s.birth[r]; }
+    if (res.overflow) atomicAdd(&C->overflow, 1u);
+    surv[v] = res.survivor;
+    birth[v] = res.birth;
+  }
+}
+
 // ---- 4. regions --------------------------------------------------------------------------------------------------------
 struct LongRegion { uint32_t v0; int maxI; int at_root; };
 __global__ void k_mser_regions_a(TreeDev td, const uint32_t* __restrict__ emu_nodes, uint32_t n_nodes, const uint32_t* __restrict__ surv,
@@ -622,7 +715,9 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
     MB2_CUDA_CHECK(ctx, B.ekind.reserve((size_t)N * 2));
     MB2_CUDA_CHECK(ctx, cudaMemsetAsync(B.uf.p, 0xff, (size_t)N * 8, st));
     EmuScratch es{N, B.uf.as<uint32_t>(), B.esz.as<uint32_t>(), B.epre.as<uint32_t>(), B.eid.as<uint32_t>(), B.ebirth.as<uint32_t>(), B.ekind.as<uint8_t>()};
-    MB2_LAUNCH(ctx, k_mser_emulate, (n_emu + 63) / 64, 64, 0, td, N, B.emu_nodes.as<uint32_t>(), n_emu, own_sorted, n_own, es, surv, birth, dC);
+    static const bool emu_warp = getenv("MB2_MSER_EMU_THREAD") == nullptr;   // A/B: the thread-per-node form
+    if (emu_warp) MB2_LAUNCH(ctx, k_mser_emulate_warp, (n_emu + 7) / 8, 256, 0, td, N, B.emu_nodes.as<uint32_t>(), n_emu, own_sorted, n_own, es, surv, birth, dC);
+    else MB2_LAUNCH(ctx, k_mser_emulate, (n_emu + 63) / 64, 64, 0, td, N, B.emu_nodes.as<uint32_t>(), n_emu, own_sorted, n_own, es, surv, birth, dC);
   }
   // 4. regions and their stability thresholds
   int n_sel = 0, n_slots = 0;
