@@ -243,6 +243,7 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
         gb = 30.0 * 2 * w * h
         rl = {"bound": "hbm", "kernel": name, "achieved": gb / 1e9 / avg_s, "peak": peaks["hbm"], "unit": "GB/s", "frac": gb / 1e9 / avg_s / peaks["hbm"],
               "traffic": 7.8068e9 if (w, h) == (4096, 3072) else None,   # dram__bytes_read+write of one launch, ncu --set full (profiles/r1_full_d.md)
+              "traffic_note": "captured before the level was packed into the union-find word (the kernel has since lost its separate lev[] reads and 11 % of its time); to be re-captured",
               "algorithmic_bytes": gb,
               "note": "component tree of both polarities: 256 level-synchronous phases, each a chain of dependent reads -- latency bound, not bandwidth bound "
                       "(DESIGN.md); peak = %s HBM copy" % peaks["src"]}
