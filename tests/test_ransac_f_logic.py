@@ -70,6 +70,20 @@ def test_f_logic_vs_reference_build_on_fresh_scenes(flogic, reference):
                     assert np.array_equal(a["inl"], b["inl"]) and same_F(a["F"], b["F"])
 
 
+@pytest.mark.parametrize("th,conf,sym,max_sam", [(4.0, 0.95, 1, 100000), (9.0, 0.999, 0, 100000), (9.0, 0.99, 1, 30), (2.25, 0.99, 0, 45), (16.0, 0.9, 1, 500)])
+def test_f_logic_parameter_sweep_vs_reference_build(flogic, reference, th, conf, sym, max_sam):
+    """Thresholds, confidence, the symmetric check off, and sample caps below ITER_SAM = 50 (only the final "do at least one LO now" block,
+    exp_ranF.c:1064-1172, optimises then) -- same outcome as the compiled reference."""
+    for cfg in (dict(n=400, n_out=200), dict(n=500, n_out=300, planar_frac=0.6), dict(n=80, n_out=30)):
+        u = general_scene(17, **cfg)
+        for seed in (3, 4):
+            for et in (0, 1):
+                a = reference.exp_ransacF(u, th=th, conf=conf, max_sam=max_sam, doSymCheck=sym, seed=seed, errorType=et, inlLimit=0)
+                b = flogic(u, th=th, conf=conf, max_sam=max_sam, doSymCheck=sym, seed=seed, errorType=et, inlLimit=0)
+                assert [a[k] for k in ("I", "samples", "lo", "Ih")] == [b[k] for k in ("I", "samples", "lo", "Ih")], (cfg, seed, et)
+                assert np.array_equal(a["inl"], b["inl"]) and same_F(a["F"], b["F"])
+
+
 def test_restated_numerics_vs_reference_pieces(flogic, reference):
     """ccmath's unsorted 3x3 svduv (bit-exact right-singular matrix), u2f / u2fw incl. the 8-point branch with its stride-9 weighting."""
     rng = np.random.default_rng(0)
