@@ -218,7 +218,7 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:   # the micro-benchmarks never take the headline down
             out["micro"] = {"error": repr(e)}
     out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1, with_mser=not args.no_mser) if (not args.no_cpu_baseline and world == 1) else None   # rank 0 at N=1 only
-    print(json.dumps(out))
+    emit_json_line(out)
 
 
 def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
@@ -405,10 +405,31 @@ def run_reference(args, rank, world):
                                       "tasks; one view per detector leaves nothing else to parallelise), scaled x4; exact FGINN (oracle port, all host threads over the queries) "
                                       "of 2000 queries vs all trains scaled to the full N1 x N2" % (cw, ch, "oracle/_ref" if use_ref else "oracle port", "HessianAffine, then MSER" if len(dets) > 1 else "HessianAffine")},
            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit_json_line(out)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries write to fd 1 during the run (NCCL prints its version banner there at communicator creation) goes to stderr,
+    so that the ONE JSON line is the only thing on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(out):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(out), flush=True)
 
 
 def main():
+    quiet_stdout()
     if os.environ.get("MB2_DUMP_AFTER"):   # diagnostics: Python stacks of all threads if the run is still alive after N seconds
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["MB2_DUMP_AFTER"]), exit=True)
