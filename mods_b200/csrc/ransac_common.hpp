@@ -196,6 +196,9 @@ inline void denormH(double* F, const double* A1, const double* A2) {
 inline void u2h(const double* u, const int* inl, int len, double* H) {
   if (len < 4) return;
   if (len == 4) {
+    // The reference fills a 9 x 8 column-major matrix (lin_hg, stride 2*len = 8) and then transposes it in place AS 9 x 9
+    // (trnm(Z2, 9), Htools.c:108-109): rows get mixed and column 8 of rows 0..7 is read from uninitialised stack memory -- undefined.
+    // Reached only when an inner sample has exactly 4 points (8 or 9 inliers).  Pinned here: the intended exact 4-point solution.
     double Z2[81], V[81];
     int nb[18];
     for (int i = 0; i < 4; i++) lin_rows(u, inl[i], Z2 + (2 * i) * 9, Z2 + (2 * i + 1) * 9);
