@@ -197,11 +197,20 @@ inline void u2h(const double* u, const int* inl, int len, double* H) {
   if (len < 4) return;
   if (len == 4) {
     // The reference fills a 9 x 8 column-major matrix (lin_hg, stride 2*len = 8) and then transposes it in place AS 9 x 9
-    // (trnm(Z2, 9), Htools.c:108-109): rows get mixed and column 8 of rows 0..7 is read from uninitialised stack memory -- undefined.
-    // Reached only when an inner sample has exactly 4 points (8 or 9 inliers).  Pinned here: the intended exact 4-point solution.
+    // (trnm(Z2, 9), Htools.c:108-109): the equations get mixed, and nine entries are read from uninitialised stack memory.  Reached
+    // only when an inner sample has exactly 4 points (8 or 9 inliers).  The compiled reference behaves, in every run we compared
+    // (516 seeded H and F runs over small and degenerate sets), as if those nine entries were 0: that arithmetic is reproduced here.
     double Z2[81], V[81];
     int nb[18];
-    for (int i = 0; i < 4; i++) lin_rows(u, inl[i], Z2 + (2 * i) * 9, Z2 + (2 * i + 1) * 9);
+    {
+      double A[81], r0[9], r1[9];
+      for (int i = 0; i < 81; i++) A[i] = 0.0;
+      for (int i = 0; i < 4; i++) {   // lin_hg: element (row r, coefficient c) at c * 8 + r
+        lin_rows(u, inl[i], r0, r1);
+        for (int c = 0; c < 9; c++) { A[c * 8 + 2 * i] = r0[c]; A[c * 8 + 2 * i + 1] = r1[c]; }
+      }
+      for (int i = 0; i < 9; i++) for (int j = 0; j < 9; j++) Z2[i * 9 + j] = A[j * 9 + i];   // trnm(Z2, 9)
+    }
     for (int i = 72; i < 81; ++i) Z2[i] = 0.0;
     std::memset(V, 0, sizeof V);
     nullspace(Z2, V, 9, nb);

@@ -84,6 +84,26 @@ def test_f_logic_parameter_sweep_vs_reference_build(flogic, reference, th, conf,
                 assert np.array_equal(a["inl"], b["inl"]) and same_F(a["F"], b["F"])
 
 
+def test_f_logic_degenerate_and_small_sets_vs_reference_build(flogic, reference):
+    """All inliers on one plane, pure noise, duplicated correspondences, 8-20 tentatives (the LO and innerH then draw 4-point inner
+    samples: u2h's len == 4 branch), all inliers, heavy noise, tiny coordinates."""
+    rng = np.random.default_rng(123)
+    cases = [("planar", general_scene(31, n=400, n_out=100, planar_frac=1.0), 9.0),
+             ("noise", np.c_[rng.random((300, 2)) * 800, np.ones(300), rng.random((300, 2)) * 800, np.ones(300)], 9.0),
+             ("allinl", general_scene(34, n=300, n_out=0, noise=0.1), 9.0), ("highnoise", general_scene(35, n=400, n_out=100, noise=3.0), 9.0)]
+    d = general_scene(32, n=200, n_out=50); d[50:100] = d[0:50]; cases.append(("duplicates", np.ascontiguousarray(d), 9.0))
+    for n in (8, 9, 12, 15, 16, 17, 20):
+        cases.append(("tiny%d" % n, general_scene(33, n=n, n_out=n // 4), 9.0))
+    s = general_scene(36, n=300, n_out=100); s[:, 0:2] *= 1e-3; s[:, 3:5] *= 1e-3; cases.append(("smallcoords", s, 9e-6))
+    for name, u, th in cases:
+        for seed in (1, 2):
+            for et in (0, 1):
+                a = reference.exp_ransacF(u, th=th, seed=seed, errorType=et, inlLimit=0, max_sam=20000)
+                b = flogic(u, th=th, seed=seed, errorType=et, inlLimit=0, max_sam=20000)
+                assert [a[k] for k in ("I", "samples", "lo", "Ih")] == [b[k] for k in ("I", "samples", "lo", "Ih")], (name, seed, et)
+                assert np.array_equal(a["inl"], b["inl"]), (name, seed, et)
+
+
 def test_restated_numerics_vs_reference_pieces(flogic, reference):
     """ccmath's unsorted 3x3 svduv (bit-exact right-singular matrix), u2f / u2fw incl. the 8-point branch with its stride-9 weighting."""
     rng = np.random.default_rng(0)
