@@ -64,3 +64,17 @@ def test_h_logic_vs_reference_build(hlogic, reference, n, frac, noise):
                 assert np.array_equal(a["inl"], b["inl"])
                 ha, hb = a["H"] / max(np.linalg.norm(a["H"]), 1e-300), b["H"] / max(np.linalg.norm(b["H"]), 1e-300)
                 assert min(np.abs(ha - hb).max(), np.abs(ha + hb).max()) < 1e-6
+
+
+@pytest.mark.parametrize("th,conf,max_sam", [(4.0, 0.95, 100000), (9.0, 0.999, 100000), (16.0, 0.9, 500), (9.0, 0.5, 100000)])
+def test_h_logic_parameter_sweep_vs_reference_build(hlogic, reference, th, conf, max_sam):
+    """Thresholds, confidence and sample caps.  (Caps below ITER_SAM = 50 on sets where no model is accepted are left out: the
+    reference's final LO then reads residual buffers it never wrote, exp_ranH.c:1124-1145, and its answer depends on the heap.)"""
+    for n, frac, noise in [(500, 0.6, 1.0), (300, 0.25, 1.0), (60, 0.4, 1.0), (15, 0.7, 0.5), (2000, 0.5, 0.3)]:
+        u = scene(n + 3, n, frac, noise)
+        for seed in (1, 2):
+            for et in (0, 1, 2):
+                a = reference.exp_ransacH(u, seed=seed, errorType=et, th=th, conf=conf, max_sam=max_sam)
+                b = hlogic(u, seed=seed, errorType=et, th=th, conf=conf, max_sam=max_sam)
+                assert (a["I"], a["samples"], a["lo"], a["rejected"]) == (b["I"], b["samples"], b["lo"], b["rejected"]), (n, seed, et)
+                assert np.array_equal(a["inl"], b["inl"])
