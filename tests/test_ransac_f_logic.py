@@ -100,8 +100,14 @@ def test_f_logic_degenerate_and_small_sets_vs_reference_build(flogic, reference)
             for et in (0, 1):
                 a = reference.exp_ransacF(u, th=th, seed=seed, errorType=et, inlLimit=0, max_sam=20000)
                 b = flogic(u, th=th, seed=seed, errorType=et, inlLimit=0, max_sam=20000)
-                assert [a[k] for k in ("I", "samples", "lo", "Ih")] == [b[k] for k in ("I", "samples", "lo", "Ih")], (name, seed, et)
-                assert np.array_equal(a["inl"], b["inl"]), (name, seed, et)
+                same = [a[k] for k in ("I", "samples", "lo", "Ih")] == [b[k] for k in ("I", "samples", "lo", "Ih")] and np.array_equal(a["inl"], b["inl"])
+                if not same and name.startswith("tiny"):
+                    # 4-point inner samples make the reference read uninitialised stack entries (Htools.c:108-109): a case on which it does
+                    # not agree with itself says nothing about us
+                    a2 = reference.exp_ransacF(u, th=th, seed=seed, errorType=et, inlLimit=0, max_sam=20000)
+                    if [a[k] for k in ("I", "samples", "lo", "Ih")] != [a2[k] for k in ("I", "samples", "lo", "Ih")] or not np.array_equal(a["inl"], a2["inl"]):
+                        continue
+                assert same, (name, seed, et)
 
 
 def test_restated_numerics_vs_reference_pieces(flogic, reference):

@@ -60,8 +60,14 @@ def test_h_logic_vs_reference_build(hlogic, reference, n, frac, noise):
                 ms = 1000 if n <= 20 else 100000    # LORANSACFiltering's rule for small sets (matching.cpp:813)
                 a = reference.exp_ransacH(u, seed=seed, errorType=et, doSymCheck=sym, max_sam=ms)
                 b = hlogic(u, seed=seed, errorType=et, doSymCheck=sym, max_sam=ms)
-                assert (a["I"], a["samples"], a["lo"], a["rejected"]) == (b["I"], b["samples"], b["lo"], b["rejected"]), (seed, et, sym)
-                assert np.array_equal(a["inl"], b["inl"])
+                same = (a["I"], a["samples"], a["lo"], a["rejected"]) == (b["I"], b["samples"], b["lo"], b["rejected"]) and np.array_equal(a["inl"], b["inl"])
+                if not same and n <= 40:
+                    # 4-point inner samples make the reference read uninitialised stack entries (Htools.c:108-109): if it does not even
+                    # agree with itself on a second run, the case says nothing about us
+                    a2 = reference.exp_ransacH(u, seed=seed, errorType=et, doSymCheck=sym, max_sam=ms)
+                    if (a["I"], a["samples"], a["lo"]) != (a2["I"], a2["samples"], a2["lo"]) or not np.array_equal(a["inl"], a2["inl"]):
+                        continue
+                assert same, (seed, et, sym, a["I"], b["I"])
                 ha, hb = a["H"] / max(np.linalg.norm(a["H"]), 1e-300), b["H"] / max(np.linalg.norm(b["H"]), 1e-300)
                 assert min(np.abs(ha - hb).max(), np.abs(ha + hb).max()) < 1e-6
 
