@@ -314,7 +314,7 @@ def micro_benchmarks(ctx):
     ctx.ransac_f(uf, seed=9, inlLimit=0)
     t0 = time.perf_counter(); r = ctx.ransac_f(uf, seed=9, inlLimit=0); dt = time.perf_counter() - t0
     out["ransac_f"] = {"tentatives": 30000, "ms": 1e3 * dt, "inliers": int(r["I"]), "samples": r["samples"], "lo": r["lo"], "launches": r["launches"]}
-    try:
+    try:   # CPU-baseline leg of the micro-benchmark: the compiled reference timed beside the driver on the same tentatives (checker / baseline only)
         from oracle import pyoracle
         if pyoracle.have_reference():
             R = pyoracle.Reference()
