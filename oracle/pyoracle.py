@@ -229,12 +229,12 @@ class Reference(Lib):
               C.c_long(seed), _p(H), _p(inl), _p(out4))
         return dict(H=H, inl=inl, I=int(out4[0]), samples=int(out4[1]), lo=int(out4[2]), rejected=int(out4[3]), J=J)
 
-    def exp_ransacF(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1, inlLimit=None):
+    def exp_ransacF(self, u, th=9.0, conf=0.99, max_sam=100000, errorType=0, doSymCheck=1, seed=1, inlLimit=None, do_lo=1):
         """Reference only (oracle/_ref): exp_ransacFcustom with a fixed seed.  inlLimit None = len (no limit); LORANSACFiltering passes 0."""
         u = _f64(u); n = len(u)
         F = np.zeros(9); inl = np.zeros(n, np.uint8); out4 = np.zeros(4, np.int32)
-        I = self.fn("exp_ransacF2")(_p(u), C.c_int(n), C.c_double(th), C.c_double(conf), C.c_int(max_sam), C.c_int(errorType), C.c_int(doSymCheck),
-                                    C.c_long(seed), C.c_uint(n if inlLimit is None else inlLimit), _p(F), _p(inl), _p(out4))
+        I = self.fn("exp_ransacF3")(_p(u), C.c_int(n), C.c_double(th), C.c_double(conf), C.c_int(max_sam), C.c_int(errorType), C.c_int(doSymCheck),
+                                    C.c_long(seed), C.c_uint(n if inlLimit is None else inlLimit), C.c_int(do_lo), _p(F), _p(inl), _p(out4))
         return dict(F=F, inl=inl, I=int(I), samples=int(out4[1]), lo=int(out4[2]), Ih=int(out4[3]))
 
     def u2h(self, u, idx):

@@ -396,22 +396,28 @@ double ref_exp_ransacH(const double* u, int len, double th, double conf, int max
 // form (inlLimit = len) the first golden vectors were made with.
 int ref_exp_ransacF2(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, unsigned inlLimit,
                      double* F, unsigned char* inl, int* out4);
+int ref_exp_ransacF3(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, unsigned inlLimit,
+                     int do_lo, double* F, unsigned char* inl, int* out4);   // do_lo = pars.localOptimization (matching.cpp:808)
 int ref_exp_ransacF(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, double* F,
                     unsigned char* inl, int* out4) {
   return ref_exp_ransacF2(u, len, th, conf, max_sam, errorType, doSymCheck, seed, (unsigned)len, F, inl, out4);
 }
-int ref_exp_ransacF2(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, unsigned inlLimit,
-                     double* F, unsigned char* inl, int* out4) {
+int ref_exp_ransacF3(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, unsigned inlLimit,
+                     int do_lo, double* F, unsigned char* inl, int* out4) {
   mb2_ref_seed = seed;
   std::vector<double> uc(u, u + (size_t)len * 6);
   std::vector<int> data_out((size_t)len * 18 + 8, 0);
   double* resids = 0; double Hbest[9] = {0}; int Ih = 0;
   FDsPtr a = errorType == 0 ? &FDs : &FDsSym;
   exFDsPtr b = errorType == 0 ? &exFDs : &exFDsSym;
-  const int I = exp_ransacFcustom(uc.data(), len, th, conf, max_sam, F, inl, data_out.data(), 1, inlLimit, &resids, Hbest, &Ih, b, a, doSymCheck);
+  const int I = exp_ransacFcustom(uc.data(), len, th, conf, max_sam, F, inl, data_out.data(), do_lo, inlLimit, &resids, Hbest, &Ih, b, a, doSymCheck);
   free(resids);
   out4[0] = I; out4[1] = data_out[0]; out4[2] = data_out[1]; out4[3] = Ih;
   return I;
+}
+int ref_exp_ransacF2(const double* u, int len, double th, double conf, int max_sam, int errorType, int doSymCheck, long seed, unsigned inlLimit,
+                     double* F, unsigned char* inl, int* out4) {
+  return ref_exp_ransacF3(u, len, th, conf, max_sam, errorType, doSymCheck, seed, inlLimit, 1, F, inl, out4);
 }
 // pieces of the F path on their own (unit comparisons of the restated numerics)
 void ref_svduv3_V(const double* A, double* V) { double a[9], d[3], U[9]; std::memcpy(a, A, sizeof a); svduv(d, a, U, 3, V, 3); }

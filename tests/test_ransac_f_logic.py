@@ -110,6 +110,18 @@ def test_f_logic_degenerate_and_small_sets_vs_reference_build(flogic, reference)
                 assert same, (name, seed, et)
 
 
+def test_f_logic_without_local_optimisation_vs_reference_build(flogic, reference):
+    """RANSACPars.localOptimization = 0 (do_lo, matching.cpp:808): the LO blocks never run; the DEGENSAC branch still does."""
+    for cfg in (dict(n=400, n_out=200), dict(n=500, n_out=300, planar_frac=0.6), dict(n=80, n_out=30)):
+        u = general_scene(19, **cfg)
+        for seed in (1, 2):
+            for et in (0, 1):
+                a = reference.exp_ransacF(u, seed=seed, errorType=et, inlLimit=0, do_lo=0)
+                b = flogic(u, seed=seed, errorType=et, inlLimit=0, do_lo=0)
+                assert a["lo"] == 0 and [a[k] for k in ("I", "samples", "lo", "Ih")] == [b[k] for k in ("I", "samples", "lo", "Ih")], (cfg, seed, et)
+                assert np.array_equal(a["inl"], b["inl"]) and same_F(a["F"], b["F"])
+
+
 def test_restated_numerics_vs_reference_pieces(flogic, reference):
     """ccmath's unsorted 3x3 svduv (bit-exact right-singular matrix), u2f / u2fw incl. the 8-point branch with its stride-9 weighting."""
     rng = np.random.default_rng(0)
