@@ -407,16 +407,18 @@ int CorrespondenceBank::MatchImgReps(ImageRepresentation& imgrep1, ImageRepresen
 // ---- DuplicateFiltering (matching.cpp:2983-3047) -------------------------------------------------
 // The reference's O(T^2) double loop keeps i and drops every later j whose endpoints are both within r
 // of i's.  The kept set is decided greedily in list order, so a uniform grid over the first image's
-// coordinates (cell = r) gives the identical result in O(T).  (std::sort in the reference is unstable;
-// ties in the sort key keep their input order here.)
+// coordinates (cell = r) gives the identical result in O(T).
 // Core on plain arrays: xy = n x (x1 y1 x2 y2), key = sort key (ignored when !sorted).  Returns the kept
 // original indices in processing order.
 std::vector<int> duplicate_filter_core(const double* xy_in, const double* key, int T, double r, bool sorted) {
   std::vector<int> order(T);
-  if (sorted) {  // std::sort(TCList, CompareCorrespondenceByRatio) made stable: ties keep their input order
+  if (sorted) {
+    // std::sort(TCList, CompareCorrespondenceByRatio), matching.cpp:2999: unstable, so the order of EQUAL keys is whatever the library's
+    // introsort leaves.  Its moves depend only on the comparison results, not on the element type: the same routine with the same
+    // comparator on (key, row) pairs yields the reference's permutation, ties included (checked against the compiled reference).
     std::vector<std::pair<double, int> > ki(T);
     for (int i = 0; i < T; i++) ki[i] = std::make_pair(key[i], i);
-    std::sort(ki.begin(), ki.end());
+    std::sort(ki.begin(), ki.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return std::fabs(a.first) < std::fabs(b.first); });
     for (int i = 0; i < T; i++) order[i] = ki[i].second;
   } else
     for (int i = 0; i < T; i++) order[i] = i;

@@ -237,6 +237,53 @@ class Reference(Lib):
                                     C.c_long(seed), C.c_uint(n if inlLimit is None else inlLimit), C.c_int(do_lo), _p(F), _p(inl), _p(out4))
         return dict(F=F, inl=inl, I=int(I), samples=int(out4[1]), lo=int(out4[2]), Ih=int(out4[3]))
 
+    # ---- matching/matching.cpp compiled in place (FLANN answered by the shim's exact linear k-NN)
+    def match_fginn(self, q, t, t_kps, ratio=0.8, contradDist=30.0, nn=50):
+        """MatchFlannFGINN (matching.cpp:357).  t_kps: nt x 9 regions or nt x 2 centres.  Rows: q idx0 idxJ idx1 d0 dJ d1."""
+        q = _f32(q); t = _f32(t); t_kps = _f64(t_kps)
+        if t_kps.shape[1] == 2:
+            k = np.zeros((len(t), KP)); k[:, :2] = t_kps; t_kps = k
+        out = np.zeros((max(1, len(q)), 7))
+        n = self.fn("match_fginn")(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), _p(t_kps), C.c_double(ratio), C.c_double(contradDist),
+                                   C.c_int(nn), _p(out), C.c_int(len(out)))
+        return out[:n].copy()
+
+    def duplicate_filter(self, frames14, ratio, r=2.0, mode=1):
+        """DuplicateFiltering (matching.cpp:2983), MODE_FGINN = 1: surviving row numbers in output order."""
+        frames14 = _f64(frames14); ratio = _f64(ratio); n = len(frames14)
+        kept = np.zeros(max(1, n), np.int32)
+        k = self.fn("duplicate_filter")(_p(frames14), _p(ratio), C.c_int(n), C.c_double(r), C.c_int(mode), _p(kept))
+        return kept[:k].copy()
+
+    def loransac_filtering(self, frames14, useF=0, err_threshold=3.0, confidence=0.99, max_samples=100000, localOptimization=1, LAFCoef=3.0,
+                           HLAFCoef=10.0, errorType=0, doSymmCheck=1, seed=1):
+        """LORANSACFiltering (matching.cpp:806) incl. NaiveHCheck / H_LAF_check / F_LAF_check.  errorType: 0 Sampson, 1 SymmMax, 2 SymmSum."""
+        frames14 = _f64(frames14); n = len(frames14)
+        ver = np.zeros(max(1, n), np.int32); inl = np.zeros(max(1, n), np.uint8); H = np.zeros(9)
+        k = self.fn("loransac_filtering")(_p(frames14), C.c_int(n), C.c_int(useF), C.c_double(err_threshold), C.c_double(confidence), C.c_int(max_samples),
+                                          C.c_int(localOptimization), C.c_double(LAFCoef), C.c_double(HLAFCoef), C.c_int(errorType), C.c_int(doSymmCheck),
+                                          C.c_long(seed), _p(ver), _p(inl), _p(H))
+        return dict(verified=ver[:k].copy(), inl=inl[:n].copy(), H=H)
+
+    def pair_back(self, groups, contradDist=30.0, nn=50, duplicateDist=2.0, useF=0, err_threshold=3.0, confidence=0.99, max_samples=100000,
+                  localOptimization=1, LAFCoef=3.0, HLAFCoef=10.0, errorType=0, doSymmCheck=1, seed=1):
+        """mods.cpp:290-351 on (q_kps, q_desc, t_kps, t_desc, ratio) groups: match every group, append, duplicate-filter, LO-RANSAC + checks.
+        Returns dict(tent = rows (group q idx0 idxJ idx1 d0 dJ d1), kept, verified (rows of tent), H, counts)."""
+        G = len(groups)
+        keep = []
+        PD = C.c_void_p * G; I = C.c_int * G
+        qk, qd, tk, td = PD(), PD(), PD(), PD(); nq, nt = I(), I(); ratio = (C.c_double * G)()
+        for g, (a, b, c, d, r) in enumerate(groups):
+            a = _f64(a); b = _f32(b); c = _f64(c); d = _f32(d); keep += [a, b, c, d]
+            qk[g] = a.ctypes.data; qd[g] = b.ctypes.data; tk[g] = c.ctypes.data; td[g] = d.ctypes.data; nq[g] = len(a); nt[g] = len(c); ratio[g] = r
+        cap = max(1, sum(len(g[0]) for g in groups))
+        tent = np.zeros((cap, 8)); kept = np.zeros(cap, np.int32); ver = np.zeros(cap, np.int32); H = np.zeros(9); counts = np.zeros(4, np.int32)
+        self.fn("pair_back")(C.c_int(G), nq, qk, qd, nt, tk, td, ratio, C.c_double(contradDist), C.c_int(nn), C.c_double(duplicateDist), C.c_int(useF),
+                             C.c_double(err_threshold), C.c_double(confidence), C.c_int(max_samples), C.c_int(localOptimization), C.c_double(LAFCoef),
+                             C.c_double(HLAFCoef), C.c_int(errorType), C.c_int(doSymmCheck), C.c_long(seed), _p(tent), C.c_int(cap), _p(kept), _p(ver),
+                             _p(H), _p(counts))
+        return dict(tent=tent[:counts[0]].copy(), kept=kept[:counts[1]].copy(), verified=ver[:counts[3]].copy(), H=H, counts=counts.tolist())
+
     def u2h(self, u, idx):
         u = _f64(u); idx = np.ascontiguousarray(idx, np.int32); H = np.zeros(9)
         self.fn("u2h", None)(_p(u), _p(idx), C.c_int(len(idx)), _p(H))

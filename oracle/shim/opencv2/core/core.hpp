@@ -50,6 +50,7 @@ struct Size {
   Size(int w, int h) : width(w), height(h) {}
 };
 struct Point { int x, y; Point() : x(0), y(0) {} Point(int a, int b) : x(a), y(b) {} };
+struct Rect { int x, y, width, height; Rect() : x(0), y(0), width(0), height(0) {} Rect(int a, int b, int c, int d) : x(a), y(b), width(c), height(d) {} };
 struct Point2f { float x, y; Point2f() : x(0), y(0) {} Point2f(float a, float b) : x(a), y(b) {} };
 struct Scalar {
   double val[4];
@@ -77,6 +78,9 @@ class Mat {
   Mat(int r, int c, int t, void* d, size_t st = 0) : rows(r), cols(c), data((unsigned char*)d), flags_type(t) {
     step = st ? st : (size_t)c * elemSize();
   }
+  template <class T> explicit Mat(const std::vector<T>&) : Mat() { shim_unsupported("Mat(vector) (drawing code)"); }
+  Mat operator()(const Rect&) const { shim_unsupported("Mat(Rect) (drawing code)"); }
+  double dot(const Mat&) const { shim_unsupported("Mat::dot"); }
   void create(int r, int c, int t) {
     rows = r; cols = c; flags_type = t;
     step = (size_t)c * elemSize();
@@ -225,6 +229,21 @@ inline void warpPerspective(const Mat&, Mat&, const Mat&, Size, int = INTER_LINE
 }
 inline void split(const Mat&, std::vector<Mat>&) { shim_unsupported("split"); }
 inline void gemm(const Mat&, const Mat&, double, const Mat&, double, Mat&, int = 0) { shim_unsupported("gemm"); }
+// drawing / colour API referenced by matching.cpp's Draw* functions (outside the hot path, never called by the oracle)
+#define CV_AA 16
+#define CV_GRAY2RGB 8
+#define CV_GRAY2BGR 8
+inline Scalar operator*(const Scalar& s, double k) { return Scalar(s.val[0] * k, s.val[1] * k, s.val[2] * k, s.val[3] * k); }
+inline Scalar operator+(const Scalar& a, const Scalar& b) { return Scalar(a.val[0] + b.val[0], a.val[1] + b.val[1], a.val[2] + b.val[2], a.val[3] + b.val[3]); }
+template <class... A> inline void circle(A&&...) { shim_unsupported("circle"); }
+template <class... A> inline void line(A&&...) { shim_unsupported("line"); }
+template <class... A> inline void ellipse(A&&...) { shim_unsupported("ellipse"); }
+template <class... A> inline void polylines(A&&...) { shim_unsupported("polylines"); }
+template <class... A> inline void cvtColor(A&&...) { shim_unsupported("cvtColor"); }
+template <class... A> inline bool clipLine(A&&...) { shim_unsupported("clipLine"); }
+template <class... A> inline void addWeighted(A&&...) { shim_unsupported("addWeighted"); }
+template <class... A> inline void rectangle(A&&...) { shim_unsupported("rectangle"); }
+template <class... A> inline void putText(A&&...) { shim_unsupported("putText"); }
 inline bool imwrite(const std::string&, const Mat&) { shim_unsupported("imwrite"); }
 inline Mat imread(const std::string&, int = 1) { shim_unsupported("imread"); }
 

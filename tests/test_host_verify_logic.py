@@ -139,3 +139,45 @@ def test_too_few_tentatives_and_failed_checks(hv):
     assert k == 0 and res.ransac_inliers == 0
     k, res, _, _ = hv(f, keys, cfg, np.zeros(9), np.ones(40, np.uint8))                                # singular model: cleared (matching.cpp:925-930)
     assert k == 0
+
+
+# ---- the same stage against the reference's own matching.cpp, compiled in place (oracle/_ref) ---------------------------------------
+@pytest.mark.parametrize("seed,errorType,ties", [(3, 0, False), (4, 0, True), (5, 1, True), (6, 2, False)])
+def test_verify_stage_vs_compiled_reference(hv, reference, seed, errorType, ties):
+    """DuplicateFiltering + LORANSACFiltering (inv(H^T), NaiveHCheck, H_LAF_check) of the host mirror == matching.cpp:2983-3047, 806-980 run
+    by the compiled reference on the same tentatives: the RANSAC model / mask planted into the host mirror are the ones the reference's own
+    exp_ransacHcustom returns for the seed, so every list (unique rows incl. the unstable std::sort's tie order, verified rows) must agree."""
+    f, keys, Hgt = make_frames(n=600, n_dup=150, seed=seed)
+    if ties:
+        keys = np.round(keys * 12) / 12          # many equal ratios: the order of equal keys is std::sort's
+    cfg = mb.PairConfig.default(); cfg.errorType = errorType; cfg.seed = seed
+    kept = reference.duplicate_filter(f, keys, r=cfg.duplicateDist)
+    fk = f[kept]
+    u = np.ones((len(fk), 6)); u[:, 0:2] = fk[:, 0:2]; u[:, 3:5] = fk[:, 7:9]
+    rr = reference.exp_ransacH(u, th=cfg.err_threshold ** 2, conf=cfg.confidence, max_sam=cfg.max_samples, errorType=errorType,
+                               doSymCheck=cfg.doSymmCheck, seed=seed)
+    exp = reference.loransac_filtering(fk, err_threshold=cfg.err_threshold, confidence=cfg.confidence, max_samples=cfg.max_samples,
+                                       HLAFCoef=cfg.HLAFCoef, LAFCoef=cfg.LAFCoef, errorType=errorType, doSymmCheck=cfg.doSymmCheck, seed=seed)
+    assert np.array_equal(exp["inl"], rr["inl"])                      # LORANSACFiltering ran the same RANSAC
+    k, res, ver, _ = hv(f, keys, cfg, rr["H"], rr["inl"])
+    assert res.unique_tentatives == len(kept) and res.ransac_inliers == int(rr["inl"].sum())
+    rows = fk[exp["verified"]]
+    assert 50 < len(rows) <= int(rr["inl"].sum()) and k == len(rows)
+    assert np.array_equal(ver, np.c_[rows[:, 0:2], rows[:, 7:9]])
+    assert np.allclose(np.array(res.H), exp["H"], rtol=1e-12, atol=0)
+
+
+def test_duplicate_filter_tie_order_vs_compiled_reference(hv, reference):
+    """All keys equal: the surviving rows are decided by std::sort's permutation of equal elements alone."""
+    f, keys, Hgt = make_frames(n=500, n_dup=200, seed=9)
+    keys = np.full(len(f), 0.5)
+    cfg = mb.PairConfig.default()
+    kept = reference.duplicate_filter(f, keys, r=cfg.duplicateDist)
+    assert not np.array_equal(kept, np.sort(kept))                    # the reference's order is NOT the stable one
+    k, res, ver, _ = hv(f, keys, cfg, np.linalg.inv(Hgt).T.ravel(), np.ones(len(kept), np.uint8))
+    assert res.unique_tentatives == len(kept)
+    exp = reference.loransac_filtering(f[kept], err_threshold=cfg.err_threshold, HLAFCoef=cfg.HLAFCoef, seed=1)
+    # planted all-inlier mask: compare only the order-sensitive part -- the verified rows are a subsequence of f[kept] in the reference's order
+    pos = {tuple(r): i for i, r in enumerate(np.c_[f[kept][:, 0:2], f[kept][:, 7:9]].tolist())}
+    idx = [pos[tuple(r)] for r in ver.tolist()]
+    assert idx == sorted(idx) and len(idx) > 50

@@ -212,3 +212,19 @@ def test_dog_detector_oracle_vs_reference(oracle, reference, mode, regs):
     if mode == 0:
         va, vb = oracle.view_pipeline(im, hp=hp), reference.view_pipeline(im, hp=hp)
         assert all(np.array_equal(x, y) for x, y in zip(va, vb))
+
+
+# ---- matching/matching.cpp compiled in place (FLANN answered by the shim's exact linear k-NN) ------------------------------------------
+@pytest.mark.parametrize("ratio,contrad,n,nt", [(0.8, 30.0, 1500, 1500), (0.95, 10.0, 700, 2100), (0.6, 30.0, 900, 60)])
+def test_fginn_port_equals_matching_cpp(oracle, reference, ratio, contrad, n, nt):
+    """The oracle's FGINN loop == MatchFlannFGINN (matching.cpp:357-461) driven by an exact k-NN table: every tentative row."""
+    rng = np.random.default_rng(int(ratio * 100) + n)
+    q = np.floor(rng.dirichlet(np.full(128, 0.3), n) ** 0.5 * 512).clip(0, 255).astype(np.float32)
+    t = np.floor(rng.dirichlet(np.full(128, 0.3), nt) ** 0.5 * 512).clip(0, 255).astype(np.float32)
+    m = min(n, nt) // 2
+    t[:m] = np.clip(q[:m] + rng.integers(-8, 9, (m, 128)), 0, 255)
+    t[m:m + m // 4] = t[:m // 4]                       # exact duplicates among the trains: equal distances, tie order = lower index
+    xy = rng.random((nt, 2)) * 200
+    a = oracle.match_fginn(q, t, xy, ratio=ratio, contradDist=contrad)
+    b = reference.match_fginn(q, t, xy, ratio=ratio, contradDist=contrad)
+    assert len(a) > 20 and np.array_equal(a, b)
