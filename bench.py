@@ -35,6 +35,17 @@ sys.path.insert(0, ROOT)
 
 BLOB_DENSITY = 1.5e-3   # blobs per pixel: calibrated so that HessianAffine finds ~30k keypoints at 4096x3072
 N_PAIRS = 3
+# ONE metric string for both arms (the driver only forms vs_reference ratios when metric, unit and direction are identical)
+METRIC = "image-pairs/sec (4096x3072 synthetic pair, ~30k HessAff kpts/image; matched-kpts/sec in `matched_kpts_per_s`)"
+GENERATOR = {"impl": "mods_b200/synth.py (numpy PCG64; SURVEY 8d asked for SplitMix64 in C++ -- same images for both arms, so ratios are unaffected)",
+             "blob_density_per_px": BLOB_DENSITY, "calibration": "SURVEY 8d's 5e-3 blobs/px gave far more than 30k +-15 % HessianAffine keypoints on the "
+             "identity view at 4096x3072; N_b alone was scaled to 1.5e-3 (~31.5k keypoints, oracle count)", "seeds": "pair i: A = 1 + 16 i, B = A + 1 (rank r adds 1000 r)"}
+
+
+def workload_string(w, h, no_mser):
+    return ("C3: %dx%d synthetic pair, HessianAffine(FixedTh 5.3333)+Baumberg and %s, orientation+RootSIFT, identity view, "
+            "FGINN 0.8 exact NN per detector, duplicate filter 2px, LO-RANSAC-H 3px + LAF check"
+            % (w, h, "HessianAffine only (--no-mser)" if no_mser else "MSER(min_margin 8, min_size 30, max_area 0.05)"))
 
 
 def load_peaks():
@@ -125,6 +136,8 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ver_cap = [0]   # capacity of the verified-rows output of the un-pipelined call (parity check of pair 0)
+
     def timed(buffers, steps, pipelined=True, collective=True):
         """K steps = K pairs.  collective=False: rank-local (the profiling pass runs on rank 0 only -- no barrier, no all-reduce).  pipelined: ONE mb2_mods_pairs call over the K pairs (the dataset entry point: verification of
         pair k overlaps detection of pair k+1); otherwise K separate mb2_mods_pair calls (per-pair latency)."""
@@ -139,8 +152,10 @@ def run_ours(args, rank, world, local_rank):
         else:
             for s in range(steps):
                 a, b = buffers[s % len(buffers)]
-                res, _ = ctx.mods_pair(a, b, cfg, shape1=(h, w), shape2=(h, w))
+                res, ver = ctx.mods_pair(a, b, cfg, shape1=(h, w), shape2=(h, w), capacity=ver_cap[0])
                 results.append(res)
+                if ver_cap[0] and s == 0:
+                    results[0].ver_rows = ver
         e1.record(stream)
         barrier() if collective else torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -161,6 +176,9 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e, wall_e2e, res_e2e, _ = timed(pin_pairs, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_lat, _, res_lat, _ = timed(dev_pairs, min(args.steps, 2 * N_PAIRS), pipelined=False)
+    ver_cap[0] = 1 << 17
+    _, _, res_par, _ = timed(dev_pairs, 1, pipelined=False, collective=False)   # pair 0 once more, verified rows kept (parity check below)
+    ver_cap[0] = 0
 
     # per-kernel durations (CUDA events inside the library, same stream) on extra steps
     prof = None
@@ -182,14 +200,12 @@ def run_ours(args, rank, world, local_rank):
     pairs_s = world * K / (ms_dev / 1e3)
     e2e_s = world * K / (ms_e2e / 1e3)
     out = {
-        "metric": "image-pairs/sec (4096x3072 synthetic pair, ~30k HessAff kpts/image; matched-kpts/sec in `matched_kpts_per_s`)",
+        "metric": METRIC,
         "value": pairs_s, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": max(3, args.warmup),
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (pyramid/patches), f64 (SIFT sums, RANSAC), bf16->f32 tcgen05 (NN, exact on u8 descriptors)",
         "data": "synthetic (numpy PCG64 blob images + ground-truth homography warp, mods_b200/synth.py)",
-        "config": {"workload": "C3: %dx%d synthetic pair, HessianAffine(FixedTh 5.3333)+Baumberg and %s, orientation+RootSIFT, identity view, "
-                               "FGINN 0.8 exact NN per detector, duplicate filter 2px, LO-RANSAC-H 3px + LAF check"
-                               % (w, h, "HessianAffine only (--no-mser)" if args.no_mser else "MSER(min_margin 8, min_size 30, max_area 0.05)"),
+        "config": {"workload": workload_string(w, h, args.no_mser), "generator": GENERATOR,
                    "mser_regions_per_image": float(np.mean([r.mser_regions1 + r.mser_regions2 for r in res_dev])) / 2,
                    "mser_tentatives": float(np.mean([r.mser_tentatives for r in res_dev])),
                    "pairs_in_rotation": N_PAIRS, "l2": "inputs cycle through %d pairs (%.0f MB) and the per-image pyramid working set (~1.3 GB) exceeds the 126 MB L2"
@@ -217,7 +233,18 @@ def run_ours(args, rank, world, local_rank):
             out["micro"] = micro_benchmarks(ctx)
         except Exception as e:   # the micro-benchmarks never take the headline down
             out["micro"] = {"error": repr(e)}
-    out["cpu_baseline"] = cpu_baseline(pairs[0], cfg_seed=1, with_mser=not args.no_mser) if (not args.no_cpu_baseline and world == 1) else None   # rank 0 at N=1 only
+    # results must be plausible: a failing kernel must not show up as a faster pairs/s figure
+    for r in res_dev + res_e2e + res_lat:
+        if not (r.regions1 > 0 and r.regions2 > 0 and r.tentatives > 0):
+            raise SystemExit("bench.py: a pair came back with no regions / tentatives (regions %d / %d, tentatives %d)" % (r.regions1, r.regions2, r.tentatives))
+    out["cpu_baseline"] = None
+    out["parity"] = {"checked": False}
+    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only: one full-size pair on the host cores, its outputs compared with the GPU's
+        out["cpu_baseline"], cpu = cpu_baseline(pairs[0], w, h, cfg_values(cfg), with_mser=not args.no_mser)
+        try:
+            out["parity"] = parity_check(local_rank, pairs[0], w, h, cfg, cpu, res_par[0], getattr(res_par[0], "ver_rows", None))
+        except Exception as e:
+            out["parity"] = {"checked": True, "ok": False, "error": repr(e)}
     emit_json_line(out)
 
 
@@ -325,85 +352,143 @@ def micro_benchmarks(ctx):
     return out
 
 
-def cpu_baseline(pair, cfg_seed=1, query_sample=2000, with_mser=True):
-    """The CPU oracle (port of the reference's algorithm) on a bounded sample of the same pair: view pipelines on 1 thread, the exact
-    FGINN matcher on all host threads (OpenMP over queries)."""
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())   # torchrun pins it to 1; set before the oracle's OpenMP runtime starts
-    from oracle.pyoracle import Oracle
-    O = Oracle()
+def cfg_values(cfg):
+    """The scalar settings of an mb2_pair_config the CPU arm needs (plain dict: the reference arm must not load the GPU library)."""
+    if cfg is None:   # mb2_pair_config_default (config_iter_mods_cviu.ini / iters_mods_cviu.ini)
+        return dict(matchRatio=0.8, mserMatchRatio=0.8, contradDist=30.0, duplicateDist=2.0, err_threshold=3.0, confidence=0.99, HLAFCoef=12.0, LAFCoef=2.0,
+                    max_samples=100000, errorType=0, doSymmCheck=1, seed=1, useF=0, localOptimization=1)
+    return {k: getattr(cfg, k) for k in ("matchRatio", "mserMatchRatio", "contradDist", "duplicateDist", "err_threshold", "confidence", "HLAFCoef", "LAFCoef",
+                                         "max_samples", "errorType", "doSymmCheck", "seed", "useF", "localOptimization")}
+
+
+def cpu_pair(pair, with_mser=True, cv=None):
+    """ONE full-size pair through the reference's CPU path, un-cropped and un-extrapolated (one iteration of mods.cpp:229-415):
+    detect -> orient -> describe of (image, detector) on one thread each -- 2 images x 2 detectors, as mods.cpp:255-271 +
+    imagerepresentation.cpp:612 parallelise them -- by the reference's own sources compiled in place (oracle/_ref); then the reference's
+    own matching.cpp: MatchFlannFGINN over ALL queries per detector (exact linear k-NN on all host threads standing in for FLANN, which is
+    not in the reference tree), DuplicateFiltering, LORANSACFiltering (exp_ransacHcustom + NaiveHCheck + H_LAF_check).
+    Falls back to the oracle port (views + FGINN only) when oracle/_ref is absent."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())   # torchrun pins it to 1; set before the OpenMP runtime of the CPU code starts
+    from oracle import pyoracle
+    cv = cv or cfg_values(None)
+    use_ref = pyoracle.have_reference()
+    L = pyoracle.Reference() if use_ref else pyoracle.Oracle()
     A, B = pair
-    t_pair, notes = 0.0, []
-    for det, name in ((0, "HessianAffine"),) + (((3, "MSER"),) if with_mser else ()):
-        t0 = time.perf_counter(); va = O.view_pipeline(A, detector=det); t_view = time.perf_counter() - t0
-        vb = O.view_pipeline(B[: B.shape[0] // 4], detector=det)  # trains for the matching sample (quarter image, not timed into t_view)
-        nq = min(query_sample, len(va[0]))
-        t0 = time.perf_counter()
-        O.match_fginn(va[2][:nq], vb[2], np.ascontiguousarray(vb[1][:, :2]))
-        t_match_sample = time.perf_counter() - t0
-        # one pair = 2 views + matching all queries against all trains (linear in queries x trains)
-        scale = (len(va[0]) / max(1, nq)) * (len(va[0]) / max(1, len(vb[0])))
-        t_pair += 2 * t_view + t_match_sample * scale
-        notes.append("%s: view pipeline on one full image %.1f s (%d regions, x2 per pair) + exact FGINN of %d queries vs %d trains %.1f s "
-                     "extrapolated linearly to %d x %d" % (name, t_view, len(va[0]), nq, len(vb[0]), t_match_sample, len(va[0]), len(va[0])))
-    return {"value": 1.0 / t_pair, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "oracle on the same 4096x3072 pair (view pipelines on 1 thread, FGINN matcher on all %d threads); " % os.cpu_count()
-                      + "; ".join(notes) + "; duplicate filter / RANSAC not included (small)"}
+    dets = (0, 3) if with_mser else (0,)
+    views = {}
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=lambda k=(i, d), im=im: views.__setitem__(k, L.view_pipeline(im, detector=k[1]))) for i, im in enumerate((A, B)) for d in dets]
+    [t.start() for t in th]; [t.join() for t in th]
+    t_views = time.perf_counter() - t0
+    groups = [(views[(0, d)][1], views[(0, d)][2], views[(1, d)][1], views[(1, d)][2], cv["matchRatio"] if d == 0 else cv["mserMatchRatio"]) for d in dets]
+    t0 = time.perf_counter()
+    if use_ref:
+        back = L.pair_back(groups, contradDist=cv["contradDist"], duplicateDist=cv["duplicateDist"], useF=cv["useF"], err_threshold=cv["err_threshold"],
+                           confidence=cv["confidence"], max_samples=cv["max_samples"], localOptimization=cv["localOptimization"], LAFCoef=cv["LAFCoef"],
+                           HLAFCoef=cv["HLAFCoef"], errorType=cv["errorType"], doSymmCheck=cv["doSymmCheck"], seed=cv["seed"])
+    else:
+        tent = [np.c_[np.full(len(m), g), m] for g, m in enumerate(L.match_fginn(gr[1], gr[3], np.ascontiguousarray(gr[2][:, :2]), ratio=gr[4],
+                                                                                 contradDist=cv["contradDist"]) for gr in groups)]
+        back = dict(tent=np.concatenate(tent), kept=None, verified=None, H=None, counts=[sum(len(t) for t in tent), 0, 0, 0])
+    t_back = time.perf_counter() - t0
+    return dict(t_views=t_views, t_back=t_back, t_pair=t_views + t_back, views=views, groups=groups, back=back, kind="reference" if use_ref else "port",
+                threads_views=len(th), dets=dets)
+
+
+def cpu_sample_text(r, w, h):
+    return ("ONE full %dx%d pair, nothing cropped or extrapolated: %s view pipelines (detect -> orient -> describe) of %d (image, detector) units on %d threads "
+            "%.2f s; %s %.2f s -> %d tentatives, %d unique, %d RANSAC inliers, %d verified"
+            % (w, h, "oracle/_ref (the reference's sources compiled in place)" if r["kind"] == "reference" else "oracle port", r["threads_views"], r["threads_views"],
+               r["t_views"], "matching.cpp MatchFlannFGINN over all queries (exact linear k-NN on all %d host threads in place of FLANN) + DuplicateFiltering + "
+               "LORANSACFiltering" % os.cpu_count() if r["kind"] == "reference" else "FGINN port over all queries (duplicate filter / RANSAC not run)",
+               r["t_back"], *r["back"]["counts"]))
+
+
+def cpu_baseline(pair, w, h, cv, with_mser=True):
+    r = cpu_pair(pair, with_mser, cv)
+    return {"value": 1.0 / r["t_pair"], "unit": "pairs/s", "cores": os.cpu_count(), "kind": r["kind"], "sample": cpu_sample_text(r, w, h),
+            "ms_views": 1e3 * r["t_views"], "ms_match_verify": 1e3 * r["t_back"]}, r
+
+
+def parity_check(local_rank, pair, w, h, cfg, cpu, res0, ver0):
+    """GPU outputs of pair 0 against the CPU reference run of the SAME pair in the SAME process (the cpu_baseline leg's outputs):
+    regions (det_kp, reproj_kp: 9 doubles each) and descriptors of both images and both detectors, tentatives per detector
+    (q, idx0, idxJ, idx1, d0, dJ, d1), then the counts and the verified list of the whole mb2_mods_pair call -- all bit-exact."""
+    import mods_b200 as mb
+    out = {"checked": True, "config": "C3 %dx%d, pair 0" % (w, h), "against": "oracle/_ref (compiled reference)" if cpu["kind"] == "reference" else "oracle port", "details": {}}
+    ok = True
+    ctx = mb.Context(local_rank)
+    try:
+        A, B = pair
+        for d in cpu["dets"]:
+            name = "HessianAffine" if d == 0 else "MSER"
+            det = mb.HessaffParams.default() if d == 0 else mb.MserParams.default()
+            for i, im in enumerate((A, B)):
+                g = ctx.detect_describe_view(im, det=det, ori=cfg.ori, desc=cfg.desc, slot=i)
+                o = cpu["views"][(i, d)]
+                same = (len(g[0]) == len(o[0]) and np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2].astype(np.float32), o[2]))
+                out["details"]["%s_image%d" % (name, i + 1)] = {"regions": int(len(g[0])), "reference_regions": int(len(o[0])), "bit_exact": bool(same)}
+                ok &= bool(same)
+            gi = list(cpu["dets"]).index(d)
+            gm = ctx.match_slots(0, 1, ratio=cpu["groups"][gi][4], contradDist=cfg.contradDist)
+            om = cpu["back"]["tent"]; om = om[om[:, 0] == gi][:, 1:]
+            same = len(gm) == len(om) and np.array_equal(gm, om)
+            out["details"]["%s_tentatives" % name] = {"n": int(len(gm)), "reference_n": int(len(om)), "bit_exact": bool(same)}
+            ok &= bool(same)
+        if cpu["back"]["kept"] is not None:
+            c = cpu["back"]["counts"]
+            mine = [res0.tentatives, res0.unique_tentatives, res0.ransac_inliers, res0.verified]
+            rows = cpu["back"]["tent"][cpu["back"]["verified"]]
+            exp = np.array([np.r_[cpu["groups"][int(r[0])][0][int(r[1]), :2], cpu["groups"][int(r[0])][2][int(r[2]), :2]] for r in rows]).reshape(-1, 4)
+            same_list = ver0 is not None and len(ver0) == len(exp) and np.array_equal(ver0, exp)
+            Hdiff = float(np.max(np.abs(np.array(res0.H) / res0.H[8] - cpu["back"]["H"] / cpu["back"]["H"][8]))) if c[3] else None
+            out["details"]["pair_chain"] = {"tentatives_unique_inliers_verified": mine, "reference": list(map(int, c)), "verified_list_identical": bool(same_list),
+                                            "H_max_abs_diff": Hdiff, "seed": int(cfg.seed)}
+            ok &= mine == list(map(int, c)) and bool(same_list)
+    finally:
+        ctx.close()
+    out["ok"] = bool(ok)
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path on this box's host cores: its compiled sources
-    (oracle/_ref) for detection / orientation / description, two images on two threads like mods.cpp's two
-    OpenMP tasks; exact linear kNN + FGINN loop from the oracle port (OpenCV FLANN is not buildable here)."""
+    """The reference's own CPU implementation of the path on this box's host cores, on the full-size workload (cpu_pair): every step is
+    one whole 4096x3072 pair.  --steps / --warmup are honoured while the run fits MB2_REF_BUDGET_S (default 240 s of wall clock, a step
+    takes ~10 s); otherwise warm-ups drop to one and steps to what fits -- the line reports the steps actually run."""
     if rank != 0:
         return
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())   # torchrun pins it to 1; set before the OpenMP runtime of the CPU code starts
-    from oracle import pyoracle
     w, h = args.size
-    pairs = make_pairs(w, h, 1)
-    A, B = pairs[0]
-    use_ref = pyoracle.have_reference()
-    L = pyoracle.Reference() if use_ref else pyoracle.Oracle()
-    O = pyoracle.Oracle()
-    # bounded sample: a centred crop of the pair so that K steps end within minutes; throughput is scaled by area
-    ch, cw = h // 2, w // 2
-    a = np.ascontiguousarray(A[h // 4: h // 4 + ch, w // 4: w // 4 + cw]); b = np.ascontiguousarray(B[h // 4: h // 4 + ch, w // 4: w // 4 + cw])
-    steps = max(1, min(args.steps, 3))
-
-    dets = (0,) if args.no_mser else (0, 3)
-
-    def one_step():
-        t_total = 0.0
-        for det in dets:
-            out = [None, None]
-            t0 = time.perf_counter()
-            th = [threading.Thread(target=lambda i=i, im=im: out.__setitem__(i, L.view_pipeline(im, detector=det))) for i, im in enumerate((a, b))]
-            [t.start() for t in th]; [t.join() for t in th]
-            t_views = time.perf_counter() - t0
-            va, vb = out
-            nq = min(2000, len(va[0]))
-            t0 = time.perf_counter()
-            O.match_fginn(va[2][:nq], vb[2], np.ascontiguousarray(vb[1][:, :2]))
-            t_match = time.perf_counter() - t0
-            # full-size pair: 4x the pixels per view; matching is (4 n1) x (4 n2) instead of nq x n2
-            t_total += 4.0 * t_views + t_match * (len(va[0]) / max(1, nq)) * 16.0
-        return t_total
-
-    for _ in range(min(args.warmup, 1)):
-        one_step()
-    t_tot = 0.0
-    for _ in range(steps):
-        t_tot += one_step()
+    t_start = time.perf_counter()
+    budget = float(os.environ.get("MB2_REF_BUDGET_S", "240"))
+    pair = make_pairs(w, h, 1)[0]
+    cv = cfg_values(None)
+    first = cpu_pair(pair, not args.no_mser, cv)          # warm-up step 1 (also sizes the rest of the run)
+    t_step = first["t_pair"]
+    left = budget - (time.perf_counter() - t_start)
+    warm = max(1, args.warmup)
+    steps = max(1, args.steps)
+    if (warm - 1 + steps) * t_step > left:
+        warm = 1
+        steps = max(1, min(steps, int(left / t_step)))
+    for _ in range(warm - 1):
+        cpu_pair(pair, not args.no_mser, cv)
+    t0 = time.perf_counter()
+    runs = [cpu_pair(pair, not args.no_mser, cv) for _ in range(steps)]
+    t_tot = time.perf_counter() - t0
     t_pair = t_tot / steps
     v = 1.0 / t_pair
-    out = {"impl": "reference", "metric": "image-pairs/sec (4096x3072 synthetic pair, ~30k HessAff kpts/image)", "value": v, "unit": "pairs/s",
-           "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_pair, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)", "data": "synthetic (same generator and seeds as the GPU arm)",
-           "config": {"workload": "C3: %dx%d synthetic pair (reference CPU path, %s)" % (w, h, "HessianAffine only" if args.no_mser else "HessianAffine + MSER")},
-           "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference" if use_ref else "port",
-                            "sample": "centre %dx%d crop of the pair (1/4 area): %s view pipeline (%s) for both images on 2 threads (mods.cpp's two OpenMP "
-                                      "tasks; one view per detector leaves nothing else to parallelise), scaled x4; exact FGINN (oracle port, all host threads over the queries) "
-                                      "of 2000 queries vs all trains scaled to the full N1 x N2" % (cw, ch, "oracle/_ref" if use_ref else "oracle port", "HessianAffine, then MSER" if len(dets) > 1 else "HessianAffine")},
+    r = runs[-1]
+    verified = r["back"]["counts"][3]
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s",
+           "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_pair, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)", "data": "synthetic (same generator and seeds as the GPU arm, pair 0)",
+           "config": {"workload": workload_string(w, h, args.no_mser), "generator": GENERATOR, "requested_steps": args.steps, "requested_warmup": args.warmup,
+                      "budget_s": budget, "regions_per_image": float(np.mean([len(r["views"][k][0]) for k in r["views"]])) * len(r["dets"]),
+                      "tentatives": int(r["back"]["counts"][0]), "verified": int(verified)},
+           "matched_kpts_per_s": verified * v,
+           "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": os.cpu_count(), "kind": r["kind"], "sample": cpu_sample_text(r, w, h),
+                            "ms_views": 1e3 * float(np.mean([x["t_views"] for x in runs])), "ms_match_verify": 1e3 * float(np.mean([x["t_back"] for x in runs]))},
            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_json_line(out)
 

@@ -721,12 +721,7 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->img, &ctx->pyr, &ctx->resp, &ctx->cand, &ctx->misc, &ctx->kp_a, &ctx->kp_b, &ctx->kp_c, &ctx->desc_u8,
-                    &ctx->patch_scratch, &ctx->nn_a, &ctx->nn_b, &ctx->nn_c, &ctx->nn_d, &ctx->rs_a, &ctx->rs_b, &ctx->rs_c, &ctx->rs_u, &ctx->octmap,
-                    &ctx->img2, &ctx->pair_keys, &ctx->synth_a, &ctx->synth_b, &ctx->synth_c, &ctx->synth_k};
-  for (DevBuf* b : bufs) b->release();
-  for (auto& s : ctx->slots) { s.desc.release(); s.xy.release(); }
-  ctx->h_a.release(); ctx->h_b.release(); ctx->h_c.release();
+  ctx->release_buffers();
   mb2_mser_release(ctx);
   drop_priv(ctx);
   if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
@@ -738,7 +733,11 @@ void mb2_ctx_destroy(mb2_ctx* ctx) {
 }
 
 const char* mb2_last_error(const mb2_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-int mb2_ctx_sync(mb2_ctx* ctx) { MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return MB2_OK; }
+int mb2_ctx_sync(mb2_ctx* ctx) {
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->launch_error != cudaSuccess) { ctx->launch_error = cudaSuccess; return MB2_ERR_CUDA; }   // a kernel launch failed since the last sync (message in mb2_last_error)
+  return MB2_OK;
+}
 void* mb2_ctx_stream(mb2_ctx* ctx) { return (void*)ctx->stream; }
 int mb2_ctx_device(const mb2_ctx* ctx) { return ctx ? ctx->device : -1; }
 int mb2_ctx_profiling(const mb2_ctx* ctx) { return ctx && ctx->profiling ? 1 : 0; }

@@ -90,8 +90,25 @@ struct mb2_ctx {
   cudaEvent_t ev_tree = nullptr;
   volatile long long tree_epoch = 0;
   unsigned long long prof_extract_bytes = 0;  // algorithmic gather bytes of the patch-extraction launches
+  cudaError_t launch_error = cudaSuccess;     // first failed kernel launch (MB2_LAUNCH); reported by mb2_ctx_sync and the C entry points
   void set_error(const std::string& s) { err = s; }
+  // every device buffer of the context in one list, so that mb2_ctx_destroy cannot forget a member
+  void release_buffers() {
+    DevBuf* all[] = {&img, &pyr, &resp, &cand, &misc, &kp_a, &kp_b, &kp_c, &desc_u8, &patch_scratch, &nn_a, &nn_b, &nn_c, &nn_d, &rs_a, &rs_b, &rs_c, &rs_u, &rs_v,
+                     &dog_taps, &dog_tmp, &octmap, &img2, &pair_keys, &synth_a, &synth_b, &synth_c, &synth_k};
+    for (DevBuf* b : all) b->release();
+    HostBuf* hall[] = {&h_a, &h_b, &h_c};
+    for (HostBuf* b : hall) b->release();
+    for (RegionSlot& s : slots) { s.desc.release(); s.xy.release(); s.n = 0; }
+  }
 };
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: one bit per device in a per-call-site mask
+inline bool mb2_first_use_on_device(unsigned long long* mask, int device) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
 
 // ---- exact (non-contracted) float helpers ---------------------------------------------------
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -212,6 +229,9 @@ __device__ __forceinline__ void interpolate_row(const float* __restrict__ im, in
       cudaEventRecord(_pr.a, (strm));                                      \
     }                                                                      \
     kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);              \
+    { const cudaError_t _le = cudaPeekAtLastError();                       \
+      if (_le != cudaSuccess && (ctx)->launch_error == cudaSuccess) {      \
+        (ctx)->launch_error = _le; (ctx)->set_error(std::string("launch of " #kernel ": ") + cudaGetErrorString(_le)); } } \
     if ((ctx)->profiling) { cudaEventRecord(_pr.b, (strm)); (ctx)->prof.push_back(_pr); } \
     (ctx)->launches++;                                                     \
   } while (0)

@@ -756,11 +756,10 @@ int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* k
                                const unsigned long long* d_off, float* d_scratch,
                                uint8_t* d_desc, float* d_patches, float2* d_stats, double* d_vecT, float2* d_rec) {
   if (!n) return MB2_OK;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devs = 0;
+  if (mb2_first_use_on_device(&attr_devs, ctx->device)) {
     cudaFuncSetAttribute(k_extract_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_extract_needed, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr = true;
   }
   // The few very large regions of the global-scratch class take as long as thousands of small ones: they run on
   // the side stream, next to the shared-memory classes (per-kernel profiling keeps one stream).

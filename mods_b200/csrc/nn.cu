@@ -68,10 +68,18 @@ __global__ void k_threshold(NNState st, int nq, const float* __restrict__ qn, do
   st.d0[i] = d0; st.idx0[i] = (int)(unsigned)k;
   double guess = floor((double)d0 / sqminratio);
   if (guess < 1) guess = 1;
-  float t = (float)guess;
-  // walk to the exact boundary of the float test (a couple of steps at most)
-  while (t > 1.f && (double)__fdiv_rn(d0, t - 1.f) <= sqminratio) t -= 1.f;
-  while (!((double)__fdiv_rn(d0, t) <= sqminratio)) t += 1.f;
+  // No squared distance between two u8 descriptors reaches TMAX = 128 * 255^2 + 1: a threshold at or above it classifies every train as a
+  // "failer", exactly like TMAX itself.  Clamping keeps every value below 2^24, where t +- 1.f is exact (above it `t += 1.f` would not
+  // move and the walk below would never end for small ratios with a large d0).
+  const float TMAX = 8323201.f;
+  float t;
+  if (guess >= (double)TMAX) t = TMAX;
+  else {
+    t = (float)guess;
+    // walk to the exact boundary of the float test (a couple of steps at most)
+    while (t > 1.f && (double)__fdiv_rn(d0, t - 1.f) <= sqminratio) t -= 1.f;
+    while (t < TMAX && !((double)__fdiv_rn(d0, t) <= sqminratio)) t += 1.f;
+  }
   st.thr[i] = t;
   st.thr_rel[i] = t - qn[i];  // compared against |t|^2 - 2 q.t (exact: all integers < 2^24)
 }
@@ -483,11 +491,10 @@ int mb2_nn_pass_tc(mb2_ctx* ctx, int pass, const void* q_bf16, int nq, int nq_pa
   n_chunks = (total_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
   const int n_items = n_qblocks * n_chunks;
   const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_devs = 0;
+  if (mb2_first_use_on_device(&attr_devs, ctx->device)) {
     cudaFuncSetAttribute(k_nn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(k_nn_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    attr = true;
   }
   if (pass == 1)
     MB2_LAUNCH(ctx, k_nn_tc<1>, grid, NN_THREADS, SMEM_BYTES, mq, mt, nq, nt_pad, qn, tn, st, txy, contr2, tiles_per_chunk, n_qblocks,

@@ -251,8 +251,8 @@ void mb2_launch_orientation(mb2_ctx* ctx, const ImgView& img, const KeyOut* in, 
                             const float* d_orimask, KeyOut* out, int* out_count_per_kp) {
   if (!n) return;
   const size_t smem = 256 * sizeof(double) + OW * sizeof(OriWarp);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_orientation, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static unsigned long long attr_devs = 0;
+  if (mb2_first_use_on_device(&attr_devs, ctx->device)) cudaFuncSetAttribute(k_orientation, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   MB2_LAUNCH(ctx, k_orientation, (n + OW - 1) / OW, OW * 32, smem, img, in, n, op, d_orimask, out, out_count_per_kp);
 }
 

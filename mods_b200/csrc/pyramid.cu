@@ -371,8 +371,8 @@ void launch_blur_nt(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* ds
   constexpr int H = NT / 2;
   constexpr int IN_W = TW + 2 * H + 2, IN_H = TH + 2 * H + 2;
   size_t smem = sizeof(float) * (IN_H * (IN_W + 2) + IN_H * (TW + 4));
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_blur_hess<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  static unsigned long long attr_devs = 0;
+  if (mb2_first_use_on_device(&attr_devs, ctx->device)) cudaFuncSetAttribute(k_blur_hess<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((src.cols + TW - 1) / TW, (src.rows + TH - 1) / TH);
   MB2_LAUNCH(ctx, k_blur_hess<NT>, grid, BLUR_THREADS, smem, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp);
 }

@@ -292,6 +292,17 @@ extern "C" int mb2_ransac_h(mb2_ctx* ctx, const double* u, int len, double th, d
     const int dbuf = R.errs[0];
     R.tag(dbuf, h);                                   // d = errs[0]; HDS1(Z, u, h, d, len)
     S.I = (unsigned)bI[model_idx]; S.J = bJ[model_idx]; model_idx++;
+    // The batch scorer's J is a tree sum whose partition depends on the batch; the reference (and every LO model here) sums the MSAC
+    // terms serially.  Scores are ordered by J alone (scoreLess, __SCORE__ == SC_M), so a hypothesis that could win or tie -- J within
+    // 1e-9 of a best-so-far or above it -- gets the reference's serial sum from its residuals before it is compared: the bests always
+    // carry serial sums, and a sample drawn twice (identical residuals) ties exactly instead of flipping on the last bit.
+    if (S.J >= std::min(maxS.J, maxSs.J) * (1.0 - 1e-9)) {
+      const double* dd = R.data(dbuf);
+      if (R.rc < 0) return R.rc;
+      double Js = 0;
+      for (int i = 0; i < len; ++i) Js += truncQuad(dd[i], th);
+      S.J = Js;
+    }
     bool do_iterate;
     if (scoreLess(maxS, S)) {
       if (doSymCheck) bad_model = R.sym_check_bad(h);

@@ -178,16 +178,24 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
                                                       &det_par.MSERParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0)
                       : mb2_detect_describe_view(ctx, OriginalImg.data, OriginalImg.cols, OriginalImg.rows, H, OriginalImg.cols, OriginalImg.rows,
                                                  &det_par.HessParam, &op, &sp, dev_slot, use_slot && ss.count > 0, nullptr, nullptr, nullptr, 0);
-        if (n < 0) continue;  // failures are silent, like the reference (empty lists)
-        if (use_slot) { ss.desc = curr_desc; ss.count += n; }
+        if (n < 0) { if (last_rc == 0) last_rc = n; continue; }  // silent for the class API like the reference (empty lists); LastError() keeps the code
+        // host copy first: the device slot (already appended by the call) and the host block must never go out of step
+        std::vector<double> dk((size_t)n * MB2_KP), rk((size_t)n * MB2_KP); std::vector<unsigned char> du((size_t)n * 128);
+        if (n > 0) {
+          const int frc = mb2_view_fetch(ctx, dk.data(), rk.data(), du.data(), n);
+          if (frc < 0) { if (last_rc == 0) last_rc = frc; if (use_slot) { ss.desc = curr_desc; ss.count = -1; } continue; }   // count -1: slot unusable, pair_front refuses to match it
+        }
+        if (use_slot && ss.count >= 0) { ss.desc = curr_desc; ss.count += n; }
         RegionBlock& B = Blocks[curr_det][curr_desc];
         B.det = is_mser ? DET_MSER : DET_HESSIAN; B.desc = dt;
         const size_t base = (size_t)B.n;
         B.det_kp.resize((base + n) * MB2_KP); B.reproj_kp.resize((base + n) * MB2_KP); B.desc_u8.resize((base + n) * 128);
         B.img_id.resize(base + n, (int)synth);
-        if (n > 0 && mb2_view_fetch(ctx, &B.det_kp[base * MB2_KP], &B.reproj_kp[base * MB2_KP], &B.desc_u8[base * 128], n) < 0) n = 0;
+        if (n > 0) {
+          std::memcpy(&B.det_kp[base * MB2_KP], dk.data(), dk.size() * sizeof(double)); std::memcpy(&B.reproj_kp[base * MB2_KP], rk.data(), rk.size() * sizeof(double));
+          std::memcpy(&B.desc_u8[base * 128], du.data(), du.size());
+        }
         B.n = (int)base + n;
-        B.det_kp.resize((size_t)B.n * MB2_KP); B.reproj_kp.resize((size_t)B.n * MB2_KP); B.desc_u8.resize((size_t)B.n * 128); B.img_id.resize(B.n);
         TimeSpent.DetectTime += (now_ms() - t0) / 1000.0;  // detect + orient + describe are one fused call here
       }
     }
@@ -881,6 +889,9 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
     out.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
   }
   res->ms_detect_describe = now_ms() - t0;
+  // a view call that failed (CUDA error, capacity, tap-table overflow) fails the pair: no success with partial regions
+  if (out.rep1->LastError() < 0) { out.rc = out.rep1->LastError(); return; }
+  if (out.rep2->LastError() < 0) { out.rc = out.rep2->LastError(); return; }
   res->regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name); res->regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name);
   res->mser_regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name, "MSER"); res->mser_regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name, "MSER");
   t0 = now_ms();
@@ -897,8 +908,12 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
       if (!(Q && T && Q->n > 0 && T->n > 0)) continue;
       G.rows.resize((size_t)Q->n * 7);
       const double ratio = g == 0 ? cfg->matchRatio : cfg->mserMatchRatio;
-      if (desc == ps.desc_name)   // the first descriptor of the tier is the one left resident on the device
+      if (desc == ps.desc_name) {  // the first descriptor of the tier is the one left resident on the device
+        // the device slots must hold exactly the host blocks' regions (the same check MatchImgReps makes: count == Q.n)
+        const int sq = out.rep1->SlotCount(dets[g]), st = out.rep2->SlotCount(dets[g]);
+        if ((sq > 0 && sq != Q->n) || (st > 0 && st != T->n) || sq < 0 || st < 0) { out.rc = MB2_ERR_CUDA; return; }
         G.nt = mb2_match_slots(ctx, g == 0 ? 0 : 2, g == 0 ? 1 : 3, ratio, cfg->contradDist, 50, G.rows.data(), Q->n);
+      }
       else {
         std::vector<double> txy((size_t)T->n * 2);
         for (int i = 0; i < T->n; i++) { txy[2 * i] = T->reproj_kp[(size_t)i * MB2_KP]; txy[2 * i + 1] = T->reproj_kp[(size_t)i * MB2_KP + 1]; }

@@ -158,6 +158,14 @@ class ImageRepresentation {
   std::string Name;
   // device-resident copies of RegionVectorMap[det][desc] for the matcher: HessianAffine in `slot`, MSER in `slot + 2`
   int slot;
+  // The class API keeps the reference's silent behaviour (a failing view yields empty lists, imagerepresentation.h:44-47 has no return
+  // code); the first negative code of a view call is remembered here so that the C entry points (mb2_mods_pair / mb2_mods_pairs) can fail.
+  int last_rc = 0;
+ public:
+  int LastError() const { return last_rc; }
+  void ClearError() { last_rc = 0; }
+  int SlotCount(const std::string& det) const { auto it = slot_state.find(det); return it == slot_state.end() ? 0 : it->second.count; }
+ protected:
   struct SlotState { std::string desc; int count = 0; };   // which descriptor the slot currently holds ("" = none)
   std::map<std::string, SlotState> slot_state;              // per detector
   int slot_of(const std::string& det) const { return slot < 0 ? -1 : (det == "MSER" ? slot + 2 : slot); }

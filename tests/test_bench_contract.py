@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_prints_the_contract_line():
@@ -17,6 +18,23 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "MSER" in d["config"]["workload"]
+    # both arms print the SAME metric string (the driver forms vs_reference only then), and the arm reports what it ran
+    import bench
+    assert d["metric"] == bench.METRIC and d["steps"] == 1 and d["warmup"] >= 1
+    assert "nothing cropped or extrapolated" in d["cpu_baseline"]["sample"] and d["config"]["tentatives"] > 0
+
+
+def test_reference_arm_honours_steps_within_its_budget():
+    env = dict(os.environ, MB2_REF_BUDGET_S="1000")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "2", "--size", "384x288"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert (d["steps"], d["warmup"]) == (3, 2)
+    env["MB2_REF_BUDGET_S"] = "0"      # nothing fits: one warm-up, one step, and the line says so
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "2", "--size", "384x288"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert (d["steps"], d["warmup"]) == (1, 1) and d["config"]["requested_steps"] == 3
 
 
 def test_ours_refuses_to_run_without_a_gpu():
