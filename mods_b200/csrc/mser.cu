@@ -3,13 +3,12 @@
 //
 // The reference is sequential in (intensity, raster) order.  Here both polarities are handled as ONE problem: the
 // inverted image (MSER-) is stacked under the image (MSER+) in one pixel index space of 2*W*H pixels whose halves are never
-// neighbours, so every level-synchronous phase below serves both at once:
-//   1. k_mser_prep / radix sort      u8 image of the polarity, pixels ordered by (level, raster)      [HBM streaming]
-//   2. k_mser_tree (union / final)   component tree of the level sets, level by level: lock-free union-find with
-//                                    "larger (level, index) wins" hooking, so the representative of a component
-//                                    is a pixel of its top level; every element that stops being a root is recorded once
-//                                    (`hooked`, grouped by level), gets its canonical parent and adds its area / inner
-//                                    edge count to the new representative                              [L2 latency]
+// neighbours, so every pass below serves both at once:
+//   1. k_mtree_tiles                 u8 image of both polarities; component tree of every 64 x 64 tile built in shared memory by
+//                                    lock-free merging of all inner pixel pairs at once (mser_tree_build.cuh)         [shared memory]
+//   2. k_mtree_borders / canon /     the same merge over the pixel pairs across tile borders (3 % of the edges) on global words;
+//      accum                         canonical parents + own area / inner-edge counts; sums up the tree, one level per step
+//                                    (nothing is sorted, no barrier per level while the tree is built)     [L2 atomics / HBM streaming]
 //   3. k_mser_best .. k_mser_emulate survivor of every merge = largest tracked child; nodes where the reference's
 //                                    answer depends on its pixel order (births, equal sizes) are replayed by one
 //                                    thread each (mser_logic.cuh: emulate_node)
@@ -23,6 +22,7 @@
 #define MB2_NS mb2_mser_detail
 #include "pyramid.cuh"
 #include "mser_logic.cuh"
+#include "mser_tree_build.cuh"
 
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
@@ -42,7 +42,7 @@ struct MserCounters {
   uint32_t overflow, thr_overflow, cap_overflow, n_stack, root[8], n_img[4];   // n_stack = 2 x images; n_img = regions per image
   uint32_t hist[256];
   uint32_t lvl_off[257];
-  uint32_t hook_off[258];
+  uint32_t lvl_cnt[256];   // representatives per level (k_mtree_canon)
 };
 
 struct SelRec {  // one (region, threshold): a row of getRLEExtrema's output
@@ -52,12 +52,12 @@ struct SelRec {  // one (region, threshold): a row of getRLEExtrema's output
 };
 
 struct MserBufs {
-  DevBuf lev, zpar, parent, area, nedge, order, order_in, keys8, hooked, best, surv, birth, flag, emu_nodes, own_a, own_b;
+  DevBuf lev, gpar, parent, area, nedge, nodes, best, surv, birth, flag, emu_nodes, own_a, own_b;
   DevBuf uf, esz, epre, eid, ebirth, ekind, longr, sel, sel_sorted, selkey_a, selkey_b, selidx_a, selidx_b, slot_of_node, node_of_slot;
   DevBuf sa, up_sel, ev_a, ev_b, ev_c, ev_d, mom, cub_tmp, counters, table;
   HostBuf h_counters;
   void release() {
-    DevBuf* all[] = {&lev, &zpar, &parent, &area, &nedge, &order, &order_in, &keys8, &hooked, &best, &surv, &birth, &flag, &emu_nodes, &own_a,
+    DevBuf* all[] = {&lev, &gpar, &parent, &area, &nedge, &nodes, &best, &surv, &birth, &flag, &emu_nodes, &own_a,
                      &own_b, &uf, &esz, &epre, &eid, &ebirth, &ekind, &longr, &sel, &sel_sorted, &selkey_a, &selkey_b, &selidx_a, &selidx_b,
                      &slot_of_node, &node_of_slot, &sa, &up_sel, &ev_a, &ev_b, &ev_c, &ev_d, &mom, &cub_tmp, &counters, &table};
     for (DevBuf* b : all) b->release();
@@ -65,210 +65,187 @@ struct MserBufs {
   }
 };
 
-// ---- union-find on zpar ---------------------------------------------------------------------------------------------
-// In a level where a big component forms, every find ends on the same root: read through L2 (__ldcg) that one sector
-// becomes a hot spot that serialises the whole level.  The fast path therefore reads through L1 (possibly stale: a stale
-// pointer is still an ancestor, a stale "root" is caught by the CAS, which then falls back to L2-coherent reads).
-// One 8-byte word per element: low half = parent pointer, bits 32..39 = level of THIS element (written once by k_mser_prep).  A
-// neighbour's level and pointer, and a root's level for the hooking order, come with the load that is needed anyway -- the separate
-// lev[] reads (one more 32-byte sector per neighbour row and two per hooking attempt) are gone.  Hooking swaps the pointer half with a
-// 64-bit CAS whose expected value carries the (immutable) level; path compression stores the pointer half only.
-typedef unsigned long long zp_t;
-__device__ __forceinline__ uint32_t zp_ptr(zp_t z) { return (uint32_t)z; }
-__device__ __forceinline__ int zp_lev(zp_t z) { return (int)(z >> 32); }
-__device__ __forceinline__ zp_t zp_make(uint32_t ptr, int lev) { return ((zp_t)(uint32_t)lev << 32) | ptr; }
-__device__ __forceinline__ void zp_set_ptr(zp_t* z, uint32_t ptr) { __stcg(reinterpret_cast<uint32_t*>(z), ptr); }   // little endian: low word
-template <bool COHERENT>
-__device__ __forceinline__ zp_t uf_load(const zp_t* p) { return COHERENT ? __ldcg(p) : __ldca(p); }
-// root of x; *lev_out (optional) = its level
-template <bool COHERENT>
-__device__ __forceinline__ uint32_t uf_find(zp_t* zpar, uint32_t x, int* lev_out = nullptr) {
-  for (;;) {
-    const zp_t zx = uf_load<COHERENT>(zpar + x);
-    const uint32_t p = zp_ptr(zx);
-    if (p == x) { if (lev_out) *lev_out = zp_lev(zx); return x; }
-    const zp_t zp = uf_load<COHERENT>(zpar + p);
-    const uint32_t g = zp_ptr(zp);
-    if (g == p) { if (lev_out) *lev_out = zp_lev(zp); return p; }
-    zp_set_ptr(zpar + x, g);  // path halving; values only ever move towards the root
-    x = g;
-  }
-}
-// Hooking order: a root of a lower level always goes under a pixel of the current level; inside a level the SMALLER
-// raster index wins.  Threads reach the pixels of a level in ascending order, so a late pixel hooks its own (uncontended)
-// root under the established one instead of dethroning it -- with "larger index wins" the root of a big component would
-// change once per joining pixel, one contended CAS after the other.  Which pixel of its level names a node is irrelevant
-// to every output (mser_logic.cuh).
-__device__ __forceinline__ bool key_less(int la, uint32_t a, int lb, uint32_t b) { return la < lb || (la == lb && a > b); }
+// ---- 1 + 2. component trees by lock-free merging (mser_tree_build.cuh) -----------------------------------------------------------
+// k_mtree_tiles    one CTA per 64 x 64 tile: float -> u8 as extrema.cpp:401-403 does ((unsigned char) of the float: truncation) and its
+//                  inversion (InvertImageAndHistogram, sortPixels.cpp:131-153); the trees of BOTH polarities of the tile are built in
+//                  shared memory by connect() over the tile's inner edges, all threads at once; written out as global words
+// k_mtree_borders  connect() over the edges that cross tile borders (3 % of all edges), one thread each, on the global words
+// k_mtree_canon    canonical parent of every pixel, own area / inner-edge count of every node, representatives listed per level
+// k_mtree_accum    areas and edge counts summed up the tree, one level per step (one cooperative launch, a grid barrier per level)
+// Words: 32 bit (level << 24 | pixel index inside its image) up to 2^24 pixels per image, else 64 bit (level << 32 | index).
+typedef mser_tree::KeyT<uint32_t, 24> GKey32;
+typedef mser_tree::KeyT<unsigned long long, 32> GKey64;
+typedef mser_tree::KeyT<uint32_t, 12> TKey;      // inside a tile: 4096 elements
+#define MT_TILE 64
+#define MT_THREADS 256
 
-// ---- 1. preparation ------------------------------------------------------------------------------------------------
-// float -> u8 as extrema.cpp:401-403 does ((unsigned char) of the float: truncation); second half = inverted image
-// (InvertImageAndHistogram, sortPixels.cpp:131-153)
+struct SmemWords {
+  uint32_t* w;
+  __device__ __forceinline__ uint32_t load(uint32_t i) { return *(volatile uint32_t*)(w + i); }
+  __device__ __forceinline__ void store(uint32_t i, uint32_t v) { *(volatile uint32_t*)(w + i) = v; }
+  __device__ __forceinline__ bool cas(uint32_t i, uint32_t expect, uint32_t desired) { return atomicCAS(w + i, expect, desired) == expect; }
+};
+template <class WordT>
+struct GmemWords {   // L2-coherent accesses: a stale L1 line would make a failed compare-and-swap repeat forever
+  WordT* w;
+  __device__ __forceinline__ WordT load(uint32_t i) { return __ldcg(w + i); }
+  __device__ __forceinline__ void store(uint32_t i, WordT v) { __stcg(w + i, v); }
+  __device__ __forceinline__ bool cas(uint32_t i, WordT expect, WordT desired) { return atomicCAS(w + i, expect, desired) == expect; }
+};
+
 struct MserImages { const float* p[4]; int pitch[4]; int n; };   // same-size images processed together (a pair: n = 2)
-__global__ void k_mser_prep(MserImages im, int W, int H, uint8_t* __restrict__ lev,
-                            zp_t* __restrict__ zpar, uint32_t* __restrict__ parent, uint32_t* __restrict__ area,
-                            uint32_t* __restrict__ order_in, MserCounters* __restrict__ C) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t N = (uint32_t)W * H;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N * im.n; i += gridDim.x * blockDim.x) {
-    const uint32_t k = i / N, pi = i - k * N;
-    const int y = pi / W, x = pi - y * W;
-    const int v = ((int)im.p[k][(size_t)y * im.pitch[k] + x]) & 0xff;
-    const uint32_t a = 2 * k * N + pi, j = a + N;
-    lev[a] = (uint8_t)v; zpar[a] = zp_make(a, v); parent[a] = a; area[a] = 1; order_in[a] = a;
-    lev[j] = (uint8_t)(255 - v); zpar[j] = zp_make(j, 255 - v); parent[j] = j; area[j] = 1; order_in[j] = j;
-    atomicAdd(&h[v], 1u); atomicAdd(&h[255 - v], 1u);
+
+template <class GK>
+__global__ void __launch_bounds__(MT_THREADS) k_mtree_tiles(MserImages im, int W, int H, uint8_t* __restrict__ lev, typename GK::word* __restrict__ gpar,
+                                                            MserCounters* __restrict__ C) {
+  __shared__ uint32_t par[2][MT_TILE * MT_TILE];
+  __shared__ uint32_t hist[256];
+  __shared__ uint8_t sv[MT_TILE * MT_TILE];
+  const int k = blockIdx.z, x0 = blockIdx.x * MT_TILE, y0 = blockIdx.y * MT_TILE;
+  const int tw = min(MT_TILE, W - x0), th = min(MT_TILE, H - y0);
+  const uint32_t Nimg = (uint32_t)W * H;
+  hist[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    int v = 0;
+    if (lx < tw && ly < th) v = ((int)im.p[k][(size_t)(y0 + ly) * im.pitch[k] + x0 + lx]) & 0xff;
+    par[0][i] = TKey::make(v, i); par[1][i] = TKey::make(255 - v, i); sv[i] = (uint8_t)v;
   }
   __syncthreads();
-  if (h[threadIdx.x]) atomicAdd(&C->hist[threadIdx.x], h[threadIdx.x]);
-  if (blockIdx.x == 0 && threadIdx.x == 0) C->n_stack = 2 * im.n;
+  // Merge order: pixel pairs first, then 2 x 1 blocks into 2 x 2, ... up to the two halves of the tile (12 stages).  A stage only joins
+  // trees that are complete inside their blocks, so the one full walk up two root paths ("zipping") that every join of two trees
+  // costs happens mostly while the trees are tiny; the other pixel pairs of a block border find their paths already merged.
+  // (All edges at once, in arbitrary order, is the same tree but ~20 x the work: 6.1 ms instead of 0.3 ms per 4096 x 3072 image.)
+  for (int s = 0; s < 12; s++) {
+    const bool horiz = !(s & 1);
+    const int b = 1 << (s >> 1), per_line = (MT_TILE / 2) / b, ntask = 2 * MT_TILE * per_line;
+    for (int t = threadIdx.x; t < ntask; t += MT_THREADS) {
+      const int pol = t & 1, u = t >> 1, line = u / per_line, c = (2 * (u - line * per_line) + 1) * b - 1;
+      const int lx = horiz ? c : line, ly = horiz ? line : c;
+      if ((horiz ? lx + 1 : lx) >= tw || (horiz ? ly : ly + 1) >= th) continue;
+      const int i = ly * MT_TILE + lx, j = horiz ? i + 1 : i + MT_TILE;
+      const int vi = pol ? 255 - sv[i] : sv[i], vj = pol ? 255 - sv[j] : sv[j];   // the word of i may already point elsewhere: its own level is the image value
+      SmemWords m{par[pol]};
+      mser_tree::connect<TKey>(m, TKey::make(vi, i), TKey::make(vj, j));
+    }
+    __syncthreads();
+  }
+  // write-out: tile-local index -> index inside the image; sub-image 2k = MSER+, 2k + 1 = MSER-
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    if (lx >= tw || ly >= th) continue;
+    const uint32_t pi = (uint32_t)(y0 + ly) * W + x0 + lx;
+#pragma unroll
+    for (int pol = 0; pol < 2; pol++) {
+      const uint32_t w = par[pol][i];
+      const uint32_t j = TKey::idx(w);
+      const uint32_t pj = (uint32_t)(y0 + (j >> 6)) * W + x0 + (j & (MT_TILE - 1));
+      const size_t a = (size_t)(2 * k + pol) * Nimg + pi;
+      gpar[a] = GK::make(TKey::lev(w), pj);
+    }
+    const int v = sv[i];
+    lev[(size_t)(2 * k) * Nimg + pi] = (uint8_t)v; lev[(size_t)(2 * k + 1) * Nimg + pi] = (uint8_t)(255 - v);
+    atomicAdd(&hist[v], 1u); atomicAdd(&hist[255 - v], 1u);
+  }
+  __syncthreads();
+  if (hist[threadIdx.x]) atomicAdd(&C->hist[threadIdx.x], hist[threadIdx.x]);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) C->n_stack = 2 * im.n;
 }
 __global__ void k_mser_offsets(MserCounters* C) {
   if (threadIdx.x || blockIdx.x) return;
   uint32_t s = 0;
   for (int i = 0; i < 256; i++) { C->lvl_off[i] = s; s += C->hist[i]; }
   C->lvl_off[256] = s;
-  C->hook_off[0] = 0;
 }
 
-// ---- 2. component tree, one level per launch pair ---------------------------------------------------------------------
-// A pixel joins every 4-neighbour that the reference has already labelled when it reaches the pixel: lower level, or the
-// same level and earlier in raster order (getExtrema.cpp:216-263).  nedge[p] counts them (border_num / 2).
-// The phase is latency bound (a chain of dependent L2 reads per pixel), so the four neighbour roots are chased together
-// and de-duplicated before anything is hooked; lanes of a warp hold raster neighbours of one level and mostly want to hook
-// the SAME lower root: one lane per distinct root issues the CAS, the others continue from its outcome.
-__device__ __forceinline__ void mser_union_phase(int L, int W, int H, const uint32_t* __restrict__ order, zp_t* zpar,
-                             uint32_t* __restrict__ nedge, uint32_t* __restrict__ hooked, MserCounters* C) {
-  const uint32_t beg = C->lvl_off[L], end = C->lvl_off[L + 1];
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t base = beg + warp * 32; base < end; base += nwarps * 32) {
-    const uint32_t k = base + lane;
-    uint32_t hk[4]; int cnt = 0;
-    const bool act = k < end;
-    uint32_t p = 0, r[4]; int rl[4] = {0, 0, 0, 0}; bool valid[4] = {false, false, false, false};
-    if (act) {
-      p = order[k];
-      const int yy = p / W, x = p - yy * W, y = yy % H;
-      uint32_t q[4] = {p - W, p - 1, p + 1, p + W};
-      valid[0] = y > 0; valid[1] = x > 0; valid[2] = x < W - 1; valid[3] = y < H - 1;
-      zp_t zq[4];
-#pragma unroll
-      for (int d = 0; d < 4; d++) zq[d] = valid[d] ? __ldca(zpar + q[d]) : zp_make(q[d], 256);   // level and pointer of a neighbour in one access
-      uint32_t e = 0;
-      bool moving = false;
-#pragma unroll
-      for (int d = 0; d < 4; d++) {
-        const int lq = zp_lev(zq[d]);
-        valid[d] = lq < L || (lq == L && q[d] < p); e += valid[d] ? 1u : 0u;
-        r[d] = q[d]; rl[d] = lq;
-        if (valid[d] && zp_ptr(zq[d]) != q[d]) { r[d] = zp_ptr(zq[d]); moving = true; }
-      }
-      nedge[p] = e;
-      // the (up to) four root searches advance together: independent loads in flight instead of four serial chains
-      while (moving) {
-        zp_t z[4];
-#pragma unroll
-        for (int d = 0; d < 4; d++) z[d] = valid[d] ? __ldca(zpar + r[d]) : zp_make(r[d], 0);
-        moving = false;
-#pragma unroll
-        for (int d = 0; d < 4; d++) if (valid[d]) { rl[d] = zp_lev(z[d]); if (zp_ptr(z[d]) != r[d]) { r[d] = zp_ptr(z[d]); moving = true; } }
-      }
-#pragma unroll
-      for (int d = 0; d < 4; d++) if (valid[d] && r[d] != q[d]) zp_set_ptr(zpar + q[d], r[d]);   // compress the start of the path
-      if (valid[1] && valid[0] && r[1] == r[0]) valid[1] = false;
-      if (valid[2] && ((valid[0] && r[2] == r[0]) || (valid[1] && r[2] == r[1]))) valid[2] = false;
-      if (valid[3] && ((valid[0] && r[3] == r[0]) || (valid[1] && r[3] == r[1]) || (valid[2] && r[3] == r[2]))) valid[3] = false;
-    }
-    // distinct roots packed to the front: most pixels have one, so the warp-synchronous rounds below are one or two, not four
-    uint32_t rr[4]; int rrl[4]; int nr = 0;
-#pragma unroll
-    for (int d = 0; d < 4; d++) if (valid[d]) { rr[nr] = r[d]; rrl[nr] = rl[d]; nr++; }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      bool pend = act && j < nr;
-      if (!__ballot_sync(0xffffffffu, pend)) break;
-      uint32_t ra = 0, rb = 0; int la = 0, lb = 0;
-      if (pend) { ra = uf_find<false>(zpar, p, &la); rb = rr[j]; lb = rrl[j]; }
-      for (;;) {
-        if (pend) {
-          if (ra == rb) pend = false;
-          else if (key_less(lb, rb, la, ra)) { const uint32_t t = ra; ra = rb; rb = t; const int tl = la; la = lb; lb = tl; }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, pend);
-        if (!m) break;
-        if (pend) {
-          const unsigned grp = __match_any_sync(m, ra);
-          const int leader = __ffs(grp) - 1;
-          const zp_t expect = zp_make(ra, la);   // the level of ra is the same in every lane that holds ra
-          zp_t old = 0;
-          if (lane == leader) old = atomicCAS(zpar + ra, expect, zp_make(rb, la));
-          old = __shfl_sync(grp, old, leader);
-          const uint32_t rb_lead = __shfl_sync(grp, rb, leader);
-          if (old == expect) {                   // ra now hangs under the leader's rb
-            if (lane == leader) { hk[cnt++] = ra; pend = false; }
-            else ra = uf_find<false>(zpar, rb_lead, &la);
-          } else ra = uf_find<false>(zpar, zp_ptr(old), &la);  // somebody else hooked ra first: go on from its true parent
-        }
-      }
-    }
-    __syncwarp();
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t b0 = 0;
-    if (lane == 31 && tot) b0 = atomicAdd(&C->hook_cnt, (uint32_t)tot);
-    b0 = __shfl_sync(0xffffffffu, b0, 31);
-    for (int j = 0; j < cnt; j++) hooked[b0 + incl - cnt + j] = hk[j];
+// edges across tile borders: first the horizontal borders (pixel pairs (x, y - 1) / (x, y) with y a multiple of the tile size: threads
+// run along x), then the vertical ones
+template <class GK>
+__global__ void __launch_bounds__(256) k_mtree_borders(int W, int H, int n_sub, const uint8_t* __restrict__ lev, typename GK::word* gpar) {
+  const uint32_t Nimg = (uint32_t)W * H;
+  const uint32_t nh = (uint32_t)((H - 1) / MT_TILE) * W, nv = (uint32_t)((W - 1) / MT_TILE) * H, per = nh + nv;
+  const unsigned long long total = (unsigned long long)per * n_sub;
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t sub = (uint32_t)(t / per), e = (uint32_t)(t - (unsigned long long)sub * per);
+    uint32_t p, q;
+    if (e < nh) { const uint32_t b = e / W, x = e - b * W; q = (b + 1) * MT_TILE * W + x; p = q - W; }
+    else { const uint32_t f = e - nh, b = f / H, y = f - b * H; q = y * W + (b + 1) * MT_TILE; p = q - 1; }
+    const uint8_t* l = lev + (size_t)sub * Nimg;
+    GmemWords<typename GK::word> m{gpar + (size_t)sub * Nimg};
+    mser_tree::connect<GK>(m, GK::make(l[p], p), GK::make(l[q], q));
   }
 }
-// Every element hooked during level L now learns its canonical parent (the representative of the level-L node) and hands
-// its totals over; lanes that share a representative combine first.
-__device__ __forceinline__ void mser_final_phase(int L, zp_t* zpar, uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge,
-                             const uint32_t* __restrict__ hooked, MserCounters* C, uint32_t beg, uint32_t end) {
+
+// canonical parents, own counts, representatives per level.  nedge of a pixel = 4-neighbours the reference has already labelled when it
+// reaches the pixel: lower level, or the same level and earlier in raster order (getExtrema.cpp:216-263); summed over a component it
+// counts the pixel pairs inside, so that the reference's border count (+4 - 2 x labelled neighbours per pixel) is 4 area - 2 edges.
+template <class GK>
+__global__ void __launch_bounds__(256) k_mtree_canon(int W, int H, uint32_t N, const uint8_t* __restrict__ lev, typename GK::word* gpar,
+                                                     uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge, uint32_t* __restrict__ nodes,
+                                                     MserCounters* C) {
+  const uint32_t Nimg = (uint32_t)W * H;
   const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t base = beg + warp * 32; base < end; base += nwarps * 32) {
-    const uint32_t i = base + lane;
-    const bool act = i < end;
+  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < N; base += gridDim.x * blockDim.x) {
+    const uint32_t x = base + lane;
+    const bool act = x < N;
+    uint32_t r = 0, e = 0; int L = 0; bool rep = false;
+    if (act) {
+      const uint32_t sub = x / Nimg, pi = x - sub * Nimg, off = sub * Nimg;
+      L = lev[x];
+      GmemWords<typename GK::word> m{gpar + (size_t)off};
+      const typename GK::word ck = mser_tree::canonical_parent<GK>(m, GK::make(L, pi));
+      const uint32_t cp = off + GK::idx(ck);
+      parent[x] = cp;
+      rep = cp == x || GK::lev(ck) > L;
+      r = rep ? x : cp;
+      const int y = pi / W, xx = pi - y * W;
+      const uint8_t* l = lev + off;
+      if (y > 0) { const int lq = l[pi - W]; e += lq <= L; }                    // q < p: lower or equal level counts
+      if (xx > 0) { const int lq = l[pi - 1]; e += lq <= L; }
+      if (xx < W - 1) { const int lq = l[pi + 1]; e += lq < L; }                // q > p: strictly lower level only
+      if (y < H - 1) { const int lq = l[pi + W]; e += lq < L; }
+    }
     const unsigned mask = __ballot_sync(0xffffffffu, act);
     if (act) {
-      const uint32_t x = hooked[i];
-      const uint32_t r = uf_find<false>(zpar, x);   // no hooking during this kernel: every pointer read is a valid ancestor
-      parent[x] = r;
-      const uint32_t a = area[x], e = nedge[x];
       const unsigned grp = __match_any_sync(mask, r);
-      const uint32_t sa = __reduce_add_sync(grp, a), se = __reduce_add_sync(grp, e);
-      if (lane == __ffs(grp) - 1) { atomicAdd(area + r, sa); atomicAdd(nedge + r, se); }
+      const uint32_t se = __reduce_add_sync(grp, e);
+      if (lane == __ffs(grp) - 1) { atomicAdd(area + r, (uint32_t)__popc(grp)); if (se) atomicAdd(nedge + r, se); }
+    }
+    const unsigned reps = __ballot_sync(0xffffffffu, act && rep);
+    if (act && rep) {
+      const unsigned grp = __match_any_sync(reps, L);
+      uint32_t b0 = 0;
+      const int leader = __ffs(grp) - 1;
+      if (lane == leader) b0 = atomicAdd(&C->lvl_cnt[L], (uint32_t)__popc(grp));
+      b0 = __shfl_sync(grp, b0, leader);
+      nodes[C->lvl_off[L] + b0 + __popc(grp & ((1u << lane) - 1))] = x;
     }
   }
 }
-// The whole tree in ONE cooperative launch: levels in order, a grid barrier between the hooking phase and the hand-over
-// phase of every non-empty level (two launches per level would cost more than the levels themselves).
-__global__ void __launch_bounds__(256) k_mser_tree(int W, int H, const uint8_t* __restrict__ lev, const uint32_t* __restrict__ order, zp_t* zpar,
-                                                   uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge, uint32_t* __restrict__ hooked, MserCounters* C,
-                                                   unsigned long long* dbg /* optional: 3 x 256 phase time stamps (ns) */) {
+
+__global__ void __launch_bounds__(512) k_mtree_accum(const uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge, const uint32_t* __restrict__ nodes,
+                                                     const MserCounters* __restrict__ C) {
   cg::grid_group grid = cg::this_grid();
-  uint32_t hook_beg = 0;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   for (int L = 0; L < 256; L++) {
-    if (C->lvl_off[L] == C->lvl_off[L + 1]) { if (blockIdx.x == 0 && threadIdx.x == 0) C->hook_off[L + 1] = hook_beg; continue; }
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L] = t; }
-    mser_union_phase(L, W, H, order, zpar, nedge, hooked, C);
+    const uint32_t n = C->lvl_cnt[L], off = C->lvl_off[L];
+    if (n == 0) continue;                        // the same decision in every thread: the counts are final before the launch
+    for (uint32_t base = tid & ~31u; base < n; base += nthreads) {
+      const uint32_t i = base + lane;
+      const bool act = i < n;
+      uint32_t v = 0, p = 0;
+      if (act) { v = nodes[off + i]; p = parent[v]; }
+      const bool push = act && p != v;
+      const unsigned mask = __ballot_sync(0xffffffffu, push);
+      if (push) {
+        const uint32_t a = __ldcg(area + v), e = __ldcg(nedge + v);
+        const unsigned grp = __match_any_sync(mask, p);
+        const uint32_t sa = __reduce_add_sync(grp, a), se = __reduce_add_sync(grp, e);
+        if (lane == __ffs(grp) - 1) { atomicAdd(area + p, sa); atomicAdd(nedge + p, se); }
+      }
+    }
     grid.sync();
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L + 1] = t; }
-    const uint32_t hook_end = *(volatile uint32_t*)&C->hook_cnt;
-    if (blockIdx.x == 0 && threadIdx.x == 0) C->hook_off[L + 1] = hook_end;
-    mser_final_phase(L, zpar, parent, area, nedge, hooked, C, hook_beg, hook_end);
-    hook_beg = hook_end;
-    grid.sync();
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[3 * L + 2] = t; }
-  }
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    for (uint32_t i = 0; i < C->n_stack; i++) C->root[i] = uf_find<true>(zpar, i * (uint32_t)W * H);
-    C->hook_off[257] = hook_beg;
   }
 }
 
@@ -632,57 +609,46 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
   MB2_CUDA_CHECK(ctx, B.h_counters.reserve(sizeof(MserCounters)));
   MserCounters* dC = B.counters.as<MserCounters>();
   MserCounters* hc = B.h_counters.as<MserCounters>();
-  MB2_CUDA_CHECK(ctx, B.lev.reserve(N)); MB2_CUDA_CHECK(ctx, B.keys8.reserve(N));
-  MB2_CUDA_CHECK(ctx, B.zpar.reserve((size_t)N * 8));   // pointer + level per element (zp_t)
-  DevBuf* u32bufs[] = {&B.parent, &B.area, &B.nedge, &B.order, &B.order_in, &B.hooked, &B.surv, &B.birth, &B.slot_of_node, &B.sa};
+  const bool wide = Nimg > (1u << 24);          // 64-bit tree words above 2^24 pixels per image
+  MB2_CUDA_CHECK(ctx, B.lev.reserve(N));
+  MB2_CUDA_CHECK(ctx, B.gpar.reserve((size_t)N * (wide ? 8 : 4)));
+  DevBuf* u32bufs[] = {&B.parent, &B.area, &B.nedge, &B.nodes, &B.surv, &B.birth, &B.slot_of_node, &B.sa};
   for (DevBuf* b : u32bufs) MB2_CUDA_CHECK(ctx, b->reserve((size_t)N * 4));
   MB2_CUDA_CHECK(ctx, B.best.reserve((size_t)N * 8));
   MB2_CUDA_CHECK(ctx, B.flag.reserve(N));
   uint8_t* lev = B.lev.as<uint8_t>();
-  zp_t* zpar = B.zpar.as<zp_t>();
-  uint32_t *parent = B.parent.as<uint32_t>(), *area = B.area.as<uint32_t>(), *nedge = B.nedge.as<uint32_t>();
-  uint32_t *order = B.order.as<uint32_t>(), *order_in = B.order_in.as<uint32_t>(), *hooked = B.hooked.as<uint32_t>();
+  uint32_t *parent = B.parent.as<uint32_t>(), *area = B.area.as<uint32_t>(), *nedge = B.nedge.as<uint32_t>(), *nodes = B.nodes.as<uint32_t>();
   uint32_t *surv = B.surv.as<uint32_t>(), *birth = B.birth.as<uint32_t>(), *slot_of_node = B.slot_of_node.as<uint32_t>(), *sa = B.sa.as<uint32_t>();
 
-  // 1. u8 images, histogram, (level, raster) order
+  // 1 + 2. component trees: tiles in shared memory, tile borders in global memory, canonical form, attributes up the tree
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(dC, 0, sizeof(MserCounters), st));
-  MB2_LAUNCH(ctx, k_mser_prep, grid_for(Nimg * K, 256, G), 256, 0, mi, W, H, lev, zpar, parent, area, order_in, dC);
-  MB2_LAUNCH(ctx, k_mser_offsets, 1, 32, 0, dC);
+  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(area, 0, (size_t)N * 4, st));
+  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(nedge, 0, (size_t)N * 4, st));
   {
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, lev, B.keys8.as<uint8_t>(), order_in, order, (int)N, 0, 8, st);
-    MB2_CUDA_CHECK(ctx, B.cub_tmp.reserve(tmp));
-    cub::DeviceRadixSort::SortPairs(B.cub_tmp.p, tmp, lev, B.keys8.as<uint8_t>(), order_in, order, (int)N, 0, 8, st);
-    ctx->launches += 3;
-  }
-  // 2. component trees
-  {
+    const dim3 tg((W + MT_TILE - 1) / MT_TILE, (H + MT_TILE - 1) / MT_TILE, K);
+    const unsigned long long n_border = ((unsigned long long)((H - 1) / MT_TILE) * W + (unsigned long long)((W - 1) / MT_TILE) * H) * 2 * K;
+    const int bg = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_border + 255) / 256, (unsigned long long)ctx->num_sms * 64));
+    if (wide) {
+      MB2_LAUNCH(ctx, k_mtree_tiles<GKey64>, tg, MT_THREADS, 0, mi, W, H, lev, B.gpar.as<unsigned long long>(), dC);
+      MB2_LAUNCH(ctx, k_mser_offsets, 1, 32, 0, dC);
+      if (n_border) MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, B.gpar.as<unsigned long long>());
+      MB2_LAUNCH(ctx, k_mtree_canon<GKey64>, grid_for(N, 256, G), 256, 0, W, H, N, lev, B.gpar.as<unsigned long long>(), parent, area, nedge, nodes, dC);
+    } else {
+      MB2_LAUNCH(ctx, k_mtree_tiles<GKey32>, tg, MT_THREADS, 0, mi, W, H, lev, B.gpar.as<uint32_t>(), dC);
+      MB2_LAUNCH(ctx, k_mser_offsets, 1, 32, 0, dC);
+      if (n_border) MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, B.gpar.as<uint32_t>());
+      MB2_LAUNCH(ctx, k_mtree_canon<GKey32>, grid_for(N, 256, G), 256, 0, W, H, N, lev, B.gpar.as<uint32_t>(), parent, area, nedge, nodes, dC);
+    }
     int occ = 0;
-    MB2_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mser_tree, 256, 0));
-    static const int gmul = getenv("MB2_MSER_GRID") ? atoi(getenv("MB2_MSER_GRID")) : 4;   // CTAs per SM of the persistent kernel
-    const int Gc = ctx->num_sms * std::max(1, std::min(occ, gmul));   // co-resident by construction
-    int Wv = W, Hv = H;
-    static const bool level_prof = getenv("MB2_MSER_LEVEL_PROF") != nullptr;   // diagnostics: per-level phase times to stderr
-    unsigned long long* dbg = nullptr;
-    if (level_prof) { MB2_CUDA_CHECK(ctx, B.table.reserve(3 * 256 * 8)); dbg = B.table.as<unsigned long long>(); cudaMemsetAsync(dbg, 0, 3 * 256 * 8, st); }
-    void* args[] = {&Wv, &Hv, &lev, &order, &zpar, &parent, &area, &nedge, &hooked, &dC, &dbg};
-    mb2_ctx::ProfRec pr{"k_mser_tree", nullptr, nullptr};
+    MB2_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mtree_accum, 512, 0));
+    const int Gc = ctx->num_sms * std::max(1, std::min(occ, 2));   // co-resident by construction; few CTAs keep the grid barrier cheap
+    void* args[] = {&parent, &area, &nedge, &nodes, &dC};
+    mb2_ctx::ProfRec pr{"k_mtree_accum", nullptr, nullptr};
     if (ctx->profiling) { cudaEventCreate(&pr.a); cudaEventCreate(&pr.b); cudaEventRecord(pr.a, st); }
-    MB2_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_mser_tree, dim3(Gc), dim3(256), args, 0, st));
+    MB2_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_mtree_accum, dim3(Gc), dim3(512), args, 0, st));
     if (ctx->profiling) { cudaEventRecord(pr.b, st); ctx->prof.push_back(pr); }
     ctx->launches++;
     if (ctx->ev_tree) { cudaEventRecord(ctx->ev_tree, st); __sync_synchronize(); ctx->tree_epoch = ctx->tree_epoch + 1; }
-    if (level_prof) {
-      std::vector<unsigned long long> t(3 * 256); std::vector<uint32_t> hist(256);
-      cudaMemcpyAsync(t.data(), dbg, 3 * 256 * 8, cudaMemcpyDeviceToHost, st);
-      cudaMemcpyAsync(hist.data(), &dC->hist[0], 256 * 4, cudaMemcpyDeviceToHost, st);
-      cudaStreamSynchronize(st);
-      double tu = 0, tf = 0;
-      for (int L = 0; L < 256; L++) if (t[3 * L]) { tu += (t[3 * L + 1] - t[3 * L]) * 1e-3; tf += (t[3 * L + 2] - t[3 * L + 1]) * 1e-3; }
-      fprintf(stderr, "[mser] grid %d x 256: union %.0f us, final %.0f us; per level (pixels: union us / final us):", Gc, tu, tf);
-      for (int L = 0; L < 256; L++) if (t[3 * L]) fprintf(stderr, " L%d(%u: %.0f/%.0f)", L, hist[L], (t[3 * L + 1] - t[3 * L]) * 1e-3, (t[3 * L + 2] - t[3 * L + 1]) * 1e-3);
-      fprintf(stderr, "\n");
-    }
   }
   // 3. survivors
   TreeDev td{W, H, lev, parent, area, nedge, track_size};

@@ -15,7 +15,7 @@
 //
 // The same code runs on a 64 x 64 tile in shared memory (all edges inside the tile), on the tile borders in global memory, and --
 // compiled for the host by tests/native/mser_tree_cpu.cpp -- sequentially and on several host threads in the logic tests.
-// `Mem` supplies: uint32_t load(uint32_t idx); bool cas(uint32_t idx, uint32_t expect, uint32_t desired); void store(uint32_t idx, uint32_t w).
+// `Mem` supplies: word load(uint32_t idx); bool cas(uint32_t idx, word expect, word desired); void store(uint32_t idx, word w).
 #pragma once
 #include <stdint.h>
 
@@ -29,20 +29,23 @@
 
 namespace mser_tree {
 
-template <int IDX_BITS>
-struct Key {
-  static MB2_HD uint32_t make(int lev, uint32_t idx) { return ((uint32_t)lev << IDX_BITS) | idx; }
-  static MB2_HD int lev(uint32_t k) { return (int)(k >> IDX_BITS); }
-  static MB2_HD uint32_t idx(uint32_t k) { return k & ((1u << IDX_BITS) - 1u); }
+// 32-bit words hold images up to 2^24 pixels (level in the top byte); larger images use 64-bit words (KeyT<unsigned long long, 32>)
+template <class WordT, int IDX_BITS>
+struct KeyT {
+  typedef WordT word;
+  static MB2_HD WordT make(int lev, uint32_t idx) { return ((WordT)(uint32_t)lev << IDX_BITS) | (WordT)idx; }
+  static MB2_HD int lev(WordT k) { return (int)(k >> IDX_BITS); }
+  static MB2_HD uint32_t idx(WordT k) { return (uint32_t)(k & (((WordT)1 << IDX_BITS) - (WordT)1)); }
 };
+template <int IDX_BITS> using Key = KeyT<uint32_t, IDX_BITS>;
 
 // representative (level root) of x's node at this moment; xk = key of x
 template <class K, class Mem>
-MB2_HD uint32_t levroot(Mem& m, uint32_t xk) {
+MB2_HD typename K::word levroot(Mem& m, typename K::word xk) {
   for (;;) {
-    const uint32_t w = m.load(K::idx(xk));
+    const typename K::word w = m.load(K::idx(xk));
     if (w == xk || K::lev(w) != K::lev(xk)) return xk;
-    const uint32_t ww = m.load(K::idx(w));
+    const typename K::word ww = m.load(K::idx(w));
     if (ww == w || K::lev(ww) != K::lev(xk)) return w;   // w is a level root
     m.store(K::idx(xk), ww);                              // path halving: xk is not a level root, so nobody swaps its word
     xk = ww;
@@ -50,12 +53,12 @@ MB2_HD uint32_t levroot(Mem& m, uint32_t xk) {
 }
 
 template <class K, class Mem>
-MB2_HD void connect(Mem& m, uint32_t ak, uint32_t bk) {
-  uint32_t x = levroot<K>(m, ak), y = levroot<K>(m, bk);
+MB2_HD void connect(Mem& m, typename K::word ak, typename K::word bk) {
+  typename K::word x = levroot<K>(m, ak), y = levroot<K>(m, bk);
   for (;;) {
     if (x == y) return;
-    if (x > y) { const uint32_t t = x; x = y; y = t; }
-    const uint32_t z = m.load(K::idx(x));
+    if (x > y) { const typename K::word t = x; x = y; y = t; }
+    const typename K::word z = m.load(K::idx(x));
     const bool self = z == x;
     if (!self && K::lev(z) == K::lev(x)) { x = levroot<K>(m, x); continue; }    // x stopped being a level root
     if (K::lev(x) == K::lev(y)) {                // one node: x goes under y, x's parent becomes y's obligation
@@ -73,16 +76,16 @@ MB2_HD void connect(Mem& m, uint32_t ak, uint32_t bk) {
 // after all connects: canonical parent of x as mser_logic.cuh defines it -- the representative of x's node if x is not one, else the
 // representative of the parent node (the root: itself).  Returns a KEY.
 template <class K, class Mem>
-MB2_HD uint32_t canonical_parent(Mem& m, uint32_t xk) {
-  uint32_t r = xk;
+MB2_HD typename K::word canonical_parent(Mem& m, typename K::word xk) {
+  typename K::word r = xk;
   for (;;) {
-    const uint32_t w = m.load(K::idx(r));
+    const typename K::word w = m.load(K::idx(r));
     if (w == r) return r == xk ? xk : r;
     if (K::lev(w) != K::lev(r)) {
       if (r != xk) return r;
       r = w;                                     // xk is the representative: continue inside the parent node
       for (;;) {
-        const uint32_t v = m.load(K::idx(r));
+        const typename K::word v = m.load(K::idx(r));
         if (v == r || K::lev(v) != K::lev(r)) return r;
         r = v;
       }

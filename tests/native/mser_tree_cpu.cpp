@@ -9,11 +9,30 @@
 #include <cstring>
 #include <vector>
 
+#include <atomic>
+#include <random>
+#include <thread>
+
 #include "../../mods_b200/csrc/mser_logic.cuh"
+#include "../../mods_b200/csrc/mser_tree_build.cuh"
 
 using namespace mser_logic;
 
+// how the tree is built: 0 = level-by-level union-find (the original sequential builder), 1 = the lock-free merge of
+// mser_tree_build.cuh run sequentially (tiles first, then tile borders, edges in a seeded random order), 2 = the same on several host
+// threads at once (real compare-and-swap races), every edge in random order
+static int g_mode = 0, g_tile = 64, g_threads = 4; static unsigned g_seed = 1;
+extern "C" void mser_tree_set_mode(int mode, int tile, int threads, unsigned seed) { g_mode = mode; g_tile = tile; g_threads = threads; g_seed = seed; }
+
 namespace {
+struct HostMem {   // plain words, or real atomics when several threads run
+  uint32_t* w;
+  uint32_t load(uint32_t i) { return __atomic_load_n(w + i, __ATOMIC_RELAXED); }
+  void store(uint32_t i, uint32_t v) { __atomic_store_n(w + i, v, __ATOMIC_RELAXED); }
+  bool cas(uint32_t i, uint32_t expect, uint32_t desired) { return __atomic_compare_exchange_n(w + i, &expect, desired, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED); }
+};
+typedef mser_tree::Key<24> K24;
+
 struct Build {
   int W, H, N;
   std::vector<uint8_t> lev;
@@ -24,7 +43,56 @@ struct Build {
     return x;
   }
   bool less(uint32_t a, uint32_t b) const { return lev[a] < lev[b] || (lev[a] == lev[b] && a > b); }  // same hooking order as mser.cu
+  // the lock-free merge: par words, canonical parents, then own counts summed up the tree level by level (as mser.cu does)
+  void run_merge() {
+    N = W * H;
+    std::vector<uint32_t> par(N);
+    for (int i = 0; i < N; i++) par[i] = K24::make(lev[i], (uint32_t)i);
+    HostMem m{par.data()};
+    struct E { uint32_t a, b; };
+    std::vector<E> inner, border;
+    for (int y = 0; y < H; y++)
+      for (int x = 0; x < W; x++) {
+        const uint32_t p = (uint32_t)(y * W + x);
+        if (x + 1 < W) ((x + 1) % g_tile == 0 ? border : inner).push_back(E{p, p + 1});
+        if (y + 1 < H) ((y + 1) % g_tile == 0 ? border : inner).push_back(E{p, p + (uint32_t)W});
+      }
+    std::mt19937 rng(g_seed);
+    std::shuffle(inner.begin(), inner.end(), rng); std::shuffle(border.begin(), border.end(), rng);
+    auto key = [&](uint32_t p) { return K24::make(lev[p], p); };
+    auto work = [&](const std::vector<E>& e, int t, int nt) { HostMem mm{par.data()}; for (size_t i = t; i < e.size(); i += nt) mser_tree::connect<K24>(mm, key(e[i].a), key(e[i].b)); };
+    if (g_mode == 1) { work(inner, 0, 1); work(border, 0, 1); }
+    else {
+      for (const std::vector<E>* e : {&inner, &border}) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < g_threads; t++) th.emplace_back(work, std::cref(*e), t, g_threads);
+        for (auto& t : th) t.join();
+      }
+    }
+    parent.resize(N); area.assign(N, 0); nedge.assign(N, 0);
+    for (int i = 0; i < N; i++) parent[i] = K24::idx(mser_tree::canonical_parent<K24>(m, key(i)));
+    std::vector<std::vector<uint32_t>> by_level(256);
+    for (int p = 0; p < N; p++) {
+      const bool rep = parent[p] == (uint32_t)p || lev[parent[p]] > lev[p];
+      const uint32_t r = rep ? (uint32_t)p : parent[p];
+      if (rep) by_level[lev[p]].push_back(p);
+      const int x = p % W, y = p / W;
+      uint32_t e = 0;
+      const int dx[4] = {0, -1, 1, 0}, dy[4] = {-1, 0, 0, 1};
+      for (int d = 0; d < 4; d++) {
+        const int qx = x + dx[d], qy = y + dy[d];
+        if (qx < 0 || qy < 0 || qx >= W || qy >= H) continue;
+        const uint32_t q = qy * W + qx;
+        if (lev[q] < lev[p] || (lev[q] == lev[p] && q < (uint32_t)p)) e++;
+      }
+      area[r] += 1; nedge[r] += e;
+    }
+    for (int L = 0; L < 256; L++)
+      for (uint32_t v : by_level[L]) if (parent[v] != v) { area[parent[v]] += area[v]; nedge[parent[v]] += nedge[v]; }
+    root = 0; while (parent[root] != root) root = parent[root];
+  }
   void run() {
+    if (g_mode != 0) { run_merge(); return; }
     N = W * H;
     zpar.resize(N); parent.resize(N); area.assign(N, 1); nedge.assign(N, 0);
     for (int i = 0; i < N; i++) zpar[i] = parent[i] = i;
@@ -151,6 +219,34 @@ extern "C" int mser_tree_regions(const float* img, int w, int h, double max_area
     }
   }
   return n_out;
+}
+
+// node-level comparison of two builders on one image: for every pixel the (level, area, edge count) of its node and of its parent node
+extern "C" int mser_tree_compare(const float* img, int w, int h, int pol) {
+  const int N = w * h;
+  auto build = [&](int mode) {
+    const int keep = g_mode; g_mode = mode;
+    Build b; b.W = w; b.H = h; b.lev.resize(N);
+    for (int i = 0; i < N; i++) { uint8_t v = (unsigned char)img[i]; b.lev[i] = pol ? (uint8_t)(255 - v) : v; }
+    b.run(); g_mode = keep;
+    return b;
+  };
+  Build a = build(0), b = build(g_mode);
+  int bad = 0;
+  auto sig = [&](Build& t, int p, uint32_t* o) {
+    const bool rep = t.parent[p] == (uint32_t)p || t.lev[t.parent[p]] > t.lev[p];
+    const uint32_t r = rep ? (uint32_t)p : t.parent[p];
+    if (t.lev[r] != t.lev[p]) { o[0] = 0xdeadbeef; return; }
+    const uint32_t pr = t.parent[r];
+    o[0] = t.area[r]; o[1] = t.nedge[r]; o[2] = pr == r ? 256u : t.lev[pr]; o[3] = t.area[pr]; o[4] = t.nedge[pr];
+    o[5] = (pr == r || t.parent[pr] == pr || t.lev[t.parent[pr]] > t.lev[pr]) ? 1u : 0u;   // the parent pointer of a representative names a representative
+  };
+  for (int p = 0; p < N; p++) {
+    uint32_t sa[6] = {0}, sb[6] = {0};
+    sig(a, p, sa); sig(b, p, sb);
+    if (std::memcmp(sa, sb, sizeof sa) != 0 || sb[5] != 1u) bad++;
+  }
+  return bad;
 }
 
 extern "C" void mser_tree_ellipse_to_A(double sxx, double sxy, double syy, double* A) { ellipse_to_A(sxx, sxy, syy, A); }
