@@ -254,7 +254,7 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
     gather_bytes = prof.pop("__extract_gather_bytes__", (1, 0.0))[1]
     tot = sum(v[1] for v in prof.values()) or 1.0
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
-    kernels = [{"kernel": k, "launches": v[0], "ms_per_pair": v[1] / steps, "share": v[1] / tot} for k, v in top[:8]]
+    kernels = [{"kernel": k, "launches": v[0], "ms_per_pair": v[1] / steps, "share": v[1] / tot} for k, v in top[:16]]
     name, (n_launch, ms) = top[0]
     avg_s = ms / 1e3 / max(1, n_launch)
     rl = None

@@ -6,9 +6,10 @@
 // neighbours, so every pass below serves both at once:
 //   1. k_mtree_tiles                 u8 image of both polarities; component tree of every 64 x 64 tile built in shared memory by
 //                                    lock-free merging of all inner pixel pairs at once (mser_tree_build.cuh)         [shared memory]
-//   2. k_mtree_borders / canon /     the same merge over the pixel pairs across tile borders (3 % of the edges) on global words;
-//      accum                         canonical parents + own area / inner-edge counts; sums up the tree, one level per step
-//                                    (nothing is sorted, no barrier per level while the tree is built)     [L2 atomics / HBM streaming]
+//   2. k_mtree_local / borders /     canonical form + area / inner-edge sums of every subtree inside its tile; the same merge over the
+//      fix                           pixel pairs across tile borders (3 % of the edges) on global words; final parents, and the local
+//                                    sums added along the gaps the border merge opened (nothing is sorted, no pass per level)
+//                                                                                                   [L2 atomics / HBM streaming]
 //   3. k_mser_best .. k_mser_emulate survivor of every merge = largest tracked child; nodes where the reference's
 //                                    answer depends on its pixel order (births, equal sizes) are replayed by one
 //                                    thread each (mser_logic.cuh: emulate_node)
@@ -38,11 +39,8 @@ namespace cg = cooperative_groups;
 typedef unsigned long long u64;
 
 struct MserCounters {
-  uint32_t hook_cnt, emu_nodes, own_keys, long_regions, n_sel, n_slots, n_starts, n_ends;
+  uint32_t hook_cnt, n_walk, emu_nodes, own_keys, long_regions, n_sel, n_slots, n_starts, n_ends;
   uint32_t overflow, thr_overflow, cap_overflow, n_stack, root[8], n_img[4];   // n_stack = 2 x images; n_img = regions per image
-  uint32_t hist[256];
-  uint32_t lvl_off[257];
-  uint32_t lvl_cnt[256];   // representatives per level (k_mtree_canon)
 };
 
 struct SelRec {  // one (region, threshold): a row of getRLEExtrema's output
@@ -52,12 +50,12 @@ struct SelRec {  // one (region, threshold): a row of getRLEExtrema's output
 };
 
 struct MserBufs {
-  DevBuf lev, gpar, parent, area, nedge, nodes, best, surv, birth, flag, emu_nodes, own_a, own_b;
+  DevBuf lev, gpar, parent, area, nedge, lsum, hi, best, surv, birth, flag, emu_nodes, own_a, own_b;
   DevBuf uf, esz, epre, eid, ebirth, ekind, longr, sel, sel_sorted, selkey_a, selkey_b, selidx_a, selidx_b, slot_of_node, node_of_slot;
   DevBuf sa, up_sel, ev_a, ev_b, ev_c, ev_d, mom, cub_tmp, counters, table;
   HostBuf h_counters;
   void release() {
-    DevBuf* all[] = {&lev, &gpar, &parent, &area, &nedge, &nodes, &best, &surv, &birth, &flag, &emu_nodes, &own_a,
+    DevBuf* all[] = {&lev, &gpar, &parent, &area, &nedge, &lsum, &hi, &best, &surv, &birth, &flag, &emu_nodes, &own_a,
                      &own_b, &uf, &esz, &epre, &eid, &ebirth, &ekind, &longr, &sel, &sel_sorted, &selkey_a, &selkey_b, &selidx_a, &selidx_b,
                      &slot_of_node, &node_of_slot, &sa, &up_sel, &ev_a, &ev_b, &ev_c, &ev_d, &mom, &cub_tmp, &counters, &table};
     for (DevBuf* b : all) b->release();
@@ -69,9 +67,9 @@ struct MserBufs {
 // k_mtree_tiles    one CTA per 64 x 64 tile: float -> u8 as extrema.cpp:401-403 does ((unsigned char) of the float: truncation) and its
 //                  inversion (InvertImageAndHistogram, sortPixels.cpp:131-153); the trees of BOTH polarities of the tile are built in
 //                  shared memory by connect() over the tile's inner edges, all threads at once; written out as global words
+// k_mtree_local    per (tile, polarity): canonical words, area / inner-edge sums of every subtree inside the tile
 // k_mtree_borders  connect() over the edges that cross tile borders (3 % of all edges), one thread each, on the global words
-// k_mtree_canon    canonical parent of every pixel, own area / inner-edge count of every node, representatives listed per level
-// k_mtree_accum    areas and edge counts summed up the tree, one level per step (one cooperative launch, a grid barrier per level)
+// k_mtree_fix      canonical parent of every pixel in the final tree; local sums added along the gaps the border merge opened
 // Words: 32 bit (level << 24 | pixel index inside its image) up to 2^24 pixels per image, else 64 bit (level << 32 | index).
 typedef mser_tree::KeyT<uint32_t, 24> GKey32;
 typedef mser_tree::KeyT<unsigned long long, 32> GKey64;
@@ -99,12 +97,10 @@ template <class GK>
 __global__ void __launch_bounds__(MT_THREADS) k_mtree_tiles(MserImages im, int W, int H, uint8_t* __restrict__ lev, typename GK::word* __restrict__ gpar,
                                                             MserCounters* __restrict__ C) {
   __shared__ uint32_t par[2][MT_TILE * MT_TILE];
-  __shared__ uint32_t hist[256];
   __shared__ uint8_t sv[MT_TILE * MT_TILE];
   const int k = blockIdx.z, x0 = blockIdx.x * MT_TILE, y0 = blockIdx.y * MT_TILE;
   const int tw = min(MT_TILE, W - x0), th = min(MT_TILE, H - y0);
   const uint32_t Nimg = (uint32_t)W * H;
-  hist[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
     const int lx = i & (MT_TILE - 1), ly = i >> 6;
     int v = 0;
@@ -115,7 +111,8 @@ __global__ void __launch_bounds__(MT_THREADS) k_mtree_tiles(MserImages im, int W
   // Merge order: pixel pairs first, then 2 x 1 blocks into 2 x 2, ... up to the two halves of the tile (12 stages).  A stage only joins
   // trees that are complete inside their blocks, so the one full walk up two root paths ("zipping") that every join of two trees
   // costs happens mostly while the trees are tiny; the other pixel pairs of a block border find their paths already merged.
-  // (All edges at once, in arbitrary order, is the same tree but ~20 x the work: 6.1 ms instead of 0.3 ms per 4096 x 3072 image.)
+  // (Measured at 4096 x 3072, both polarities: all inner edges at once in arbitrary order 6.1 ms; this order 1.9 ms; pixels in level order with
+  // union-find shortcuts and a barrier per level 11 ms -- too few pixels per level and tile to keep the warps busy between barriers.)
   for (int s = 0; s < 12; s++) {
     const bool horiz = !(s & 1);
     const int b = 1 << (s >> 1), per_line = (MT_TILE / 2) / b, ntask = 2 * MT_TILE * per_line;
@@ -145,107 +142,200 @@ __global__ void __launch_bounds__(MT_THREADS) k_mtree_tiles(MserImages im, int W
     }
     const int v = sv[i];
     lev[(size_t)(2 * k) * Nimg + pi] = (uint8_t)v; lev[(size_t)(2 * k + 1) * Nimg + pi] = (uint8_t)(255 - v);
-    atomicAdd(&hist[v], 1u); atomicAdd(&hist[255 - v], 1u);
   }
-  __syncthreads();
-  if (hist[threadIdx.x]) atomicAdd(&C->hist[threadIdx.x], hist[threadIdx.x]);
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) C->n_stack = 2 * im.n;
 }
-__global__ void k_mser_offsets(MserCounters* C) {
-  if (threadIdx.x || blockIdx.x) return;
-  uint32_t s = 0;
-  for (int i = 0; i < 256; i++) { C->lvl_off[i] = s; s += C->hist[i]; }
-  C->lvl_off[256] = s;
+// Per (tile, polarity), after the tile's tree is complete and before the borders are merged: the tile's words are rewritten in canonical
+// form (a pixel points to the representative of its node, a representative to the representative of its parent node), and every
+// representative gets the area / inner-edge count of its subtree INSIDE the tile (lsum: area | edges << 16) together with the level
+// of its parent in the tile (hi; 256 for the tile's root).  k_mtree_fix turns these local sums into the sums of the final tree.
+// nedge of a pixel = 4-neighbours the reference has already labelled when it reaches the pixel: lower level, or the same level and
+// earlier in raster order (getExtrema.cpp:216-263) -- neighbours across the tile border included; summed over a component it counts the
+// pixel pairs inside, so that the reference's border count (+4 - 2 x labelled neighbours per pixel) is 4 area - 2 edges.
+template <class GK>
+__global__ void __launch_bounds__(MT_THREADS) k_mtree_local(int W, int H, const uint8_t* __restrict__ lev, typename GK::word* __restrict__ gpar,
+                                                            uint32_t* __restrict__ lsum, uint16_t* __restrict__ hi, uint32_t* __restrict__ area,
+                                                            uint32_t* __restrict__ nedge) {
+  __shared__ uint32_t par[MT_TILE * MT_TILE];
+  __shared__ uint32_t acc[MT_TILE * MT_TILE];
+  __shared__ uint16_t list[MT_TILE * MT_TILE];
+  __shared__ uint8_t sl[(MT_TILE + 2) * (MT_TILE + 2)];   // levels with a one-pixel halo
+  __shared__ uint32_t cnt[256], off[257];   // cnt: representatives per level, re-used as the fill cursor of the counting sort
+  __shared__ int nz[256], n_nz;
+  const int sub = blockIdx.z, x0 = blockIdx.x * MT_TILE, y0 = blockIdx.y * MT_TILE;
+  const int tw = min(MT_TILE, W - x0), th = min(MT_TILE, H - y0);
+  const uint32_t Nimg = (uint32_t)W * H;
+  const uint8_t* l = lev + (size_t)sub * Nimg;
+  typename GK::word* gp = gpar + (size_t)sub * Nimg;
+  const int SW = MT_TILE + 2;
+  cnt[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < SW * SW; i += MT_THREADS) {
+    const int gx = x0 + (i % SW) - 1, gy = y0 + (i / SW) - 1;
+    sl[i] = (gx >= 0 && gy >= 0 && gx < W && gy < H) ? l[(size_t)gy * W + gx] : 0;
+  }
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    acc[i] = 0;
+    if (lx < tw && ly < th) {
+      const typename GK::word w = gp[(size_t)(y0 + ly) * W + x0 + lx];
+      const uint32_t pj = GK::idx(w);
+      const int jy = (int)(pj / (uint32_t)W) - y0, jx = (int)(pj % (uint32_t)W) - x0;
+      par[i] = TKey::make(GK::lev(w), (uint32_t)(jy * MT_TILE + jx));
+    } else par[i] = TKey::make(0, i);
+  }
+  __syncthreads();
+  // canonical form, in place: a word replaced by its canonical value is still a valid pointer for every other walk
+  SmemWords m{par};
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    if (lx >= tw || ly >= th) continue;
+    const int L = sl[(ly + 1) * SW + lx + 1];
+    par[i] = mser_tree::canonical_parent<TKey>(m, TKey::make(L, i));
+  }
+  __syncthreads();
+  // own counts of every node, representatives counted per level
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    if (lx >= tw || ly >= th) continue;
+    const int c = (ly + 1) * SW + lx + 1, L = sl[c];
+    const uint32_t w = par[i];
+    const bool rep = w == TKey::make(L, i) || TKey::lev(w) > L;
+    uint32_t e = 0;
+    if (y0 + ly > 0) e += sl[c - SW] <= L;              // q < p: lower or equal level
+    if (x0 + lx > 0) e += sl[c - 1] <= L;
+    if (x0 + lx < W - 1) e += sl[c + 1] < L;            // q > p: strictly lower level
+    if (y0 + ly < H - 1) e += sl[c + SW] < L;
+    atomicAdd(&acc[rep ? i : TKey::idx(w)], 1u | (e << 16));
+    if (rep) atomicAdd(&cnt[L], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {   // exclusive scan of the 256 level counts, list of the levels that occur
+    uint32_t v[8], sum = 0;
+    for (int j = 0; j < 8; j++) { v[j] = cnt[threadIdx.x * 8 + j]; sum += v[j]; }
+    uint32_t incl = sum;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)threadIdx.x >= d) incl += t; }
+    uint32_t run = incl - sum;
+    int mine = 0;
+    for (int j = 0; j < 8; j++) { off[threadIdx.x * 8 + j] = run; run += v[j]; mine += v[j] != 0; cnt[threadIdx.x * 8 + j] = 0; }
+    if (threadIdx.x == 31) off[256] = run;
+    int pre = mine;
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, d); if ((int)threadIdx.x >= d) pre += t; }
+    int o = pre - mine;
+    for (int j = 0; j < 8; j++) if (v[j]) nz[o++] = threadIdx.x * 8 + j;
+    if (threadIdx.x == 31) n_nz = pre;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    if (lx >= tw || ly >= th) continue;
+    const int L = sl[(ly + 1) * SW + lx + 1];
+    const uint32_t w = par[i];
+    if (w == TKey::make(L, i) || TKey::lev(w) > L) list[off[L] + atomicAdd(&cnt[L], 1u)] = (uint16_t)i;
+  }
+  __syncthreads();
+  // subtree sums inside the tile: children live on lower levels, so one ascending pass over the levels that occur
+  const int n_levels = n_nz;
+  for (int k = 0; k < n_levels; k++) {
+    const int L = nz[k];
+    for (uint32_t j = off[L] + threadIdx.x; j < off[L + 1]; j += MT_THREADS) {
+      const uint32_t v = list[j], w = par[v];
+      if (w != TKey::make(L, v)) atomicAdd(&acc[TKey::idx(w)], acc[v]);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    if (lx >= tw || ly >= th) continue;
+    const int L = sl[(ly + 1) * SW + lx + 1];
+    const uint32_t w = par[i], j = TKey::idx(w);
+    const size_t g = (size_t)(y0 + ly) * W + x0 + lx;
+    gp[g] = GK::make(TKey::lev(w), (uint32_t)(y0 + (j >> 6)) * W + x0 + (j & (MT_TILE - 1)));
+    const bool self = w == TKey::make(L, i), rep = self || TKey::lev(w) > L;
+    const uint32_t a = rep ? acc[i] : 0u;
+    lsum[(size_t)sub * Nimg + g] = a;
+    hi[(size_t)sub * Nimg + g] = (uint16_t)(self ? 256 : TKey::lev(w));
+    area[(size_t)sub * Nimg + g] = a & 0xffffu; nedge[(size_t)sub * Nimg + g] = a >> 16;   // a representative's own contribution to its own final node
+  }
 }
 
 // edges across tile borders: first the horizontal borders (pixel pairs (x, y - 1) / (x, y) with y a multiple of the tile size: threads
 // run along x), then the vertical ones
 template <class GK>
-__global__ void __launch_bounds__(256) k_mtree_borders(int W, int H, int n_sub, const uint8_t* __restrict__ lev, typename GK::word* gpar) {
+__global__ void __launch_bounds__(256) k_mtree_borders(int W, int H, int n_sub, const uint8_t* __restrict__ lev, typename GK::word* gpar, int phase) {
   const uint32_t Nimg = (uint32_t)W * H;
   const uint32_t nh = (uint32_t)((H - 1) / MT_TILE) * W, nv = (uint32_t)((W - 1) / MT_TILE) * H, per = nh + nv;
   const unsigned long long total = (unsigned long long)per * n_sub;
   for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
     const uint32_t sub = (uint32_t)(t / per), e = (uint32_t)(t - (unsigned long long)sub * per);
     uint32_t p, q;
-    if (e < nh) { const uint32_t b = e / W, x = e - b * W; q = (b + 1) * MT_TILE * W + x; p = q - W; }
-    else { const uint32_t f = e - nh, b = f / H, y = f - b * H; q = y * W + (b + 1) * MT_TILE; p = q - 1; }
+    // phase 0: one pair in the middle of every tile border (these join the tile trees: the long walks up two root paths, without the
+    // other 63 pairs of the border swapping the same words); phase 1: the rest
+    if (e < nh) { const uint32_t b = e / W, x = e - b * W; if (((x & (MT_TILE - 1)) == MT_TILE / 2) != (phase == 0)) continue; q = (b + 1) * MT_TILE * W + x; p = q - W; }
+    else { const uint32_t f = e - nh, b = f / H, y = f - b * H; if (((y & (MT_TILE - 1)) == MT_TILE / 2) != (phase == 0)) continue; q = y * W + (b + 1) * MT_TILE; p = q - 1; }
     const uint8_t* l = lev + (size_t)sub * Nimg;
     GmemWords<typename GK::word> m{gpar + (size_t)sub * Nimg};
     mser_tree::connect<GK>(m, GK::make(l[p], p), GK::make(l[q], q));
   }
 }
 
-// canonical parents, own counts, representatives per level.  nedge of a pixel = 4-neighbours the reference has already labelled when it
-// reaches the pixel: lower level, or the same level and earlier in raster order (getExtrema.cpp:216-263); summed over a component it
-// counts the pixel pairs inside, so that the reference's border count (+4 - 2 x labelled neighbours per pixel) is 4 area - 2 edges.
+// After the borders: canonical parent of every pixel in the final tree, and the final sums.  A representative u of a tile tree carries
+// the sums of its subtree inside the tile; they belong to every node of the FINAL tree between u's node and the node of u's parent in
+// the tile (exclusive: that one receives them through the parent's own local sums) -- one node when nothing was inserted from other
+// tiles, the whole trunk for a tile's root.  Every representative walks that gap and adds its sums; no level-by-level pass is needed.
 template <class GK>
-__global__ void __launch_bounds__(256) k_mtree_canon(int W, int H, uint32_t N, const uint8_t* __restrict__ lev, typename GK::word* gpar,
-                                                     uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge, uint32_t* __restrict__ nodes,
-                                                     MserCounters* C) {
+__global__ void __launch_bounds__(256) k_mtree_fix(int W, int H, uint32_t N, const uint8_t* __restrict__ lev, typename GK::word* gpar,
+                                                   const uint32_t* __restrict__ lsum, const uint16_t* __restrict__ hi,
+                                                   uint32_t* __restrict__ parent, uint32_t* __restrict__ work, MserCounters* C) {
   const uint32_t Nimg = (uint32_t)W * H;
-  const int lane = threadIdx.x & 31;
-  for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < N; base += gridDim.x * blockDim.x) {
-    const uint32_t x = base + lane;
-    const bool act = x < N;
-    uint32_t r = 0, e = 0; int L = 0; bool rep = false;
-    if (act) {
-      const uint32_t sub = x / Nimg, pi = x - sub * Nimg, off = sub * Nimg;
-      L = lev[x];
-      GmemWords<typename GK::word> m{gpar + (size_t)off};
-      const typename GK::word ck = mser_tree::canonical_parent<GK>(m, GK::make(L, pi));
-      const uint32_t cp = off + GK::idx(ck);
-      parent[x] = cp;
-      rep = cp == x || GK::lev(ck) > L;
-      r = rep ? x : cp;
-      const int y = pi / W, xx = pi - y * W;
-      const uint8_t* l = lev + off;
-      if (y > 0) { const int lq = l[pi - W]; e += lq <= L; }                    // q < p: lower or equal level counts
-      if (xx > 0) { const int lq = l[pi - 1]; e += lq <= L; }
-      if (xx < W - 1) { const int lq = l[pi + 1]; e += lq < L; }                // q > p: strictly lower level only
-      if (y < H - 1) { const int lq = l[pi + W]; e += lq < L; }
-    }
-    const unsigned mask = __ballot_sync(0xffffffffu, act);
-    if (act) {
-      const unsigned grp = __match_any_sync(mask, r);
-      const uint32_t se = __reduce_add_sync(grp, e);
-      if (lane == __ffs(grp) - 1) { atomicAdd(area + r, (uint32_t)__popc(grp)); if (se) atomicAdd(nedge + r, se); }
-    }
-    const unsigned reps = __ballot_sync(0xffffffffu, act && rep);
-    if (act && rep) {
-      const unsigned grp = __match_any_sync(reps, L);
-      uint32_t b0 = 0;
-      const int leader = __ffs(grp) - 1;
-      if (lane == leader) b0 = atomicAdd(&C->lvl_cnt[L], (uint32_t)__popc(grp));
-      b0 = __shfl_sync(grp, b0, leader);
-      nodes[C->lvl_off[L] + b0 + __popc(grp & ((1u << lane) - 1))] = x;
-    }
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;   // one pixel per thread: the chains are short, the loads independent
+  bool walk = false;
+  if (x < N) {
+    const uint32_t sub = x / Nimg, pi = x - sub * Nimg, off = sub * Nimg;
+    const int L = lev[x];
+    GmemWords<typename GK::word> m{gpar + (size_t)off};
+    const typename GK::word xk = GK::make(L, pi);
+    const typename GK::word ck = mser_tree::canonical_parent<GK>(m, xk);
+    parent[x] = off + GK::idx(ck);
+    // a representative of a tile tree whose sums belong to more than its own node: it was merged into another node of its level, or
+    // nodes of other tiles were inserted below its parent in the tile
+    if (lsum[x] != 0) walk = ck == xk ? false : (GK::lev(ck) == L || GK::lev(ck) < (int)hi[x]);
+  }
+  const unsigned mk = __ballot_sync(0xffffffffu, walk);
+  if (mk) {
+    const int lane = threadIdx.x & 31;
+    uint32_t b0 = 0;
+    if (lane == 0) b0 = atomicAdd(&C->n_walk, (uint32_t)__popc(mk));
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    if (walk) work[b0 + __popc(mk & ((1u << lane) - 1))] = x;
   }
 }
-
-__global__ void __launch_bounds__(512) k_mtree_accum(const uint32_t* __restrict__ parent, uint32_t* area, uint32_t* nedge, const uint32_t* __restrict__ nodes,
-                                                     const MserCounters* __restrict__ C) {
-  cg::grid_group grid = cg::this_grid();
-  const int lane = threadIdx.x & 31;
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  for (int L = 0; L < 256; L++) {
-    const uint32_t n = C->lvl_cnt[L], off = C->lvl_off[L];
-    if (n == 0) continue;                        // the same decision in every thread: the counts are final before the launch
-    for (uint32_t base = tid & ~31u; base < n; base += nthreads) {
-      const uint32_t i = base + lane;
-      const bool act = i < n;
-      uint32_t v = 0, p = 0;
-      if (act) { v = nodes[off + i]; p = parent[v]; }
-      const bool push = act && p != v;
-      const unsigned mask = __ballot_sync(0xffffffffu, push);
-      if (push) {
-        const uint32_t a = __ldcg(area + v), e = __ldcg(nedge + v);
-        const unsigned grp = __match_any_sync(mask, p);
-        const uint32_t sa = __reduce_add_sync(grp, a), se = __reduce_add_sync(grp, e);
-        if (lane == __ffs(grp) - 1) { atomicAdd(area + p, sa); atomicAdd(nedge + p, se); }
+template <class GK>
+__global__ void __launch_bounds__(128) k_mtree_walk(int W, int H, const uint8_t* __restrict__ lev, typename GK::word* gpar,
+                                                    const uint32_t* __restrict__ lsum, const uint16_t* __restrict__ hi, const uint32_t* __restrict__ work,
+                                                    const MserCounters* __restrict__ C, uint32_t* area, uint32_t* nedge) {
+  const uint32_t Nimg = (uint32_t)W * H, n = C->n_walk;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t x = work[i];
+    const uint32_t sub = x / Nimg, pi = x - sub * Nimg, off = sub * Nimg;
+    const int L = lev[x];
+    GmemWords<typename GK::word> m{gpar + (size_t)off};
+    const typename GK::word xk = GK::make(L, pi);
+    const typename GK::word ck = mser_tree::canonical_parent<GK>(m, xk);
+    const uint32_t ls = lsum[x], sa = ls & 0xffffu, se = ls >> 16;
+    const int H_ = hi[x];
+    typename GK::word vk = (ck == xk || GK::lev(ck) > L) ? xk : ck;   // the final node of x
+    for (;;) {
+      if (vk != xk) {                                                 // (x's own node already holds x's sums: k_mtree_local)
+        atomicAdd(area + off + GK::idx(vk), sa);
+        if (se) atomicAdd(nedge + off + GK::idx(vk), se);
       }
+      const typename GK::word z = m.load(GK::idx(vk));
+      if (z == vk) break;                                             // the root
+      typename GK::word r = z;                                        // representative of the parent node
+      for (;;) { const typename GK::word v = m.load(GK::idx(r)); if (v == r || GK::lev(v) != GK::lev(r)) break; r = v; }
+      if (GK::lev(r) >= H_) break;
+      vk = r;
     }
-    grid.sync();
   }
 }
 
@@ -612,42 +702,37 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
   const bool wide = Nimg > (1u << 24);          // 64-bit tree words above 2^24 pixels per image
   MB2_CUDA_CHECK(ctx, B.lev.reserve(N));
   MB2_CUDA_CHECK(ctx, B.gpar.reserve((size_t)N * (wide ? 8 : 4)));
-  DevBuf* u32bufs[] = {&B.parent, &B.area, &B.nedge, &B.nodes, &B.surv, &B.birth, &B.slot_of_node, &B.sa};
+  DevBuf* u32bufs[] = {&B.parent, &B.area, &B.nedge, &B.lsum, &B.surv, &B.birth, &B.slot_of_node, &B.sa};
   for (DevBuf* b : u32bufs) MB2_CUDA_CHECK(ctx, b->reserve((size_t)N * 4));
+  MB2_CUDA_CHECK(ctx, B.hi.reserve((size_t)N * 2));
   MB2_CUDA_CHECK(ctx, B.best.reserve((size_t)N * 8));
   MB2_CUDA_CHECK(ctx, B.flag.reserve(N));
   uint8_t* lev = B.lev.as<uint8_t>();
-  uint32_t *parent = B.parent.as<uint32_t>(), *area = B.area.as<uint32_t>(), *nedge = B.nedge.as<uint32_t>(), *nodes = B.nodes.as<uint32_t>();
+  uint32_t *parent = B.parent.as<uint32_t>(), *area = B.area.as<uint32_t>(), *nedge = B.nedge.as<uint32_t>(), *lsum = B.lsum.as<uint32_t>();
+  uint16_t* hi = B.hi.as<uint16_t>();
   uint32_t *surv = B.surv.as<uint32_t>(), *birth = B.birth.as<uint32_t>(), *slot_of_node = B.slot_of_node.as<uint32_t>(), *sa = B.sa.as<uint32_t>();
 
-  // 1 + 2. component trees: tiles in shared memory, tile borders in global memory, canonical form, attributes up the tree
+  // 1 + 2. component trees: tiles in shared memory, local sums, tile borders in global memory, final parents and sums
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(dC, 0, sizeof(MserCounters), st));
-  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(area, 0, (size_t)N * 4, st));
-  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(nedge, 0, (size_t)N * 4, st));
   {
-    const dim3 tg((W + MT_TILE - 1) / MT_TILE, (H + MT_TILE - 1) / MT_TILE, K);
+    const dim3 tg((W + MT_TILE - 1) / MT_TILE, (H + MT_TILE - 1) / MT_TILE, K), lg(tg.x, tg.y, 2 * K);
     const unsigned long long n_border = ((unsigned long long)((H - 1) / MT_TILE) * W + (unsigned long long)((W - 1) / MT_TILE) * H) * 2 * K;
     const int bg = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_border + 255) / 256, (unsigned long long)ctx->num_sms * 64));
     if (wide) {
-      MB2_LAUNCH(ctx, k_mtree_tiles<GKey64>, tg, MT_THREADS, 0, mi, W, H, lev, B.gpar.as<unsigned long long>(), dC);
-      MB2_LAUNCH(ctx, k_mser_offsets, 1, 32, 0, dC);
-      if (n_border) MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, B.gpar.as<unsigned long long>());
-      MB2_LAUNCH(ctx, k_mtree_canon<GKey64>, grid_for(N, 256, G), 256, 0, W, H, N, lev, B.gpar.as<unsigned long long>(), parent, area, nedge, nodes, dC);
+      unsigned long long* gp = B.gpar.as<unsigned long long>();
+      MB2_LAUNCH(ctx, k_mtree_tiles<GKey64>, tg, MT_THREADS, 0, mi, W, H, lev, gp, dC);
+      MB2_LAUNCH(ctx, k_mtree_local<GKey64>, lg, MT_THREADS, 0, W, H, lev, gp, lsum, hi, area, nedge);
+      if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
+      MB2_LAUNCH(ctx, k_mtree_fix<GKey64>, (N + 255) / 256, 256, 0, W, H, N, lev, gp, lsum, hi, parent, sa, dC);
+      MB2_LAUNCH(ctx, k_mtree_walk<GKey64>, ctx->num_sms * 16, 128, 0, W, H, lev, gp, lsum, hi, sa, dC, area, nedge);
     } else {
-      MB2_LAUNCH(ctx, k_mtree_tiles<GKey32>, tg, MT_THREADS, 0, mi, W, H, lev, B.gpar.as<uint32_t>(), dC);
-      MB2_LAUNCH(ctx, k_mser_offsets, 1, 32, 0, dC);
-      if (n_border) MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, B.gpar.as<uint32_t>());
-      MB2_LAUNCH(ctx, k_mtree_canon<GKey32>, grid_for(N, 256, G), 256, 0, W, H, N, lev, B.gpar.as<uint32_t>(), parent, area, nedge, nodes, dC);
+      uint32_t* gp = B.gpar.as<uint32_t>();
+      MB2_LAUNCH(ctx, k_mtree_tiles<GKey32>, tg, MT_THREADS, 0, mi, W, H, lev, gp, dC);
+      MB2_LAUNCH(ctx, k_mtree_local<GKey32>, lg, MT_THREADS, 0, W, H, lev, gp, lsum, hi, area, nedge);
+      if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
+      MB2_LAUNCH(ctx, k_mtree_fix<GKey32>, (N + 255) / 256, 256, 0, W, H, N, lev, gp, lsum, hi, parent, sa, dC);
+      MB2_LAUNCH(ctx, k_mtree_walk<GKey32>, ctx->num_sms * 16, 128, 0, W, H, lev, gp, lsum, hi, sa, dC, area, nedge);
     }
-    int occ = 0;
-    MB2_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mtree_accum, 512, 0));
-    const int Gc = ctx->num_sms * std::max(1, std::min(occ, 2));   // co-resident by construction; few CTAs keep the grid barrier cheap
-    void* args[] = {&parent, &area, &nedge, &nodes, &dC};
-    mb2_ctx::ProfRec pr{"k_mtree_accum", nullptr, nullptr};
-    if (ctx->profiling) { cudaEventCreate(&pr.a); cudaEventCreate(&pr.b); cudaEventRecord(pr.a, st); }
-    MB2_CUDA_CHECK(ctx, cudaLaunchCooperativeKernel((void*)k_mtree_accum, dim3(Gc), dim3(512), args, 0, st));
-    if (ctx->profiling) { cudaEventRecord(pr.b, st); ctx->prof.push_back(pr); }
-    ctx->launches++;
     if (ctx->ev_tree) { cudaEventRecord(ctx->ev_tree, st); __sync_synchronize(); ctx->tree_epoch = ctx->tree_epoch + 1; }
   }
   // 3. survivors
