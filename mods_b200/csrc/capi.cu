@@ -327,9 +327,10 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
   const size_t px0 = (size_t)L.rows[0] * L.cols[0];
   const int cand_cap = (int)std::min<size_t>(px0 / 8 + 4096, (size_t)1 << 26);
   const int kp_cap = (int)std::min<size_t>(px0 / 16 + 4096, (size_t)1 << 25);
-  MB2_CUDA_CHECK(ctx, ctx->cand.reserve((size_t)cand_cap * (sizeof(Candidate) + sizeof(Localized)) + 64));
+  MB2_CUDA_CHECK(ctx, ctx->cand.reserve((size_t)cand_cap * (2 * sizeof(Candidate) + sizeof(Localized)) + 64));
   Candidate* d_cand = ctx->cand.as<Candidate>();
   Localized* d_loc = (Localized*)(d_cand + cand_cap);
+  Candidate* d_pre = (Candidate*)(d_loc + cand_cap);   // pixels that passed the in-level extremum test (k_blur_hess_tma)
   MB2_CUDA_CHECK(ctx, ctx->kp_a.reserve((size_t)kp_cap * sizeof(KeypointRec) + 64));
   KeypointRec* d_kp = ctx->kp_a.as<KeypointRec>();
   MB2_CUDA_CHECK(ctx, ctx->octmap.reserve(px0 * 8 + 64));
@@ -368,7 +369,8 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
       float n0 = levelSigma[0] * levelSigma[0];
       if (par.initialSigma > curSigma0) {
         const float sigma = std::sqrt(par.initialSigma * par.initialSigma - curSigma0 * curSigma0);
-        rc = mb2_launch_blur(ctx, img, (float*)oc.blur[0].p, (float*)oc.resp[0].p, oc.blur[0].pitch, make_taps(sigma), n0 * n0, dog ? 0 : 1);
+        if (dog) rc = mb2_launch_blur(ctx, img, (float*)oc.blur[0].p, (float*)oc.resp[0].p, oc.blur[0].pitch, make_taps(sigma), n0 * n0, 0);
+        else rc = mb2_launch_blur_tma(ctx, img, (float*)oc.blur[0].p, (float*)oc.resp[0].p, oc.blur[0].pitch, make_taps(sigma), n0 * n0, PrefilterArgs{0, 0, 0, 0, 0, nullptr, nullptr, 0});
         if (rc) return rc;
         if (dog) dog_response(oc, 0);
       } else {
@@ -382,18 +384,24 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
       float n0 = levelSigma[0] * levelSigma[0];
       if (dog) dog_response(oc, 0); else mb2_launch_hessian(ctx, oc.blur[0], (float*)oc.resp[0].p, oc.resp[0].pitch, n0 * n0);
     }
+    MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int), ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts + 2, 0, sizeof(int), ctx->stream));
     for (int i = 1; i < NL; i++) {
       float nrm = levelSigma[i] * levelSigma[i];  // Response(nextBlur, sigma*sigma); HessianResponse squares it again
-      rc = mb2_launch_blur(ctx, oc.blur[i - 1], (float*)oc.blur[i].p, (float*)oc.resp[i].p, oc.blur[i].pitch, make_taps(incSigma[i]),
-                           nrm * nrm, dog ? 0 : 1);
+      if (dog) rc = mb2_launch_blur(ctx, oc.blur[i - 1], (float*)oc.blur[i].p, (float*)oc.resp[i].p, oc.blur[i].pitch, make_taps(incSigma[i]), nrm * nrm, 0);
+      else   // detection levels 1..S: the kernel that produces the level also lists its in-level extrema beyond the gate
+        rc = mb2_launch_blur_tma(ctx, oc.blur[i - 1], (float*)oc.blur[i].p, (float*)oc.resp[i].p, oc.blur[i].pitch, make_taps(incSigma[i]), nrm * nrm,
+                                 PrefilterArgs{i <= S ? 1 : 0, par.border, positiveThreshold, negativeThreshold, i, d_pre, d_counts + 2, cand_cap});
       if (rc) return rc;
       if (dog) dog_response(oc, i);
     }
     // ---- extrema -> localisation -> de-duplication, levels 1..S in the reference's order --------
-    MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int), ctx->stream));
-    for (int lv = 1; lv <= S; lv++)
-      mb2_launch_nms(ctx, oc.resp[lv - 1], oc.resp[lv], oc.resp[lv + 1], par.border, positiveThreshold, negativeThreshold, lv, d_cand,
-                     d_counts, cand_cap);
+    if (dog) {
+      for (int lv = 1; lv <= S; lv++)
+        mb2_launch_nms(ctx, oc.resp[lv - 1], oc.resp[lv], oc.resp[lv + 1], par.border, positiveThreshold, negativeThreshold, lv, d_cand,
+                       d_counts, cand_cap);
+    } else if (oc.blur[0].cols - 2 * par.border > 0 && oc.blur[0].rows - 2 * par.border > 0)
+      mb2_launch_nms_finish(ctx, oc, d_pre, d_counts + 2, cand_cap, d_cand, d_counts, cand_cap);
     int n_cand = 0;
     MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_cand, d_counts, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

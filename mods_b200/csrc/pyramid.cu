@@ -13,6 +13,7 @@
 #undef MB2_NS
 #define MB2_NS mb2_pyramid_detail
 #include "pyramid.cuh"
+#include <cuda.h>
 
 // ---------------------------------------------------------------------------------------------
 // Blur (+ optional Hessian response of the blurred image) -- one pass over HBM per level:
@@ -118,11 +119,225 @@ k_blur_hess(ImgView src, float* __restrict__ dst_blur, float* __restrict__ dst_r
           const float v31 = c[CP_WP - 1], v32 = c[CP_WP], v33 = c[CP_WP + 1];
           const float Lxx = fadd(fsub(v21, fmul(2.f, v22)), v23);
           const float Lyy = fadd(fsub(v12, fmul(2.f, v22)), v32);
-          const float Lxy = fdiv(fsub(fadd(fsub(v13, v11), v31), v33), 4.0f);
+          const float Lxy = fmul(fsub(fadd(fsub(v13, v11), v31), v33), 0.25f) /* == x / 4.0f exactly: a power-of-two scale */;
           r = fmul(fsub(fmul(Lxx, Lyy), fmul(Lxy, Lxy)), norm2);
         }
         dst_resp[(size_t)gy * dst_pitch + gx] = r;
       }
+    }
+  }
+}
+
+__device__ __forceinline__ bool is_max9(const ImgView& im, float val, int r, int c);
+__device__ __forceinline__ bool is_min9(const ImgView& im, float val, int r, int c);
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged form of the same pass (the one the library runs for DET_HESSIAN): the source tile with its halo arrives in shared memory
+// through ONE cp.async.bulk.tensor.2d per CTA (a 2-D tensor map over the source plane; out-of-image elements come back as zeros and
+// are then overwritten with the replicated border -- BORDER_REPLICATE -- from the tile itself, on border tiles only), so the load costs
+// no address arithmetic in the SM.  The tile carries one more pixel of halo than k_blur_hess: the response is formed on (TW + 2) x
+// (TH + 2) pixels, which lets the kernel that PRODUCES a detection level also run the in-level part of the 3x3x3 extremum test
+// (pyramid.cpp:42-64, 432-452) from shared memory.  Only the pixels that pass it (|val| beyond the gate and a non-strict 3x3 extremum of
+// their own level, ~1 % of the pixels) are listed; k_nms_finish checks the levels below and above for those.  The response planes are
+// no longer re-read in full by a separate pass.
+// Arithmetic per output is the one of k_blur_hess (row pass left to right, column pass centre tap then symmetric pairs, no FMA).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pyr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int NT>
+struct TmaBlurGeom {
+  static constexpr int H = NT / 2, HALO = H + 2;
+  // The inner start coordinate of a tensor-map box must be a multiple of 16 bytes (measured: tools/micro/tma2d.cu), so the tile starts
+  // HX >= HALO columns left of the output tile, HX a multiple of 4; the row pass starts XS - E columns into the tile (an even offset: its
+  // windows are read as float2) and its output column lx stands for image column x0 - 2 - E + lx.
+  static constexpr int HX = (HALO + 3) / 4 * 4, XS = HX - HALO, E = XS & 1;
+  static constexpr int RP_W = 72, RP_WP = 74;                       // row-pass result: 72 columns (12 strips of 6; 68 + E are needed), pitch 74
+  static constexpr int IN_H = TH + 2 * HALO;
+  static constexpr int BOXW = ((XS - E + RP_W + 2 * H) + 3) / 4 * 4; // TMA box width: whole 16-byte units
+  static constexpr int CP_W = TW + 4, CP_H = TH + 4, CP_WP = RP_WP; // column-pass result (aliases the source tile)
+  static constexpr int RS_W = TW + 2, RS_H = TH + 2, RS_WP = TW + 4;// response incl. a one-pixel halo (aliases the row-pass result)
+  static constexpr size_t SMEM = 128 /*align*/ + sizeof(float) * (size_t)(IN_H * BOXW + IN_H * RP_WP) + 16 /*mbarrier*/;
+  static_assert(CP_H * CP_WP <= IN_H * BOXW, "col-pass tile must fit in the source tile");
+  static_assert(RS_H * RS_WP <= IN_H * RP_WP, "response tile must fit in the row-pass tile");
+  static_assert(BOXW <= 256 && IN_H <= 256, "TMA box limits");
+};
+
+template <int NT>
+__global__ void __launch_bounds__(BLUR_THREADS)
+k_blur_hess_tma(const __grid_constant__ CUtensorMap tmap, int rows, int cols, float* __restrict__ dst_blur, float* __restrict__ dst_resp, int dst_pitch,
+                BlurTaps taps, float norm2, int prefilter, int border, float posThr, float negThr, int level, Candidate* __restrict__ pre,
+                int* __restrict__ pre_count, int pre_cap) {
+  typedef TmaBlurGeom<NT> G;
+  constexpr int H = G::H, HALO = G::HALO, IN_H = G::IN_H, BOXW = G::BOXW, RP_W = G::RP_W, RP_WP = G::RP_WP;
+  constexpr int CP_W = G::CP_W, CP_H = G::CP_H, CP_WP = G::CP_WP, RS_W = G::RS_W, RS_H = G::RS_H, RS_WP = G::RS_WP;
+  extern __shared__ unsigned char smem_raw_[];
+  float* s_in = reinterpret_cast<float*>(((uintptr_t)smem_raw_ + 127) & ~(uintptr_t)127);   // IN_H x BOXW, written by the TMA unit
+  float* s_rp = s_in + IN_H * BOXW;                                                          // IN_H x RP_WP
+  float* s_cp = s_in;                                                                        // CP_H x CP_WP
+  float* s_rs = s_rp;                                                                        // RS_H x RS_WP
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_rp + IN_H * RP_WP);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int gx0 = x0 - G::HX, gy0 = y0 - HALO;           // image coordinates of the tile's first element (gx0 is a multiple of 4)
+  float k[NT];
+#pragma unroll
+  for (int j = 0; j < NT; j++) k[j] = taps.k[j];
+  // 1. one bulk tensor copy brings the whole tile
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pyr_smem_u32(bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pyr_smem_u32(bar)), "r"((uint32_t)(IN_H * BOXW * sizeof(float))) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(pyr_smem_u32(s_in)),
+                 "l"(&tmap), "r"(pyr_smem_u32(bar)), "r"(gx0), "r"(gy0)
+                 : "memory");
+  }
+  __syncthreads();
+  {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(pyr_smem_u32(bar)), "r"(0u) : "memory");
+  }
+  // BORDER_REPLICATE on tiles that reach over the image: every out-of-image element takes the value of the nearest image pixel, which
+  // lies inside the tile (never itself overwritten)
+  if (gx0 < 0 || gy0 < 0 || gx0 + BOXW > cols || gy0 + IN_H > rows) {
+    for (int i = tid; i < IN_H * BOXW; i += BLUR_THREADS) {
+      const int ly = i / BOXW, lx = i - ly * BOXW;
+      const int gy = gy0 + ly, gx = gx0 + lx;
+      if (gy < 0 || gy >= rows || gx < 0 || gx >= cols) {
+        const int cy = min(max(gy, 0), rows - 1) - gy0, cx = min(max(gx, 0), cols - 1) - gx0;
+        s_in[i] = s_in[cy * BOXW + cx];
+      }
+    }
+    __syncthreads();
+  }
+  // 2. row pass: item = (row ly, strip of RS outputs); output column lx is centred on source column lx + H
+  for (int item = tid; item < IN_H * (RP_W / RS); item += BLUR_THREADS) {
+    const int ly = item / (RP_W / RS), st = item - ly * (RP_W / RS);
+    const float* p = s_in + ly * BOXW + (G::XS - G::E) + st * RS;
+    float w[RS + NT - 1];
+#pragma unroll
+    for (int j = 0; j < RS + NT - 1; j += 2) {
+      const float2 v = *reinterpret_cast<const float2*>(p + j);
+      w[j] = v.x;
+      if (j + 1 < RS + NT - 1) w[j + 1] = v.y;
+    }
+    float* o = s_rp + ly * RP_WP + st * RS;
+#pragma unroll
+    for (int q = 0; q < RS; q++) {
+      float acc = fmul(k[0], w[q]);
+#pragma unroll
+      for (int j = 1; j < NT; j++) acc = fadd(acc, fmul(k[j], w[q + j]));
+      o[q] = acc;
+    }
+  }
+  __syncthreads();
+  // 3. column pass (symmetric pairs): item = (column lx, strip of CS rows); output row ly is centred on row ly + H
+  constexpr int NSTRIP = CP_H / CS;
+  static_assert(CP_H % CS == 0, "column strips");
+  for (int item = tid; item < CP_W * NSTRIP; item += BLUR_THREADS) {
+    const int st = item / CP_W, lx = item - st * CP_W;
+    const int ly0 = st * CS;
+    const float* p = s_rp + ly0 * RP_WP + lx + G::E;   // s_cp column lx <-> image column x0 - 2 + lx
+    float w[CS + 2 * H];
+#pragma unroll
+    for (int j = 0; j < CS + 2 * H; j++) w[j] = p[j * RP_WP];
+#pragma unroll
+    for (int q = 0; q < CS; q++) {
+      float acc = fmul(k[H], w[q + H]);
+#pragma unroll
+      for (int j = 1; j <= H; j++) acc = fadd(acc, fmul(k[H + j], fadd(w[q + H + j], w[q + H - j])));
+      s_cp[(ly0 + q) * CP_WP + lx] = acc;
+    }
+  }
+  __syncthreads();
+  // 4. Hessian response (pyramid.cpp:223-281; 0 on the one-pixel frame of the image) on the tile and a one-pixel ring around it
+  for (int i = tid; i < RS_H * RS_W; i += BLUR_THREADS) {
+    const int ly = i / RS_W, lx = i - ly * RS_W;         // response (ly, lx) <-> image (y0 - 1 + ly, x0 - 1 + lx) <-> s_cp (ly + 1, lx + 1)
+    const int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+    float r = 0.f;
+    if (gy >= 1 && gy < rows - 1 && gx >= 1 && gx < cols - 1) {
+      const float* c = s_cp + (ly + 1) * CP_WP + (lx + 1);
+      const float v11 = c[-CP_WP - 1], v12 = c[-CP_WP], v13 = c[-CP_WP + 1];
+      const float v21 = c[-1], v22 = c[0], v23 = c[1];
+      const float v31 = c[CP_WP - 1], v32 = c[CP_WP], v33 = c[CP_WP + 1];
+      const float Lxx = fadd(fsub(v21, fmul(2.f, v22)), v23);
+      const float Lyy = fadd(fsub(v12, fmul(2.f, v22)), v32);
+      const float Lxy = fmul(fsub(fadd(fsub(v13, v11), v31), v33), 0.25f) /* == x / 4.0f exactly: a power-of-two scale */;
+      r = fmul(fsub(fmul(Lxx, Lyy), fmul(Lxy, Lxy)), norm2);
+    }
+    s_rs[ly * RS_WP + lx] = r;
+  }
+  // blur goes out while the response tile settles (s_cp is read-only from here on)
+  for (int ly = warp; ly < TH; ly += BLUR_THREADS / 32) {
+    const int gy = y0 + ly;
+    if (gy >= rows) break;
+#pragma unroll
+    for (int half = 0; half < TW / 32; half++) {
+      const int lx = lane + 32 * half, gx = x0 + lx;
+      if (gx < cols) dst_blur[(size_t)gy * dst_pitch + gx] = s_cp[(ly + 2) * CP_WP + lx + 2];
+    }
+  }
+  __syncthreads();
+  // 5. response out + in-level extremum test
+  for (int ly = warp; ly < TH; ly += BLUR_THREADS / 32) {
+    const int gy = y0 + ly;
+    if (gy >= rows) break;
+#pragma unroll
+    for (int half = 0; half < TW / 32; half++) {
+      const int lx = lane + 32 * half, gx = x0 + lx;
+      bool hit = false;
+      if (gx < cols) {
+        const float* c = s_rs + (ly + 1) * RS_WP + lx + 1;
+        const float val = c[0];
+        dst_resp[(size_t)gy * dst_pitch + gx] = val;
+        if (prefilter && gy >= border && gy < rows - border && gx >= border && gx < cols - border) {
+          if (val > posThr) {
+            hit = true;
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+              for (int dc = -1; dc <= 1; dc++) hit = hit && !(c[dr * RS_WP + dc] > val);
+          } else if (val < negThr) {
+            hit = true;
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+              for (int dc = -1; dc <= 1; dc++) hit = hit && !(c[dr * RS_WP + dc] < val);
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(pre_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & ((1u << lane) - 1));
+        if (hit && base < pre_cap) pre[base] = Candidate{gy, gx, level, 0};
+      }
+    }
+  }
+}
+
+// The levels below and above, for the pixels that passed the in-level test (pyramid.cpp:42-64: non-strict, ties pass)
+__global__ void __launch_bounds__(128) k_nms_finish(OctaveLevels oct, const Candidate* __restrict__ pre, const int* __restrict__ pre_count, int pre_cap,
+                                                    Candidate* __restrict__ out, int* __restrict__ count, int capacity) {
+  const int n = min(*pre_count, pre_cap), lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    bool hit = false;
+    Candidate cd{0, 0, 0, 0};
+    if (i < n) {
+      cd = pre[i];
+      const ImgView low = oct.resp[cd.level - 1], cur = oct.resp[cd.level], high = oct.resp[cd.level + 1];
+      const float val = cur.at(cd.r, cd.c);
+      hit = val > 0 ? (is_max9(low, val, cd.r, cd.c) && is_max9(high, val, cd.r, cd.c)) : (is_min9(low, val, cd.r, cd.c) && is_min9(high, val, cd.r, cd.c));
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      int b0 = 0;
+      if (lane == 0) b0 = atomicAdd(count, __popc(m));
+      b0 = __shfl_sync(0xffffffffu, b0, 0) + __popc(m & ((1u << lane) - 1));
+      if (hit && b0 < capacity) out[b0] = cd;
     }
   }
 }
@@ -138,7 +353,7 @@ __global__ void k_hessian(ImgView src, float* __restrict__ dst, int dst_pitch, f
     const float v31 = src.at(gy + 1, gx - 1), v32 = src.at(gy + 1, gx), v33 = src.at(gy + 1, gx + 1);
     const float Lxx = fadd(fsub(v21, fmul(2.f, v22)), v23);
     const float Lyy = fadd(fsub(v12, fmul(2.f, v22)), v32);
-    const float Lxy = fdiv(fsub(fadd(fsub(v13, v11), v31), v33), 4.0f);
+    const float Lxy = fmul(fsub(fadd(fsub(v13, v11), v31), v33), 0.25f) /* == x / 4.0f exactly: a power-of-two scale */;
     r = fmul(fsub(fmul(Lxx, Lyy), fmul(Lxy, Lxy)), norm2);
   }
   dst[(size_t)gy * dst_pitch + gx] = r;
@@ -377,6 +592,45 @@ void launch_blur_nt(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* ds
   MB2_LAUNCH(ctx, k_blur_hess<NT>, grid, BLUR_THREADS, smem, src, dst_blur, dst_resp, dst_pitch, taps, norm2, want_resp);
 }
 
+
+typedef CUresult (*PFN_pyrEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// 2-D tensor map over one f32 plane (cols x rows, row pitch in floats: a multiple of 4), box = the kernel's tile with halo
+int make_plane_tmap(mb2_ctx* ctx, CUtensorMap* m, const ImgView& src, int boxw, int boxh) {
+  if (!ctx->tmap_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return MB2_ERR_CUDA; }
+    ctx->tmap_encode = fn;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)src.cols, (cuuint64_t)src.rows};
+  cuuint64_t strides[1] = {(cuuint64_t)src.pitch * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)boxw, (cuuint32_t)boxh};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((PFN_pyrEncodeTiled)ctx->tmap_encode)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)src.p, dims, strides, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled (pyramid plane) failed: " + std::to_string((int)r)); return MB2_ERR_CUDA; }
+  return MB2_OK;
+}
+
+template <int NT>
+int launch_blur_tma_nt(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps, float norm2,
+                       const PrefilterArgs& pf) {
+  typedef TmaBlurGeom<NT> G;
+  CUtensorMap tm;
+  int rc = make_plane_tmap(ctx, &tm, src, G::BOXW, G::IN_H);
+  if (rc) return rc;
+  static unsigned long long attr_devs = 0;
+  if (mb2_first_use_on_device(&attr_devs, ctx->device)) cudaFuncSetAttribute(k_blur_hess_tma<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+  dim3 grid((src.cols + TW - 1) / TW, (src.rows + TH - 1) / TH);
+  MB2_LAUNCH(ctx, k_blur_hess_tma<NT>, grid, BLUR_THREADS, G::SMEM, tm, src.rows, src.cols, dst_blur, dst_resp, dst_pitch, taps, norm2, pf.enable, pf.border,
+             pf.posThr, pf.negThr, pf.level, pf.pre, pf.pre_count, pf.pre_cap);
+  return MB2_OK;
+}
+
 }  // namespace
 using namespace MB2_NS;
 
@@ -429,6 +683,32 @@ int mb2_launch_blur(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* ds
       return MB2_ERR_UNSUPPORTED;
   }
   return MB2_OK;
+}
+
+// TMA-staged blur + Hessian (+ in-level extremum pre-filter).  The plane must satisfy the tensor-map rules: 16-byte aligned base, pitch a
+// multiple of 4 floats (every plane of the library has a pitch that is a multiple of 32 floats).
+int mb2_launch_blur_tma(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps, float norm2,
+                        const PrefilterArgs& pf) {
+  if (((uintptr_t)src.p & 15) != 0 || (src.pitch & 3) != 0) { ctx->set_error("pyramid blur: plane not aligned for a tensor map"); return MB2_ERR_ARG; }
+  switch (taps.n) {
+    case 3: return launch_blur_tma_nt<3>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 5: return launch_blur_tma_nt<5>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 7: return launch_blur_tma_nt<7>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 9: return launch_blur_tma_nt<9>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 11: return launch_blur_tma_nt<11>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 13: return launch_blur_tma_nt<13>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 15: return launch_blur_tma_nt<15>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 17: return launch_blur_tma_nt<17>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 19: return launch_blur_tma_nt<19>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    case 21: return launch_blur_tma_nt<21>(ctx, src, dst_blur, dst_resp, dst_pitch, taps, norm2, pf);
+    default:
+      ctx->set_error("pyramid blur: unsupported tap count " + std::to_string(taps.n));
+      return MB2_ERR_UNSUPPORTED;
+  }
+}
+void mb2_launch_nms_finish(mb2_ctx* ctx, const OctaveLevels& oct, const Candidate* pre, const int* pre_count, int pre_cap, Candidate* out, int* count,
+                           int capacity) {
+  MB2_LAUNCH(ctx, k_nms_finish, ctx->num_sms * 4, 128, 0, oct, pre, pre_count, pre_cap, out, count, capacity);
 }
 
 void mb2_launch_hessian(mb2_ctx* ctx, const ImgView& src, float* dst, int dst_pitch, float norm2) {

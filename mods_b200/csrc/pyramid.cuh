@@ -42,6 +42,12 @@ struct LocalizeParams {
 void mb2_launch_dog(mb2_ctx* ctx, const ImgView& level, float* resp, int resp_pitch, const float* d_taps, int n, float* d_tmp);
 int mb2_launch_blur(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps,
                     float norm2, int want_resp);
+// in-level part of the 3x3x3 extremum test, run by the kernel that produces a detection level (k_blur_hess_tma)
+struct PrefilterArgs { int enable, border; float posThr, negThr; int level; Candidate* pre; int* pre_count; int pre_cap; };
+int mb2_launch_blur_tma(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps, float norm2,
+                        const PrefilterArgs& pf);
+void mb2_launch_nms_finish(mb2_ctx* ctx, const OctaveLevels& oct, const Candidate* pre, const int* pre_count, int pre_cap, Candidate* out, int* count,
+                           int capacity);
 void mb2_launch_hessian(mb2_ctx* ctx, const ImgView& src, float* dst, int dst_pitch, float norm2);
 void mb2_launch_resize_half(mb2_ctx* ctx, const ImgView& src, float* dst, int orows, int ocols, int dst_pitch);
 void mb2_launch_nms(mb2_ctx* ctx, const ImgView& low, const ImgView& cur, const ImgView& high, int border, float posThr,
