@@ -221,6 +221,28 @@ int mb2_ctx_wait_tree(mb2_ctx* ctx, mb2_ctx* src);
  * outputs to learn the count first) to the host.  Returns that count. */
 int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* desc_u8, int capacity);
 
+/* ---- device-resident region records (view-sharded multi-GPU path) --------------------------------------------------
+ * One record per described region, MB2_REGION_RECORD_BYTES = 184: the 128-byte descriptor followed by 7 doubles of reproj_kp
+ * (x y a11 a12 a21 a22 s) -- everything MatchFlannFGINN, DuplicateFiltering and the LAF checks read of an AffineRegion
+ * (imagerepresentation.h:66 holds them per (detector, descriptor); the reference appends the views of an image in view-index order,
+ * imagerepresentation.cpp:2044-2045).  Records never leave the device between detection and matching: ranks exchange them with one
+ * ncclAllGather (mods_b200/host: mb2_views_sharded_pair).
+ * mb2_view_pack: records of the most recent mb2_detect_describe*_view into d_dst [D] (capacity records); returns the region count.
+ * mb2_slot_from_records: region set `slot` (descriptors + centres, as the view calls leave it) from n records [D].
+ * mb2_match_slots_range: mb2_match_slots for the queries [q_lo, q_hi) only (row-sharded N1 x N2 matching); rows carry the query's
+ * index in the whole set. */
+#define MB2_REGION_RECORD_BYTES 184
+/* device scratch + stream-ordered copies on the context's stream for callers above the C ABI that keep data on the device (the
+ * view-sharded driver): kind 0 host->device, 1 device->host, 2 device->device.  mb2_ctx_sync() waits for them. */
+int mb2_ctx_make_current(mb2_ctx* ctx);   /* cudaSetDevice(device of ctx) on the calling thread */
+void* mb2_dev_alloc(mb2_ctx* ctx, size_t bytes);
+void mb2_dev_free(mb2_ctx* ctx, void* p);
+int mb2_dev_copy(mb2_ctx* ctx, void* dst, const void* src, size_t bytes, int kind);
+int mb2_view_pack(mb2_ctx* ctx, void* d_dst, int capacity);
+int mb2_slot_from_records(mb2_ctx* ctx, int slot, const void* d_records, int n);
+int mb2_match_slots_range(mb2_ctx* ctx, int q_slot, int t_slot, int q_lo, int q_hi, double matchRatio, double contradDist, int nn,
+                          double* out, int capacity);
+
 /* Hands a device-resident region set over to another context on the same GPU (no copy).  Lets two host
  * threads run mb2_detect_describe_view for the two images of a pair on two contexts (= two streams), the
  * way mods.cpp:255-271 runs them as two OpenMP tasks, and match them afterwards on one. */

@@ -19,6 +19,7 @@ EXPORTS = [
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
     "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_ransac_f", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
     "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair", "mb2_synth_view", "mb2_detect_describe_synth_view", "mb2_ctx_tree_epoch", "mb2_ctx_wait_tree", "mb2_ctx_create_prio",
+    "mb2_view_pack", "mb2_slot_from_records", "mb2_match_slots_range", "mb2_dev_alloc", "mb2_dev_free", "mb2_dev_copy", "mb2_ctx_make_current",
 ]
 
 
@@ -116,6 +117,8 @@ def host_lib():
         _host.mb2_mods_launch_count.argtypes = [C.c_void_p]
         _host.mb2_mods_release.argtypes = [C.c_void_p]
         _host.mb2_mods_release.restype = None
+        _host.mb2_dist_comm_destroy.restype = None
+        _host.mb2_shard_view_cost.restype = C.c_double
     return _host
 
 
@@ -125,7 +128,7 @@ class PairConfig(C.Structure):
                 ("err_threshold", C.c_double), ("confidence", C.c_double), ("HLAFCoef", C.c_double),
                 ("max_samples", C.c_int), ("errorType", C.c_int), ("doSymmCheck", C.c_int), ("seed", C.c_long),
                 ("use_mser", C.c_int), ("mser", MserParams), ("mserMatchRatio", C.c_double),
-                ("n_hess_views", C.c_int), ("n_mser_views", C.c_int), ("hess_views", ViewParams * 32), ("mser_views", ViewParams * 32),
+                ("n_hess_views", C.c_int), ("n_mser_views", C.c_int), ("hess_views", ViewParams * 64), ("mser_views", ViewParams * 64),
                 ("useF", C.c_int), ("localOptimization", C.c_int), ("LAFCoef", C.c_double),
                 ("halfRootSIFT", C.c_int), ("reserved", C.c_int)]
 
@@ -133,7 +136,7 @@ class PairConfig(C.Structure):
         """View tiers of the step: lists of (tilt, phi, zoom[, InitSigma]) as SetVSPars produces them; None = identity view only."""
         for name, views in (("hess", hess), ("mser", mser)):
             views = views or []
-            assert len(views) <= 32
+            assert len(views) <= 64
             setattr(self, "n_%s_views" % name, len(views))
             arr = getattr(self, "%s_views" % name)
             for i, v in enumerate(views):
@@ -144,6 +147,29 @@ class PairConfig(C.Structure):
         c = PairConfig()
         host_lib().mb2_pair_config_default(C.byref(c))
         return c
+
+
+def set_vs_pars(scales, tilts, phi, prev=()):
+    """SetVSPars (synth-detection.cpp:103-234) through the host mirror: rows (zoom, tilt, phi) of one step, de-duplicated against `prev`."""
+    scales = np.asarray(scales, np.float64); tilts = np.asarray(tilts, np.float64)
+    prev = np.ascontiguousarray(np.asarray(prev, np.float64).reshape(-1, 3)); out = np.zeros((512, 3))
+    n = host_lib().mb2_host_set_vs_pars(scales.ctypes.data_as(C.c_void_p), C.c_int(len(scales)), tilts.ctypes.data_as(C.c_void_p), C.c_int(len(tilts)),
+                                        C.c_double(phi), prev.ctypes.data_as(C.c_void_p), C.c_int(len(prev)), out.ctypes.data_as(C.c_void_p), C.c_int(512))
+    return out[:n].copy()
+
+
+def iters_mods_cviu_views(which="c4"):
+    """View tiers of build/iters_mods_cviu.ini as (tilt, phi, zoom, InitSigma) lists for PairConfig.set_views: "small" = [HessianAffine4]
+    (11 views) + [MSER2] (3); "c4" = every SIFT tier, [HessianAffine4..6] (11 + 20 + 30) and [MSER2..3] (3 + 24) -- BASELINE config C4."""
+    m2 = set_vs_pars([1, 0.25, 0.125], [1], 360)
+    h4 = set_vs_pars([1], [1, 2, 4, 6, 8], 360)
+    if which == "small":
+        hess, mser = h4, m2
+    else:
+        m3 = set_vs_pars([1, 0.25, 0.125], [1, 3, 6, 9], 360, m2)
+        h5 = set_vs_pars([1], [1, 2, 4, 6, 8], 120, h4); h6 = set_vs_pars([1], [1, 2, 4, 6, 8], 60, np.concatenate([h4, h5]))
+        hess, mser = np.concatenate([h4, h5, h6]), np.concatenate([m2, m3])
+    return [(r[1], r[2], r[0], 0.2) for r in hess], [(r[1], r[2], r[0], 0.8) for r in mser]
 
 
 class PairResult(C.Structure):
@@ -405,6 +431,38 @@ class Context:
         self._check(host_lib().mb2_mods_pairs(self.h, C.c_int(n), p1, w1, h1, p2, w2, h2, C.byref(cfg), res, vo, caps), "mods_pairs")
         results = [res[k] for k in range(n)]
         return results, ([outs[k][:min(results[k].verified, capacity)] for k in range(n)] if capacity else None)
+
+    def views_sharded_pair(self, img1, img2, cfg, comm=None, rank=0, world=1, shape1=None, shape2=None, capacity=0):
+        """One pair with its synthesised views dealt out over the ranks (mb2_views_sharded_pair).  comm: dist_comm_create() handle
+        (None when world == 1).  Returns (PairResult, verified rows or None, digest (4 ints), stats dict)."""
+        h1, w1 = shape1 if shape1 is not None else img1.shape
+        h2, w2 = shape2 if shape2 is not None else img2.shape
+        res = PairResult(); dig = (C.c_ulonglong * 4)(); st = (C.c_double * 8)()
+        out = np.zeros((max(1, capacity), 4)) if capacity else None
+        f = host_lib().mb2_views_sharded_pair
+        n = self._check(f(self.h, C.c_void_p(comm or 0), C.c_int(rank), C.c_int(world), _ptr(img1), C.c_int(w1), C.c_int(h1), _ptr(img2), C.c_int(w2),
+                          C.c_int(h2), C.byref(cfg), C.byref(res), _ptr(out), C.c_int(capacity), dig, st), "views_sharded_pair")
+        stats = dict(zip(("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify", "allgather_bytes_per_rank", "regions", "units"), list(st)))
+        return res, (out[:min(n, capacity)] if capacity else None), [int(v) for v in dig], stats
+
+    def dist_comm_create(self, rank, world):
+        """ncclComm_t for the view-sharded driver: rank 0 draws the unique id, torch.distributed (already initialised by the caller) hands
+        it to every rank.  Returns an opaque handle for views_sharded_pair / dist_comm_destroy."""
+        import torch
+        import torch.distributed as dist
+        idb = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(host_lib().mb2_dist_unique_id(idb), "dist_unique_id")
+        t = torch.tensor(list(idb), dtype=torch.uint8, device="cuda:%d" % self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        idb = (C.c_ubyte * 128)(*[int(v) for v in t.cpu().tolist()])
+        comm = C.c_void_p()
+        self._check(host_lib().mb2_dist_comm_create(self.h, C.c_int(rank), C.c_int(world), idb, C.byref(comm)), "dist_comm_create")
+        return comm.value
+
+    def dist_comm_destroy(self, comm):
+        if comm:
+            host_lib().mb2_dist_comm_destroy(C.c_void_p(comm))
 
     def verify(self, frames14, keys, cfg=None, capacity=0):
         """DuplicateFiltering + LORANSACFiltering of gathered tentatives (mb2_host_verify).  Returns (PairResult, verified rows)."""

@@ -1097,6 +1097,73 @@ int mb2_match_slots(mb2_ctx* ctx, int q_slot, int t_slot, double matchRatio, dou
   return match_core(ctx, q.desc.as<uint8_t>(), q.n, t.desc.as<uint8_t>(), t.n, t.xy.as<double>(), matchRatio, contradDist, nn, out, capacity);
 }
 
+int mb2_match_slots_range(mb2_ctx* ctx, int q_slot, int t_slot, int q_lo, int q_hi, double matchRatio, double contradDist, int nn, double* out,
+                          int capacity) {
+  if (!ctx || q_slot < 0 || q_slot >= MB2_MAX_SLOTS || t_slot < 0 || t_slot >= MB2_MAX_SLOTS || !out) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RegionSlot &q = ctx->slots[q_slot], &t = ctx->slots[t_slot];
+  if (q_lo < 0 || q_hi > q.n || q_lo > q_hi) return MB2_ERR_ARG;
+  if (q_hi == q_lo || t.n == 0) return 0;
+  const int n = match_core(ctx, q.desc.as<uint8_t>() + (size_t)q_lo * 128, q_hi - q_lo, t.desc.as<uint8_t>(), t.n, t.xy.as<double>(), matchRatio, contradDist,
+                           nn, out, capacity);
+  for (int i = 0; i < n && i < capacity; i++) out[(size_t)i * 7] += q_lo;
+  return n;
+}
+
+namespace MB2_NS {
+__global__ void k_pack_records(const KeyOut* __restrict__ reproj, const uint8_t* __restrict__ desc, int n, uint8_t* __restrict__ dst) {
+  // one warp per record: 128 descriptor bytes as 32 words, then 7 doubles
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  uint8_t* r = dst + (size_t)i * MB2_REGION_RECORD_BYTES;
+  reinterpret_cast<uint32_t*>(r)[lane] = reinterpret_cast<const uint32_t*>(desc + (size_t)i * 128)[lane];
+  if (lane < 7) reinterpret_cast<double*>(r + 128)[lane] = reproj[i].v[lane];
+}
+__global__ void k_unpack_records(const uint8_t* __restrict__ src, int n, uint8_t* __restrict__ desc, double* __restrict__ xy) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const uint8_t* r = src + (size_t)i * MB2_REGION_RECORD_BYTES;
+  reinterpret_cast<uint32_t*>(desc + (size_t)i * 128)[lane] = reinterpret_cast<const uint32_t*>(r)[lane];
+  if (lane < 2) xy[(size_t)i * 2 + lane] = reinterpret_cast<const double*>(r + 128)[lane];
+}
+}  // namespace MB2_NS
+
+int mb2_ctx_make_current(mb2_ctx* ctx) { if (!ctx) return MB2_ERR_ARG; MB2_CUDA_CHECK(ctx, cudaSetDevice(ctx->device)); return MB2_OK; }
+void* mb2_dev_alloc(mb2_ctx* ctx, size_t bytes) {
+  if (!ctx) return nullptr;
+  cudaSetDevice(ctx->device);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { ctx->set_error("mb2_dev_alloc: out of device memory"); return nullptr; }
+  return p;
+}
+void mb2_dev_free(mb2_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+int mb2_dev_copy(mb2_ctx* ctx, void* dst, const void* src, size_t bytes, int kind) {
+  if (!ctx || kind < 0 || kind > 2 || (bytes && (!dst || !src))) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (bytes) MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+  return MB2_OK;
+}
+
+int mb2_view_pack(mb2_ctx* ctx, void* d_dst, int capacity) {
+  if (!ctx || (!d_dst && capacity > 0)) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const int k = ctx->last_view_n;
+  if (k > capacity) { ctx->set_error("view_pack: capacity too small"); return MB2_ERR_CAPACITY; }
+  if (k > 0) MB2_LAUNCH(ctx, MB2_NS::k_pack_records, (k * 32 + 255) / 256, 256, 0, ctx->rs_c.as<KeyOut>(), ctx->desc_u8.as<uint8_t>(), k, (uint8_t*)d_dst);
+  return k;
+}
+
+int mb2_slot_from_records(mb2_ctx* ctx, int slot, const void* d_records, int n) {
+  if (!ctx || slot < 0 || slot >= MB2_MAX_SLOTS || n < 0 || (n > 0 && !d_records)) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  RegionSlot& s = ctx->slots[slot];
+  MB2_CUDA_CHECK(ctx, s.desc.reserve((size_t)std::max(n, 1) * 128));
+  MB2_CUDA_CHECK(ctx, s.xy.reserve((size_t)std::max(n, 1) * 16));
+  if (n > 0) MB2_LAUNCH(ctx, MB2_NS::k_unpack_records, (n * 32 + 255) / 256, 256, 0, (const uint8_t*)d_records, n, s.desc.as<uint8_t>(), s.xy.as<double>());
+  s.n = n;
+  return n;
+}
+
 int mb2_score_models(mb2_ctx* ctx, int which, const double* u, int len, const double* models, int K, double th, double* resid, int* I,
                      double* J) {
   if (!ctx || !u || !models || len < 0 || K < 0 || which < 0 || which > 5) return MB2_ERR_ARG;

@@ -202,7 +202,7 @@ int loransac_core(mb2_ctx* ctx, const double* frames14, int n, const RANSACPars&
 // ---- C door for bench.py / tests: one MODS iteration on one image pair (mods.cpp:229-415, step 0 of
 // an iters file that has a single HessianAffine view tier with the identity view) --------------------
 extern "C" {
-#define MB2_MAX_PAIR_VIEWS 32
+#define MB2_MAX_PAIR_VIEWS 64
 typedef struct {
   mb2_hessaff_params det;
   mb2_orientation_params ori;
@@ -249,6 +249,19 @@ int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img1, const in
  * driver (mods_b200/sharding.py), where rank 0 verifies the tentatives gathered from all ranks.  Returns the verified count. */
 int mb2_host_verify(mb2_ctx* ctx, const double* frames14, const double* key, int n, const mb2_pair_config* cfg, mb2_pair_result* res,
                     double* verified_out, int capacity);
+/* ---- view-sharded pair over the ranks of one node (BASELINE config C4; mods_sharded.cpp) ----------------------------
+ * mb2_dist_unique_id (rank 0) -> hand the 128 bytes to every rank -> mb2_dist_comm_create on every rank (its ncclComm_t).  NCCL is
+ * bound at run time (libnccl.so.2).  mb2_views_sharded_pair: see mods_sharded.cpp; img1 / img2 are the same on every rank, the result
+ * is complete on rank 0; digest (4 x u64, optional) is identical on every rank and for every world size. */
+int mb2_dist_unique_id(unsigned char* id128);
+int mb2_dist_comm_create(mb2_ctx* ctx, int rank, int world, const unsigned char* id128, void** comm);
+void mb2_dist_comm_destroy(void* comm);
+int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
+                           const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity, unsigned long long* digest, double* stats);
+/* the unit plan on its own (checked without a GPU): cost of a view, longest-processing-time-first owners, offsets in the gathered buffer */
+double mb2_shard_view_cost(int w, int h, double tilt, double zoom);
+void mb2_shard_assign(const double* costs, int n_units, int world, int* owner);
+int mb2_shard_layout(const int* owner, const int* counts, int n_units, int world, int* src_off);
 /* test doors: feature cache of one (detector, descriptor) set through ImageRepresentation::SaveRegions / LoadRegions */
 int mb2_host_save_regions(const char* fname, const char* det, const char* desc, int n, const double* det_kp, const double* reproj_kp, const uint8_t* desc_u8);
 int mb2_host_load_regions(const char* fname, const char* det, const char* desc, int capacity, double* det_kp, double* reproj_kp, uint8_t* desc_u8);

@@ -1,0 +1,314 @@
+// View-sharded pair driver (BASELINE config C4): the synthesised views of both images -- the reference's own unit of
+// parallelism (`#pragma omp parallel for` over views, imagerepresentation.cpp:621) -- are dealt out over the ranks of ONE node, one
+// process per GPU.  Every rank detects / describes its views (mb2_detect_describe_synth_view) and leaves the regions on its device as
+// 184-byte records; ONE ncclAllGather of the padded record buffers (plus an all-gather of the per-unit counts) gives every rank all
+// regions; they are put in the reference's order -- detector, then view index, then detection order (imagerepresentation.cpp:2044-2045)
+// -- by device-to-device copies; the N1 x N2 matching of every detector is split by query rows (mb2_match_slots_range); the tentative
+// rows are all-gathered; rank 0 runs DuplicateFiltering + LORANSACFiltering (mb2_host_verify).  Nothing on this path goes through host
+// numpy; the host sees counts, the tentative rows and (rank 0) the 7-double frames of the regions for the verification.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2: in a process that imported torch this is torch's own copy), so libmods_host.so has
+// no link-time dependency on it and single-GPU users never load it.
+#include "mods_host.hpp"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+// ---- the five NCCL entry points, restated from nccl.h (2.x ABI) ------------------------------------------------------------------
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void* ncclComm_h;
+typedef int (*fn_GetUniqueId)(ncclUniqueId_t*);
+typedef int (*fn_CommInitRank)(ncclComm_h*, int, ncclUniqueId_t, int);
+typedef int (*fn_CommDestroy)(ncclComm_h);
+typedef int (*fn_AllGather)(const void*, void*, size_t, int /*ncclDataType_t*/, ncclComm_h, void* /*cudaStream_t*/);
+typedef const char* (*fn_GetErrorString)(int);
+struct Nccl {
+  void* lib = nullptr;
+  fn_GetUniqueId GetUniqueId = nullptr; fn_CommInitRank CommInitRank = nullptr; fn_CommDestroy CommDestroy = nullptr;
+  fn_AllGather AllGather = nullptr; fn_GetErrorString GetErrorString = nullptr;
+  bool load() {
+    if (lib) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return false;
+    GetUniqueId = (fn_GetUniqueId)dlsym(lib, "ncclGetUniqueId"); CommInitRank = (fn_CommInitRank)dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (fn_CommDestroy)dlsym(lib, "ncclCommDestroy"); AllGather = (fn_AllGather)dlsym(lib, "ncclAllGather");
+    GetErrorString = (fn_GetErrorString)dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllGather;
+  }
+};
+Nccl g_nccl;
+const int NCCL_INT8 = 0;   // ncclInt8 / ncclChar (nccl.h: ncclDataType_t)
+
+struct DBuf {   // device scratch of one call (through the C ABI: the host library does not link the CUDA runtime)
+  mb2_ctx* ctx = nullptr; void* p = nullptr; size_t cap = 0;
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    if (p) mb2_dev_free(ctx, p);
+    p = mb2_dev_alloc(ctx, n + 256); cap = p ? n + 256 : 0;
+    return p != nullptr;
+  }
+  ~DBuf() { if (p) mb2_dev_free(ctx, p); }
+};
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+extern "C" {
+
+// ---- unit plan (plain C, checked without a GPU by tests/test_sharding_gloo.py) --------------------------------------------------------
+// Pixel count of a synthesised view: tilt t shrinks one side by 1 / t, zoom z both sides by z (synth-detection.cpp:301-342).
+double mb2_shard_view_cost(int w, int h, double tilt, double zoom) { return ((double)w * zoom) * ((double)h * zoom) / std::max(std::fabs(tilt), 1e-9); }
+
+// Longest-processing-time-first over `world` ranks, deterministic (ties: lower unit, lower rank): owner[u] = rank of unit u.
+void mb2_shard_assign(const double* costs, int n_units, int world, int* owner) {
+  std::vector<int> order(n_units);
+  for (int i = 0; i < n_units; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return costs[a] > costs[b]; });
+  std::vector<double> load(std::max(world, 1), 0.0);
+  for (int u : order) {
+    int r = 0;
+    for (int k = 1; k < world; k++) if (load[k] < load[r]) r = k;
+    owner[u] = r; load[r] += costs[u];
+  }
+}
+
+// Where the records of every unit sit in the all-gathered buffer (world blocks of `stride` records; a rank packs its units in ascending
+// unit order): src_off[u] in records.  Returns the stride = the largest per-rank total (at least 1).
+int mb2_shard_layout(const int* owner, const int* counts, int n_units, int world, int* src_off) {
+  std::vector<long long> tot(std::max(world, 1), 0);
+  for (int u = 0; u < n_units; u++) tot[owner[u]] += counts[u];
+  long long stride = 1;
+  for (long long t : tot) stride = std::max(stride, t);
+  std::vector<long long> run(std::max(world, 1), 0);
+  for (int u = 0; u < n_units; u++) { src_off[u] = (int)(owner[u] * stride + run[owner[u]]); run[owner[u]] += counts[u]; }
+  return (int)stride;
+}
+
+// ---- communicator ----------------------------------------------------------------------------------------------------------------
+int mb2_dist_unique_id(unsigned char* id128) {
+  if (!id128 || !g_nccl.load()) return MB2_ERR_UNSUPPORTED;
+  ncclUniqueId_t id;
+  if (g_nccl.GetUniqueId(&id) != 0) return MB2_ERR_CUDA;
+  std::memcpy(id128, id.internal, 128);
+  return MB2_OK;
+}
+int mb2_dist_comm_create(mb2_ctx* ctx, int rank, int world, const unsigned char* id128, void** comm) {
+  if (!ctx || !comm || !id128 || rank < 0 || rank >= world || !g_nccl.load()) return MB2_ERR_ARG;
+  if (mb2_ctx_make_current(ctx) != MB2_OK) return MB2_ERR_CUDA;   // the communicator lives on the context's device
+  ncclUniqueId_t id; std::memcpy(id.internal, id128, 128);
+  ncclComm_h c = nullptr;
+  if (g_nccl.CommInitRank(&c, world, id, rank) != 0) return MB2_ERR_CUDA;
+  *comm = c;
+  return MB2_OK;
+}
+void mb2_dist_comm_destroy(void* comm) { if (comm && g_nccl.lib) g_nccl.CommDestroy((ncclComm_h)comm); }
+
+// ---- one pair, views sharded over the ranks ------------------------------------------------------------------------------------------
+// img1 / img2: gray f32 [H|D], the SAME on every rank.  comm: mb2_dist_comm_create (may be NULL when world == 1).  The result is
+// complete on rank 0 (other ranks fill regions / tentatives only).  digest (optional, 4 x u64): order-sensitive checksums of the
+// gathered region records and of the tentative rows -- identical on every rank and for every world size, which is what the tests
+// and bench.py assert.  stats (optional, 8 doubles): ms views, ms gather, ms match, ms tentative gather, ms verify, all-gather payload
+// bytes per rank, regions of both images, units of this rank.
+int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
+                           const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity, unsigned long long* digest, double* stats) {
+  if (!ctx || !img1 || !img2 || !cfg || !res || world < 1 || rank < 0 || rank >= world || (world > 1 && (!comm || !g_nccl.load()))) return MB2_ERR_ARG;
+  std::memset(res, 0, sizeof *res);
+  void* st = mb2_ctx_stream(ctx);
+  const double t_start = now_ms();
+  // ---- units: (image, detector, view), detector-major inside an image as RegionVectorMap orders them
+  struct Unit { int image, det; mb2_view_params vp; };
+  std::vector<Unit> units;
+  const mb2_view_params ident{1.0, 0.0, 1.0, 0.5, 1};
+  for (int im = 0; im < 2; im++)
+    for (int det = 0; det < (cfg->use_mser ? 2 : 1); det++) {
+      const int n = det == 0 ? cfg->n_hess_views : cfg->n_mser_views;
+      const mb2_view_params* v = det == 0 ? cfg->hess_views : cfg->mser_views;
+      if (n <= 0) units.push_back(Unit{im, det, ident});
+      for (int i = 0; i < n && i < MB2_MAX_PAIR_VIEWS; i++) units.push_back(Unit{im, det, v[i]});
+    }
+  const int U = (int)units.size();
+  std::vector<double> costs(U);
+  for (int u = 0; u < U; u++) costs[u] = mb2_shard_view_cost(units[u].image ? w2 : w1, units[u].image ? h2 : h1, units[u].vp.tilt, units[u].vp.zoom);
+  std::vector<int> owner(U), counts(U, 0);
+  mb2_shard_assign(costs.data(), U, world, owner.data());
+
+  // ---- my views: records appended to the send buffer (grown by doubling; capacity in records)
+  const int REC = MB2_REGION_RECORD_BYTES;
+  DBuf send, recv, d_counts, ordered[4], d_rows;
+  for (DBuf* b : {&send, &recv, &d_counts, &ordered[0], &ordered[1], &ordered[2], &ordered[3], &d_rows}) b->ctx = ctx;
+  size_t send_cap = (size_t)std::max(w1 * h1, w2 * h2) / 16 + 65536, used = 0;
+  if (!send.reserve(send_cap * REC)) return MB2_ERR_CUDA;
+  int my_units = 0;
+  for (int u = 0; u < U; u++) {
+    if (owner[u] != rank) continue;
+    my_units++;
+    const Unit& un = units[u];
+    const int n = mb2_detect_describe_synth_view(ctx, un.image ? img2 : img1, un.image ? w2 : w1, un.image ? h2 : h1, &un.vp, un.det == 0 ? 0 : 3, &cfg->det,
+                                                 &cfg->mser, &cfg->ori, &cfg->desc, MB2_MAX_SLOTS - 1, 0, nullptr, nullptr, nullptr, 0);
+    if (n < 0) return n;
+    if (used + (size_t)n > send_cap) {   // grow, keeping what is already packed
+      size_t ncap = std::max(send_cap * 2, used + (size_t)n);
+      void* np_ = mb2_dev_alloc(ctx, ncap * REC + 256);
+      if (!np_) return MB2_ERR_CUDA;
+      mb2_dev_copy(ctx, np_, send.p, used * REC, 2);
+      mb2_ctx_sync(ctx);
+      mb2_dev_free(ctx, send.p); send.p = np_; send.cap = ncap * REC + 256; send_cap = ncap;
+    }
+    const int k = mb2_view_pack(ctx, (unsigned char*)send.p + used * REC, (int)(send_cap - used));
+    if (k < 0) return k;
+    counts[u] = k; used += (size_t)k;
+  }
+  const double t_views = now_ms();
+
+  // ---- counts of every unit on every rank (each rank contributes its own units, zeros elsewhere), then ONE all-gather of the records
+  std::vector<int> all_counts(counts);
+  if (world > 1) {
+    if (!d_counts.reserve((size_t)U * 4 * (world + 1))) return MB2_ERR_CUDA;
+    int* d_mine = (int*)d_counts.p; int* d_all = d_mine + U;
+    mb2_dev_copy(ctx, d_mine, counts.data(), (size_t)U * 4, 0);
+    if (g_nccl.AllGather(d_mine, d_all, (size_t)U * 4, NCCL_INT8, (ncclComm_h)comm, st) != 0) return MB2_ERR_CUDA;
+    std::vector<int> g((size_t)U * world);
+    mb2_dev_copy(ctx, g.data(), d_all, g.size() * 4, 1);
+    if (mb2_ctx_sync(ctx) != MB2_OK) return MB2_ERR_CUDA;
+    for (int u = 0; u < U; u++) all_counts[u] = g[(size_t)owner[u] * U + u];
+  }
+  std::vector<int> src_off(U);
+  const int stride = mb2_shard_layout(owner.data(), all_counts.data(), U, world, src_off.data());
+  const unsigned char* gathered = (const unsigned char*)send.p;
+  if (world > 1) {
+    if ((size_t)stride > send_cap) {   // the padded block must be readable: grow the send buffer to the stride
+      void* np_ = mb2_dev_alloc(ctx, (size_t)stride * REC + 256);
+      if (!np_) return MB2_ERR_CUDA;
+      mb2_dev_copy(ctx, np_, send.p, used * REC, 2);
+      mb2_ctx_sync(ctx);
+      mb2_dev_free(ctx, send.p); send.p = np_; send.cap = (size_t)stride * REC + 256; send_cap = stride;
+    }
+    if (!recv.reserve((size_t)stride * REC * world)) return MB2_ERR_CUDA;
+    if (g_nccl.AllGather(send.p, recv.p, (size_t)stride * REC, NCCL_INT8, (ncclComm_h)comm, st) != 0) return MB2_ERR_CUDA;
+    gathered = (const unsigned char*)recv.p;
+  }
+  // ---- the reference's order: per (image, detector) the units in view-index order
+  int set_n[4] = {0, 0, 0, 0};
+  for (int u = 0; u < U; u++) set_n[units[u].image * 2 + units[u].det] += all_counts[u];
+  for (int s = 0; s < 4; s++) if (!ordered[s].reserve((size_t)std::max(set_n[s], 1) * REC)) return MB2_ERR_CUDA;
+  {
+    int fill[4] = {0, 0, 0, 0};
+    for (int u = 0; u < U; u++) {
+      const int s = units[u].image * 2 + units[u].det;
+      if (all_counts[u] > 0)
+        mb2_dev_copy(ctx, (unsigned char*)ordered[s].p + (size_t)fill[s] * REC, gathered + (size_t)src_off[u] * REC, (size_t)all_counts[u] * REC, 2);
+      fill[s] += all_counts[u];
+    }
+  }
+  // slots: image 0 -> 0 (HessianAffine), 2 (MSER); image 1 -> 1, 3 -- the numbering mb2_mods_pair uses
+  for (int s = 0; s < 4; s++) {
+    const int rc = mb2_slot_from_records(ctx, (s >> 1) + 2 * (s & 1), ordered[s].p, set_n[s]);
+    if (rc < 0) return rc;
+  }
+  if (mb2_ctx_sync(ctx) != MB2_OK) return MB2_ERR_CUDA;
+  const double t_gather = now_ms();
+  res->regions1 = set_n[0] + set_n[1]; res->regions2 = set_n[2] + set_n[3]; res->mser_regions1 = set_n[1]; res->mser_regions2 = set_n[3];
+
+  // ---- matching, split by query rows; rows of all ranks gathered per detector
+  std::vector<double> rows_all;   // 8 doubles: detector + the 7 tentative columns, detector-major, query order
+  double t_match = 0, t_tgather = 0;
+  for (int det = 0; det < (cfg->use_mser ? 2 : 1); det++) {
+    const int nq = set_n[det], nt = set_n[2 + det];
+    const int lo = (int)((long long)nq * rank / world), hi = (int)((long long)nq * (rank + 1) / world);
+    std::vector<double> rows((size_t)std::max(hi - lo, 1) * 7);
+    int n = 0;
+    const double tm0 = now_ms();
+    if (hi > lo && nt > 0) {
+      n = mb2_match_slots_range(ctx, det == 0 ? 0 : 2, det == 0 ? 1 : 3, lo, hi, det == 0 ? cfg->matchRatio : cfg->mserMatchRatio, cfg->contradDist, 50, rows.data(), hi - lo);
+      if (n < 0) return n;
+    }
+    const double tm1 = now_ms();
+    t_match += tm1 - tm0;
+    std::vector<int> ncnt(world, n);
+    std::vector<double> got;
+    if (world > 1) {
+      if (!d_counts.reserve((size_t)4 * (world + 1))) return MB2_ERR_CUDA;
+      int* d_mine = (int*)d_counts.p; int* d_all = d_mine + 1;
+      mb2_dev_copy(ctx, d_mine, &n, 4, 0);
+      if (g_nccl.AllGather(d_mine, d_all, 4, NCCL_INT8, (ncclComm_h)comm, st) != 0) return MB2_ERR_CUDA;
+      mb2_dev_copy(ctx, ncnt.data(), d_all, (size_t)4 * world, 1);
+      if (mb2_ctx_sync(ctx) != MB2_OK) return MB2_ERR_CUDA;
+      int mx = 1;
+      for (int c : ncnt) mx = std::max(mx, c);
+      if (!d_rows.reserve((size_t)mx * 56 * (world + 1))) return MB2_ERR_CUDA;
+      unsigned char* d_mr = (unsigned char*)d_rows.p; unsigned char* d_ar = d_mr + (size_t)mx * 56;
+      mb2_dev_copy(ctx, d_mr, rows.data(), (size_t)n * 56, 0);
+      if (g_nccl.AllGather(d_mr, d_ar, (size_t)mx * 56, NCCL_INT8, (ncclComm_h)comm, st) != 0) return MB2_ERR_CUDA;
+      got.resize((size_t)mx * 7 * world);
+      mb2_dev_copy(ctx, got.data(), d_ar, got.size() * 8, 1);
+      if (mb2_ctx_sync(ctx) != MB2_OK) return MB2_ERR_CUDA;
+      for (int r = 0; r < world; r++)
+        for (int i = 0; i < ncnt[r]; i++) { rows_all.push_back(det); for (int c = 0; c < 7; c++) rows_all.push_back(got[((size_t)r * mx + i) * 7 + c]); }
+    } else
+      for (int i = 0; i < n; i++) { rows_all.push_back(det); for (int c = 0; c < 7; c++) rows_all.push_back(rows[(size_t)i * 7 + c]); }
+    int tot = 0;
+    for (int c : ncnt) tot += c;
+    if (world == 1) tot = n;
+    res->tentatives += tot;
+    if (det == 1) res->mser_tentatives = tot;
+    t_tgather += now_ms() - tm1;
+  }
+  // ---- checksums (order-sensitive): records of the four sets, tentative rows
+  if (digest) {
+    digest[0] = digest[1] = digest[2] = digest[3] = 0;
+    std::vector<unsigned char> h;
+    for (int s = 0; s < 4; s++) {
+      h.resize((size_t)set_n[s] * REC);
+      if (set_n[s]) { mb2_dev_copy(ctx, h.data(), ordered[s].p, h.size(), 1); mb2_ctx_sync(ctx); }
+      unsigned long long a = 1469598103934665603ull;   // FNV-1a over the bytes
+      for (unsigned char b : h) { a ^= b; a *= 1099511628211ull; }
+      digest[s >> 1] ^= a * (unsigned long long)(2 * (s & 1) + 1);
+    }
+    unsigned long long a = 1469598103934665603ull;
+    const unsigned char* rb = (const unsigned char*)rows_all.data();
+    for (size_t i = 0; i < rows_all.size() * 8; i++) { a ^= rb[i]; a *= 1099511628211ull; }
+    digest[2] = a; digest[3] = (unsigned long long)res->tentatives;
+  }
+  // ---- rank 0 verifies (mods.cpp:298-415)
+  const double t_v0 = now_ms();
+  int k = 0;
+  if (rank == 0 && res->tentatives > 0) {
+    std::vector<std::vector<double> > fr(4);   // the 7 doubles of every region of the four sets
+    for (int s = 0; s < 4; s++) {
+      std::vector<unsigned char> h((size_t)set_n[s] * REC);
+      if (set_n[s]) { mb2_dev_copy(ctx, h.data(), ordered[s].p, h.size(), 1); mb2_ctx_sync(ctx); }
+      fr[s].resize((size_t)set_n[s] * 7);
+      for (int i = 0; i < set_n[s]; i++) std::memcpy(&fr[s][(size_t)i * 7], &h[(size_t)i * REC + 128], 56);
+    }
+    const int T = res->tentatives;
+    std::vector<double> frames((size_t)T * 14), key(T);
+    for (int i = 0; i < T; i++) {
+      const double* r = &rows_all[(size_t)i * 8];
+      const int det = (int)r[0], q = (int)r[1], t0 = (int)r[2];
+      std::memcpy(&frames[(size_t)i * 14], &fr[det][(size_t)q * 7], 56);
+      std::memcpy(&frames[(size_t)i * 14 + 7], &fr[2 + det][(size_t)t0 * 7], 56);
+      key[i] = std::fabs(std::sqrt((double)((float)r[5] / (float)r[6])));   // TentativeCorrespExt::ratio = sqrt(d1 / d2), matching.cpp:449
+    }
+    mb2_pair_result vr; std::memset(&vr, 0, sizeof vr);
+    k = mb2_host_verify(ctx, frames.data(), key.data(), T, cfg, &vr, verified_out, capacity);
+    if (k < 0) return k;
+    res->unique_tentatives = vr.unique_tentatives; res->ransac_inliers = vr.ransac_inliers; res->verified = vr.verified;
+    std::memcpy(res->H, vr.H, sizeof vr.H); res->ms_duplicate = vr.ms_duplicate; res->ms_ransac = vr.ms_ransac;
+  }
+  const double t_end = now_ms();
+  res->ms_detect_describe = t_gather - t_start; res->ms_match = t_match; res->ms_total = t_end - t_start;
+  if (stats) {
+    stats[0] = t_views - t_start; stats[1] = t_gather - t_views; stats[2] = t_match; stats[3] = t_tgather; stats[4] = t_end - t_v0;
+    stats[5] = world > 1 ? (double)stride * REC : 0.0; stats[6] = res->regions1 + res->regions2; stats[7] = my_units;
+  }
+  return k;
+}
+
+}  // extern "C"

@@ -8,21 +8,38 @@ position in RegionVectorMap[det][desc] (views appended in view-index order, imag
 import numpy as np
 
 
+def _host():
+    import mods_b200 as mb
+    return mb.host_lib()
+
+
+def owners_c(costs, world):
+    """The shipped plan (mb2_shard_assign, mods_b200/host/mods_sharded.cpp): owner rank of every unit."""
+    import ctypes as C
+    costs = np.ascontiguousarray(costs, np.float64); owner = np.zeros(max(1, len(costs)), np.int32)
+    _host().mb2_shard_assign(costs.ctypes.data_as(C.c_void_p), C.c_int(len(costs)), C.c_int(world), owner.ctypes.data_as(C.c_void_p))
+    return owner[:len(costs)]
+
+
+def layout_c(owner, counts, world):
+    """mb2_shard_layout: (stride in records, offset of every unit's records in the all-gathered buffer of world x stride records)."""
+    import ctypes as C
+    owner = np.ascontiguousarray(owner, np.int32); counts = np.ascontiguousarray(counts, np.int32); off = np.zeros(max(1, len(owner)), np.int32)
+    stride = _host().mb2_shard_layout(owner.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), C.c_int(len(owner)), C.c_int(world),
+                                      off.ctypes.data_as(C.c_void_p))
+    return stride, off[:len(owner)]
+
+
 def assign_units(costs, world):
-    """Longest-processing-time-first: returns a list (per rank) of unit indices, deterministic."""
-    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
-    load = [0.0] * world
-    out = [[] for _ in range(world)]
-    for i in order:
-        r = min(range(world), key=lambda k: (load[k], k))
-        out[r].append(i)
-        load[r] += costs[i]
-    return [sorted(u) for u in out]
+    """Longest-processing-time-first (the C plan): returns a list (per rank) of unit indices, deterministic."""
+    owner = owners_c(costs, world)
+    return [[int(i) for i in np.flatnonzero(owner == r)] for r in range(world)]
 
 
 def view_cost(w, h, tilt=1.0, zoom=1.0):
     """Pixel count of a synthesised view: tilt t shrinks one side by 1/t, zoom z both by z (synth-detection.cpp:301-342)."""
-    return (w * zoom) * (h * zoom) / max(tilt, 1e-9)
+    import ctypes as C
+    return float(_host().mb2_shard_view_cost(C.c_int(int(w)), C.c_int(int(h)), C.c_double(tilt), C.c_double(zoom)))
 
 
 def merge_in_unit_order(gathered):

@@ -79,3 +79,22 @@ def test_mods_pair_with_view_tiers_equals_per_view_composition(ctx):
     cfg1 = mb.PairConfig.default(); cfg1.seed = 77; cfg1.use_mser = 1
     res1, _ = ctx.mods_pair(A, B, cfg1)
     assert res.regions1 > res1.regions1 and res.tentatives > res1.tentatives
+
+
+def test_views_sharded_driver_equals_pair_driver(ctx):
+    """mb2_views_sharded_pair at world size 1 (views -> 184-byte device records -> ordered sets -> row-range matching -> verification) gives
+    exactly what mb2_mods_pair gives for the same view tiers: counts and the verified list."""
+    import mods_b200 as mb
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(640, 480, seed=51, n_blobs=700); B = warp_image(A, gt_homography(640, 480), seed=52)
+    cfg = mb.PairConfig.default(); cfg.use_mser = 1; cfg.seed = 5
+    hess = [(1.0, 0.0, 1.0, 0.2), (2.0, 0.0, 1.0, 0.2), (4.0, 0.0, 1.0, 0.2), (4.0, np.pi / 2, 1.0, 0.2)]
+    mser = [(1.0, 0.0, 1.0, 0.8), (1.0, 0.0, 0.25, 0.8)]
+    cfg.set_views(hess, mser)
+    r1, v1 = ctx.mods_pair(A, B, cfg, capacity=1 << 15)
+    r2, v2, dig, st = ctx.views_sharded_pair(A, B, cfg, capacity=1 << 15)
+    f = lambda r: (r.regions1, r.regions2, r.mser_regions1, r.mser_regions2, r.tentatives, r.mser_tentatives, r.unique_tentatives, r.ransac_inliers, r.verified)
+    assert f(r1) == f(r2) and r1.verified > 100
+    assert np.array_equal(v1, v2) and np.array_equal(np.array(r1.H), np.array(r2.H))
+    r3, v3, dig3, _ = ctx.views_sharded_pair(A, B, cfg, capacity=1 << 15)
+    assert dig == dig3 and st["units"] == 12

@@ -122,3 +122,52 @@ def test_view_sharded_pair_equals_serial():
     assert len(want["HessianAffine"][4]) > 5
     frames, keys = sharding.frames_and_keys(got)
     assert frames.shape[1] == 14 and len(frames) == len(keys) == sum(len(v[4]) for v in got.values())
+
+
+# ---- the C driver's plan and wire layout (mods_b200/host/mods_sharded.cpp) with two gloo ranks ---------------------------------------
+def _layout_worker(rank, world, port, q):
+    """What mb2_views_sharded_pair does between detection and matching, on the CPU: every rank packs the 184-byte records of its units
+    in ascending unit order, the per-unit counts and the padded record blocks are all-gathered, and mb2_shard_layout says where every
+    unit sits in the gathered buffer."""
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    compute, match, units, costs = _oracle_workers()
+    owner = sharding.owners_c(costs, world)
+    counts = np.zeros(len(units), np.int32); blocks = []
+    for u in range(len(units)):
+        if owner[u] != rank:
+            continue
+        det, rep, desc = compute(units[u])
+        counts[u] = len(rep); blocks.append(sharding.pack_regions(rep, desc))
+    allc = [torch.zeros(len(units), dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(allc, torch.from_numpy(counts))
+    counts_all = np.array([int(allc[owner[u]][u]) for u in range(len(units))], np.int32)
+    stride, off = sharding.layout_c(owner, counts_all, world)
+    mine = np.concatenate(blocks) if blocks else np.zeros((0, sharding.REC), np.uint8)
+    pad = np.zeros((stride, sharding.REC), np.uint8); pad[:len(mine)] = mine
+    got = [torch.zeros((stride, sharding.REC), dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(got, torch.from_numpy(pad))
+    buf = np.concatenate([g.numpy() for g in got])
+    per_unit = [buf[off[u]: off[u] + counts_all[u]].copy() for u in range(len(units))]
+    if rank == 1:
+        q.put((owner.tolist(), counts_all.tolist(), int(stride), per_unit))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_c_plan_and_record_layout_with_two_ranks():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_layout_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    owner, counts, stride, per_unit = q.get(timeout=300)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    compute, match, units, costs = _oracle_workers()
+    assert sorted(set(owner)) == [0, 1] and stride == max(sum(c for c, o in zip(counts, owner) if o == r) for r in (0, 1))
+    for u, unit in enumerate(units):   # every unit's records arrive intact, wherever it was computed
+        det, rep, desc = compute(unit)
+        assert counts[u] == len(rep) and np.array_equal(per_unit[u], sharding.pack_regions(rep, desc)), u
+    assert sharding.REC == 184
