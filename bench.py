@@ -344,6 +344,9 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
     kernels = [{"kernel": k, "launches": v[0], "ms_per_pair": v[1] / steps, "share": v[1] / tot} for k, v in top[:16]]
     name, (n_launch, ms) = top[0]
+    tree_ms = sum(v[1] for k, v in prof.items() if "k_mtree" in k)
+    if tree_ms >= ms and tree_ms > 0:     # the component-tree pass (five kernels) is the dominant logical kernel even when one other kernel tops its parts
+        name, (n_launch, ms) = max(((k, v) for k, v in prof.items() if "k_mtree" in k), key=lambda kv: kv[1][1])
     avg_s = ms / 1e3 / max(1, n_launch)
     rl = None
     if "k_extract" in name:
@@ -353,15 +356,30 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
         rl = {"bound": "hbm", "kernel": name, "achieved": gb / 1e9 / avg_s if gb else None, "peak": peaks["hbm"], "unit": "GB/s",
               "frac": (gb / 1e9 / avg_s / peaks["hbm"]) if gb else None, "traffic": None,
               "note": "L2-gather / FP32-ALU kernel: algorithmic bytes = bilinear taps read + patch written (SURVEY 8d), peak = %s HBM copy" % peaks["src"]}
-    elif "k_mser_tree" in name:
-        # ~30 B/px per polarity (u8 read + sorted offset + label R/W + boundary pass); both polarities in one launch
+    elif "k_mtree" in name:
+        # The dominant work is the component tree of the MSER detector, now five kernels per image (tiles in shared memory, local sums,
+        # tile borders x 2, fix, gap walk): reported as ONE pass against SURVEY 8d's figure for it, ~30 B/px per polarity (u8 read + sorted
+        # offset + label R/W + boundary pass), both polarities of one image per launch group.
+        tree = {k: v for k, v in prof.items() if "k_mtree" in k}
+        groups = max(v[0] for k, v in tree.items() if "k_mtree_tiles" in k)          # launch groups (= images) in the profiled steps
+        ms_group = sum(v[1] for v in tree.values()) / max(1, groups)
         gb = 30.0 * 2 * w * h
-        rl = {"bound": "hbm", "kernel": name, "achieved": gb / 1e9 / avg_s, "peak": peaks["hbm"], "unit": "GB/s", "frac": gb / 1e9 / avg_s / peaks["hbm"],
-              "traffic": 7.8068e9 if (w, h) == (4096, 3072) else None,   # dram__bytes_read+write of one launch, ncu --set full (profiles/r1_full_d.md)
-              "traffic_note": "captured before the level was packed into the union-find word (the kernel has since lost its separate lev[] reads and 11 % of its time); to be re-captured",
-              "algorithmic_bytes": gb,
-              "note": "component tree of both polarities: 256 level-synchronous phases, each a chain of dependent reads -- latency bound, not bandwidth bound "
-                      "(DESIGN.md); peak = %s HBM copy" % peaks["src"]}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+                traffic = json.load(f).get("component_tree_%dx%d" % (w, h))
+        except Exception:
+            pass
+        rl = {"bound": "hbm", "kernel": "component tree of one image, both polarities: " + " + ".join(sorted(k.split("<")[0] for k in tree)),
+              "achieved": gb / 1e9 / (ms_group / 1e3), "peak": peaks["hbm"], "unit": "GB/s", "frac": gb / 1e9 / (ms_group / 1e3) / peaks["hbm"],
+              "traffic": traffic, "traffic_src": "dram__bytes_read.sum + dram__bytes_write.sum of the five kernels, ncu --set full (profiles/r2_full_tree.md, profiles/r2_traffic.json)",
+              "algorithmic_bytes": gb, "ms_per_launch_group": ms_group, "launches_per_group": sum(v[0] for v in tree.values()) / max(1, groups),
+              "top_kernel": {"name": name, "ms_per_launch": ms / max(1, n_launch), "algorithmic_bytes": 14.0 * w * h,
+                             "achieved_GBps": 14.0 * w * h / 1e9 / (ms / 1e3 / max(1, n_launch)),
+                             "note": "k_mtree_tiles alone: reads the f32 image (4 B/px), writes level + tree word of both polarities (10 B/px); issue bound "
+                                     "(67 pct issue slots, 7 of 32 lanes active: divergent pointer walks in shared memory), not bandwidth bound"},
+              "note": "lock-free merge of per-tile trees (mser_tree_build.cuh); round 1's level-synchronous k_mser_tree moved 10.3x its algorithmic bytes at 1.0 pct "
+                      "of the HBM peak; peak = " + peaks["src"] + " HBM copy"}
     elif "k_blur_hess" in name:
         # per image: every octave runs 4 incremental blurs with the Hessian fused (read 4 B + write blur 4 B + write response 4 B per pixel
         # of the octave, octaves sum to 4/3 W H) plus the initial blur of octave 0 (read 4 B + write 4 B): DESIGN.md, kernel table
@@ -374,15 +392,21 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
               "frac": gb / 1e9 / (ms / 1e3) / peaks["hbm"], "traffic": None, "algorithmic_bytes_per_launch": gb / max(1, n_launch)}
     elif "k_nn_tc" in name:
         rl = {"bound": "tensor", "kernel": name, "achieved": None, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": None, "traffic": None}
+    if rl is None:   # a per-region gather kernel on top (orientation / Baumberg / SIFT): L2-gather / FP32 bound, no HBM model -- say so instead of omitting the key
+        rl = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None,
+              "note": "per-region gather kernel (L2 / FP32 bound); see roofline_pyramid and roofline_nn for the two kernels the north star names"}
     # the two kernels the north star names, always reported
     extra = {}
-    pyr = [(k, v) for k, v in prof.items() if "k_blur_hess" in k or "k_nms" in k or "k_hessian" in k or "k_resize_half" in k]
+    pyr = [(k, v) for k, v in prof.items() if "k_blur_hess" in k or "k_nms" in k or "k_hessian" in k or "k_resize_half" in k]   # k_blur_hess_tma, k_nms_finish included
     if pyr:
         ms_pyr = sum(v[1] for _, v in pyr) / (2 * steps)  # per image
         bytes_pyr = 110.7 * w * h                          # level-granular model, B/px
         extra["roofline_pyramid"] = {"bound": "hbm", "achieved": bytes_pyr / 1e9 / (ms_pyr / 1e3), "peak": peaks["hbm"], "unit": "GB/s",
                                      "frac": bytes_pyr / 1e9 / (ms_pyr / 1e3) / peaks["hbm"], "ms_per_image": ms_pyr,
-                                     "algorithmic_bytes": bytes_pyr, "kernels": "k_blur_hess*+k_hessian+k_resize_half+k_nms (whole scale space of one image)"}
+                                     "algorithmic_bytes": bytes_pyr, "kernels": "k_blur_hess_tma*+k_hessian+k_resize_half+k_nms_finish (whole scale space of one image; TMA-staged tiles, in-level extremum test fused)",
+                                     "compulsory_bytes_if_fully_fused": 30.7 * w * h,
+                                     "note": "issue bound, not bandwidth bound: the parity contract forbids FMA (2 FP32 instructions per tap) and packed f32x2 "
+                                             "arithmetic gives no extra lane throughput on B200 (tools/micro/f32x2.cu: 36 T lane-ops/s either way)"}
     nn = [(k, v) for k, v in prof.items() if "k_nn_tc" in k]
     if nn:
         ms_nn = sum(v[1] for _, v in nn) / steps

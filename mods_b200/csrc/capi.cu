@@ -1126,7 +1126,30 @@ __global__ void k_unpack_records(const uint8_t* __restrict__ src, int n, uint8_t
   reinterpret_cast<uint32_t*>(desc + (size_t)i * 128)[lane] = reinterpret_cast<const uint32_t*>(r)[lane];
   if (lane < 2) xy[(size_t)i * 2 + lane] = reinterpret_cast<const double*>(r + 128)[lane];
 }
+__global__ void k_gather_frames(const uint8_t* __restrict__ q, const uint8_t* __restrict__ t, const int* __restrict__ qi, const int* __restrict__ ti, int n,
+                                double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 14) return;
+  const int r = i / 14, c = i - r * 14;
+  const uint8_t* rec = c < 7 ? q + (size_t)qi[r] * MB2_REGION_RECORD_BYTES : t + (size_t)ti[r] * MB2_REGION_RECORD_BYTES;
+  out[i] = reinterpret_cast<const double*>(rec + 128)[c < 7 ? c : c - 7];
+}
 }  // namespace MB2_NS
+
+int mb2_records_gather_frames(mb2_ctx* ctx, const void* d_q, const void* d_t, const int* q_idx, const int* t_idx, int n, double* frames14) {
+  if (!ctx || n < 0 || (n > 0 && (!d_q || !d_t || !q_idx || !t_idx || !frames14))) return MB2_ERR_ARG;
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)n * 8));
+  MB2_CUDA_CHECK(ctx, ctx->rs_b.reserve((size_t)n * 14 * 8));
+  int* d_qi = ctx->rs_a.as<int>(); int* d_ti = d_qi + n;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(d_qi, q_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(d_ti, t_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  MB2_LAUNCH(ctx, MB2_NS::k_gather_frames, (n * 14 + 255) / 256, 256, 0, (const uint8_t*)d_q, (const uint8_t*)d_t, d_qi, d_ti, n, ctx->rs_b.as<double>());
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(frames14, ctx->rs_b.p, (size_t)n * 14 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return n;
+}
 
 int mb2_ctx_make_current(mb2_ctx* ctx) { if (!ctx) return MB2_ERR_ARG; MB2_CUDA_CHECK(ctx, cudaSetDevice(ctx->device)); return MB2_OK; }
 void* mb2_dev_alloc(mb2_ctx* ctx, size_t bytes) {

@@ -280,21 +280,21 @@ int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const 
   const double t_v0 = now_ms();
   int k = 0;
   if (rank == 0 && res->tentatives > 0) {
-    std::vector<std::vector<double> > fr(4);   // the 7 doubles of every region of the four sets
-    for (int s = 0; s < 4; s++) {
-      std::vector<unsigned char> h((size_t)set_n[s] * REC);
-      if (set_n[s]) { mb2_dev_copy(ctx, h.data(), ordered[s].p, h.size(), 1); mb2_ctx_sync(ctx); }
-      fr[s].resize((size_t)set_n[s] * 7);
-      for (int i = 0; i < set_n[s]; i++) std::memcpy(&fr[s][(size_t)i * 7], &h[(size_t)i * REC + 128], 56);
-    }
+    // frames of the tentatives straight from the device records (per detector: image-0 set x image-1 set); keys from the distances
     const int T = res->tentatives;
     std::vector<double> frames((size_t)T * 14), key(T);
-    for (int i = 0; i < T; i++) {
-      const double* r = &rows_all[(size_t)i * 8];
-      const int det = (int)r[0], q = (int)r[1], t0 = (int)r[2];
-      std::memcpy(&frames[(size_t)i * 14], &fr[det][(size_t)q * 7], 56);
-      std::memcpy(&frames[(size_t)i * 14 + 7], &fr[2 + det][(size_t)t0 * 7], 56);
-      key[i] = std::fabs(std::sqrt((double)((float)r[5] / (float)r[6])));   // TentativeCorrespExt::ratio = sqrt(d1 / d2), matching.cpp:449
+    std::vector<int> qi(T), ti(T);
+    int done = 0;
+    for (int det = 0; det < (cfg->use_mser ? 2 : 1); det++) {
+      int n = 0;
+      for (int i = done; i < T && (int)rows_all[(size_t)i * 8] == det; i++, n++) {
+        const double* r = &rows_all[(size_t)i * 8];
+        qi[i] = (int)r[1]; ti[i] = (int)r[2];
+        key[i] = std::fabs(std::sqrt((double)((float)r[5] / (float)r[6])));   // TentativeCorrespExt::ratio = sqrt(d1 / d2), matching.cpp:449
+      }
+      const int rc = mb2_records_gather_frames(ctx, ordered[det].p, ordered[2 + det].p, qi.data() + done, ti.data() + done, n, frames.data() + (size_t)done * 14);
+      if (rc < 0) return rc;
+      done += n;
     }
     mb2_pair_result vr; std::memset(&vr, 0, sizeof vr);
     k = mb2_host_verify(ctx, frames.data(), key.data(), T, cfg, &vr, verified_out, capacity);

@@ -11,24 +11,7 @@ from mods_b200 import synth
 
 
 def tiers(which):
-    H = mb.host_lib()
-
-    def vs(scales, tilts, phi, prev):
-        scales = np.asarray(scales, np.float64); tilts = np.asarray(tilts, np.float64)
-        prev = np.ascontiguousarray(np.asarray(prev, np.float64).reshape(-1, 3)); out = np.zeros((512, 3))
-        n = H.mb2_host_set_vs_pars(scales.ctypes.data_as(C.c_void_p), C.c_int(len(scales)), tilts.ctypes.data_as(C.c_void_p), C.c_int(len(tilts)),
-                                   C.c_double(phi), prev.ctypes.data_as(C.c_void_p), C.c_int(len(prev)), out.ctypes.data_as(C.c_void_p), C.c_int(512))
-        return out[:n].copy()
-    m2 = vs([1, 0.25, 0.125], [1], 360, [])
-    h4 = vs([1], [1, 2, 4, 6, 8], 360, [])
-    if which == "small":
-        hess, mser = h4, m2
-    else:   # every SIFT tier of iters_mods_cviu.ini: [MSER2] 3 + [MSER3] 24, [HessianAffine4] 11 + [5] 20 + [6] 30
-        m3 = vs([1, 0.25, 0.125], [1, 3, 6, 9], 360, m2)
-        h5 = vs([1], [1, 2, 4, 6, 8], 120, h4); h6 = vs([1], [1, 2, 4, 6, 8], 60, np.concatenate([h4, h5]))
-        hess, mser = np.concatenate([h4, h5, h6]), np.concatenate([m2, m3])
-    # rows are (zoom, tilt, phi); set_views wants (tilt, phi, zoom, InitSigma)
-    return [(r[1], r[2], r[0], 0.2) for r in hess], [(r[1], r[2], r[0], 0.8) for r in mser]
+    return mb.iters_mods_cviu_views(which)
 
 
 def main():
@@ -67,7 +50,7 @@ def main():
     if rank == 0:
         print(json.dumps({"size": [w, h], "tiers": which, "views_per_image": [len(hess), len(mser)], "n_gpus": world, "ms_per_pair": 1e3 * float(np.median(times)),
                           "regions": [res.regions1, res.regions2], "tentatives": res.tentatives, "unique": res.unique_tentatives, "inliers": res.ransac_inliers,
-                          "verified": res.verified, "digest": ["%016x" % d for d in dig], "digest_same_on_all_ranks": all(d == dig for d in digs), "rank0_stats": st}))
+                          "verified": res.verified, "digest": ["%016x" % d for d in dig], "digest_same_on_all_ranks": all(d == dig for d in digs), "rank0_stats": st, "ms_duplicate": res.ms_duplicate, "ms_ransac": res.ms_ransac}))
     if world > 1:
         dist.barrier()
         ctx.dist_comm_destroy(comm)
