@@ -51,7 +51,7 @@ typedef struct {
   float rel_reg_number;
   int patchSize;              /* 41 */
   float mrSize;               /* 3*sqrt(3) */
-  int detectorType;           /* detector_type (structures.hpp): 0 DET_HESSIAN, 1 DET_DOG -- the response of every level becomes
+  int detectorType;           /* detector_type (structures.hpp): 0 DET_HESSIAN, 1 DET_DOG, 2 DET_HARRIS (pyramid.cpp:283-305) -- for DET_DOG the response of every level becomes
                                * level - GaussianBlur(level, sigma = curSigma^2) (pyramid.cpp:176-181, Response() :132-175), the
                                * threshold is used un-squared (pyramid.h:56-57) and the point type is the sign (DOG_DARK 10 /
                                * DOG_BRIGHT 11, pyramid.cpp:92-99); everything else is the same scale-space detector */
@@ -259,7 +259,8 @@ int mb2_slot_move(mb2_ctx* dst, int dst_slot, mb2_ctx* src, int src_slot);
  * [H|D].  out [H]: rows of 7 doubles { query, idx0, idxJ, idx1, d0, dJ, d1 } in query order,
  * i.e. TentativeCorrespExt{first, second, secondbad, secondbadby2ndcl, d1, d2, d2by2ndcl}.
  * Ties between equal distances: lower train index first (FLANN's order is unspecified).
- * matchRatio >= 1 (the "all points" branch, matching.cpp:402-428) is MB2_ERR_UNSUPPORTED.
+ * matchRatio >= 1 selects the "all points" branch (matching.cpp:397-428: NN paired with its first geometrically inconsistent neighbour,
+ * or with neighbour nn - 1), evaluated from an exact sorted k-NN table per query (2 <= nn <= 64).
  * Returns the number of tentatives. */
 int mb2_match_fginn(mb2_ctx* ctx, const uint8_t* q_desc, int nq, const uint8_t* t_desc, int nt,
                     const double* t_xy, double matchRatio, double contradDist, int nn, double* out,

@@ -40,6 +40,11 @@ class HessaffParams(C.Structure):
         return HessaffParams(5.3333, 3, 1.6, 10.0, 5, 16, 0.05, 19, 1, 0, 2000, -1.0, -1.0, 41, 3.0 * 3.0 ** 0.5, 0)
 
     @staticmethod
+    def harris():
+        """[HarrisAffine] of config_iter_mods_cviu.ini:28-44 (mode FixedTh, threshold 15, Baumberg with convergence threshold 0.1)."""
+        return HessaffParams(15.0, 3, 1.6, 10.0, 5, 16, 0.1, 19, 1, 0, 1000, 0.1, 0.5, 41, 3.0 * 3.0 ** 0.5, 2)
+
+    @staticmethod
     def dog():
         """[DoG] of config_iter_mods_cviu_wxbs.ini:45-59 with mode FixedTh: threshold 8, no Baumberg iteration."""
         return HessaffParams(8.0, 3, 1.6, 10.0, 5, 16, 0.05, 19, 0, 0, 3000, 0.01, 0.5, 41, 3.0 * 3.0 ** 0.5, 1)
@@ -431,6 +436,37 @@ class Context:
         self._check(host_lib().mb2_mods_pairs(self.h, C.c_int(n), p1, w1, h1, p2, w2, h2, C.byref(cfg), res, vo, caps), "mods_pairs")
         results = [res[k] for k in range(n)]
         return results, ([outs[k][:min(results[k].verified, capacity)] for k in range(n)] if capacity else None)
+
+    def mods_multi(self, img1, imgs2, cfg=None, capacity=0):
+        """mods_multi.cpp:232-330: one query image against N images (the query is described once).  Returns ([PairResult], [verified rows])."""
+        cfg = cfg or PairConfig.default()
+        n = len(imgs2)
+        P = C.c_void_p * max(1, n); I = C.c_int * max(1, n)
+        p2, w2, h2 = P(), I(), I()
+        for k, b in enumerate(imgs2):
+            p2[k] = _ptr(b).value; h2[k], w2[k] = b.shape
+        res = (PairResult * max(1, n))()
+        outs = [np.zeros((capacity, 4)) for _ in range(n)] if capacity else None
+        vo = P(*[o.ctypes.data for o in outs]) if capacity and n else None
+        caps = I(*([capacity] * n)) if capacity and n else None
+        self._check(host_lib().mb2_mods_multi(self.h, _ptr(img1), C.c_int(img1.shape[1]), C.c_int(img1.shape[0]), C.c_int(n), p2, w2, h2, C.byref(cfg), res, vo, caps),
+                    "mods_multi")
+        results = [res[k] for k in range(n)]
+        return results, ([outs[k][:min(results[k].verified, capacity)] for k in range(n)] if capacity else None)
+
+    def extract_features(self, img, fname, cfg=None):
+        """extract_features.cpp: describe the image and write the reference's text feature cache.  Returns the region count."""
+        cfg = cfg or PairConfig.default()
+        return self._check(host_lib().mb2_extract_features(self.h, _ptr(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.byref(cfg), str(fname).encode()),
+                           "extract_features")
+
+    def mods_pair_cached(self, cache1, cache2, cfg=None, capacity=0):
+        """mods.cpp's read_pre_extracted flow: LoadRegions for both images, then match + verify."""
+        cfg = cfg or PairConfig.default()
+        res = PairResult(); out = np.zeros((max(1, capacity), 4)) if capacity else None
+        n = self._check(host_lib().mb2_mods_pair_cached(self.h, str(cache1).encode(), str(cache2).encode(), C.byref(cfg), C.byref(res), _ptr(out), C.c_int(capacity)),
+                        "mods_pair_cached")
+        return res, (out[:min(n, capacity)] if capacity else None)
 
     def views_sharded_pair(self, img1, img2, cfg, comm=None, rank=0, world=1, shape1=None, shape2=None, capacity=0):
         """One pair with its synthesised views dealt out over the ranks (mb2_views_sharded_pair).  comm: dist_comm_create() handle

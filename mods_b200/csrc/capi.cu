@@ -257,7 +257,7 @@ struct PyramidLayout {
 int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par, double tilt, double zoom, int as_regions, int* n_out) {
   *n_out = 0;
   if (par.mode < 0 || par.mode > 4) { ctx->set_error("hessaff: unknown DetectorMode"); return MB2_ERR_ARG; }
-  if (par.detectorType < 0 || par.detectorType > 1) { ctx->set_error("scale-space detector: only DET_HESSIAN (0) and DET_DOG (1) are built"); return MB2_ERR_UNSUPPORTED; }
+  if (par.detectorType < 0 || par.detectorType > 2) { ctx->set_error("scale-space detector: DET_HESSIAN (0), DET_DOG (1) and DET_HARRIS (2) are built"); return MB2_ERR_UNSUPPORTED; }
   if (par.numberOfScales + 2 > MB2_MAX_LEVELS || par.smmWindowSize != 19 || par.border < 2) {
     ctx->set_error("hessaff: unsupported numberOfScales / smmWindowSize / border"); return MB2_ERR_ARG;
   }
@@ -317,7 +317,8 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
 
   // thresholds (pyramid.h:46-69)
   // every mode but FIXED_TH opens all response gates: every 3x3x3 extremum is localised and goes through Baumberg (pyramid.h:59-60)
-  const bool dog = par.detectorType == 1;
+  const bool harris = par.detectorType == 2;
+  const bool dog = par.detectorType != 0;   // "the response comes from its own kernels after the blur" (DET_DOG and DET_HARRIS)
   const float finalThreshold = par.mode != 0 ? 0.0f : (dog ? par.threshold : par.threshold * par.threshold);   // squared for DET_HESSIAN only
   const float positiveThreshold = par.mode != 0 ? 0.0f : (float)(0.8 * par.threshold), negativeThreshold = -positiveThreshold;
   const double er = par.edgeEigenValueRatio;
@@ -342,7 +343,8 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
   // DET_DOG: the response of level l is level - GaussianBlur(level, sigma = levelSigma[l]^2) in every octave: taps of the NL wide
   // kernels on the device (ctx->dog_taps), one scratch plane for the row pass
   std::vector<int> dog_n(NL, 0), dog_off(NL, 0);
-  if (dog) {
+  if (harris) MB2_CUDA_CHECK(ctx, ctx->dog_tmp.reserve((size_t)L.pitch[0] * L.rows[0] * 4 * 6));   // gradient products and their blurs
+  if (dog && !harris) {
     std::vector<float> all;
     for (int l = 0; l < NL; l++) {
       const float sg = levelSigma[l] * levelSigma[l];
@@ -355,7 +357,15 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
     MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // `all` is a host temporary
     MB2_CUDA_CHECK(ctx, ctx->dog_tmp.reserve((size_t)L.pitch[0] * L.rows[0] * 4));
   }
+  int resp_rc = MB2_OK;   // first failure of a separate response pass
   auto dog_response = [&](const OctaveLevels& oc, int l) {
+    if (harris) {   // HarrisResponse(level, norm = levelSigma^2): sigmasq = 0.6 norm, sigma = sqrt(sigmasq) (pyramid.cpp:287-288)
+      const float norm = levelSigma[l] * levelSigma[l];
+      const float sigmasq = 0.6 * norm;
+      const int hrc = mb2_launch_harris(ctx, oc.blur[l], (float*)oc.resp[l].p, oc.resp[l].pitch, make_taps(std::sqrt(sigmasq)), sigmasq, ctx->dog_tmp.as<float>());
+      if (hrc && !resp_rc) resp_rc = hrc;
+      return;
+    }
     mb2_launch_dog(ctx, oc.blur[l], (float*)oc.resp[l].p, oc.resp[l].pitch, ctx->dog_taps.as<float>() + dog_off[l], dog_n[l], ctx->dog_tmp.as<float>());
   };
 
@@ -409,7 +419,7 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
     if (n_cand > 0) {
       LocalizeParams lp;
       lp.edgeScoreThreshold = edgeScoreThreshold; lp.finalThreshold = finalThreshold; lp.pixelDistance = pixelDistance;
-      lp.numberOfScales = S; lp.detectorType = dog ? 1 : 0;
+      lp.numberOfScales = S; lp.detectorType = par.detectorType;
       // findLevelKeypoints(curSigma): curSigma at level lv is initialSigma * sigmaStep^lv accumulated in float
       {
         float cs = par.initialSigma;
@@ -421,6 +431,7 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
     }
     pixelDistance *= 2.0;
   }
+  if (resp_rc) return resp_rc;
   int n_kp = 0;
   MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_kp, d_counts + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -624,7 +635,8 @@ int match_core(mb2_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int
   if (nq <= 0 || nt <= 0) return 0;
   if (!(matchRatio > 0)) { ctx->set_error("match: matchRatio must be > 0"); return MB2_ERR_ARG; }
   const double sqminratio = matchRatio * matchRatio, contr2 = contradDist * contradDist;
-  if (sqminratio >= 1.0) { ctx->set_error("match: the matchRatio >= 1 branch (matching.cpp:402-428) is not built"); return MB2_ERR_UNSUPPORTED; }
+  const bool all_points = sqminratio >= 1.0;   // matching.cpp:397-428
+  if (all_points && (nn < 2 || nn > 64)) { ctx->set_error("match: matchRatio >= 1 needs 2 <= nn <= 64"); return MB2_ERR_ARG; }
   const int nq_pad = (nq + 255) & ~255, nt_pad = (nt + 255) & ~255;
   MB2_CUDA_CHECK(ctx, ctx->nn_a.reserve((size_t)nq_pad * 128 * 2 + (size_t)nq_pad * 4));
   MB2_CUDA_CHECK(ctx, ctx->nn_b.reserve((size_t)nt_pad * 128 * 2 + (size_t)nt_pad * 4));
@@ -646,12 +658,15 @@ int match_core(mb2_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int
   const char* impl = std::getenv("MB2_NN_IMPL");
   const bool simt = impl && std::strcmp(impl, "simt") == 0;
   int rc;
-  for (int pass = 1; pass <= 2; pass++) {
-    if (simt) mb2_nn_pass_simt(ctx, pass, d_q, nq, d_t, nt, qn, tn, st, d_txy, contr2);
-    else if ((rc = mb2_nn_pass_tc(ctx, pass, q_bf16, nq, nq_pad, t_bf16, nt_pad, qn, tn, st, d_txy, contr2))) return rc;
-    if (pass == 1) mb2_nn_threshold(ctx, st, nq, qn, sqminratio);
+  if (all_points) mb2_nn_topk(ctx, d_q, nq, d_t, nt, qn, tn, d_txy, contr2, nn, rows, accept);
+  else {
+    for (int pass = 1; pass <= 2; pass++) {
+      if (simt) mb2_nn_pass_simt(ctx, pass, d_q, nq, d_t, nt, qn, tn, st, d_txy, contr2);
+      else if ((rc = mb2_nn_pass_tc(ctx, pass, q_bf16, nq, nq_pad, t_bf16, nt_pad, qn, tn, st, d_txy, contr2))) return rc;
+      if (pass == 1) mb2_nn_threshold(ctx, st, nq, qn, sqminratio);
+    }
+    mb2_nn_finalize(ctx, st, nq, nt, nn, rows, accept);
   }
-  mb2_nn_finalize(ctx, st, nq, nt, nn, rows, accept);
   // ordered compaction of the accepted rows
   size_t cub_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr, nq, ctx->stream);

@@ -427,6 +427,48 @@ __global__ void k_finalize(NNState st, int nq, int nt, int nn, MatchRow* __restr
   rows[i] = r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// matchRatio >= 1: the "all points" branch of MatchFlannFGINN (matching.cpp:397-428), which needs the sorted k-NN table itself: the
+// tentative of a query is its NN paired with the first neighbour (in distance order, ties by train index) that lies farther than
+// contradDist from the NN in the image, or with neighbour nn - 1 when there is none.  One thread per query keeps the exact nn nearest
+// (distance, index) pairs in an insertion-sorted list while it walks all trains (every lane of a warp reads the same train row: one
+// broadcast load); distances are exact integers in f32.  Rarely used (no shipped iters file sets a ratio >= 1), not tuned.
+// ---------------------------------------------------------------------------------------------
+#define MB2_NN_MAXK 64
+__global__ void __launch_bounds__(128)
+k_nn_topk(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt, const float* __restrict__ qn, const float* __restrict__ tn,
+          const double* __restrict__ txy, double contr2, int nn, MatchRow* __restrict__ rows, int* __restrict__ accept) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned qa[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) qa[i] = ((const unsigned*)(q + (size_t)qi * 128))[i];
+  const int k = nn < nt ? nn : nt;
+  float dk[MB2_NN_MAXK]; int ik[MB2_NN_MAXK];
+  int cnt = 0;
+  const float qq = qn[qi];
+  for (int j = 0; j < nt; j++) {
+    const unsigned* tp = (const unsigned*)(t + (size_t)j * 128);
+    unsigned dot = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) dot = __dp4a(qa[i], tp[i], dot);
+    const float v = __fadd_rn(qq, __fmaf_rn(-2.f, (float)dot, tn[j]));   // |q|^2 + |t|^2 - 2 q.t: integers below 2^24, exact
+    if (cnt < k || v < dk[cnt - 1]) {      // trains come in index order: an equal distance stays behind the earlier one
+      int p = cnt < k ? cnt : k - 1;
+      while (p > 0 && dk[p - 1] > v) { dk[p] = dk[p - 1]; ik[p] = ik[p - 1]; p--; }
+      dk[p] = v; ik[p] = j;
+      if (cnt < k) cnt++;
+    }
+  }
+  MatchRow r; r.q = qi; r.idx0 = ik[0]; r.d0 = dk[0]; r.idxJ = -1; r.dJ = 0; r.idx1 = k > 1 ? ik[1] : -1; r.d1 = k > 1 ? dk[1] : 0; r.pad = 0;
+  int ok = 0;
+  for (int j = 1; j < k; j++) {
+    const double dx = txy[2 * ik[0]] - txy[2 * ik[j]], dy = txy[2 * ik[0] + 1] - txy[2 * ik[j] + 1];
+    if (j == nn - 1 || dx * dx + dy * dy > contr2) { r.idxJ = ik[j]; r.dJ = dk[j]; ok = 1; break; }
+  }
+  rows[qi] = r; accept[qi] = ok;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -464,6 +506,10 @@ void mb2_nn_init_state(mb2_ctx* ctx, const NNState& st, int nq) {
 }
 void mb2_nn_threshold(mb2_ctx* ctx, const NNState& st, int nq, const float* qn, double sqminratio) {
   MB2_LAUNCH(ctx, k_threshold, (nq + 255) / 256, 256, 0, st, nq, qn, sqminratio);
+}
+void mb2_nn_topk(mb2_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, const float* qn, const float* tn, const double* txy, double contr2,
+                 int nn, MatchRow* rows, int* accept) {
+  MB2_LAUNCH(ctx, k_nn_topk, (nq + 127) / 128, 128, 0, q, nq, t, nt, qn, tn, txy, contr2, nn, rows, accept);
 }
 void mb2_nn_finalize(mb2_ctx* ctx, const NNState& st, int nq, int nt, int nn, MatchRow* rows, int* accept) {
   MB2_LAUNCH(ctx, k_finalize, (nq + 255) / 256, 256, 0, st, nq, nt, nn, rows, accept);

@@ -17,6 +17,8 @@ void mb2_nn_prepare(mb2_ctx* ctx, const uint8_t* d_desc, int n, int n_pad, void*
 void mb2_nn_init_state(mb2_ctx* ctx, const NNState& st, int nq);
 void mb2_nn_threshold(mb2_ctx* ctx, const NNState& st, int nq, const float* qn, double sqminratio);
 void mb2_nn_finalize(mb2_ctx* ctx, const NNState& st, int nq, int nt, int nn, MatchRow* rows, int* accept);
+void mb2_nn_topk(mb2_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, const float* qn, const float* tn, const double* txy, double contr2,
+                 int nn, MatchRow* rows, int* accept);   // matchRatio >= 1 (matching.cpp:397-428): exact sorted k-NN table per query, nn <= 64
 void mb2_nn_pass_simt(mb2_ctx* ctx, int pass, const uint8_t* q, int nq, const uint8_t* t, int nt, const float* qn, const float* tn,
                       const NNState& st, const double* txy, double contr2);
 int mb2_nn_pass_tc(mb2_ctx* ctx, int pass, const void* q_bf16, int nq, int nq_pad, const void* t_bf16, int nt_pad, const float* qn,

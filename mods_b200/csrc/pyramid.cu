@@ -541,6 +541,7 @@ __global__ void k_emit_keypoints(OctaveLevels oct, const Localized* __restrict__
   // evaluates it -- see detect_core; here we only carry b2.
   int type;
   if (lp.detectorType == 1) type = L.val < 0 ? 11 : 10;   // DOG_BRIGHT : DOG_DARK
+  else if (lp.detectorType == 2) type = L.val < 0 ? 31 : 30;   // HARRIS_BRIGHT : HARRIS_DARK (pyramid.h:38-39)
   else if (L.val < 0) type = 2;
   else {
     const ImgView blur = oct.blur[L.level];
@@ -657,8 +658,49 @@ __global__ void k_dog_cols(ImgView level, const float* __restrict__ tmp, const f
   resp[(size_t)y * resp_pitch + x] = fsub(level.p[(size_t)y * level.pitch + x], d);
 }
 
+// DET_HARRIS response (pyramid.cpp:283-305): products of the level's gradient (computeGradient, helpers.cpp:779-797: central differences,
+// one-sided on the image frame), each blurred with sigma = sqrt(0.6 norm) by the separable blur above, then the Harris measure -- every
+// cv::Mat operation of the reference rounded to float on its own (scalar * Mat with the scalar widened to double).
+__global__ void k_harris_products(ImgView im, float* __restrict__ xx, float* __restrict__ yy, float* __restrict__ xy) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= im.cols || r >= im.rows) return;
+  float gx, gy;
+  if (c == 0) gx = fsub(im.at(r, c + 1), im.at(r, c));
+  else if (c == im.cols - 1) gx = fsub(im.at(r, c), im.at(r, c - 1));
+  else gx = fsub(im.at(r, c + 1), im.at(r, c - 1));
+  if (r == 0) gy = fsub(im.at(r + 1, c), im.at(r, c));
+  else if (r == im.rows - 1) gy = fsub(im.at(r, c), im.at(r - 1, c));
+  else gy = fsub(im.at(r + 1, c), im.at(r - 1, c));
+  const size_t o = (size_t)r * im.pitch + c;
+  xx[o] = fmul(gx, gx); yy[o] = fmul(gy, gy); xy[o] = fmul(gx, gy);
+}
+__global__ void k_harris_combine(int rows, int cols, int pitch, const float* __restrict__ bxx, const float* __restrict__ byy, const float* __restrict__ bxy,
+                                 float sigmasq, float* __restrict__ resp, int resp_pitch) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= cols || r >= rows) return;
+  const size_t o = (size_t)r * pitch + c;
+  const double s = (double)sigmasq;
+  const float dx2 = (float)d_mul((double)bxx[o], s), dy2 = (float)d_mul((double)byy[o], s), dxdy = (float)d_mul((double)bxy[o], s);
+  const float sum = fadd(dx2, dy2);
+  const float ab = fsub(fmul(dx2, dy2), fmul(dxdy, dxdy));
+  resp[(size_t)r * resp_pitch + c] = fsub(ab, (float)d_mul((double)fmul(sum, sum), 0.04));
+}
+
 // host launchers
 // ---------------------------------------------------------------------------------------------
+int mb2_launch_harris(mb2_ctx* ctx, const ImgView& level, float* resp, int resp_pitch, const BlurTaps& taps, float sigmasq, float* d_tmp6) {
+  const size_t plane = (size_t)level.pitch * level.rows;
+  float *xx = d_tmp6, *yy = d_tmp6 + plane, *xy = d_tmp6 + 2 * plane, *bxx = d_tmp6 + 3 * plane, *byy = d_tmp6 + 4 * plane, *bxy = d_tmp6 + 5 * plane;
+  dim3 block(32, 8), grid((level.cols + 31) / 32, (level.rows + 7) / 8);
+  MB2_LAUNCH(ctx, k_harris_products, grid, block, 0, level, xx, yy, xy);
+  int rc;
+  const float* src[3] = {xx, yy, xy}; float* dst[3] = {bxx, byy, bxy};
+  for (int i = 0; i < 3; i++)
+    if ((rc = mb2_launch_blur(ctx, ImgView{src[i], level.rows, level.cols, level.pitch}, dst[i], nullptr, level.pitch, taps, 0.f, 0))) return rc;
+  MB2_LAUNCH(ctx, k_harris_combine, grid, block, 0, level.rows, level.cols, level.pitch, (const float*)bxx, (const float*)byy, (const float*)bxy, sigmasq, resp,
+             resp_pitch);
+  return MB2_OK;
+}
 void mb2_launch_dog(mb2_ctx* ctx, const ImgView& level, float* resp, int resp_pitch, const float* d_taps, int n, float* d_tmp) {
   dim3 block(32, 8), grid((level.cols + 31) / 32, (level.rows + 7) / 8);
   MB2_LAUNCH(ctx, k_wide_rows, grid, block, 0, level, d_taps, n, d_tmp);

@@ -34,12 +34,14 @@ struct LocalizeParams {
   float pixelDistance;
   int numberOfScales;
   float levelSigma[MB2_MAX_LEVELS];
-  int detectorType;   // 0 DET_HESSIAN, 1 DET_DOG (getPointType, pyramid.cpp:66-130)
+  int detectorType;   // 0 DET_HESSIAN, 1 DET_DOG, 2 DET_HARRIS (getPointType, pyramid.cpp:66-130)
 };
 
 // DET_DOG response (pyramid.cpp:176-181): resp = level - GaussianBlur(level, ksize(sigma), sigma, BORDER_REPLICATE); d_taps: n taps on
 // the device, d_tmp: one plane of the level's size (row pass)
 void mb2_launch_dog(mb2_ctx* ctx, const ImgView& level, float* resp, int resp_pitch, const float* d_taps, int n, float* d_tmp);
+// DET_HARRIS response (pyramid.cpp:283-305); taps: Gaussian of sigma = sqrt(0.6 norm), sigmasq = (float)(0.6 norm); d_tmp6: six planes of the level's size
+int mb2_launch_harris(mb2_ctx* ctx, const ImgView& level, float* resp, int resp_pitch, const BlurTaps& taps, float sigmasq, float* d_tmp6);
 int mb2_launch_blur(mb2_ctx* ctx, const ImgView& src, float* dst_blur, float* dst_resp, int dst_pitch, const BlurTaps& taps,
                     float norm2, int want_resp);
 // in-level part of the 3x3x3 extremum test, run by the kernel that produces a detection level (k_blur_hess_tma)

@@ -792,12 +792,13 @@ struct PairSetup {  // what getCLIparam would read from config_iter_mods_cviu.in
 
 // Everything the verification stage needs from the detection / matching stage, on the host.
 struct PairFront {
-  std::unique_ptr<ImageRepresentation> rep1, rep2;
+  std::shared_ptr<ImageRepresentation> rep1, rep2;   // shared: the 1-to-N caller (mb2_mods_multi) keeps one query image for all pairs
   // tentatives per (descriptor, detector), in the order GetCorresponcesVector("All", "All") concatenates them
   // (CorrespondencesMapMap[desc][det], std::map order: "HalfRootSIFT" < "RootSIFT", "HessianAffine" < "MSER")
   struct Group { const char* det; std::string desc; std::vector<double> rows; int nt = 0; };
   Group groups[4];
   int n_groups = 0, nt = 0, rc = MB2_OK;
+  int slot1 = 0, slot2 = 1;   // device slots of the HessianAffine sets of the two images (MSER: + 2)
   double t_start = 0;
 };
 
@@ -809,6 +810,48 @@ struct MserAhead {
   mb2_ctx* c = nullptr; std::thread th; int rc = MB2_OK, n1 = 0, n2 = 0; double ms = 0;
   ~MserAhead() { if (th.joinable()) th.join(); }
 };
+
+// MatchImgReps of the pair (correspondencebank.cpp:237-351): every (descriptor, detector) group separately; fills out.groups / res.
+void match_reps(mb2_ctx* ctx, const mb2_pair_config* cfg, PairSetup& ps, mb2_pair_result* res, PairFront& out) {
+  double t0;
+  // a view call that failed (CUDA error, capacity, tap-table overflow) fails the pair: no success with partial regions
+  if (out.rep1->LastError() < 0) { out.rc = out.rep1->LastError(); return; }
+  if (out.rep2->LastError() < 0) { out.rc = out.rep2->LastError(); return; }
+  res->regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name); res->regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name);
+  res->mser_regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name, "MSER"); res->mser_regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name, "MSER");
+  t0 = now_ms();
+  const char* dets[2] = {"HessianAffine", "MSER"};
+  std::vector<std::string> desc_order = ps.descs;
+  std::sort(desc_order.begin(), desc_order.end());
+  for (const std::string& desc : desc_order)
+    for (int g = 0; g < (cfg->use_mser ? 2 : 1); g++) {   // MatchImgReps, separate detectors x separate descriptors (correspondencebank.cpp:291-347)
+      PairFront::Group& G = out.groups[out.n_groups];
+      G.det = dets[g]; G.desc = desc;
+      const ImageRepresentation::RegionBlock* Q = out.rep1->block(dets[g], desc);
+      const ImageRepresentation::RegionBlock* T = out.rep2->block(dets[g], desc);
+      out.n_groups++;
+      if (!(Q && T && Q->n > 0 && T->n > 0)) continue;
+      G.rows.resize((size_t)Q->n * 7);
+      const double ratio = g == 0 ? cfg->matchRatio : cfg->mserMatchRatio;
+      // the first descriptor of the tier is the one left resident on the device; the slots must then hold exactly the host blocks'
+      // regions (the same check MatchImgReps makes: count == Q.n).  Regions read from a feature cache live on the host only.
+      const int sq = out.rep1->SlotCount(dets[g]), st = out.rep2->SlotCount(dets[g]);
+      if (desc == ps.desc_name && (sq < 0 || st < 0 || (sq > 0 && sq != Q->n) || (st > 0 && st != T->n))) { out.rc = MB2_ERR_CUDA; return; }
+      if (desc == ps.desc_name && sq == Q->n && st == T->n)
+        G.nt = mb2_match_slots(ctx, g == 0 ? out.slot1 : out.slot1 + 2, g == 0 ? out.slot2 : out.slot2 + 2, ratio, cfg->contradDist, 50, G.rows.data(), Q->n);
+      else {
+        std::vector<double> txy((size_t)T->n * 2);
+        for (int i = 0; i < T->n; i++) { txy[2 * i] = T->reproj_kp[(size_t)i * MB2_KP]; txy[2 * i + 1] = T->reproj_kp[(size_t)i * MB2_KP + 1]; }
+        G.nt = mb2_match_fginn(ctx, Q->desc_u8.data(), Q->n, T->desc_u8.data(), T->n, txy.data(), ratio, cfg->contradDist, 50, G.rows.data(), Q->n);
+      }
+      if (G.nt < 0) { out.rc = G.nt; G.nt = 0; return; }
+      out.nt += G.nt;
+      if (g == 1) res->mser_tentatives += G.nt;
+    }
+  res->ms_match = now_ms() - t0;
+  res->tentatives = out.nt;
+}
+
 
 void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* img2, int w2, int h2, const mb2_pair_config* cfg,
                 PairSetup& ps, mb2_pair_result* res, PairFront& out, MserAhead* pre = nullptr) {
@@ -889,42 +932,7 @@ void pair_front(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* im
     out.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
   }
   res->ms_detect_describe = now_ms() - t0;
-  // a view call that failed (CUDA error, capacity, tap-table overflow) fails the pair: no success with partial regions
-  if (out.rep1->LastError() < 0) { out.rc = out.rep1->LastError(); return; }
-  if (out.rep2->LastError() < 0) { out.rc = out.rep2->LastError(); return; }
-  res->regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name); res->regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name);
-  res->mser_regions1 = out.rep1->GetDescriptorsNumber(ps.desc_name, "MSER"); res->mser_regions2 = out.rep2->GetDescriptorsNumber(ps.desc_name, "MSER");
-  t0 = now_ms();
-  const char* dets[2] = {"HessianAffine", "MSER"};
-  std::vector<std::string> desc_order = ps.descs;
-  std::sort(desc_order.begin(), desc_order.end());
-  for (const std::string& desc : desc_order)
-    for (int g = 0; g < (cfg->use_mser ? 2 : 1); g++) {   // MatchImgReps, separate detectors x separate descriptors (correspondencebank.cpp:291-347)
-      PairFront::Group& G = out.groups[out.n_groups];
-      G.det = dets[g]; G.desc = desc;
-      const ImageRepresentation::RegionBlock* Q = out.rep1->block(dets[g], desc);
-      const ImageRepresentation::RegionBlock* T = out.rep2->block(dets[g], desc);
-      out.n_groups++;
-      if (!(Q && T && Q->n > 0 && T->n > 0)) continue;
-      G.rows.resize((size_t)Q->n * 7);
-      const double ratio = g == 0 ? cfg->matchRatio : cfg->mserMatchRatio;
-      if (desc == ps.desc_name) {  // the first descriptor of the tier is the one left resident on the device
-        // the device slots must hold exactly the host blocks' regions (the same check MatchImgReps makes: count == Q.n)
-        const int sq = out.rep1->SlotCount(dets[g]), st = out.rep2->SlotCount(dets[g]);
-        if ((sq > 0 && sq != Q->n) || (st > 0 && st != T->n) || sq < 0 || st < 0) { out.rc = MB2_ERR_CUDA; return; }
-        G.nt = mb2_match_slots(ctx, g == 0 ? 0 : 2, g == 0 ? 1 : 3, ratio, cfg->contradDist, 50, G.rows.data(), Q->n);
-      }
-      else {
-        std::vector<double> txy((size_t)T->n * 2);
-        for (int i = 0; i < T->n; i++) { txy[2 * i] = T->reproj_kp[(size_t)i * MB2_KP]; txy[2 * i + 1] = T->reproj_kp[(size_t)i * MB2_KP + 1]; }
-        G.nt = mb2_match_fginn(ctx, Q->desc_u8.data(), Q->n, T->desc_u8.data(), T->n, txy.data(), ratio, cfg->contradDist, 50, G.rows.data(), Q->n);
-      }
-      if (G.nt < 0) { out.rc = G.nt; G.nt = 0; return; }
-      out.nt += G.nt;
-      if (g == 1) res->mser_tentatives += G.nt;
-    }
-  res->ms_match = now_ms() - t0;
-  res->tentatives = out.nt;
+  match_reps(ctx, cfg, ps, res, out);
 }
 
 // mods.cpp:330-415: DuplicateFiltering(MODE_FGINN) + LORANSACFiltering on the region blocks and index lists
@@ -1008,6 +1016,65 @@ extern "C" int mb2_host_verify(mb2_ctx* ctx, const double* frames14, const doubl
       const double* f = &frames[(size_t)verified[i] * 14];
       verified_out[4 * i] = f[0]; verified_out[4 * i + 1] = f[1]; verified_out[4 * i + 2] = f[7]; verified_out[4 * i + 3] = f[8];
     }
+  return k;
+}
+
+// ---- other callers of the same path: 1-to-N matching and the feature cache ---------------------------------------
+// mods_multi.cpp:232-330: the query image is detected / described ONCE, then every other image is detected, matched against it,
+// duplicate-filtered and verified.  res[i] / verified_out[i] as mb2_mods_pair returns them for the pair (img1, imgs2[i]).
+extern "C" int mb2_mods_multi(mb2_ctx* ctx, const float* img1, int w1, int h1, int n, const float* const* imgs2, const int* w2, const int* h2,
+                              const mb2_pair_config* cfg, mb2_pair_result* res, double* const* verified_out, const int* capacity) {
+  if (!ctx || !img1 || !cfg || !res || n < 0 || (n > 0 && (!imgs2 || !w2 || !h2))) return MB2_ERR_ARG;
+  PairSetup ps(cfg);
+  std::shared_ptr<ImageRepresentation> rep1(new ImageRepresentation(ctx, GrayImage{img1, h1, w1}, "img1", 0));
+  const double t0 = now_ms();
+  rep1->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);   // mods_multi.cpp:244-247
+  const double t_img1 = now_ms() - t0;
+  for (int i = 0; i < n; i++) {
+    std::memset(&res[i], 0, sizeof res[i]);
+    PairFront f;
+    f.t_start = now_ms();
+    f.rep1 = rep1;
+    f.rep2.reset(new ImageRepresentation(ctx, GrayImage{imgs2[i], h2[i], w2[i]}, "img2", 1));
+    f.rep2->SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);   // :252-256
+    res[i].ms_detect_describe = now_ms() - f.t_start + (i == 0 ? t_img1 : 0.0);
+    match_reps(ctx, cfg, ps, &res[i], f);                                              // :275-277
+    if (f.rc < 0) return f.rc;
+    const int k = pair_back(ctx, cfg, ps, f, &res[i], verified_out ? verified_out[i] : nullptr, capacity ? capacity[i] : 0);   // :291-330
+    if (k < 0) return k;
+    res[i].ms_total = now_ms() - f.t_start;
+  }
+  return n;
+}
+
+// extract_features.cpp: SynthDetectDescribeKeypoints + SaveRegions -- the feature cache the reference's `read_pre_extracted` flow
+// (mods.cpp:224-240) and build/read_features.m read.  Returns the number of described regions written.
+extern "C" int mb2_extract_features(mb2_ctx* ctx, const float* img, int w, int h, const mb2_pair_config* cfg, const char* fname) {
+  if (!ctx || !img || !cfg || !fname) return MB2_ERR_ARG;
+  PairSetup ps(cfg);
+  ImageRepresentation rep(ctx, GrayImage{img, h, w}, "img", -1);
+  rep.SynthDetectDescribeKeypoints(ps.iters, ps.det_par, ps.desc_par, ps.dom);
+  if (rep.LastError() < 0) return rep.LastError();
+  rep.SaveRegions(fname, 0);
+  return rep.GetDescriptorsNumber();
+}
+
+// mods.cpp:224-240 + 290-415 on two feature caches: LoadRegions for both images, then MatchImgReps -> DuplicateFiltering ->
+// LORANSACFiltering.  The descriptors are uploaded for the matching (loaded regions are not resident on the device).
+extern "C" int mb2_mods_pair_cached(mb2_ctx* ctx, const char* cache1, const char* cache2, const mb2_pair_config* cfg, mb2_pair_result* res,
+                                    double* verified_out, int capacity) {
+  if (!ctx || !cache1 || !cache2 || !cfg || !res) return MB2_ERR_ARG;
+  std::memset(res, 0, sizeof *res);
+  PairSetup ps(cfg);
+  PairFront f;
+  f.t_start = now_ms();
+  f.rep1.reset(new ImageRepresentation(ctx, GrayImage{nullptr, 0, 0}, "img1", -1));
+  f.rep2.reset(new ImageRepresentation(ctx, GrayImage{nullptr, 0, 0}, "img2", -1));
+  f.rep1->LoadRegions(cache1); f.rep2->LoadRegions(cache2);
+  match_reps(ctx, cfg, ps, res, f);
+  if (f.rc < 0) return f.rc;
+  const int k = pair_back(ctx, cfg, ps, f, res, verified_out, capacity);
+  res->ms_total = now_ms() - f.t_start;
   return k;
 }
 

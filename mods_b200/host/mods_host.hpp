@@ -244,6 +244,14 @@ int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, const float* 
 int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img1, const int* w1, const int* h1, const float* const* img2,
                    const int* w2, const int* h2, const mb2_pair_config* cfg, mb2_pair_result* res, double* const* verified_out,
                    const int* capacity);
+/* Other callers of the same path.  mb2_mods_multi = mods_multi.cpp:232-330 (1-to-N: the query image is described once);
+ * mb2_extract_features = extract_features.cpp (describe + SaveRegions in the reference's text format); mb2_mods_pair_cached = the
+ * read_pre_extracted flow of mods.cpp:224-240 (LoadRegions for both images, then match + verify). */
+int mb2_mods_multi(mb2_ctx* ctx, const float* img1, int w1, int h1, int n, const float* const* imgs2, const int* w2, const int* h2,
+                   const mb2_pair_config* cfg, mb2_pair_result* res, double* const* verified_out, const int* capacity);
+int mb2_extract_features(mb2_ctx* ctx, const float* img, int w, int h, const mb2_pair_config* cfg, const char* fname);
+int mb2_mods_pair_cached(mb2_ctx* ctx, const char* cache1, const char* cache2, const mb2_pair_config* cfg, mb2_pair_result* res,
+                         double* verified_out, int capacity);
 /* mods.cpp:298-415 on plain arrays: DuplicateFiltering(MODE_FGINN) + LORANSACFiltering of n tentatives.  frames: n rows of 14 doubles
  * (reproj_kp x y a11 a12 a21 a22 s of the first region, then of the second), key[n] = sqrt(d1/d2) ratios.  Used by the view-sharded
  * driver (mods_b200/sharding.py), where rank 0 verifies the tentatives gathered from all ranks.  Returns the verified count. */

@@ -51,7 +51,7 @@ struct HessParams {  // [HessianAffine] of config_iter_mods_cviu.ini; structures
   int smmWindowSize = 19;
   int doBaumberg = 1;
   int mode = 0;  // FIXED_TH
-  int detectorType = 0;  // detector_type (structures.hpp): 0 DET_HESSIAN, 1 DET_DOG
+  int detectorType = 0;  // detector_type (structures.hpp): 0 DET_HESSIAN, 1 DET_DOG, 2 DET_HARRIS
   int reg_number = -1;
   float rel_threshold = -1;
   float rel_reg_number = -1;
@@ -310,6 +310,26 @@ inline Image dogResponse(const Image& in, float norm) {  // pyramid.cpp:176-181:
   return out;
 }
 
+// pyramid.cpp:283-305: Harris measure of the level's gradient, every Mat operation rounded to float on its own as cv::Mat arithmetic does
+// (Lx.mul(Lx), the three blurs with sigma = sqrt(0.6 norm), scalar * Mat with the scalar widened to double, +, -)
+inline Image harrisResponse(const Image& in, float norm) {
+  const int rows = in.rows, cols = in.cols;
+  const float sigmasq = 0.6 * norm;
+  const float sigma = std::sqrt(sigmasq);
+  Image Lx(rows, cols), Ly(rows, cols), xx(rows, cols), yy(rows, cols), xy(rows, cols), out(rows, cols);
+  computeGradient(in.px.data(), cols, rows, Lx.px.data(), Ly.px.data());
+  for (size_t i = 0; i < out.px.size(); i++) { xx.px[i] = Lx.px[i] * Lx.px[i]; yy.px[i] = Ly.px[i] * Ly.px[i]; xy.px[i] = Lx.px[i] * Ly.px[i]; }
+  Image bxx = gaussianBlur(xx, sigma), byy = gaussianBlur(yy, sigma), bxy = gaussianBlur(xy, sigma);
+  for (size_t i = 0; i < out.px.size(); i++) {
+    const float dx2 = (float)(bxx.px[i] * (double)sigmasq), dy2 = (float)(byy.px[i] * (double)sigmasq), dxdy = (float)(bxy.px[i] * (double)sigmasq);
+    const float sum = dx2 + dy2;
+    const float a = dx2 * dy2, b = dxdy * dxdy, c = sum * sum;
+    const float ab = a - b;
+    out.px[i] = ab - (float)(c * 0.04);
+  }
+  return out;
+}
+
 struct Candidate { int r, c; };  // 3x3x3 extremum before localisation
 
 struct HessianAffineDetector {
@@ -430,6 +450,7 @@ struct HessianAffineDetector {
     float scale = curScale * std::pow(2.0f, b[2] / par.numberOfScales);
     int type;  // getPointType, pyramid.cpp:66-130
     if (par.detectorType == 1) type = val < 0 ? 11 : 10;   // DOG_BRIGHT : DOG_DARK (pyramid.h:36-37)
+    else if (par.detectorType == 2) type = val < 0 ? 31 : 30;   // HARRIS_BRIGHT : HARRIS_DARK (pyramid.h:38-39)
     else if (val < 0) type = 2;
     else {
       const float* p = blur.row(r) + c;
@@ -458,7 +479,8 @@ struct HessianAffineDetector {
     float curSigma = par.initialSigma;
     int numLevels = 1;
     Image blur = firstLevel, prevBlur, low, cur, high;
-    auto response = [&](const Image& im, float norm) { return par.detectorType == 1 ? dogResponse(im, norm) : hessianResponse(im, norm); };   // pyramid.cpp:132-175
+    auto response = [&](const Image& im, float norm) {   // pyramid.cpp:132-175
+      return par.detectorType == 1 ? dogResponse(im, norm) : par.detectorType == 2 ? harrisResponse(im, norm) : hessianResponse(im, norm); };
     cur = response(blur, curSigma * curSigma);
     if (keep_levels) { dump_blur.push_back(blur); dump_resp.push_back(cur); dump_info.push_back({octave, 0, blur.rows, blur.cols, pixelDistance, curSigma}); }
     for (int i = 1; i < par.numberOfScales + 2; i++) {

@@ -27,6 +27,11 @@ class HessParams(C.Structure):
         return HessParams(5.3333, 3, 1.6, 10.0, 5, 16, 0.05, 19, 1, 0, 2000, -1.0, -1.0, 41, 3.0 * 3.0 ** 0.5, 0)
 
     @staticmethod
+    def harris():
+        """[HarrisAffine] of config_iter_mods_cviu.ini:28-44 (mode FixedTh, threshold 15, Baumberg with convergence threshold 0.1)."""
+        return HessParams(15.0, 3, 1.6, 10.0, 5, 16, 0.1, 19, 1, 0, 1000, 0.1, 0.5, 41, 3.0 * 3.0 ** 0.5, 2)
+
+    @staticmethod
     def dog():
         """[DoG] of config_iter_mods_cviu_wxbs.ini:45-59 with mode FixedTh: threshold 8, no Baumberg iteration."""
         return HessParams(8.0, 3, 1.6, 10.0, 5, 16, 0.05, 19, 0, 0, 3000, 0.01, 0.5, 41, 3.0 * 3.0 ** 0.5, 1)

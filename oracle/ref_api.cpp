@@ -63,7 +63,7 @@ struct HessParamsC {       // mirrors the [HessianAffine] section of config_iter
   float threshold; int numberOfScales; float initialSigma; float edgeEigenValueRatio; int border;
   int maxIterations; float convergenceThreshold; int smmWindowSize; int doBaumberg;
   int mode; int reg_number; float rel_threshold; float rel_reg_number; int patchSize; float mrSize;
-  int detectorType;   // 0 DET_HESSIAN, 1 DET_DOG
+  int detectorType;   // 0 DET_HESSIAN, 1 DET_DOG, 2 DET_HARRIS
 };
 
 ScaleSpaceDetectorParams to_ref(const HessParamsC& p) {
@@ -77,7 +77,7 @@ ScaleSpaceDetectorParams to_ref(const HessParamsC& p) {
   sp.PyramidPars.reg_number = p.reg_number;
   sp.PyramidPars.rel_threshold = p.rel_threshold;
   sp.PyramidPars.rel_reg_number = p.rel_reg_number;
-  sp.PyramidPars.DetectorType = p.detectorType == 1 ? DET_DOG : DET_HESSIAN;
+  sp.PyramidPars.DetectorType = p.detectorType == 1 ? DET_DOG : p.detectorType == 2 ? DET_HARRIS : DET_HESSIAN;
   sp.AffineShapePars.maxIterations = p.maxIterations;
   sp.AffineShapePars.convergenceThreshold = p.convergenceThreshold;
   sp.AffineShapePars.smmWindowSize = p.smmWindowSize;

@@ -187,8 +187,15 @@ def test_fginn_empty_and_unsupported(ctx):
     q, t, txy = _match_case(10, 20, 1)
     assert len(ctx.match_fginn(q[:0], t, txy)) == 0
     assert len(ctx.match_fginn(q, t[:0], txy[:0])) == 0
-    with pytest.raises(mb.Mb2Error):
-        ctx.match_fginn(q, t, txy, ratio=1.0)
+
+
+@pytest.mark.parametrize("ratio,cd,shape", [(1.0, 30.0, (700, 900, 21)), (1.2, 10.0, (300, 55, 22)), (1.0, 1e9, (200, 400, 23)), (1.0, 30.0, (50, 30, 24))])
+def test_fginn_all_points_branch(ctx, oracle, ratio, cd, shape):
+    """matchRatio >= 1 (matching.cpp:397-428): NN + first geometrically inconsistent neighbour, or neighbour nn - 1; fewer trains than nn."""
+    q, t, txy = _match_case(*shape)
+    g = ctx.match_fginn(q, t, txy, ratio=ratio, contradDist=cd)
+    o = oracle.match_fginn(q.astype(np.float32), t.astype(np.float32), txy, ratio=ratio, contradDist=cd)
+    assert np.array_equal(g, o) and (len(o) > 0 or shape[1] < 50)
 
 
 def test_fginn_full_size_properties(ctx):
@@ -306,6 +313,29 @@ def test_dog_detector_vs_oracle_and_golden(ctx, oracle, mode, regs):
         g, o = ctx.detect_describe_view(im, det=gp), oracle.view_pipeline(im, hp=hp)
         assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2].astype(np.float32), o[2])
         # pyramid levels: the response plane is the level minus its wide blur, bit for bit
+        p = oracle.pyramid(im, hp)
+        ctx.hessaff_detect(im, gp)
+        for lv in p["levels"][:7]:
+            assert np.array_equal(ctx.pyramid_level(lv["octave"], lv["level"], want_resp=True)[0], lv["resp"])
+
+
+# ---- Harris flavour of the scale-space detector ---------------------------------------------------------
+@pytest.mark.parametrize("mode,regs", [(0, 1000), (4, 200), (2, 150)])
+def test_harris_detector_vs_oracle_and_golden(ctx, oracle, mode, regs):
+    """mb2_hessaff_params.detectorType = 2 (DET_HARRIS, pyramid.cpp:283-305): gradient products, three blurs, Harris measure; un-squared
+    threshold, sign point types 30 / 31; keys bit-exact against the oracle (== compiled reference) and the reference's golden vectors."""
+    from oracle.pyoracle import HessParams
+    im = synth.blob_image(480, 360, seed=34)
+    hp = HessParams.harris(); hp.mode = mode; hp.reg_number = regs
+    gp = mb.HessaffParams.harris(); gp.mode = mode; gp.reg_number = regs
+    a = ctx.hessaff_detect(im, gp, as_regions=False)
+    assert len(a) > 100 and np.array_equal(a, oracle.hessaff_detect(im, hp, raw=True)) and set(a[:, 8].astype(int)) <= {30, 31}
+    if mode == 0:
+        GD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "harris_vectors.npz"))
+        img = GD["image"].astype(np.float32)
+        assert np.array_equal(ctx.hessaff_detect(img, mb.HessaffParams.harris(), as_regions=False), GD["raw_fixed_th"])
+        v = ctx.detect_describe_view(img, det=mb.HessaffParams.harris())
+        assert np.array_equal(v[0], GD["view_det"]) and np.array_equal(v[2], GD["view_desc"])
         p = oracle.pyramid(im, hp)
         ctx.hessaff_detect(im, gp)
         for lv in p["levels"][:7]:

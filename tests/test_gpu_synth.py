@@ -98,3 +98,24 @@ def test_views_sharded_driver_equals_pair_driver(ctx):
     assert np.array_equal(v1, v2) and np.array_equal(np.array(r1.H), np.array(r2.H))
     r3, v3, dig3, _ = ctx.views_sharded_pair(A, B, cfg, capacity=1 << 15)
     assert dig == dig3 and st["units"] == 12
+
+
+def test_mods_multi_and_feature_cache_callers(ctx, tmp_path):
+    """mods_multi.cpp (1-to-N, query described once) == mb2_mods_pair per pair; extract_features + the read_pre_extracted flow: the same
+    tentatives from the cache files (descriptors are integers; positions carry the 6 significant digits of the reference's text format)."""
+    import mods_b200 as mb
+    from synth import blob_image, warp_image, gt_homography
+    A = blob_image(512, 384, seed=61, n_blobs=500)
+    Bs = [warp_image(A, gt_homography(512, 384), seed=62 + k) for k in range(2)]
+    cfg = mb.PairConfig.default(); cfg.use_mser = 1; cfg.seed = 3
+    multi, vers = ctx.mods_multi(A, Bs, cfg, capacity=1 << 14)
+    f = lambda r: (r.regions1, r.regions2, r.mser_regions1, r.mser_regions2, r.tentatives, r.unique_tentatives, r.ransac_inliers, r.verified)
+    for k, B in enumerate(Bs):
+        r, v = ctx.mods_pair(A, B, cfg, capacity=1 << 14)
+        assert f(r) == f(multi[k]) and r.verified > 100 and np.array_equal(v, vers[k])
+    c1, c2 = tmp_path / "a.txt", tmp_path / "b.txt"
+    n1 = ctx.extract_features(A, c1, cfg); n2 = ctx.extract_features(Bs[0], c2, cfg)
+    assert (n1, n2) == (multi[0].regions1, multi[0].regions2)
+    rc, vc = ctx.mods_pair_cached(c1, c2, cfg, capacity=1 << 14)
+    assert (rc.regions1, rc.regions2, rc.tentatives) == (multi[0].regions1, multi[0].regions2, multi[0].tentatives)
+    assert abs(rc.verified - multi[0].verified) <= 0.03 * multi[0].verified

@@ -92,3 +92,16 @@ def test_dog_detector_matches_reference(oracle):
     assert np.array_equal(oracle.hessaff_detect(im, hp, raw=True), GD["raw_not_less_80"])
     v = oracle.view_pipeline(im, hp=HessParams.dog())
     assert np.array_equal(v[0], GD["view_det"]) and np.array_equal(v[2].astype(np.uint8), GD["view_desc"])
+
+
+def test_harris_detector_matches_reference(oracle):
+    """DET_HARRIS flavour of the scale-space detector (pyramid.cpp:283-305): tests/golden/make_golden_harris.py."""
+    from oracle.pyoracle import HessParams
+    GD = np.load(os.path.join(os.path.dirname(__file__), "golden", "harris_vectors.npz"))
+    im = GD["image"].astype(np.float32)
+    hp = HessParams.harris()
+    assert np.array_equal(oracle.hessaff_detect(im, hp, raw=True), GD["raw_fixed_th"]) and len(GD["raw_fixed_th"]) > 50
+    hp.mode = 4; hp.reg_number = 80
+    assert np.array_equal(oracle.hessaff_detect(im, hp, raw=True), GD["raw_not_less_80"])
+    v = oracle.view_pipeline(im, hp=HessParams.harris())
+    assert np.array_equal(v[0], GD["view_det"]) and np.array_equal(v[2].astype(np.uint8), GD["view_desc"])

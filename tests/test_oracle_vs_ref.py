@@ -215,7 +215,7 @@ def test_dog_detector_oracle_vs_reference(oracle, reference, mode, regs):
 
 
 # ---- matching/matching.cpp compiled in place (FLANN answered by the shim's exact linear k-NN) ------------------------------------------
-@pytest.mark.parametrize("ratio,contrad,n,nt", [(0.8, 30.0, 1500, 1500), (0.95, 10.0, 700, 2100), (0.6, 30.0, 900, 60)])
+@pytest.mark.parametrize("ratio,contrad,n,nt", [(0.8, 30.0, 1500, 1500), (0.95, 10.0, 700, 2100), (0.6, 30.0, 900, 60), (1.0, 30.0, 800, 900), (1.3, 1e9, 300, 200)])
 def test_fginn_port_equals_matching_cpp(oracle, reference, ratio, contrad, n, nt):
     """The oracle's FGINN loop == MatchFlannFGINN (matching.cpp:357-461) driven by an exact k-NN table: every tentative row."""
     rng = np.random.default_rng(int(ratio * 100) + n)
@@ -228,3 +228,16 @@ def test_fginn_port_equals_matching_cpp(oracle, reference, ratio, contrad, n, nt
     a = oracle.match_fginn(q, t, xy, ratio=ratio, contradDist=contrad)
     b = reference.match_fginn(q, t, xy, ratio=ratio, contradDist=contrad)
     assert len(a) > 20 and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode,regs", [(0, 1000), (4, 200), (2, 150)])
+def test_harris_detector_oracle_vs_reference(oracle, reference, mode, regs):
+    """DET_HARRIS (HarrisResponse, pyramid.cpp:283-305; point types 30 / 31): oracle == the compiled reference in every DetectorMode."""
+    from oracle.pyoracle import HessParams
+    im = synth.blob_image(320, 240, seed=6)
+    hp = HessParams.harris(); hp.mode = mode; hp.reg_number = regs
+    a, b = oracle.hessaff_detect(im, hp, raw=True), reference.hessaff_detect(im, hp, raw=True)
+    assert len(a) > 50 and np.array_equal(a, b) and set(a[:, 8].astype(int)) <= {30, 31}
+    if mode == 0:
+        va, vb = oracle.view_pipeline(im, hp=hp), reference.view_pipeline(im, hp=hp)
+        assert all(np.array_equal(x, y) for x, y in zip(va, vb))
