@@ -643,6 +643,10 @@ def main():
                          "iters_mods_cviu.ini on ONE 4096x3072 pair, views sharded over the ranks + one NCCL all-gather (strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl != "reference":
+        # torchrun pins OMP_NUM_THREADS to 1; the host legs of the library (duplicate filter, libm legs, LO-RANSAC set-up) use OpenMP:
+        # give every rank its share of the host cores (set before any OpenMP runtime is loaded)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world)))
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif args.workload == "c4":
