@@ -100,7 +100,11 @@ typedef struct {
                     * normalisation on the 64 entries.  Rows of desc_u8 stay 128 wide: entries 0..63 hold the descriptor, 64..127 are 0
                     * (L2 distances between such rows equal the 64-D distances).  doHalfSIFT without rootSIFT is refused: the reference's
                     * SIFTnorm reads 128 entries of the 64-entry vector (siftdesc.cpp:251, 267). */
-  int reserved;
+  int dspScales;   /* 0 = off.  > 0 = DSPSIFT (imagerepresentation.cpp:1547-1598; DomainSizePolingParams, siftdesc.h:19-30: numScales 3,
+                    * startCoef 0.5, endCoef 1.5): the un-normalised plain-SIFT votes described at dspScales + 1 measurement-region sizes
+                    * mrSize * (dspStartCoef + i (dspEndCoef - dspStartCoef) / dspScales), summed in float, then SIFTnorm on the float
+                    * vector.  rootSIFT / doHalfSIFT are ignored (the reference forces plain SIFT here). */
+  double dspStartCoef, dspEndCoef;
 } mb2_sift_params;
 
 /* ---- context --------------------------------------------------------------------------- */
@@ -234,6 +238,8 @@ int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* des
 #define MB2_REGION_RECORD_BYTES 184
 /* device scratch + stream-ordered copies on the context's stream for callers above the C ABI that keep data on the device (the
  * view-sharded driver): kind 0 host->device, 1 device->host, 2 device->device.  mb2_ctx_sync() waits for them. */
+/* measured FP64 FMA throughput of the device (TFLOP/s, a DFMA micro-kernel): the denominator of the scorer's roofline in bench.py */
+int mb2_debug_fp64_peak(mb2_ctx* ctx, double* tflops);
 int mb2_ctx_make_current(mb2_ctx* ctx);   /* cudaSetDevice(device of ctx) on the calling thread */
 void* mb2_dev_alloc(mb2_ctx* ctx, size_t bytes);
 void mb2_dev_free(mb2_ctx* ctx, void* p);

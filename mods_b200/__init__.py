@@ -19,7 +19,7 @@ EXPORTS = [
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
     "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_ransac_f", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
     "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair", "mb2_synth_view", "mb2_detect_describe_synth_view", "mb2_ctx_tree_epoch", "mb2_ctx_wait_tree", "mb2_ctx_create_prio",
-    "mb2_view_pack", "mb2_slot_from_records", "mb2_match_slots_range", "mb2_dev_alloc", "mb2_dev_free", "mb2_dev_copy", "mb2_ctx_make_current", "mb2_records_gather_frames",
+    "mb2_view_pack", "mb2_slot_from_records", "mb2_match_slots_range", "mb2_dev_alloc", "mb2_dev_free", "mb2_dev_copy", "mb2_ctx_make_current", "mb2_debug_fp64_peak", "mb2_records_gather_frames",
 ]
 
 
@@ -76,11 +76,16 @@ class OrientationParams(C.Structure):
 
 class SiftParams(C.Structure):
     _fields_ = [("mrSize", C.c_double), ("patchSize", C.c_int), ("photoNorm", C.c_int), ("rootSIFT", C.c_int),
-                ("fastPatchExtraction", C.c_int), ("doHalfSIFT", C.c_int), ("reserved", C.c_int)]
+                ("fastPatchExtraction", C.c_int), ("doHalfSIFT", C.c_int), ("dspScales", C.c_int), ("dspStartCoef", C.c_double), ("dspEndCoef", C.c_double)]
 
     @staticmethod
     def default():
-        return SiftParams(5.1962, 41, 1, 1, 0, 0, 0)
+        return SiftParams(5.1962, 41, 1, 1, 0, 0, 0, 0.5, 1.5)
+
+    @staticmethod
+    def dspsift(numScales=3, startCoef=0.5, endCoef=1.5):
+        """DSPSIFT (imagerepresentation.cpp:1547-1598) with the DomainSizePolingParams defaults (siftdesc.h:19-30)."""
+        return SiftParams(5.1962, 41, 1, 0, 0, 0, numScales, startCoef, endCoef)
 
 
 def build(force=False):
@@ -237,6 +242,12 @@ class Context:
         if _host is not None:
             return _host.mb2_mods_launch_count(self.h)
         return lib().mb2_ctx_launch_count(self.h)
+
+    def fp64_peak(self):
+        """Measured FP64 FMA throughput (TFLOP/s) of this device."""
+        v = C.c_double()
+        self._check(lib().mb2_debug_fp64_peak(self.h, C.byref(v)), "fp64_peak")
+        return v.value
 
     def profile_begin(self):
         self._check(lib().mb2_ctx_profile_begin(self.h), "profile_begin")

@@ -567,7 +567,25 @@ int orient_core(mb2_ctx* ctx, const ImgView& img, int n, const mb2_orientation_p
 }
 
 // describe the n records at d_keys; descriptors -> ctx->desc_u8 (device)
+int describe_core_one(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n, const mb2_sift_params& sp, float* d_dsp_acc, int dsp_first);
+// DescribeRegions for one descriptor; DSPSIFT (sp.dspScales > 0) = the raw plain-SIFT votes at dspScales + 1 measurement-region sizes,
+// summed in float, then the float SIFTnorm (imagerepresentation.cpp:1547-1598)
 int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n, const mb2_sift_params& sp) {
+  if (n <= 0) return MB2_OK;
+  if (sp.dspScales <= 0) return describe_core_one(ctx, img, d_keys, n, sp, nullptr, 0);
+  MB2_CUDA_CHECK(ctx, ctx->rs_u.reserve((size_t)n * 128 * 4));
+  float* acc = ctx->rs_u.as<float>();
+  for (int i = 0; i < sp.dspScales + 1; i++) {
+    mb2_sift_params one = sp;
+    one.rootSIFT = 0; one.doHalfSIFT = 0;
+    one.mrSize = sp.mrSize * (sp.dspStartCoef + i * (sp.dspEndCoef - sp.dspStartCoef) / sp.dspScales);
+    const int rc = describe_core_one(ctx, img, d_keys, n, one, acc, i == 0);
+    if (rc) return rc;
+  }
+  mb2_launch_dsp_norm(ctx, acc, n, ctx->desc_u8.as<uint8_t>());
+  return MB2_OK;
+}
+int describe_core_one(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n, const mb2_sift_params& sp, float* d_dsp_acc, int dsp_first) {
   if (n <= 0) return MB2_OK;
   if (sp.patchSize != 41) { ctx->set_error("describe: patchSize must be 41"); return MB2_ERR_ARG; }
   int rc;
@@ -577,7 +595,7 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
     ctx->set_error("describe: HalfSIFT without RootSIFT is undefined in the reference (SIFTnorm reads past the 64-entry vector)");
     return MB2_ERR_UNSUPPORTED;
   }
-  DescribeParams dp{sp.mrSize, sp.patchSize, sp.photoNorm, sp.rootSIFT, sp.fastPatchExtraction, sp.doHalfSIFT != 0 ? 1 : 0};
+  DescribeParams dp{sp.mrSize, sp.patchSize, sp.photoNorm, sp.rootSIFT, sp.fastPatchExtraction, sp.doHalfSIFT != 0 ? 1 : 0, d_dsp_acc ? 1 : 0};
   // largest possible m: the region must fit in the image for the earlier boundary tests, bound by the image diagonal
   const int max_m = (int)std::ceil(std::sqrt((double)img.rows * img.rows + (double)img.cols * img.cols)) + 8;
   TapTable taps;
@@ -624,9 +642,11 @@ int describe_core(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, int n,
   MB2_CUDA_CHECK(ctx, ctx->desc_u8.reserve((size_t)n * 128));
   float* base = ctx->patch_scratch.as<float>();
   priv(ctx)->last_patches = base + f_patches;
-  return mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, priv(ctx)->t.tap_n_host.data(), plan, d_off, base,
-                                    ctx->desc_u8.as<uint8_t>(), base + f_patches, (float2*)(base + f_stats), (double*)(base + f_vec),
-                                    (float2*)(base + f_rec));
+  rc = mb2_launch_describe_kernel(ctx, img, d_keys, n, dp, priv(ctx)->t.desc_tables.as<DescTables>(), taps, priv(ctx)->t.tap_n_host.data(), plan, d_off, base,
+                                  ctx->desc_u8.as<uint8_t>(), base + f_patches, (float2*)(base + f_stats), (double*)(base + f_vec),
+                                  (float2*)(base + f_rec));
+  if (rc == MB2_OK && d_dsp_acc) mb2_launch_dsp_accumulate(ctx, (const double*)(base + f_vec), n, d_dsp_acc, dsp_first);
+  return rc;
 }
 
 // FGINN on device-resident data.  out rows on host.
@@ -1164,6 +1184,38 @@ int mb2_records_gather_frames(mb2_ctx* ctx, const void* d_q, const void* d_t, co
   MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(frames14, ctx->rs_b.p, (size_t)n * 14 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return n;
+}
+
+namespace MB2_NS {
+// FP64 peak probe for the scorer's roofline (MEASURED_PEAKS.json has no FP64 figure): 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, double a, double b, int iters) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; it++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = __fma_rn(x[i], a, b);
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace MB2_NS
+int mb2_debug_fp64_peak(mb2_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const int grid = ctx->num_sms * 8, iters = 4096;
+  MB2_CUDA_CHECK(ctx, ctx->rs_a.reserve((size_t)grid * 256 * 8));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  MB2_NS::k_dfma_peak<<<grid, 256, 0, ctx->stream>>>(ctx->rs_a.as<double>(), 1.0000001, 1e-9, iters);
+  cudaEventRecord(e0, ctx->stream);
+  for (int r = 0; r < 5; r++) MB2_NS::k_dfma_peak<<<grid, 256, 0, ctx->stream>>>(ctx->rs_a.as<double>(), 1.0000001, 1e-9, iters);
+  cudaEventRecord(e1, ctx->stream);
+  MB2_CUDA_CHECK(ctx, cudaEventSynchronize(e1));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = 5.0 * 2.0 * grid * 256.0 * 8.0 * iters / (ms * 1e-3) / 1e12;
+  return MB2_OK;
 }
 
 int mb2_ctx_make_current(mb2_ctx* ctx) { if (!ctx) return MB2_ERR_ARG; MB2_CUDA_CHECK(ctx, cudaSetDevice(ctx->device)); return MB2_OK; }

@@ -717,8 +717,53 @@ k_sift_finish(double* __restrict__ vecT, int n, DescribeParams dp, uint8_t* __re
   for (int i = D; i < 128; i++) desc_out[(size_t)r * 128 + i] = 0;
 }
 
+// DSPSIFT (imagerepresentation.cpp:1547-1598): the raw votes of one measurement-region size, narrowed to float as SIFTDescriptor::operator()
+// hands them out (desc[i] = (float)vec[i], siftdesc.cpp:436-440), added in float to the running sum of the domains
+__global__ void k_dsp_accumulate(const double* __restrict__ vecT, int n, float* __restrict__ acc, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 128) return;
+  const int r = i >> 7, b = i & 127;
+  const float v = (float)vecT[(size_t)b * n + r];
+  acc[i] = first ? v : fadd(acc[i], v);
+}
+// SIFTnorm(std::vector<float>&) with the float normalize (siftdesc.cpp:160-184, 263-278), one thread per region
+__global__ void __launch_bounds__(128) k_dsp_norm(float* __restrict__ acc, int n, uint8_t* __restrict__ desc_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float* v = acc + (size_t)r * 128;
+  const double maxBinValue = (double)0.2f;
+  for (int pass = 0; pass < 2; pass++) {
+    float len = 0.0f;
+    for (int i = 0; i < 128; i += 4) {
+      const float sq0 = fmul(v[i], v[i]), sq1 = fmul(v[i + 1], v[i + 1]), sq2 = fmul(v[i + 2], v[i + 2]), sq3 = fmul(v[i + 3], v[i + 3]);
+      len = fadd(len, fadd(fadd(fadd(sq0, sq1), sq2), sq3));
+    }
+    len = (float)__dsqrt_rn((double)len);
+    const float fac = (float)__ddiv_rn(1.0, (double)len);
+    bool changed = false;
+    for (int i = 0; i < 128; i++) {
+      float x = fmul(v[i], fac);
+      if (pass == 0 && (double)x > maxBinValue) { x = (float)maxBinValue; changed = true; }
+      v[i] = x;
+    }
+    if (pass == 1 || !changed) break;
+  }
+  for (int i = 0; i < 128; i++) {
+    int b = (int)d_add((double)fmul(512.0f, v[i]), 0.5);
+    b = b < 0 ? 0 : (b > 255 ? 255 : b);
+    desc_out[(size_t)r * 128 + i] = (uint8_t)b;
+  }
+}
+
 }  // namespace
 using namespace MB2_NS;
+
+void mb2_launch_dsp_accumulate(mb2_ctx* ctx, const double* d_vecT, int n, float* d_acc, int first) {
+  if (n) MB2_LAUNCH(ctx, k_dsp_accumulate, (n * 128 + 255) / 256, 256, 0, d_vecT, n, d_acc, first);
+}
+void mb2_launch_dsp_norm(mb2_ctx* ctx, float* d_acc, int n, uint8_t* d_desc) {
+  if (n) MB2_LAUNCH(ctx, k_dsp_norm, (n + 127) / 128, 128, 0, d_acc, n, d_desc);
+}
 
 int mb2_describe_plan(mb2_ctx* ctx, const KeyOut* kps, int n, const DescribeParams& dp, int max_m, unsigned long long* d_need,
                       int* d_too_big, unsigned long long* d_sum_p2sq, unsigned long long* d_keys, int* d_cls_cnt) {
@@ -793,6 +838,6 @@ int mb2_launch_describe_kernel(mb2_ctx* ctx, const ImgView& img, const KeyOut* k
   if (dp.photoNorm) MB2_LAUNCH(ctx, k_photonorm_stats, (n + PN_T - 1) / PN_T, PN_T, 0, d_patches, n, d_tables, d_stats);
   MB2_LAUNCH(ctx, k_sift_grad, n, DT, 0, d_patches, n, dp, d_tables, d_stats, d_rec);
   MB2_LAUNCH(ctx, k_sift_votes, (n + VW - 1) / VW, VW * 32, 0, d_rec, n, d_tables, d_vecT);
-  MB2_LAUNCH(ctx, k_sift_finish, (n + 127) / 128, 128, 0, d_vecT, n, dp, d_desc);
+  if (!dp.raw) MB2_LAUNCH(ctx, k_sift_finish, (n + 127) / 128, 128, 0, d_vecT, n, dp, d_desc);   // raw: the caller takes the votes (DSPSIFT)
   return MB2_OK;
 }

@@ -84,7 +84,9 @@ void mb2_launch_extract_angles(mb2_ctx* ctx, const KeyOut* keys, int n, float* d
 void mb2_launch_apply_rotation(mb2_ctx* ctx, KeyOut* keys, const double* d_cs, int n);
 
 // describe.cu
-struct DescribeParams { double mrSize; int patchSize; int photoNorm; int rootSIFT; int fast; int half; };
+struct DescribeParams { double mrSize; int patchSize; int photoNorm; int rootSIFT; int fast; int half; int raw; };   // raw: leave the un-normalised votes (DSPSIFT)
+void mb2_launch_dsp_accumulate(mb2_ctx* ctx, const double* d_vecT, int n, float* d_acc, int first);
+void mb2_launch_dsp_norm(mb2_ctx* ctx, float* d_acc, int n, uint8_t* d_desc);
 struct DescTables {      // precomputed on the host exactly as the reference's constructors do
   float mask[41 * 41];   // computeCircularGaussMask(41), siftdesc.h:87 / synth-detection.hpp:181
   int bin0[41], bin1[41];

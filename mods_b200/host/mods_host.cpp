@@ -42,8 +42,8 @@ DetectorsParameters::DetectorsParameters() {
   MSERParam = mb2_mser_params{0.05, 30, 8.0, 0, 0, -1, -1.f, -1.f};
 }
 DescriptorsParameters::DescriptorsParameters() {
-  SIFTParam = mb2_sift_params{5.1962, 41, 1, 0, 0, 0, 0};
-  RootSIFTParam = mb2_sift_params{5.1962, 41, 1, 1, 0, 0, 0};
+  SIFTParam = mb2_sift_params{5.1962, 41, 1, 0, 0, 0, 0, 0.5, 1.5};
+  RootSIFTParam = mb2_sift_params{5.1962, 41, 1, 1, 0, 0, 0, 0.5, 1.5};
   HalfRootSIFTParam = RootSIFTParam; HalfRootSIFTParam.doHalfSIFT = 1;   // io_mods.cpp:752-753
   HalfSIFTParam = HalfRootSIFTParam;                                     // io_mods.cpp:756 (HalfSIFT is HalfRootSIFT in the reference)
 }
@@ -99,6 +99,7 @@ descriptor_type ImageRepresentation::GetDescriptorType(std::string n) const {
   if (n == "RootSIFT") return DESC_ROOT_SIFT;
   if (n == "HalfSIFT") return DESC_HALF_SIFT;
   if (n == "HalfRootSIFT") return DESC_HALF_ROOT_SIFT;
+  if (n == "DSPSIFT") return DESC_DSP_SIFT;
   return DESC_UNKNOWN;
 }
 detector_type ImageRepresentation::GetDetectorType(std::string n) const {
@@ -165,6 +166,7 @@ void ImageRepresentation::SynthDetectDescribeKeypoints(IterationViewsynthesisPar
         if (dt == DESC_UNKNOWN) continue;
         mb2_sift_params sp = dt == DESC_ROOT_SIFT ? desc_par.RootSIFTParam : dt == DESC_HALF_ROOT_SIFT ? desc_par.HalfRootSIFTParam
                              : dt == DESC_HALF_SIFT ? desc_par.HalfSIFTParam : desc_par.SIFTParam;
+        if (dt == DESC_DSP_SIFT) { sp.rootSIFT = 0; sp.doHalfSIFT = 0; sp.dspScales = desc_par.DSPScales; sp.dspStartCoef = desc_par.DSPStartCoef; sp.dspEndCoef = desc_par.DSPEndCoef; }   // imagerepresentation.cpp:1547-1598
         mb2_orientation_params op{dom_ori_par.mrSize, dom_ori_par.patchSize, dom_ori_par.maxAngles, (double)dom_ori_par.threshold, half_like ? 1 : 0, 0};
         const double t0 = now_ms();
         const bool use_slot = slot >= 0 && (ss.desc.empty() || ss.desc == curr_desc);

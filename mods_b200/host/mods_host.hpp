@@ -23,7 +23,7 @@
 namespace mods {
 
 enum detector_type { DET_HESSIAN = 0, DET_DOG = 1, DET_HARRIS = 2, DET_MSER = 3, DET_UNKNOWN = 1000 };
-enum descriptor_type { DESC_SIFT = 0, DESC_ROOT_SIFT = 1, DESC_HALF_SIFT = 2, DESC_HALF_ROOT_SIFT = 3, DESC_UNKNOWN = 1000 };
+enum descriptor_type { DESC_SIFT = 0, DESC_ROOT_SIFT = 1, DESC_HALF_SIFT = 2, DESC_HALF_ROOT_SIFT = 3, DESC_DSP_SIFT = 19, DESC_UNKNOWN = 1000 };   // detectors/structures.hpp:76-97
 enum RANSAC_error_t { SAMPSON, SYMM_MAX, SYMM_SUM };
 const int MODE_RANDOM = 0, MODE_FGINN = 1, MODE_DISTANCE = 2, MODE_BIGGER_REGION = 3;  // configuration.hpp:31-34
 
@@ -69,7 +69,11 @@ struct TimeLog {  // detectors/structures.hpp:51-74
 };
 
 struct DetectorsParameters { mb2_hessaff_params HessParam; mb2_mser_params MSERParam; DetectorsParameters(); };
-struct DescriptorsParameters { mb2_sift_params SIFTParam, RootSIFTParam, HalfRootSIFTParam, HalfSIFTParam; DescriptorsParameters(); };
+struct DescriptorsParameters {
+  mb2_sift_params SIFTParam, RootSIFTParam, HalfRootSIFTParam, HalfSIFTParam;
+  int DSPScales = 3; double DSPStartCoef = 0.5, DSPEndCoef = 1.5;   // SIFTParam.DSPParam (DomainSizePolingParams, siftdesc.h:19-30)
+  DescriptorsParameters();
+};
 struct DominantOrientationParams {  // descriptors_parameters.hpp:23-36 + [DominantOrientation]
   int maxAngles = 1; float threshold = 0.8f; bool addUpRight = false; bool halfSIFTMode = false;
   double mrSize = 1.0; int patchSize = 41;

@@ -199,6 +199,10 @@ void orc_describe(const float* img, int w, int h, const double* kps, int n, doub
   SIFTDescriptor D(patchSize, (rootsift & 1) != 0); D.doHalfSIFT = (rootsift & 2) != 0;   // flags: bit0 RootSIFT, bit1 Half descriptor
   describeRegions(keys_in(kps, n), image_in(img, w, h), D, mrSize, patchSize, fast != 0, photoNorm != 0, desc, patches);
 }
+void orc_describe_dsp(const float* img, int w, int h, const double* kps, int n, double mrSize, int patchSize, int fast, int photoNorm, int numScales,
+                      double startCoef, double endCoef, float* desc) {
+  describeRegionsDSP(keys_in(kps, n), image_in(img, w, h), mrSize, patchSize, fast != 0, photoNorm != 0, numScales, startCoef, endCoef, desc);
+}
 void orc_sift_patch(const float* patch41, int rootsift, float* desc128) {
   SIFTDescriptor D(41, (rootsift & 1) != 0); D.doHalfSIFT = (rootsift & 2) != 0;
   D(patch41, desc128);

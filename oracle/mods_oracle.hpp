@@ -784,6 +784,7 @@ struct SIFTDescriptor {
   double maxBinValue = 0.2f;  // siftdesc.h:56 (a float literal stored in a double)
   bool useRootSIFT = false;
   bool doHalfSIFT = false;   // with useRootSIFT: HalfRootSIFT (64 entries; rows stay 128 wide, the upper 64 are 0)
+  bool doNorm = true;        // siftdesc.h:47; false: the raw votes come back (DSPSIFT, imagerepresentation.cpp:1549-1551)
   std::vector<float> mask, grad, ori;
   std::vector<int> bin0, bin1;
   std::vector<double> w0, w1, vec;
@@ -877,8 +878,26 @@ struct SIFTDescriptor {
       for (size_t i = 0; i < vec.size(); i++) desc[i] = i < half_vec.size() ? (float)half_vec[i] : 0.0f;
       return;
     }
-    finish(vec);
+    if (doNorm) finish(vec);
     for (size_t i = 0; i < vec.size(); i++) desc[i] = (float)vec[i];
+  }
+  // SIFTnorm(std::vector<float>&) with the float normalize (siftdesc.cpp:160-184, 263-278): what DSPSIFT applies to the summed votes
+  void finishFloat(float* v) const {
+    auto normalizef = [](float* x) {
+      float len = 0.0f;
+      for (int i = 0; i < 128; i += 4) {
+        const float sq0 = x[i] * x[i], sq1 = x[i + 1] * x[i + 1], sq2 = x[i + 2] * x[i + 2], sq3 = x[i + 3] * x[i + 3];
+        len += sq0 + sq1 + sq2 + sq3;
+      }
+      len = (float)std::sqrt((double)len);
+      const double fac = 1.0 / len;
+      for (int i = 0; i < 128; i++) x[i] *= (float)fac;
+    };
+    normalizef(v);
+    bool changed = false;
+    for (int i = 0; i < 128; i++) if (v[i] > maxBinValue) { v[i] = (float)maxBinValue; changed = true; }
+    if (changed) normalizef(v);
+    for (int i = 0; i < 128; i++) { int b = std::max(0, std::min((int)(512.0f * v[i] + 0.5), 255)); v[i] = float(b); }
   }
 };
 
@@ -918,6 +937,22 @@ inline void describeRegions(const std::vector<Key>& kps, const Image& img, SIFTD
     if (patch_out) std::memcpy(patch_out + i * patch.size(), patch.data(), sizeof(float) * patch.size());
     D(patch.data(), desc_out + i * 128);
   }
+}
+
+// imagerepresentation.cpp:1547-1598 ("DSPSIFT"): the un-normalised SIFT votes described at numScales + 1 measurement-region sizes
+// mrSize * (start + i (end - start) / numScales), summed in float, then SIFTnorm on the float vector
+inline void describeRegionsDSP(const std::vector<Key>& kps, const Image& img, double mrSize, int patchSize, bool fast_extraction, bool photoNorm,
+                               int numScales, double startCoef, double endCoef, float* desc_out) {
+  SIFTDescriptor D(patchSize, false);
+  D.doNorm = false;
+  std::vector<float> tmp(kps.size() * 128);
+  for (int dsp_idx = 0; dsp_idx < numScales + 1; dsp_idx++) {
+    const double curr_mrSize = mrSize * (startCoef + dsp_idx * (endCoef - startCoef) / numScales);
+    describeRegions(kps, img, D, curr_mrSize, patchSize, fast_extraction, photoNorm, tmp.data());
+    for (size_t i = 0; i < tmp.size(); i++) desc_out[i] = dsp_idx == 0 ? tmp[i] : desc_out[i] + tmp[i];
+  }
+  D.doNorm = true;
+  for (size_t k = 0; k < kps.size(); k++) D.finishFloat(desc_out + k * 128);
 }
 
 // ------------------------------------------------------------------------------------------

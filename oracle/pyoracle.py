@@ -127,6 +127,14 @@ class Lib:
         self.fn("describe", None)(*args)
         return (desc[:n].copy(), patches[:n].copy()) if want_patches else desc[:n].copy()
 
+    def describe_dsp(self, img, kps, mrSize=5.1962, patchSize=41, fast=False, photoNorm=True, numScales=3, startCoef=0.5, endCoef=1.5):
+        """DSPSIFT (imagerepresentation.cpp:1547-1598; DomainSizePolingParams defaults siftdesc.h:23-29)."""
+        img = _f32(img); kps = _f64(kps); n = len(kps)
+        desc = np.zeros((max(1, n), 128), np.float32)
+        self.fn("describe_dsp", None)(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(kps), C.c_int(n), C.c_double(mrSize), C.c_int(patchSize),
+                                      C.c_int(int(fast)), C.c_int(int(photoNorm)), C.c_int(numScales), C.c_double(startCoef), C.c_double(endCoef), _p(desc))
+        return desc[:n].copy()
+
     def sift_patch(self, patch, rootsift=True):
         patch = _f32(patch); out = np.zeros(128, np.float32)
         self.fn("sift_patch", None)(_p(patch), C.c_int(int(rootsift)), _p(out))

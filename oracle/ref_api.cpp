@@ -253,6 +253,38 @@ void ref_describe(const float* img, int w, int h, const double* kps, int n, doub
   for (int i = 0; i < n; i++)
     for (int j = 0; j < 128; j++) desc[(size_t)i * 128 + j] = j < (int)l[i].desc.vec.size() ? l[i].desc.vec[j] : 0.f;
 }
+// The "DSPSIFT" branch of SynthDetectDescribeKeypoints (imagerepresentation.cpp:1547-1598), which cannot be compiled here (it pulls
+// every descriptor family): the same reference calls in the same order -- DescribeRegions with an un-normalised plain-SIFT functor at
+// numScales + 1 measurement-region sizes, float sums, SIFTnorm(std::vector<float>&) of a functor with doNorm on.
+void ref_describe_dsp(const float* img, int w, int h, const double* kps, int n, double mrSize, int patchSize, int fast, int photoNorm, int numScales,
+                      double startCoef, double endCoef, float* desc /* n x 128 */) {
+  SynthImage view; identity_view(view, img, w, h);
+  AffineRegionList temp_kp1_desc = regions_in(kps, n), dsp_desc;
+  SIFTDescriptorParams dspsiftparams;
+  dspsiftparams.PEParam.patchSize = patchSize; dspsiftparams.PEParam.mrSize = mrSize;
+  dspsiftparams.useRootSIFT = false;
+  dspsiftparams.doNorm = false;
+  SIFTDescriptor DSPSIFTdesc(dspsiftparams);
+  const int num_domains = numScales;
+  for (int dsp_idx = 0; dsp_idx < num_domains + 1; dsp_idx++) {
+    dsp_desc = temp_kp1_desc;
+    const double curr_mrSize = mrSize * (startCoef + dsp_idx * (endCoef - startCoef) / num_domains);
+    DescribeRegions(dsp_desc, view, DSPSIFTdesc, curr_mrSize, patchSize, fast != 0, photoNorm != 0);
+    for (size_t kp_idx = 0; kp_idx < dsp_desc.size(); kp_idx++) {
+      const int desc_dim = (int)dsp_desc[kp_idx].desc.vec.size();
+      temp_kp1_desc[kp_idx].desc.vec.resize(desc_dim);
+      for (int e = 0; e < desc_dim; e++) {
+        if (dsp_idx == 0) temp_kp1_desc[kp_idx].desc.vec[e] = dsp_desc[kp_idx].desc.vec[e];
+        else temp_kp1_desc[kp_idx].desc.vec[e] += dsp_desc[kp_idx].desc.vec[e];
+      }
+    }
+  }
+  dspsiftparams.doNorm = true;
+  SIFTDescriptor DSPSIFTdesc1(dspsiftparams);
+  for (size_t kp_idx = 0; kp_idx < temp_kp1_desc.size(); kp_idx++) DSPSIFTdesc1.SIFTnorm(temp_kp1_desc[kp_idx].desc.vec);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < 128; j++) desc[(size_t)i * 128 + j] = j < (int)temp_kp1_desc[i].desc.vec.size() ? temp_kp1_desc[i].desc.vec[j] : 0.f;
+}
 void ref_sift_patch(const float* patch41, int rootsift, float* desc128) {
   SIFTDescriptorParams sp; sp.useRootSIFT = rootsift & 1; sp.doHalfSIFT = (rootsift & 2) ? 1 : 0;
   SIFTDescriptor D(sp);

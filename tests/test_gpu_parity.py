@@ -319,6 +319,22 @@ def test_dog_detector_vs_oracle_and_golden(ctx, oracle, mode, regs):
             assert np.array_equal(ctx.pyramid_level(lv["octave"], lv["level"], want_resp=True)[0], lv["resp"])
 
 
+# ---- DSPSIFT ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scales,start,end,photo", [(3, 0.5, 1.5, 1), (4, 0.6, 1.2, 0)])
+def test_dspsift_vs_oracle_and_golden(ctx, oracle, scales, start, end, photo):
+    """mb2_sift_params.dspScales > 0 (imagerepresentation.cpp:1547-1598): raw votes at dspScales + 1 region sizes summed in float, float
+    SIFTnorm; bit-exact against the oracle (== compiled reference) and the reference's golden vectors."""
+    im = synth.blob_image(480, 360, seed=35)
+    k = oracle.detect_orientation(im, oracle.hessaff_detect(im))
+    sp = mb.SiftParams.dspsift(scales, start, end); sp.photoNorm = photo
+    g = ctx.describe_sift(im, k, sp)
+    o = oracle.describe_dsp(im, k, numScales=scales, startCoef=start, endCoef=end, photoNorm=bool(photo))
+    assert len(k) > 500 and np.array_equal(g.astype(np.float32), o)
+    if photo:
+        GD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dsp_vectors.npz"))
+        assert np.array_equal(ctx.describe_sift(GD["image"].astype(np.float32), GD["keys"], mb.SiftParams.dspsift()), GD["desc_default"])
+
+
 # ---- Harris flavour of the scale-space detector ---------------------------------------------------------
 @pytest.mark.parametrize("mode,regs", [(0, 1000), (4, 200), (2, 150)])
 def test_harris_detector_vs_oracle_and_golden(ctx, oracle, mode, regs):

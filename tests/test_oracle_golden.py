@@ -105,3 +105,12 @@ def test_harris_detector_matches_reference(oracle):
     assert np.array_equal(oracle.hessaff_detect(im, hp, raw=True), GD["raw_not_less_80"])
     v = oracle.view_pipeline(im, hp=HessParams.harris())
     assert np.array_equal(v[0], GD["view_det"]) and np.array_equal(v[2].astype(np.uint8), GD["view_desc"])
+
+
+def test_dspsift_matches_reference(oracle):
+    """DSPSIFT (imagerepresentation.cpp:1547-1598): tests/golden/make_golden_dsp.py."""
+    GD = np.load(os.path.join(os.path.dirname(__file__), "golden", "dsp_vectors.npz"))
+    im = GD["image"].astype(np.float32)
+    assert len(GD["keys"]) > 100
+    assert np.array_equal(oracle.describe_dsp(im, GD["keys"]).astype(np.uint8), GD["desc_default"])
+    assert np.array_equal(oracle.describe_dsp(im, GD["keys"], numScales=5, startCoef=0.7, endCoef=1.3, photoNorm=False).astype(np.uint8), GD["desc_5_07_13_nophoto"])

@@ -241,3 +241,13 @@ def test_harris_detector_oracle_vs_reference(oracle, reference, mode, regs):
     if mode == 0:
         va, vb = oracle.view_pipeline(im, hp=hp), reference.view_pipeline(im, hp=hp)
         assert all(np.array_equal(x, y) for x, y in zip(va, vb))
+
+
+@pytest.mark.parametrize("scales,start,end,photo", [(3, 0.5, 1.5, True), (1, 1.0, 2.0, True), (4, 0.6, 1.2, False)])
+def test_dspsift_oracle_vs_reference(oracle, reference, scales, start, end, photo):
+    """DSPSIFT: the restated glue + float SIFTnorm == the reference's DescribeRegions / SIFTDescriptor driven the same way."""
+    im = synth.blob_image(320, 240, seed=8)
+    k = oracle.detect_orientation(im, oracle.hessaff_detect(im))
+    a = oracle.describe_dsp(im, k, numScales=scales, startCoef=start, endCoef=end, photoNorm=photo)
+    b = reference.describe_dsp(im, k, numScales=scales, startCoef=start, endCoef=end, photoNorm=photo)
+    assert len(k) > 100 and np.array_equal(a, b) and a.max() <= 255
