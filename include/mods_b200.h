@@ -251,6 +251,8 @@ int mb2_match_slots_range(mb2_ctx* ctx, int q_slot, int t_slot, int q_lo, int q_
 /* frames14 [H]: n rows of 14 doubles = the 7 reproj_kp doubles of record q_idx[i] of d_q followed by those of record t_idx[i] of d_t
  * (q_idx / t_idx [H]) -- what DuplicateFiltering / LORANSACFiltering read of a TentativeCorrespExt, without moving whole record sets. */
 int mb2_records_gather_frames(mb2_ctx* ctx, const void* d_q, const void* d_t, const int* q_idx, const int* t_idx, int n, double* frames14);
+/* order-sensitive 64-bit checksum of n records [D], computed on the device: sum over i of (i + 1) * FNV-1a(record i) modulo 2^64 */
+int mb2_records_checksum(mb2_ctx* ctx, const void* d_records, int n, unsigned long long* out);
 
 /* Hands a device-resident region set over to another context on the same GPU (no copy).  Lets two host
  * threads run mb2_detect_describe_view for the two images of a pair on two contexts (= two streams), the

@@ -1171,6 +1171,33 @@ __global__ void k_gather_frames(const uint8_t* __restrict__ q, const uint8_t* __
 }
 }  // namespace MB2_NS
 
+namespace MB2_NS {
+__global__ void k_records_checksum(const uint8_t* __restrict__ rec, int n, unsigned long long* __restrict__ out) {
+  unsigned long long acc = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(rec + (size_t)i * MB2_REGION_RECORD_BYTES);
+    unsigned long long h = 1469598103934665603ull;
+    for (int k = 0; k < MB2_REGION_RECORD_BYTES / 4; k++) { h ^= w[k]; h *= 1099511628211ull; }
+    acc += h * (unsigned long long)(i + 1);
+  }
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+}  // namespace MB2_NS
+int mb2_records_checksum(mb2_ctx* ctx, const void* d_records, int n, unsigned long long* out) {
+  if (!ctx || !out || n < 0 || (n > 0 && !d_records)) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  *out = 0;
+  if (n == 0) return MB2_OK;
+  MB2_CUDA_CHECK(ctx, ctx->misc.reserve(4096));
+  unsigned long long* d = ctx->misc.as<unsigned long long>() + 64;
+  MB2_CUDA_CHECK(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+  MB2_LAUNCH(ctx, MB2_NS::k_records_checksum, ctx->num_sms * 4, 256, 0, (const uint8_t*)d_records, n, d);
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MB2_OK;
+}
+
 int mb2_records_gather_frames(mb2_ctx* ctx, const void* d_q, const void* d_t, const int* q_idx, const int* t_idx, int n, double* frames14) {
   if (!ctx || n < 0 || (n > 0 && (!d_q || !d_t || !q_idx || !t_idx || !frames14))) return MB2_ERR_ARG;
   if (n == 0) return 0;

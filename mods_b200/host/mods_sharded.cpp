@@ -249,10 +249,16 @@ int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const 
       got.resize((size_t)mx * 7 * world);
       mb2_dev_copy(ctx, got.data(), d_ar, got.size() * 8, 1);
       if (mb2_ctx_sync(ctx) != MB2_OK) return MB2_ERR_CUDA;
-      for (int r = 0; r < world; r++)
-        for (int i = 0; i < ncnt[r]; i++) { rows_all.push_back(det); for (int c = 0; c < 7; c++) rows_all.push_back(got[((size_t)r * mx + i) * 7 + c]); }
-    } else
-      for (int i = 0; i < n; i++) { rows_all.push_back(det); for (int c = 0; c < 7; c++) rows_all.push_back(rows[(size_t)i * 7 + c]); }
+      for (int r = 0; r < world; r++) {
+        const size_t base = rows_all.size();
+        rows_all.resize(base + (size_t)ncnt[r] * 8);
+        for (int i = 0; i < ncnt[r]; i++) { double* o = &rows_all[base + (size_t)i * 8]; o[0] = det; std::memcpy(o + 1, &got[((size_t)r * mx + i) * 7], 56); }
+      }
+    } else {
+      const size_t base = rows_all.size();
+      rows_all.resize(base + (size_t)n * 8);
+      for (int i = 0; i < n; i++) { double* o = &rows_all[base + (size_t)i * 8]; o[0] = det; std::memcpy(o + 1, &rows[(size_t)i * 7], 56); }
+    }
     int tot = 0;
     for (int c : ncnt) tot += c;
     if (world == 1) tot = n;
@@ -260,20 +266,18 @@ int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const 
     if (det == 1) res->mser_tentatives = tot;
     t_tgather += now_ms() - tm1;
   }
-  // ---- checksums (order-sensitive): records of the four sets, tentative rows
+  // ---- checksums (order-sensitive): records of the four sets on the device, tentative rows on the host
   if (digest) {
     digest[0] = digest[1] = digest[2] = digest[3] = 0;
-    std::vector<unsigned char> h;
     for (int s = 0; s < 4; s++) {
-      h.resize((size_t)set_n[s] * REC);
-      if (set_n[s]) { mb2_dev_copy(ctx, h.data(), ordered[s].p, h.size(), 1); mb2_ctx_sync(ctx); }
-      unsigned long long a = 1469598103934665603ull;   // FNV-1a over the bytes
-      for (unsigned char b : h) { a ^= b; a *= 1099511628211ull; }
-      digest[s >> 1] ^= a * (unsigned long long)(2 * (s & 1) + 1);
+      unsigned long long a = 0;
+      const int rc = mb2_records_checksum(ctx, ordered[s].p, set_n[s], &a);
+      if (rc < 0) return rc;
+      digest[s >> 1] ^= (a + (unsigned long long)set_n[s]) * (unsigned long long)(2 * (s & 1) + 1);
     }
     unsigned long long a = 1469598103934665603ull;
-    const unsigned char* rb = (const unsigned char*)rows_all.data();
-    for (size_t i = 0; i < rows_all.size() * 8; i++) { a ^= rb[i]; a *= 1099511628211ull; }
+    const unsigned long long* rb = (const unsigned long long*)rows_all.data();
+    for (size_t i = 0; i < rows_all.size(); i++) { a ^= rb[i]; a *= 1099511628211ull; }
     digest[2] = a; digest[3] = (unsigned long long)res->tentatives;
   }
   // ---- rank 0 verifies (mods.cpp:298-415)
