@@ -273,6 +273,16 @@ int mb2_slot_move(mb2_ctx* dst, int dst_slot, mb2_ctx* src, int src_slot);
 int mb2_match_fginn(mb2_ctx* ctx, const uint8_t* q_desc, int nq, const uint8_t* t_desc, int nt,
                     const double* t_xy, double matchRatio, double contradDist, int nn, double* out,
                     int capacity);
+/* Replaces `int MatchFLANNDistance(const AffineRegionList& q, const AffineRegionList& t, TentativeCorrespListExt&, const MatchPars&,
+ * int nn = 50)` (matching/matching.cpp:607-666; called from correspondencebank.cpp:284,343 for binary descriptors when
+ * matchDistanceThreshold > 0) for binary_matcher = linear, binary_dist = Hamming: exact 2-NN on the number of differing bits, a query
+ * is kept when its first distance is <= (int)(float)matchDistanceThreshold.  q_desc / t_desc: n * desc_bytes bytes [H|D]
+ * (the reference floors AffineRegion::desc.vec to bytes itself), desc_bytes 1..64 (ORB 32, BRISK / FREAK 64); nt >= 2.
+ * out [H]: rows of 7 doubles in the layout of mb2_match_fginn { query, idx0, idx1, idx1, d0, d1, d1 }: TentativeCorrespExt{first,
+ * second, d1, d2}, ratio = d0 / d1 in double is the caller's (matching.cpp:659).  Ties: lower train index first.
+ * Returns the number of tentatives. */
+int mb2_match_hamming(mb2_ctx* ctx, const uint8_t* q_desc, int nq, const uint8_t* t_desc, int nt, int desc_bytes,
+                      double matchDistanceThreshold, double* out, int capacity);
 /* Same, on two device-resident region sets left by mb2_detect_describe_view. */
 int mb2_match_slots(mb2_ctx* ctx, int q_slot, int t_slot, double matchRatio, double contradDist, int nn,
                     double* out, int capacity);

@@ -17,7 +17,7 @@ KP = 9
 EXPORTS = [
     "mb2_ctx_create", "mb2_ctx_destroy", "mb2_last_error", "mb2_ctx_sync", "mb2_ctx_stream", "mb2_ctx_launch_count",
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
-    "mb2_match_fginn", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_ransac_f", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
+    "mb2_match_fginn", "mb2_match_hamming", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_ransac_f", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
     "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair", "mb2_synth_view", "mb2_detect_describe_synth_view", "mb2_ctx_tree_epoch", "mb2_ctx_wait_tree", "mb2_ctx_create_prio",
     "mb2_view_pack", "mb2_slot_from_records", "mb2_match_slots_range", "mb2_dev_alloc", "mb2_dev_free", "mb2_dev_copy", "mb2_ctx_make_current", "mb2_debug_fp64_peak", "mb2_records_gather_frames", "mb2_records_checksum",
 ]
@@ -395,6 +395,16 @@ class Context:
         n = self._check(lib().mb2_match_fginn(self.h, _ptr(q_desc), C.c_int(nq), _ptr(t_desc), C.c_int(nt), _ptr(t_xy),
                                               C.c_double(ratio), C.c_double(contradDist), C.c_int(nn), _ptr(out), C.c_int(len(out))),
                         "match_fginn")
+        return out[:n].copy()
+
+    def match_hamming(self, q_desc, t_desc, max_distance=64.0):
+        """MatchFLANNDistance (matching.cpp:607-666): exact Hamming 2-NN of byte descriptors.  Rows: q idx0 idx1 idx1 d0 d1 d1."""
+        q_desc = np.ascontiguousarray(q_desc, np.uint8); t_desc = np.ascontiguousarray(t_desc, np.uint8)
+        nq, nt = len(q_desc), len(t_desc)
+        nbytes = q_desc.shape[1] if q_desc.ndim == 2 else t_desc.shape[1]
+        out = np.zeros((max(1, nq), 7))
+        n = self._check(lib().mb2_match_hamming(self.h, _ptr(q_desc), C.c_int(nq), _ptr(t_desc), C.c_int(nt), C.c_int(nbytes),
+                                                C.c_double(max_distance), _ptr(out), C.c_int(len(out))), "match_hamming")
         return out[:n].copy()
 
     def match_slots(self, q_slot, t_slot, ratio=0.8, contradDist=30.0, nn=50, capacity=1 << 20):

@@ -649,6 +649,31 @@ int describe_core_one(mb2_ctx* ctx, const ImgView& img, const KeyOut* d_keys, in
   return rc;
 }
 
+// ordered compaction of the accepted rows of a matcher; out rows on the host
+int compact_rows(mb2_ctx* ctx, const MatchRow* rows, const int* accept, int nq, double* out, int capacity) {
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr, nq, ctx->stream);
+  const int cap = std::min(capacity, nq);
+  MB2_CUDA_CHECK(ctx, ctx->nn_d.reserve((size_t)nq * 4 + 16 + cub_bytes + 64 + (size_t)std::max(cap, 1) * 7 * 8));
+  int* pos = ctx->nn_d.as<int>();
+  int* total = pos + nq;
+  void* cub_tmp = (void*)(((uintptr_t)(total + 1) + 15) & ~(uintptr_t)15);
+  double* d_out = (double*)(((uintptr_t)((uint8_t*)cub_tmp + cub_bytes) + 15) & ~(uintptr_t)15);
+  MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, accept, pos, nq, ctx->stream));
+  ctx->launches += 1;
+  LAUNCH1D(ctx, k_match_scatter, nq, rows, accept, pos, nq, d_out, cap, total);
+  int n_match = 0;
+  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_match, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const int m = std::min(n_match, cap);
+  if (m > 0) {
+    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_out, (size_t)m * 7 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (n_match > capacity) { ctx->set_error("match: output capacity too small"); return MB2_ERR_CAPACITY; }
+  return n_match;
+}
+
 // FGINN on device-resident data.  out rows on host.
 int match_core(mb2_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, const double* d_txy, double matchRatio,
                double contradDist, int nn, double* out, int capacity) {
@@ -682,33 +707,36 @@ int match_core(mb2_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int
   else {
     for (int pass = 1; pass <= 2; pass++) {
       if (simt) mb2_nn_pass_simt(ctx, pass, d_q, nq, d_t, nt, qn, tn, st, d_txy, contr2);
-      else if ((rc = mb2_nn_pass_tc(ctx, pass, q_bf16, nq, nq_pad, t_bf16, nt_pad, qn, tn, st, d_txy, contr2))) return rc;
+      else if ((rc = mb2_nn_pass_tc(ctx, pass, q_bf16, nq, nq_pad, t_bf16, nt_pad, qn, tn, st, d_txy, contr2, std::min(nn, nt) - 1))) return rc;
+      // the tcgen05 passes record a minimum with its 32-column block: recover the train index of the one winning block per query
+      mb2_nn_resolve(ctx, pass == 1 ? st.best0 : st.bestP, nq, d_q, d_t, nt, qn, tn);
       if (pass == 1) mb2_nn_threshold(ctx, st, nq, qn, sqminratio);
     }
     mb2_nn_finalize(ctx, st, nq, nt, nn, rows, accept);
   }
-  // ordered compaction of the accepted rows
-  size_t cub_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr, nq, ctx->stream);
-  const int cap = std::min(capacity, nq);
-  MB2_CUDA_CHECK(ctx, ctx->nn_d.reserve((size_t)nq * 4 + 16 + cub_bytes + 64 + (size_t)std::max(cap, 1) * 7 * 8));
-  int* pos = ctx->nn_d.as<int>();
-  int* total = pos + nq;
-  void* cub_tmp = (void*)(((uintptr_t)(total + 1) + 15) & ~(uintptr_t)15);
-  double* d_out = (double*)(((uintptr_t)((uint8_t*)cub_tmp + cub_bytes) + 15) & ~(uintptr_t)15);
-  MB2_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, accept, pos, nq, ctx->stream));
-  ctx->launches += 1;
-  LAUNCH1D(ctx, k_match_scatter, nq, rows, accept, pos, nq, d_out, cap, total);
-  int n_match = 0;
-  MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_match, total, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  const int m = std::min(n_match, cap);
-  if (m > 0) {
-    MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_out, (size_t)m * 7 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  }
-  if (n_match > capacity) { ctx->set_error("match: output capacity too small"); return MB2_ERR_CAPACITY; }
-  return n_match;
+  return compact_rows(ctx, rows, accept, nq, out, capacity);
+}
+
+// MatchFLANNDistance (matching.cpp:607-666) on device-resident byte descriptors
+int match_hamming_core(mb2_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int desc_bytes, double matchDistanceThreshold,
+                       double* out, int capacity) {
+  if (nq <= 0 || nt <= 0) return 0;
+  if (desc_bytes < 1 || desc_bytes > 64) { ctx->set_error("hamming match: descriptors of 1..64 bytes"); return MB2_ERR_UNSUPPORTED; }
+  if (nt < 2) { ctx->set_error("hamming match: fewer than 2 trains (knnSearch with knn = 2 is undefined in the reference)"); return MB2_ERR_ARG; }
+  const int W = desc_bytes <= 16 ? 4 : desc_bytes <= 32 ? 8 : 16;
+  const int max_distance = (int)float(matchDistanceThreshold);   // matching.cpp:609
+  const int n_chunks = mb2_nn_hamming_chunks(ctx, nq, nt);
+  MB2_CUDA_CHECK(ctx, ctx->nn_a.reserve((size_t)nq * W * 4));
+  MB2_CUDA_CHECK(ctx, ctx->nn_b.reserve((size_t)nt * W * 4));
+  MB2_CUDA_CHECK(ctx, ctx->nn_c.reserve((size_t)nq * n_chunks * 16 + (size_t)nq * (sizeof(MatchRow) + 4) + 64));
+  uint32_t *qw = ctx->nn_a.as<uint32_t>(), *tw = ctx->nn_b.as<uint32_t>();
+  unsigned long long* part = ctx->nn_c.as<unsigned long long>();
+  MatchRow* rows = (MatchRow*)(part + (size_t)nq * n_chunks * 2);
+  int* accept = (int*)(rows + nq);
+  mb2_nn_hamming_words(ctx, d_q, nq, desc_bytes, W, qw);
+  mb2_nn_hamming_words(ctx, d_t, nt, desc_bytes, W, tw);
+  mb2_nn_hamming(ctx, qw, nq, tw, nt, W, n_chunks, max_distance, part, rows, accept);
+  return compact_rows(ctx, rows, accept, nq, out, capacity);
 }
 
 }  // namespace
@@ -1123,6 +1151,18 @@ int mb2_match_fginn(mb2_ctx* ctx, const uint8_t* q_desc, int nq, const uint8_t* 
   if ((rc = mb2_stage_in(ctx, t_desc, (size_t)nt * 128, ctx->rs_b, &dt))) return rc;
   if ((rc = mb2_stage_in(ctx, t_xy, (size_t)nt * 16, ctx->rs_c, &dxy))) return rc;
   return match_core(ctx, (const uint8_t*)dq, nq, (const uint8_t*)dt, nt, (const double*)dxy, matchRatio, contradDist, nn, out, capacity);
+}
+
+int mb2_match_hamming(mb2_ctx* ctx, const uint8_t* q_desc, int nq, const uint8_t* t_desc, int nt, int desc_bytes, double matchDistanceThreshold,
+                      double* out, int capacity) {
+  if (!ctx || nq < 0 || nt < 0 || !out || desc_bytes <= 0) return MB2_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (nq == 0 || nt == 0) return 0;
+  const void *dq, *dt;
+  int rc;
+  if ((rc = mb2_stage_in(ctx, q_desc, (size_t)nq * desc_bytes, ctx->rs_a, &dq))) return rc;
+  if ((rc = mb2_stage_in(ctx, t_desc, (size_t)nt * desc_bytes, ctx->rs_b, &dt))) return rc;
+  return match_hamming_core(ctx, (const uint8_t*)dq, nq, (const uint8_t*)dt, nt, desc_bytes, matchDistanceThreshold, out, capacity);
 }
 
 int mb2_match_slots(mb2_ctx* ctx, int q_slot, int t_slot, double matchRatio, double contradDist, int nn, double* out, int capacity) {

@@ -17,6 +17,12 @@
 //            closest failer != idx0 (2nd NN) and the closest passer (the neighbour the loop accepts).
 //   accept  <=> no inconsistent failer, #failers <= min(nn, N2) - 1, a passer exists.
 //
+// Epilogue economy (round 2): the streaming loops only keep running MINIMA (one FFMA + half an FMNMX3 per distance); a minimum is
+// recorded with the 32-column block it came from, and the train index inside that block is recovered afterwards for the one winning
+// block per query (k_nn_resolve: 32 dp4a distances per query).  Pass 2 looks at single distances only in blocks that hold a
+// "failer" (d < thr), and a query that can no longer be accepted (an inconsistent failer, or more failers than the k-NN list is
+// long) stops looking altogether.
+//
 // The contraction runs on tcgen05 (UMMA 128x128x16, bf16 -> fp32 in TMEM), operands staged by TMA
 // with 128B swizzle; a SIMT dp4a kernel computes the same per-(query, chunk) partials and is used
 // as the on-GPU cross-check (MB2_NN_IMPL=simt) -- both feed the same merge + finalize kernels.
@@ -108,10 +114,25 @@ struct Pass2Acc {
   }
 };
 
-// Rare path of pass 2, kept out of line so the unrolled streaming loop stays small: replay the
-// failers of one 32-column slab in column order.
-__device__ __noinline__ void pass2_failers(Pass2Acc& a, const uint32_t* vals, unsigned failmask, int col0, int idx0,
-                                           const double* __restrict__ txy, double contr2) {
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+  return r;
+}
+
+// Rare path of pass 2, kept out of line so the streaming loop stays small: one 32-column block that holds at least one failer.
+// vals = the 32 distances (relative: |t|^2 - 2 q.t).  The failers are replayed in column order; the block's closest passer is returned.
+__device__ __noinline__ float pass2_block(Pass2Acc& a, const uint32_t* vals, float thr_rel, int col0, int idx0, const double* __restrict__ txy,
+                                          double contr2) {
+  unsigned failmask = 0;
+  float mp = 3.0e38f;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const float v = __uint_as_float(vals[j]);
+    const bool f = v < thr_rel;
+    failmask |= (unsigned)f << j;
+    mp = fminf(mp, f ? 3.0e38f : v);
+  }
   while (failmask) {
     const int j = __ffs(failmask) - 1;
     failmask &= failmask - 1;
@@ -124,8 +145,11 @@ __device__ __noinline__ void pass2_failers(Pass2Acc& a, const uint32_t* vals, un
       if (dx * dx + dy * dy > contr2) a.incons = 1;   // distanceSq, matching.cpp:174-179
     }
   }
+  return mp;
 }
 
+// keys of best0 / bestP carry (distance, train index) from the SIMT kernel and (distance, first column of the 32-column block) from
+// the tcgen05 kernel; both order equal distances by the lower index, and k_nn_resolve turns either into the exact index.
 __device__ __forceinline__ void merge_pass1(NNState& st, int q, float qn, const Pass1Acc& a) {
   if (a.idx >= 0) atomicMin(&st.best0[q], make_key(a.best + qn, a.idx));
 }
@@ -134,6 +158,33 @@ __device__ __forceinline__ void merge_pass2(NNState& st, int q, float qn, const 
   if (a.incons) atomicOr(&st.incons[q], 1);
   if (a.idx1 >= 0) atomicMin(&st.best1[q], make_key(a.best1 + qn, a.idx1));
   if (a.idxP >= 0) atomicMin(&st.bestP[q], make_key(a.bestP + qn, a.idxP));
+}
+
+// The low word of a key names a 32-column block (index & ~31): find the lowest train index inside it whose distance equals the key's.
+// One warp per query, lane = column of the block; the distance is formed exactly as in the streaming kernels.
+__global__ void __launch_bounds__(256)
+k_nn_resolve(unsigned long long* __restrict__ keys, int nq, const uint8_t* __restrict__ q, const uint8_t* __restrict__ t, int nt,
+             const float* __restrict__ qn, const float* __restrict__ tn) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  const unsigned long long key = keys[qi];
+  if (key == KEY_INIT) return;
+  const float d = __uint_as_float((unsigned)(key >> 32));
+  const int col = (int)((unsigned)key & ~31u) + lane;
+  bool hit = false;
+  if (col < nt) {
+    const uint4* qp = (const uint4*)(q + (size_t)qi * 128);
+    const uint4* tp = (const uint4*)(t + (size_t)col * 128);
+    unsigned dot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint4 a = __ldg(qp + i), b = __ldg(tp + i);
+      dot = __dp4a(a.x, b.x, dot); dot = __dp4a(a.y, b.y, dot); dot = __dp4a(a.z, b.z, dot); dot = __dp4a(a.w, b.w, dot);
+    }
+    hit = __fadd_rn(__fmaf_rn(-2.f, (float)dot, tn[col]), qn[qi]) == d;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0 && m) keys[qi] = ((unsigned long long)(unsigned)(key >> 32) << 32) | (unsigned)(((unsigned)key & ~31u) + __ffs(m) - 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -175,7 +226,10 @@ constexpr int TSTAGES = 2;         // TMEM accumulator ring (2 x 256 columns)
 constexpr int TILE_BYTES = 128 * BK * 2;          // one [128 x 64] bf16 box = 16 KB
 constexpr int A_BYTES = 2 * KBLOCKS * TILE_BYTES; // 64 KB
 constexpr int B_STAGE_BYTES = KBLOCKS * TILE_BYTES;  // 32 KB
-constexpr int NN_THREADS = 32 * 10;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps = one per 32 rows x 128 columns of a tile (pass 1: the double-buffered TMEM loads
+// need the registers), 16 warps = one per 32 rows x 64 columns (pass 2: the rare failer path stalls a warp on dependent loads, more
+// warps hide it).  Measured at 30k x 30k / 60k x 60k: pass 1 0.215 / 0.807 ms with 8 warps (0.234 / 0.912 with 16), pass 2 0.273 /
+// 0.918 ms with 16 (0.299 / 1.055 with 8).
 constexpr int SMEM_BYTES = A_BYTES + STAGES * B_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -249,11 +303,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(NN_THREADS, 1)
+template <int PASS, int EW>
+__global__ void __launch_bounds__(32 * (2 + EW), 1)
 k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, int nq, int nt_pad,
         const float* __restrict__ qn, const float* __restrict__ tn, NNState st, const double* __restrict__ txy, double contr2,
-        int tiles_per_chunk, int n_qblocks, int n_chunks) {
+        int tiles_per_chunk, int n_qblocks, int n_chunks, int kmax) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                          // [half][kblock] 16 KB tiles
@@ -273,7 +327,7 @@ k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUte
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < TSTAGES; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < TSTAGES; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EW); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -291,7 +345,7 @@ k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUte
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int qb = item / n_chunks, ch = item - qb * n_chunks;
+        const int ch = item / n_qblocks, qb = item - ch * n_qblocks;   // chunk-major: the query blocks of one train chunk run side by side
         const int tile0 = ch * tiles_per_chunk, tile1 = min(total_tiles, tile0 + tiles_per_chunk);
         mbar_wait(a_empty, a_phase ^ 1);
         mbar_expect_tx(a_full, A_BYTES);
@@ -313,9 +367,8 @@ k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUte
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, tstage = 0, tphase = 0, a_phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int qb = item / n_chunks, ch = item - qb * n_chunks;
+        const int ch = item / n_qblocks;
         const int tile0 = ch * tiles_per_chunk, tile1 = min(total_tiles, tile0 + tiles_per_chunk);
-        (void)qb;
         mbar_wait(a_full, a_phase);
         a_phase ^= 1;
         for (int tile = tile0; tile < tile1; tile++) {
@@ -341,26 +394,37 @@ k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUte
       }
     }
   } else {
-    // ===== epilogue: warps 2..9; TMEM lane group = warp % 4, query half = (warp - 2) / 4 =====
-    const int lg = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue: warps 2..; TMEM lane group = warp % 4 (a warp only reaches its own 32 TMEM lanes), query half and -- with 16
+    // warps -- column half of the tile from (warp - 2) / 4 =====
+    // A thread owns one query row.  Per 32-column block: 32 FFMA (|t|^2 - 2 q.t) and a tree of FMNMX3 give the block minimum; that
+    // is all pass 1 needs (the winning block is recorded, the index inside it is recovered by k_nn_resolve), and all pass 2 needs
+    // for a block without failers (block minimum >= thr: every column is a passer).  The TMEM load of the next block is in flight
+    // while the current one is reduced.
+    constexpr int CSPLIT = EW / 8, NBLK = BN / 32 / CSPLIT;   // column split of a tile among warps, 32-column blocks per warp
+    const int lg = warp & 3, half = ((warp - 2) >> 2) / CSPLIT, cpart = ((warp - 2) >> 2) % CSPLIT;
     uint32_t tstage = 0, tphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int qb = item / n_chunks, ch = item - qb * n_chunks;
+      const int ch = item / n_qblocks, qb = item - ch * n_qblocks;
       const int tile0 = ch * tiles_per_chunk, tile1 = min(total_tiles, tile0 + tiles_per_chunk);
       const int q = qb * BM + half * 128 + lg * 32 + lane;
       const bool qvalid = q < nq;
       Pass1Acc a1; Pass2Acc a2; a1.init(); a2.init();
-      float thr_rel = 0.f; int idx0 = -1;
-      if (PASS == 2 && qvalid) { thr_rel = st.thr_rel[q]; idx0 = st.idx0[q]; }
+      float thr_rel = -3.0e38f; int idx0 = -1;
+      if (PASS == 2 && qvalid) {
+        // a query that earlier work items already proved unacceptable (inconsistent failer, too many failers) looks at nothing
+        if (__ldcg(&st.incons[q]) == 0 && __ldcg(&st.cnt[q]) <= kmax) { thr_rel = st.thr_rel[q]; idx0 = st.idx0[q]; }
+      }
       for (int tile = tile0; tile < tile1; tile++) {
         mbar_wait(&tfull[tstage], tphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + tstage * 256 + half * 128;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          const int col0 = tile * BN + c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + tstage * 256 + half * 128 + cpart * NBLK * 32;
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
+#pragma unroll
+        for (int c = 0; c < NBLK; c++) {
+          uint32_t* cur = (c & 1) ? rb : ra;
+          uint32_t* nxt = (c & 1) ? ra : rb;
+          const int col0 = tile * BN + (cpart * NBLK + c) * 32;
           float tnv[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -368,25 +432,31 @@ k_nn_tc(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUte
             tnv[j] = t4.x; tnv[j + 1] = t4.y; tnv[j + 2] = t4.z; tnv[j + 3] = t4.w;
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 1 < NBLK) tmem_ld32(taddr + (c + 1) * 32, nxt);
+          float m[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const float v0 = __fmaf_rn(-2.f, __uint_as_float(cur[j + 2 * k]), tnv[j + 2 * k]);
+              const float v1 = __fmaf_rn(-2.f, __uint_as_float(cur[j + 2 * k + 1]), tnv[j + 2 * k + 1]);
+              if (PASS == 2) { cur[j + 2 * k] = __float_as_uint(v0); cur[j + 2 * k + 1] = __float_as_uint(v1); }
+              m[k] = fmin3(m[k], v0, v1);
+            }
+          }
+          const float mn = fminf(fmin3(m[0], m[1], m[2]), m[3]);
           if (PASS == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) a1.add(__fmaf_rn(-2.f, __uint_as_float(r[j]), tnv[j]), col0 + j);
+            if (mn < a1.best) { a1.best = mn; a1.idx = col0; }
           } else {
-            unsigned failmask = 0;
+            float mp = mn;
+            if (mn < thr_rel) {   // the block holds a failer
+              uint32_t tmp[32];   // the out-of-line call takes the block through local memory; only this rare path pays for it
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const float v = __fmaf_rn(-2.f, __uint_as_float(r[j]), tnv[j]);
-              r[j] = __float_as_uint(v);
-              const bool f = v < thr_rel;
-              failmask |= (unsigned)f << j;
-              if (!f && v < a2.bestP) { a2.bestP = v; a2.idxP = col0 + j; }
+              for (int j = 0; j < 32; j++) tmp[j] = cur[j];
+              mp = pass2_block(a2, tmp, thr_rel, col0, idx0, txy, contr2);
+              if (a2.incons | (a2.cnt > kmax)) thr_rel = -3.0e38f;   // cannot be accepted any more
             }
-            if (failmask) {
-              uint32_t tmp[32];
-#pragma unroll
-              for (int j = 0; j < 32; j++) tmp[j] = r[j];
-              pass2_failers(a2, tmp, failmask, col0, idx0, txy, contr2);
-            }
+            if (mp < a2.bestP) { a2.bestP = mp; a2.idxP = col0; }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -469,6 +539,61 @@ k_nn_topk(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, 
   rows[qi] = r; accept[qi] = ok;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hamming 2-NN of binary descriptors (MatchFLANNDistance, matching/matching.cpp:607-666, binary_matcher = linear): one thread per query
+// with the query's words in registers, the trains of the CTA's chunk staged through shared memory (every lane reads the same train
+// word: broadcast), XOR + POPC.  The two smallest (distance << 32 | train index) keys per (query, chunk) go to `part`; keys are
+// unique, so ties resolve to the lower train index.  k_hamming_finish merges the chunks and applies the distance threshold (:653).
+// ---------------------------------------------------------------------------------------------
+#define HM_TILE 128
+template <int W>
+__global__ void __launch_bounds__(128)
+k_hamming_2nn(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ t, int nt, int chunk, unsigned long long* __restrict__ part) {
+  __shared__ uint32_t st[HM_TILE * W];
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t qa[W];
+#pragma unroll
+  for (int i = 0; i < W; i++) qa[i] = qi < nq ? q[(size_t)qi * W + i] : 0u;
+  const int j_lo = blockIdx.y * chunk, j_hi = min(nt, j_lo + chunk);
+  unsigned long long b0 = ~0ull, b1 = ~0ull;
+  for (int j0 = j_lo; j0 < j_hi; j0 += HM_TILE) {
+    const int m = min(HM_TILE, j_hi - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * W; i += blockDim.x) st[i] = t[(size_t)j0 * W + i];
+    __syncthreads();
+    for (int j = 0; j < m; j++) {
+      unsigned d = 0;
+#pragma unroll
+      for (int i = 0; i < W; i++) d += __popc(qa[i] ^ st[j * W + i]);
+      const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)(j0 + j);
+      if (key < b1) { if (key < b0) { b1 = b0; b0 = key; } else b1 = key; }
+    }
+  }
+  if (qi < nq) { part[((size_t)qi * gridDim.y + blockIdx.y) * 2] = b0; part[((size_t)qi * gridDim.y + blockIdx.y) * 2 + 1] = b1; }
+}
+__global__ void k_hamming_finish(const unsigned long long* __restrict__ part, int nq, int n_chunks, int max_distance, MatchRow* __restrict__ rows,
+                                 int* __restrict__ accept) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long b0 = ~0ull, b1 = ~0ull;
+  for (int c = 0; c < 2 * n_chunks; c++) {
+    const unsigned long long key = part[(size_t)qi * n_chunks * 2 + c];
+    if (key < b1) { if (key < b0) { b1 = b0; b0 = key; } else b1 = key; }
+  }
+  MatchRow r; r.q = qi; r.idx0 = (int)(unsigned)b0; r.d0 = (float)(unsigned)(b0 >> 32);
+  r.idxJ = r.idx1 = (int)(unsigned)b1; r.dJ = r.d1 = (float)(unsigned)(b1 >> 32); r.pad = 0;
+  rows[qi] = r; accept[qi] = (int)(unsigned)(b0 >> 32) <= max_distance;
+}
+// rows of `bytes` bytes -> rows of W zero-padded 32-bit words (equal padding adds nothing to a bit count)
+__global__ void k_hamming_words(const uint8_t* __restrict__ src, int n, int bytes, int W, uint32_t* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * W) return;
+  const size_t r = i / W; const int w = (int)(i - r * W);
+  uint32_t v = 0;
+  for (int b = 0; b < 4; b++) { const int e = w * 4 + b; if (e < bytes) v |= (uint32_t)src[r * bytes + e] << (8 * b); }
+  dst[i] = v;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -511,6 +636,30 @@ void mb2_nn_topk(mb2_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int n
                  int nn, MatchRow* rows, int* accept) {
   MB2_LAUNCH(ctx, k_nn_topk, (nq + 127) / 128, 128, 0, q, nq, t, nt, qn, tn, txy, contr2, nn, rows, accept);
 }
+void mb2_nn_hamming_words(mb2_ctx* ctx, const uint8_t* src, int n, int bytes, int W, uint32_t* dst) {
+  const size_t total = (size_t)n * W;
+  if (total) MB2_LAUNCH(ctx, k_hamming_words, (unsigned)((total + 255) / 256), 256, 0, src, n, bytes, W, dst);
+}
+int mb2_nn_hamming_chunks(mb2_ctx* ctx, int nq, int nt) {
+  // enough CTAs to fill the SMs a few times over; a chunk is a whole number of shared-memory tiles
+  const int qblocks = (nq + 127) / 128;
+  int n_chunks = (4 * ctx->num_sms + qblocks - 1) / qblocks;
+  const int max_chunks = (nt + HM_TILE - 1) / HM_TILE;
+  if (n_chunks > max_chunks) n_chunks = max_chunks;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > 4096) n_chunks = 4096;
+  return n_chunks;
+}
+void mb2_nn_hamming(mb2_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int W, int n_chunks, int max_distance,
+                    unsigned long long* part, MatchRow* rows, int* accept) {
+  int chunk = (nt + n_chunks - 1) / n_chunks;
+  chunk = (chunk + HM_TILE - 1) / HM_TILE * HM_TILE;
+  dim3 grid((nq + 127) / 128, n_chunks);
+  if (W == 4) MB2_LAUNCH(ctx, k_hamming_2nn<4>, grid, 128, 0, q, nq, t, nt, chunk, part);
+  else if (W == 8) MB2_LAUNCH(ctx, k_hamming_2nn<8>, grid, 128, 0, q, nq, t, nt, chunk, part);
+  else MB2_LAUNCH(ctx, k_hamming_2nn<16>, grid, 128, 0, q, nq, t, nt, chunk, part);
+  MB2_LAUNCH(ctx, k_hamming_finish, (nq + 255) / 256, 256, 0, part, nq, n_chunks, max_distance, rows, accept);
+}
 void mb2_nn_finalize(mb2_ctx* ctx, const NNState& st, int nq, int nt, int nn, MatchRow* rows, int* accept) {
   MB2_LAUNCH(ctx, k_finalize, (nq + 255) / 256, 256, 0, st, nq, nt, nn, rows, accept);
 }
@@ -521,8 +670,11 @@ void mb2_nn_pass_simt(mb2_ctx* ctx, int pass, const uint8_t* q, int nq, const ui
   if (pass == 1) MB2_LAUNCH(ctx, k_nn_simt<1>, grid, 128, 0, q, nq, t, nt, qn, tn, st, txy, contr2, chunk);
   else MB2_LAUNCH(ctx, k_nn_simt<2>, grid, 128, 0, q, nq, t, nt, qn, tn, st, txy, contr2, chunk);
 }
+void mb2_nn_resolve(mb2_ctx* ctx, unsigned long long* keys, int nq, const uint8_t* q, const uint8_t* t, int nt, const float* qn, const float* tn) {
+  if (nq > 0) MB2_LAUNCH(ctx, k_nn_resolve, (nq + 7) / 8, 256, 0, keys, nq, q, t, nt, qn, tn);
+}
 int mb2_nn_pass_tc(mb2_ctx* ctx, int pass, const void* q_bf16, int nq, int nq_pad, const void* t_bf16, int nt_pad, const float* qn,
-                   const float* tn, const NNState& st, const double* txy, double contr2) {
+                   const float* tn, const NNState& st, const double* txy, double contr2, int kmax) {
   CUtensorMap mq, mt;
   int rc = make_tmap(ctx, &mq, q_bf16, nq_pad);
   if (rc) return rc;
@@ -539,14 +691,16 @@ int mb2_nn_pass_tc(mb2_ctx* ctx, int pass, const void* q_bf16, int nq, int nq_pa
   const int grid = n_items < ctx->num_sms ? n_items : ctx->num_sms;
   static unsigned long long attr_devs = 0;
   if (mb2_first_use_on_device(&attr_devs, ctx->device)) {
-    cudaFuncSetAttribute(k_nn_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(k_nn_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_nn_tc<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_nn_tc<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_nn_tc<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(k_nn_tc<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   }
-  if (pass == 1)
-    MB2_LAUNCH(ctx, k_nn_tc<1>, grid, NN_THREADS, SMEM_BYTES, mq, mt, nq, nt_pad, qn, tn, st, txy, contr2, tiles_per_chunk, n_qblocks,
-               n_chunks);
-  else
-    MB2_LAUNCH(ctx, k_nn_tc<2>, grid, NN_THREADS, SMEM_BYTES, mq, mt, nq, nt_pad, qn, tn, st, txy, contr2, tiles_per_chunk, n_qblocks,
-               n_chunks);
+  const char* ew_env = std::getenv("MB2_NN_EPI_WARPS");   // A/B switch for measurements
+  const int ew = ew_env ? std::atoi(ew_env) : (pass == 1 ? 8 : 16);
+#define MB2_NN_GO(P, E) MB2_LAUNCH(ctx, (k_nn_tc<P, E>), grid, 32 * (2 + E), SMEM_BYTES, mq, mt, nq, nt_pad, qn, tn, st, txy, contr2, tiles_per_chunk, n_qblocks, n_chunks, kmax)
+  if (ew == 8) { if (pass == 1) MB2_NN_GO(1, 8); else MB2_NN_GO(2, 8); }
+  else { if (pass == 1) MB2_NN_GO(1, 16); else MB2_NN_GO(2, 16); }
+#undef MB2_NN_GO
   return MB2_OK;
 }

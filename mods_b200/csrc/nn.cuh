@@ -22,4 +22,11 @@ void mb2_nn_topk(mb2_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int n
 void mb2_nn_pass_simt(mb2_ctx* ctx, int pass, const uint8_t* q, int nq, const uint8_t* t, int nt, const float* qn, const float* tn,
                       const NNState& st, const double* txy, double contr2);
 int mb2_nn_pass_tc(mb2_ctx* ctx, int pass, const void* q_bf16, int nq, int nq_pad, const void* t_bf16, int nt_pad, const float* qn,
-                   const float* tn, const NNState& st, const double* txy, double contr2);
+                   const float* tn, const NNState& st, const double* txy, double contr2, int kmax);   // kmax = min(nn, nt) - 1 failers at most
+// low word of every key: 32-column block (or any index inside it) -> exact lowest train index with the key's distance
+void mb2_nn_resolve(mb2_ctx* ctx, unsigned long long* keys, int nq, const uint8_t* q, const uint8_t* t, int nt, const float* qn, const float* tn);
+// Hamming 2-NN of binary descriptors (MatchFLANNDistance, matching.cpp:607-666): descriptors as rows of W (4 / 8 / 16) 32-bit words
+void mb2_nn_hamming_words(mb2_ctx* ctx, const uint8_t* src, int n, int bytes, int W, uint32_t* dst);
+int mb2_nn_hamming_chunks(mb2_ctx* ctx, int nq, int nt);
+void mb2_nn_hamming(mb2_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int W, int n_chunks, int max_distance,
+                    unsigned long long* part, MatchRow* rows, int* accept);

@@ -339,6 +339,31 @@ int MatchFlannFGINN(mb2_ctx* ctx, const AffineRegionList& list1, const AffineReg
   return n;
 }
 
+// matching/matching.cpp:607-666.  Binary descriptors: entries floored to bytes (:631-632), exact Hamming 2-NN on the device,
+// kept when d1 <= (int)(float)matchDistanceThreshold; ratio = d1 / d2 in double (:659), no square root here.
+int MatchFLANNDistance(mb2_ctx* ctx, const AffineRegionList& list1, const AffineRegionList& list2, TentativeCorrespListExt& corresp,
+                       const MatchPars& par, const int /*nn*/) {
+  if (list1.empty() || list2.empty()) return 0;
+  const size_t dim = list1[0].desc.vec.size();
+  std::vector<uint8_t> q(list1.size() * dim), t(list2.size() * dim);
+  for (size_t i = 0; i < list1.size(); i++) for (size_t j = 0; j < dim; j++) q[i * dim + j] = (uint8_t)std::floor(list1[i].desc.vec[j]);
+  for (size_t i = 0; i < list2.size(); i++) for (size_t j = 0; j < dim; j++) t[i * dim + j] = (uint8_t)std::floor(list2[i].desc.vec[j]);
+  std::vector<double> rows(list1.size() * 7);
+  const int n = mb2_match_hamming(ctx, q.data(), (int)list1.size(), t.data(), (int)list2.size(), (int)dim, par.matchDistanceThreshold, rows.data(),
+                                  (int)list1.size());
+  corresp.TCList.clear();
+  if (n < 0) return 0;
+  corresp.TCList.resize(n);
+  for (int i = 0; i < n; i++) {
+    const double* r = rows.data() + (size_t)i * 7;
+    TentativeCorrespExt& c = corresp.TCList[i];
+    c.first = list1[(int)r[0]]; c.second = list2[(int)r[1]];
+    c.d1 = r[4]; c.d2 = r[5];
+    c.ratio = (double)c.d1 / (double)c.d2;
+  }
+  return n;
+}
+
 int CorrespondenceBank::GetCorrespondencesNumber(std::string desc_name, std::string det_name) const {
   int n = 0;
   for (auto& d : CorrespondencesMapMap) {

@@ -5,6 +5,7 @@
 //   ImageRepresentation::SynthDetectDescribeKeypoints   imagerepresentation.h:44-47, .cpp:603-2047
 //   CorrespondenceBank::MatchImgReps                    correspondencebank.h:29-31, .cpp:237-351
 //   MatchFlannFGINN                                     matching/matching.hpp:268-269, .cpp:357-461
+//   MatchFLANNDistance                                  matching/matching.hpp:273, .cpp:607-666
 //   DuplicateFiltering                                  matching/matching.hpp:300, .cpp:2983-3047
 //   LORANSACFiltering (+ NaiveHCheck, H_LAF_check)      matching/matching.hpp:284-286, .cpp:806-980, 1171-1200, 251-309
 //
@@ -193,6 +194,8 @@ class CorrespondenceBank {
 
 int MatchFlannFGINN(mb2_ctx* ctx, const AffineRegionList& list1, const AffineRegionList& list2, TentativeCorrespListExt& corresp,
                     const MatchPars& par, const int nn = 50);
+int MatchFLANNDistance(mb2_ctx* ctx, const AffineRegionList& list1, const AffineRegionList& list2, TentativeCorrespListExt& corresp,
+                       const MatchPars& par, const int nn = 50);   // matching.hpp:273, .cpp:607-666 (binary descriptors, Hamming 2-NN)
 void DuplicateFiltering(TentativeCorrespListExt& in_corresp, const double r = 3.0, const int mode = MODE_RANDOM);
 int LORANSACFiltering(mb2_ctx* ctx, TentativeCorrespListExt& in_corresp, TentativeCorrespListExt& out_corresp, double* H,
                       const RANSACPars pars);

@@ -310,4 +310,14 @@ int orc_match_fginn(const float* q, int nq, const float* t, int nt, const double
   return (int)m.size();
 }
 
+// out rows of 6 doubles: q idx0 idx1 d0 d1 ratio
+int orc_match_hamming(const float* q, int nq, const float* t, int nt, int dim, double matchDistanceThreshold, double* out, int max_out) {
+  std::vector<HammingTentative> m = matchHamming(q, nq, t, nt, dim, matchDistanceThreshold);
+  for (size_t i = 0; i < m.size() && (int)i < max_out; i++) {
+    double* o = out + i * 6;
+    o[0] = m[i].q; o[1] = m[i].i0; o[2] = m[i].i1; o[3] = m[i].d0; o[4] = m[i].d1; o[5] = m[i].ratio;
+  }
+  return (int)m.size();
+}
+
 }  // extern "C"

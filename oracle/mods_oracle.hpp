@@ -1025,6 +1025,41 @@ inline std::vector<Tentative> matchFGINN(const float* q, int nq, const float* t,
 }
 
 // ------------------------------------------------------------------------------------------
+// matching/matching.cpp:607-666  MatchFLANNDistance with binary_matcher = linear (exact 2-NN), binary_dist = Hamming.
+// Descriptor entries are floored to bytes (:631-632, :638-639); distance = number of differing bits (cvflann::Hamming, int);
+// a query is kept when its first distance is <= (int)(float)matchDistanceThreshold (:609, :653); ratio = d1 / d2 in double (:659,
+// inf / nan for d2 = 0 as in the reference).  Ties between equal distances: lower train index first (FLANN's order is unpinned).
+// Fewer than 2 trains is undefined in the reference (knnSearch with knn = 2): returns nothing here.
+// ------------------------------------------------------------------------------------------
+struct HammingTentative { int q, i0, i1; int d0, d1; double ratio; };
+
+inline std::vector<HammingTentative> matchHamming(const float* q, int nq, const float* t, int nt, int dim, double matchDistanceThreshold) {
+  std::vector<HammingTentative> out;
+  if (nq == 0 || nt < 2) return out;
+  const int max_distance = (int)float(matchDistanceThreshold);
+  std::vector<unsigned char> q8((size_t)nq * dim), t8((size_t)nt * dim);
+  for (size_t i = 0; i < q8.size(); i++) q8[i] = (unsigned char)std::floor(q[i]);
+  for (size_t i = 0; i < t8.size(); i++) t8[i] = (unsigned char)std::floor(t[i]);
+  std::vector<HammingTentative> per_q(nq);
+  std::vector<char> has(nq, 0);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int i = 0; i < nq; i++) {
+    const unsigned char* a = q8.data() + (size_t)i * dim;
+    int b0 = -1, b1 = -1, d0 = 1 << 30, d1 = 1 << 30;
+    for (int j = 0; j < nt; j++) {
+      const unsigned char* b = t8.data() + (size_t)j * dim;
+      int s = 0;
+      for (int e = 0; e < dim; e++) s += __builtin_popcount((unsigned)(a[e] ^ b[e]));
+      if (s < d0) { d1 = d0; b1 = b0; d0 = s; b0 = j; }
+      else if (s < d1) { d1 = s; b1 = j; }
+    }
+    if (d0 <= max_distance) { per_q[i] = {i, b0, b1, d0, d1, (double)d0 / (double)d1}; has[i] = 1; }
+  }
+  for (int i = 0; i < nq; i++) if (has[i]) out.push_back(per_q[i]);
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------
 // degensac: scorers (closed form, f64)
 // ------------------------------------------------------------------------------------------
 // Htools.c:17-55 lin_hg + :132-196 pinvJ/HDs, fused: lin is never materialised.

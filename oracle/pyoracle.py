@@ -196,6 +196,14 @@ class Oracle(Lib):
                                    C.c_int(nn), _p(out), C.c_int(len(out)))
         return out[:n].copy()
 
+    def match_hamming(self, q, t, max_distance=64.0):
+        """MatchFLANNDistance (matching.cpp:607) restated: rows q idx0 idx1 d0 d1 ratio."""
+        q = _f32(q); t = _f32(t)
+        out = np.zeros((max(1, len(q)), 6))
+        n = self.fn("match_hamming")(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), C.c_int(q.shape[1]), C.c_double(max_distance), _p(out),
+                                     C.c_int(len(out)))
+        return out[:n].copy()
+
     def resize_half(self, img):
         img = _f32(img)
         oh, ow = int(np.rint(img.shape[0] * 0.5)), int(np.rint(img.shape[1] * 0.5))
@@ -259,6 +267,14 @@ class Reference(Lib):
         out = np.zeros((max(1, len(q)), 7))
         n = self.fn("match_fginn")(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), _p(t_kps), C.c_double(ratio), C.c_double(contradDist),
                                    C.c_int(nn), _p(out), C.c_int(len(out)))
+        return out[:n].copy()
+
+    def match_hamming(self, q, t, max_distance=64.0):
+        """MatchFLANNDistance (matching.cpp:607), Hamming 2-NN.  Rows: q second.id d1 d2 ratio."""
+        q = _f32(q); t = _f32(t)
+        out = np.zeros((max(1, len(q)), 5))
+        n = self.fn("match_hamming")(_p(q), C.c_int(len(q)), _p(t), C.c_int(len(t)), C.c_int(q.shape[1]), C.c_double(max_distance), _p(out),
+                                     C.c_int(len(out)))
         return out[:n].copy()
 
     def duplicate_filter(self, frames14, ratio, r=2.0, mode=1):

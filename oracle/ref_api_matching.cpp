@@ -87,6 +87,26 @@ int ref_match_fginn(const float* q, int nq, const float* t, int nt, const double
   return n;
 }
 
+// MatchFLANNDistance (matching.cpp:607-666) on plain arrays: 2-NN of binary descriptors in Hamming distance, a query is kept when its
+// first distance is <= (int)(float)matchDistanceThreshold.  Descriptors arrive as floats (AffineRegion::desc.vec) and are floored to
+// bytes by the reference itself.  out rows (5 doubles): query, second.id, d1, d2, ratio.
+int ref_match_hamming(const float* q, int nq, const float* t, int nt, int dim, double matchDistanceThreshold, double* out, int max_out) {
+  std::vector<double> qk((size_t)nq * KP, 0.0), tk((size_t)nt * KP, 0.0);
+  AffineRegionList l1 = regions_in(qk.data(), q, nq, dim), l2 = regions_in(tk.data(), t, nt, dim);
+  MatchPars p;
+  p.matchDistanceThreshold = matchDistanceThreshold;
+  p.binary_matcher = cvflann::FLANN_INDEX_LINEAR; p.binary_dist = cvflann::FLANN_DIST_HAMMING;
+  TentativeCorrespListExt tents;
+  MatchFLANNDistance(l1, l2, tents, p, 2);
+  const int n = (int)tents.TCList.size();
+  for (int i = 0; i < n && i < max_out; i++) {
+    const TentativeCorrespExt& c = tents.TCList[i];
+    double* o = out + (size_t)i * 5;
+    o[0] = c.first.id; o[1] = c.second.id; o[2] = c.d1; o[3] = c.d2; o[4] = c.ratio;
+  }
+  return n;
+}
+
 // DuplicateFiltering (matching.cpp:2983): kept_idx receives the surviving rows in the reference's output order.
 int ref_duplicate_filter(const double* frames14, const double* ratio, int n, double r, int mode, int* kept_idx) {
   TentativeCorrespListExt L = tentatives_in(frames14, ratio, n);

@@ -4,6 +4,7 @@
 // distances are ordered by the lower train index (FLANN's tie order is unspecified).  Descriptor entries are integers
 // 0..255 held in floats, so the float sum cvflann::L2<float> forms is an exact integer < 2^24 in any order: it is evaluated in
 // 32-bit integer arithmetic (vectorisable) when that holds, in float otherwise.  Queries run on all OpenMP threads.
+// Binary descriptors (u8 rows, FLANN_DIST_HAMMING; MatchFLANNDistance): exact linear k-NN on the bit count, int distances.
 #ifndef MB2_ORACLE_SHIM_FLANN_HPP
 #define MB2_ORACLE_SHIM_FLANN_HPP
 #include "../core/core.hpp"
@@ -22,13 +23,37 @@ class Index {
  public:
   Mat feats;
   Index() {}
+  bool hamming = false;
   Index(const Mat& features, const IndexParams&, cvflann::flann_distance_t d = cvflann::FLANN_DIST_L2) : feats(features) {
-    if (d != cvflann::FLANN_DIST_L2 || features.depth() != CV_32F) shim_unsupported("flann::Index other than float L2");
+    hamming = d == cvflann::FLANN_DIST_HAMMING && features.depth() == CV_8U;   // binary descriptors (MatchFLANNDistance, matching.cpp:607)
+    if (!hamming && (d != cvflann::FLANN_DIST_L2 || features.depth() != CV_32F)) shim_unsupported("flann::Index other than float L2 / u8 Hamming");
   }
   void release() { feats = Mat(); }
   void knnSearch(const Mat& queries, Mat& indices, Mat& dists, int knn, const SearchParams& = SearchParams()) {
     const int nq = queries.rows, nt = feats.rows, D = feats.cols;
     if (nt < knn) shim_unsupported("flann knnSearch with fewer trains than neighbours (undefined in the reference)");
+    if (hamming) {   // cvflann::Hamming: number of differing bits, int distances (CV_32S); exact linear scan, lower train index first
+      if (queries.depth() != CV_8U || queries.cols != D) shim_unsupported("Hamming knnSearch query type");
+      indices = Mat(nq, knn, CV_32S); dists = Mat(nq, knn, CV_32S);
+#pragma omp parallel
+      {
+        std::vector<std::pair<int, int> > d(nt);
+#pragma omp for schedule(dynamic, 16)
+        for (int i = 0; i < nq; i++) {
+          const unsigned char* a = queries.ptr<unsigned char>(i);
+          for (int j = 0; j < nt; j++) {
+            const unsigned char* b = feats.ptr<unsigned char>(j);
+            int s = 0;
+            for (int e = 0; e < D; e++) s += __builtin_popcount((unsigned)(a[e] ^ b[e]));
+            d[j] = std::make_pair(s, j);
+          }
+          std::partial_sort(d.begin(), d.begin() + knn, d.end());
+          int* ir = indices.ptr<int>(i); int* dr = dists.ptr<int>(i);
+          for (int j = 0; j < knn; j++) { ir[j] = d[j].second; dr[j] = d[j].first; }
+        }
+      }
+      return;
+    }
     indices = Mat(nq, knn, CV_32S); dists = Mat(nq, knn, CV_32F);
     bool integral = true;
     for (int i = 0; i < nq && integral; i++) { const float* r = queries.ptr<float>(i); for (int e = 0; e < D; e++) if (!(r[e] >= 0 && r[e] <= 255 && r[e] == (float)(int)r[e])) { integral = false; break; } }

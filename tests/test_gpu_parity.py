@@ -551,3 +551,42 @@ def test_mods_pairs_pipeline_equals_single_calls(ctx):
             assert getattr(r1, f) == getattr(r2, f), f
         assert r1.verified >= 8 and np.array_equal(v1, v2) and np.array_equal(np.array(r1.H[:]), np.array(r2.H[:]))
     assert ctx.mods_pairs([], cfg)[0] == []
+
+
+# ---- Hamming matcher (MatchFLANNDistance, matching.cpp:607-666) --------------------------------------------------------
+def _hamming_rows(o):
+    """oracle rows (q idx0 idx1 d0 d1 ratio) in the C ABI's 7-column layout (q idx0 idx1 idx1 d0 d1 d1)"""
+    return o[:, [0, 1, 2, 2, 3, 4, 4]]
+
+
+def test_hamming_matcher_golden_and_oracle(ctx, oracle):
+    """Bit-exact against the compiled reference's golden vectors (descriptor lengths 16 / 20 / 32 / 64 bytes, duplicates among the
+    trains, only two trains, thresholds 64 / 30.5 / 0) and against the oracle on fresh, larger inputs."""
+    import sys
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hamming_vectors.npz"))
+    for name in sorted(k[2:] for k in G.files if k.startswith("q_")):
+        q, t = G["q_" + name], G["t_" + name]
+        for th in (64.0, 30.5, 0.0):
+            want = G["rows_%s_%g" % (name, th)]            # q second.id d1 d2 ratio
+            got = ctx.match_hamming(q, t, th)
+            assert np.array_equal(got[:, [0, 1, 4, 5]], want[:, :4]), (name, th)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                assert np.array_equal(got[:, 4] / got[:, 5], want[:, 4], equal_nan=True)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_hamming import case
+    for nq, nt, nb, th in ((5000, 7000, 32, 64.0), (3000, 20000, 64, 150.0), (129, 513, 7, 9.0), (20000, 300, 32, 80.0)):
+        q, t = case(nq, nt, nb, seed=nq)
+        g = ctx.match_hamming(q, t, th)
+        o = oracle.match_hamming(q.astype(np.float32), t.astype(np.float32), th)
+        assert len(o) > 0 and np.array_equal(g, _hamming_rows(o)), (nq, nt, nb)
+
+
+def test_hamming_matcher_edges(ctx):
+    q = np.zeros((4, 32), np.uint8); t = np.zeros((3, 32), np.uint8)
+    assert len(ctx.match_hamming(q[:0], t)) == 0 and len(ctx.match_hamming(q, t[:0])) == 0
+    with pytest.raises(mb.Mb2Error):
+        ctx.match_hamming(q, t[:1])                         # knnSearch with knn = 2 on one train: undefined in the reference, refused
+    with pytest.raises(mb.Mb2Error):
+        ctx.match_hamming(np.zeros((4, 65), np.uint8), np.zeros((3, 65), np.uint8))
+    r = ctx.match_hamming(q, t, 0.0)                        # all equal: distance 0, first two trains in index order
+    assert np.array_equal(r[:, 1], np.zeros(4)) and np.array_equal(r[:, 2], np.ones(4)) and not r[:, 4:].any()

@@ -114,3 +114,17 @@ def test_dspsift_matches_reference(oracle):
     assert len(GD["keys"]) > 100
     assert np.array_equal(oracle.describe_dsp(im, GD["keys"]).astype(np.uint8), GD["desc_default"])
     assert np.array_equal(oracle.describe_dsp(im, GD["keys"], numScales=5, startCoef=0.7, endCoef=1.3, photoNorm=False).astype(np.uint8), GD["desc_5_07_13_nophoto"])
+
+
+def test_hamming_matcher_golden(oracle):
+    """MatchFLANNDistance (matching.cpp:607-666): the oracle reproduces the compiled reference's tentatives on the committed vectors
+    (tests/golden/make_golden_hamming.py): descriptor lengths 16 / 20 / 32 / 64 bytes, duplicates among the trains, two trains only."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hamming_vectors.npz"))
+    names = sorted(k[2:] for k in G.files if k.startswith("q_"))
+    assert len(names) == 5
+    for name in names:
+        q, t = G["q_" + name].astype(np.float32), G["t_" + name].astype(np.float32)
+        for th in (64.0, 30.5, 0.0):
+            want = G["rows_%s_%g" % (name, th)]
+            got = oracle.match_hamming(q, t, th)
+            assert np.array_equal(got[:, [0, 1, 3, 4, 5]], want, equal_nan=True), (name, th)

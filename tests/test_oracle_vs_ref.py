@@ -1,5 +1,8 @@
 """Restatement vs the reference compiled in place, on fresh inputs (only where oracle/_ref exists:
 the build container, and the GPU box through the prebuilt .so)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -251,3 +254,15 @@ def test_dspsift_oracle_vs_reference(oracle, reference, scales, start, end, phot
     a = oracle.describe_dsp(im, k, numScales=scales, startCoef=start, endCoef=end, photoNorm=photo)
     b = reference.describe_dsp(im, k, numScales=scales, startCoef=start, endCoef=end, photoNorm=photo)
     assert len(k) > 100 and np.array_equal(a, b) and a.max() <= 255
+
+
+@pytest.mark.parametrize("nq,nt,nbytes,th", [(500, 700, 32, 64.0), (300, 200, 64, 200.0), (250, 300, 16, 20.9), (100, 2, 32, 300.0), (120, 150, 20, 0.0)])
+def test_hamming_port_equals_matching_cpp(oracle, reference, nq, nt, nbytes, th):
+    """The oracle's Hamming 2-NN == MatchFLANNDistance (matching.cpp:607-666) of the compiled reference: every tentative (query, train, d1, d2,
+    ratio incl. 0 / 0)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_hamming import case
+    q, t = case(nq, nt, nbytes, seed=nq + nt)
+    a = oracle.match_hamming(q.astype(np.float32) + 0.5, t.astype(np.float32) + 0.25, th)     # fractional entries: floored by both
+    b = reference.match_hamming(q.astype(np.float32) + 0.5, t.astype(np.float32) + 0.25, th)
+    assert len(b) > 0 and np.array_equal(a[:, [0, 1, 3, 4, 5]], b, equal_nan=True)
