@@ -41,6 +41,11 @@ int upload_lut(mb2_ctx* ctx) {
   double lut[256];
   mb2host::build_atan_lut(lut);
   MB2_CUDA_CHECK(ctx, cudaMemcpyToSymbol(c_atan_lut, lut, sizeof lut));
+  static float sift_o[mb2host::ATAN_CODES];
+  static unsigned char ori_bin[mb2host::ATAN_CODES];
+  mb2host::build_atan_derived(lut, sift_o, ori_bin);
+  MB2_CUDA_CHECK(ctx, cudaMemcpyToSymbol(g_atan_sift_o, sift_o, sizeof sift_o));
+  MB2_CUDA_CHECK(ctx, cudaMemcpyToSymbol(g_atan_ori_bin, ori_bin, sizeof ori_bin));
   if (ctx->device < 64) g_lut_uploaded[ctx->device] = true;
   return MB2_OK;
 }

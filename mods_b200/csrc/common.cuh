@@ -131,6 +131,9 @@ struct ImgView {
 // The library is built as ONE translation unit (mods_b200.cu includes every kernel file), so this
 // is the single definition.
 __constant__ double c_atan_lut[256];
+// what the hot kernels derive from atan2LUTff's result alone, per (branch, table index): host_tables.hpp build_atan_derived
+__device__ float g_atan_sift_o[2049];
+__device__ unsigned char g_atan_ori_bin[2049];
 
 // detectors/helpers.cpp:160-207.  The eight branches of the reference differ only in which of |x|, |y| is the
 // numerator and in the final affine map of the table value, so the table is read ONCE (index from the same
@@ -150,6 +153,16 @@ __device__ __forceinline__ float atan2LUTff_dev(float y, float x, const double* 
   if (big) return (float)d_add(-PId, t);
   if (x == 0.f) return 0.f;
   return (float)d_sub(-PI_2d, t);
+}
+
+// (branch, table index) of atan2LUTff for (y, x): same index arithmetic and branch conditions as atan2LUTff_dev above
+__device__ __forceinline__ int atan2LUT_code(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool big = ax > ay;
+  const float num = big ? ay : ax, den = big ? ax : ay;
+  const int idx = (int)(fdiv(fmul(255.f, num), den));
+  if (!(x > 0.f) && !(y > 0.f) && !big && x == 0.f) return 2048;
+  return (((x > 0.f) ? 4 : 0) | ((y > 0.f) ? 2 : 0) | (big ? 1 : 0)) * 256 + idx;
 }
 
 // detectors/helpers.cpp:524-549

@@ -526,33 +526,54 @@ k_extract_needed(ImgView img, const KeyOut* __restrict__ kps, const unsigned lon
 // pixels in raster order.  Float addition is not associative, so the sums stay serial, but 32 regions
 // are summed side by side by one warp: lane = region, the patches are staged through shared memory in
 // coalesced 32-pixel slabs (padded rows: conflict-free columns).
-constexpr int PN_T = 32, PN_SLAB = 32;
+// The slabs arrive through a ring of cp.async groups three slabs ahead of the sums (one warp per CTA cannot hide a DRAM round trip per
+// slab otherwise: 320 us per 31k regions before, bound by exposed latency at 10 % occupancy).
+constexpr int PN_T = 32, PN_SLAB = 32, PN_RING = 4, PN_NSLAB = (NPIX + PN_SLAB - 1) / PN_SLAB;
 __global__ void __launch_bounds__(PN_T)
 k_photonorm_stats(const float* __restrict__ patches, int n, const DescTables* __restrict__ tab, float2* __restrict__ stats) {
-  __shared__ float s_tile[PN_T][PN_SLAB + 1];
-  __shared__ float s_mask[NPIX];
+  __shared__ float s_tile[PN_RING][PN_T][PN_SLAB + 1];
+  __shared__ unsigned s_mbits[PN_NSLAB];   // bit k of word j: pixel 32 j + k is inside the mask
   const int lane = threadIdx.x;
   const int r0 = blockIdx.x * PN_T;
-  for (int p = lane; p < NPIX; p += PN_T) s_mask[p] = tab->mask[p];
-  float sum = 0.f, gsum = 0.f, var = 0.f;
-  for (int pass = 0; pass < 2; pass++) {
-    for (int p0 = 0; p0 < NPIX; p0 += PN_SLAB) {
-      __syncwarp();
-      const int p = p0 + lane;
+  int inside = 0;
+  for (int j = 0; j < PN_NSLAB; j++) {
+    const int p = j * PN_SLAB + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, p < NPIX && tab->mask[p] > 0);
+    if (lane == 0) s_mbits[j] = m;
+    inside += __popc(m);
+  }
+  const float gsum = (float)inside;   // the reference adds 1.f per masked pixel: exact integers
+  auto issue = [&](int s) {           // slab s of the two passes (pass 1 re-reads the patches) into ring slot s % PN_RING
+    if (s < 2 * PN_NSLAB) {
+      const int p = min((s % PN_NSLAB) * PN_SLAB + lane, NPIX - 1);   // clamped: the surplus columns of the last slab are never summed
+      float* dst = &s_tile[s % PN_RING][0][lane];
 #pragma unroll 8
       for (int rr = 0; rr < PN_T; rr++) {
-        const int region = r0 + rr;
-        s_tile[rr][lane] = (region < n && p < NPIX) ? patches[(size_t)region * NPIX + p] : 0.f;
-      }
-      __syncwarp();
-      const int lim = min(PN_SLAB, NPIX - p0);
-      if (pass == 0) {
-        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { sum = fadd(sum, s_tile[lane][k]); gsum = fadd(gsum, 1.f); }
-      } else {
-        for (int k = 0; k < lim; k++) if (s_mask[p0 + k] > 0) { const float d = fsub(sum, s_tile[lane][k]); var = fadd(var, fmul(d, d)); }
+        const int region = min(r0 + rr, n - 1);
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + rr * (PN_SLAB + 1));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(patches + (size_t)region * NPIX + p) : "memory");
       }
     }
-    if (pass == 0) sum = fdiv(sum, gsum);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int s = 0; s < PN_RING - 1; s++) issue(s);
+  float sum = 0.f, var = 0.f;
+  for (int s = 0; s < 2 * PN_NSLAB; s++) {
+    issue(s + PN_RING - 1);   // into the slot consumed in the previous iteration
+    asm volatile("cp.async.wait_group %0;" ::"n"(PN_RING - 1) : "memory");
+    __syncwarp();
+    const int j = s % PN_NSLAB;
+    const unsigned mb = s_mbits[j];
+    const float* mine = s_tile[s % PN_RING][lane];
+    if (s < PN_NSLAB) {
+#pragma unroll
+      for (int k = 0; k < PN_SLAB; k++) if ((mb >> k) & 1u) sum = fadd(sum, mine[k]);
+      if (s == PN_NSLAB - 1) sum = fdiv(sum, gsum);
+    } else {
+#pragma unroll
+      for (int k = 0; k < PN_SLAB; k++) if ((mb >> k) & 1u) { const float d = fsub(sum, mine[k]); var = fadd(var, fmul(d, d)); }
+    }
+    __syncwarp();
   }
   var = sqrtf(fdiv(var, gsum));
   if (r0 + lane < n) stats[r0 + lane] = make_float2(sum, var);
@@ -565,10 +586,8 @@ __global__ void __launch_bounds__(DT)
 k_sift_grad(float* __restrict__ patches, int n, DescribeParams dp, const DescTables* __restrict__ tab,
             const float2* __restrict__ stats, float2* __restrict__ rec) {
   __shared__ float s_patch[NPIX];
-  __shared__ double s_lut[256];
   const int kidx = blockIdx.x, tid = threadIdx.x;
   if (kidx >= n) return;
-  for (int i = tid; i < 256; i += DT) s_lut[i] = c_atan_lut[i];
   float* gp = patches + (size_t)kidx * NPIX;
   bool normalise = false;
   float sum = 0.f, fac = 0.f;
@@ -599,9 +618,9 @@ k_sift_grad(float* __restrict__ patches, int n, DescribeParams dp, const DescTab
     else if (r == PS - 1) yg = fsub(s_patch[p], s_patch[p - PS]);
     else yg = fsub(s_patch[p + PS], s_patch[p - PS]);
     const float grad = sqrtf(fadd(fmul(xg, xg), fmul(yg, yg)));
-    const float ori = atan2LUTff_dev(yg, xg, s_lut);
-    const double M_PI_DOUBLED = 6.28318530718;
-    const float o = (float)(8.0 * ((double)ori + M_PI_DOUBLED) / M_PI_DOUBLED);
+    // o = (float)(8.0 * ((double)atan2LUTff(yg, xg) + 2 pi) / (2 pi)): a function of the LUT branch and index alone, tabulated on the
+    // host with exactly that expression (host_tables.hpp) -- no double arithmetic per pixel
+    const float o = __ldg(&g_atan_sift_o[atan2LUT_code(yg, xg)]);
     out[p] = make_float2(fmul(tab->mask[p], grad), o);
   }
 }
@@ -615,26 +634,26 @@ k_sift_grad(float* __restrict__ patches, int n, DescribeParams dp, const DescTab
 constexpr int VW = 4;  // warps (regions) per CTA
 __global__ void __launch_bounds__(VW * 32)
 k_sift_votes(const float2* __restrict__ rec, int n, const DescTables* __restrict__ tab, double* __restrict__ vecT /* [128][n] */) {
-  __shared__ double s_acc[VW][32][9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kidx = blockIdx.x * VW + warp;
   if (kidx >= n) return;
   const int rb = lane >> 3, cb = (lane >> 1) & 3, h = lane & 1;
-  double* acc = s_acc[warp][lane];
+  // the lane's 8 orientation accumulators in shared memory, bin-major: s_acc[b][lane] puts the 32 lanes of a warp on distinct
+  // banks whatever their bins (a 64-bit access of a full warp is then the minimal 2 wavefronts; the lane-major layout used before
+  // cost 4+ and made the kernel shared-memory bound).  The two votes of a pixel go to different bins (bo1 = bo0 + 1 mod 8), so both
+  // are loaded before either is stored: one dependent shared-memory round trip per pixel instead of two.
+  __shared__ double s_acc[VW][8][32];
+  double* acc = &s_acc[warp][0][lane];
 #pragma unroll
-  for (int b = 0; b < 8; b++) acc[b] = 0.0;
+  for (int b = 0; b < 8; b++) acc[b * 32] = 0.0;
   const float2* R = rec + (size_t)kidx * NPIX;
   const int c_lo = 8 * cb + 8 * h;
   float wcol[8];
 #pragma unroll
   for (int t = 0; t < 8; t++) {
-    const int c = c_lo + t;
-    float w = 0.f;
-    if (c < PS) {
-      if (h == 0) { if (tab->bin1[c] == cb * 8) w = tab->w1[c]; }
-      else { if (tab->bin0[c] == cb * 8) w = tab->w0[c]; }
-    }
-    wcol[t] = w;
+    const int c = min(c_lo + t, PS - 1);
+    const float w = h == 0 ? (tab->bin1[c] == cb * 8 ? tab->w1[c] : 0.f) : (tab->bin0[c] == cb * 8 ? tab->w0[c] : 0.f);
+    wcol[t] = c_lo + t < PS ? w : 0.f;
   }
   for (int tr = 0; tr < 16; tr++) {
     const int r = 8 * rb + tr;
@@ -654,15 +673,16 @@ k_sift_votes(const float2* __restrict__ rec, int n, const DescTables* __restrict
         const int io = (int)px.y;
         const float wo1 = fsub(px.y, (float)io);
         const int bo0 = io & 7, bo1 = (bo0 + 1) & 7;   // io >= 0: io % 8 == io & 7
-        acc[bo0] += (double)fmul(val, fsub(1.0f, wo1));
-        acc[bo1] += (double)fmul(val, wo1);
+        const double a0 = acc[bo0 * 32], a1 = acc[bo1 * 32];
+        acc[bo0 * 32] = a0 + (double)fmul(val, fsub(1.0f, wo1));
+        acc[bo1 * 32] = a1 + (double)fmul(val, wo1);
       }
     }
   }
   __syncwarp();
   // lanes (rb, cb, 0) and (rb, cb, 1) are neighbours: h = 0 segment first (lower columns), as in a raster walk
   for (int b = lane & 1 ? 4 : 0, e = b + 4; b < e; b++) {
-    const double v = s_acc[warp][lane & ~1][b] + s_acc[warp][lane | 1][b];
+    const double v = s_acc[warp][b][lane & ~1] + s_acc[warp][b][lane | 1];
     vecT[(size_t)((rb * 4 + cb) * 8 + b) * n + kidx] = v;
   }
 }

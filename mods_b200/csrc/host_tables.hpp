@@ -19,6 +19,37 @@ inline void build_atan_lut(double* v) {
   v[32] = 0.1248376255; v[83] = 0.3146752558; v[100] = 0.3737268255;
 }
 
+// atan2LUTff (detectors/helpers.cpp:160-207) has 8 branches x 256 table values + the x == 0 corner: its result, and everything
+// the hot kernels compute from that result alone, is a function of (branch, table index).  Built here with the very expressions the
+// kernels used to evaluate per pixel (IEEE double / float on the host, no contraction):
+//   sift_o[code]   = (float)(8.0 * ((double)ori + M_PI_DOUBLED) / M_PI_DOUBLED)          siftdesc.cpp:99-107 (orientation bin coordinate)
+//   ori_bin[code]  = (int)(36.f * (ori / PIf + 1.f) * 0.5f)                              synth-detection.cpp:786 (36-bin histogram)
+// code = branch * 256 + index; branch = (x > 0) * 4 + (y > 0) * 2 + (|x| > |y|); code 2048 = the x == 0 corner (ori = 0).
+constexpr int ATAN_CODES = 2049;
+inline float atan_branch_value(int branch, double t) {
+  const double PI_2d = (double)1.57079632679489661923f, PId = (double)3.14159265358979323846f;
+  switch (branch) {
+    case 7: return (float)t;             // x > 0, y > 0, big
+    case 6: return (float)(PI_2d - t);   // x > 0, y > 0
+    case 5: return (float)(-t);          // x > 0, y <= 0, big
+    case 4: return (float)(-PI_2d + t);  // x > 0, y <= 0
+    case 3: return (float)(PId - t);     // x <= 0, y > 0, big
+    case 2: return (float)(PI_2d + t);   // x <= 0, y > 0
+    case 1: return (float)(-PId + t);    // x <= 0, y <= 0, big
+    default: return (float)(-PI_2d - t); // x < 0, y <= 0
+  }
+}
+inline void build_atan_derived(const double* lut, float* sift_o, unsigned char* ori_bin) {
+  const double M_PI_DOUBLED = 6.28318530718;
+  const float PIf = 3.14159265358979323846f;
+  for (int code = 0; code < ATAN_CODES; code++) {
+    const float ori = code == 2048 ? 0.f : atan_branch_value(code >> 8, lut[code & 255]);
+    sift_o[code] = (float)(8.0 * ((double)ori + M_PI_DOUBLED) / M_PI_DOUBLED);
+    volatile float a = ori / PIf; volatile float b = a + 1.0f; volatile float c = 36.f * b; volatile float d = c * 0.5f;
+    ori_bin[code] = (unsigned char)(int)d;
+  }
+}
+
 // computeGaussMask, detectors/helpers.cpp:411-440
 inline void gauss_mask(float* mask, int size) {
   int halfSize = size >> 1;

@@ -33,11 +33,8 @@ extern __shared__ unsigned char s_ori_raw[];
 __global__ void __launch_bounds__(OW * 32)
 k_orientation(ImgView img, const KeyOut* __restrict__ in, int n, OrientParams op, const float* __restrict__ orimask,
               KeyOut* __restrict__ out, int* __restrict__ out_count) {
-  double* s_lut = reinterpret_cast<double*>(s_ori_raw);
-  OriWarp* s_w = reinterpret_cast<OriWarp*>(s_ori_raw + 256 * sizeof(double));
+  OriWarp* s_w = reinterpret_cast<OriWarp*>(s_ori_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 256; i += OW * 32) s_lut[i] = c_atan_lut[i];
-  __syncthreads();
   const int kidx = blockIdx.x * OW + warp;
   if (kidx >= n) return;
   const KeyOut k = in[kidx];
@@ -85,8 +82,9 @@ k_orientation(ImgView img, const KeyOut* __restrict__ in, int n, OrientParams op
       const float mag = sqrtf(fadd(fmul(xg, xg), fmul(yg, yg)));
       const float m = orimask[p];
       if (m > 0 && (double)mag > 1.0) {
-        const float ori = atan2LUTff_dev(yg, xg, s_lut);
-        b = (int)fmul(fmul(36.f, fadd(fdiv(ori, PIf), 1.0f)), 0.5f);  // x / 2.0f == x * 0.5f exactly; 36 (ori == +pi): a slot the reference never reads
+        // bin = (int)(36 (atan2LUTff(yg, xg) / pi + 1) / 2): a function of the LUT branch and index alone, tabulated on the host with
+        // that float expression (host_tables.hpp); 36 (ori == +pi) is a slot the reference never reads
+        b = g_atan_ori_bin[atan2LUT_code(yg, xg)];
         w = fmul(mag, m);
       }
     }
@@ -250,7 +248,7 @@ using namespace MB2_NS;
 void mb2_launch_orientation(mb2_ctx* ctx, const ImgView& img, const KeyOut* in, int n, const OrientParams& op,
                             const float* d_orimask, KeyOut* out, int* out_count_per_kp) {
   if (!n) return;
-  const size_t smem = 256 * sizeof(double) + OW * sizeof(OriWarp);
+  const size_t smem = OW * sizeof(OriWarp);
   static unsigned long long attr_devs = 0;
   if (mb2_first_use_on_device(&attr_devs, ctx->device)) cudaFuncSetAttribute(k_orientation, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   MB2_LAUNCH(ctx, k_orientation, (n + OW - 1) / OW, OW * 32, smem, img, in, n, op, d_orimask, out, out_count_per_kp);
