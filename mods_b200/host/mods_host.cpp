@@ -4,6 +4,9 @@
 // post-RANSAC checks.
 #include "mods_host.hpp"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -461,15 +464,29 @@ std::vector<int> duplicate_filter_core(const double* xy_in, const double* key, i
   for (int j = 0; j < T; j++) std::memcpy(&xy[4 * (size_t)j], xy_in + 4 * (size_t)order[j], 4 * sizeof(double));
   const double r_sq = r * r;
   // Two phases instead of one hash probe per tentative (random memory accesses: 260 ms for the 419k tentatives of the C4 workload).
-  // (1) Spatial join, cell by cell: the tentatives are bucketed by the grid cell (cell = r) of their first-image point; for every
+  // (1) Spatial join, cell by cell: the tentatives are bucketed by the grid cell (cell >= r) of their first-image point; for every
   //     tentative the EARLIER ones (in processing order) that lie within r in both images are listed -- contiguous buckets, independent
   //     per tentative, so the loop runs on all host threads.
   // (2) The reference's greedy rule in processing order over those short lists: j is dropped iff one of its listed predecessors is kept.
   // The close-pair relation and the order are the reference's, so the kept set is identical.
+  // Cell size: any cell >= r keeps every close pair inside a 3 x 3 neighbourhood.  Cells of exactly r make a dense grid of millions
+  // of cells for a 4096 x 3072 image (building and scanning it cost 6 of the 6.8 ms this step took for 30k tentatives), so the cell
+  // grows until there are about as many cells as tentatives; the distance tests below are unchanged, so is the kept set.
+  double cell = r;
+  {
+    double lox = 0, hix = 0, loy = 0, hiy = 0;
+    for (int j = 0; j < T; j++) {
+      const double x = xy[4 * (size_t)j], y = xy[4 * (size_t)j + 1];
+      if (j == 0) { lox = hix = x; loy = hiy = y; }
+      lox = std::min(lox, x); hix = std::max(hix, x); loy = std::min(loy, y); hiy = std::max(hiy, y);
+    }
+    const double area = (hix - lox + r) * (hiy - loy + r);
+    if (T > 0 && area > 0 && std::isfinite(area)) cell = std::max(r, std::sqrt(area / (double)T));
+  }
   std::vector<long long> cx(T), cy(T);
   long long minx = 0, miny = 0, maxx = 0, maxy = 0;
   for (int j = 0; j < T; j++) {
-    cx[j] = (long long)std::floor(xy[4 * (size_t)j] / r); cy[j] = (long long)std::floor(xy[4 * (size_t)j + 1] / r);
+    cx[j] = (long long)std::floor(xy[4 * (size_t)j] / cell); cy[j] = (long long)std::floor(xy[4 * (size_t)j + 1] / cell);
     if (j == 0) { minx = maxx = cx[j]; miny = maxy = cy[j]; }
     minx = std::min(minx, cx[j]); maxx = std::max(maxx, cx[j]); miny = std::min(miny, cy[j]); maxy = std::max(maxy, cy[j]);
   }
@@ -481,39 +498,59 @@ std::vector<int> duplicate_filter_core(const double* xy_in, const double* key, i
     for (int j = 0; j < T; j++) cell_start[(size_t)((cy[j] - miny) * gw + (cx[j] - minx)) + 1]++;
     for (size_t c = 0; c < (size_t)(gw * gh); c++) cell_start[c + 1] += cell_start[c];
     { std::vector<int> cur(cell_start.begin(), cell_start.end() - 1); for (int j = 0; j < T; j++) by_cell[cur[(size_t)((cy[j] - miny) * gw + (cx[j] - minx))]++] = j; }   // ascending j inside a cell
-    std::vector<int> pred_off(T + 1, 0);
-    std::vector<int> npred(T, 0);
-    std::vector<int> preds;                       // CSR, filled in a second sweep
-    for (int pass = 0; pass < 2; pass++) {
-      if (pass == 1) { for (int j = 0; j < T; j++) pred_off[j + 1] = pred_off[j] + npred[j]; preds.resize(pred_off[T]); }
-#pragma omp parallel for schedule(dynamic, 1024) if (T > 20000)
-      for (int j = 0; j < T; j++) {
-        const double x1 = xy[4 * (size_t)j], y1 = xy[4 * (size_t)j + 1], x2 = xy[4 * (size_t)j + 2], y2 = xy[4 * (size_t)j + 3];
-        int n = 0;
-        for (long long dy = -1; dy <= 1; dy++) {
-          const long long yy = cy[j] - miny + dy;
-          if (yy < 0 || yy >= gh) continue;
-          for (long long dx = -1; dx <= 1; dx++) {
-            const long long xx = cx[j] - minx + dx;
-            if (xx < 0 || xx >= gw) continue;
-            const size_t c = (size_t)(yy * gw + xx);
-            for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
-              const int i = by_cell[k];
-              if (i >= j) break;                   // ascending inside the cell: only earlier tentatives can drop j
-              double ddx = xy[4 * (size_t)i] - x1, ddy = xy[4 * (size_t)i + 1] - y1;
-              if (ddx * ddx + ddy * ddy > r_sq) continue;
-              ddx = xy[4 * (size_t)i + 2] - x2; ddy = xy[4 * (size_t)i + 3] - y2;
-              if (ddx * ddx + ddy * ddy <= r_sq) { if (pass == 1) preds[pred_off[j] + n] = i; n++; }
+    // coordinates gathered in bucket order: the join then reads contiguous memory (in processing order every candidate was a cache
+    // miss: 8 of the 12 ms this function took for 30k tentatives on one core)
+    std::vector<double> xyc((size_t)T * 4);
+    for (int k = 0; k < T; k++) std::memcpy(&xyc[4 * (size_t)k], &xy[4 * (size_t)by_cell[k]], 4 * sizeof(double));
+    // one sweep over the cells (grid rows dealt out to the host threads); the predecessors of a tentative go to the sweeping thread's
+    // own list, remembered per tentative as (thread, offset, count)
+    int n_thr = 1;
+#ifdef _OPENMP
+    if (T > 20000) n_thr = std::max(1, omp_get_max_threads());
+#endif
+    std::vector<std::vector<int> > preds(n_thr);
+    std::vector<int> pred_off(T, 0), npred(T, 0);
+    std::vector<unsigned short> pred_thr(T, 0);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_thr) if (n_thr > 1)
+    for (long long gy = 0; gy < gh; gy++) {
+#ifdef _OPENMP
+      const int me = n_thr > 1 ? omp_get_thread_num() : 0;
+#else
+      const int me = 0;
+#endif
+      std::vector<int>& mine = preds[me];
+      for (long long gx = 0; gx < gw; gx++) {
+        const size_t c0 = (size_t)(gy * gw + gx);
+        for (int kj = cell_start[c0]; kj < cell_start[c0 + 1]; kj++) {
+          const int j = by_cell[kj];
+          const double x1 = xyc[4 * (size_t)kj], y1 = xyc[4 * (size_t)kj + 1], x2 = xyc[4 * (size_t)kj + 2], y2 = xyc[4 * (size_t)kj + 3];
+          const size_t first = mine.size();
+          for (long long dy = -1; dy <= 1; dy++) {
+            const long long yy = gy + dy;
+            if (yy < 0 || yy >= gh) continue;
+            for (long long dx = -1; dx <= 1; dx++) {
+              const long long xx = gx + dx;
+              if (xx < 0 || xx >= gw) continue;
+              const size_t c = (size_t)(yy * gw + xx);
+              for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
+                const int i = by_cell[k];
+                if (i >= j) break;                   // ascending inside the cell: only earlier tentatives can drop j
+                double ddx = xyc[4 * (size_t)k] - x1, ddy = xyc[4 * (size_t)k + 1] - y1;
+                if (ddx * ddx + ddy * ddy > r_sq) continue;
+                ddx = xyc[4 * (size_t)k + 2] - x2; ddy = xyc[4 * (size_t)k + 3] - y2;
+                if (ddx * ddx + ddy * ddy <= r_sq) mine.push_back(i);
+              }
             }
           }
+          pred_off[j] = (int)first; npred[j] = (int)(mine.size() - first); pred_thr[j] = (unsigned short)me;
         }
-        npred[j] = n;
       }
     }
     std::vector<char> is_kept(T, 0);
     for (int j = 0; j < T; j++) {
       bool dup = false;
-      for (int k = pred_off[j]; k < pred_off[j + 1] && !dup; k++) dup = is_kept[preds[k]] != 0;
+      const int* pl = npred[j] ? preds[pred_thr[j]].data() + pred_off[j] : nullptr;
+      for (int k = 0; k < npred[j] && !dup; k++) dup = is_kept[pl[k]] != 0;
       if (!dup) { is_kept[j] = 1; kept.push_back(order[j]); }
     }
     return kept;
