@@ -273,6 +273,8 @@ def run_ours_c4(args, rank, world, local_rank):
     dev = (torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda())
     pin = (torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory())
 
+    step_ms = []   # host clock around every call (diagnostics: warm-up, resident-image steps, host-image steps, profiled step)
+
     def timed(imgs, steps):
         torch.cuda.synchronize()
         if world > 1:
@@ -281,7 +283,11 @@ def run_ours_c4(args, rank, world, local_rank):
         l0 = ctx.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        out = [ctx.views_sharded_pair(imgs[0], imgs[1], cfg, comm, rank, world, shape1=(h, w), shape2=(h, w), capacity=1 << 18) for _ in range(steps)]
+        out = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            out.append(ctx.views_sharded_pair(imgs[0], imgs[1], cfg, comm, rank, world, shape1=(h, w), shape2=(h, w), capacity=1 << 18))
+            step_ms.append(round((time.perf_counter() - t0) * 1e3, 1))
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -325,7 +331,7 @@ def run_ours_c4(args, rank, world, local_rank):
                       "processing time first), ONE ncclAllGather of device-resident region records + count / tentative exchanges; verification on rank 0",
                       "l2": "176 view pipelines per step, working set far beyond the 126 MB L2",
                       "digest": ["%016x" % d for d in dig], "digest_identical_on_all_ranks": all(d == dig for d in digs),
-                      "allgather_bytes_per_rank": st["allgather_bytes_per_rank"], "rank0_ms": {k: st[k] for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")}},
+                      "allgather_bytes_per_rank": st["allgather_bytes_per_rank"], "step_ms_rank0": step_ms, "steps_rank0_ms": [[round(o[3][k], 1) for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")] for o in out_dev + out_e2e], "rank0_ms": {k: st[k] for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")}},
            "matched_kpts_per_s": res.verified * v,
            "e2e": {"value": e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * w * h * 4, "d2h_bytes_per_step": int(res.tentatives * 56 + (res.regions1 + res.regions2) * 184 + res.verified * 32),
                    "ms_per_step": ms_e2e / K, "entry": "mb2_views_sharded_pair (libmods_host.so), pinned host images on every rank, verified list on the host"},

@@ -241,6 +241,7 @@ int mb2_view_fetch(mb2_ctx* ctx, double* det_kp, double* reproj_kp, uint8_t* des
 /* measured FP64 FMA throughput of the device (TFLOP/s, a DFMA micro-kernel): the denominator of the scorer's roofline in bench.py */
 int mb2_debug_fp64_peak(mb2_ctx* ctx, double* tflops);
 int mb2_ctx_make_current(mb2_ctx* ctx);   /* cudaSetDevice(device of ctx) on the calling thread */
+int mb2_is_device_pointer(const void* p);   /* 1: device (or managed) memory, 0: host */
 void* mb2_dev_alloc(mb2_ctx* ctx, size_t bytes);
 void mb2_dev_free(mb2_ctx* ctx, void* p);
 int mb2_dev_copy(mb2_ctx* ctx, void* dst, const void* src, size_t bytes, int kind);

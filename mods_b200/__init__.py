@@ -19,7 +19,7 @@ EXPORTS = [
     "mb2_hessaff_detect", "mb2_detect_orientation", "mb2_describe_sift", "mb2_detect_describe_view", "mb2_view_fetch",
     "mb2_match_fginn", "mb2_match_hamming", "mb2_match_slots", "mb2_score_models", "mb2_ransac_h", "mb2_ransac_f", "mb2_debug_pyramid_level", "mb2_ctx_profile_begin", "mb2_ctx_profile_end", "mb2_ctx_device", "mb2_ctx_profiling", "mb2_slot_move",
     "mb2_mser_detect", "mb2_mser_regions", "mb2_detect_describe_view_mser", "mb2_mser_detect_pair", "mb2_describe_view_of_pair", "mb2_synth_view", "mb2_detect_describe_synth_view", "mb2_ctx_tree_epoch", "mb2_ctx_wait_tree", "mb2_ctx_create_prio",
-    "mb2_view_pack", "mb2_slot_from_records", "mb2_match_slots_range", "mb2_dev_alloc", "mb2_dev_free", "mb2_dev_copy", "mb2_ctx_make_current", "mb2_debug_fp64_peak", "mb2_records_gather_frames", "mb2_records_checksum",
+    "mb2_view_pack", "mb2_slot_from_records", "mb2_match_slots_range", "mb2_is_device_pointer", "mb2_dev_alloc", "mb2_dev_free", "mb2_dev_copy", "mb2_ctx_make_current", "mb2_debug_fp64_peak", "mb2_records_gather_frames", "mb2_records_checksum",
 ]
 
 

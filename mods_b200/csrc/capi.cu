@@ -241,8 +241,14 @@ int ensure_taps(mb2_ctx* ctx, int max_m, int patchSize, TapTable* out) {
 }
 
 // ---- staging -------------------------------------------------------------------------------
-int stage_image(mb2_ctx* ctx, const float* pixels, int w, int h, ImgView* view) {
+// alias_ok: the caller only READS the image during this call -- a device-resident image whose rows are already at the plane pitch is
+// used where it lies (no 50 MB copy per synthesised view)
+int stage_image(mb2_ctx* ctx, const float* pixels, int w, int h, ImgView* view, bool alias_ok = false) {
   const int pitch = pitch_of(w);
+  if (alias_ok && pitch == w && ((uintptr_t)pixels & 127) == 0 && mb2_is_device_ptr(pixels)) {
+    view->p = pixels; view->rows = h; view->cols = w; view->pitch = pitch;
+    return MB2_OK;
+  }
   MB2_CUDA_CHECK(ctx, ctx->img.reserve((size_t)pitch * h * 4));
   cudaMemcpyKind kind = mb2_is_device_ptr(pixels) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   MB2_CUDA_CHECK(ctx, cudaMemcpy2DAsync(ctx->img.p, (size_t)pitch * 4, pixels, (size_t)w * 4, (size_t)w * 4, h, kind, ctx->stream));
@@ -1055,7 +1061,7 @@ int mb2_detect_describe_synth_view(mb2_ctx* ctx, const float* pixels, int w, int
   int rc, n = 0;
   double H[9];
   ctx->last_view_n = 0;
-  if ((rc = stage_image(ctx, pixels, w, h, &img))) return rc;
+  if ((rc = stage_image(ctx, pixels, w, h, &img, true))) return rc;
   if ((rc = mb2_synth_core(ctx, img, *view, &v, H)) < 0) return rc;
   const double tilt = std::fabs(view->tilt), zoom = view->zoom;   // SynthImage::tilt / zoom as DetectAffineRegions passes them on
   if (detector == 0) { if ((rc = detect_core(ctx, v, *hess, tilt, zoom, 1, &n))) return rc; }
@@ -1299,6 +1305,7 @@ void* mb2_dev_alloc(mb2_ctx* ctx, size_t bytes) {
   return p;
 }
 void mb2_dev_free(mb2_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+int mb2_is_device_pointer(const void* p) { return p && mb2_is_device_ptr(p) ? 1 : 0; }
 int mb2_dev_copy(mb2_ctx* ctx, void* dst, const void* src, size_t bytes, int kind) {
   if (!ctx || kind < 0 || kind > 2 || (bytes && (!dst || !src))) return MB2_ERR_ARG;
   cudaSetDevice(ctx->device);

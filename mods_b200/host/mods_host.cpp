@@ -822,6 +822,9 @@ mb2_ctx* sibling_ctx(mb2_ctx* ctx, int which = 0) {
 }
 }  // namespace
 
+// helper context `which` of a primary context (same device, its own stream); created on first use, released by mb2_mods_release
+extern "C" mb2_ctx* mb2_mods_sibling(mb2_ctx* ctx, int which) { return (ctx && which >= 0 && which < 6) ? sibling_ctx(ctx, which) : nullptr; }
+
 extern "C" long long mb2_mods_launch_count(mb2_ctx* ctx) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
   long long n = mb2_ctx_launch_count(ctx);
@@ -830,7 +833,9 @@ extern "C" long long mb2_mods_launch_count(mb2_ctx* ctx) {
     for (mb2_ctx* c : it->second.c) if (c) n += mb2_ctx_launch_count(c);
   return n;
 }
+extern "C" void mb2_sharded_release(mb2_ctx* ctx);   // mods_sharded.cpp: the view-sharded driver's device scratch of this context
 extern "C" void mb2_mods_release(mb2_ctx* ctx) {
+  mb2_sharded_release(ctx);
   std::lock_guard<std::mutex> lk(g_sib_mutex);
   auto it = g_siblings.find(ctx);
   if (it == g_siblings.end()) return;

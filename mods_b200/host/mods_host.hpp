@@ -285,6 +285,8 @@ int mb2_host_set_vs_pars(const double* scales, int n_scales, const double* tilts
                          double* out, int capacity);
 /* kernels launched by ctx and by the helper contexts mb2_mods_pair(s) keep (second image, verification) */
 long long mb2_mods_launch_count(mb2_ctx* ctx);
+/* helper context `which` (0..5) of ctx: same device, its own stream; created on first use, released by mb2_mods_release */
+mb2_ctx* mb2_mods_sibling(mb2_ctx* ctx, int which);
 /* destroys the helper context of ctx (call before mb2_ctx_destroy(ctx)) */
 void mb2_mods_release(mb2_ctx* ctx);
 }

@@ -14,11 +14,15 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -58,7 +62,28 @@ struct DBuf {   // device scratch of one call (through the C ABI: the host libra
   ~DBuf() { if (p) mb2_dev_free(ctx, p); }
 };
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Device scratch of mb2_views_sharded_pair, kept per primary context between calls (grow-only): a call moves ~1 GB through these
+// buffers at C4, and cudaMalloc / cudaFree of that much memory cost up to several hundred ms per call when they were per-call objects.
+struct ShardScratch { DBuf send, recv, d_counts, ordered[4], d_rows, d_img[2], wbuf[4]; };
+std::mutex g_scratch_mutex;
+std::unordered_map<mb2_ctx*, ShardScratch*> g_scratch;
+ShardScratch* scratch_of(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_scratch_mutex);
+  ShardScratch*& s = g_scratch[ctx];
+  if (!s) s = new ShardScratch();
+  return s;
+}
 }  // namespace
+
+// called by mb2_mods_release (before the helper contexts go away: worker buffers belong to them)
+extern "C" void mb2_sharded_release(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_scratch_mutex);
+  auto it = g_scratch.find(ctx);
+  if (it == g_scratch.end()) return;
+  delete it->second;
+  g_scratch.erase(it);
+}
 
 extern "C" {
 
@@ -139,31 +164,89 @@ int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const 
   std::vector<int> owner(U), counts(U, 0);
   mb2_shard_assign(costs.data(), U, world, owner.data());
 
-  // ---- my views: records appended to the send buffer (grown by doubling; capacity in records)
+  // ---- my views.  A view pipeline alone leaves the GPU idle between its kernels (host legs, count read-backs: 35 % of the 693 ms the
+  // 176 views of C4 took one after the other on one GPU), so the units of this rank are run by several host threads, each on its
+  // own context (stream) of the device, longest view first; every worker packs its regions into its own device buffer, and the send
+  // buffer is assembled from them in ascending unit order -- the layout mb2_shard_layout describes -- by device-to-device copies.
   const int REC = MB2_REGION_RECORD_BYTES;
-  DBuf send, recv, d_counts, ordered[4], d_rows;
-  for (DBuf* b : {&send, &recv, &d_counts, &ordered[0], &ordered[1], &ordered[2], &ordered[3], &d_rows}) b->ctx = ctx;
-  size_t send_cap = (size_t)std::max(w1 * h1, w2 * h2) / 16 + 65536, used = 0;
-  if (!send.reserve(send_cap * REC)) return MB2_ERR_CUDA;
-  int my_units = 0;
-  for (int u = 0; u < U; u++) {
-    if (owner[u] != rank) continue;
-    my_units++;
-    const Unit& un = units[u];
-    const int n = mb2_detect_describe_synth_view(ctx, un.image ? img2 : img1, un.image ? w2 : w1, un.image ? h2 : h1, &un.vp, un.det == 0 ? 0 : 3, &cfg->det,
-                                                 &cfg->mser, &cfg->ori, &cfg->desc, MB2_MAX_SLOTS - 1, 0, nullptr, nullptr, nullptr, 0);
-    if (n < 0) return n;
-    if (used + (size_t)n > send_cap) {   // grow, keeping what is already packed
-      size_t ncap = std::max(send_cap * 2, used + (size_t)n);
-      void* np_ = mb2_dev_alloc(ctx, ncap * REC + 256);
-      if (!np_) return MB2_ERR_CUDA;
-      mb2_dev_copy(ctx, np_, send.p, used * REC, 2);
-      mb2_ctx_sync(ctx);
-      mb2_dev_free(ctx, send.p); send.p = np_; send.cap = ncap * REC + 256; send_cap = ncap;
+  ShardScratch& S = *scratch_of(ctx);
+  DBuf &send = S.send, &recv = S.recv, &d_counts = S.d_counts, &d_rows = S.d_rows;
+  DBuf* ordered = S.ordered; DBuf* d_img = S.d_img;
+  for (DBuf* b : {&send, &recv, &d_counts, &ordered[0], &ordered[1], &ordered[2], &ordered[3], &d_rows, &d_img[0], &d_img[1]}) b->ctx = ctx;
+  // host images go to the device once (every view call would stage its own copy otherwise)
+  const float* dimg[2] = {img1, img2};
+  for (int im = 0; im < 2; im++) {
+    const float* src = im ? img2 : img1;
+    if (mb2_is_device_pointer(src)) continue;
+    const size_t bytes = (size_t)(im ? w2 : w1) * (im ? h2 : h1) * 4;
+    if (!d_img[im].reserve(bytes)) return MB2_ERR_CUDA;
+    mb2_dev_copy(ctx, d_img[im].p, src, bytes, 0);
+    dimg[im] = (const float*)d_img[im].p;
+  }
+  if (mb2_ctx_sync(ctx) != MB2_OK) return MB2_ERR_CUDA;
+  std::vector<int> mine;
+  for (int u = 0; u < U; u++) if (owner[u] == rank) mine.push_back(u);
+  const int my_units = (int)mine.size();
+  std::stable_sort(mine.begin(), mine.end(), [&](int a, int b) { return costs[a] > costs[b]; });
+  int n_workers = world >= 4 ? 2 : 4;   // host threads are the limit when 8 ranks share one node's cores
+  if (const char* e = getenv("MB2_VIEW_WORKERS")) n_workers = std::max(1, std::min(4, atoi(e)));
+  if (mb2_ctx_profiling(ctx)) n_workers = 1;   // per-kernel profiling keeps everything on one stream
+  n_workers = std::max(1, std::min(n_workers, my_units));
+  struct Worker { mb2_ctx* c = nullptr; DBuf* bufp = nullptr; size_t cap = 0, used = 0; int rc = MB2_OK; };
+  std::vector<Worker> workers(n_workers);
+  for (int wk = 0; wk < n_workers; wk++) {
+    workers[wk].c = wk == 0 ? ctx : mb2_mods_sibling(ctx, wk - 1);
+    if (!workers[wk].c) { n_workers = wk; break; }
+    workers[wk].bufp = &S.wbuf[wk];
+    workers[wk].bufp->ctx = workers[wk].c;
+  }
+  workers.resize(n_workers);
+  std::vector<int> unit_worker(U, -1);
+  std::vector<size_t> unit_off(U, 0);
+  auto run = [&](int wk) {
+    Worker& W = workers[wk];
+    DBuf& buf = *W.bufp;
+    if (!buf.reserve(((size_t)std::max(w1 * h1, w2 * h2) / 16 + 65536) * REC)) { W.rc = MB2_ERR_CUDA; return; }
+    W.cap = (buf.cap - 256) / REC;
+    // static deal of the cost-sorted units (worker wk takes every n_workers-th): the same worker meets the same views in every call,
+    // so its context's buffers stop growing after the first call
+    for (int i = wk; i < my_units; i += n_workers) {
+      const int u = mine[i];
+      const Unit& un = units[u];
+      const int n = mb2_detect_describe_synth_view(W.c, dimg[un.image], un.image ? w2 : w1, un.image ? h2 : h1, &un.vp, un.det == 0 ? 0 : 3, &cfg->det,
+                                                   &cfg->mser, &cfg->ori, &cfg->desc, MB2_MAX_SLOTS - 1, 0, nullptr, nullptr, nullptr, 0);
+      if (n < 0) { W.rc = n; break; }
+      if (W.used + (size_t)n > W.cap) {   // grow, keeping what is already packed
+        const size_t ncap = std::max(W.cap * 2, W.used + (size_t)n);
+        void* np_ = mb2_dev_alloc(W.c, ncap * REC + 256);
+        if (!np_) { W.rc = MB2_ERR_CUDA; break; }
+        mb2_dev_copy(W.c, np_, buf.p, W.used * REC, 2);
+        mb2_ctx_sync(W.c);
+        mb2_dev_free(W.c, buf.p); buf.p = np_; buf.cap = ncap * REC + 256; W.cap = ncap;
+      }
+      const int k = mb2_view_pack(W.c, (unsigned char*)buf.p + W.used * REC, (int)(W.cap - W.used));
+      if (k < 0) { W.rc = k; break; }
+      counts[u] = k; unit_worker[u] = wk; unit_off[u] = W.used; W.used += (size_t)k;
     }
-    const int k = mb2_view_pack(ctx, (unsigned char*)send.p + used * REC, (int)(send_cap - used));
-    if (k < 0) return k;
-    counts[u] = k; used += (size_t)k;
+    if (mb2_ctx_sync(W.c) != MB2_OK && W.rc >= 0) W.rc = MB2_ERR_CUDA;
+  };
+  {
+    std::vector<std::thread> th;
+    for (int wk = 1; wk < n_workers; wk++) th.emplace_back(run, wk);
+    run(0);
+    for (auto& t : th) t.join();
+  }
+  size_t used = 0;
+  for (Worker& W : workers) { if (W.rc < 0) return W.rc; used += W.used; }
+  if (!send.reserve(std::max<size_t>(used, 1) * REC)) return MB2_ERR_CUDA;
+  size_t send_cap = (send.cap - 256) / REC;   // the buffer is kept between calls: it may be larger than this call needs
+  {
+    size_t o = 0;
+    for (int u = 0; u < U; u++) {
+      if (owner[u] != rank || counts[u] <= 0) continue;
+      mb2_dev_copy(ctx, (unsigned char*)send.p + o * REC, (const unsigned char*)workers[unit_worker[u]].bufp->p + unit_off[u] * REC, (size_t)counts[u] * REC, 2);
+      o += (size_t)counts[u];
+    }
   }
   const double t_views = now_ms();
 
