@@ -331,7 +331,7 @@ def run_ours_c4(args, rank, world, local_rank):
                       "processing time first), ONE ncclAllGather of device-resident region records + count / tentative exchanges; verification on rank 0",
                       "l2": "176 view pipelines per step, working set far beyond the 126 MB L2",
                       "digest": ["%016x" % d for d in dig], "digest_identical_on_all_ranks": all(d == dig for d in digs),
-                      "allgather_bytes_per_rank": st["allgather_bytes_per_rank"], "step_ms_rank0": step_ms, "steps_rank0_ms": [[round(o[3][k], 1) for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")] for o in out_dev + out_e2e], "rank0_ms": {k: st[k] for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")}},
+                      "allgather_bytes_per_rank": st["allgather_bytes_per_rank"], "verify_ms_rank0": {"duplicate_filter": res.ms_duplicate, "lo_ransac_and_laf": res.ms_ransac}, "step_ms_rank0": step_ms, "steps_rank0_ms": [[round(o[3][k], 1) for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")] for o in out_dev + out_e2e], "rank0_ms": {k: st[k] for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")}},
            "matched_kpts_per_s": res.verified * v,
            "e2e": {"value": e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * w * h * 4, "d2h_bytes_per_step": int(res.tentatives * 56 + (res.regions1 + res.regions2) * 184 + res.verified * 32),
                    "ms_per_step": ms_e2e / K, "entry": "mb2_views_sharded_pair (libmods_host.so), pinned host images on every rank, verified list on the host"},

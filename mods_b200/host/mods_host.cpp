@@ -822,6 +822,18 @@ mb2_ctx* sibling_ctx(mb2_ctx* ctx, int which = 0) {
 }
 }  // namespace
 
+// device staging of mb2_mods_pairs' host images: two buffer pairs per primary context, grow-only, released by mb2_mods_release
+namespace {
+struct Staged { void* d[2] = {nullptr, nullptr}; size_t cap[2] = {0, 0}; const float* use[2] = {nullptr, nullptr}; int rc = MB2_OK; mb2_ctx* owner = nullptr; };
+std::unordered_map<mb2_ctx*, Staged*> g_staged;
+Staged* staged_of(mb2_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_sib_mutex);
+  Staged*& s = g_staged[ctx];
+  if (!s) s = new Staged[2];
+  return s;
+}
+}  // namespace
+
 // helper context `which` of a primary context (same device, its own stream); created on first use, released by mb2_mods_release
 extern "C" mb2_ctx* mb2_mods_sibling(mb2_ctx* ctx, int which) { return (ctx && which >= 0 && which < 6) ? sibling_ctx(ctx, which) : nullptr; }
 
@@ -837,6 +849,14 @@ extern "C" void mb2_sharded_release(mb2_ctx* ctx);   // mods_sharded.cpp: the vi
 extern "C" void mb2_mods_release(mb2_ctx* ctx) {
   mb2_sharded_release(ctx);
   std::lock_guard<std::mutex> lk(g_sib_mutex);
+  {
+    auto st = g_staged.find(ctx);
+    if (st != g_staged.end()) {
+      for (int b = 0; b < 2; b++) for (int im = 0; im < 2; im++) if (st->second[b].d[im]) mb2_dev_free(st->second[b].owner, st->second[b].d[im]);
+      delete[] st->second;
+      g_staged.erase(st);
+    }
+  }
   auto it = g_siblings.find(ctx);
   if (it == g_siblings.end()) return;
   for (mb2_ctx* c : it->second.c) if (c) mb2_ctx_destroy(c);
@@ -1266,6 +1286,34 @@ extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img
     });
     inflight.push_back(std::move(a));
   };
+  // Host images: the two images of pair k + 1 travel to the device (copy engine, own stream) while pair k is computed, into one of two
+  // buffer pairs; the front stage then starts from device-resident images.  (Staged inside the view calls, every context uploaded its
+  // own copy -- HessianAffine and MSER contexts: 200 MB per pair -- ahead of its first kernel.)
+  mb2_ctx* cctx = ahead == 0 ? sibling_ctx(ctx, 5) : nullptr;
+  Staged* staged = staged_of(ctx);   // two buffer pairs, kept per context between calls (cudaMalloc / cudaFree of 200 MB per call otherwise)
+  auto upload = [&](int k) {
+    Staged& S = staged[k & 1];
+    S.rc = MB2_OK;
+    const double t_up = now_ms();
+    for (int im = 0; im < 2; im++) {
+      const float* src = im ? img2[k] : img1[k];
+      S.use[im] = src;
+      if (!cctx || mb2_is_device_pointer(src)) continue;
+      const size_t bytes = (size_t)(im ? w2[k] : w1[k]) * (im ? h2[k] : h1[k]) * 4;
+      if (bytes > S.cap[im]) {
+        if (S.d[im]) mb2_dev_free(cctx, S.d[im]);
+        S.d[im] = mb2_dev_alloc(cctx, bytes); S.cap[im] = S.d[im] ? bytes : 0; S.owner = cctx;
+        if (!S.d[im]) { S.rc = MB2_ERR_CUDA; return; }
+      }
+      if (mb2_dev_copy(cctx, S.d[im], src, bytes, 0) != MB2_OK) { S.rc = MB2_ERR_CUDA; return; }
+      S.use[im] = (const float*)S.d[im];
+    }
+    if (cctx && mb2_ctx_sync(cctx) != MB2_OK) S.rc = MB2_ERR_CUDA;
+    static const bool timing = getenv("MB2_PAIR_TIMING") != nullptr;
+    if (timing) fprintf(stderr, "[pair upload] pair %d: %.2f ms\n", k, now_ms() - t_up);
+  };
+  std::thread up;
+  if (n_pairs > 0) upload(0);
   for (int k = 0; k < n_pairs; k++) {
     std::memset(&res[k], 0, sizeof res[k]);
     std::unique_ptr<PairFront> f(new PairFront);
@@ -1274,7 +1322,10 @@ extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img
       while (next_launch < n_pairs && next_launch <= k + ahead) launch_ahead(next_launch++);
       pre = std::move(inflight.front()); inflight.pop_front();
     }
-    pair_front(ctx, img1[k], w1[k], h1[k], img2[k], w2[k], h2[k], cfg, ps, &res[k], *f, pre.get());
+    if (up.joinable()) up.join();                       // pair k is on the device
+    if (staged[k & 1].rc < 0) { rc = staged[k & 1].rc; break; }
+    if (k + 1 < n_pairs) up = std::thread(upload, k + 1);   // pair k + 1 follows while pair k is computed (the other buffer pair)
+    pair_front(ctx, staged[k & 1].use[0], w1[k], h1[k], staged[k & 1].use[1], w2[k], h2[k], cfg, ps, &res[k], *f, pre.get());
     pre.reset();
     std::unique_lock<std::mutex> lk(m);
     if (f->rc < 0) { rc = f->rc; break; }
@@ -1284,6 +1335,7 @@ extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img
     cv.notify_all();
   }
   inflight.clear();   // joins detections that were started for pairs an error kept us from reaching
+  if (up.joinable()) up.join();
   { std::lock_guard<std::mutex> lk(m); done = true; }
   cv.notify_all();
   back.join();
