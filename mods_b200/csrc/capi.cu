@@ -2,6 +2,7 @@
 // No oracle / CPU fallback anywhere on this path: every entry point either runs the CUDA kernels
 // or fails with an error code.
 #include "common.cuh"
+#include "parallel_host.hpp"
 #undef MB2_NS
 #define MB2_NS mb2_capi_detail
 #include "pyramid.cuh"
@@ -464,13 +465,14 @@ int detect_core(mb2_ctx* ctx, const ImgView& img, const mb2_hessaff_params& par,
     float lvlSigma[MB2_MAX_LEVELS];
     { float cs = par.initialSigma; for (int l = 0; l < NL; l++) { lvlSigma[l] = cs; cs *= sigmaStep; } }
     const int nscales = par.numberOfScales;
-#pragma omp parallel for schedule(static) if (n_kp > 4096)
-    for (int i = 0; i < n_kp; i++) {
-      const float scale = lvlSigma[req[i].level] * std::pow(2.0f, req[i].b2 / nscales);
-      float pd = 1.0f;
-      for (int o = 0; o < req[i].octave; o++) pd *= 2.0f;
-      hs[i] = pd * scale;
-    }
+    mb2par::parallel_chunks((n_kp + 4095) / 4096, [&](int ck) {
+      for (int i = ck * 4096, e = std::min(n_kp, i + 4096); i < e; i++) {
+        const float scale = lvlSigma[req[i].level] * std::pow(2.0f, req[i].b2 / nscales);
+        float pd = 1.0f;
+        for (int o = 0; o < req[i].octave; o++) pd *= 2.0f;
+        hs[i] = pd * scale;
+      }
+    });
     MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(d_s, hs, (size_t)n_kp * 4, cudaMemcpyHostToDevice, ctx->stream));
     mb2_launch_set_scales(ctx, d_kp, n_kp, d_s);
   }
@@ -569,8 +571,9 @@ int orient_core(mb2_ctx* ctx, const ImgView& img, int n, const mb2_orientation_p
     MB2_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     const float* ang = ctx->h_a.as<float>();
     double* cs = ctx->h_b.as<double>();
-#pragma omp parallel for schedule(static) if (m > 4096)
-    for (int i = 0; i < m; i++) { cs[2 * i] = std::cos(-ang[i]); cs[2 * i + 1] = std::sin(-ang[i]); }
+    mb2par::parallel_chunks((m + 4095) / 4096, [&](int ck) {
+      for (int i = ck * 4096, e = std::min(m, i + 4096); i < e; i++) { cs[2 * i] = std::cos(-ang[i]); cs[2 * i + 1] = std::sin(-ang[i]); }
+    });
     MB2_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cs, cs, (size_t)m * 16, cudaMemcpyHostToDevice, ctx->stream));
     mb2_launch_apply_rotation(ctx, ctx->kp_c.as<KeyOut>(), d_cs, m);
   }

@@ -2,6 +2,7 @@
 // code is compiled into the library and into tests/native/ransac_f_cpu.cpp.
 // Reference: degensac/rtools.c, utools.c, Htools.c, hash.c (line numbers at each function).
 #pragma once
+#include "parallel_host.hpp"
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -223,14 +224,13 @@ inline void u2h(const double* u, const int* inl, int len, double* H) {
   // computes C[i][j] = sum_k Z[k][i] * Z[k][j] with k running over the rows in order; adding row 2i and
   // then row 2i+1 of every point to all 45 accumulators performs exactly those additions in exactly that
   // order, in one pass over the correspondences instead of 45 strided passes over a 2n x 9 matrix.
-  // Large inlier sets (LO on tens of thousands of points) are summed in fixed chunks on all host cores;
+  // Large inlier sets (LO on tens of thousands of points) are summed in fixed chunks on the host pool (parallel_host.hpp);
   // the chunk boundaries do not depend on the thread count, so the result is machine-independent.  Short
   // lists (one chunk) keep the reference's single serial chain bit for bit.
   const int CH = 2048;
   const int nchunks = len <= 2 * CH ? 1 : (len + CH - 1) / CH;
   std::vector<double> part((size_t)nchunks * 45, 0.0);
-#pragma omp parallel for schedule(static) if (nchunks > 1)
-  for (int ck = 0; ck < nchunks; ck++) {
+  mb2par::parallel_chunks(nchunks, [&](int ck) {
     double* acc = part.data() + (size_t)ck * 45;
     const int lo = nchunks == 1 ? 0 : ck * CH, hi = nchunks == 1 ? len : std::min(len, lo + CH);
     for (int i = lo; i < hi; i++) {
@@ -252,7 +252,7 @@ inline void u2h(const double* u, const int* inl, int len, double* H) {
           if (p % 3 != 0 && q % 3 != 0) acc[t] += r1[p] * r1[q];
         }
     }
-  }
+  });
   double acc[45];
   for (int t = 0; t < 45; t++) { acc[t] = part[t]; for (int ck = 1; ck < nchunks; ck++) acc[t] += part[(size_t)ck * 45 + t]; }
   {

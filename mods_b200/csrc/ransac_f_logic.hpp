@@ -25,6 +25,7 @@
 //  * Undefined corners of the reference that are refused or pinned here: u2f with fewer than 8 points reads an uninitialised
 //    buffer in the reference -> the model is left unchanged; a run in which no model is ever accepted returns an all-zero mask.
 #pragma once
+#include "parallel_host.hpp"
 #include "ransac_common.hpp"
 #include "minv3.hpp"
 
@@ -245,8 +246,7 @@ inline void u2f_w(const double* u, const int* inl, const double* w, int len, dou
   const int CH = 2048;
   const int nchunks = len <= 2 * CH ? 1 : (len + CH - 1) / CH;
   std::vector<double> part((size_t)nchunks * 45, 0.0);
-#pragma omp parallel for schedule(static) if (nchunks > 1)
-  for (int ck = 0; ck < nchunks; ck++) {
+  mb2par::parallel_chunks(nchunks, [&](int ck) {
     double* acc = part.data() + (size_t)ck * 45;
     const int lo = nchunks == 1 ? 0 : ck * CH, hi = nchunks == 1 ? len : std::min(len, lo + CH);
     for (int i = lo; i < hi; i++) {
@@ -260,7 +260,7 @@ inline void u2f_w(const double* u, const int* inl, const double* w, int len, dou
       int t = 0;
       for (int p = 0; p < 9; p++) for (int q = 0; q <= p; q++, t++) acc[t] += z[p] * z[q];
     }
-  }
+  });
   double C[81];
   {
     int t = 0;

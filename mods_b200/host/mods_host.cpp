@@ -3,10 +3,8 @@
 // region bookkeeping, the O(T) (grid-accelerated, same result) duplicate filter and the small
 // post-RANSAC checks.
 #include "mods_host.hpp"
+#include "../csrc/parallel_host.hpp"
 
-#ifdef _OPENMP
-#include <omp.h>
-#endif
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -502,23 +500,16 @@ std::vector<int> duplicate_filter_core(const double* xy_in, const double* key, i
     // miss: 8 of the 12 ms this function took for 30k tentatives on one core)
     std::vector<double> xyc((size_t)T * 4);
     for (int k = 0; k < T; k++) std::memcpy(&xyc[4 * (size_t)k], &xy[4 * (size_t)by_cell[k]], 4 * sizeof(double));
-    // one sweep over the cells (grid rows dealt out to the host threads); the predecessors of a tentative go to the sweeping thread's
-    // own list, remembered per tentative as (thread, offset, count)
-    int n_thr = 1;
-#ifdef _OPENMP
-    if (T > 20000) n_thr = std::max(1, omp_get_max_threads());
-#endif
-    std::vector<std::vector<int> > preds(n_thr);
-    std::vector<int> pred_off(T, 0), npred(T, 0);
-    std::vector<unsigned short> pred_thr(T, 0);
-#pragma omp parallel for schedule(dynamic, 4) num_threads(n_thr) if (n_thr > 1)
-    for (long long gy = 0; gy < gh; gy++) {
-#ifdef _OPENMP
-      const int me = n_thr > 1 ? omp_get_thread_num() : 0;
-#else
-      const int me = 0;
-#endif
-      std::vector<int>& mine = preds[me];
+    // one sweep over the cells, bands of grid rows dealt out to the host pool (parallel_host.hpp); the predecessors of a tentative go to
+    // its band's own list, remembered per tentative as (band, offset, count)
+    const int BAND = 4;
+    const int n_bands = T > 20000 ? (int)((gh + BAND - 1) / BAND) : 1;
+    const long long band_rows = n_bands > 1 ? BAND : gh;
+    std::vector<std::vector<int> > preds(n_bands);
+    std::vector<int> pred_off(T, 0), npred(T, 0), pred_band(T, 0);
+    mb2par::parallel_chunks(n_bands, [&](int band) {
+      std::vector<int>& mine = preds[band];
+      for (long long gy = band * band_rows, gy_end = std::min<long long>(gh, gy + band_rows); gy < gy_end; gy++)
       for (long long gx = 0; gx < gw; gx++) {
         const size_t c0 = (size_t)(gy * gw + gx);
         for (int kj = cell_start[c0]; kj < cell_start[c0 + 1]; kj++) {
@@ -542,14 +533,14 @@ std::vector<int> duplicate_filter_core(const double* xy_in, const double* key, i
               }
             }
           }
-          pred_off[j] = (int)first; npred[j] = (int)(mine.size() - first); pred_thr[j] = (unsigned short)me;
+          pred_off[j] = (int)first; npred[j] = (int)(mine.size() - first); pred_band[j] = band;
         }
       }
-    }
+    });
     std::vector<char> is_kept(T, 0);
     for (int j = 0; j < T; j++) {
       bool dup = false;
-      const int* pl = npred[j] ? preds[pred_thr[j]].data() + pred_off[j] : nullptr;
+      const int* pl = npred[j] ? preds[pred_band[j]].data() + pred_off[j] : nullptr;
       for (int k = 0; k < npred[j] && !dup; k++) dup = is_kept[pl[k]] != 0;
       if (!dup) { is_kept[j] = 1; kept.push_back(order[j]); }
     }
@@ -845,9 +836,10 @@ extern "C" long long mb2_mods_launch_count(mb2_ctx* ctx) {
     for (mb2_ctx* c : it->second.c) if (c) n += mb2_ctx_launch_count(c);
   return n;
 }
-extern "C" void mb2_sharded_release(mb2_ctx* ctx);   // mods_sharded.cpp: the view-sharded driver's device scratch of this context
+// mods_sharded.cpp: the view-sharded driver's device scratch of this context (weak: the CPU test harness builds this file alone)
+extern "C" void mb2_sharded_release(mb2_ctx* ctx) __attribute__((weak));
 extern "C" void mb2_mods_release(mb2_ctx* ctx) {
-  mb2_sharded_release(ctx);
+  if (mb2_sharded_release) mb2_sharded_release(ctx);
   std::lock_guard<std::mutex> lk(g_sib_mutex);
   {
     auto st = g_staged.find(ctx);
