@@ -68,17 +68,59 @@ def make_pairs(w, h, n_pairs, seed0=1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md's clocks line).  Sampled in-process through NVML (nvidia_ml_py)
+    every 100 ms.  A spawned `nvidia-smi -lms 100` attaches to the driver ~0.5 s after the fork, i.e. in the middle of the timed arms: one
+    round-2 run measured the end-to-end arm at half speed that way (15.6 against 31.1 pairs/s device-resident); with the sampler already up
+    (tools/e2e_probe.py) neither source costs anything.  `nvidia-smi` stays as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows = []
+    def __init__(self, gpu_index, force_smi=False, period_s=0.1):
+        self.rows = []      # (sm_mhz, sm_max_mhz, [reason names])
         self.proc = None
+        self.nvml = None
         self.gpu = gpu_index
+        self.period = period_s
+        self.stop_flag = threading.Event()
+        self.source = None
+        if not force_smi:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = gpu_index
+                if vis:
+                    try:
+                        phys = int(vis.split(",")[gpu_index])
+                    except Exception:
+                        phys = gpu_index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+                self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+                self.nvml = pynvml
+            except Exception:
+                self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        bits = ((n.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"), (n.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"), (n.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap"))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((sm, self.sm_max, [name for bit, name in bits if r & bit]))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
+        if self.nvml is not None:
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._sample_nvml, daemon=True)
+            self.t.start()
+            return
         try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -88,26 +130,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            c = [v.strip() for v in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.rows.append((float(c[1]), float(c[2]), [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8])
+                                                             if v.lower().startswith("active")]))
             except Exception:
                 pass
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+    def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no clock source (NVML and nvidia-smi unavailable)"])
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = set()
+        for r in self.rows:
+            reasons.update(r[2])
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm), source=self.source)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -168,6 +215,7 @@ def run_ours(args, rank, world, local_rank):
 
     # warm-up (allocations, module load) then the two timed arms
     timed(dev_pairs, max(3, args.warmup))
+    timed(pin_pairs, max(3, args.warmup))   # the end-to-end arm gets its own warm-up (staging buffers of the upload path)
     timed(dev_pairs, 2, pipelined=False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
