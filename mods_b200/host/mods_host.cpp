@@ -6,6 +6,7 @@
 #include "../csrc/parallel_host.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -798,7 +799,9 @@ namespace {
 std::mutex g_sib_mutex;
 //   [4], [5] further MSER contexts: with MB2_MSER_AHEAD=n the dataset call (mb2_mods_pairs) runs the MSER detection of the next n pairs
 //   while the current pair is in its HessianAffine / description stage; a detection owns its context until it is described.
-struct Helpers { mb2_ctx* c[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; bool tried[6] = {false, false, false, false, false, false}; };
+//   [6] the primary context of the SECOND LANE of the dataset call (mb2_mods_pairs runs two pairs' front stages side by side); it has
+//   helper contexts [0], [2], [3], [5] of its own.
+struct Helpers { mb2_ctx* c[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; bool tried[7] = {false, false, false, false, false, false, false}; };
 std::unordered_map<mb2_ctx*, Helpers> g_siblings;
 mb2_ctx* sibling_ctx(mb2_ctx* ctx, int which = 0) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
@@ -832,14 +835,26 @@ extern "C" long long mb2_mods_launch_count(mb2_ctx* ctx) {
   std::lock_guard<std::mutex> lk(g_sib_mutex);
   long long n = mb2_ctx_launch_count(ctx);
   auto it = g_siblings.find(ctx);
-  if (it != g_siblings.end())
+  if (it != g_siblings.end()) {
     for (mb2_ctx* c : it->second.c) if (c) n += mb2_ctx_launch_count(c);
+    if (mb2_ctx* lane = it->second.c[6]) {   // the second lane's own helpers
+      auto jt = g_siblings.find(lane);
+      if (jt != g_siblings.end()) for (mb2_ctx* c : jt->second.c) if (c) n += mb2_ctx_launch_count(c);
+    }
+  }
   return n;
 }
 // mods_sharded.cpp: the view-sharded driver's device scratch of this context (weak: the CPU test harness builds this file alone)
 extern "C" void mb2_sharded_release(mb2_ctx* ctx) __attribute__((weak));
 extern "C" void mb2_mods_release(mb2_ctx* ctx) {
   if (mb2_sharded_release) mb2_sharded_release(ctx);
+  mb2_ctx* lane = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_sib_mutex);
+    auto it = g_siblings.find(ctx);
+    if (it != g_siblings.end()) lane = it->second.c[6];
+  }
+  if (lane) mb2_mods_release(lane);   // the second lane's helpers and staging buffers first (the lane context itself goes with ctx's helpers below)
   std::lock_guard<std::mutex> lk(g_sib_mutex);
   {
     auto st = g_staged.find(ctx);
@@ -1278,56 +1293,78 @@ extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img
     });
     inflight.push_back(std::move(a));
   };
-  // Host images: the two images of pair k + 1 travel to the device (copy engine, own stream) while pair k is computed, into one of two
-  // buffer pairs; the front stage then starts from device-resident images.  (Staged inside the view calls, every context uploaded its
-  // own copy -- HessianAffine and MSER contexts: 200 MB per pair -- ahead of its first kernel.)
-  mb2_ctx* cctx = ahead == 0 ? sibling_ctx(ctx, 5) : nullptr;
-  Staged* staged = staged_of(ctx);   // two buffer pairs, kept per context between calls (cudaMalloc / cudaFree of 200 MB per call otherwise)
-  auto upload = [&](int k) {
-    Staged& S = staged[k & 1];
-    S.rc = MB2_OK;
-    const double t_up = now_ms();
-    for (int im = 0; im < 2; im++) {
-      const float* src = im ? img2[k] : img1[k];
-      S.use[im] = src;
-      if (!cctx || mb2_is_device_pointer(src)) continue;
-      const size_t bytes = (size_t)(im ? w2[k] : w1[k]) * (im ? h2[k] : h1[k]) * 4;
-      if (bytes > S.cap[im]) {
-        if (S.d[im]) mb2_dev_free(cctx, S.d[im]);
-        S.d[im] = mb2_dev_alloc(cctx, bytes); S.cap[im] = S.d[im] ? bytes : 0; S.owner = cctx;
-        if (!S.d[im]) { S.rc = MB2_ERR_CUDA; return; }
+  // LANES (MB2_LANES=1|2, default 1): with 2, the front stages of pairs k and k + 1 run side by side, each lane on its own set of contexts
+  // (lane 1: helper context [6] as its primary, with helpers of its own).  Results do not depend on the schedule (every pair is computed
+  // by the same calls on private contexts); verification of finished pairs stays on the one helper thread below.  MEASURED AND NOT ADOPTED
+  // (round 2, C3, one B200, tools/e2e_probe.py): 33.7 ms per pair with two lanes against 31.6 ms with one -- the three chains of ONE pair
+  // already keep the GPU throughput bound (the kernels of a second pair only slow the first pair's down), so a pair costs the sum of its
+  // kernels' work either way.  Kept as a switch for smaller images, where one pair does not fill the GPU.
+  int n_lanes = 1;
+  if (const char* e = getenv("MB2_LANES")) n_lanes = std::max(1, std::min(2, atoi(e)));
+  if (ahead > 0 || n_pairs < 2) n_lanes = 1;
+  mb2_ctx* lane_ctx[2] = {ctx, n_lanes > 1 ? sibling_ctx(ctx, 6) : nullptr};
+  if (n_lanes > 1 && (!lane_ctx[1] || !sibling_ctx(lane_ctx[1], 0))) n_lanes = 1;
+  std::atomic<bool> failed(false);
+  // Host images: the two images of a lane's next pair travel to the device (copy engine, own stream) while its current pair is computed,
+  // into one of two buffer pairs per lane; the front stage then starts from device-resident images.  (Staged inside the view calls, every
+  // context uploaded its own copy -- HessianAffine and MSER contexts: 200 MB per pair -- ahead of its first kernel.)
+  auto run_lane = [&](const int lane) {
+    mb2_ctx* lctx = lane_ctx[lane];
+    PairSetup ps_lane(cfg);
+    mb2_ctx* cctx = ahead == 0 ? sibling_ctx(lctx, 5) : nullptr;
+    Staged* staged = staged_of(lctx);   // two buffer pairs, kept per context between calls (cudaMalloc / cudaFree of 200 MB per call otherwise)
+    auto upload = [&](int k) {
+      Staged& S = staged[(k / n_lanes) & 1];
+      S.rc = MB2_OK;
+      const double t_up = now_ms();
+      for (int im = 0; im < 2; im++) {
+        const float* src = im ? img2[k] : img1[k];
+        S.use[im] = src;
+        if (!cctx || mb2_is_device_pointer(src)) continue;
+        const size_t bytes = (size_t)(im ? w2[k] : w1[k]) * (im ? h2[k] : h1[k]) * 4;
+        if (bytes > S.cap[im]) {
+          if (S.d[im]) mb2_dev_free(cctx, S.d[im]);
+          S.d[im] = mb2_dev_alloc(cctx, bytes); S.cap[im] = S.d[im] ? bytes : 0; S.owner = cctx;
+          if (!S.d[im]) { S.rc = MB2_ERR_CUDA; return; }
+        }
+        if (mb2_dev_copy(cctx, S.d[im], src, bytes, 0) != MB2_OK) { S.rc = MB2_ERR_CUDA; return; }
+        S.use[im] = (const float*)S.d[im];
       }
-      if (mb2_dev_copy(cctx, S.d[im], src, bytes, 0) != MB2_OK) { S.rc = MB2_ERR_CUDA; return; }
-      S.use[im] = (const float*)S.d[im];
+      if (cctx && mb2_ctx_sync(cctx) != MB2_OK) S.rc = MB2_ERR_CUDA;
+      static const bool timing = getenv("MB2_PAIR_TIMING") != nullptr;
+      if (timing) fprintf(stderr, "[pair upload] pair %d: %.2f ms\n", k, now_ms() - t_up);
+    };
+    auto fail = [&](int code) { std::lock_guard<std::mutex> lk(m); if (rc >= 0) rc = code; failed = true; };
+    std::thread up;
+    if (lane < n_pairs) upload(lane);
+    for (int k = lane; k < n_pairs && !failed; k += n_lanes) {
+      std::memset(&res[k], 0, sizeof res[k]);
+      std::unique_ptr<PairFront> f(new PairFront);
+      std::unique_ptr<MserAhead> pre;
+      if (ahead > 0) {   // (single lane only)
+        while (next_launch < n_pairs && next_launch <= k + ahead) launch_ahead(next_launch++);
+        pre = std::move(inflight.front()); inflight.pop_front();
+      }
+      if (up.joinable()) up.join();                       // pair k is on the device
+      Staged& S = staged[(k / n_lanes) & 1];
+      if (S.rc < 0) { fail(S.rc); break; }
+      if (k + n_lanes < n_pairs) up = std::thread(upload, k + n_lanes);   // the lane's next pair follows while pair k is computed (the other buffer pair)
+      pair_front(lctx, S.use[0], w1[k], h1[k], S.use[1], w2[k], h2[k], cfg, ps_lane, &res[k], *f, pre.get());
+      pre.reset();
+      if (f->rc < 0) { fail(f->rc); break; }
+      std::unique_lock<std::mutex> lk(m);
+      cv.wait(lk, [&] { return q.size() < 2; });   // at most two pairs waiting for verification
+      q.emplace_back(k, std::move(f));
+      lk.unlock();
+      cv.notify_all();
     }
-    if (cctx && mb2_ctx_sync(cctx) != MB2_OK) S.rc = MB2_ERR_CUDA;
-    static const bool timing = getenv("MB2_PAIR_TIMING") != nullptr;
-    if (timing) fprintf(stderr, "[pair upload] pair %d: %.2f ms\n", k, now_ms() - t_up);
+    if (up.joinable()) up.join();
   };
-  std::thread up;
-  if (n_pairs > 0) upload(0);
-  for (int k = 0; k < n_pairs; k++) {
-    std::memset(&res[k], 0, sizeof res[k]);
-    std::unique_ptr<PairFront> f(new PairFront);
-    std::unique_ptr<MserAhead> pre;
-    if (ahead > 0) {
-      while (next_launch < n_pairs && next_launch <= k + ahead) launch_ahead(next_launch++);
-      pre = std::move(inflight.front()); inflight.pop_front();
-    }
-    if (up.joinable()) up.join();                       // pair k is on the device
-    if (staged[k & 1].rc < 0) { rc = staged[k & 1].rc; break; }
-    if (k + 1 < n_pairs) up = std::thread(upload, k + 1);   // pair k + 1 follows while pair k is computed (the other buffer pair)
-    pair_front(ctx, staged[k & 1].use[0], w1[k], h1[k], staged[k & 1].use[1], w2[k], h2[k], cfg, ps, &res[k], *f, pre.get());
-    pre.reset();
-    std::unique_lock<std::mutex> lk(m);
-    if (f->rc < 0) { rc = f->rc; break; }
-    cv.wait(lk, [&] { return q.size() < 2; });   // at most two pairs waiting for verification
-    q.emplace_back(k, std::move(f));
-    lk.unlock();
-    cv.notify_all();
-  }
+  std::thread lane1;
+  if (n_lanes > 1) lane1 = std::thread(run_lane, 1);
+  run_lane(0);
+  if (lane1.joinable()) lane1.join();
   inflight.clear();   // joins detections that were started for pairs an error kept us from reaching
-  if (up.joinable()) up.join();
   { std::lock_guard<std::mutex> lk(m); done = true; }
   cv.notify_all();
   back.join();

@@ -26,15 +26,26 @@ def timed(bufs, n):
 
 
 timed(dev, 3)
-for mode in ("none", "nvidia-smi", "nvml"):   # what samples the clocks while the arms run
-    sampler = None
-    if mode != "none":
-        sampler = bench.ClockSampler(0, force_smi=(mode == "nvidia-smi"))
-        sampler.start()
-        time.sleep(1.0 if mode == "nvidia-smi" else 0.1)   # nvidia-smi takes a moment to come up
+configs = [dict(MB2_LANES="1"), dict(MB2_LANES="2"), dict(MB2_LANES="1", MB2_MSER_AHEAD="1")]
+if os.environ.get("PROBE_SAMPLERS"):   # what samples the clocks while the arms run (bench.ClockSampler)
+    for mode in ("none", "nvidia-smi", "nvml"):
+        sampler = None
+        if mode != "none":
+            sampler = bench.ClockSampler(0, force_smi=(mode == "nvidia-smi"))
+            sampler.start()
+            time.sleep(1.0 if mode == "nvidia-smi" else 0.1)   # nvidia-smi takes a moment to come up
+        for r in range(reps):
+            for name, bufs in (("dev", dev), ("pin", pin)):
+                ms, res = timed(bufs, steps)
+                print("[sampler %s] %s rep %d: %.2f ms per pair (%.1f pairs/s)  verified %d" % (mode, name, r, ms, 1e3 / ms, res[0].verified), flush=True)
+        if sampler:
+            print("   ", sampler.stop(), flush=True)
+for env in configs:   # schedule toggles of mb2_mods_pairs (read per call)
+    for k in ("MB2_LANES", "MB2_MSER_AHEAD"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    timed(dev, 4); timed(pin, 4)
     for r in range(reps):
         for name, bufs in (("dev", dev), ("pin", pin)):
             ms, res = timed(bufs, steps)
-            print("[sampler %s] %s rep %d: %.2f ms per pair (%.1f pairs/s)  verified %d" % (mode, name, r, ms, 1e3 / ms, res[0].verified), flush=True)
-    if sampler:
-        print("   ", sampler.stop(), flush=True)
+            print("%s %s rep %d: %.2f ms per pair (%.1f pairs/s)  verified %s" % (env, name, r, ms, 1e3 / ms, [x.verified for x in res[:3]]), flush=True)
