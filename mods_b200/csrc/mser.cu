@@ -76,12 +76,19 @@ typedef mser_tree::KeyT<unsigned long long, 32> GKey64;
 typedef mser_tree::KeyT<uint32_t, 12> TKey;      // inside a tile: 4096 elements
 #define MT_TILE 64
 #define MT_THREADS 256
+#define MT_TILES_THREADS 512   // k_mtree_tiles: 3 CTAs of 512 per SM beat 6 of 256 (late stages have few pixel pairs per tile)
 
 struct SmemWords {
   uint32_t* w;
   __device__ __forceinline__ uint32_t load(uint32_t i) { return *(volatile uint32_t*)(w + i); }
   __device__ __forceinline__ void store(uint32_t i, uint32_t v) { *(volatile uint32_t*)(w + i) = v; }
   __device__ __forceinline__ bool cas(uint32_t i, uint32_t expect, uint32_t desired) { return atomicCAS(w + i, expect, desired) == expect; }
+};
+struct SmemWordsOwned {   // words only the calling thread touches (the sequential 4 x 4 phase of k_mtree_tiles)
+  uint32_t* w;
+  __device__ __forceinline__ uint32_t load(uint32_t i) { return w[i]; }
+  __device__ __forceinline__ void store(uint32_t i, uint32_t v) { w[i] = v; }
+  __device__ __forceinline__ bool cas(uint32_t i, uint32_t, uint32_t desired) { w[i] = desired; return true; }
 };
 template <class WordT>
 struct GmemWords {   // L2-coherent accesses: a stale L1 line would make a failed compare-and-swap repeat forever
@@ -91,32 +98,61 @@ struct GmemWords {   // L2-coherent accesses: a stale L1 line would make a faile
   __device__ __forceinline__ bool cas(uint32_t i, WordT expect, WordT desired) { return atomicCAS(w + i, expect, desired) == expect; }
 };
 
+template <class WordT>
+struct GmemWordsRO {   // kernels that only READ the finished words (k_mtree_fix, k_mtree_walk): through L1 -- the pixels of a warp mostly name the same few nodes
+  const WordT* w;
+  __device__ __forceinline__ WordT load(uint32_t i) { return __ldg(w + i); }
+};
+
 struct MserImages { const float* p[4]; int pitch[4]; int n; };   // same-size images processed together (a pair: n = 2)
 
 template <class GK>
-__global__ void __launch_bounds__(MT_THREADS) k_mtree_tiles(MserImages im, int W, int H, uint8_t* __restrict__ lev, typename GK::word* __restrict__ gpar,
+__global__ void __launch_bounds__(MT_TILES_THREADS) k_mtree_tiles(MserImages im, int W, int H, uint8_t* __restrict__ lev, typename GK::word* __restrict__ gpar,
                                                             MserCounters* __restrict__ C) {
   __shared__ uint32_t par[2][MT_TILE * MT_TILE];
   __shared__ uint8_t sv[MT_TILE * MT_TILE];
   const int k = blockIdx.z, x0 = blockIdx.x * MT_TILE, y0 = blockIdx.y * MT_TILE;
   const int tw = min(MT_TILE, W - x0), th = min(MT_TILE, H - y0);
   const uint32_t Nimg = (uint32_t)W * H;
-  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_TILES_THREADS) {
     const int lx = i & (MT_TILE - 1), ly = i >> 6;
     int v = 0;
     if (lx < tw && ly < th) v = ((int)im.p[k][(size_t)(y0 + ly) * im.pitch[k] + x0 + lx]) & 0xff;
     par[0][i] = TKey::make(v, i); par[1][i] = TKey::make(255 - v, i); sv[i] = (uint8_t)v;
   }
   __syncthreads();
-  // Merge order: pixel pairs first, then 2 x 1 blocks into 2 x 2, ... up to the two halves of the tile (12 stages).  A stage only joins
-  // trees that are complete inside their blocks, so the one full walk up two root paths ("zipping") that every join of two trees
-  // costs happens mostly while the trees are tiny; the other pixel pairs of a block border find their paths already merged.
-  // (Measured at 4096 x 3072, both polarities: all inner edges at once in arbitrary order 6.1 ms; this order 1.9 ms; pixels in level order with
-  // union-find shortcuts and a barrier per level 11 ms -- too few pixels per level and tile to keep the warps busy between barriers.)
-  for (int s = 0; s < 12; s++) {
+  // Merge order: small blocks first, up to the two halves of the tile (12 stages; stage s joins blocks across b = 1 << (s >> 1) wide gaps,
+  // even s left-right, odd s top-bottom).  A join of two trees walks both root paths once ("zipping"), so joins should happen while the
+  // trees are small; the other pixel pairs of a block border find their paths already merged.
+  //   stages 0-3: ONE thread builds the tree of a whole 4 x 4 block (24 pixel pairs in turn; nobody else touches the block's words, so
+  //               plain loads / stores instead of compare-and-swap, no barriers, every lane busy with the same amount of work);
+  //   stages 4-11: one thread per pixel pair across the block border, all pairs of a border zipping concurrently (connect() is lock free).
+  // Measured at 4096 x 3072, both polarities (tools/micro/mtree_tiles.cu, every variant checked node by node against this one):
+  // all inner edges at once in arbitrary order 6.1 ms; 12 cooperative stages, 256 threads 1.87 ms; 4 x 4 blocks per thread + 8 stages,
+  // 512 threads 1.33 ms (this kernel); 8 x 8 per thread 1.49; block pairs joined by one thread each up to stage 8 / 12: 2.0 / 3.8 ms; one
+  // middle pair of every border first, then the rest: 1.6 - 2.2 ms; pixels in level order with union-find shortcuts and a barrier per
+  // level 11 ms (too few pixels per level and tile to keep the warps busy between barriers).
+  for (int t = threadIdx.x; t < 2 * (MT_TILE / 4) * (MT_TILE / 4); t += MT_TILES_THREADS) {
+    const int pol = t & 1, u = t >> 1, bx = (u & 15) * 4, by = (u >> 4) * 4;
+    SmemWordsOwned m{par[pol]};
+    for (int s = 0; s < 4; s++) {
+      const bool horiz = !(s & 1);
+      const int b = 1 << (s >> 1);
+      for (int line = 0; line < 4; line++)
+        for (int c = b - 1; c < 3; c += 2 * b) {
+          const int lx = bx + (horiz ? c : line), ly = by + (horiz ? line : c);
+          if ((horiz ? lx + 1 : lx) >= tw || (horiz ? ly : ly + 1) >= th) continue;
+          const int i = ly * MT_TILE + lx, j = horiz ? i + 1 : i + MT_TILE;
+          const int vi = pol ? 255 - sv[i] : sv[i], vj = pol ? 255 - sv[j] : sv[j];
+          mser_tree::connect<TKey>(m, TKey::make(vi, i), TKey::make(vj, j));
+        }
+    }
+  }
+  __syncthreads();
+  for (int s = 4; s < 12; s++) {
     const bool horiz = !(s & 1);
     const int b = 1 << (s >> 1), per_line = (MT_TILE / 2) / b, ntask = 2 * MT_TILE * per_line;
-    for (int t = threadIdx.x; t < ntask; t += MT_THREADS) {
+    for (int t = threadIdx.x; t < ntask; t += MT_TILES_THREADS) {
       const int pol = t & 1, u = t >> 1, line = u / per_line, c = (2 * (u - line * per_line) + 1) * b - 1;
       const int lx = horiz ? c : line, ly = horiz ? line : c;
       if ((horiz ? lx + 1 : lx) >= tw || (horiz ? ly : ly + 1) >= th) continue;
@@ -128,7 +164,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_mtree_tiles(MserImages im, int W
     __syncthreads();
   }
   // write-out: tile-local index -> index inside the image; sub-image 2k = MSER+, 2k + 1 = MSER-
-  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_TILES_THREADS) {
     const int lx = i & (MT_TILE - 1), ly = i >> 6;
     if (lx >= tw || ly >= th) continue;
     const uint32_t pi = (uint32_t)(y0 + ly) * W + x0 + lx;
@@ -283,7 +319,7 @@ __global__ void __launch_bounds__(256) k_mtree_borders(int W, int H, int n_sub, 
 // the tile (exclusive: that one receives them through the parent's own local sums) -- one node when nothing was inserted from other
 // tiles, the whole trunk for a tile's root.  Every representative walks that gap and adds its sums; no level-by-level pass is needed.
 template <class GK>
-__global__ void __launch_bounds__(256) k_mtree_fix(int W, int H, uint32_t N, const uint8_t* __restrict__ lev, typename GK::word* gpar,
+__global__ void __launch_bounds__(256) k_mtree_fix(int W, int H, uint32_t N, const uint8_t* __restrict__ lev, const typename GK::word* __restrict__ gpar,
                                                    const uint32_t* __restrict__ lsum, const uint16_t* __restrict__ hi,
                                                    uint32_t* __restrict__ parent, uint32_t* __restrict__ work, MserCounters* C) {
   const uint32_t Nimg = (uint32_t)W * H;
@@ -292,7 +328,7 @@ __global__ void __launch_bounds__(256) k_mtree_fix(int W, int H, uint32_t N, con
   if (x < N) {
     const uint32_t sub = x / Nimg, pi = x - sub * Nimg, off = sub * Nimg;
     const int L = lev[x];
-    GmemWords<typename GK::word> m{gpar + (size_t)off};
+    GmemWordsRO<typename GK::word> m{gpar + (size_t)off};
     const typename GK::word xk = GK::make(L, pi);
     const typename GK::word ck = mser_tree::canonical_parent<GK>(m, xk);
     parent[x] = off + GK::idx(ck);
@@ -310,7 +346,7 @@ __global__ void __launch_bounds__(256) k_mtree_fix(int W, int H, uint32_t N, con
   }
 }
 template <class GK>
-__global__ void __launch_bounds__(128) k_mtree_walk(int W, int H, const uint8_t* __restrict__ lev, typename GK::word* gpar,
+__global__ void __launch_bounds__(128) k_mtree_walk(int W, int H, const uint8_t* __restrict__ lev, const typename GK::word* __restrict__ gpar,
                                                     const uint32_t* __restrict__ lsum, const uint16_t* __restrict__ hi, const uint32_t* __restrict__ work,
                                                     const MserCounters* __restrict__ C, uint32_t* area, uint32_t* nedge) {
   const uint32_t Nimg = (uint32_t)W * H, n = C->n_walk;
@@ -318,7 +354,7 @@ __global__ void __launch_bounds__(128) k_mtree_walk(int W, int H, const uint8_t*
     const uint32_t x = work[i];
     const uint32_t sub = x / Nimg, pi = x - sub * Nimg, off = sub * Nimg;
     const int L = lev[x];
-    GmemWords<typename GK::word> m{gpar + (size_t)off};
+    GmemWordsRO<typename GK::word> m{gpar + (size_t)off};
     const typename GK::word xk = GK::make(L, pi);
     const typename GK::word ck = mser_tree::canonical_parent<GK>(m, xk);
     const uint32_t ls = lsum[x], sa = ls & 0xffffu, se = ls >> 16;
@@ -720,14 +756,14 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
     const int bg = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_border + 255) / 256, (unsigned long long)ctx->num_sms * 64));
     if (wide) {
       unsigned long long* gp = B.gpar.as<unsigned long long>();
-      MB2_LAUNCH(ctx, k_mtree_tiles<GKey64>, tg, MT_THREADS, 0, mi, W, H, lev, gp, dC);
+      MB2_LAUNCH(ctx, k_mtree_tiles<GKey64>, tg, MT_TILES_THREADS, 0, mi, W, H, lev, gp, dC);
       MB2_LAUNCH(ctx, k_mtree_local<GKey64>, lg, MT_THREADS, 0, W, H, lev, gp, lsum, hi, area, nedge);
       if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
       MB2_LAUNCH(ctx, k_mtree_fix<GKey64>, (N + 255) / 256, 256, 0, W, H, N, lev, gp, lsum, hi, parent, sa, dC);
       MB2_LAUNCH(ctx, k_mtree_walk<GKey64>, ctx->num_sms * 16, 128, 0, W, H, lev, gp, lsum, hi, sa, dC, area, nedge);
     } else {
       uint32_t* gp = B.gpar.as<uint32_t>();
-      MB2_LAUNCH(ctx, k_mtree_tiles<GKey32>, tg, MT_THREADS, 0, mi, W, H, lev, gp, dC);
+      MB2_LAUNCH(ctx, k_mtree_tiles<GKey32>, tg, MT_TILES_THREADS, 0, mi, W, H, lev, gp, dC);
       MB2_LAUNCH(ctx, k_mtree_local<GKey32>, lg, MT_THREADS, 0, W, H, lev, gp, lsum, hi, area, nedge);
       if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
       MB2_LAUNCH(ctx, k_mtree_fix<GKey32>, (N + 255) / 256, 256, 0, W, H, N, lev, gp, lsum, hi, parent, sa, dC);

@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -x -q -k "mods_pairs or mods_pair_with_mser" 2>&1 | tail -3
-python tools/e2e_probe.py 12 2 2>&1 | tail -20
+python -m pytest tests/test_gpu_mser.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -3
+TOPK=24 python tools/mser_probe.py 2>&1 | grep -v "pixels per level" | head -50
