@@ -194,24 +194,21 @@ __global__ void __launch_bounds__(MT_THREADS) k_mtree_local(int W, int H, const 
                                                             uint32_t* __restrict__ nedge) {
   __shared__ uint32_t par[MT_TILE * MT_TILE];
   __shared__ uint32_t acc[MT_TILE * MT_TILE];
-  __shared__ uint16_t list[MT_TILE * MT_TILE];
+  __shared__ uint32_t pend[MT_TILE * MT_TILE / 2];        // children (representatives) that have not yet delivered their subtree sums: 16-bit counters, two per word
   __shared__ uint8_t sl[(MT_TILE + 2) * (MT_TILE + 2)];   // levels with a one-pixel halo
-  __shared__ uint32_t cnt[256], off[257];   // cnt: representatives per level, re-used as the fill cursor of the counting sort
-  __shared__ int nz[256], n_nz;
   const int sub = blockIdx.z, x0 = blockIdx.x * MT_TILE, y0 = blockIdx.y * MT_TILE;
   const int tw = min(MT_TILE, W - x0), th = min(MT_TILE, H - y0);
   const uint32_t Nimg = (uint32_t)W * H;
   const uint8_t* l = lev + (size_t)sub * Nimg;
   typename GK::word* gp = gpar + (size_t)sub * Nimg;
   const int SW = MT_TILE + 2;
-  cnt[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < SW * SW; i += MT_THREADS) {
     const int gx = x0 + (i % SW) - 1, gy = y0 + (i / SW) - 1;
     sl[i] = (gx >= 0 && gy >= 0 && gx < W && gy < H) ? l[(size_t)gy * W + gx] : 0;
   }
   for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
     const int lx = i & (MT_TILE - 1), ly = i >> 6;
-    acc[i] = 0;
+    acc[i] = 0; if (!(i & 1)) pend[i >> 1] = 0;
     if (lx < tw && ly < th) {
       const typename GK::word w = gp[(size_t)(y0 + ly) * W + x0 + lx];
       const uint32_t pj = GK::idx(w);
@@ -229,56 +226,47 @@ __global__ void __launch_bounds__(MT_THREADS) k_mtree_local(int W, int H, const 
     par[i] = mser_tree::canonical_parent<TKey>(m, TKey::make(L, i));
   }
   __syncthreads();
-  // own counts of every node, representatives counted per level
+  // own counts of every node; every representative announces itself to its parent
   for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
     const int lx = i & (MT_TILE - 1), ly = i >> 6;
     if (lx >= tw || ly >= th) continue;
     const int c = (ly + 1) * SW + lx + 1, L = sl[c];
     const uint32_t w = par[i];
-    const bool rep = w == TKey::make(L, i) || TKey::lev(w) > L;
+    const bool self = w == TKey::make(L, i), rep = self || TKey::lev(w) > L;
     uint32_t e = 0;
     if (y0 + ly > 0) e += sl[c - SW] <= L;              // q < p: lower or equal level
     if (x0 + lx > 0) e += sl[c - 1] <= L;
     if (x0 + lx < W - 1) e += sl[c + 1] < L;            // q > p: strictly lower level
     if (y0 + ly < H - 1) e += sl[c + SW] < L;
     atomicAdd(&acc[rep ? i : TKey::idx(w)], 1u | (e << 16));
-    if (rep) atomicAdd(&cnt[L], 1u);
+    if (rep && !self) atomicAdd(&pend[TKey::idx(w) >> 1], 1u << (16 * (TKey::idx(w) & 1)));
   }
   __syncthreads();
-  if (threadIdx.x < 32) {   // exclusive scan of the 256 level counts, list of the levels that occur
-    uint32_t v[8], sum = 0;
-    for (int j = 0; j < 8; j++) { v[j] = cnt[threadIdx.x * 8 + j]; sum += v[j]; }
-    uint32_t incl = sum;
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)threadIdx.x >= d) incl += t; }
-    uint32_t run = incl - sum;
-    int mine = 0;
-    for (int j = 0; j < 8; j++) { off[threadIdx.x * 8 + j] = run; run += v[j]; mine += v[j] != 0; cnt[threadIdx.x * 8 + j] = 0; }
-    if (threadIdx.x == 31) off[256] = run;
-    int pre = mine;
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, d); if ((int)threadIdx.x >= d) pre += t; }
-    int o = pre - mine;
-    for (int j = 0; j < 8; j++) if (v[j]) nz[o++] = threadIdx.x * 8 + j;
-    if (threadIdx.x == 31) n_nz = pre;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
+  // Subtree sums inside the tile WITHOUT a pass per level: the leaves start, every representative hands its finished sums to its parent,
+  // and whoever delivers the LAST outstanding child of a node carries on with that node (one thread climbs the trunk at the end).  The
+  // leaves are fixed before anybody climbs (a node whose counter drops to zero later must not be mistaken for one).
+  uint32_t leaf_mask = 0;
+  for (int i = threadIdx.x, q = 0; i < MT_TILE * MT_TILE; i += MT_THREADS, q++) {
     const int lx = i & (MT_TILE - 1), ly = i >> 6;
     if (lx >= tw || ly >= th) continue;
     const int L = sl[(ly + 1) * SW + lx + 1];
     const uint32_t w = par[i];
-    if (w == TKey::make(L, i) || TKey::lev(w) > L) list[off[L] + atomicAdd(&cnt[L], 1u)] = (uint16_t)i;
+    if ((w == TKey::make(L, i) || TKey::lev(w) > L) && ((pend[i >> 1] >> (16 * (i & 1))) & 0xffffu) == 0) leaf_mask |= 1u << q;
   }
   __syncthreads();
-  // subtree sums inside the tile: children live on lower levels, so one ascending pass over the levels that occur
-  const int n_levels = n_nz;
-  for (int k = 0; k < n_levels; k++) {
-    const int L = nz[k];
-    for (uint32_t j = off[L] + threadIdx.x; j < off[L + 1]; j += MT_THREADS) {
-      const uint32_t v = list[j], w = par[v];
-      if (w != TKey::make(L, v)) atomicAdd(&acc[TKey::idx(w)], acc[v]);
+  for (int i = threadIdx.x, q = 0; i < MT_TILE * MT_TILE; i += MT_THREADS, q++) {
+    if (!((leaf_mask >> q) & 1u)) continue;
+    uint32_t u = (uint32_t)i;
+    for (;;) {
+      const uint32_t p = TKey::idx(par[u]);
+      if (p == u) break;                                        // the tile's root
+      atomicAdd(&acc[p], *(volatile uint32_t*)&acc[u]);          // u's sums are complete: all its children delivered before the counter reached zero
+      __threadfence_block();
+      if (((atomicSub(&pend[p >> 1], 1u << (16 * (p & 1))) >> (16 * (p & 1))) & 0xffffu) != 1u) break;                 // somebody else delivers p's last child and goes on from there
+      u = p;
     }
-    __syncthreads();
   }
+  __syncthreads();
   for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += MT_THREADS) {
     const int lx = i & (MT_TILE - 1), ly = i >> 6;
     if (lx >= tw || ly >= th) continue;
