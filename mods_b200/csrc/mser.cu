@@ -294,8 +294,8 @@ __global__ void __launch_bounds__(256) k_mtree_borders(int W, int H, int n_sub, 
     uint32_t p, q;
     // phase 0: one pair in the middle of every tile border (these join the tile trees: the long walks up two root paths, without the
     // other 63 pairs of the border swapping the same words); phase 1: the rest
-    if (e < nh) { const uint32_t b = e / W, x = e - b * W; if (((x & (MT_TILE - 1)) == MT_TILE / 2) != (phase == 0)) continue; q = (b + 1) * MT_TILE * W + x; p = q - W; }
-    else { const uint32_t f = e - nh, b = f / H, y = f - b * H; if (((y & (MT_TILE - 1)) == MT_TILE / 2) != (phase == 0)) continue; q = y * W + (b + 1) * MT_TILE; p = q - 1; }
+    if (e < nh) { const uint32_t b = e / W, x = e - b * W; if (phase < 2 && ((x & (MT_TILE - 1)) == MT_TILE / 2) != (phase == 0)) continue; q = (b + 1) * MT_TILE * W + x; p = q - W; }
+    else { const uint32_t f = e - nh, b = f / H, y = f - b * H; if (phase < 2 && ((y & (MT_TILE - 1)) == MT_TILE / 2) != (phase == 0)) continue; q = y * W + (b + 1) * MT_TILE; p = q - 1; }
     const uint8_t* l = lev + (size_t)sub * Nimg;
     GmemWords<typename GK::word> m{gpar + (size_t)sub * Nimg};
     mser_tree::connect<GK>(m, GK::make(l[p], p), GK::make(l[q], q));
@@ -740,20 +740,23 @@ int mser_stack(mb2_ctx* ctx, const ImgView* imgs, int K, const mb2_mser_params& 
   MB2_CUDA_CHECK(ctx, cudaMemsetAsync(dC, 0, sizeof(MserCounters), st));
   {
     const dim3 tg((W + MT_TILE - 1) / MT_TILE, (H + MT_TILE - 1) / MT_TILE, K), lg(tg.x, tg.y, 2 * K);
+    const bool borders_one = getenv("MB2_BORDERS_TWO") == nullptr;   // all border pairs in ONE launch (0.73 ms per image; one middle pair of every border first, then the rest: 0.76 -- MB2_BORDERS_TWO=1)
     const unsigned long long n_border = ((unsigned long long)((H - 1) / MT_TILE) * W + (unsigned long long)((W - 1) / MT_TILE) * H) * 2 * K;
     const int bg = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((n_border + 255) / 256, (unsigned long long)ctx->num_sms * 64));
     if (wide) {
       unsigned long long* gp = B.gpar.as<unsigned long long>();
       MB2_LAUNCH(ctx, k_mtree_tiles<GKey64>, tg, MT_TILES_THREADS, 0, mi, W, H, lev, gp, dC);
       MB2_LAUNCH(ctx, k_mtree_local<GKey64>, lg, MT_THREADS, 0, W, H, lev, gp, lsum, hi, area, nedge);
-      if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
+      if (n_border && borders_one) MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 2);
+      else if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey64>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
       MB2_LAUNCH(ctx, k_mtree_fix<GKey64>, (N + 255) / 256, 256, 0, W, H, N, lev, gp, lsum, hi, parent, sa, dC);
       MB2_LAUNCH(ctx, k_mtree_walk<GKey64>, ctx->num_sms * 16, 128, 0, W, H, lev, gp, lsum, hi, sa, dC, area, nedge);
     } else {
       uint32_t* gp = B.gpar.as<uint32_t>();
       MB2_LAUNCH(ctx, k_mtree_tiles<GKey32>, tg, MT_TILES_THREADS, 0, mi, W, H, lev, gp, dC);
       MB2_LAUNCH(ctx, k_mtree_local<GKey32>, lg, MT_THREADS, 0, W, H, lev, gp, lsum, hi, area, nedge);
-      if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
+      if (n_border && borders_one) MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 2);
+      else if (n_border) { MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 0); MB2_LAUNCH(ctx, k_mtree_borders<GKey32>, bg, 256, 0, W, H, 2 * K, lev, gp, 1); }
       MB2_LAUNCH(ctx, k_mtree_fix<GKey32>, (N + 255) / 256, 256, 0, W, H, N, lev, gp, lsum, hi, parent, sa, dC);
       MB2_LAUNCH(ctx, k_mtree_walk<GKey32>, ctx->num_sms * 16, 128, 0, W, H, lev, gp, lsum, hi, sa, dC, area, nedge);
     }

@@ -127,6 +127,117 @@ __global__ void __launch_bounds__(THREADS) k_tiles(const uint8_t* __restrict__ i
   }
 }
 
+// ---- 8 x 8 blocks built by ONE thread each with the sequential union-find algorithm (pixels in key order, Berger et al.) ------------
+// instead of pair-by-pair merging: a counting sort of the block's 64 pixels (two 4-bit passes, byte counters packed in registers), then
+// every pixel in turn adopts the current tops of its already processed neighbours' components.  The words come out with the same
+// invariants connect() keeps (pointers go up in key order; same-level chains end at the node's representative, whose word names a pixel
+// of the parent node), so the cooperative stages 6-11 continue from them.
+#define BT 128   // tasks per tile: 64 blocks x 2 polarities
+__device__ __forceinline__ uint32_t sc_addr(int t, int i) { return (uint32_t)((((i >> 2) * BT + t) << 2) | (i & 3)); }   // byte i of task t, word-interleaved over the tasks
+template <int THREADS, bool PROF>
+__global__ void __launch_bounds__(THREADS) k_tiles_seq8(const uint8_t* __restrict__ img, int W, int H, uint32_t* __restrict__ out, unsigned long long* prof) {
+  extern __shared__ uint32_t dyn[];
+  uint32_t (*par)[MT_TILE * MT_TILE] = reinterpret_cast<uint32_t (*)[MT_TILE * MT_TILE]>(dyn);
+  uint8_t* sv = reinterpret_cast<uint8_t*>(dyn + 2 * MT_TILE * MT_TILE);
+  uint8_t* ordb = sv + MT_TILE * MT_TILE;          // [64 x BT] sorted pixel lists
+  uint8_t* zpb = ordb + 64 * BT;                    // [64 x BT] union-find forest (first: scratch of the sort)
+  const int x0 = blockIdx.x * MT_TILE, y0 = blockIdx.y * MT_TILE;
+  const int tw = min(MT_TILE, W - x0), th = min(MT_TILE, H - y0);
+  const uint32_t Nimg = (uint32_t)W * H;
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    int v = 0;
+    if (lx < tw && ly < th) v = img[(size_t)(y0 + ly) * W + x0 + lx];
+    par[0][i] = TKey::make(v, i); par[1][i] = TKey::make(255 - v, i); sv[i] = (uint8_t)v;
+  }
+  __syncthreads();
+  long long t_prev = 0;
+  if (PROF && threadIdx.x == 0) t_prev = clock64();
+  for (int t = threadIdx.x; t < BT; t += THREADS) {
+    const int pol = t & 1, u = t >> 1, bx = (u & 7) * 8, by = (u >> 3) * 8, base = by * MT_TILE + bx;
+    const uint32_t flip = pol ? 255u : 0u;
+    auto level = [&](int j) -> uint32_t { return (uint32_t)sv[base + (j >> 3) * MT_TILE + (j & 7)] ^ flip; };   // 255 - v == v ^ 255
+    // counting sort, stable, by (level, j): pass 1 on the low nibble j -> zpb, pass 2 on the high nibble zpb -> ordb
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 4
+      for (int k = 0; k < 64; k++) {
+        const int j = pass ? zpb[sc_addr(t, k)] : k;
+        const uint32_t d = (level(j) >> (4 * pass)) & 15u, inc = 1u << ((d & 3u) * 8u), m = d >> 2;
+        c0 += m == 0 ? inc : 0u; c1 += m == 1 ? inc : 0u; c2 += m == 2 ? inc : 0u; c3 += m == 3 ? inc : 0u;
+      }
+      const uint32_t p0 = c0 * 0x01010101u, p1 = c1 * 0x01010101u, p2 = c2 * 0x01010101u, p3 = c3 * 0x01010101u;
+      const uint32_t t0 = p0 >> 24, t1 = t0 + (p1 >> 24), t2 = t1 + (p2 >> 24);
+      c0 = p0 - c0; c1 = p1 - c1 + t0 * 0x01010101u; c2 = p2 - c2 + t1 * 0x01010101u; c3 = p3 - c3 + t2 * 0x01010101u;   // exclusive offsets per digit
+#pragma unroll 4
+      for (int k = 0; k < 64; k++) {
+        const int j = pass ? zpb[sc_addr(t, k)] : k;
+        const uint32_t d = (level(j) >> (4 * pass)) & 15u, sh = (d & 3u) * 8u, inc = 1u << sh, m = d >> 2;
+        const uint32_t cm = m == 0 ? c0 : m == 1 ? c1 : m == 2 ? c2 : c3;
+        const uint32_t o = (cm >> sh) & 0xffu;
+        (pass ? ordb : zpb)[sc_addr(t, (int)o)] = (uint8_t)j;
+        c0 += m == 0 ? inc : 0u; c1 += m == 1 ? inc : 0u; c2 += m == 2 ? inc : 0u; c3 += m == 3 ? inc : 0u;
+      }
+    }
+    // union-find in key order
+    uint32_t* pw = par[pol];
+#pragma unroll 1
+    for (int k = 0; k < 64; k++) {
+      const int p = ordb[sc_addr(t, k)];
+      const int px = p & 7, py = p >> 3, ip = base + py * MT_TILE + px;
+      const uint32_t lp = level(p), kp = TKey::make((int)lp, (uint32_t)ip);
+      zpb[sc_addr(t, p)] = (uint8_t)p;
+      if (bx + px >= tw || by + py >= th) continue;          // outside the image: stays alone
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) {
+        const int qx = px + (nb == 0 ? -1 : nb == 1 ? 1 : 0), qy = py + (nb == 2 ? -1 : nb == 3 ? 1 : 0);
+        if (qx < 0 || qx > 7 || qy < 0 || qy > 7 || bx + qx >= tw || by + qy >= th) continue;
+        const int q = qy * 8 + qx;
+        const uint32_t lq = level(q);
+        if (!(lq < lp || (lq == lp && q < p))) continue;     // not processed yet
+        int r = q;
+        for (;;) {                                            // find with path halving
+          const int z = zpb[sc_addr(t, r)];
+          if (z == r) break;
+          const int zz = zpb[sc_addr(t, z)];
+          zpb[sc_addr(t, r)] = (uint8_t)zz;
+          r = zz;
+        }
+        if (r != p) { pw[base + (r >> 3) * MT_TILE + (r & 7)] = kp; zpb[sc_addr(t, r)] = (uint8_t)p; }
+      }
+    }
+  }
+  __syncthreads();
+  if (PROF && threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&prof[12], (unsigned long long)(t - t_prev)); t_prev = t; }
+  for (int s = 6; s < 12; s++) {
+    const bool horiz = !(s & 1);
+    const int b = 1 << (s >> 1), per_line = (MT_TILE / 2) / b, ntask = 2 * MT_TILE * per_line;
+    for (int t = threadIdx.x; t < ntask; t += THREADS) {
+      const int pol = t & 1, u = t >> 1, line = u / per_line, c = (2 * (u - line * per_line) + 1) * b - 1;
+      const int lx = horiz ? c : line, ly = horiz ? line : c;
+      if ((horiz ? lx + 1 : lx) >= tw || (horiz ? ly : ly + 1) >= th) continue;
+      const int i = ly * MT_TILE + lx, j = horiz ? i + 1 : i + MT_TILE;
+      const int vi = pol ? 255 - sv[i] : sv[i], vj = pol ? 255 - sv[j] : sv[j];
+      SmemWords<false> m{par[pol]};
+      mser_tree::connect<TKey>(m, TKey::make(vi, i), TKey::make(vj, j));
+    }
+    __syncthreads();
+    if (PROF && threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&prof[s], (unsigned long long)(t - t_prev)); t_prev = t; }
+  }
+  for (int i = threadIdx.x; i < MT_TILE * MT_TILE; i += THREADS) {
+    const int lx = i & (MT_TILE - 1), ly = i >> 6;
+    if (lx >= tw || ly >= th) continue;
+    const uint32_t pi = (uint32_t)(y0 + ly) * W + x0 + lx;
+    out[pi] = par[0][i]; out[Nimg + pi] = par[1][i];
+  }
+}
+#define SEQ8_SMEM (2 * MT_TILE * MT_TILE * 4 + MT_TILE * MT_TILE + 2 * 64 * BT)
+template <int T, bool P> static void launch8(dim3 g, const uint8_t* img, int W, int H, uint32_t* out, unsigned long long* prof) {
+  cudaFuncSetAttribute(k_tiles_seq8<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ8_SMEM);
+  k_tiles_seq8<T, P><<<g, T, SEQ8_SMEM>>>(img, W, H, out, prof);
+}
+
 // ---- host: canonical form of one tile's tree ---------------------------------------------------------------------------------------
 static void canon(const std::vector<uint32_t>& out, const std::vector<uint8_t>& img, int W, int H, int tx, int ty, int pol, std::vector<int>& A, std::vector<int>& B) {
   const int x0 = tx * MT_TILE, y0 = ty * MT_TILE, tw = std::min(MT_TILE, W - x0), th = std::min(MT_TILE, H - y0);
@@ -165,18 +276,11 @@ int main(int argc, char** argv) {
   cudaMemcpy(d_img, img.data(), N, cudaMemcpyHostToDevice);
   dim3 g((W + 63) / 64, (H + 63) / 64);
   struct V { const char* name; Launch fn; } vs[] = {
-      {"shipped: 256 threads, 12 cooperative stages", launch<256, 0, 0, false, false>},
-      {"seq 4x4, 512 threads", launch<512, 2, 0, false, false>},
-      {"seq 4x4, 512, middle edge first from stage 4", launch<512, 2, 0, false, false, 4>},
-      {"seq 4x4, 512, middle edge first from stage 6", launch<512, 2, 0, false, false, 6>},
-      {"seq 4x4, 512, middle edge first from stage 8", launch<512, 2, 0, false, false, 8>},
-      {"seq 4x4, 512, middle edge first from stage 10", launch<512, 2, 0, false, false, 10>},
-      {"seq 4x4, 512, k-major task order", launch<512, 2, 0, false, false, 12, true>},
-      {"seq 4x4, 512, k-major, middle first from 6", launch<512, 2, 0, false, false, 6, true>},
-      {"seq 4x4, 256, middle first from 6", launch<256, 2, 0, false, false, 6>},
-      {"seq 4x4, 1024 threads", launch<1024, 2, 0, false, false>},
-      {"seq 4x4, 1024, middle first from 6", launch<1024, 2, 0, false, false, 6>},
-      {"seq 8x8, 512, middle first from 6", launch<512, 3, 0, false, false, 6>},
+      {"shipped round-2a: 256 threads, 12 cooperative stages", launch<256, 0, 0, false, false>},
+      {"seq 4x4 by connect(), 512 threads", launch<512, 2, 0, false, false>},
+      {"seq 8x8 sorted union-find, 512 threads", launch8<512, false>},
+      {"seq 8x8 sorted union-find, 256 threads", launch8<256, false>},
+      {"seq 8x8 sorted union-find, 128 threads", launch8<128, false>},
   };
   std::vector<uint32_t> ref, out(2 * N);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -205,10 +309,10 @@ int main(int argc, char** argv) {
   // per-stage share of the shipped kernel and of the 4x4 variant (cycles of thread 0 between barriers, summed over the CTAs)
   for (int which = 0; which < 2; which++) {
     cudaMemset(d_prof, 0, 16 * 8);
-    if (which == 0) launch<512, 2, 0, false, true>(g, d_img, W, H, d_out, d_prof); else launch<512, 2, 0, false, true, 6>(g, d_img, W, H, d_out, d_prof);
+    if (which == 0) launch<512, 2, 0, false, true>(g, d_img, W, H, d_out, d_prof); else launch8<512, true>(g, d_img, W, H, d_out, d_prof);
     unsigned long long p[16]; cudaMemcpy(p, d_prof, sizeof p, cudaMemcpyDeviceToHost);
     double tot = 0; for (int s = 0; s < 13; s++) tot += (double)p[s];
-    printf("%s stage cycles per CTA:", which ? "seq 4x4, middle first from 6 (512)" : "seq 4x4 (512)");
+    printf("%s stage cycles per CTA:", which ? "seq 8x8 sorted union-find (512)" : "seq 4x4 (512)");
     printf("  [seq] %.0f (%.0f%%)", (double)p[12] / (g.x * g.y), 100.0 * p[12] / tot);
     for (int s = 0; s < 12; s++) printf("  [%d] %.0f (%.0f%%)", s, (double)p[s] / (g.x * g.y), 100.0 * p[s] / tot);
     printf("\n");
