@@ -420,13 +420,13 @@ def roofline_from_profile(prof, w, h, regions, peaks, steps, mser_regions=0.0):
         gb = 30.0 * 2 * w * h
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2c_traffic.json")) as f:
                 traffic = json.load(f).get("component_tree_%dx%d" % (w, h))
         except Exception:
             pass
         rl = {"bound": "hbm", "kernel": "component tree of one image, both polarities: " + " + ".join(sorted(k.split("<")[0] for k in tree)),
               "achieved": gb / 1e9 / (ms_group / 1e3), "peak": peaks["hbm"], "unit": "GB/s", "frac": gb / 1e9 / (ms_group / 1e3) / peaks["hbm"],
-              "traffic": traffic, "traffic_src": "dram__bytes_read.sum + dram__bytes_write.sum of the five kernels, ncu --set full (profiles/r2_full_tree.md, profiles/r2_traffic.json)",
+              "traffic": traffic, "traffic_src": "dram__bytes_read.sum + dram__bytes_write.sum of the five kernels, ncu --set full (profiles/r2c_full_tree.md, profiles/r2c_traffic.json)",
               "algorithmic_bytes": gb, "ms_per_launch_group": ms_group, "launches_per_group": sum(v[0] for v in tree.values()) / max(1, groups),
               "top_kernel": {"name": name, "ms_per_launch": ms / max(1, n_launch), "algorithmic_bytes": 14.0 * w * h,
                              "achieved_GBps": 14.0 * w * h / 1e9 / (ms / 1e3 / max(1, n_launch)),

@@ -1,15 +1,7 @@
-MB2_RANSAC_TRACE=1 python - <<'P' 2>&1 | tail -12
-import sys, time
-sys.path.insert(0, '.')
-import torch, bench
-import mods_b200 as mb
-w, h = 4096, 3072
-pairs = bench.make_pairs(w, h, 1, seed0=1)
-ctx = mb.Context(0)
-cfg = mb.PairConfig.default(); cfg.use_mser = 1
-a, b = (torch.from_numpy(x).cuda() for x in pairs[0])
-for it in range(3):
-    t0 = time.perf_counter()
-    res, _ = ctx.mods_pair(a, b, cfg, shape1=(h, w), shape2=(h, w))
-    print("pair %.1f ms: detect %.1f match %.1f dup %.1f ransac %.1f" % (1e3 * (time.perf_counter() - t0), res.ms_detect_describe, res.ms_match, res.ms_duplicate, res.ms_ransac), flush=True)
-P
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/s3_final_tests.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/s3_final_ref.json 2> gpurun_out/s3_final_ref.err
+python bench.py > gpurun_out/s3_final_bench.json 2> gpurun_out/s3_final_bench.err
+bash tools/ncu_capture_r2.sh r2c > gpurun_out/s3_final_ncu.log 2>&1
+cat gpurun_out/s3_final_tests.log; tail -c 600 gpurun_out/s3_final_ref.json; python -c "
+import json; d=json.loads(open('gpurun_out/s3_final_bench.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['latency_ms_per_pair'], d['roofline']['frac'], d['roofline']['ms_per_launch_group'], d['parity']['ok'], d['clocks'])"
+tail -3 gpurun_out/s3_final_ncu.log
