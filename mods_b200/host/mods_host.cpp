@@ -654,8 +654,11 @@ int loransac_core(mb2_ctx* ctx, const double* frames, int tent_size, const RANSA
     if ((int)verified.size() < MIN_POINTS) verified.clear();
     return (int)verified.size();
   }
+  static const bool vtrace = getenv("MB2_VERIFY_TRACE") != nullptr;   // diagnostics: wall time of the legs of the verification stage
+  const double tv0 = now_ms();
   int I = mb2_ransac_h(ctx, u.data(), tent_size, pars.err_threshold * pars.err_threshold, pars.confidence, max_samples,
                        (int)pars.errorType, pars.doSymmCheck, seed, Hloran, inl.data(), data_out, &J);
+  const double tv1 = now_ms();
   if (I < 0) return 0;
   for (int i = 0; i < tent_size; i++) if (inl[i] || pars.justMarkOutliers) verified.push_back(i);
   // H = inv(Hloran^T) (matching.cpp:920-938)
@@ -684,6 +687,7 @@ int loransac_core(mb2_ctx* ctx, const double* frames, int tent_size, const RANSA
     }
     if (corr_numb < MIN_POINTS) verified.clear();
   }
+  const double tv2 = now_ms();
   // H_LAF_check (matching.cpp:251-309): three points per local affine frame scored with HDsSymMax in one batch
   const double affineFerror = 3.0 * pars.HLAFCoef * pars.err_threshold;
   if (affineFerror > 0 && !verified.empty()) {
@@ -709,6 +713,7 @@ int loransac_core(mb2_ctx* ctx, const double* frames, int tent_size, const RANSA
     }
     verified.swap(good);
   }
+  if (vtrace) fprintf(stderr, "[verify] %d tentatives: mb2_ransac_h %.2f ms, inv(H) + NaiveHCheck %.2f ms, H_LAF_check %.2f ms\n", tent_size, tv1 - tv0, tv2 - tv1, now_ms() - tv2);
   if ((int)verified.size() < MIN_POINTS) verified.clear();
   return (int)verified.size();
 }
