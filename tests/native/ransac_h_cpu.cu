@@ -56,3 +56,7 @@ extern "C" int t_ransac_h(score_fn fn, const double* u, int len, double th, doub
   data_out[3] = (int)g_calls;
   return r;
 }
+
+// the least-squares set-up alone (ransac_common.hpp: u2h), for the comparison with the compiled reference's u2h at sizes up to the
+// chunked / pooled large-set path
+extern "C" void t_u2h(const double* u, const int* inl, int len, double* H) { mb2_ransac_common::u2h(u, inl, len, H); }

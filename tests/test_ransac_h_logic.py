@@ -84,3 +84,25 @@ def test_h_logic_parameter_sweep_vs_reference_build(hlogic, reference, th, conf,
                 b = hlogic(u, seed=seed, errorType=et, th=th, conf=conf, max_sam=max_sam)
                 assert (a["I"], a["samples"], a["lo"], a["rejected"]) == (b["I"], b["samples"], b["lo"], b["rejected"]), (n, seed, et)
                 assert np.array_equal(a["inl"], b["inl"])
+
+
+@pytest.mark.parametrize("n", [8, 100, 4096, 4097, 9000, 60000])
+def test_u2h_vs_reference_build(hlogic, reference, n):
+    """Least-squares set-up (Htools.c:98-130) on n listed correspondences: up to 4096 the covariance is the reference's single serial chain
+    (bit for bit the same matrix; H differs only by the eigen-solver: Jacobi here, LAPACK dsyev there); above, the sums run in fixed chunks
+    of 2048 on the host pool (dense gather, square roots in parallel, serial coordinate / distance sums) -- H must agree to 1e-8."""
+    lib = C.CDLL(os.path.join(HERE, "native", "libransac_h_cpu.so"))
+    u = scene(100 + n, max(n * 5 // 4, n + 3), 1.0, noise=0.7)
+    idx = np.ascontiguousarray(np.sort(np.random.default_rng(n).permutation(len(u))[:n]).astype(np.int32))
+    H = np.zeros(9)
+    lib.t_u2h(_p(u), _p(idx), C.c_int(n), _p(H))
+    Hr = reference.u2h(u, idx)
+    a, b = H / np.linalg.norm(H), Hr / np.linalg.norm(Hr)
+    if np.dot(a, b) < 0:
+        b = -b
+    assert np.abs(a - b).max() < 1e-8
+    # and the result does not depend on the number of pool threads (fixed chunk boundaries): one more call, another thread count is not
+    # selectable inside one process, so at least repeatability
+    H2 = np.zeros(9)
+    lib.t_u2h(_p(u), _p(idx), C.c_int(n), _p(H2))
+    assert np.array_equal(H, H2)
