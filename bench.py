@@ -301,7 +301,8 @@ C4_WORKLOAD = ("C4: %dx%d synthetic pair, full SIFT view tiers of iters_mods_cvi
 
 
 def run_ours_c4(args, rank, world, local_rank):
-    """BASELINE config 4 through mb2_views_sharded_pair (libmods_host.so): strong scaling of ONE pair over the ranks."""
+    """BASELINE config 4 through the view-sharded driver (libmods_host.so): K pairs through mb2_views_sharded_pairs (throughput; strong scaling: the
+    same K pairs on every world size) and single pairs through mb2_views_sharded_pair (latency)."""
     import torch
     import torch.distributed as dist
     import mods_b200 as mb
@@ -323,7 +324,9 @@ def run_ours_c4(args, rank, world, local_rank):
 
     step_ms = []   # host clock around every call (diagnostics: warm-up, resident-image steps, host-image steps, profiled step)
 
-    def timed(imgs, steps):
+    def timed(imgs, steps, dataset=False):
+        """dataset: ONE mb2_views_sharded_pairs call over `steps` pairs (pair k verified by rank k % world on a helper thread while all ranks go on
+        with pair k + 1); otherwise `steps` separate mb2_views_sharded_pair calls (latency of one pair, verification on rank 0)."""
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -332,7 +335,12 @@ def run_ours_c4(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         out = []
-        for _ in range(steps):
+        if dataset:
+            t0 = time.perf_counter()
+            rs, vs, ds, ss = ctx.views_sharded_pairs([imgs] * steps, cfg, comm, rank, world, shapes=[((h, w), (h, w))] * steps, capacity=1 << 18)
+            out = [(rs[k], vs[k], ds[k], ss[k]) for k in range(steps)]
+            step_ms.append(round((time.perf_counter() - t0) * 1e3, 1))
+        for _ in range(0 if dataset else steps):
             t0 = time.perf_counter()
             out.append(ctx.views_sharded_pair(imgs[0], imgs[1], cfg, comm, rank, world, shape1=(h, w), shape2=(h, w), capacity=1 << 18))
             step_ms.append(round((time.perf_counter() - t0) * 1e3, 1))
@@ -346,12 +354,14 @@ def run_ours_c4(args, rank, world, local_rank):
         return ms, out, ctx.launches - l0
 
     timed(dev, max(3, args.warmup))
+    timed(pin, max(3, args.warmup), dataset=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, out_dev, launches = timed(dev, args.steps)
-    ms_e2e, out_e2e, _ = timed(pin, args.steps)
+    ms_dev, out_dev, launches = timed(dev, args.steps, dataset=True)
+    ms_e2e, out_e2e, _ = timed(pin, args.steps, dataset=True)
     clocks = sampler.stop() if rank == 0 else None
+    ms_one, out_one, _ = timed(dev, min(args.steps, 3))   # latency of one pair: separate calls, verification on rank 0
     prof = None
     if rank == 0:
         ctx.profile_begin()
@@ -364,9 +374,13 @@ def run_ours_c4(args, rank, world, local_rank):
         dist.barrier(); ctx.dist_comm_destroy(comm); dist.destroy_process_group()
     if rank != 0:
         return
-    res, ver, dig, st = out_dev[-1]
+    res, ver, dig, st = out_one[-1]
     if not (res.regions1 > 0 and res.tentatives > 0 and res.verified > 0):
         raise SystemExit("bench.py: the C4 pair came back empty")
+    f = lambda r: (r.regions1, r.regions2, r.tentatives, r.unique_tentatives, r.ransac_inliers, r.verified)
+    for o in out_dev + out_e2e:   # the dataset call gives every pair the result of the single call, on every rank
+        if f(o[0]) != f(res) or o[2] != dig:
+            raise SystemExit("bench.py: the dataset call differs from the single-pair call: %r vs %r" % (f(o[0]), f(res)))
     peaks = load_peaks()
     K = args.steps
     v = K / (ms_dev / 1e3); e = K / (ms_e2e / 1e3)
@@ -376,13 +390,16 @@ def run_ours_c4(args, rank, world, local_rank):
            "data": "synthetic (numpy PCG64 blob images + ground-truth homography warp, mods_b200/synth.py)",
            "config": {"workload": C4_WORKLOAD % (w, h), "generator": GENERATOR, "views_per_image": [len(hess), len(mser)], "regions": [res.regions1, res.regions2],
                       "tentatives": res.tentatives, "unique": res.unique_tentatives, "verified": res.verified, "parallelism": "views sharded over ranks (longest "
-                      "processing time first), ONE ncclAllGather of device-resident region records + count / tentative exchanges; verification on rank 0",
+                      "processing time first), ONE ncclAllGather of device-resident region records + count / tentative exchanges; `value` / `e2e`: ONE "
+                      "mb2_views_sharded_pairs call over the K pairs -- pair k is verified by rank k % world on a helper thread while all ranks go on with pair "
+                      "k + 1; `single_pair`: separate mb2_views_sharded_pair calls, verification on rank 0",
+                      "single_pair": {"ms_per_pair": ms_one / max(1, len(out_one)), "pairs_per_s": len(out_one) / (ms_one / 1e3)},
                       "l2": "176 view pipelines per step, working set far beyond the 126 MB L2",
                       "digest": ["%016x" % d for d in dig], "digest_identical_on_all_ranks": all(d == dig for d in digs),
-                      "allgather_bytes_per_rank": st["allgather_bytes_per_rank"], "verify_ms_rank0": {"duplicate_filter": res.ms_duplicate, "lo_ransac_and_laf": res.ms_ransac}, "step_ms_rank0": step_ms, "steps_rank0_ms": [[round(o[3][k], 1) for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")] for o in out_dev + out_e2e], "rank0_ms": {k: st[k] for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")}},
+                      "allgather_bytes_per_rank": st["allgather_bytes_per_rank"], "verify_ms_rank0": {"duplicate_filter": res.ms_duplicate, "lo_ransac_and_laf": res.ms_ransac}, "step_ms_rank0": step_ms, "steps_rank0_ms": [[round(o[3][k], 1) for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")] for o in out_dev + out_one], "rank0_ms": {k: st[k] for k in ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify")}},
            "matched_kpts_per_s": res.verified * v,
            "e2e": {"value": e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * w * h * 4, "d2h_bytes_per_step": int(res.tentatives * 56 + (res.regions1 + res.regions2) * 184 + res.verified * 32),
-                   "ms_per_step": ms_e2e / K, "entry": "mb2_views_sharded_pair (libmods_host.so), pinned host images on every rank, verified list on the host"},
+                   "ms_per_step": ms_e2e / K, "entry": "mb2_views_sharded_pairs (libmods_host.so), pinned host images on every rank, results on every rank, verified lists on the verifying rank"},
            "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None, "parity": {"checked": False, "note": "C4 parity: tests/test_gpu_fullsize.py "
                       "(cat pair, 11-view tier vs the compiled reference) and the digest, identical for every world size"}}
     if prof:

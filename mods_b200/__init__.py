@@ -502,6 +502,30 @@ class Context:
         stats = dict(zip(("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify", "allgather_bytes_per_rank", "regions", "units"), list(st)))
         return res, (out[:min(n, capacity)] if capacity else None), [int(v) for v in dig], stats
 
+    def views_sharded_pairs(self, pairs, cfg, comm=None, rank=0, world=1, shapes=None, capacity=0):
+        """A list of pairs through the view-sharded dataset call (mb2_views_sharded_pairs): pair k is verified by rank k % world while all
+        ranks go on with pair k + 1.  Returns ([PairResult] -- complete on every rank --, [verified rows or None] -- filled on rank
+        k % world --, [digest (4 ints)], [stats dict])."""
+        n = len(pairs)
+        P = C.c_void_p * max(1, n); I = C.c_int * max(1, n)
+        p1, p2, w1, h1, w2, h2 = P(), P(), I(), I(), I(), I()
+        for k, (a, b) in enumerate(pairs):
+            (ha, wa), (hb, wb) = shapes[k] if shapes is not None else (a.shape, b.shape)
+            p1[k] = _ptr(a).value; p2[k] = _ptr(b).value
+            w1[k], h1[k], w2[k], h2[k] = wa, ha, wb, hb
+        res = (PairResult * max(1, n))()
+        dig = (C.c_ulonglong * (4 * max(1, n)))(); st = (C.c_double * (8 * max(1, n)))()
+        outs = [np.zeros((capacity, 4)) for _ in range(n)] if capacity else None
+        vo = P(*[o.ctypes.data for o in outs]) if capacity and n else None
+        caps = I(*([capacity] * n)) if capacity and n else None
+        f = host_lib().mb2_views_sharded_pairs
+        self._check(f(self.h, C.c_void_p(comm or 0), C.c_int(rank), C.c_int(world), C.c_int(n), p1, w1, h1, p2, w2, h2, C.byref(cfg), res, vo, caps, dig, st),
+                    "views_sharded_pairs")
+        names = ("ms_views", "ms_gather", "ms_match", "ms_tentative_gather", "ms_verify", "allgather_bytes_per_rank", "regions", "units")
+        results = [res[k] for k in range(n)]
+        ver = [outs[k][:min(results[k].verified, capacity)] if (k % world) == rank else None for k in range(n)] if capacity else None
+        return results, ver, [[int(v) for v in dig[4 * k:4 * k + 4]] for k in range(n)], [dict(zip(names, list(st[8 * k:8 * k + 8]))) for k in range(n)]
+
     def dist_comm_create(self, rank, world):
         """ncclComm_t for the view-sharded driver: rank 0 draws the unique id, torch.distributed (already initialised by the caller) hands
         it to every rank.  Returns an opaque handle for views_sharded_pair / dist_comm_destroy."""

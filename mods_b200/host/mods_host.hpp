@@ -273,6 +273,13 @@ int mb2_dist_comm_create(mb2_ctx* ctx, int rank, int world, const unsigned char*
 void mb2_dist_comm_destroy(void* comm);
 int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
                            const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity, unsigned long long* digest, double* stats);
+/* Dataset form: a list of independent pairs, views sharded over the ranks as above; pair k is VERIFIED by rank k % world on a helper thread
+ * while all ranks go on with the views of pair k + 1 (after the tentative exchange every rank holds all records and rows of the pair).
+ * res[k] is complete on every rank (one all-gather of the result records at the end); verified_out[k] on rank k % world only.
+ * digest: 4 x n_pairs, stats: 8 x n_pairs, both optional. */
+int mb2_views_sharded_pairs(mb2_ctx* ctx, void* comm, int rank, int world, int n_pairs, const float* const* img1, const int* w1, const int* h1,
+                            const float* const* img2, const int* w2, const int* h2, const mb2_pair_config* cfg, mb2_pair_result* res,
+                            double* const* verified_out, const int* capacity, unsigned long long* digest, double* stats);
 /* the unit plan on its own (checked without a GPU): cost of a view, longest-processing-time-first owners, offsets in the gathered buffer */
 double mb2_shard_view_cost(int w, int h, double tilt, double zoom);
 void mb2_shard_assign(const double* costs, int n_units, int world, int* owner);

@@ -17,8 +17,11 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -141,8 +144,14 @@ void mb2_dist_comm_destroy(void* comm) { if (comm && g_nccl.lib) g_nccl.CommDest
 // gathered region records and of the tentative rows -- identical on every rank and for every world size, which is what the tests
 // and bench.py assert.  stats (optional, 8 doubles): ms views, ms gather, ms match, ms tentative gather, ms verify, all-gather payload
 // bytes per rank, regions of both images, units of this rank.
-int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
-                           const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity, unsigned long long* digest, double* stats) {
+}  // extern "C"
+namespace {
+// What the verification stage needs of a pair, on the host: the 14-double frames of the tentatives and their sort keys.
+struct ShardFront { int T = 0; std::vector<double> frames, key; double t_start = 0, t_gather = 0, t_match = 0; };
+
+// Everything up to and including the tentative exchange; `verifier` = this rank will verify the pair (its frames are fetched).
+int sharded_front(mb2_ctx* ctx, void* comm, int rank, int world, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
+                  const mb2_pair_config* cfg, mb2_pair_result* res, unsigned long long* digest, double* stats, bool verifier, ShardFront& F) {
   if (!ctx || !img1 || !img2 || !cfg || !res || world < 1 || rank < 0 || rank >= world || (world > 1 && (!comm || !g_nccl.load()))) return MB2_ERR_ARG;
   std::memset(res, 0, sizeof *res);
   void* st = mb2_ctx_stream(ctx);
@@ -363,13 +372,13 @@ int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const 
     for (size_t i = 0; i < rows_all.size(); i++) { a ^= rb[i]; a *= 1099511628211ull; }
     digest[2] = a; digest[3] = (unsigned long long)res->tentatives;
   }
-  // ---- rank 0 verifies (mods.cpp:298-415)
+  // ---- frames of the tentatives for the rank that verifies (mods.cpp:298-415), straight from the device records (per detector: image-0 set
+  // x image-1 set); keys from the distances
   const double t_v0 = now_ms();
-  int k = 0;
-  if (rank == 0 && res->tentatives > 0) {
-    // frames of the tentatives straight from the device records (per detector: image-0 set x image-1 set); keys from the distances
+  F.T = 0;
+  if (verifier && res->tentatives > 0) {
     const int T = res->tentatives;
-    std::vector<double> frames((size_t)T * 14), key(T);
+    F.frames.resize((size_t)T * 14); F.key.resize(T);
     std::vector<int> qi(T), ti(T);
     int done = 0;
     for (int det = 0; det < (cfg->use_mser ? 2 : 1); det++) {
@@ -377,25 +386,123 @@ int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const 
       for (int i = done; i < T && (int)rows_all[(size_t)i * 8] == det; i++, n++) {
         const double* r = &rows_all[(size_t)i * 8];
         qi[i] = (int)r[1]; ti[i] = (int)r[2];
-        key[i] = std::fabs(std::sqrt((double)((float)r[5] / (float)r[6])));   // TentativeCorrespExt::ratio = sqrt(d1 / d2), matching.cpp:449
+        F.key[i] = std::fabs(std::sqrt((double)((float)r[5] / (float)r[6])));   // TentativeCorrespExt::ratio = sqrt(d1 / d2), matching.cpp:449
       }
-      const int rc = mb2_records_gather_frames(ctx, ordered[det].p, ordered[2 + det].p, qi.data() + done, ti.data() + done, n, frames.data() + (size_t)done * 14);
+      const int rc = mb2_records_gather_frames(ctx, ordered[det].p, ordered[2 + det].p, qi.data() + done, ti.data() + done, n, F.frames.data() + (size_t)done * 14);
       if (rc < 0) return rc;
       done += n;
     }
-    mb2_pair_result vr; std::memset(&vr, 0, sizeof vr);
-    k = mb2_host_verify(ctx, frames.data(), key.data(), T, cfg, &vr, verified_out, capacity);
-    if (k < 0) return k;
-    res->unique_tentatives = vr.unique_tentatives; res->ransac_inliers = vr.ransac_inliers; res->verified = vr.verified;
-    std::memcpy(res->H, vr.H, sizeof vr.H); res->ms_duplicate = vr.ms_duplicate; res->ms_ransac = vr.ms_ransac;
+    F.T = T;
   }
-  const double t_end = now_ms();
-  res->ms_detect_describe = t_gather - t_start; res->ms_match = t_match; res->ms_total = t_end - t_start;
+  F.t_start = t_start; F.t_gather = t_gather; F.t_match = t_match;
+  res->ms_detect_describe = t_gather - t_start; res->ms_match = t_match; res->ms_total = now_ms() - t_start;
   if (stats) {
-    stats[0] = t_views - t_start; stats[1] = t_gather - t_views; stats[2] = t_match; stats[3] = t_tgather; stats[4] = t_end - t_v0;
+    stats[0] = t_views - t_start; stats[1] = t_gather - t_views; stats[2] = t_match; stats[3] = t_tgather; stats[4] = now_ms() - t_v0;
     stats[5] = world > 1 ? (double)stride * REC : 0.0; stats[6] = res->regions1 + res->regions2; stats[7] = my_units;
   }
+  return MB2_OK;
+}
+
+// DuplicateFiltering + LORANSACFiltering of a pair's tentatives on context vctx (mb2_host_verify); fills the verification fields of res.
+int sharded_back(mb2_ctx* vctx, const mb2_pair_config* cfg, ShardFront& F, mb2_pair_result* res, double* verified_out, int capacity, double* stats) {
+  if (F.T <= 0) return 0;
+  const double t0 = now_ms();
+  mb2_pair_result vr; std::memset(&vr, 0, sizeof vr);
+  const int k = mb2_host_verify(vctx, F.frames.data(), F.key.data(), F.T, cfg, &vr, verified_out, capacity);
+  if (k < 0) return k;
+  res->unique_tentatives = vr.unique_tentatives; res->ransac_inliers = vr.ransac_inliers; res->verified = vr.verified;
+  std::memcpy(res->H, vr.H, sizeof vr.H); res->ms_duplicate = vr.ms_duplicate; res->ms_ransac = vr.ms_ransac;
+  if (stats) stats[4] += now_ms() - t0;
   return k;
+}
+}  // namespace
+
+extern "C" {
+int mb2_views_sharded_pair(mb2_ctx* ctx, void* comm, int rank, int world, const float* img1, int w1, int h1, const float* img2, int w2, int h2,
+                           const mb2_pair_config* cfg, mb2_pair_result* res, double* verified_out, int capacity, unsigned long long* digest, double* stats) {
+  ShardFront F;
+  const int rc = sharded_front(ctx, comm, rank, world, img1, w1, h1, img2, w2, h2, cfg, res, digest, stats, rank == 0, F);
+  if (rc < 0) return rc;
+  const int k = rank == 0 ? sharded_back(ctx, cfg, F, res, verified_out, capacity, stats) : 0;
+  if (k < 0) return k;
+  res->ms_total = now_ms() - F.t_start;
+  return k;
+}
+
+// A list of independent pairs (a dataset run), views sharded over the ranks as above, with the part that does NOT shard inside one pair --
+// duplicate filter + LO-RANSAC + LAF checks, 250 ms of a C4 pair -- spread over the ranks pair by pair and taken off the critical path:
+// after the tentative exchange every rank holds all records and all tentative rows of pair k, so pair k is verified by rank k % world,
+// on a helper thread and context of that rank, while all ranks go on with the views of pair k + 1.  At the end the small result records
+// are all-gathered: res[k] is complete on EVERY rank; verified_out[k] (optional) is filled on rank k % world only.
+// digest: 4 x n_pairs, stats: 8 x n_pairs (both optional).  Results are identical to calling mb2_views_sharded_pair pair by pair.
+int mb2_views_sharded_pairs(mb2_ctx* ctx, void* comm, int rank, int world, int n_pairs, const float* const* img1, const int* w1, const int* h1,
+                            const float* const* img2, const int* w2, const int* h2, const mb2_pair_config* cfg, mb2_pair_result* res,
+                            double* const* verified_out, const int* capacity, unsigned long long* digest, double* stats) {
+  if (!ctx || n_pairs < 0 || !cfg || !res || world < 1 || rank < 0 || rank >= world || (n_pairs > 0 && (!img1 || !img2 || !w1 || !h1 || !w2 || !h2))) return MB2_ERR_ARG;
+  if (world > 1 && (!comm || !g_nccl.load())) return MB2_ERR_ARG;
+  mb2_ctx* vctx = mb2_mods_sibling(ctx, 4);   // [0..2] run views next to ctx; [4] verifies
+  if (!vctx) return MB2_ERR_CUDA;
+  std::mutex m;
+  std::condition_variable cv;
+  std::deque<std::pair<int, std::unique_ptr<ShardFront> > > q;
+  bool done = false;
+  int rc = MB2_OK;
+  std::thread back([&] {
+    for (;;) {
+      std::pair<int, std::unique_ptr<ShardFront> > item;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return done || !q.empty(); });
+        if (q.empty()) return;
+        item = std::move(q.front()); q.pop_front();
+      }
+      cv.notify_all();
+      const int k = item.first;
+      const int r = sharded_back(vctx, cfg, *item.second, &res[k], verified_out ? verified_out[k] : nullptr, capacity ? capacity[k] : 0, stats ? stats + 8 * k : nullptr);
+      if (r < 0) { std::lock_guard<std::mutex> lk(m); if (rc >= 0) rc = r; }
+    }
+  });
+  for (int k = 0; k < n_pairs; k++) {
+    std::unique_ptr<ShardFront> F(new ShardFront);
+    const bool mine = (k % world) == rank;
+    const int r = sharded_front(ctx, comm, rank, world, img1[k], w1[k], h1[k], img2[k], w2[k], h2[k], cfg, &res[k], digest ? digest + 4 * k : nullptr,
+                                stats ? stats + 8 * k : nullptr, mine, *F);
+    if (r < 0) { std::lock_guard<std::mutex> lk(m); if (rc >= 0) rc = r; break; }   // a failed collective fails on every rank alike
+    if (!mine) continue;
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return q.size() < 2; });   // at most two of this rank's pairs waiting for verification
+    q.emplace_back(k, std::move(F));
+    lk.unlock();
+    cv.notify_all();
+  }
+  { std::lock_guard<std::mutex> lk(m); done = true; }
+  cv.notify_all();
+  back.join();
+  // every rank learns every pair's result: one all-gather of the result records, pair k taken from rank k % world
+  if (world > 1 && n_pairs > 0) {
+    int bad = rc < 0 ? 1 : 0;
+    const size_t bytes = (size_t)n_pairs * sizeof(mb2_pair_result) + 8;
+    ShardScratch& S = *scratch_of(ctx);
+    S.d_rows.ctx = ctx;
+    if (!S.d_rows.reserve(bytes * (world + 1))) return MB2_ERR_CUDA;
+    unsigned char* d_mine = (unsigned char*)S.d_rows.p; unsigned char* d_all = d_mine + bytes;
+    std::vector<unsigned char> h(bytes * world, 0);
+    std::memcpy(h.data(), res, (size_t)n_pairs * sizeof(mb2_pair_result));
+    std::memcpy(h.data() + (size_t)n_pairs * sizeof(mb2_pair_result), &bad, sizeof bad);
+    mb2_dev_copy(ctx, d_mine, h.data(), bytes, 0);
+    if (g_nccl.AllGather(d_mine, d_all, bytes, NCCL_INT8, (ncclComm_h)comm, mb2_ctx_stream(ctx)) != 0) return MB2_ERR_CUDA;
+    mb2_dev_copy(ctx, h.data(), d_all, bytes * world, 1);
+    if (mb2_ctx_sync(ctx) != MB2_OK) return MB2_ERR_CUDA;
+    for (int r = 0; r < world; r++) {
+      int b = 0;
+      std::memcpy(&b, h.data() + (size_t)r * bytes + (size_t)n_pairs * sizeof(mb2_pair_result), sizeof b);
+      if (b && rc >= 0) rc = MB2_ERR_CUDA;   // some rank failed: the call fails everywhere
+    }
+    for (int k = 0; k < n_pairs; k++) {
+      std::memcpy(&res[k], h.data() + (size_t)(k % world) * bytes + (size_t)k * sizeof(mb2_pair_result), sizeof(mb2_pair_result));
+    }
+  }
+  return rc < 0 ? rc : n_pairs;
 }
 
 }  // extern "C"

@@ -100,6 +100,26 @@ def test_views_sharded_driver_equals_pair_driver(ctx):
     assert dig == dig3 and st["units"] == 12
 
 
+def test_views_sharded_dataset_call_equals_single_calls(ctx):
+    """mb2_views_sharded_pairs (pair k verified on a helper thread / context while pair k + 1 is in its views) == mb2_views_sharded_pair per pair:
+    counts, H, verified lists and digests, for pairs of different sizes."""
+    import mods_b200 as mb
+    from synth import blob_image, warp_image, gt_homography
+    pairs = []
+    for k in range(3):
+        A = blob_image(480 + 32 * k, 360 + 16 * k, seed=71 + k, n_blobs=450 + 60 * k)
+        pairs.append((A, warp_image(A, gt_homography(A.shape[1], A.shape[0]), seed=81 + k)))
+    cfg = mb.PairConfig.default(); cfg.use_mser = 1; cfg.seed = 7
+    cfg.set_views([(1.0, 0.0, 1.0, 0.2), (2.0, 0.0, 1.0, 0.2), (2.0, np.pi / 2, 1.0, 0.2)], [(1.0, 0.0, 1.0, 0.8)])
+    single = [ctx.views_sharded_pair(a, b, cfg, capacity=1 << 14) for a, b in pairs]
+    res, ver, dig, st = ctx.views_sharded_pairs(pairs, cfg, capacity=1 << 14)
+    f = lambda r: (r.regions1, r.regions2, r.mser_regions1, r.mser_regions2, r.tentatives, r.mser_tentatives, r.unique_tentatives, r.ransac_inliers, r.verified)
+    for (r1, v1, d1, _), r2, v2, d2 in zip(single, res, ver, dig):
+        assert f(r1) == f(r2) and r1.verified > 50
+        assert np.array_equal(v1, v2) and np.array_equal(np.array(r1.H), np.array(r2.H)) and d1 == d2
+    assert ctx.views_sharded_pairs([], cfg)[0] == []
+
+
 def test_mods_multi_and_feature_cache_callers(ctx, tmp_path):
     """mods_multi.cpp (1-to-N, query described once) == mb2_mods_pair per pair; extract_features + the read_pre_extracted flow: the same
     tentatives from the cache files (descriptors are integers; positions carry the 6 significant digits of the reference's text format)."""

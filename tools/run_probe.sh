@@ -1,7 +1,4 @@
-python -m pytest tests -m gpu -x -q -k "ransac or fullsize or mods_pair or verif" 2>&1 | tail -2
-MB2_RANSAC_TRACE=1 MB2_VERIFY_TRACE=1 python bench.py --workload c4 --steps 2 --warmup 1 2>gpurun_out/s3_c4_trace.err >gpurun_out/s3_c4_b.json; grep "verify\|mb2_ransac_h" gpurun_out/s3_c4_trace.err | tail -2
-python -c "
-import json; d=json.loads(open('gpurun_out/s3_c4_b.json').read().strip().splitlines()[-1]); print('c4', d['value'], d['ms_per_step'], d['config']['digest'], d['config']['rank0_ms'])"
-python bench.py > gpurun_out/s3_bench4.json 2>gpurun_out/s3_bench4.err
-python -c "
-import json; d=json.loads(open('gpurun_out/s3_bench4.json').read().strip().splitlines()[-1]); print('c3', d['value'], d['e2e']['value'], d['latency_ms_per_pair'], d['stage_ms'], d['parity']['ok'])"
+python bench.py --workload c4 --steps 6 --warmup 3 > gpurun_out/s3_c4_ds_n1.json 2> gpurun_out/s3_c4_ds_n1.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --workload c4 --steps 6 --warmup 3 > gpurun_out/s3_c4_ds_n2.json 2> gpurun_out/s3_c4_ds_n2.err; tail -3 gpurun_out/s3_c4_ds_n2.err
+for f in s3_c4_ds_n1 s3_c4_ds_n2; do python -c "
+import json; d=json.loads(open('gpurun_out/$f.json').read().strip().splitlines()[-1]); print('$f', d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['single_pair'], d['config']['digest'], d['config']['digest_identical_on_all_ranks'], d['config']['verified'])"; done
