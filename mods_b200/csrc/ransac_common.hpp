@@ -167,42 +167,35 @@ inline void smallest_eigvec9(const double* C, double* v) {
 }
 
 // utools.c:7-50
-// Scratch of the large-set path of normu / u2h (per calling thread): x1 y1 x2 y2 d1 d2 of every listed correspondence, in list order.
+// Scratch of the large-set path of normu (per calling thread): the two distances of every listed correspondence, in list order.
 inline std::vector<double>& normu_scratch() { static thread_local std::vector<double> g; return g; }
 constexpr int NORMU_BIG = 4096;
 inline void normu(const double* u, const int* inl, int len, double* A1, double* A2) {
   for (int j = 0; j < 3; j++) { A1[j] = 0; A2[j] = 0; }
+  for (int j = 0; j < len; j++) { const double* p = u + 6 * inl[j]; A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[3]; A2[2] += p[4]; }
+  if (len > 0) for (int i = 1; i < 3; i++) { A1[i] /= len; A2[i] /= len; }
   if (len > NORMU_BIG) {
-    // Large inlier sets (the LO steps of a view-sharded pair run on 200 k inliers).  The reference's four coordinate sums and two distance
-    // sums are single serial chains and stay that: same values added in the same order.  Everything around them -- the gather of the listed
-    // correspondences into a dense array, the (independent, correctly rounded) square roots -- runs in chunks on the host pool, so the
-    // serial loops stream over contiguous memory at the latency of one addition per element.
-    std::vector<double>& g = normu_scratch();
-    if (g.size() < (size_t)6 * len) g.resize((size_t)6 * len);
-    double* G = g.data();
+    // Large inlier sets (the LO steps of a view-sharded pair run on 200 k inliers): the square roots -- independent, correctly rounded -- are
+    // taken in chunks on the host pool, the two sums stay single serial chains over the stored distances.  Same values, same additions.
+    // (Measured and dropped: also gathering the coordinates into a dense array on the pool, so that the serial coordinate sums stream over
+    // contiguous memory -- 3.4 ms per call at 200 k inliers against 2.2 ms: the serial thread then reads 10 MB written by other cores.)
+    std::vector<double>& d = normu_scratch();
+    if (d.size() < (size_t)2 * len) d.resize((size_t)2 * len);
+    double* D = d.data();
     const int CHN = 8192, nch = (len + CHN - 1) / CHN;
     mb2par::parallel_chunks(nch, [&](int ck) {
       const int lo = ck * CHN, hi = std::min(len, lo + CHN);
-      for (int j = lo; j < hi; j++) { const double* p = u + 6 * inl[j]; double* q = G + 6 * (size_t)j; q[0] = p[0]; q[1] = p[1]; q[2] = p[3]; q[3] = p[4]; }
-    });
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (int j = 0; j < len; j++) { const double* q = G + 6 * (size_t)j; s0 += q[0]; s1 += q[1]; s2 += q[2]; s3 += q[3]; }
-    A1[1] = s0 / len; A1[2] = s1 / len; A2[1] = s2 / len; A2[2] = s3 / len;
-    mb2par::parallel_chunks(nch, [&](int ck) {
-      const int lo = ck * CHN, hi = std::min(len, lo + CHN);
       for (int j = lo; j < hi; j++) {
-        double* q = G + 6 * (size_t)j;
-        const double a = q[0] - A1[1], b = q[1] - A1[2], c = q[2] - A2[1], e = q[3] - A2[2];
-        q[4] = std::sqrt(a * a + b * b);
-        q[5] = std::sqrt(c * c + e * e);
+        const double* p = u + 6 * inl[j];
+        const double a = p[0] - A1[1], b = p[1] - A1[2], c = p[3] - A2[1], e = p[4] - A2[2];
+        D[2 * (size_t)j] = std::sqrt(a * a + b * b);
+        D[2 * (size_t)j + 1] = std::sqrt(c * c + e * e);
       }
     });
-    double d1 = 0, d2 = 0;
-    for (int j = 0; j < len; j++) { d1 += G[6 * (size_t)j + 4]; d2 += G[6 * (size_t)j + 5]; }
-    A1[0] = d1; A2[0] = d2;
+    double s1 = A1[0], s2 = A2[0];
+    for (int j = 0; j < len; j++) { s1 += D[2 * (size_t)j]; s2 += D[2 * (size_t)j + 1]; }
+    A1[0] = s1; A2[0] = s2;
   } else {
-    for (int j = 0; j < len; j++) { const double* p = u + 6 * inl[j]; A1[1] += p[0]; A1[2] += p[1]; A2[1] += p[3]; A2[2] += p[4]; }
-    if (len > 0) for (int i = 1; i < 3; i++) { A1[i] /= len; A2[i] /= len; }
     for (int j = 0; j < len; j++) {
       const double* p = u + 6 * inl[j];
       double a = p[0] - A1[1], b = p[1] - A1[2];
@@ -263,7 +256,6 @@ inline void u2h(const double* u, const int* inl, int len, double* H) {
   const int CH = 2048;
   const int nchunks = len <= 2 * CH ? 1 : (len + CH - 1) / CH;
   std::vector<double> part((size_t)nchunks * 45, 0.0);
-  const double* G = len > NORMU_BIG ? normu_scratch().data() : nullptr;
   mb2par::parallel_chunks(nchunks, [&](int ck) {
     const int lo = nchunks == 1 ? 0 : ck * CH, hi = nchunks == 1 ? len : std::min(len, lo + CH);
     // Row 2i has entries only at columns S0 = {0, 2, 3, 5, 6, 8} (b0, -a0 b0, b1, -a0 b1, 1, -a0), row 2i + 1 only at S1 = {1, 2, 4, 5, 7, 8}
@@ -273,11 +265,9 @@ inline void u2h(const double* u, const int* inl, int len, double* H) {
     // other 9 stay 0).  Same additions in the same order as the generic double loop, about 3x fewer instructions.
     double e[15] = {0}, o[15] = {0}, m[6] = {0};
     for (int i = lo; i < hi; i++) {
-      double c0, c1, c3, c4;   // x1 y1 x2 y2 of correspondence inl[i]: from normu's dense copy on the large path
-      if (G) { const double* s = G + 6 * (size_t)i; c0 = s[0]; c1 = s[1]; c3 = s[2]; c4 = s[3]; }
-      else { const double* s = u + 6 * inl[i]; c0 = s[0]; c1 = s[1]; c3 = s[3]; c4 = s[4]; }
-      const double a0 = c0 * A1[0] + A1[1], a1 = c1 * A1[0] + A1[2];
-      const double b0 = c3 * A2[0] + A2[1], b1 = c4 * A2[0] + A2[2];
+      const double* s = u + 6 * inl[i];
+      const double a0 = s[0] * A1[0] + A1[1], a1 = s[1] * A1[0] + A1[2];
+      const double b0 = s[3] * A2[0] + A2[1], b1 = s[4] * A2[0] + A2[2];
       const double x0 = b0, x2 = -a0 * b0, x3 = b1, x5 = -a0 * b1, x8 = -a0 * 1.0;   // row 2i   (x6 = 1)
       const double y1 = b0, y2 = -a1 * b0, y4 = b1, y5 = -a1 * b1, y8 = -a1 * 1.0;   // row 2i+1 (y7 = 1)
       // row 2i only: (p, q) with p, q in S0, not both in {2, 5, 8}

@@ -1,4 +1,8 @@
-python bench.py --workload c4 --steps 6 --warmup 3 > gpurun_out/s3_c4_ds_n1.json 2> gpurun_out/s3_c4_ds_n1.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --workload c4 --steps 6 --warmup 3 > gpurun_out/s3_c4_ds_n2.json 2> gpurun_out/s3_c4_ds_n2.err; tail -3 gpurun_out/s3_c4_ds_n2.err
-for f in s3_c4_ds_n1 s3_c4_ds_n2; do python -c "
-import json; d=json.loads(open('gpurun_out/$f.json').read().strip().splitlines()[-1]); print('$f', d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['single_pair'], d['config']['digest'], d['config']['digest_identical_on_all_ranks'], d['config']['verified'])"; done
+# final validation of a round: GPU tests, the C3 bench line, one traced C4 run
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/final_tests.log
+python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
+MB2_RANSAC_TRACE=1 MB2_VERIFY_TRACE=1 python bench.py --workload c4 --steps 2 --warmup 3 > gpurun_out/final_c4_n1.json 2> gpurun_out/final_c4_n1.err
+cat gpurun_out/final_tests.log; grep "verify\|mb2_ransac_h" gpurun_out/final_c4_n1.err | tail -2
+python -c "
+import json; d=json.loads(open('gpurun_out/final_bench.json').read().strip().splitlines()[-1]); print('c3', d['value'], d['e2e']['value'], d['latency_ms_per_pair'], d['roofline']['frac'], d['roofline']['traffic'], d['parity']['ok'], d['stage_ms'])
+d=json.loads(open('gpurun_out/final_c4_n1.json').read().strip().splitlines()[-1]); print('c4', d['value'], d['e2e']['value'], d['config']['single_pair'], d['config']['verify_ms_rank0'], d['config']['digest'][0])"
