@@ -31,6 +31,19 @@ def test_header_symbols_exported(library):
     assert set(mb.EXPORTS) <= set(syms)
 
 
+def test_host_mirror_symbols_exported(library):
+    """libmods_host.so (the C++ mirror of the reference's plugin surface) exports every extern "C" entry mods_host.hpp declares."""
+    text = open(os.path.join(ROOT, "mods_b200", "host", "mods_host.hpp")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    block = text[text.index('extern "C" {'):]
+    syms = sorted(set(re.findall(r"\b(mb2_[a-z0-9_]+)\s*\(", block)))
+    assert len(syms) >= 10 and "mb2_views_sharded_pairs" in syms and "mb2_mods_pairs" in syms
+    host = ctypes.CDLL(mb.HOST_LIB_PATH)
+    for s in syms:
+        assert hasattr(host, s) or hasattr(library, s), "mods_host.hpp declares %s but neither library exports it" % s
+
+
 def test_no_cpu_fallback_without_gpu():
     try:
         import torch
