@@ -1298,13 +1298,18 @@ extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img
     });
     inflight.push_back(std::move(a));
   };
-  // LANES (MB2_LANES=1|2, default 1): with 2, the front stages of pairs k and k + 1 run side by side, each lane on its own set of contexts
-  // (lane 1: helper context [6] as its primary, with helpers of its own).  Results do not depend on the schedule (every pair is computed
-  // by the same calls on private contexts); verification of finished pairs stays on the one helper thread below.  MEASURED AND NOT ADOPTED
-  // (round 2, C3, one B200, tools/e2e_probe.py): 33.7 ms per pair with two lanes against 31.6 ms with one -- the three chains of ONE pair
-  // already keep the GPU throughput bound (the kernels of a second pair only slow the first pair's down), so a pair costs the sum of its
-  // kernels' work either way.  Kept as a switch for smaller images, where one pair does not fill the GPU.
+  // LANES (MB2_LANES=1|2; default: 2 for images up to 4 Mpx, else 1): with 2, the front stages of pairs k and k + 1 run side by side, each
+  // lane on its own set of contexts (lane 1: helper context [6] as its primary, with helpers of its own).  Results do not depend on the
+  // schedule (every pair is computed by the same calls on private contexts); verification of finished pairs stays on the one helper
+  // thread below.  Measured on one B200 (tools/e2e_probe.py): 1920 x 1080 pairs (BASELINE config 5's size) 7.0 -> 5.9 ms per pair
+  // (142 -> 168 pairs/s) -- one pair's kernels do not fill the GPU and its host legs leave gaps; 4096 x 3072 pairs 31.6 -> 33.7 ms -- the
+  // three chains of ONE pair already keep the GPU throughput bound there, a second pair's kernels only slow the first pair's down.
   int n_lanes = 1;
+  {
+    long long max_px = 0;
+    for (int k = 0; k < n_pairs; k++) max_px = std::max(max_px, std::max((long long)w1[k] * h1[k], (long long)w2[k] * h2[k]));
+    if (n_pairs > 0 && max_px <= 4000000LL) n_lanes = 2;
+  }
   if (const char* e = getenv("MB2_LANES")) n_lanes = std::max(1, std::min(2, atoi(e)));
   if (ahead > 0 || n_pairs < 2) n_lanes = 1;
   mb2_ctx* lane_ctx[2] = {ctx, n_lanes > 1 ? sibling_ctx(ctx, 6) : nullptr};

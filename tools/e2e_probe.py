@@ -9,7 +9,7 @@ import bench
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-w, h = 4096, 3072
+w, h = (int(v) for v in os.environ.get("PROBE_SIZE", "4096x3072").split("x"))
 pairs = bench.make_pairs(w, h, bench.N_PAIRS, seed0=1)
 ctx = mb.Context(0)
 cfg = mb.PairConfig.default(); cfg.use_mser = 1
@@ -26,7 +26,7 @@ def timed(bufs, n):
 
 
 timed(dev, 3)
-configs = [dict(MB2_LANES="1"), dict(MB2_LANES="2"), dict(MB2_LANES="1", MB2_MSER_AHEAD="1")]
+configs = [dict(MB2_LANES="1"), dict(MB2_LANES="2"), dict(MB2_LANES="1", MB2_MSER_AHEAD="1")] if not os.environ.get("PROBE_LANES_ONLY") else [dict(MB2_LANES="1"), dict(MB2_LANES="2")]
 if os.environ.get("PROBE_SAMPLERS"):   # what samples the clocks while the arms run (bench.ClockSampler)
     for mode in ("none", "nvidia-smi", "nvml"):
         sampler = None
