@@ -42,7 +42,12 @@ GENERATOR = {"impl": "mods_b200/synth.py (numpy PCG64; SURVEY 8d asked for Split
              "identity view at 4096x3072; N_b alone was scaled to 1.5e-3 (~31.5k keypoints, oracle count)", "seeds": "pair i: A = 1 + 16 i, B = A + 1 (rank r adds 1000 r)"}
 
 
-def workload_string(w, h, no_mser):
+def workload_string(w, h, no_mser, wxbs=False):
+    if wxbs:
+        return ("C5: independent %dx%d synthetic pairs streamed through the dataset call (two pairs in flight per GPU), WxBS descriptor lists "
+                "(Descriptors=RootSIFT,HalfRootSIFT, iters_mods_cviu_wxbs.ini: regions oriented modulo pi, both descriptors, four (descriptor, detector) "
+                "matching groups), HessianAffine(FixedTh 5.3333)+Baumberg and MSER, identity view, FGINN 0.8, duplicate filter 2px, LO-RANSAC-H 3px + LAF "
+                "check; pairs sharded over the ranks" % (w, h))
     return ("C3: %dx%d synthetic pair, HessianAffine(FixedTh 5.3333)+Baumberg and %s, orientation+RootSIFT, identity view, "
             "FGINN 0.8 exact NN per detector, duplicate filter 2px, LO-RANSAC-H 3px + LAF check"
             % (w, h, "HessianAffine only (--no-mser)" if no_mser else "MSER(min_margin 8, min_size 30, max_area 0.05)"))
@@ -173,6 +178,9 @@ def run_ours(args, rank, world, local_rank):
     ctx = mb.Context(local_rank)
     cfg = mb.PairConfig.default()
     cfg.use_mser = 0 if args.no_mser else 1
+    wxbs = args.workload == "c5"
+    if wxbs:
+        cfg.halfRootSIFT = 1   # Descriptors=RootSIFT,HalfRootSIFT (the WxBS tiers)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     dev_pairs = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in pairs]
     pin_pairs = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
@@ -253,7 +261,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (pyramid/patches), f64 (SIFT sums, RANSAC), bf16->f32 tcgen05 (NN, exact on u8 descriptors)",
         "data": "synthetic (numpy PCG64 blob images + ground-truth homography warp, mods_b200/synth.py)",
-        "config": {"workload": workload_string(w, h, args.no_mser), "generator": GENERATOR,
+        "config": {"workload": workload_string(w, h, args.no_mser, wxbs), "generator": GENERATOR,
                    "mser_regions_per_image": float(np.mean([r.mser_regions1 + r.mser_regions2 for r in res_dev])) / 2,
                    "mser_tentatives": float(np.mean([r.mser_tentatives for r in res_dev])),
                    "pairs_in_rotation": N_PAIRS, "l2": "inputs cycle through %d pairs (%.0f MB) and the per-image pyramid working set (~1.3 GB) exceeds the 126 MB L2"
@@ -287,7 +295,7 @@ def run_ours(args, rank, world, local_rank):
             raise SystemExit("bench.py: a pair came back with no regions / tentatives (regions %d / %d, tentatives %d)" % (r.regions1, r.regions2, r.tentatives))
     out["cpu_baseline"] = None
     out["parity"] = {"checked": False}
-    if not args.no_cpu_baseline and world == 1:   # rank 0 at N=1 only: one full-size pair on the host cores, its outputs compared with the GPU's
+    if not args.no_cpu_baseline and world == 1 and not wxbs:   # rank 0 at N=1 only (the reference arm has no WxBS descriptor-list leg: C5 reports no CPU baseline): one full-size pair on the host cores, its outputs compared with the GPU's
         out["cpu_baseline"], cpu = cpu_baseline(pairs[0], w, h, cfg_values(cfg), with_mser=not args.no_mser)
         try:
             out["parity"] = parity_check(local_rank, pairs[0], w, h, cfg, cpu, res_par[0], getattr(res_par[0], "ver_rows", None))
@@ -667,7 +675,7 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_pair, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)", "data": "synthetic (same generator and seeds as the GPU arm, pair 0)",
-           "config": {"workload": workload_string(w, h, args.no_mser), "generator": GENERATOR, "requested_steps": args.steps, "requested_warmup": args.warmup,
+           "config": {"workload": workload_string(w, h, args.no_mser, wxbs), "generator": GENERATOR, "requested_steps": args.steps, "requested_warmup": args.warmup,
                       "budget_s": budget, "regions_per_image": float(np.mean([len(r["views"][k][0]) for k in r["views"]])) * len(r["dets"]),
                       "tentatives": int(r["back"]["counts"][0]), "verified": int(verified)},
            "matched_kpts_per_s": verified * v,
@@ -710,10 +718,13 @@ def main():
     ap.add_argument("--size", default="4096x3072", type=lambda s: tuple(int(v) for v in s.lower().split("x")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mser", action="store_true", help="HessianAffine-only variant of the workload")
-    ap.add_argument("--workload", default=os.environ.get("MB2_BENCH_WORKLOAD", "c3"), choices=["c3", "c4"],
+    ap.add_argument("--workload", default=os.environ.get("MB2_BENCH_WORKLOAD", "c3"), choices=["c3", "c4", "c5"],
                     help="c3 (default): BASELINE config 3, pairs sharded over the ranks (weak scaling).  c4: BASELINE config 4, the full view tiers of "
-                         "iters_mods_cviu.ini on ONE 4096x3072 pair, views sharded over the ranks + one NCCL all-gather (strong scaling)")
+                         "iters_mods_cviu.ini on 4096x3072 pairs, views sharded over the ranks + one NCCL all-gather (strong scaling).  c5: BASELINE "
+                         "config 5, independent 1920x1080 pairs with the WxBS descriptor lists, pairs sharded over the ranks (weak scaling)")
     args = ap.parse_args()
+    if args.workload == "c5" and "--size" not in sys.argv:
+        args.size = (1920, 1080)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl != "reference":
         # torchrun pins OMP_NUM_THREADS to 1; the host legs of the library (duplicate filter, libm legs, LO-RANSAC set-up) use OpenMP:
