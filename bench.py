@@ -675,7 +675,7 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_pair, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)", "data": "synthetic (same generator and seeds as the GPU arm, pair 0)",
-           "config": {"workload": workload_string(w, h, args.no_mser, wxbs), "generator": GENERATOR, "requested_steps": args.steps, "requested_warmup": args.warmup,
+           "config": {"workload": workload_string(w, h, args.no_mser), "generator": GENERATOR, "requested_steps": args.steps, "requested_warmup": args.warmup,
                       "budget_s": budget, "regions_per_image": float(np.mean([len(r["views"][k][0]) for k in r["views"]])) * len(r["dets"]),
                       "tentatives": int(r["back"]["counts"][0]), "verified": int(verified)},
            "matched_kpts_per_s": verified * v,
