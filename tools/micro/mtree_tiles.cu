@@ -275,12 +275,26 @@ int main(int argc, char** argv) {
   cudaMalloc(&d_img, N); cudaMalloc(&d_out, 2 * N * 4); cudaMalloc(&d_prof, 16 * 8);
   cudaMemcpy(d_img, img.data(), N, cudaMemcpyHostToDevice);
   dim3 g((W + 63) / 64, (H + 63) / 64);
+  // every formulation DESIGN.md section 7 quotes a time for (ms per 4096 x 3072 image, both polarities, one B200)
   struct V { const char* name; Launch fn; } vs[] = {
-      {"shipped round-2a: 256 threads, 12 cooperative stages", launch<256, 0, 0, false, false>},
-      {"seq 4x4 by connect(), 512 threads", launch<512, 2, 0, false, false>},
-      {"seq 8x8 sorted union-find, 512 threads", launch8<512, false>},
-      {"seq 8x8 sorted union-find, 256 threads", launch8<256, false>},
-      {"seq 8x8 sorted union-find, 128 threads", launch8<128, false>},
+      {"round-2a kernel: 256 threads, 12 cooperative stages", launch<256, 0, 0, false, false>},       // 1.87
+      {"12 cooperative stages, 128 threads", launch<128, 0, 0, false, false>},                       // 2.70
+      {"12 cooperative stages, 512 threads", launch<512, 0, 0, false, false>},                       // 1.78
+      {"seq 2x2 per thread + 10 stages, 256", launch<256, 1, 0, false, false>},                      // 1.72
+      {"seq 4x4 per thread + 8 stages, 256", launch<256, 2, 0, false, false>},                       // 1.48
+      {"seq 4x4 per thread + 8 stages, 512 (SHIPPED)", launch<512, 2, 0, false, false>},             // 1.33
+      {"seq 4x4 per thread + 8 stages, 1024", launch<1024, 2, 0, false, false>},                     // 1.85
+      {"seq 8x8 per thread + 6 stages, 256", launch<256, 3, 0, false, false>},                       // 1.49
+      {"seq 4x4 bank-swizzled, 512", launch<512, 2, 0, true, false>},                                // 1.42
+      {"seq 4x4 + block pairs by one thread up to stage 6, 512", launch<512, 2, 6, false, false>},   // 1.36
+      {"seq 4x4 + block pairs by one thread up to stage 8, 512", launch<512, 2, 8, false, false>},   // 2.00
+      {"seq 4x4 + block pairs by one thread up to stage 12, 512", launch<512, 2, 12, false, false>}, // 3.79
+      {"block pairs by one thread from stage 0 up to 8, 512", launch<512, 0, 8, false, false>},      // 2.26
+      {"seq 4x4, 512, middle pair of a border first from stage 10", launch<512, 2, 0, false, false, 10>},   // 1.57
+      {"seq 4x4, 512, middle pair of a border first from stage 4", launch<512, 2, 0, false, false, 4>},     // 2.23
+      {"seq 4x4, 512, k-major task order", launch<512, 2, 0, false, false, 12, true>},               // 1.37
+      {"seq 8x8 by sorted union-find + 6 stages, 512", launch8<512, false>},                         // 1.56
+      {"seq 8x8 by sorted union-find + 6 stages, 256", launch8<256, false>},                         // 1.76
   };
   std::vector<uint32_t> ref, out(2 * N);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
