@@ -46,3 +46,21 @@ def test_ours_refuses_to_run_without_a_gpu():
         pass
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """The clocks sampler (NVML in-process, nvidia-smi as fallback) must never take the bench down: without a driver it reports no source."""
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(out)
+    if out["sm_mhz"] is None:
+        assert out["reasons"] and "unavailable" in out["reasons"][0] or out.get("samples", 0) == 0
+
+
+def test_workload_strings_name_the_baseline_configs():
+    import bench
+    assert bench.workload_string(4096, 3072, False).startswith("C3:") and "MSER" in bench.workload_string(4096, 3072, False)
+    assert bench.workload_string(1920, 1080, False, True).startswith("C5:") and "HalfRootSIFT" in bench.workload_string(1920, 1080, False, True)
+    assert (bench.C4_WORKLOAD % (4096, 3072)).startswith("C4:")
