@@ -1237,6 +1237,8 @@ extern "C" int mb2_mods_pair(mb2_ctx* ctx, const float* img1, int w1, int h1, co
 // A list of independent pairs (a dataset run: mods.cpp is started once per pair by the EVD / WxBS scripts),
 // software-pipelined over two host threads: while pair k is being verified (duplicate filter + LO-RANSAC on
 // the helper context [1]), pair k+1 is already in detection / description / matching on the primary one.
+// Host images of the next pair are uploaded on the copy engine meanwhile; for images up to 4 Mpx two pairs' front stages run side by side
+// (two "lanes", each on its own set of contexts: one such pair does not fill the GPU).
 // Results are identical to calling mb2_mods_pair on every pair in turn.
 extern "C" int mb2_mods_pairs(mb2_ctx* ctx, int n_pairs, const float* const* img1, const int* w1, const int* h1, const float* const* img2,
                               const int* w2, const int* h2, const mb2_pair_config* cfg, mb2_pair_result* res, double* const* verified_out,
