@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_mtree_local(int W, int H, const 
       atomicAdd(&acc[p], *(volatile uint32_t*)&acc[u]);          // u's sums are complete: all its children delivered before the counter reached zero
       __threadfence_block();
       if (((atomicSub(&pend[p >> 1], 1u << (16 * (p & 1))) >> (16 * (p & 1))) & 0xffffu) != 1u) break;                 // somebody else delivers p's last child and goes on from there
+      __threadfence_block();                                    // acquire side: p's other children added their sums before they decremented the counter
       u = p;
     }
   }
